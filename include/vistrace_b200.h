@@ -1,0 +1,234 @@
+/*
+ * vistrace_b200.h — C ABI of the B200-native ray-query engine that sits behind
+ * VisTrace's `vistrace.CreateAccel` / `accel:Traverse` surface.
+ *
+ * Plain C: pointers, sizes and POD records only.  No STL, no torch types, no
+ * exceptions cross this boundary.  Every entry point returns 0 on success (or
+ * a handle / NULL) and leaves a message for vt_last_error() on failure.
+ *
+ * Each declaration cites the reference interface it replaces as
+ * `path:line` relative to the Derpius/VisTrace tree.
+ */
+#ifndef VISTRACE_B200_H
+#define VISTRACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_ABI_VERSION 1u
+#define VT_MISS 0xFFFFFFFFu /* vt_hit.prim for "Traverse returned nil" (source/objects/AccelStruct.cpp:837) */
+
+/* ------------------------------------------------------------------ records */
+
+/* One ray.  Replaces bvh::Ray<float> (source/objects/Primitives.h:9-33) minus the
+ * pAccel back-pointer.  The direction is NOT normalised for traversal, t is in
+ * units of |d| (source/objects/AccelStruct.cpp:810-815). 32 bytes. */
+typedef struct vt_ray {
+    float ox, oy, oz, tmin;
+    float dx, dy, dz, tmax;
+} vt_ray;
+
+/* Closest hit.  Replaces ClosestPrimitiveIntersector::Result
+ * (libs/bvh/include/bvh/primitive_intersectors.hpp:48-53) +
+ * TriangleBackfaceCull::Intersection (source/objects/Primitives.h:46-50).
+ * prim indexes the ORIGINAL triangle array; VT_MISS when nothing was hit
+ * (then t = u = v = 0). 16 bytes. */
+typedef struct vt_hit {
+    float t, u, v;
+    uint32_t prim;
+} vt_hit;
+
+/* BVH node, bit-compatible with bvh::Bvh<float>::Node
+ * (libs/bvh/include/bvh/bvh.hpp:25-31): bounds = {minx,maxx,miny,maxy,minz,maxz},
+ * prim_count != 0 marks a leaf, `first` is the first child (children are
+ * adjacent: first, first+1) or the first slot of prim_indices. 32 bytes. */
+typedef struct vt_node {
+    float bounds[6];
+    uint32_t prim_count;
+    uint32_t first;
+} vt_node;
+
+/* Input triangle: what mesh ingestion hands to the Triangle constructor
+ * (source/objects/Primitives.h:75-89, source/objects/Model.cpp:82-89) plus the
+ * per-vertex attributes the ingestion code fills in afterwards. 152 bytes. */
+typedef struct vt_tri_in {
+    float p[3][3];        /* p0, p1, p2 */
+    float normals[3][3];  /* Triangle::normals */
+    float tangents[3][3]; /* Triangle::tangents */
+    float uvs[3][2];      /* Triangle::uvs */
+    float alphas[3];      /* Triangle::alphas */
+    uint32_t material;    /* global material index (Triangle::material) */
+    uint16_t ent_idx;     /* index into the entity array (Triangle::entIdx) */
+    uint8_t one_sided;    /* Triangle::oneSided */
+    uint8_t pad;
+} vt_tri_in;
+
+/* Texture: decoded RGBA8888 mip chain exactly as VTFTexture keeps it in memory,
+ * i.e. SMALLEST mip first (libs/VTFParser/VTFParser.cpp:44-78,178-188), one
+ * frame, one face, depth 1.  flags are VTF TEXTURE_FLAGS (CLAMPS 0x4, CLAMPT 0x8). */
+#define VT_TEXFLAG_CLAMPS 0x00000004u
+#define VT_TEXFLAG_CLAMPT 0x00000008u
+typedef struct vt_texture {
+    uint16_t width, height; /* size of mip 0 */
+    uint16_t mip_count;
+    uint16_t pad;
+    uint32_t flags;
+    uint32_t pad2;
+    const uint8_t *rgba;    /* host pointer, nbytes long */
+    uint64_t nbytes;
+} vt_texture;
+
+/* Material subset on the path (source/objects/Material.h:74-125).  Texture slots
+ * are indices into the texture array, -1 = nullptr.  *_mat are glm::mat2x4 in
+ * memory order: [0..3] = column 0 (drives u), [4..7] = column 1 (drives v)
+ * (source/Utils.h:65-72). */
+#define VT_MATFLAG_ALPHATEST 256u  /* MaterialFlags::alphatest */
+#define VT_MATFLAG_NOCULL    8192u /* MaterialFlags::nocull */
+#define VT_SURF_SKY          0x4u  /* BSPEnums::SURF::SKY */
+typedef struct vt_material {
+    uint32_t flags;       /* MaterialFlags */
+    uint32_t surf_flags;  /* BSPEnums::SURF */
+    float alphatest_reference;
+    float tex_scale;
+    float colour[4];
+    float base_tex_mat[8];
+    float base_tex_mat2[8];
+    float normal_map_mat[8];
+    float normal_map_mat2[8];
+    float blend_tex_mat[8];
+    float detail_mat[8];
+    float detail_scale;
+    float detail_blend_factor;
+    float detail_tint[3];
+    int32_t base_texture;
+    int32_t base_texture2;
+    int32_t normal_map;
+    int32_t normal_map2;
+    int32_t mrao;
+    int32_t mrao2;
+    int32_t blend_texture;
+    int32_t detail;
+    uint8_t detail_blend_mode; /* DetailBlendMode */
+    uint8_t masked_blending;
+    uint8_t detail_alpha_mask_base_texture;
+    uint8_t water;
+} vt_material;
+
+/* Entity subset on the path (source/objects/AccelStruct.h:33-40). */
+typedef struct vt_entity {
+    uint32_t id;     /* Entity::id, what TraceResult::entIdx reports */
+    float colour[4]; /* Entity::colour */
+} vt_entity;
+
+/* Headless scene: the three containers AccelStruct owns after ingestion
+ * (source/objects/AccelStruct.h:72-77).  All host pointers, borrowed for the
+ * duration of the call. */
+typedef struct vt_scene {
+    const vt_tri_in *tris;
+    uint64_t n_tris;
+    const vt_material *materials;
+    uint32_t n_materials;
+    const vt_entity *entities;
+    uint32_t n_entities;
+    const vt_texture *textures;
+    uint32_t n_textures;
+} vt_scene;
+
+/* Eager, batched TraceResult (source/objects/TraceResult.h:54-111): everything the
+ * VisTraceResult getters return for the default (no LOD cone) call. 128 bytes. */
+#define VT_ATTR_FRONT_FACING 1u
+#define VT_ATTR_HIT_SKY      2u
+#define VT_ATTR_HIT_WATER    4u
+typedef struct vt_attr {
+    float pos[3];              /* TraceResult::GetPos            TraceResult.cpp:255-262 */
+    float distance;            /* TraceResult::distance (units of |dir|) */
+    float normal[3];           /* GetNormal   (CalcTBN)          TraceResult.cpp:132-187 */
+    float alpha;               /* GetAlpha    (CalcShadingData)  TraceResult.cpp:189-253 */
+    float tangent[3];          /* GetTangent */
+    float metalness;           /* GetMetalness */
+    float binormal[3];         /* GetBinormal */
+    float roughness;           /* GetRoughness */
+    float geometric_normal[3]; /* TraceResult::geometricNormal */
+    float base_mip;            /* GetBaseMIPLevel */
+    float albedo[3];           /* GetAlbedo */
+    uint32_t ent_id;           /* TraceResult::entIdx = Entity::id */
+    float uvw[3];              /* TraceResult::uvw = (u, v, 1-u-v) */
+    uint32_t submat_idx;       /* TraceResult::submatIdx = Triangle::material */
+    float tex_uv[2];           /* TraceResult::texUV */
+    uint32_t flags;            /* VT_ATTR_* */
+    uint32_t prim;             /* original triangle index, VT_MISS on a miss (rest zero) */
+} vt_attr;
+
+/* --------------------------------------------------------------- entry points */
+
+typedef struct vt_accel vt_accel; /* opaque; replaces AccelStruct (source/objects/AccelStruct.h:61-86) */
+
+/* Number of CUDA devices visible; <0 on error. */
+int vt_device_count(void);
+
+/* AccelStruct::AccelStruct (source/objects/AccelStruct.cpp:510-523) bound to one GPU.
+ * NULL on failure (no CUDA device: the engine has no CPU fallback). */
+vt_accel *vt_accel_create(int device);
+
+/* AccelStruct::~AccelStruct (source/objects/AccelStruct.cpp:525-531). */
+void vt_accel_destroy(vt_accel *accel);
+
+/* Headless AccelStruct::PopulateAccel (source/objects/AccelStruct.cpp:533-776):
+ * copy the scene, derive e1/e2/n/nNorm/lod per triangle (Primitives.h:75-102),
+ * build the hierarchy on the host (the step at AccelStruct.cpp:762-770), flatten
+ * it to the device layout and upload.  Rebuild = call again. */
+int vt_accel_populate(vt_accel *accel, const vt_scene *scene);
+
+/* Same, but with a hierarchy the caller already built, in bvh::Bvh<float> form
+ * (`mAccel.nodes`, `mAccel.primitive_indices`, `mAccel.node_count`;
+ * libs/bvh/include/bvh/bvh.hpp:96-99).  This is what the reference's own
+ * PopulateAccel would pass right after LeafCollapser::collapse
+ * (source/objects/AccelStruct.cpp:769-770). */
+int vt_accel_populate_with_bvh(vt_accel *accel, const vt_scene *scene,
+                               const vt_node *nodes, uint64_t node_count,
+                               const uint64_t *prim_indices);
+
+/* Read the hierarchy back in bvh::Bvh<float> form.  Call with nodes == NULL to get
+ * the counts.  prim_indices has n_tris entries. */
+int vt_accel_get_bvh(const vt_accel *accel, vt_node *nodes, uint64_t *node_count,
+                     uint64_t *prim_indices, uint64_t *n_tris);
+
+/* Batched AccelStruct::Traverse (source/objects/AccelStruct.cpp:778-838).
+ *   rays/hits/attrs : n records each; host pointers unless VT_TRAVERSE_DEVICE_PTRS.
+ *   attrs           : NULL = hit record only; else the eager TraceResult per ray.
+ *   stream          : cudaStream_t or NULL (legacy default stream).
+ * Host pointers: synchronous — results are in `hits` on return.  Device pointers:
+ * enqueued on `stream`, returns immediately.
+ * Per-ray argument rules of the reference (tMin < 0, tMax <= tMin: AccelStruct.cpp:805-806)
+ * turn the ray into a miss and are counted in vt_accel_invalid_rays(). */
+#define VT_TRAVERSE_DEVICE_PTRS 1u
+#define VT_TRAVERSE_ANY_HIT     2u /* early-out occlusion query: hit.prim != VT_MISS is all that is defined */
+int vt_accel_traverse(vt_accel *accel, const vt_ray *rays, uint64_t n, vt_hit *hits,
+                      vt_attr *attrs, uint32_t flags, void *stream);
+
+/* Eager TraceResult for hits that were produced earlier (device or host pointers as
+ * per flags): the constructor + getters of source/objects/TraceResult.cpp:45-262. */
+int vt_accel_trace_result(vt_accel *accel, const vt_ray *rays, const vt_hit *hits,
+                          uint64_t n, vt_attr *attrs, uint32_t flags, void *stream);
+
+/* Rays rejected by the argument rules during the last synchronous traverse. */
+uint64_t vt_accel_invalid_rays(const vt_accel *accel);
+
+/* Kernel launches issued by this handle so far (bench.py's gpu_launches). */
+uint64_t vt_accel_launch_count(const vt_accel *accel);
+
+/* Scene statistics: n_tris, node_count, bytes resident in HBM. */
+int vt_accel_stats(const vt_accel *accel, uint64_t *n_tris, uint64_t *node_count,
+                   uint64_t *device_bytes);
+
+/* Last error message of the calling thread ("" if none). */
+const char *vt_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISTRACE_B200_H */

@@ -1,0 +1,171 @@
+"""CPU checkers for the accel:Traverse path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Two interchangeable back ends behind one Python class:
+
+* ``kind="port"``      oracle/libvt_oracle.so — our plain-C restatement (oracle/vt_oracle.c),
+                       every function citing the reference file:line it follows.
+* ``kind="reference"`` oracle/_ref/libvt_ref.so — the UNMODIFIED reference compiled from
+                       /root/reference by oracle/Makefile (ref_harness.cpp drives it headless).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference``
+legs may import this package.  vistrace_b200 (the product) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from vistrace_b200 import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "libvt_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libvt_ref.so")
+REFERENCE_ROOT = "/root/reference"
+
+
+def build(ref=True, quiet=True):
+    """Compile the C restatement and, when /root/reference is present, the real reference."""
+    out = subprocess.DEVNULL if quiet else None
+    subprocess.check_call(["make", "-C", HERE, "oracle"], stdout=out)
+    if ref and os.path.isdir(REFERENCE_ROOT):
+        subprocess.check_call(["make", "-C", HERE, "-j8", "ref"], stdout=out)
+
+
+def available(kind):
+    return os.path.exists(PORT_SO if kind == "port" else REF_SO)
+
+
+_libs = {}
+
+
+def _lib(kind):
+    if kind in _libs:
+        return _libs[kind]
+    path, pre = (PORT_SO, "vto_") if kind == "port" else (REF_SO, "vtref_")
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} missing: run `make -C oracle {'oracle' if kind == 'port' else 'ref'}`")
+    lib = C.CDLL(path)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    sig = {
+        "max_threads": (i32, []),
+        "create": (vp, [vp, i32]),
+        "destroy": (None, [vp]),
+        "get_tri_derived": (None, [vp, vp]),
+        "get_bvh": (None, [vp, vp, vp, vp, vp]),
+        "set_bvh": (None, [vp, vp, u64, vp]),
+        "traverse": (C.c_double, [vp, vp, u64, vp, vp, i32, vp]),
+        "trace_result": (None, [vp, vp, vp, u64, vp, i32]),
+        "sample": (None, [vp, i32, vp, u64, vp]),
+        "node_intersect": (None, [vp, vp, vp]),
+        "tri_intersect": (i32, [vp, u64, vp, vp]),
+    }
+    ns = type("ns", (), {})()
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, pre + name)
+        fn.restype, fn.argtypes = res, args
+        setattr(ns, name, fn)
+    _libs[kind] = ns
+    return ns
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+class CpuScene:
+    """One scene held by a CPU checker (the reference's AccelStruct or the C port of it)."""
+
+    def __init__(self, scene, kind="reference", build_bvh=True):
+        self.kind = kind
+        self.lib = _lib(kind)
+        self.scene = scene  # keep the numpy buffers alive
+        self.h = self.lib.create(C.cast(scene.ptr(), C.c_void_p), 1 if build_bvh else 0)
+        if not self.h:
+            raise RuntimeError("oracle scene creation failed")
+        self.n_tris = scene.n_tris
+
+    def close(self):
+        if self.h:
+            self.lib.destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def max_threads(self):
+        return self.lib.max_threads()
+
+    def tri_derived(self):
+        """(n, 16) float32: p0, e1, e2, n, nNorm, lod as the Triangle constructor derives them."""
+        out = np.zeros((self.n_tris, 16), np.float32)
+        self.lib.get_tri_derived(self.h, out.ctypes.data)
+        return out
+
+    def get_bvh(self):
+        cnt, nt = C.c_uint64(0), C.c_uint64(0)
+        self.lib.get_bvh(self.h, None, C.addressof(cnt), None, C.addressof(nt))
+        nodes = np.zeros(cnt.value, abi.NODE)
+        prims = np.zeros(nt.value, np.uint64)
+        self.lib.get_bvh(self.h, nodes.ctypes.data, None, prims.ctypes.data, None)
+        return nodes, prims
+
+    def set_bvh(self, nodes, prim_indices):
+        nodes = np.ascontiguousarray(nodes, abi.NODE)
+        prim_indices = np.ascontiguousarray(prim_indices, np.uint64)
+        assert len(prim_indices) == self.n_tris
+        self.lib.set_bvh(self.h, nodes.ctypes.data, len(nodes), prim_indices.ctypes.data)
+
+    def traverse(self, rays, want_attrs=False, threads=0, want_stats=False):
+        """Returns dict(hits, attrs?, seconds, steps?, isects?)."""
+        rays = np.ascontiguousarray(rays, abi.RAY)
+        hits = np.zeros(len(rays), abi.HIT)
+        attrs = np.zeros(len(rays), abi.ATTR) if want_attrs else None
+        stats = np.zeros(2, np.uint64) if want_stats else None
+        sec = self.lib.traverse(self.h, rays.ctypes.data, len(rays), hits.ctypes.data, _p(attrs), threads, _p(stats))
+        if sec < 0:
+            raise RuntimeError("oracle traverse: acceleration structure not built")
+        out = {"hits": hits, "seconds": sec}
+        if want_attrs:
+            out["attrs"] = attrs
+        if want_stats:
+            out["steps"], out["isects"] = int(stats[0]), int(stats[1])
+        return out
+
+    def time_traverse(self, rays, threads=0, reps=3):
+        """Best-of-reps seconds for the traversal-only loop."""
+        rays = np.ascontiguousarray(rays, abi.RAY)
+        hits = np.zeros(len(rays), abi.HIT)
+        best = float("inf")
+        for _ in range(reps):
+            best = min(best, self.lib.traverse(self.h, rays.ctypes.data, len(rays), hits.ctypes.data, None, threads, None))
+        return best
+
+    def trace_result(self, rays, hits, threads=0):
+        rays = np.ascontiguousarray(rays, abi.RAY)
+        hits = np.ascontiguousarray(hits, abi.HIT)
+        attrs = np.zeros(len(rays), abi.ATTR)
+        self.lib.trace_result(self.h, rays.ctypes.data, hits.ctypes.data, len(rays), attrs.ctypes.data, threads)
+        return attrs
+
+    def sample(self, tex, uvm):
+        uvm = np.ascontiguousarray(uvm, np.float32).reshape(-1, 3)
+        out = np.zeros((len(uvm), 4), np.float32)
+        self.lib.sample(self.h, tex, uvm.ctypes.data, len(uvm), out.ctypes.data)
+        return out
+
+    def tri_intersect(self, prim, ray):
+        ray = np.ascontiguousarray(ray, abi.RAY).reshape(1)
+        tuv = np.zeros(3, np.float32)
+        ok = self.lib.tri_intersect(self.h, prim, ray.ctypes.data, tuv.ctypes.data)
+        return (bool(ok), tuv)
+
+
+def node_intersect(node, ray, kind="reference"):
+    """FastNodeIntersector::intersect on one node -> (entry, exit)."""
+    node = np.ascontiguousarray(node, abi.NODE).reshape(1)
+    ray = np.ascontiguousarray(ray, abi.RAY).reshape(1)
+    out = np.zeros(2, np.float32)
+    _lib(kind).node_intersect(node.ctypes.data, ray.ctypes.data, out.ctypes.data)
+    return float(out[0]), float(out[1])

@@ -1,0 +1,407 @@
+// oracle/ref_harness.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Headless driver around the UNMODIFIED Derpius/VisTrace reference.  It is
+// compiled by oracle/Makefile against the sources where they lie under
+// /root/reference (nothing is copied) into oracle/_ref/libvt_ref.so.  Only
+// tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / reference arm
+// load it.  The product library (vistrace_b200/csrc) never does.
+//
+// What runs here is the reference's own code:
+//   * Triangle ctor + ComputeNormalAndLoD           source/objects/Primitives.h:75-102
+//   * the build sequence                            source/objects/AccelStruct.cpp:762-775
+//   * per ray, the statements of AccelStruct::Traverse  source/objects/AccelStruct.cpp:810-831
+//     (bvh::SingleRayTraverser + ClosestPrimitiveIntersector + Triangle::intersect)
+//   * TraceResult ctor and getters                  source/objects/TraceResult.cpp:45-262
+//   * VTFTexture(const uint8_t*, size_t)::Sample    libs/VTFParser/VTFParser.cpp:311-330
+// The ingestion paths (Lua, engine filesystem) are bypassed by filling the
+// private containers directly, which is why `private` is opened up below.
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <omp.h>
+
+#define private public
+#include "AccelStruct.h"
+#include "TraceResult.h"
+#undef private
+
+#include "VTFParser.h"
+#include "bvh/leaf_collapser.hpp"
+#include "bvh/locally_ordered_clustering_builder.hpp"
+#include "bvh/node_intersectors.hpp"
+
+#include "../include/vistrace_b200.h"
+
+namespace {
+
+// In-memory IVTFTexture over the reference's VTFTexture parser/sampler.
+class MemVTF final : public VisTrace::IVTFTexture {
+    std::unique_ptr<VTFTexture> tex;
+
+public:
+    explicit MemVTF(const vt_texture &t) {
+        VTFHeader hdr;
+        std::memset(&hdr, 0, sizeof(hdr));
+        std::memcpy(hdr.signature, "VTF\0", 4);
+        hdr.version[0] = 7;
+        hdr.version[1] = 2;
+        hdr.headerSize = 80;
+        hdr.width = t.width;
+        hdr.height = t.height;
+        hdr.flags = t.flags;
+        hdr.frames = 1;
+        hdr.firstFrame = 0;
+        hdr.bumpmapScale = 1.f;
+        hdr.highResImageFormat = IMAGE_FORMAT::RGBA8888;
+        hdr.mipmapCount = static_cast<uint8_t>(t.mip_count);
+        hdr.lowResImageFormat = IMAGE_FORMAT::NONE;
+        hdr.depth = 1;
+        std::vector<uint8_t> file(80 + t.nbytes);
+        std::memcpy(file.data(), &hdr, 80);
+        std::memcpy(file.data() + 80, t.rgba, t.nbytes);
+        tex = std::make_unique<VTFTexture>(file.data(), file.size());
+    }
+    bool IsValid() const override { return tex && tex->IsValid(); }
+    VisTrace::VTFTextureFormatInfo GetFormat() const override {
+        ImageFormatInfo f = tex->GetFormat();
+        VisTrace::VTFTextureFormatInfo o;
+        std::memcpy(&o, &f, sizeof(o));
+        return o;
+    }
+    uint32_t GetVersionMajor() const override { return tex->GetVersionMajor(); }
+    uint32_t GetVersionMinor() const override { return tex->GetVersionMinor(); }
+    uint16_t GetWidth(uint8_t m = 0) const override { return tex->GetWidth(m); }
+    uint16_t GetHeight(uint8_t m = 0) const override { return tex->GetHeight(m); }
+    uint16_t GetDepth(uint8_t m = 0) const override { return tex->GetDepth(m); }
+    uint8_t GetFaces() const override { return tex->GetFaces(); }
+    uint16_t GetMIPLevels() const override { return tex->GetMIPLevels(); }
+    uint16_t GetFrames() const override { return tex->GetFrames(); }
+    uint16_t GetFirstFrame() const override { return tex->GetFirstFrame(); }
+    VisTrace::Pixel GetPixel(uint16_t x, uint16_t y, uint16_t z, uint8_t m, uint16_t fr, uint8_t fa) const override {
+        VTFPixel p = tex->GetPixel(x, y, z, m, fr, fa);
+        return VisTrace::Pixel{p.r, p.g, p.b, p.a};
+    }
+    VisTrace::Pixel Sample(float u, float v, uint16_t z, float m, uint16_t fr, uint8_t fa) const override {
+        VTFPixel p = tex->Sample(u, v, z, m, fr, fa);
+        return VisTrace::Pixel{p.r, p.g, p.b, p.a};
+    }
+};
+
+struct RefScene {
+    AccelStruct accel;
+    std::vector<std::unique_ptr<MemVTF>> textures;
+};
+
+glm::mat2x4 to_mat(const float m[8]) {
+    glm::mat2x4 r;
+    r[0] = glm::vec4(m[0], m[1], m[2], m[3]);
+    r[1] = glm::vec4(m[4], m[5], m[6], m[7]);
+    return r;
+}
+
+void build_reference_sequence(AccelStruct &a) {
+    // Verbatim statement sequence of source/objects/AccelStruct.cpp:762-775
+    if (a.mAccelBuilt) {
+        delete a.mpIntersector;
+        delete a.mpTraverser;
+        a.mAccelBuilt = false;
+    }
+    a.mAccel = BVH();
+    bvh::LocallyOrderedClusteringBuilder<BVH, uint32_t> builder(a.mAccel);
+    auto [bboxes, centers] = bvh::compute_bounding_boxes_and_centers(a.mTriangles.data(), a.mTriangles.size());
+    auto global_bbox = bvh::compute_bounding_boxes_union(bboxes.get(), a.mTriangles.size());
+    builder.build(global_bbox, bboxes.get(), centers.get(), a.mTriangles.size());
+
+    bvh::LeafCollapser collapser(a.mAccel);
+    collapser.collapse();
+
+    a.mpIntersector = new Intersector(a.mAccel, a.mTriangles.data());
+    a.mpTraverser = new Traverser(a.mAccel);
+    a.mAccelBuilt = true;
+}
+
+} // namespace
+
+extern "C" {
+
+int vtref_max_threads() { return omp_get_max_threads(); }
+
+// Fill the containers the way ingestion would and (optionally) build.
+void *vtref_create(const vt_scene *s, int build) {
+    auto *rs = new RefScene();
+    AccelStruct &a = rs->accel;
+    a.mpWorld = nullptr;
+
+    for (uint32_t i = 0; i < s->n_textures; i++) rs->textures.push_back(std::make_unique<MemVTF>(s->textures[i]));
+    // Ingestion never leaves baseTexture null (fallback MISSING_TEXTURE, source/objects/AccelStruct.cpp:120,286;
+    // TraceResult::CalcShadingData dereferences it unconditionally, TraceResult.cpp:199).  Headless stand-in:
+    // a 1x1 opaque white RGBA8888 texture appended after the caller's textures.
+    static const uint8_t white[4] = {255, 255, 255, 255};
+    vt_texture fb{1, 1, 1, 0, 0, 0, white, 4};
+    rs->textures.push_back(std::make_unique<MemVTF>(fb));
+    const VisTrace::IVTFTexture *fallback = rs->textures.back().get();
+    auto tex = [&](int32_t idx) -> const VisTrace::IVTFTexture * {
+        return (idx >= 0 && static_cast<uint32_t>(idx) < s->n_textures) ? rs->textures[idx].get() : nullptr;
+    };
+
+    a.mMaterials.resize(s->n_materials);
+    for (uint32_t i = 0; i < s->n_materials; i++) {
+        const vt_material &m = s->materials[i];
+        Material &o = a.mMaterials[i];
+        o.path = "synthetic/" + std::to_string(i);
+        o.colour = glm::vec4(m.colour[0], m.colour[1], m.colour[2], m.colour[3]);
+        o.baseTexture = tex(m.base_texture);
+        if (!o.baseTexture) o.baseTexture = fallback;
+        o.baseTexMat = to_mat(m.base_tex_mat);
+        o.normalMap = tex(m.normal_map);
+        o.normalMapMat = to_mat(m.normal_map_mat);
+        o.mrao = tex(m.mrao);
+        o.baseTexture2 = tex(m.base_texture2);
+        o.baseTexMat2 = to_mat(m.base_tex_mat2);
+        o.normalMap2 = tex(m.normal_map2);
+        o.normalMapMat2 = to_mat(m.normal_map_mat2);
+        o.mrao2 = tex(m.mrao2);
+        o.blendTexture = tex(m.blend_texture);
+        o.blendTexMat = to_mat(m.blend_tex_mat);
+        o.maskedBlending = m.masked_blending != 0;
+        o.detail = tex(m.detail);
+        o.detailMat = to_mat(m.detail_mat);
+        o.detailScale = m.detail_scale;
+        o.detailBlendFactor = m.detail_blend_factor;
+        o.detailBlendMode = static_cast<DetailBlendMode>(m.detail_blend_mode);
+        o.detailTint = glm::vec3(m.detail_tint[0], m.detail_tint[1], m.detail_tint[2]);
+        o.detailAlphaMaskBaseTexture = m.detail_alpha_mask_base_texture != 0;
+        o.texScale = m.tex_scale;
+        o.flags = static_cast<MaterialFlags>(m.flags);
+        o.surfFlags = static_cast<BSPEnums::SURF>(m.surf_flags);
+        o.alphatestreference = m.alphatest_reference;
+        o.water = m.water != 0;
+    }
+
+    a.mEntities.resize(s->n_entities);
+    for (uint32_t i = 0; i < s->n_entities; i++) {
+        Entity &e = a.mEntities[i];
+        e.rawEntity = nullptr;
+        e.id = s->entities[i].id;
+        e.colour = glm::vec4(s->entities[i].colour[0], s->entities[i].colour[1], s->entities[i].colour[2],
+                             s->entities[i].colour[3]);
+    }
+
+    a.mTriangles.resize(s->n_tris);
+#pragma omp parallel for
+    for (int64_t i = 0; i < static_cast<int64_t>(s->n_tris); i++) {
+        const vt_tri_in &t = s->tris[i];
+        glm::vec2 uvs[3] = {glm::vec2(t.uvs[0][0], t.uvs[0][1]), glm::vec2(t.uvs[1][0], t.uvs[1][1]),
+                            glm::vec2(t.uvs[2][0], t.uvs[2][1])};
+        // Reference constructor: source/objects/Primitives.h:75-89
+        Triangle tri(Vector3(t.p[0][0], t.p[0][1], t.p[0][2]), Vector3(t.p[1][0], t.p[1][1], t.p[1][2]),
+                     Vector3(t.p[2][0], t.p[2][1], t.p[2][2]), 0, uvs, t.one_sided != 0);
+        tri.material = t.material; // ctor takes int16_t; ingestion overwrites it with the global index anyway
+        tri.entIdx = t.ent_idx;
+        for (int k = 0; k < 3; k++) {
+            tri.normals[k] = glm::vec3(t.normals[k][0], t.normals[k][1], t.normals[k][2]);
+            tri.tangents[k] = glm::vec3(t.tangents[k][0], t.tangents[k][1], t.tangents[k][2]);
+            tri.alphas[k] = t.alphas[k];
+            tri.numBones[k] = 0;
+        }
+        a.mTriangles[i] = tri;
+    }
+
+    if (build) build_reference_sequence(a);
+    return rs;
+}
+
+void vtref_destroy(void *h) { delete static_cast<RefScene *>(h); }
+
+// p0,e1,e2,n,nNorm (15 floats) + lod as derived by the reference constructor.
+void vtref_get_tri_derived(void *h, float *out16) {
+    AccelStruct &a = static_cast<RefScene *>(h)->accel;
+    for (size_t i = 0; i < a.mTriangles.size(); i++) {
+        const Triangle &t = a.mTriangles[i];
+        float *o = out16 + i * 16;
+        for (int k = 0; k < 3; k++) {
+            o[k] = t.p0[k];
+            o[3 + k] = t.e1[k];
+            o[6 + k] = t.e2[k];
+            o[9 + k] = t.n[k];
+            o[12 + k] = t.nNorm[k];
+        }
+        o[15] = t.lod;
+    }
+}
+
+void vtref_get_bvh(void *h, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices, uint64_t *n_tris) {
+    AccelStruct &a = static_cast<RefScene *>(h)->accel;
+    static_assert(sizeof(vt_node) == sizeof(BVH::Node), "node layout");
+    if (node_count) *node_count = a.mAccel.node_count;
+    if (n_tris) *n_tris = a.mTriangles.size();
+    if (nodes) std::memcpy(nodes, a.mAccel.nodes.get(), a.mAccel.node_count * sizeof(vt_node));
+    if (prim_indices)
+        for (size_t i = 0; i < a.mTriangles.size(); i++) prim_indices[i] = a.mAccel.primitive_indices[i];
+}
+
+// Replace the hierarchy with one built elsewhere (same bvh::Bvh<float> form) so the
+// reference traverser can be run over the product builder's tree.
+void vtref_set_bvh(void *h, const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices) {
+    AccelStruct &a = static_cast<RefScene *>(h)->accel;
+    if (a.mAccelBuilt) {
+        delete a.mpIntersector;
+        delete a.mpTraverser;
+        a.mAccelBuilt = false;
+    }
+    a.mAccel = BVH();
+    a.mAccel.nodes = std::make_unique<BVH::Node[]>(node_count);
+    std::memcpy(a.mAccel.nodes.get(), nodes, node_count * sizeof(vt_node));
+    a.mAccel.node_count = node_count;
+    a.mAccel.primitive_indices = std::make_unique<size_t[]>(a.mTriangles.size());
+    for (size_t i = 0; i < a.mTriangles.size(); i++) a.mAccel.primitive_indices[i] = prim_indices[i];
+    a.mpIntersector = new Intersector(a.mAccel, a.mTriangles.data());
+    a.mpTraverser = new Traverser(a.mAccel);
+    a.mAccelBuilt = true;
+}
+
+static inline void fill_attr(const AccelStruct &a, const vt_ray &r, size_t prim, float t, float u, float v,
+                             float coneWidth, float coneAngle, vt_attr &o) {
+    // source/objects/AccelStruct.cpp:819-831
+    const Triangle &tri = a.mTriangles[prim];
+    const Entity &ent = a.mEntities[tri.entIdx];
+    const Material &mat = a.mMaterials[tri.material];
+    TraceResult res(glm::normalize(glm::vec3(r.dx, r.dy, r.dz)), t, coneWidth, coneAngle, tri, glm::vec2(u, v), ent, mat);
+    const glm::vec3 &pos = res.GetPos();
+    const glm::vec3 &n = res.GetNormal();
+    const glm::vec3 &tg = res.GetTangent();
+    const glm::vec3 &bn = res.GetBinormal();
+    const glm::vec3 &alb = res.GetAlbedo();
+    for (int k = 0; k < 3; k++) {
+        o.pos[k] = pos[k];
+        o.normal[k] = n[k];
+        o.tangent[k] = tg[k];
+        o.binormal[k] = bn[k];
+        o.geometric_normal[k] = res.geometricNormal[k];
+        o.albedo[k] = alb[k];
+        o.uvw[k] = res.uvw[k];
+    }
+    o.distance = res.distance;
+    o.alpha = res.GetAlpha();
+    o.metalness = res.GetMetalness();
+    o.roughness = res.GetRoughness();
+    o.base_mip = res.GetBaseMIPLevel();
+    o.ent_id = res.entIdx;
+    o.submat_idx = res.submatIdx;
+    o.tex_uv[0] = res.texUV[0];
+    o.tex_uv[1] = res.texUV[1];
+    o.flags = (res.frontFacing ? VT_ATTR_FRONT_FACING : 0u) | (res.hitSky ? VT_ATTR_HIT_SKY : 0u) |
+              (res.HitWater() ? VT_ATTR_HIT_WATER : 0u);
+    o.prim = static_cast<uint32_t>(prim);
+}
+
+// Batched loop over the reference's single-ray Traverse body.  stats (nullable) =
+// {traversal_steps, intersections} from SingleRayTraverser::Statistics
+// (libs/bvh/include/bvh/single_ray_traverser.hpp:132-135).  Returns seconds spent in the loop.
+double vtref_traverse(void *h, const vt_ray *rays, uint64_t n, vt_hit *hits, vt_attr *attrs, int threads,
+                      uint64_t *stats) {
+    AccelStruct &a = static_cast<RefScene *>(h)->accel;
+    if (!a.mAccelBuilt) return -1.0;
+    if (threads <= 0) threads = omp_get_max_threads();
+    uint64_t steps = 0, isects = 0;
+    const bool want_stats = stats != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads) reduction(+ : steps, isects)
+    for (int64_t i = 0; i < static_cast<int64_t>(n); i++) {
+        const vt_ray &r = rays[i];
+        // source/objects/AccelStruct.cpp:810-818
+        Ray ray(Vector3(r.ox, r.oy, r.oz), Vector3(r.dx, r.dy, r.dz), &a, r.tmin, r.tmax);
+        std::optional<Intersector::Result> hit;
+        if (want_stats) {
+            Traverser::Statistics st;
+            hit = a.mpTraverser->traverse(ray, *a.mpIntersector, st);
+            steps += st.traversal_steps;
+            isects += st.intersections;
+        } else {
+            hit = a.mpTraverser->traverse(ray, *a.mpIntersector);
+        }
+        if (hit) {
+            if (hits) hits[i] = vt_hit{hit->intersection.t, hit->intersection.u, hit->intersection.v,
+                                       static_cast<uint32_t>(hit->primitive_index)};
+            if (attrs) fill_attr(a, r, hit->primitive_index, hit->distance(), hit->intersection.u, hit->intersection.v, -1.f, -1.f, attrs[i]);
+        } else {
+            if (hits) hits[i] = vt_hit{0.f, 0.f, 0.f, VT_MISS};
+            if (attrs) {
+                std::memset(&attrs[i], 0, sizeof(vt_attr));
+                attrs[i].prim = VT_MISS;
+            }
+        }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (stats) {
+        stats[0] = steps;
+        stats[1] = isects;
+    }
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// TraceResult for given hits (so the attribute stage can be checked on its own).
+void vtref_trace_result(void *h, const vt_ray *rays, const vt_hit *hits, uint64_t n, vt_attr *attrs, int threads) {
+    AccelStruct &a = static_cast<RefScene *>(h)->accel;
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+    for (int64_t i = 0; i < static_cast<int64_t>(n); i++) {
+        if (hits[i].prim == VT_MISS) {
+            std::memset(&attrs[i], 0, sizeof(vt_attr));
+            attrs[i].prim = VT_MISS;
+        } else {
+            fill_attr(a, rays[i], hits[i].prim, hits[i].t, hits[i].u, hits[i].v, -1.f, -1.f, attrs[i]);
+        }
+    }
+}
+
+// IVTFTexture::Sample(u, v, mip) through the reference sampler: in = n × (u, v, mip), out = n × rgba.
+void vtref_sample(void *h, int tex, const float *uvm, uint64_t n, float *rgba) {
+    auto *rs = static_cast<RefScene *>(h);
+    const VisTrace::IVTFTexture &t = *rs->textures[tex]; // 3-arg inline overload, include/vistrace/IVTFTexture.h:139-142
+    for (uint64_t i = 0; i < n; i++) {
+        VisTrace::Pixel p = t.Sample(uvm[i * 3], uvm[i * 3 + 1], uvm[i * 3 + 2]);
+        rgba[i * 4] = p.r;
+        rgba[i * 4 + 1] = p.g;
+        rgba[i * 4 + 2] = p.b;
+        rgba[i * 4 + 3] = p.a;
+    }
+}
+
+// FastNodeIntersector on one node (libs/bvh/include/bvh/node_intersectors.hpp:82-103): out = {entry, exit}.
+void vtref_node_intersect(const vt_node *node, const vt_ray *r, float *out2) {
+    BVH::Node nd;
+    std::memcpy(&nd, node, sizeof(nd));
+    Ray ray(Vector3(r->ox, r->oy, r->oz), Vector3(r->dx, r->dy, r->dz), nullptr, r->tmin, r->tmax);
+    bvh::FastNodeIntersector<BVH> ni(ray);
+    auto d = ni.intersect(nd, ray);
+    out2[0] = d.first;
+    out2[1] = d.second;
+}
+
+// Triangle::intersect on one input triangle without a hierarchy (source/objects/Primitives.h:168-215).
+// Returns 1 and fills tuv on a hit.
+int vtref_tri_intersect(void *h, uint64_t prim, const vt_ray *r, float *tuv) {
+    AccelStruct &a = static_cast<RefScene *>(h)->accel;
+    Ray ray(Vector3(r->ox, r->oy, r->oz), Vector3(r->dx, r->dy, r->dz), &a, r->tmin, r->tmax);
+    auto hit = a.mTriangles[prim].intersect(ray);
+    if (!hit) return 0;
+    tuv[0] = hit->t;
+    tuv[1] = hit->u;
+    tuv[2] = hit->v;
+    return 1;
+}
+
+} // extern "C"
