@@ -210,6 +210,11 @@ int vt_accel_get_bvh(const vt_accel *accel, vt_node *nodes, uint64_t *node_count
 int vt_accel_traverse(vt_accel *accel, const vt_ray *rays, uint64_t n, vt_hit *hits,
                       vt_attr *attrs, uint32_t flags, void *stream);
 
+/* Same with per-ray texture-LOD cones: cones = n x {coneWidth, coneAngle}, the 5th and 6th
+ * arguments of accel:Traverse (source/objects/AccelStruct.cpp:795-803).  NULL = (-1, -1) = mip 0. */
+int vt_accel_traverse_cones(vt_accel *accel, const vt_ray *rays, const float *cones, uint64_t n,
+                            vt_hit *hits, vt_attr *attrs, uint32_t flags, void *stream);
+
 /* Eager TraceResult for hits that were produced earlier (device or host pointers as
  * per flags): the constructor + getters of source/objects/TraceResult.cpp:45-262. */
 int vt_accel_trace_result(vt_accel *accel, const vt_ray *rays, const vt_hit *hits,
@@ -224,6 +229,23 @@ uint64_t vt_accel_launch_count(const vt_accel *accel);
 /* Scene statistics: n_tris, node_count, bytes resident in HBM. */
 int vt_accel_stats(const vt_accel *accel, uint64_t *n_tris, uint64_t *node_count,
                    uint64_t *device_bytes);
+
+/* What the Triangle constructor derived per input triangle, n x 16 floats
+ * {p0, e1, e2, n, nNorm, lod} (source/objects/Primitives.h:75-102). */
+int vt_accel_get_tri_derived(const vt_accel *accel, float *out16);
+
+/* Host-only (no GPU touched): the hierarchy build step on its own, bvh::Bvh<float> form out.
+ * Call with nodes == NULL to get the node count; *node_count is the capacity of `nodes` on
+ * entry and the node count on return; prim_indices has scene->n_tris entries. */
+int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices);
+
+/* Host-only: flatten a bvh::Bvh<float>-form hierarchy to the device layout — (node_count-1)/2
+ * 64-byte sibling pairs (the first bfs_pairs in breadth-first order, depth-first below) and the
+ * leaf-order permutation of the triangles.  Validates the tree (adjacent odd child pairs, every
+ * primitive covered once, depth <= 64). */
+int vt_flatten_bvh(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris,
+                   uint32_t bfs_pairs, void *pairs_out, uint32_t *leaf_order_out,
+                   uint32_t *root_leaf_count, uint32_t *max_depth);
 
 /* Last error message of the calling thread ("" if none). */
 const char *vt_last_error(void);

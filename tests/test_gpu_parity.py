@@ -1,0 +1,199 @@
+"""-m gpu parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): hit/miss, primitive id and (t, u, v) BIT-EXACT — the kernel
+traverses the same hierarchy in the reference's order with the reference's arithmetic, so even
+exact ties must agree; TraceResult attributes within 1e-5 relative (they are bit-exact in
+practice; the tolerance covers sqrt/div differences the spec allows).
+"""
+import numpy as np
+import pytest
+
+from conftest import attr_max_rel_err, compare_hits, oracle_kinds
+
+pytestmark = pytest.mark.gpu
+
+FLT_MAX = np.finfo(np.float32).max
+ATTR_FLOAT_FIELDS = ("pos", "distance", "normal", "alpha", "tangent", "metalness", "binormal", "roughness",
+                     "geometric_normal", "base_mip", "albedo", "uvw", "tex_uv")
+ATTR_INT_FIELDS = ("ent_id", "submat_idx", "flags", "prim")
+
+
+@pytest.fixture(scope="module")
+def vt(built):
+    import vistrace_b200
+
+    assert vistrace_b200.lib().vt_device_count() >= 1, "no CUDA device"
+    return vistrace_b200
+
+
+def _check_against(vt, oracle_mod, scene, rays, kind, bvh_from, any_hit=False):
+    """Run GPU and oracle over the SAME hierarchy and compare everything."""
+    from vistrace_b200 import abi
+
+    accel = vt.Accel(0)
+    cpu = oracle_mod.CpuScene(scene, kind, build_bvh=(bvh_from == "reference"))
+    if bvh_from == "reference":
+        accel.populate(scene, bvh=cpu.get_bvh())  # the reference's own PLOC + LeafCollapser tree
+    else:
+        accel.populate(scene)  # product builder; hand the same tree to the oracle
+        cpu.set_bvh(*accel.get_bvh())
+    np.testing.assert_array_equal(accel.tri_derived().view(np.uint32), cpu.tri_derived().view(np.uint32))
+    want = cpu.traverse(rays, want_attrs=True)
+    if any_hit:
+        hits = accel.traverse(rays, any_hit=True)
+        np.testing.assert_array_equal(hits["prim"] == abi.VT_MISS, want["hits"]["prim"] == abi.VT_MISS)
+        return accel, cpu, hits, None, want
+    hits, attrs = accel.traverse(rays, want_attrs=True)
+    rep = compare_hits(hits, want["hits"])
+    assert rep["hit_miss_mismatch"] == 0 and rep["prim_mismatch"] == 0 and rep["tuv_bit_mismatch"] == 0, rep
+    assert hits.tobytes() == want["hits"].tobytes()
+    err = attr_max_rel_err(attrs, want["attrs"])
+    for f in ATTR_FLOAT_FIELDS:
+        assert err[f] <= 1e-5, (f, err[f])  # tolerance from BASELINE.json north_star
+    for f in ATTR_INT_FIELDS:
+        assert err[f] == 0, (f, err[f])
+    miss = hits["prim"] == abi.VT_MISS
+    assert not attrs[miss].view(np.uint32).reshape(miss.sum(), -1)[:, :-1].any()  # miss records are zero
+    return accel, cpu, hits, attrs, want
+
+
+@pytest.mark.parametrize("kind", oracle_kinds())
+@pytest.mark.parametrize("bvh_from", ["product", "reference"])
+def test_config1_heightfield_primary_and_bounce(vt, oracle_mod, kind, bvh_from):
+    from vistrace_b200 import scenes
+
+    if bvh_from == "reference" and kind != "reference":
+        pytest.skip("the reference-built tree needs oracle/_ref")
+    scene = scenes.scene_heightfield(96)
+    rays = scenes.pinhole_rays(480, 270, (0, -80, 60), (0, 0, 5))
+    accel, cpu, hits, attrs, want = _check_against(vt, oracle_mod, scene, rays, kind, bvh_from)
+    bounce, _ = scenes.bounce_rays(attrs, spp=2)
+    assert len(bounce) > 1000
+    got = accel.traverse(bounce)
+    assert got.tobytes() == cpu.traverse(bounce)["hits"].tobytes()
+
+
+@pytest.mark.parametrize("kind", oracle_kinds())
+def test_config2_props_primary_and_shadow(vt, oracle_mod, kind):
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_props(24, 31, 15, 24)
+    rays = scenes.pinhole_rays(480, 270, (0, -95, 40), (0, 0, 10))
+    accel, cpu, hits, attrs, want = _check_against(vt, oracle_mod, scene, rays, kind, "product")
+    assert len(np.unique(attrs["ent_id"][hits["prim"] != abi.VT_MISS])) > 5  # several entities visible
+    shadow, _ = scenes.shadow_rays(attrs)
+    got = accel.traverse(shadow)
+    assert got.tobytes() == cpu.traverse(shadow)["hits"].tobytes()
+    occl = accel.traverse(shadow, any_hit=True)  # early-out variant: only hit / no-hit is defined
+    np.testing.assert_array_equal(occl["prim"] == abi.VT_MISS, got["prim"] == abi.VT_MISS)
+
+
+@pytest.mark.parametrize("kind", oracle_kinds())
+@pytest.mark.parametrize("bvh_from", ["product", "reference"])
+def test_config4_foliage_alpha_test_and_attrs(vt, oracle_mod, kind, bvh_from):
+    from vistrace_b200 import abi, scenes
+
+    if bvh_from == "reference" and kind != "reference":
+        pytest.skip("the reference-built tree needs oracle/_ref")
+    scene = scenes.scene_foliage(n_cards=6000, tex_size=128)
+    rays = scenes.pinhole_rays(480, 270, (0, -48, 20), (0, 0, 8))
+    accel, cpu, hits, attrs, want = _check_against(vt, oracle_mod, scene, rays, kind, bvh_from)
+    mats = scene.tris["material"][hits["prim"][hits["prim"] != abi.VT_MISS]]
+    assert (mats >= 2).sum() > 1000  # alpha-tested cards are actually being hit ...
+    assert (attrs["alpha"][hits["prim"] != abi.VT_MISS][mats >= 2] >= 0.5 - 1e-6).all()  # ... and only where opaque
+    bounce, _ = scenes.bounce_rays(attrs, spp=1)
+    assert accel.traverse(bounce).tobytes() == cpu.traverse(bounce)["hits"].tobytes()
+
+
+@pytest.mark.parametrize("kind", oracle_kinds())
+def test_incoherent_rays_finite_tmax(vt, oracle_mod, kind):
+    from vistrace_b200 import scenes
+
+    scene = scenes.scene_props(8, 31, 15, 16)
+    rays = scenes.random_rays(60000, (-90, -90, -5), (90, 90, 70), seed=11)
+    rays["tmax"][::3] = 25.0  # shadow-style finite interval
+    rays["tmin"][::5] = 3.0
+    rays["d"][::7] *= 3.5  # un-normalised directions: t is parametric (AccelStruct.cpp:810-815)
+    _check_against(vt, oracle_mod, scene, rays, kind, "product")
+
+
+def test_edge_cases(vt, oracle_mod):
+    from vistrace_b200 import abi, scenes
+
+    # (a) a scene small enough for the root to be a leaf (single_ray_traverser.hpp:72-73)
+    tiny = abi.SceneData(scenes.box((-1, -1, -1), (1, 1, 1), inward=False)[:2])
+    rays = scenes.random_rays(4096, (-3, -3, -3), (3, 3, 3), seed=3)
+    accel, cpu, hits, attrs, want = _check_against(vt, oracle_mod, tiny, rays, "port", "product")
+    assert (hits["prim"] != abi.VT_MISS).any()
+    # (b) empty batch
+    assert len(accel.traverse(rays[:0])) == 0
+    # (c) ragged batch sizes around the warp / CTA granularity
+    for n in (1, 31, 32, 33, 127, 129, 1000):
+        assert accel.traverse(rays[:n]).tobytes() == want["hits"][:n].tobytes()
+    # (d) argument rules (AccelStruct.cpp:805-806): invalid rays become counted misses
+    bad = rays[:64].copy()
+    bad["tmin"][:10] = -1.0
+    bad["tmax"][10:20] = 0.0
+    bad["tmax"][20:30] = np.nan
+    got = accel.traverse(bad)
+    assert (got["prim"][:30] == abi.VT_MISS).all() and accel.invalid_rays == 30
+    assert got[30:].tobytes() == want["hits"][30:64].tobytes()
+    # (e) axis-parallel rays and signed zeros (the octant logic; libs/bvh/test/node_intersectors.cpp)
+    scene = scenes.scene_heightfield(32)
+    ax = np.zeros(6 * 500, abi.RAY)
+    rng = np.random.default_rng(0)
+    ax["o"] = rng.uniform(-40, 40, (len(ax), 3)).astype(np.float32)
+    ax["o"][:, 2] = rng.uniform(12, 40, len(ax))
+    dirs = np.array([[0, 0, -1], [0, -0.0, -1], [-0.0, 0, -1], [1, 0, 0], [0, 1, -0.0], [-1, -0.0, 0]], np.float32)
+    ax["d"] = np.tile(dirs, (500, 1))
+    ax["tmax"] = FLT_MAX
+    _check_against(vt, oracle_mod, scene, ax, "port", "product")
+
+
+def test_trace_result_stage_alone(vt, oracle_mod):
+    """K2 on its own: attributes for hits produced elsewhere (here: by the oracle)."""
+    from vistrace_b200 import scenes
+
+    scene = scenes.scene_foliage(n_cards=3000, tex_size=64)
+    rays = scenes.pinhole_rays(320, 180, (0, -48, 20), (0, 0, 8))
+    accel = vt.Accel(0).populate(scene)
+    cpu = oracle_mod.CpuScene(scene, "port", build_bvh=False)
+    cpu.set_bvh(*accel.get_bvh())
+    want = cpu.traverse(rays, want_attrs=True)
+    attrs = accel.trace_result(rays, want["hits"])
+    err = attr_max_rel_err(attrs, want["attrs"])
+    for f in ATTR_FLOAT_FIELDS:
+        assert err[f] <= 1e-5, (f, err[f])
+
+
+def test_single_ray_traverse_surface(vt, oracle_mod):
+    """Host buffers, n = 1: what the Lua-facing accel:Traverse does per call."""
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_heightfield(32)
+    accel = vt.Accel(0).populate(scene)
+    ray = np.zeros(1, abi.RAY)
+    ray["o"], ray["d"], ray["tmax"] = (0, 0, 50), (0, 0, -1), FLT_MAX
+    hit, attr = accel.traverse(ray, want_attrs=True)
+    assert hit["prim"][0] != abi.VT_MISS and attr["flags"][0] & abi.VT_ATTR_FRONT_FACING
+    ray["d"] = (0, 0, 1)
+    hit, attr = accel.traverse(ray, want_attrs=True)
+    assert attr["flags"][0] & abi.VT_ATTR_HIT_SKY  # the room's ceiling is a sky brush: a hit, not a miss
+
+
+def test_large_batch_properties(vt):
+    """BASELINE-size batch (1920x1080) checked through size-independent properties: every ray of a
+    closed room hits, t reproduces the hit position, and splitting the batch changes nothing."""
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_heightfield(224)
+    rays = scenes.pinhole_rays(1920, 1080, (0, -80, 60), (0, 0, 5))
+    accel = vt.Accel(0).populate(scene)
+    hits, attrs = accel.traverse(rays, want_attrs=True)
+    assert (hits["prim"] != abi.VT_MISS).all()
+    pos_from_t = rays["o"] + rays["d"] * hits["t"][:, None]
+    assert np.abs(pos_from_t - attrs["pos"]).max() < 2e-2
+    assert np.abs(attrs["uvw"].sum(-1) - 1).max() < 1e-5
+    half = len(rays) // 2
+    again = np.concatenate([accel.traverse(rays[:half]), accel.traverse(rays[half:])])
+    assert again.tobytes() == hits.tobytes()

@@ -1,0 +1,100 @@
+"""GPU exploration harness (not a test, not the bench): times K1/K2 over knob settings.
+
+usage: python tools/gpu_explore.py [--quads 1582] [--res 1920x1080] [--spp 4] [--knobs a=b,c=d;...]
+Knobs are the VT_* environment variables read at populate time.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import vistrace_b200 as vt  # noqa: E402
+from vistrace_b200 import abi, scenes  # noqa: E402
+
+
+def to_dev(a):
+    return torch.from_numpy(a.view(np.uint8).reshape(-1)).cuda()
+
+
+def time_traverse(accel, d_rays, n, d_hits, reps=5, any_hit=False, d_attrs=None):
+    stream = torch.cuda.current_stream()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        accel.traverse_device(d_rays.data_ptr(), n, d_hits.data_ptr(), None if d_attrs is None else d_attrs.data_ptr(), any_hit=any_hit, stream=stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quads", type=int, default=224)
+    ap.add_argument("--res", default="1920x1080")
+    ap.add_argument("--spp", type=int, default=4)
+    ap.add_argument("--knobs", default="")
+    ap.add_argument("--props", type=int, default=0)
+    ap.add_argument("--cpu", type=int, default=0, help="time the CPU reference on this many rays")
+    args = ap.parse_args()
+    w, h = map(int, args.res.split("x"))
+    t0 = time.time()
+    if args.quads <= 400:
+        scene = scenes.scene_heightfield(args.quads)
+        cam = ((0, -80, 60), (0, 0, 5))
+    else:
+        scene = scenes.scene_terrain_closed(args.quads, n_props=args.props)
+        cam = ((0, -330, 200), (0, 0, 10))
+    print(f"scene: {scene.n_tris} tris, gen {time.time()-t0:.1f}s", flush=True)
+    t0 = time.time()
+    bvh = vt.build_bvh(scene)
+    print(f"build: {len(bvh[0])} nodes in {time.time()-t0:.2f}s", flush=True)
+    rays = scenes.pinhole_rays(w, h, *cam)
+    knob_sets = [dict(kv.split("=") for kv in ks.split(",") if kv) for ks in args.knobs.split(";")] if args.knobs else [{}]
+    bounce = None
+    for knobs in knob_sets:
+        for k in list(os.environ):
+            if k.startswith("VT_"):
+                del os.environ[k]
+        os.environ.update(knobs)
+        accel = vt.Accel(0)
+        t0 = time.time()
+        accel.populate(scene, bvh=bvh)
+        t_up = time.time() - t0
+        if bounce is None:
+            hits, attrs = accel.traverse(rays, want_attrs=True)
+            bounce, _ = scenes.bounce_rays(attrs, spp=args.spp)
+            print(f"primary hit frac {(hits['prim'] != abi.VT_MISS).mean():.3f}; bounce rays {len(bounce)}", flush=True)
+            d_rays, d_bounce = to_dev(rays), to_dev(bounce)
+            d_hits = torch.empty(max(len(rays), len(bounce)) * 16, dtype=torch.uint8, device="cuda")
+            d_attrs = torch.empty(len(rays) * 128, dtype=torch.uint8, device="cuda")
+        ms_p = time_traverse(accel, d_rays, len(rays), d_hits)
+        ms_b = time_traverse(accel, d_bounce, len(bounce), d_hits)
+        ms_a = time_traverse(accel, d_bounce, len(bounce), d_hits, any_hit=True)
+        ms_pa = time_traverse(accel, d_rays, len(rays), d_hits, d_attrs=d_attrs)
+        print(json.dumps({"knobs": knobs, "upload_s": round(t_up, 2), "primary_Mrays": round(len(rays) / ms_p / 1e3, 1),
+                          "bounce_Mrays": round(len(bounce) / ms_b / 1e3, 1), "bounce_anyhit_Mrays": round(len(bounce) / ms_a / 1e3, 1),
+                          "primary+attrs_Mrays": round(len(rays) / ms_pa / 1e3, 1), "ms": [round(ms_p, 3), round(ms_b, 3), round(ms_a, 3), round(ms_pa, 3)]}), flush=True)
+        accel.close()
+    if args.cpu:
+        import oracle
+
+        kind = "reference" if oracle.available("reference") else "port"
+        cpu = oracle.CpuScene(scene, kind, build_bvh=False)
+        cpu.set_bvh(*bvh)
+        for name, rr in (("primary", rays), ("bounce", bounce)):
+            sub = rr[:: max(1, len(rr) // args.cpu)][: args.cpu]
+            r = cpu.traverse(sub, want_stats=True)
+            print(json.dumps({"cpu": kind, "rays": name, "threads": cpu.max_threads, "Mrays": round(len(sub) / r["seconds"] / 1e6, 2),
+                              "steps_per_ray": round(r["steps"] / len(sub), 1), "isects_per_ray": round(r["isects"] / len(sub), 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

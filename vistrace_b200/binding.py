@@ -1,0 +1,203 @@
+"""ctypes binding of include/vistrace_b200.h (plumbing; see package docstring)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def library_path():
+    return os.path.join(HERE, "libvistrace_b200.so")
+
+
+_lib = None
+
+# every symbol include/vistrace_b200.h declares: (restype, argtypes)
+_vp, _u64, _u32, _i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+SYMBOLS = {
+    "vt_device_count": (_i32, []),
+    "vt_accel_create": (_vp, [_i32]),
+    "vt_accel_destroy": (None, [_vp]),
+    "vt_accel_populate": (_i32, [_vp, _vp]),
+    "vt_accel_populate_with_bvh": (_i32, [_vp, _vp, _vp, _u64, _vp]),
+    "vt_accel_get_bvh": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "vt_accel_traverse": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32, _vp]),
+    "vt_accel_traverse_cones": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
+    "vt_accel_trace_result": (_i32, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
+    "vt_accel_invalid_rays": (_u64, [_vp]),
+    "vt_accel_launch_count": (_u64, [_vp]),
+    "vt_accel_stats": (_i32, [_vp, _vp, _vp, _vp]),
+    "vt_accel_get_tri_derived": (_i32, [_vp, _vp]),
+    "vt_build_bvh": (_i32, [_vp, _vp, _vp, _vp]),
+    "vt_flatten_bvh": (_i32, [_vp, _u64, _vp, _u64, _u32, _vp, _vp, _vp, _vp]),
+    "vt_last_error": (C.c_char_p, []),
+}
+
+
+def lib():
+    """Load libvistrace_b200.so or fail loudly (there is no fallback)."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"{path} is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C vistrace_b200/csrc`; vistrace_b200 has no CPU fallback"
+            )
+        L = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _err():
+    return lib().vt_last_error().decode()
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what}: {_err()}")
+
+
+def _ptr(x):
+    """numpy array -> host address; int -> passed through (device pointer); None -> NULL."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return int(x)
+
+
+def build_bvh(scene):
+    """Host-only hierarchy build -> (nodes, prim_indices) in bvh::Bvh<float> form."""
+    L = lib()
+    cnt = C.c_uint64(0)
+    _check(L.vt_build_bvh(C.cast(scene.ptr(), _vp), None, C.addressof(cnt), None), "vt_build_bvh")
+    nodes = np.zeros(cnt.value, abi.NODE)
+    prims = np.zeros(scene.n_tris, np.uint64)
+    cap = C.c_uint64(len(nodes))
+    _check(L.vt_build_bvh(C.cast(scene.ptr(), _vp), nodes.ctypes.data, C.addressof(cap), prims.ctypes.data), "vt_build_bvh")
+    return nodes, prims
+
+
+PAIR = np.dtype(
+    [
+        ("l_bounds", np.float32, 6),
+        ("l_count", np.uint32),
+        ("l_first", np.uint32),
+        ("r_bounds", np.float32, 6),
+        ("r_count", np.uint32),
+        ("r_first", np.uint32),
+    ]
+)
+
+
+def flatten_bvh(nodes, prim_indices, bfs_pairs=384):
+    """Host-only flatten -> dict(pairs, leaf_order, root_leaf_count, max_depth)."""
+    L = lib()
+    nodes = np.ascontiguousarray(nodes, abi.NODE)
+    prim_indices = np.ascontiguousarray(prim_indices, np.uint64)
+    n_pairs = max(0, (len(nodes) - 1) // 2)
+    pairs = np.zeros(n_pairs, PAIR)
+    order = np.zeros(len(prim_indices), np.uint32)
+    rl, md = C.c_uint32(0), C.c_uint32(0)
+    _check(
+        L.vt_flatten_bvh(nodes.ctypes.data, len(nodes), prim_indices.ctypes.data, len(prim_indices), bfs_pairs,
+                         pairs.ctypes.data, order.ctypes.data, C.addressof(rl), C.addressof(md)),
+        "vt_flatten_bvh",
+    )
+    return {"pairs": pairs, "leaf_order": order, "root_leaf_count": rl.value, "max_depth": md.value}
+
+
+class Accel:
+    """vt_accel handle: the AccelStruct of source/objects/AccelStruct.h:61-86 bound to one GPU."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        self.h = self.L.vt_accel_create(device)
+        if not self.h:
+            raise RuntimeError(f"vt_accel_create: {_err()}")
+        self.scene = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vt_accel_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def populate(self, scene, bvh=None):
+        """PopulateAccel: build on the host (or take the caller's bvh=(nodes, prim_indices)) and upload."""
+        self.scene = scene
+        if bvh is None:
+            _check(self.L.vt_accel_populate(self.h, C.cast(scene.ptr(), _vp)), "vt_accel_populate")
+        else:
+            nodes = np.ascontiguousarray(bvh[0], abi.NODE)
+            prims = np.ascontiguousarray(bvh[1], np.uint64)
+            _check(
+                self.L.vt_accel_populate_with_bvh(self.h, C.cast(scene.ptr(), _vp), nodes.ctypes.data, len(nodes), prims.ctypes.data),
+                "vt_accel_populate_with_bvh",
+            )
+        return self
+
+    def get_bvh(self):
+        cnt, nt = C.c_uint64(0), C.c_uint64(0)
+        _check(self.L.vt_accel_get_bvh(self.h, None, C.addressof(cnt), None, C.addressof(nt)), "vt_accel_get_bvh")
+        nodes = np.zeros(cnt.value, abi.NODE)
+        prims = np.zeros(nt.value, np.uint64)
+        _check(self.L.vt_accel_get_bvh(self.h, nodes.ctypes.data, None, prims.ctypes.data, None), "vt_accel_get_bvh")
+        return nodes, prims
+
+    def tri_derived(self):
+        out = np.zeros((self.scene.n_tris, 16), np.float32)
+        _check(self.L.vt_accel_get_tri_derived(self.h, out.ctypes.data), "vt_accel_get_tri_derived")
+        return out
+
+    def traverse(self, rays, want_attrs=False, any_hit=False, cones=None):
+        """Host-buffer call: numpy rays in, numpy hits (and attrs) out, synchronous."""
+        rays = np.ascontiguousarray(rays, abi.RAY)
+        hits = np.zeros(len(rays), abi.HIT)
+        attrs = np.zeros(len(rays), abi.ATTR) if want_attrs else None
+        flags = abi.VT_TRAVERSE_ANY_HIT if any_hit else 0
+        if cones is None:
+            rc = self.L.vt_accel_traverse(self.h, rays.ctypes.data, len(rays), hits.ctypes.data, _ptr(attrs), flags, None)
+        else:
+            cones = np.ascontiguousarray(cones, np.float32)
+            rc = self.L.vt_accel_traverse_cones(self.h, rays.ctypes.data, cones.ctypes.data, len(rays), hits.ctypes.data,
+                                                _ptr(attrs), flags, None)
+        _check(rc, "vt_accel_traverse")
+        return (hits, attrs) if want_attrs else hits
+
+    def traverse_device(self, d_rays, n, d_hits, d_attrs=None, any_hit=False, stream=None):
+        """Device-pointer call (ints = CUDA device addresses): enqueues on `stream` and returns."""
+        flags = abi.VT_TRAVERSE_DEVICE_PTRS | (abi.VT_TRAVERSE_ANY_HIT if any_hit else 0)
+        _check(self.L.vt_accel_traverse(self.h, _ptr(d_rays), n, _ptr(d_hits), _ptr(d_attrs), flags, _ptr(stream)), "vt_accel_traverse")
+
+    def trace_result(self, rays, hits):
+        rays = np.ascontiguousarray(rays, abi.RAY)
+        hits = np.ascontiguousarray(hits, abi.HIT)
+        attrs = np.zeros(len(rays), abi.ATTR)
+        _check(
+            self.L.vt_accel_trace_result(self.h, rays.ctypes.data, hits.ctypes.data, len(rays), attrs.ctypes.data, 0, None),
+            "vt_accel_trace_result",
+        )
+        return attrs
+
+    @property
+    def invalid_rays(self):
+        return int(self.L.vt_accel_invalid_rays(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.vt_accel_launch_count(self.h))
+
+    def stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(self.L.vt_accel_stats(self.h, C.addressof(a), C.addressof(b), C.addressof(c)), "vt_accel_stats")
+        return {"n_tris": a.value, "node_count": b.value, "device_bytes": c.value}

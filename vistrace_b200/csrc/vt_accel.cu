@@ -1,0 +1,651 @@
+// vt_accel.cu — host objects + the extern "C" boundary of include/vistrace_b200.h.
+//
+// Host code stays C++ (as in the reference); the kernels are reached only from here.  There is
+// NO CPU fallback: without a CUDA device vt_accel_create fails and every later call errors out.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "vt_host.h"
+#include "vt_kernels.h"
+
+namespace vt {
+
+static thread_local std::string g_last_error;
+
+#define VT_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr); \
+    } while (0)
+
+static int env_int(const char *name, int def) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : def;
+}
+static float env_float(const char *name, float def) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? (float)std::atof(v) : def;
+}
+
+// ------------------------------------------------------------------------------ Triangle
+Triangle::Triangle(const float p0_[3], const float p1[3], const float p2[3], uint32_t material_, const float uvs_[3][2],
+                   bool oneSided_)
+    : oneSided(oneSided_), material(material_) {
+    for (int k = 0; k < 3; k++) {
+        p0[k] = p0_[k];
+        e1[k] = p0_[k] - p1[k];  // e1 = p0 - p1, e2 = p2 - p0  (Primitives.h:82)
+        e2[k] = p2[k] - p0_[k];
+    }
+    std::memcpy(uvs, uvs_, sizeof(uvs));
+    std::memset(normals, 0, sizeof(normals));
+    std::memset(tangents, 0, sizeof(tangents));
+    alphas[0] = alphas[1] = alphas[2] = 0.f;
+    ComputeNormalAndLoD();
+}
+
+// Primitives.h:91-102.  Compiled with -ffp-contract=off / --fmad=false: every product and sum
+// below rounds separately, as in the reference build.
+void Triangle::ComputeNormalAndLoD() {
+    n[0] = e1[1] * e2[2] - e1[2] * e2[1];  // cross(e1, e2), LeftHandedNormal (vector.hpp:159-167)
+    n[1] = e1[2] * e2[0] - e1[0] * e2[2];
+    n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+    const float uv10x = uvs[1][0] - uvs[0][0], uv10y = uvs[1][1] - uvs[0][1];
+    const float uv20x = uvs[2][0] - uvs[0][0], uv20y = uvs[2][1] - uvs[0][1];
+    const float triUVArea = std::fabs(uv10x * uv20y - uv20x * uv10y);
+    float d = n[0] * n[0];  // bvh::dot / bvh::length (vector.hpp:134-147)
+    d += n[1] * n[1];
+    d += n[2] * n[2];
+    const float len = std::sqrt(d);
+    lod = 0.5f * std::log2(triUVArea / len);
+    for (int k = 0; k < 3; k++) nNorm[k] = n[k] / len;
+}
+
+// --------------------------------------------------------------------------- DeviceScene
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        VT_CUDA(cudaMalloc(&p, n * sizeof(T)));
+        cap = n;
+    }
+    void upload(const T *src, size_t n) {
+        ensure(n ? n : 1);
+        if (n) VT_CUDA(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    size_t bytes() const { return cap * sizeof(T); }
+};
+
+constexpr int kCounterSlots = 256;  // 16-byte {queue head, invalid rays} records, one per in-flight call
+
+struct DeviceScene {
+    DevBuf<VtPair> pairs;
+    DevBuf<VtTriRec> tris;
+    DevBuf<float> tri_uv;
+    DevBuf<VtTriAttr> attrs;
+    DevBuf<VtDevMaterial> mats;
+    DevBuf<VtDevEntity> ents;
+    DevBuf<VtDevTexture> texs;
+    DevBuf<uint8_t> texels;
+    DevBuf<unsigned long long> counters;
+    // staging for host-pointer calls
+    DevBuf<vt_ray> s_rays;
+    DevBuf<vt_hit> s_hits;
+    DevBuf<vt_attr> s_attrs;
+    DevBuf<float> s_cones;
+    VtSceneView view{};
+    VtLaunchConfig cfg;
+    std::atomic<uint32_t> next_slot{0};
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+
+    ~DeviceScene() {
+        pairs.release();
+        tris.release();
+        tri_uv.release();
+        attrs.release();
+        mats.release();
+        ents.release();
+        texs.release();
+        texels.release();
+        counters.release();
+        s_rays.release();
+        s_hits.release();
+        s_attrs.release();
+        s_cones.release();
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+    uint64_t scene_bytes() const {
+        return pairs.bytes() + tris.bytes() + tri_uv.bytes() + attrs.bytes() + mats.bytes() + ents.bytes() + texs.bytes() +
+               texels.bytes();
+    }
+};
+
+// ----------------------------------------------------------------------------- AccelStruct
+AccelStruct::AccelStruct(int device) : mDevice(device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw std::runtime_error(std::string("no CUDA device (the engine has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) throw std::runtime_error("device index out of range");
+    VT_CUDA(cudaSetDevice(device));
+    mpDevice = new DeviceScene();
+    cudaDeviceProp prop;
+    VT_CUDA(cudaGetDeviceProperties(&prop, device));
+    mpDevice->sm_count = prop.multiProcessorCount;
+    mpDevice->counters.ensure(kCounterSlots * 2);
+    VT_CUDA(cudaMemset(mpDevice->counters.p, 0, kCounterSlots * 2 * sizeof(unsigned long long)));
+    VT_CUDA(cudaStreamCreateWithFlags(&mpDevice->own_stream, cudaStreamNonBlocking));
+}
+
+AccelStruct::~AccelStruct() {
+    if (mpDevice) {
+        cudaSetDevice(mDevice);
+        delete mpDevice;
+    }
+}
+
+uint64_t AccelStruct::DeviceBytes() const { return mpDevice ? mpDevice->scene_bytes() : 0; }
+
+void AccelStruct::Ingest(const vt_scene &scene) {
+    // PopulateAccel prologue (source/objects/AccelStruct.cpp:537-556): drop the old structure, refill containers
+    mAccelBuilt = false;
+    mTriangles.clear();
+    mEntities.clear();
+    mMaterials.clear();
+    if (scene.n_tris > 0xFFFFFFF0ull) throw std::runtime_error("too many triangles (Bvh::IndexType is uint32_t, bvh.hpp:20)");
+    if (scene.n_tris && !scene.tris) throw std::runtime_error("scene.tris is null");
+    if (scene.n_materials == 0 || scene.n_entities == 0) throw std::runtime_error("scene needs at least one material and one entity");
+    if (scene.n_materials >= (1u << 30)) throw std::runtime_error("too many materials");
+    mMaterials.assign(scene.materials, scene.materials + scene.n_materials);
+    mEntities.assign(scene.entities, scene.entities + scene.n_entities);
+    for (const Material &m : mMaterials) {
+        const int32_t slots[8] = {m.base_texture, m.base_texture2, m.normal_map, m.normal_map2, m.mrao, m.mrao2, m.blend_texture, m.detail};
+        for (int32_t s : slots)
+            if (s >= (int32_t)scene.n_textures) throw std::runtime_error("material references a texture index past n_textures");
+    }
+    for (uint32_t i = 0; i < scene.n_textures; i++) {
+        const vt_texture &t = scene.textures[i];
+        if (t.width == 0 || t.height == 0 || t.mip_count == 0 || t.mip_count > 16 || !t.rgba)
+            throw std::runtime_error("texture " + std::to_string(i) + ": bad header");
+        uint64_t need = 0;
+        for (uint32_t m = 0; m < t.mip_count; m++) need += (uint64_t)std::max(1, t.width >> m) * std::max(1, t.height >> m) * 4;
+        if (need != t.nbytes) throw std::runtime_error("texture " + std::to_string(i) + ": nbytes does not match the RGBA8888 mip chain");
+    }
+    mTriangles.resize(scene.n_tris);
+    bool bad = false;
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)scene.n_tris; i++) {
+        const vt_tri_in &in = scene.tris[i];
+        Triangle t(in.p[0], in.p[1], in.p[2], in.material, in.uvs, in.one_sided != 0);
+        std::memcpy(t.normals, in.normals, sizeof(t.normals));
+        std::memcpy(t.tangents, in.tangents, sizeof(t.tangents));
+        std::memcpy(t.alphas, in.alphas, sizeof(t.alphas));
+        t.entIdx = in.ent_idx;
+        if (in.material >= scene.n_materials || in.ent_idx >= scene.n_entities) bad = true;
+        mTriangles[i] = t;
+    }
+    if (bad) throw std::runtime_error("triangle references a material or entity out of range");
+}
+
+void AccelStruct::Upload(const vt_scene &scene) {
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    D.cfg.persistent = env_int("VT_PERSISTENT", 1);
+    D.cfg.refill_threshold = env_int("VT_REFILL", 20);
+    const size_t n = mTriangles.size();
+
+    // how many leading pairs fit the shared-memory budget of one CTA
+    uint32_t smem_pairs = (uint32_t)env_int("VT_SMEM_PAIRS", 384);
+    FlatBvh flat;
+    std::string err;
+    if (!flatten_bvh(mAccel, n, smem_pairs, flat, err)) throw std::runtime_error(err);
+    smem_pairs = (uint32_t)std::min<size_t>(smem_pairs, flat.pairs.size());
+
+    // leaf-order geometry records + UVs; original-order attribute records
+    std::vector<VtTriRec> recs(n);
+    std::vector<float> uv(n * 6);
+    std::vector<VtTriAttr> attrs(n);
+    uint32_t any_alpha = 0;
+#pragma omp parallel for reduction(| : any_alpha)
+    for (int64_t s = 0; s < (int64_t)n; s++) {
+        const uint32_t orig = flat.leaf_order[s];
+        const Triangle &t = mTriangles[orig];
+        const Material &m = mMaterials[t.material];
+        VtTriRec &r = recs[s];
+        for (int k = 0; k < 3; k++) {
+            r.p0[k] = t.p0[k];
+            r.e1[k] = t.e1[k];
+            r.e2[k] = t.e2[k];
+        }
+        uint32_t fl = 0;
+        if (t.oneSided && (m.flags & VT_MATFLAG_NOCULL) == 0) fl |= VT_TRI_FLAG_CULL;  // Primitives.h:174
+        if (m.flags & VT_MATFLAG_ALPHATEST) fl |= VT_TRI_FLAG_ALPHATEST;               // Primitives.h:195
+        any_alpha |= (fl & VT_TRI_FLAG_ALPHATEST);
+        r.matflags = (t.material << 2) | fl;
+        r.orig = orig;
+        r.pad = 0;
+        std::memcpy(&uv[6 * s], t.uvs, 6 * sizeof(float));
+    }
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const Triangle &t = mTriangles[i];
+        VtTriAttr &a = attrs[i];
+        std::memcpy(a.p0, t.p0, 12);
+        std::memcpy(a.e1, t.e1, 12);
+        std::memcpy(a.e2, t.e2, 12);
+        std::memcpy(a.nNorm, t.nNorm, 12);
+        std::memcpy(a.normals, t.normals, 36);
+        std::memcpy(a.tangents, t.tangents, 36);
+        std::memcpy(a.uvs, t.uvs, 24);
+        std::memcpy(a.alphas, t.alphas, 12);
+        a.lod = t.lod;
+        a.material = t.material;
+        a.ent_idx = t.entIdx;
+    }
+
+    // materials / entities / textures (+ the 1x1 white stand-in for a null baseTexture: ingestion never
+    // leaves it null — fallback MISSING_TEXTURE, source/objects/AccelStruct.cpp:120,286)
+    std::vector<VtDevMaterial> dm(mMaterials.size());
+    for (size_t i = 0; i < mMaterials.size(); i++) {
+        const Material &m = mMaterials[i];
+        VtDevMaterial &o = dm[i];
+        std::memset(&o, 0, sizeof(o));
+        o.flags = m.flags;
+        o.surf_flags = m.surf_flags;
+        o.alphatest_reference = m.alphatest_reference;
+        o.tex_scale = m.tex_scale;
+        std::memcpy(o.colour, m.colour, 16);
+        std::memcpy(o.base_tex_mat, m.base_tex_mat, 32);
+        std::memcpy(o.base_tex_mat2, m.base_tex_mat2, 32);
+        std::memcpy(o.normal_map_mat, m.normal_map_mat, 32);
+        std::memcpy(o.normal_map_mat2, m.normal_map_mat2, 32);
+        std::memcpy(o.blend_tex_mat, m.blend_tex_mat, 32);
+        std::memcpy(o.detail_mat, m.detail_mat, 32);
+        o.detail_scale = m.detail_scale;
+        o.detail_blend_factor = m.detail_blend_factor;
+        o.base_texture = m.base_texture;
+        o.base_texture2 = m.base_texture2;
+        o.normal_map = m.normal_map;
+        o.normal_map2 = m.normal_map2;
+        o.mrao = m.mrao;
+        o.mrao2 = m.mrao2;
+        o.blend_texture = m.blend_texture;
+        o.detail = m.detail;
+        o.detail_blend_mode = m.detail_blend_mode;
+        o.masked_blending = m.masked_blending;
+        o.water = m.water;
+    }
+    std::vector<VtDevEntity> de(mEntities.size());
+    for (size_t i = 0; i < mEntities.size(); i++) {
+        de[i].id = mEntities[i].id;
+        std::memcpy(de[i].colour, mEntities[i].colour, 16);
+    }
+    std::vector<VtDevTexture> dt(scene.n_textures + 1);
+    std::vector<uint8_t> texels;
+    auto add_texture = [&](VtDevTexture &o, uint32_t w, uint32_t h, uint32_t mips, uint32_t flags, const uint8_t *px, uint64_t nbytes) {
+        std::memset(&o, 0, sizeof(o));
+        o.width = w;
+        o.height = h;
+        o.mips = mips;
+        o.flags = flags;
+        o.base = texels.size();
+        // chain is smallest mip first: offset of mip m = sizes of mips m+1 .. last (VTFParser.cpp:219-229)
+        for (uint32_t m = 0; m < mips; m++) {
+            uint32_t off = 0;
+            for (uint32_t i = m + 1; i < mips; i++) off += std::max(1u, w >> i) * std::max(1u, h >> i) * 4u;
+            o.mip_offset[m] = off;
+        }
+        texels.insert(texels.end(), px, px + nbytes);
+        while (texels.size() & 15) texels.push_back(0);
+    };
+    for (uint32_t i = 0; i < scene.n_textures; i++) {
+        const vt_texture &t = scene.textures[i];
+        add_texture(dt[i], t.width, t.height, t.mip_count, t.flags, t.rgba, t.nbytes);
+    }
+    const uint8_t white[4] = {255, 255, 255, 255};
+    add_texture(dt[scene.n_textures], 1, 1, 1, 0, white, 4);
+
+    D.pairs.upload(flat.pairs.data(), flat.pairs.size());
+    D.tris.upload(recs.data(), n);
+    D.tri_uv.upload(uv.data(), uv.size());
+    D.attrs.upload(attrs.data(), n);
+    D.mats.upload(dm.data(), dm.size());
+    D.ents.upload(de.data(), de.size());
+    D.texs.upload(dt.data(), dt.size());
+    D.texels.upload(texels.data(), texels.size());
+
+    VtSceneView &V = D.view;
+    V.pairs = D.pairs.p;
+    V.tris = D.tris.p;
+    V.tri_uv = D.tri_uv.p;
+    V.attrs = D.attrs.p;
+    V.mats = D.mats.p;
+    V.ents = D.ents.p;
+    V.texs = D.texs.p;
+    V.texels = D.texels.p;
+    V.n_pairs = (uint32_t)flat.pairs.size();
+    V.n_tris = (uint32_t)n;
+    V.root_leaf_count = flat.root_leaf_count;
+    V.n_smem_pairs = smem_pairs;
+    V.has_alphatest = any_alpha ? 1u : 0u;
+    V.fallback_tex = scene.n_textures;
+
+    int blocks = 0;
+    VT_CUDA(vt_traverse_occupancy(&blocks, (size_t)smem_pairs * sizeof(VtPair)));
+    if (blocks < 1) blocks = 1;
+    const int mult = env_int("VT_GRID_BLOCKS_PER_SM", blocks);
+    D.cfg.grid = D.sm_count * std::max(1, std::min(mult, blocks));
+    mAccelBuilt = true;
+}
+
+void AccelStruct::Populate(const vt_scene &scene) {
+    Ingest(scene);
+    // the build step of source/objects/AccelStruct.cpp:762-770, host side
+    build_bvh(mTriangles, mAccel, env_int("VT_MAX_LEAF", 4), env_float("VT_TRAV_COST", 1.0f));
+    Upload(scene);
+}
+
+void AccelStruct::PopulateWithBvh(const vt_scene &scene, const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices) {
+    Ingest(scene);
+    if (!nodes || !prim_indices || node_count == 0) throw std::runtime_error("populate_with_bvh: null hierarchy");
+    mAccel.nodes.assign(nodes, nodes + node_count);
+    mAccel.prim_indices.assign(prim_indices, prim_indices + scene.n_tris);
+    Upload(scene);
+}
+
+static void check_built(bool built) {
+    // source/objects/AccelStruct.cpp:780
+    if (!built) throw std::runtime_error("Unable to perform traversal, acceleration structure invalid (use AccelStruct:Rebuild to rebuild it)");
+}
+
+void AccelStruct::TraverseBatch(const vt_ray *rays, uint64_t n, vt_hit *hits, vt_attr *attrs, const float *cones,
+                                uint32_t flags, void *stream_) {
+    check_built(mAccelBuilt);
+    if (n == 0) return;
+    if (!rays || !hits) throw std::runtime_error("traverse: rays and hits must not be null");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    const bool dev_ptrs = (flags & VT_TRAVERSE_DEVICE_PTRS) != 0;
+    const bool any_hit = (flags & VT_TRAVERSE_ANY_HIT) != 0;
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : (dev_ptrs ? (cudaStream_t) nullptr : D.own_stream);
+    const uint32_t slot = D.next_slot.fetch_add(1) % kCounterSlots;
+    unsigned long long *ctr = D.counters.p + 2 * slot;
+    VT_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), stream));
+
+    const vt_ray *d_rays = rays;
+    vt_hit *d_hits = hits;
+    vt_attr *d_attrs = attrs;
+    const float *d_cones = cones;
+    if (!dev_ptrs) {
+        D.s_rays.ensure(n);
+        D.s_hits.ensure(n);
+        VT_CUDA(cudaMemcpyAsync(D.s_rays.p, rays, n * sizeof(vt_ray), cudaMemcpyHostToDevice, stream));
+        d_rays = D.s_rays.p;
+        d_hits = D.s_hits.p;
+        if (attrs) {
+            D.s_attrs.ensure(n);
+            d_attrs = D.s_attrs.p;
+            if (cones) {
+                D.s_cones.ensure(2 * n);
+                VT_CUDA(cudaMemcpyAsync(D.s_cones.p, cones, 2 * n * sizeof(float), cudaMemcpyHostToDevice, stream));
+                d_cones = D.s_cones.p;
+            }
+        }
+    }
+    VT_CUDA(vt_launch_traverse(D.view, d_rays, d_hits, n, any_hit, ctr, D.cfg, stream));
+    mLaunches++;
+    if (attrs) {
+        VT_CUDA(vt_launch_trace_result(D.view, d_rays, d_hits, d_cones, d_attrs, n, stream));
+        mLaunches++;
+    }
+    if (!dev_ptrs) {
+        unsigned long long invalid[2] = {0, 0};
+        VT_CUDA(cudaMemcpyAsync(hits, d_hits, n * sizeof(vt_hit), cudaMemcpyDeviceToHost, stream));
+        if (attrs) VT_CUDA(cudaMemcpyAsync(attrs, d_attrs, n * sizeof(vt_attr), cudaMemcpyDeviceToHost, stream));
+        VT_CUDA(cudaMemcpyAsync(invalid, ctr, sizeof(invalid), cudaMemcpyDeviceToHost, stream));
+        VT_CUDA(cudaStreamSynchronize(stream));
+        mInvalidRays = invalid[1];
+    }
+}
+
+void AccelStruct::TraceResultBatch(const vt_ray *rays, const vt_hit *hits, uint64_t n, vt_attr *attrs, const float *cones,
+                                   uint32_t flags, void *stream_) {
+    check_built(mAccelBuilt);
+    if (n == 0) return;
+    if (!rays || !hits || !attrs) throw std::runtime_error("trace_result: rays, hits and attrs must not be null");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    const bool dev_ptrs = (flags & VT_TRAVERSE_DEVICE_PTRS) != 0;
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : (dev_ptrs ? (cudaStream_t) nullptr : D.own_stream);
+    if (dev_ptrs) {
+        VT_CUDA(vt_launch_trace_result(D.view, rays, hits, cones, attrs, n, stream));
+        mLaunches++;
+        return;
+    }
+    D.s_rays.ensure(n);
+    D.s_hits.ensure(n);
+    D.s_attrs.ensure(n);
+    VT_CUDA(cudaMemcpyAsync(D.s_rays.p, rays, n * sizeof(vt_ray), cudaMemcpyHostToDevice, stream));
+    VT_CUDA(cudaMemcpyAsync(D.s_hits.p, hits, n * sizeof(vt_hit), cudaMemcpyHostToDevice, stream));
+    const float *d_cones = nullptr;
+    if (cones) {
+        D.s_cones.ensure(2 * n);
+        VT_CUDA(cudaMemcpyAsync(D.s_cones.p, cones, 2 * n * sizeof(float), cudaMemcpyHostToDevice, stream));
+        d_cones = D.s_cones.p;
+    }
+    VT_CUDA(vt_launch_trace_result(D.view, D.s_rays.p, D.s_hits.p, d_cones, D.s_attrs.p, n, stream));
+    mLaunches++;
+    VT_CUDA(cudaMemcpyAsync(attrs, D.s_attrs.p, n * sizeof(vt_attr), cudaMemcpyDeviceToHost, stream));
+    VT_CUDA(cudaStreamSynchronize(stream));
+}
+
+TraceResult *AccelStruct::Traverse(const float origin[3], const float direction[3], float tMin, float tMax, float coneWidth,
+                                   float coneAngle) {
+    check_built(mAccelBuilt);
+    // argument rules and messages of source/objects/AccelStruct.cpp:802-806
+    if (coneWidth >= 0 && coneAngle <= 0.f) throw std::invalid_argument("Valid cone width but invalid cone angle passed");
+    if (coneWidth < 0 && coneAngle > 0.f) throw std::invalid_argument("Valid cone angle but invalid cone width passed");
+    if (tMin < 0.f) throw std::invalid_argument("tMin cannot be less than 0");
+    if (tMax <= tMin) throw std::invalid_argument("tMax must be greater than tMin");
+    vt_ray ray{origin[0], origin[1], origin[2], tMin, direction[0], direction[1], direction[2], tMax};
+    vt_hit hit;
+    vt_attr attr;
+    const float cone[2] = {coneWidth, coneAngle};
+    TraverseBatch(&ray, 1, &hit, &attr, cone, 0, nullptr);
+    if (hit.prim == VT_MISS) return nullptr;  // Lua nil (AccelStruct.cpp:837)
+    return new TraceResult(attr);
+}
+
+}  // namespace vt
+
+// ================================================================================ C ABI
+struct vt_accel {
+    vt::AccelStruct impl;
+    explicit vt_accel(int device) : impl(device) {}
+};
+
+#define VT_TRY try {
+#define VT_CATCH(ret)                     \
+    }                                     \
+    catch (const std::exception &e) {     \
+        vt::g_last_error = e.what();      \
+        return ret;                       \
+    }                                     \
+    catch (...) {                         \
+        vt::g_last_error = "unknown error"; \
+        return ret;                       \
+    }
+
+extern "C" {
+
+const char *vt_last_error(void) { return vt::g_last_error.c_str(); }
+
+int vt_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        vt::g_last_error = cudaGetErrorString(e);
+        return -1;
+    }
+    return n;
+}
+
+vt_accel *vt_accel_create(int device) {
+    VT_TRY
+    return new vt_accel(device);
+    VT_CATCH(nullptr)
+}
+
+void vt_accel_destroy(vt_accel *a) { delete a; }
+
+int vt_accel_populate(vt_accel *a, const vt_scene *scene) {
+    VT_TRY
+    if (!a || !scene) throw std::runtime_error("null argument");
+    a->impl.Populate(*scene);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_populate_with_bvh(vt_accel *a, const vt_scene *scene, const vt_node *nodes, uint64_t node_count,
+                               const uint64_t *prim_indices) {
+    VT_TRY
+    if (!a || !scene) throw std::runtime_error("null argument");
+    a->impl.PopulateWithBvh(*scene, nodes, node_count, prim_indices);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_get_bvh(const vt_accel *a, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices, uint64_t *n_tris) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    const vt::HostBvh &b = a->impl.Bvh();
+    if (node_count) *node_count = b.nodes.size();
+    if (n_tris) *n_tris = b.prim_indices.size();
+    if (nodes) std::memcpy(nodes, b.nodes.data(), b.nodes.size() * sizeof(vt_node));
+    if (prim_indices) std::memcpy(prim_indices, b.prim_indices.data(), b.prim_indices.size() * sizeof(uint64_t));
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_traverse(vt_accel *a, const vt_ray *rays, uint64_t n, vt_hit *hits, vt_attr *attrs, uint32_t flags, void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.TraverseBatch(rays, n, hits, attrs, nullptr, flags, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_traverse_cones(vt_accel *a, const vt_ray *rays, const float *cones, uint64_t n, vt_hit *hits, vt_attr *attrs,
+                            uint32_t flags, void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.TraverseBatch(rays, n, hits, attrs, cones, flags, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_trace_result(vt_accel *a, const vt_ray *rays, const vt_hit *hits, uint64_t n, vt_attr *attrs, uint32_t flags,
+                          void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.TraceResultBatch(rays, hits, n, attrs, nullptr, flags, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+uint64_t vt_accel_invalid_rays(const vt_accel *a) { return a ? a->impl.InvalidRays() : 0; }
+uint64_t vt_accel_launch_count(const vt_accel *a) { return a ? a->impl.Launches() : 0; }
+
+int vt_accel_stats(const vt_accel *a, uint64_t *n_tris, uint64_t *node_count, uint64_t *device_bytes) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    if (n_tris) *n_tris = a->impl.Triangles().size();
+    if (node_count) *node_count = a->impl.Bvh().nodes.size();
+    if (device_bytes) *device_bytes = a->impl.DeviceBytes();
+    return 0;
+    VT_CATCH(1)
+}
+
+// Triangle constructor output for parity checks of the derived fields: n x 16 floats
+// {p0, e1, e2, n, nNorm, lod} (source/objects/Primitives.h:75-102).
+int vt_accel_get_tri_derived(const vt_accel *a, float *out16) {
+    VT_TRY
+    if (!a || !out16) throw std::runtime_error("null argument");
+    const auto &tris = a->impl.Triangles();
+    for (size_t i = 0; i < tris.size(); i++) {
+        const vt::Triangle &t = tris[i];
+        float *o = out16 + i * 16;
+        for (int k = 0; k < 3; k++) {
+            o[k] = t.p0[k];
+            o[3 + k] = t.e1[k];
+            o[6 + k] = t.e2[k];
+            o[9 + k] = t.n[k];
+            o[12 + k] = t.nNorm[k];
+        }
+        o[15] = t.lod;
+    }
+    return 0;
+    VT_CATCH(1)
+}
+
+// ---- host-only entry points (no GPU touched): the build and flatten steps on their own
+
+int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices) {
+    VT_TRY
+    if (!scene || !node_count) throw std::runtime_error("null argument");
+    std::vector<vt::Triangle> tris(scene->n_tris);
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)scene->n_tris; i++) {
+        const vt_tri_in &in = scene->tris[i];
+        tris[i] = vt::Triangle(in.p[0], in.p[1], in.p[2], in.material, in.uvs, in.one_sided != 0);
+    }
+    vt::HostBvh bvh;
+    vt::build_bvh(tris, bvh, vt::env_int("VT_MAX_LEAF", 4), vt::env_float("VT_TRAV_COST", 1.0f));
+    if (nodes) {
+        if (*node_count < bvh.nodes.size()) throw std::runtime_error("node buffer too small");
+        std::memcpy(nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(vt_node));
+        if (prim_indices) std::memcpy(prim_indices, bvh.prim_indices.data(), bvh.prim_indices.size() * sizeof(uint64_t));
+    }
+    *node_count = bvh.nodes.size();
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_flatten_bvh(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris,
+                   uint32_t bfs_pairs, void *pairs_out, uint32_t *leaf_order_out, uint32_t *root_leaf_count,
+                   uint32_t *max_depth) {
+    VT_TRY
+    if (!nodes || !prim_indices) throw std::runtime_error("null argument");
+    vt::HostBvh bvh;
+    bvh.nodes.assign(nodes, nodes + node_count);
+    bvh.prim_indices.assign(prim_indices, prim_indices + n_tris);
+    vt::FlatBvh flat;
+    std::string err;
+    if (!vt::flatten_bvh(bvh, n_tris, bfs_pairs, flat, err)) throw std::runtime_error(err);
+    if (pairs_out) std::memcpy(pairs_out, flat.pairs.data(), flat.pairs.size() * sizeof(VtPair));
+    if (leaf_order_out) std::memcpy(leaf_order_out, flat.leaf_order.data(), flat.leaf_order.size() * sizeof(uint32_t));
+    if (root_leaf_count) *root_leaf_count = flat.root_leaf_count;
+    if (max_depth) *max_depth = flat.max_depth;
+    return 0;
+    VT_CATCH(1)
+}
+
+}  // extern "C"

@@ -1,0 +1,391 @@
+// vt_bvh_build.cpp — host-side hierarchy construction (the step at
+// source/objects/AccelStruct.cpp:762-770) and flattening to the device layout.
+//
+// Construction stays on the host, as in the reference, and emits the same data structure the
+// reference traverses: bvh::Bvh<float> form (libs/bvh/include/bvh/bvh.hpp:17-99) — root at node 0,
+// the two children of an inner node adjacent at `first`, `first + 1`, leaves addressing a run of
+// `prim_indices`.  The builder itself is our own: a top-down binned-SAH build (OpenMP tasks over
+// subtrees) with the reference's cost model (traversal cost 1 vs. one unit per primitive,
+// libs/bvh/include/bvh/sah_based_algorithm.hpp:16) and a hard depth bound of 60 so the 64-entry
+// traversal stack (single_ray_traverser.hpp:14) can never overflow.  A caller that prefers the
+// reference's own PLOC + LeafCollapser tree passes it in through vt_accel_populate_with_bvh.
+#include "vt_host.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <omp.h>
+
+namespace vt {
+
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() {
+        for (int k = 0; k < 3; k++) {
+            lo[k] = std::numeric_limits<float>::max();
+            hi[k] = -std::numeric_limits<float>::max();
+        }
+    }
+    void grow(const float *mn, const float *mx) {
+        for (int k = 0; k < 3; k++) {
+            lo[k] = std::min(lo[k], mn[k]);
+            hi[k] = std::max(hi[k], mx[k]);
+        }
+    }
+    void grow(const Box &b) { grow(b.lo, b.hi); }
+    void grow_pt(const float *p) { grow(p, p); }
+    float half_area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    bool valid() const { return lo[0] <= hi[0]; }
+};
+
+constexpr int kBins = 16;
+constexpr int kMaxDepth = 60;
+
+struct BuildCtx {
+    const float *bmin, *bmax, *cen;  // n x 3 each
+    uint32_t *idx;
+    vt_node *nodes;
+    std::atomic<uint32_t> next_node;
+    int max_leaf;
+    float trav_cost;
+};
+
+void set_bounds(vt_node &nd, const Box &b) {
+    nd.bounds[0] = b.lo[0];
+    nd.bounds[1] = b.hi[0];
+    nd.bounds[2] = b.lo[1];
+    nd.bounds[3] = b.hi[1];
+    nd.bounds[4] = b.lo[2];
+    nd.bounds[5] = b.hi[2];
+}
+
+int ceil_log2(uint64_t v) {
+    int l = 0;
+    while ((1ull << l) < v) l++;
+    return l;
+}
+
+// Build the subtree over idx[begin, end) into nodes[node]; `box` is its bounds.
+void build_range(BuildCtx &c, uint32_t node, uint32_t begin, uint32_t end, const Box &box, int depth) {
+    vt_node &nd = c.nodes[node];
+    set_bounds(nd, box);
+    const uint32_t count = end - begin;
+    auto make_leaf = [&]() {
+        nd.prim_count = count;
+        nd.first = begin;
+    };
+    if (count <= 1) return make_leaf();
+
+    Box cb;
+    cb.reset();
+    for (uint32_t i = begin; i < end; i++) cb.grow_pt(c.cen + 3 * (size_t)c.idx[i]);
+
+    // binned SAH over the three axes
+    float best_cost = std::numeric_limits<float>::max();
+    int best_axis = -1, best_bin = -1;
+    const bool force_balance = depth + ceil_log2((count + c.max_leaf - 1) / c.max_leaf) >= kMaxDepth - 1;
+    if (!force_balance) {
+        for (int axis = 0; axis < 3; axis++) {
+            const float ext = cb.hi[axis] - cb.lo[axis];
+            if (!(ext > 0.f)) continue;
+            const float scale = kBins / ext;
+            Box bb[kBins];
+            uint32_t bc[kBins];
+            for (int b = 0; b < kBins; b++) {
+                bb[b].reset();
+                bc[b] = 0;
+            }
+            for (uint32_t i = begin; i < end; i++) {
+                const size_t p = c.idx[i];
+                int b = (int)((c.cen[3 * p + axis] - cb.lo[axis]) * scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                bb[b].grow(c.bmin + 3 * p, c.bmax + 3 * p);
+                bc[b]++;
+            }
+            float right_area[kBins];
+            uint32_t right_cnt[kBins];
+            Box acc;
+            acc.reset();
+            uint32_t n = 0;
+            for (int b = kBins - 1; b > 0; b--) {
+                if (bc[b]) acc.grow(bb[b]);
+                n += bc[b];
+                right_area[b] = acc.valid() ? acc.half_area() : 0.f;
+                right_cnt[b] = n;
+            }
+            acc.reset();
+            n = 0;
+            for (int b = 0; b < kBins - 1; b++) {
+                if (bc[b]) acc.grow(bb[b]);
+                n += bc[b];
+                if (n == 0 || right_cnt[b + 1] == 0) continue;
+                const float cost = acc.half_area() * (float)n + right_area[b + 1] * (float)right_cnt[b + 1];
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best_axis = axis;
+                    best_bin = b;
+                }
+            }
+        }
+    }
+    // SAH termination: leaf cost = N * area, split cost = traversal * area + children
+    const float area = box.half_area();
+    if ((int)count <= c.max_leaf) {
+        const float leaf_cost = (float)count * area;
+        if (best_axis < 0 || best_cost + c.trav_cost * area >= leaf_cost) return make_leaf();
+    }
+
+    uint32_t mid;
+    if (best_axis >= 0) {
+        const float lo = cb.lo[best_axis], scale = kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+        const int axis = best_axis, bin = best_bin;
+        uint32_t *m = std::partition(c.idx + begin, c.idx + end, [&](uint32_t p) {
+            int b = (int)((c.cen[3 * (size_t)p + axis] - lo) * scale);
+            b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+            return b <= bin;
+        });
+        mid = (uint32_t)(m - c.idx);
+    } else {
+        // all centroids coincide, or the depth budget forces a balanced split: median along the widest axis
+        int axis = 0;
+        for (int k = 1; k < 3; k++)
+            if (cb.hi[k] - cb.lo[k] > cb.hi[axis] - cb.lo[axis]) axis = k;
+        mid = begin + count / 2;
+        std::nth_element(c.idx + begin, c.idx + mid, c.idx + end, [&](uint32_t a, uint32_t b) {
+            const float ca = c.cen[3 * (size_t)a + axis], cb2 = c.cen[3 * (size_t)b + axis];
+            return ca < cb2 || (ca == cb2 && a < b);
+        });
+    }
+    if (mid == begin || mid == end) mid = begin + count / 2;
+
+    Box lb, rb;
+    lb.reset();
+    rb.reset();
+    for (uint32_t i = begin; i < mid; i++) lb.grow(c.bmin + 3 * (size_t)c.idx[i], c.bmax + 3 * (size_t)c.idx[i]);
+    for (uint32_t i = mid; i < end; i++) rb.grow(c.bmin + 3 * (size_t)c.idx[i], c.bmax + 3 * (size_t)c.idx[i]);
+
+    const uint32_t child = c.next_node.fetch_add(2);
+    nd.prim_count = 0;
+    nd.first = child;
+    if (count > 4096) {
+#pragma omp task shared(c) firstprivate(child, begin, mid, lb, depth)
+        build_range(c, child, begin, mid, lb, depth + 1);
+#pragma omp task shared(c) firstprivate(child, mid, end, rb, depth)
+        build_range(c, child + 1, mid, end, rb, depth + 1);
+    } else {
+        build_range(c, child, begin, mid, lb, depth + 1);
+        build_range(c, child + 1, mid, end, rb, depth + 1);
+    }
+}
+
+}  // namespace
+
+// Build a bvh::Bvh<float>-form hierarchy over the triangles.  Deterministic: the tree depends only
+// on the input, and the final node order is a depth-first relayout of it.
+void build_bvh(const std::vector<Triangle> &tris, HostBvh &out, int max_leaf, float trav_cost) {
+    const size_t n = tris.size();
+    out.nodes.clear();
+    out.prim_indices.clear();
+    if (n == 0) return;
+    std::vector<float> bmin(3 * n), bmax(3 * n), cen(3 * n);
+    Box global;
+    global.reset();
+#pragma omp parallel
+    {
+        Box local;
+        local.reset();
+#pragma omp for nowait
+        for (int64_t i = 0; i < (int64_t)n; i++) {
+            const Triangle &t = tris[i];
+            // Triangle::bounding_box / center over p0, p1() = p0 - e1, p2() = p0 + e2
+            // (source/objects/Primitives.h:104-118): the vertices the intersection test actually sees.
+            for (int k = 0; k < 3; k++) {
+                const float a = t.p0[k], b = t.p0[k] - t.e1[k], cc = t.p0[k] + t.e2[k];
+                bmin[3 * i + k] = std::min(a, std::min(b, cc));
+                bmax[3 * i + k] = std::max(a, std::max(b, cc));
+                cen[3 * i + k] = (a + b + cc) * (1.0f / 3.0f);
+            }
+            local.grow(&bmin[3 * i], &bmax[3 * i]);
+        }
+#pragma omp critical
+        global.grow(local);
+    }
+    std::vector<uint32_t> idx(n);
+    for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)i;
+    std::vector<vt_node> tmp(2 * n + 1);
+    BuildCtx c{bmin.data(), bmax.data(), cen.data(), idx.data(), tmp.data(), {1}, max_leaf, trav_cost};
+#pragma omp parallel
+#pragma omp single
+    build_range(c, 0, 0, (uint32_t)n, global, 0);
+
+    // depth-first relayout: node ids handed out by the task scheduler are not reproducible, this order is
+    const uint32_t total = c.next_node.load();
+    out.nodes.resize(total);
+    out.prim_indices.resize(n);
+    out.nodes[0] = tmp[0];
+    uint32_t next = 1;
+    std::vector<std::pair<uint32_t, uint32_t>> stack;  // (old index, new index) of inner nodes to expand
+    if (tmp[0].prim_count == 0) stack.push_back({0u, 0u});
+    while (!stack.empty()) {
+        auto [oi, ni] = stack.back();
+        stack.pop_back();
+        const uint32_t oc = tmp[oi].first, nc = next;
+        next += 2;
+        out.nodes[ni].first = nc;
+        out.nodes[nc] = tmp[oc];
+        out.nodes[nc + 1] = tmp[oc + 1];
+        if (tmp[oc + 1].prim_count == 0) stack.push_back({oc + 1, nc + 1});
+        if (tmp[oc].prim_count == 0) stack.push_back({oc, nc});  // left subtree is laid out first
+    }
+    for (size_t i = 0; i < n; i++) out.prim_indices[i] = idx[i];
+}
+
+// ------------------------------------------------------------------------------------ flatten
+// bvh::Bvh<float> form -> VtPair array + leaf-order triangle permutation.
+// Pair order: breadth-first for the first `bfs_pairs` pairs (the part the traversal kernel stages
+// in shared memory), depth-first (left subtree first) below that.  Left/right inside a pair and
+// the primitive order inside a leaf are preserved, so traversal order is unchanged.
+bool flatten_bvh(const HostBvh &bvh, uint64_t n_tris, uint32_t bfs_pairs, FlatBvh &out, std::string &err) {
+    out.pairs.clear();
+    out.leaf_order.clear();
+    out.root_leaf_count = 0;
+    out.max_depth = 0;
+    const size_t node_count = bvh.nodes.size();
+    if (node_count == 0 || n_tris == 0) return true;
+    const vt_node &root = bvh.nodes[0];
+    out.leaf_order.reserve(n_tris);
+    auto emit_leaf = [&](const vt_node &nd, uint32_t &first_out) -> bool {
+        if ((uint64_t)nd.first + nd.prim_count > n_tris) {
+            err = "BVH leaf addresses primitives past the end of prim_indices";
+            return false;
+        }
+        first_out = (uint32_t)out.leaf_order.size();
+        for (uint32_t k = 0; k < nd.prim_count; k++) {
+            const uint64_t p = bvh.prim_indices[nd.first + k];
+            if (p >= n_tris) {
+                err = "BVH primitive index out of range";
+                return false;
+            }
+            out.leaf_order.push_back((uint32_t)p);
+        }
+        return true;
+    };
+    if (root.prim_count != 0) {  // the root is a leaf (single_ray_traverser.hpp:72-73)
+        uint32_t f;
+        if (!emit_leaf(root, f)) return false;
+        out.root_leaf_count = root.prim_count;
+        return true;
+    }
+    if ((node_count & 1) == 0) {
+        err = "BVH node count must be odd (root + sibling pairs)";
+        return false;
+    }
+    const size_t n_pairs = (node_count - 1) / 2;
+    out.pairs.resize(n_pairs);
+    struct Item {
+        uint32_t old_first;  // node index of the left child of the pair
+        uint32_t new_pair;
+        uint32_t depth;
+    };
+    // Phase 1: assign new pair ids — BFS for the top, then DFS.  new_id[old pair] = new pair.
+    std::vector<uint32_t> new_id(n_pairs, 0xFFFFFFFFu);
+    std::vector<Item> order;  // pairs in new order
+    order.reserve(n_pairs);
+    auto old_pair = [](uint32_t first) { return (first - 1) / 2; };
+    auto check_child = [&](uint32_t first) -> bool {
+        if (first == 0 || (first & 1) == 0 || (size_t)first + 1 >= node_count) {
+            err = "BVH child index invalid (children must be an adjacent pair at an odd index)";
+            return false;
+        }
+        if (new_id[old_pair(first)] != 0xFFFFFFFFu) {
+            err = "BVH is not a tree (a node pair is referenced twice)";
+            return false;
+        }
+        return true;
+    };
+    std::vector<Item> frontier;
+    if (!check_child(root.first)) return false;
+    frontier.push_back({root.first, 0, 1});
+    new_id[old_pair(root.first)] = 0;
+    size_t head = 0;
+    uint32_t next = 1;
+    // BFS
+    while (head < frontier.size() && order.size() < bfs_pairs) {
+        Item it = frontier[head++];
+        order.push_back(it);
+        for (int s = 0; s < 2; s++) {
+            const vt_node &ch = bvh.nodes[it.old_first + s];
+            if (ch.prim_count == 0) {
+                if (!check_child(ch.first)) return false;
+                new_id[old_pair(ch.first)] = 0xFFFFFFFEu;  // reserved, id assigned when visited
+                frontier.push_back({ch.first, 0, it.depth + 1});
+            }
+        }
+    }
+    // ids for BFS part are their positions
+    for (size_t i = 0; i < order.size(); i++) {
+        order[i].new_pair = (uint32_t)i;
+        new_id[old_pair(order[i].old_first)] = (uint32_t)i;
+    }
+    next = (uint32_t)order.size();
+    // DFS below each remaining frontier entry, in frontier order
+    std::vector<Item> stack;
+    for (size_t f = head; f < frontier.size(); f++) {
+        stack.push_back(frontier[f]);
+        while (!stack.empty()) {
+            Item it = stack.back();
+            stack.pop_back();
+            it.new_pair = next++;
+            new_id[old_pair(it.old_first)] = it.new_pair;
+            order.push_back(it);
+            const vt_node &l = bvh.nodes[it.old_first], &r = bvh.nodes[it.old_first + 1];
+            if (r.prim_count == 0) {
+                if (!check_child(r.first)) return false;
+                new_id[old_pair(r.first)] = 0xFFFFFFFEu;
+                stack.push_back({r.first, 0, it.depth + 1});
+            }
+            if (l.prim_count == 0) {
+                if (!check_child(l.first)) return false;
+                new_id[old_pair(l.first)] = 0xFFFFFFFEu;
+                stack.push_back({l.first, 0, it.depth + 1});
+            }
+        }
+    }
+    if (order.size() != n_pairs) {
+        err = "BVH has unreachable nodes";
+        return false;
+    }
+    // Phase 2: emit pairs and leaf runs in the new order
+    for (const Item &it : order) {
+        VtPair &p = out.pairs[it.new_pair];
+        out.max_depth = std::max(out.max_depth, it.depth);
+        for (int s = 0; s < 2; s++) {
+            const vt_node &ch = bvh.nodes[it.old_first + s];
+            VtChild &o = s ? p.r : p.l;
+            std::memcpy(o.bounds, ch.bounds, sizeof(o.bounds));
+            o.count = ch.prim_count;
+            if (ch.prim_count == 0) {
+                o.first = new_id[old_pair(ch.first)];
+            } else if (!emit_leaf(ch, o.first))
+                return false;
+        }
+    }
+    if (out.leaf_order.size() != n_tris) {
+        err = "BVH leaves do not cover every primitive exactly once";
+        return false;
+    }
+    if (out.max_depth > VT_STACK_SIZE) {
+        err = "BVH deeper than the 64-entry traversal stack (single_ray_traverser.hpp:14)";
+        return false;
+    }
+    return true;
+}
+
+}  // namespace vt

@@ -1,0 +1,100 @@
+// vt_device.h — HBM-resident layouts shared by the host flattening code and the kernels.
+//
+// Everything a ray touches lives in four flat arrays:
+//
+//   pairs   64 B / sibling pair   the two children of an inner node, i.e. the two adjacent
+//                                 32-byte bvh::Bvh<float>::Node records the reference reads per
+//                                 traversal step (libs/bvh/include/bvh/bvh.hpp:25-31,
+//                                 single_ray_traverser.hpp:85-87), 64-byte aligned so one step is
+//                                 four 128-bit loads from one or two 32-byte sectors of ONE line.
+//   tris    48 B / triangle       p0, e1, e2 + packed {material, alphatest, cull} + original index,
+//                                 stored in LEAF ORDER (the permutation primitive_indices encodes,
+//                                 primitive_intersectors.hpp:17-20) so a leaf is one contiguous run.
+//   tri_uv  24 B / triangle       leaf-order UVs, read only by the alpha test (Primitives.h:198).
+//   attrs  176 B / triangle       ORIGINAL order; everything the TraceResult stage interpolates.
+#pragma once
+#include <stdint.h>
+
+#define VT_STACK_SIZE 64          // libs/bvh/include/bvh/single_ray_traverser.hpp:14
+#define VT_TRI_FLAG_CULL 1u       // oneSided && !(mat.flags & nocull)   (Primitives.h:174)
+#define VT_TRI_FLAG_ALPHATEST 2u  // mat.flags & alphatest               (Primitives.h:195)
+#define VT_LEAF_BIT 0x80000000u
+
+// One child inside a pair: bounds in bvh order {minx,maxx,miny,maxy,minz,maxz}; count != 0 marks a
+// leaf.  `first` = pair index of the child's own children (inner) or first slot in `tris` (leaf).
+struct VtChild {
+    float bounds[6];
+    uint32_t count;
+    uint32_t first;
+};
+struct alignas(64) VtPair {
+    VtChild l, r;
+};
+static_assert(sizeof(VtPair) == 64, "pair layout");
+
+struct alignas(16) VtTriRec {
+    float p0[3];
+    float e1[3];
+    float e2[3];
+    uint32_t matflags;  // (material << 2) | VT_TRI_FLAG_*
+    uint32_t orig;      // index into the caller's triangle array
+    uint32_t pad;
+};
+static_assert(sizeof(VtTriRec) == 48, "triangle layout");
+
+// Per ORIGINAL triangle: inputs of TraceResult::TraceResult (source/objects/TraceResult.cpp:45-86).
+struct alignas(16) VtTriAttr {
+    float p0[3], e1[3], e2[3];  // v0 = p0, v1 = p0 - e1, v2 = p0 + e2
+    float nNorm[3];             // geometricNormal
+    float normals[3][3];
+    float tangents[3][3];
+    float uvs[3][2];
+    float alphas[3];
+    float lod;
+    uint32_t material;
+    uint32_t ent_idx;
+};
+static_assert(sizeof(VtTriAttr) == 176, "attr layout");
+
+// Texture header; texels of all textures live in one byte buffer, each chain in VTF order
+// (smallest mip first).  mip_offset[m] = byte offset of mip m inside the chain, precomputed once —
+// the loop the reference runs per sample (libs/VTFParser/VTFParser.cpp:219-229, "TODO: Cache these").
+struct VtDevTexture {
+    uint32_t width, height, mips, flags;
+    uint64_t base;  // byte offset of the chain inside the texel buffer
+    uint32_t mip_offset[16];
+    uint32_t pad[2];
+};
+
+struct VtDevMaterial {
+    uint32_t flags, surf_flags;
+    float alphatest_reference, tex_scale;
+    float colour[4];
+    float base_tex_mat[8], base_tex_mat2[8], normal_map_mat[8], normal_map_mat2[8], blend_tex_mat[8], detail_mat[8];
+    float detail_scale, detail_blend_factor;
+    int32_t base_texture, base_texture2, normal_map, normal_map2, mrao, mrao2, blend_texture, detail;
+    uint32_t detail_blend_mode, masked_blending, water, pad;
+};
+
+struct VtDevEntity {
+    uint32_t id;
+    float colour[4];
+};
+
+// Kernel argument block (passed by value).
+struct VtSceneView {
+    const VtPair *pairs;
+    const VtTriRec *tris;
+    const float *tri_uv;  // 6 floats per leaf-order triangle
+    const VtTriAttr *attrs;
+    const VtDevMaterial *mats;
+    const VtDevEntity *ents;
+    const VtDevTexture *texs;
+    const uint8_t *texels;
+    uint32_t n_pairs;
+    uint32_t n_tris;
+    uint32_t root_leaf_count;  // != 0: the root itself is a leaf over tris[0, count)  (single_ray_traverser.hpp:72-73)
+    uint32_t n_smem_pairs;     // leading pairs staged in shared memory by the traversal kernel
+    uint32_t has_alphatest;    // any triangle carries VT_TRI_FLAG_ALPHATEST
+    uint32_t fallback_tex;     // index of the 1x1 white stand-in for a null baseTexture
+};

@@ -1,0 +1,132 @@
+// vt_host.h — host-side C++ objects: the mirror of the reference's AccelStruct / Triangle /
+// TraceResult for the accel:Traverse path.  Same names, argument meaning and error behaviour as
+// source/objects/AccelStruct.h:61-86, Primitives.h:43-217 and TraceResult.h:13-111, minus the Lua
+// and game-engine ingestion (which needs a running game) — replaced by the headless Populate().
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vistrace_b200.h"
+#include "vt_device.h"
+
+namespace vt {
+
+// TriangleBackfaceCull<float> (source/objects/Primitives.h:43-73) without the skinning scratch data.
+struct Triangle {
+    float p0[3], e1[3], e2[3], n[3], nNorm[3];
+    bool oneSided = false;
+    uint32_t material = 0;
+    uint16_t entIdx = 0;
+    float normals[3][3];
+    float tangents[3][3];
+    float uvs[3][2];
+    float alphas[3];
+    float lod = 0.f;
+
+    Triangle() = default;
+    // Triangle(p0, p1, p2, material, uvs, oneSided) — Primitives.h:75-89
+    Triangle(const float p0_[3], const float p1[3], const float p2[3], uint32_t material_, const float uvs_[3][2],
+             bool oneSided_ = false);
+    void ComputeNormalAndLoD();  // Primitives.h:91-102
+};
+
+using Entity = vt_entity;      // source/objects/AccelStruct.h:33-40 (id, colour)
+using Material = vt_material;  // source/objects/Material.h:74-125 (subset on the path)
+
+struct HostBvh {  // bvh::Bvh<float>: nodes, primitive_indices, node_count (bvh.hpp:96-99)
+    std::vector<vt_node> nodes;
+    std::vector<uint64_t> prim_indices;
+};
+
+struct FlatBvh {
+    std::vector<VtPair> pairs;
+    std::vector<uint32_t> leaf_order;  // leaf-order slot -> original triangle index
+    uint32_t root_leaf_count = 0;
+    uint32_t max_depth = 0;
+};
+
+void build_bvh(const std::vector<Triangle> &tris, HostBvh &out, int max_leaf, float trav_cost);
+bool flatten_bvh(const HostBvh &bvh, uint64_t n_tris, uint32_t bfs_pairs, FlatBvh &out, std::string &err);
+
+struct DeviceScene;  // HBM-resident copy, vt_accel.cu
+
+// Eager TraceResult for one hit (source/objects/TraceResult.h:54-111): the batched path fills
+// vt_attr records; this wrapper gives the single-ray Traverse the reference's getter surface.
+class TraceResult {
+    vt_attr a;
+
+public:
+    explicit TraceResult(const vt_attr &attr) : a(attr), distance(attr.distance), entIdx(attr.ent_id), submatIdx(attr.submat_idx) {
+        hitSky = (attr.flags & VT_ATTR_HIT_SKY) != 0;
+        frontFacing = (attr.flags & VT_ATTR_FRONT_FACING) != 0;
+    }
+    float distance;
+    uint32_t entIdx;
+    uint32_t submatIdx;
+    bool hitSky = false;
+    bool frontFacing = false;
+    const float *GetPos() const { return a.pos; }
+    const float *GetNormal() const { return a.normal; }
+    const float *GetTangent() const { return a.tangent; }
+    const float *GetBinormal() const { return a.binormal; }
+    const float *GetGeometricNormal() const { return a.geometric_normal; }
+    const float *GetAlbedo() const { return a.albedo; }
+    const float *GetBarycentric() const { return a.uvw; }
+    const float *GetTexUV() const { return a.tex_uv; }
+    float GetAlpha() const { return a.alpha; }
+    float GetMetalness() const { return a.metalness; }
+    float GetRoughness() const { return a.roughness; }
+    float GetBaseMIPLevel() const { return a.base_mip; }
+    bool HitWater() const { return (a.flags & VT_ATTR_HIT_WATER) != 0; }
+    const vt_attr &Raw() const { return a; }
+};
+
+class AccelStruct {
+    int mDevice;
+    bool mAccelBuilt = false;
+    HostBvh mAccel;
+    std::vector<Triangle> mTriangles;
+    std::vector<Entity> mEntities;
+    std::vector<Material> mMaterials;
+    DeviceScene *mpDevice = nullptr;
+    uint64_t mInvalidRays = 0;
+    uint64_t mLaunches = 0;
+
+    void Ingest(const vt_scene &scene);
+    void Upload(const vt_scene &scene);
+
+public:
+    explicit AccelStruct(int device);
+    ~AccelStruct();
+    AccelStruct(const AccelStruct &) = delete;
+    AccelStruct &operator=(const AccelStruct &) = delete;
+
+    // Headless PopulateAccel (source/objects/AccelStruct.cpp:533-776): containers, build, upload.
+    void Populate(const vt_scene &scene);
+    // Same, with a hierarchy built by the caller (e.g. the reference's PLOC + LeafCollapser).
+    void PopulateWithBvh(const vt_scene &scene, const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices);
+
+    // Batched Traverse (the entry the north star adds behind the same object).
+    void TraverseBatch(const vt_ray *rays, uint64_t n, vt_hit *hits, vt_attr *attrs, const float *cones, uint32_t flags,
+                       void *stream);
+    void TraceResultBatch(const vt_ray *rays, const vt_hit *hits, uint64_t n, vt_attr *attrs, const float *cones,
+                          uint32_t flags, void *stream);
+
+    // Single-ray Traverse with the reference's argument rules and messages
+    // (source/objects/AccelStruct.cpp:778-838).  Returns nullptr on a miss; the caller owns the result.
+    TraceResult *Traverse(const float origin[3], const float direction[3], float tMin = 0.f,
+                          float tMax = 3.402823466e+38f, float coneWidth = -1.f, float coneAngle = -1.f);
+
+    const Material &GetMaterial(size_t i) const { return mMaterials[i]; }  // AccelStruct.cpp:840-843
+    const std::vector<Triangle> &Triangles() const { return mTriangles; }
+    const HostBvh &Bvh() const { return mAccel; }
+    bool Built() const { return mAccelBuilt; }
+    uint64_t InvalidRays() const { return mInvalidRays; }
+    uint64_t Launches() const { return mLaunches; }
+    uint64_t DeviceBytes() const;
+    int Device() const { return mDevice; }
+};
+
+}  // namespace vt

@@ -1,0 +1,30 @@
+// vt_kernels.h — launch interface between the host objects and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vistrace_b200.h"
+#include "vt_device.h"
+
+#ifndef VT_TRAVERSE_BLOCK
+#define VT_TRAVERSE_BLOCK 128
+#endif
+#ifndef VT_TRAVERSE_MIN_BLOCKS
+#define VT_TRAVERSE_MIN_BLOCKS 8
+#endif
+
+struct VtLaunchConfig {
+    int persistent = 1;         // 1: machine-sized grid pulling rays from a counter; 0: one ray per thread
+    int grid = 0;               // CTAs for the persistent launch (SMs x resident CTAs)
+    int refill_threshold = 20;  // refill a warp when <= this many of its lanes are still traversing
+};
+
+// K1 — closest hit (or any hit) for n rays.  counters[0] = ray queue head (must be 0 on entry),
+// counters[1] += rays rejected by the argument rules.
+cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit *hits, uint64_t n, bool any_hit,
+                               unsigned long long *counters, const VtLaunchConfig &cfg, cudaStream_t stream);
+cudaError_t vt_traverse_occupancy(int *blocks_per_sm, size_t smem_bytes);
+
+// K2 — eager TraceResult for n (ray, hit) records; cones = n x {coneWidth, coneAngle} or nullptr.
+cudaError_t vt_launch_trace_result(const VtSceneView &S, const vt_ray *rays, const vt_hit *hits, const float *cones,
+                                   vt_attr *attrs, uint64_t n, cudaStream_t stream);

@@ -1,0 +1,275 @@
+// vt_traverse.cu — K1: closest-hit / any-hit BVH traversal for sm_100a.
+//
+// Replaces, per ray, bvh::SingleRayTraverser::intersect
+// (libs/bvh/include/bvh/single_ray_traverser.hpp:65-126) + FastNodeIntersector
+// (node_intersectors.hpp:15-47,82-103) + ClosestPrimitiveIntersector
+// (primitive_intersectors.hpp:48-53) + TriangleBackfaceCull::intersect incl. the alpha test
+// (source/objects/Primitives.h:168-215).
+//
+// Execution model: persistent warps.  The grid is sized to the machine (SMs x resident CTAs),
+// every warp pulls rays from a global counter and REFILLS idle lanes whenever too few of its 32
+// lanes are still traversing (warp-level compaction by replacement: finished lanes never ride
+// along for the longest ray of their batch).  Each lane runs the reference's loop verbatim —
+// both children of a pair are slab-tested BEFORE any leaf shrinks tmax, left leaf then right
+// leaf, near child first with ties going left, far child pushed — so the visit order, the
+// tmax-shrink order and therefore exact-tie winners are those of the reference.
+//
+// Memory: one traversal step = one 64-byte VtPair = four LDG.128 from a single 128-byte line;
+// the first n_smem_pairs pairs (the top of the tree in breadth-first order) are staged in shared
+// memory per CTA; a leaf is a contiguous run of 48-byte VtTriRec (three LDG.128 each).  The
+// 64-entry traversal stack lives in local memory (lane-interleaved, L1-resident).
+#include "vt_kernels.h"
+#include "vt_math.cuh"
+
+namespace {
+
+struct RayState {
+    V3 o, d;
+    float tmin, tmax;
+    V3 inv, so;      // safe_inverse(d), -o * inv    (node_intersectors.hpp:89-94)
+    uint32_t oct;    // bit i = signbit(d[i])        (node_intersectors.hpp:20-26)
+    float t, u, v;   // best hit
+    uint32_t prim;   // original triangle index or VT_MISS
+};
+
+VT_DEV float safe_inverse(float d) {
+    // libs/bvh/include/bvh/vector.hpp:69-74
+    return 1.0f / (fabsf(d) < FLT_EPSILON ? copysignf(FLT_EPSILON, d) : d);
+}
+
+// TriangleBackfaceCull::intersect — source/objects/Primitives.h:168-215.  Updates the ray's best
+// hit and tmax when the candidate is accepted (`t <= tmax`: a later equal-t candidate replaces).
+template <bool ALPHA>
+VT_DEV bool intersect_triangle(const VtSceneView &S, uint32_t slot, RayState &r) {
+    const float4 *tp = reinterpret_cast<const float4 *>(S.tris + slot);
+    const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+    const V3 p0 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
+    const uint32_t matflags = __float_as_uint(q2.y);
+    const V3 n = bvh_cross(e1, e2);  // ComputeNormalAndLoD, Primitives.h:93 (LeftHandedNormal)
+    const float nDotDir = bvh_dot(n, r.d);
+    if ((matflags & VT_TRI_FLAG_CULL) && nDotDir > 0.f) return false;  // :173-174
+    const V3 c = p0 - r.o;
+    const V3 rr = bvh_cross(r.d, c);
+    const float inv_det = 1.0f / nDotDir;
+    const float u = bvh_dot(rr, e2) * inv_det;
+    const float v = bvh_dot(rr, e1) * inv_det;
+    const float w = 1.0f - u - v;
+    if (u >= 0.f && v >= 0.f && w >= 0.f) {  // NaN-rejecting compares, tolerance 0 (:184-187)
+        const float t = bvh_dot(n, c) * inv_det;
+        if (t >= r.tmin && t <= r.tmax) {
+            if (ALPHA && (matflags & VT_TRI_FLAG_ALPHATEST)) {  // :195-208
+                const VtDevMaterial &m = S.mats[matflags >> 2];
+                const float *uv = S.tri_uv + (size_t)slot * 6;
+                const float w2 = 1.f - u - v;
+                V2 texUV{(w2 * __ldg(uv + 0) + u * __ldg(uv + 2)) + v * __ldg(uv + 4),
+                         (w2 * __ldg(uv + 1) + u * __ldg(uv + 3)) + v * __ldg(uv + 5)};
+                texUV = transform_texcoord(texUV, m.base_tex_mat, m.tex_scale);
+                const uint32_t ti = m.base_texture >= 0 ? (uint32_t)m.base_texture : S.fallback_tex;
+                const float alpha = sample_alpha_mip0(S.texs[ti], S.texels, texUV.x, texUV.y);
+                if (alpha < m.alphatest_reference) return false;
+            }
+            r.t = t;
+            r.u = u;
+            r.v = v;
+            r.prim = __float_as_uint(q2.z);
+            r.tmax = t;  // single_ray_traverser.hpp:59
+            return true;
+        }
+    }
+    return false;
+}
+
+// NodeIntersector::intersect for both children of one pair.  robust_max/min chains
+// (utilities.hpp:61-71) are evaluated with fmaxf/fminf in the same nesting order: identical
+// values whenever the innermost operand (tmin / tmax) is not NaN, which the argument rules
+// guarantee; they differ at most in the sign of a zero, which no comparison observes.
+VT_DEV void slab_pair(const float4 &a, const float4 &b, const float4 &c, const float4 &d, const RayState &r, float &le,
+                      float &lx, float &re, float &rx) {
+    const bool ox = r.oct & 1u, oy = r.oct & 2u, oz = r.oct & 4u;
+    // left child: a = {minx,maxx,miny,maxy}, b = {minz,maxz,count,first}
+    float e0 = fmaf(ox ? a.y : a.x, r.inv.x, r.so.x);
+    float e1 = fmaf(oy ? a.w : a.z, r.inv.y, r.so.y);
+    float e2 = fmaf(oz ? b.y : b.x, r.inv.z, r.so.z);
+    float x0 = fmaf(ox ? a.x : a.y, r.inv.x, r.so.x);
+    float x1 = fmaf(oy ? a.z : a.w, r.inv.y, r.so.y);
+    float x2 = fmaf(oz ? b.x : b.y, r.inv.z, r.so.z);
+    le = fmaxf(e0, fmaxf(e1, fmaxf(e2, r.tmin)));
+    lx = fminf(x0, fminf(x1, fminf(x2, r.tmax)));
+    e0 = fmaf(ox ? c.y : c.x, r.inv.x, r.so.x);
+    e1 = fmaf(oy ? c.w : c.z, r.inv.y, r.so.y);
+    e2 = fmaf(oz ? d.y : d.x, r.inv.z, r.so.z);
+    x0 = fmaf(ox ? c.x : c.y, r.inv.x, r.so.x);
+    x1 = fmaf(oy ? c.z : c.w, r.inv.y, r.so.y);
+    x2 = fmaf(oz ? d.x : d.y, r.inv.z, r.so.z);
+    re = fmaxf(e0, fmaxf(e1, fmaxf(e2, r.tmin)));
+    rx = fminf(x0, fminf(x1, fminf(x2, r.tmax)));
+}
+
+VT_DEV void init_ray(const vt_ray &in, RayState &r) {
+    r.o = mk3(in.ox, in.oy, in.oz);
+    r.d = mk3(in.dx, in.dy, in.dz);
+    r.tmin = in.tmin;
+    r.tmax = in.tmax;
+    r.inv = mk3(safe_inverse(r.d.x), safe_inverse(r.d.y), safe_inverse(r.d.z));
+    r.so = mk3(-r.o.x * r.inv.x, -r.o.y * r.inv.y, -r.o.z * r.inv.z);
+    r.oct = (signbit(r.d.x) ? 1u : 0u) | (signbit(r.d.y) ? 2u : 0u) | (signbit(r.d.z) ? 4u : 0u);
+    r.t = r.u = r.v = 0.f;
+    r.prim = VT_MISS;
+}
+
+template <bool ANY_HIT, bool ALPHA>
+__global__ void __launch_bounds__(VT_TRAVERSE_BLOCK, VT_TRAVERSE_MIN_BLOCKS)
+k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restrict__ hits, unsigned long long n,
+           unsigned long long *__restrict__ counters, int persistent, int refill_threshold) {
+    extern __shared__ float4 s_pairs[];
+    for (uint32_t i = threadIdx.x; i < S.n_smem_pairs * 4u; i += blockDim.x)
+        s_pairs[i] = __ldg(reinterpret_cast<const float4 *>(S.pairs) + i);
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t stack[VT_STACK_SIZE];
+    int sp = 0;
+    uint32_t cur = 0;
+    bool active = false;
+    bool exhausted = false;  // warp-uniform: the ray queue has run dry
+    unsigned long long ray_idx = 0;
+    RayState r;
+    unsigned long long n_invalid = 0;
+
+    for (;;) {
+        // ---- refill idle lanes from the global queue
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && !exhausted) {
+            const int n_idle = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if (persistent) {
+                if ((int)lane == leader) base = atomicAdd(&counters[0], (unsigned long long)n_idle);
+                base = __shfl_sync(0xffffffffu, base, leader);
+            } else {
+                base = ((unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u));
+                exhausted = true;  // one batch per warp
+            }
+            if (base + n_idle >= n) exhausted = true;
+            if (!active) {
+                ray_idx = base + __popc(idle & lt_mask);
+                if (ray_idx < n) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(rays + ray_idx);
+                    const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
+                    vt_ray in{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                    init_ray(in, r);
+                    // argument rules of AccelStruct::Traverse (source/objects/AccelStruct.cpp:805-806):
+                    // tMin < 0 or tMax <= tMin is an error there; here the ray becomes a counted miss.
+                    if (!(in.tmin >= 0.f) || !(in.tmax > in.tmin)) {
+                        n_invalid++;
+                        reinterpret_cast<float4 *>(hits)[ray_idx] = make_float4(0.f, 0.f, 0.f, __uint_as_float(VT_MISS));
+                    } else if (S.root_leaf_count) {
+                        // root is a leaf: intersect it directly, no slab test (single_ray_traverser.hpp:72-73)
+                        for (uint32_t i = 0; i < S.root_leaf_count; i++)
+                            if (intersect_triangle<ALPHA>(S, i, r) && ANY_HIT) break;
+                        reinterpret_cast<float4 *>(hits)[ray_idx] = make_float4(r.t, r.u, r.v, __uint_as_float(r.prim));
+                    } else if (S.n_pairs == 0) {
+                        reinterpret_cast<float4 *>(hits)[ray_idx] = make_float4(0.f, 0.f, 0.f, __uint_as_float(VT_MISS));
+                    } else {
+                        active = true;
+                        cur = 0;  // pair 0 = children of the root (nodes[nodes[0].first], +1)
+                        sp = 0;
+                    }
+                }
+            }
+        }
+        const unsigned act0 = __ballot_sync(0xffffffffu, active);
+        if (act0 == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        const int keep_going = exhausted ? 0 : refill_threshold;
+
+        // ---- traverse until too few lanes remain busy
+        for (;;) {
+            if (active) {
+                float4 a, b, c, d;
+                if (cur < S.n_smem_pairs) {
+                    const float4 *p = s_pairs + cur * 4u;
+                    a = p[0], b = p[1], c = p[2], d = p[3];
+                } else {
+                    const float4 *p = reinterpret_cast<const float4 *>(S.pairs + cur);
+                    a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+                }
+                float le, lx, re, rx;
+                slab_pair(a, b, c, d, r, le, lx, re, rx);  // both boxes against the tmax of step entry (:86-87)
+                const uint32_t lcount = __float_as_uint(b.z), lfirst = __float_as_uint(b.w);
+                const uint32_t rcount = __float_as_uint(d.z), rfirst = __float_as_uint(d.w);
+                bool go_l = le <= lx, go_r = re <= rx;
+                bool done = false;
+                if (go_l && lcount) {  // left leaf first (:89-97)
+                    for (uint32_t i = lfirst; i < lfirst + lcount; i++)
+                        if (intersect_triangle<ALPHA>(S, i, r) && ANY_HIT) { done = true; break; }
+                    go_l = false;
+                }
+                if (!done && go_r && rcount) {  // then right leaf (:99-107)
+                    for (uint32_t i = rfirst; i < rfirst + rcount; i++)
+                        if (intersect_triangle<ALPHA>(S, i, r) && ANY_HIT) { done = true; break; }
+                    go_r = false;
+                }
+                if (!done) {
+                    if (go_l) {
+                        if (go_r) {
+                            uint32_t near_ = lfirst, far_ = rfirst;
+                            if (le > re) { near_ = rfirst; far_ = lfirst; }  // :111-112, ties keep left first
+                            if (sp < VT_STACK_SIZE) stack[sp] = far_;       // reference: unchecked (UB past 64)
+                            sp++;
+                            cur = near_;
+                        } else
+                            cur = lfirst;
+                    } else if (go_r) {
+                        cur = rfirst;
+                    } else if (sp == 0) {
+                        done = true;
+                    } else {
+                        sp--;
+                        cur = stack[sp < VT_STACK_SIZE ? sp : VT_STACK_SIZE - 1];
+                    }
+                }
+                if (done) {
+                    reinterpret_cast<float4 *>(hits)[ray_idx] = make_float4(r.t, r.u, r.v, __uint_as_float(r.prim));
+                    active = false;
+                }
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, active);
+            if (__popc(act) <= keep_going) break;
+        }
+    }
+    if (n_invalid) atomicAdd(&counters[1], n_invalid);
+}
+
+}  // namespace
+
+cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit *hits, uint64_t n, bool any_hit,
+                               unsigned long long *counters, const VtLaunchConfig &cfg, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const size_t smem = (size_t)S.n_smem_pairs * sizeof(VtPair);
+    int grid;
+    if (cfg.persistent) {
+        grid = cfg.grid;
+    } else {
+        grid = (int)((n + VT_TRAVERSE_BLOCK - 1) / VT_TRAVERSE_BLOCK);
+    }
+    const bool alpha = S.has_alphatest != 0;
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, VT_TRAVERSE_BLOCK, smem, stream>>>(S, rays, hits, (unsigned long long)n, counters,
+                                                          cfg.persistent ? 1 : 0, cfg.refill_threshold);
+        return cudaGetLastError();
+    };
+    if (any_hit) return alpha ? launch(k_traverse<true, true>) : launch(k_traverse<true, false>);
+    return alpha ? launch(k_traverse<false, true>) : launch(k_traverse<false, false>);
+}
+
+cudaError_t vt_traverse_occupancy(int *blocks_per_sm, size_t smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k_traverse<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_traverse<false, true>, VT_TRAVERSE_BLOCK, smem_bytes);
+}
