@@ -220,6 +220,27 @@ int vt_accel_traverse_cones(vt_accel *accel, const vt_ray *rays, const float *co
 int vt_accel_trace_result(vt_accel *accel, const vt_ray *rays, const vt_hit *hits,
                           uint64_t n, vt_attr *attrs, uint32_t flags, void *stream);
 
+/* Secondary-ray generation on the device, the step GLua scripts do per hit between two
+ * accel:Traverse calls: for every non-sky hit in attrs[0, n) spawn `spp` cosine-weighted bounce
+ * rays about the shading normal — hemisphere_cos (source/libraries/BSDF.cpp:69-77) in the hit's
+ * tangent/binormal/normal frame, origin = vistrace.CalcRayOrigin(pos, geometric normal)
+ * (source/VisTrace.cpp:1478-1519) — into out_rays[i*spp + s].  Slots that spawn nothing (miss,
+ * sky) are MASKED (tmax < 0): vt_accel_traverse reports them as misses and does not count them.
+ * Random numbers are a counter-based hash of (slot, dimension, seed).  live_out (nullable, host
+ * pointer) receives the number of rays spawned and makes the call synchronous. */
+int vt_accel_bounce_rays(vt_accel *accel, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed,
+                         vt_ray *out_rays, uint64_t *live_out, uint32_t flags, void *stream);
+
+/* The "primary + diffuse" wave of the headline benchmark in one call: traverse rays[0, n), build
+ * the TraceResult of every hit, spawn spp bounce rays per hit (as vt_accel_bounce_rays) and
+ * traverse those.  Out: hits[n], bounce_hits[n*spp]; optional attrs[n], bounce_rays[n*spp]
+ * (required scratch with VT_TRAVERSE_DEVICE_PTRS).  Host pointers are processed in tiles over
+ * several CUDA streams so the host<->device copies overlap the kernels; the call returns when
+ * all results are on the host.  Device pointers: enqueued on `stream`, live_out must be NULL. */
+int vt_accel_trace_diffuse_wave(vt_accel *accel, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed,
+                                vt_hit *hits, vt_attr *attrs, vt_ray *bounce_rays, vt_hit *bounce_hits,
+                                uint64_t *live_out, uint32_t flags, void *stream);
+
 /* Rays rejected by the argument rules during the last synchronous traverse. */
 uint64_t vt_accel_invalid_rays(const vt_accel *accel);
 

@@ -53,7 +53,8 @@ def _check_against(vt, oracle_mod, scene, rays, kind, bvh_from, any_hit=False):
     for f in ATTR_INT_FIELDS:
         assert err[f] == 0, (f, err[f])
     miss = hits["prim"] == abi.VT_MISS
-    assert not attrs[miss].view(np.uint32).reshape(miss.sum(), -1)[:, :-1].any()  # miss records are zero
+    if miss.any():  # miss records are zero apart from prim = VT_MISS
+        assert not attrs[miss].view(np.uint32).reshape(int(miss.sum()), 32)[:, :-1].any()
     return accel, cpu, hits, attrs, want
 
 

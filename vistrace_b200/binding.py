@@ -27,6 +27,8 @@ SYMBOLS = {
     "vt_accel_traverse": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_traverse_cones": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_result": (_i32, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
+    "vt_accel_bounce_rays": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _u32, _vp]),
+    "vt_accel_trace_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "vt_accel_invalid_rays": (_u64, [_vp]),
     "vt_accel_launch_count": (_u64, [_vp]),
     "vt_accel_stats": (_i32, [_vp, _vp, _vp, _vp]),
@@ -188,6 +190,42 @@ class Accel:
             "vt_accel_trace_result",
         )
         return attrs
+
+    def bounce_rays(self, attrs, spp, seed=0):
+        """Host-buffer K3: (rays[n*spp] with masked slots, number spawned)."""
+        attrs = np.ascontiguousarray(attrs, abi.ATTR)
+        out = np.zeros(len(attrs) * spp, abi.RAY)
+        live = C.c_uint64(0)
+        _check(self.L.vt_accel_bounce_rays(self.h, attrs.ctypes.data, len(attrs), spp, seed, out.ctypes.data, C.addressof(live), 0, None),
+               "vt_accel_bounce_rays")
+        return out, live.value
+
+    def bounce_rays_device(self, d_attrs, n, spp, seed, d_out, stream=None):
+        _check(self.L.vt_accel_bounce_rays(self.h, _ptr(d_attrs), n, spp, seed, _ptr(d_out), None, abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)),
+               "vt_accel_bounce_rays")
+
+    def trace_diffuse_wave(self, rays, spp, seed=0, want_attrs=False, want_bounce_rays=False, out=None):
+        """Host-buffer wave.  `out` may carry preallocated (e.g. pinned) numpy views: hits, bounce_hits, attrs, bounce_rays."""
+        rays = rays if isinstance(rays, np.ndarray) and rays.dtype == abi.RAY and rays.flags.c_contiguous else np.ascontiguousarray(rays, abi.RAY)
+        n = len(rays)
+        out = dict(out or {})
+        out.setdefault("hits", np.zeros(n, abi.HIT))
+        out.setdefault("bounce_hits", np.zeros(n * spp, abi.HIT))
+        if want_attrs:
+            out.setdefault("attrs", np.zeros(n, abi.ATTR))
+        if want_bounce_rays:
+            out.setdefault("bounce_rays", np.zeros(n * spp, abi.RAY))
+        live = C.c_uint64(0)
+        _check(self.L.vt_accel_trace_diffuse_wave(self.h, rays.ctypes.data, n, spp, seed, out["hits"].ctypes.data, _ptr(out.get("attrs")),
+                                                  _ptr(out.get("bounce_rays")), out["bounce_hits"].ctypes.data, C.addressof(live), 0, None),
+               "vt_accel_trace_diffuse_wave")
+        out["live_bounce"] = live.value
+        return out
+
+    def trace_diffuse_wave_device(self, d_rays, n, spp, seed, d_hits, d_attrs, d_bounce_rays, d_bounce_hits, stream=None):
+        _check(self.L.vt_accel_trace_diffuse_wave(self.h, _ptr(d_rays), n, spp, seed, _ptr(d_hits), _ptr(d_attrs), _ptr(d_bounce_rays),
+                                                  _ptr(d_bounce_hits), None, abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)),
+               "vt_accel_trace_diffuse_wave")
 
     @property
     def invalid_rays(self):

@@ -110,6 +110,14 @@ struct DeviceScene {
     DevBuf<vt_hit> s_hits;
     DevBuf<vt_attr> s_attrs;
     DevBuf<float> s_cones;
+    // per-stream tile staging of the host-pointer diffuse wave
+    struct WaveLane {
+        cudaStream_t stream = nullptr;
+        DevBuf<vt_ray> rays, brays;
+        DevBuf<vt_hit> hits, bhits;
+        DevBuf<vt_attr> attrs;
+    } lanes[3];
+    DevBuf<unsigned long long> live;
     VtSceneView view{};
     VtLaunchConfig cfg;
     std::atomic<uint32_t> next_slot{0};
@@ -130,6 +138,15 @@ struct DeviceScene {
         s_hits.release();
         s_attrs.release();
         s_cones.release();
+        live.release();
+        for (auto &l : lanes) {
+            l.rays.release();
+            l.brays.release();
+            l.hits.release();
+            l.bhits.release();
+            l.attrs.release();
+            if (l.stream) cudaStreamDestroy(l.stream);
+        }
         if (own_stream) cudaStreamDestroy(own_stream);
     }
     uint64_t scene_bytes() const {
@@ -209,11 +226,12 @@ void AccelStruct::Upload(const vt_scene &scene) {
     VT_CUDA(cudaSetDevice(mDevice));
     DeviceScene &D = *mpDevice;
     D.cfg.persistent = env_int("VT_PERSISTENT", 1);
-    D.cfg.refill_threshold = env_int("VT_REFILL", 20);
+    D.cfg.refill_threshold = env_int("VT_REFILL", D.cfg.refill_threshold);
+    D.cfg.tri_threshold = env_int("VT_TRI_ROUND", D.cfg.tri_threshold);
     const size_t n = mTriangles.size();
 
     // how many leading pairs fit the shared-memory budget of one CTA
-    uint32_t smem_pairs = (uint32_t)env_int("VT_SMEM_PAIRS", 384);
+    uint32_t smem_pairs = (uint32_t)env_int("VT_SMEM_PAIRS", 0);
     FlatBvh flat;
     std::string err;
     if (!flatten_bvh(mAccel, n, smem_pairs, flat, err)) throw std::runtime_error(err);
@@ -234,6 +252,7 @@ void AccelStruct::Upload(const vt_scene &scene) {
             r.p0[k] = t.p0[k];
             r.e1[k] = t.e1[k];
             r.e2[k] = t.e2[k];
+            r.n[k] = t.n[k];
         }
         uint32_t fl = 0;
         if (t.oneSided && (m.flags & VT_MATFLAG_NOCULL) == 0) fl |= VT_TRI_FLAG_CULL;  // Primitives.h:174
@@ -241,7 +260,7 @@ void AccelStruct::Upload(const vt_scene &scene) {
         any_alpha |= (fl & VT_TRI_FLAG_ALPHATEST);
         r.matflags = (t.material << 2) | fl;
         r.orig = orig;
-        r.pad = 0;
+        r.pad[0] = r.pad[1] = 0;
         std::memcpy(&uv[6 * s], t.uvs, 6 * sizeof(float));
     }
 #pragma omp parallel for
@@ -457,6 +476,105 @@ void AccelStruct::TraceResultBatch(const vt_ray *rays, const vt_hit *hits, uint6
     VT_CUDA(cudaStreamSynchronize(stream));
 }
 
+void AccelStruct::BounceRays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays,
+                             uint64_t *live_out, uint32_t flags, void *stream_) {
+    if (n == 0 || spp == 0) {
+        if (live_out) *live_out = 0;
+        return;
+    }
+    if (!attrs || !out_rays) throw std::runtime_error("bounce_rays: attrs and out_rays must not be null");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    const bool dev_ptrs = (flags & VT_TRAVERSE_DEVICE_PTRS) != 0;
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : (dev_ptrs ? (cudaStream_t) nullptr : D.own_stream);
+    D.live.ensure(1);
+    if (live_out) VT_CUDA(cudaMemsetAsync(D.live.p, 0, sizeof(unsigned long long), stream));
+    const vt_attr *d_attrs = attrs;
+    vt_ray *d_out = out_rays;
+    if (!dev_ptrs) {
+        D.s_attrs.ensure(n);
+        D.s_rays.ensure(n * spp);
+        VT_CUDA(cudaMemcpyAsync(D.s_attrs.p, attrs, n * sizeof(vt_attr), cudaMemcpyHostToDevice, stream));
+        d_attrs = D.s_attrs.p;
+        d_out = D.s_rays.p;
+    }
+    VT_CUDA(vt_launch_bounce_rays(d_attrs, n, spp, seed, 0, d_out, live_out ? D.live.p : nullptr, stream));
+    mLaunches++;
+    if (!dev_ptrs) VT_CUDA(cudaMemcpyAsync(out_rays, d_out, n * spp * sizeof(vt_ray), cudaMemcpyDeviceToHost, stream));
+    if (live_out) {
+        unsigned long long v = 0;
+        VT_CUDA(cudaMemcpyAsync(&v, D.live.p, sizeof(v), cudaMemcpyDeviceToHost, stream));
+        VT_CUDA(cudaStreamSynchronize(stream));
+        *live_out = v;
+    } else if (!dev_ptrs) {
+        VT_CUDA(cudaStreamSynchronize(stream));
+    }
+}
+
+void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, vt_hit *hits, vt_attr *attrs,
+                                   vt_ray *bounce_rays, vt_hit *bounce_hits, uint64_t *live_out, uint32_t flags,
+                                   void *stream_) {
+    check_built(mAccelBuilt);
+    if (live_out) *live_out = 0;
+    if (n == 0) return;
+    if (!rays || !hits || !bounce_hits) throw std::runtime_error("diffuse_wave: rays, hits and bounce_hits must not be null");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    const bool dev_ptrs = (flags & VT_TRAVERSE_DEVICE_PTRS) != 0;
+    D.live.ensure(1);
+    auto next_counter = [&]() { return D.counters.p + 2 * (D.next_slot.fetch_add(1) % kCounterSlots); };
+    if (dev_ptrs) {
+        // everything resident: five launches on the caller's stream, no synchronisation
+        if (!attrs || !bounce_rays) throw std::runtime_error("diffuse_wave (device pointers): attrs and bounce_rays scratch required");
+        cudaStream_t stream = (cudaStream_t)stream_;
+        unsigned long long *c0 = next_counter(), *c1 = next_counter();
+        VT_CUDA(cudaMemsetAsync(c0, 0, 16, stream));
+        VT_CUDA(cudaMemsetAsync(c1, 0, 16, stream));
+        VT_CUDA(vt_launch_traverse(D.view, rays, hits, n, false, c0, D.cfg, stream));
+        VT_CUDA(vt_launch_trace_result(D.view, rays, hits, nullptr, attrs, n, stream));
+        VT_CUDA(vt_launch_bounce_rays(attrs, n, spp, seed, 0, bounce_rays, nullptr, stream));
+        VT_CUDA(vt_launch_traverse(D.view, bounce_rays, bounce_hits, n * spp, false, c1, D.cfg, stream));
+        mLaunches += 4;
+        return;
+    }
+    // host pointers: tiles round-robin over three streams — H2D(rays) | K1 K2 K3 K1 | D2H(results) overlap across tiles
+    const uint64_t tile = (uint64_t)std::max(1, env_int("VT_WAVE_TILE", 1 << 18));
+    VT_CUDA(cudaMemsetAsync(D.live.p, 0, sizeof(unsigned long long), D.own_stream));
+    VT_CUDA(cudaStreamSynchronize(D.own_stream));
+    for (auto &l : D.lanes)
+        if (!l.stream) VT_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    int li = 0;
+    for (uint64_t base = 0; base < n; base += tile, li = (li + 1) % 3) {
+        const uint64_t m = std::min(tile, n - base);
+        DeviceScene::WaveLane &l = D.lanes[li];
+        l.rays.ensure(tile);
+        l.hits.ensure(tile);
+        l.attrs.ensure(tile);
+        l.brays.ensure(tile * spp);
+        l.bhits.ensure(tile * spp);
+        unsigned long long *c0 = next_counter(), *c1 = next_counter();
+        VT_CUDA(cudaMemsetAsync(c0, 0, 16, l.stream));
+        VT_CUDA(cudaMemsetAsync(c1, 0, 16, l.stream));
+        VT_CUDA(cudaMemcpyAsync(l.rays.p, rays + base, m * sizeof(vt_ray), cudaMemcpyHostToDevice, l.stream));
+        VT_CUDA(vt_launch_traverse(D.view, l.rays.p, l.hits.p, m, false, c0, D.cfg, l.stream));
+        VT_CUDA(vt_launch_trace_result(D.view, l.rays.p, l.hits.p, nullptr, l.attrs.p, m, l.stream));
+        VT_CUDA(vt_launch_bounce_rays(l.attrs.p, m, spp, seed, base * spp, l.brays.p, D.live.p, l.stream));
+        VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, m * spp, false, c1, D.cfg, l.stream));
+        mLaunches += 4;
+        VT_CUDA(cudaMemcpyAsync(hits + base, l.hits.p, m * sizeof(vt_hit), cudaMemcpyDeviceToHost, l.stream));
+        VT_CUDA(cudaMemcpyAsync(bounce_hits + base * spp, l.bhits.p, m * spp * sizeof(vt_hit), cudaMemcpyDeviceToHost, l.stream));
+        if (attrs) VT_CUDA(cudaMemcpyAsync(attrs + base, l.attrs.p, m * sizeof(vt_attr), cudaMemcpyDeviceToHost, l.stream));
+        if (bounce_rays)
+            VT_CUDA(cudaMemcpyAsync(bounce_rays + base * spp, l.brays.p, m * spp * sizeof(vt_ray), cudaMemcpyDeviceToHost, l.stream));
+    }
+    for (auto &l : D.lanes) VT_CUDA(cudaStreamSynchronize(l.stream));
+    if (live_out) {
+        unsigned long long v = 0;
+        VT_CUDA(cudaMemcpy(&v, D.live.p, sizeof(v), cudaMemcpyDeviceToHost));
+        *live_out = v;
+    }
+}
+
 TraceResult *AccelStruct::Traverse(const float origin[3], const float direction[3], float tMin, float tMax, float coneWidth,
                                    float coneAngle) {
     check_built(mAccelBuilt);
@@ -567,6 +685,25 @@ int vt_accel_trace_result(vt_accel *a, const vt_ray *rays, const vt_hit *hits, u
     VT_TRY
     if (!a) throw std::runtime_error("null argument");
     a->impl.TraceResultBatch(rays, hits, n, attrs, nullptr, flags, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_bounce_rays(vt_accel *a, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays,
+                         uint64_t *live_out, uint32_t flags, void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.BounceRays(attrs, n, spp, seed, out_rays, live_out, flags, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_trace_diffuse_wave(vt_accel *a, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, vt_hit *hits,
+                                vt_attr *attrs, vt_ray *bounce_rays, vt_hit *bounce_hits, uint64_t *live_out, uint32_t flags,
+                                void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.TraceDiffuseWave(rays, n, spp, seed, hits, attrs, bounce_rays, bounce_hits, live_out, flags, stream);
     return 0;
     VT_CATCH(1)
 }

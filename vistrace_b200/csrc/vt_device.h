@@ -7,7 +7,7 @@
 //                                 traversal step (libs/bvh/include/bvh/bvh.hpp:25-31,
 //                                 single_ray_traverser.hpp:85-87), 64-byte aligned so one step is
 //                                 four 128-bit loads from one or two 32-byte sectors of ONE line.
-//   tris    48 B / triangle       p0, e1, e2 + packed {material, alphatest, cull} + original index,
+//   tris    64 B / triangle       p0, e1, e2, n + packed {material, alphatest, cull} + original index,
 //                                 stored in LEAF ORDER (the permutation primitive_indices encodes,
 //                                 primitive_intersectors.hpp:17-20) so a leaf is one contiguous run.
 //   tri_uv  24 B / triangle       leaf-order UVs, read only by the alpha test (Primitives.h:198).
@@ -32,15 +32,16 @@ struct alignas(64) VtPair {
 };
 static_assert(sizeof(VtPair) == 64, "pair layout");
 
-struct alignas(16) VtTriRec {
+struct alignas(64) VtTriRec {
     float p0[3];
     float e1[3];
     float e2[3];
+    float n[3];         // cross(e1, e2) exactly as the Triangle constructor rounded it (Primitives.h:93)
     uint32_t matflags;  // (material << 2) | VT_TRI_FLAG_*
     uint32_t orig;      // index into the caller's triangle array
-    uint32_t pad;
+    uint32_t pad[2];
 };
-static_assert(sizeof(VtTriRec) == 48, "triangle layout");
+static_assert(sizeof(VtTriRec) == 64, "triangle layout");
 
 // Per ORIGINAL triangle: inputs of TraceResult::TraceResult (source/objects/TraceResult.cpp:45-86).
 struct alignas(16) VtTriAttr {

@@ -114,6 +114,16 @@ public:
     void TraceResultBatch(const vt_ray *rays, const vt_hit *hits, uint64_t n, vt_attr *attrs, const float *cones,
                           uint32_t flags, void *stream);
 
+    // Secondary-ray generation from TraceResult records (device or host pointers as per flags):
+    // spp cosine-weighted bounce rays per non-sky hit, slot i*spp+s; *live_out = rays spawned.
+    void BounceRays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays, uint64_t *live_out,
+                    uint32_t flags, void *stream);
+    // "primary + diffuse" wave in one call: traverse the primary rays, build their TraceResults, spawn
+    // spp bounce rays per hit on the device and traverse those.  Host pointers are processed in tiles
+    // on several streams so the PCIe copies overlap the kernels.
+    void TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, vt_hit *hits, vt_attr *attrs,
+                          vt_ray *bounce_rays, vt_hit *bounce_hits, uint64_t *live_out, uint32_t flags, void *stream);
+
     // Single-ray Traverse with the reference's argument rules and messages
     // (source/objects/AccelStruct.cpp:778-838).  Returns nullptr on a miss; the caller owns the result.
     TraceResult *Traverse(const float origin[3], const float direction[3], float tMin = 0.f,

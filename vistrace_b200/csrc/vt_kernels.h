@@ -16,7 +16,8 @@
 struct VtLaunchConfig {
     int persistent = 1;         // 1: machine-sized grid pulling rays from a counter; 0: one ray per thread
     int grid = 0;               // CTAs for the persistent launch (SMs x resident CTAs)
-    int refill_threshold = 20;  // refill a warp when <= this many of its lanes are still traversing
+    int refill_threshold = 24;  // refill a warp when <= this many of its lanes still own a ray
+    int tri_threshold = 8;      // run a triangle round when >= this many lanes have a candidate queued
 };
 
 // K1 — closest hit (or any hit) for n rays.  counters[0] = ray queue head (must be 0 on entry),
@@ -28,3 +29,9 @@ cudaError_t vt_traverse_occupancy(int *blocks_per_sm, size_t smem_bytes);
 // K2 — eager TraceResult for n (ray, hit) records; cones = n x {coneWidth, coneAngle} or nullptr.
 cudaError_t vt_launch_trace_result(const VtSceneView &S, const vt_ray *rays, const vt_hit *hits, const float *cones,
                                    vt_attr *attrs, uint64_t n, cudaStream_t stream);
+
+// K3 — secondary-ray generation: spp cosine-weighted bounce rays per (non-sky) hit into slot i*spp+s,
+// masked slots (tmax < 0) elsewhere; *live += spawned rays.  And a pinhole primary-ray generator.
+cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, uint64_t slot_offset,
+                                  vt_ray *out, unsigned long long *live, cudaStream_t stream);
+cudaError_t vt_launch_pinhole_rays(const float *cam12, uint32_t width, uint32_t height, vt_ray *out, cudaStream_t stream);

@@ -1,0 +1,120 @@
+// vt_raygen.cu — K3: secondary-ray generation on the device (the step either side of the hot path).
+//
+// The reference has no batched ray generator: GLua scripts call vistrace.CalcRayOrigin
+// (source/VisTrace.cpp:1478-1519) and the BSDF sampler (source/libraries/BSDF.cpp:69-77,
+// hemisphere_cos) per hit and feed the result back into accel:Traverse.  For a wavefront that
+// round trip would leave the GPU idle, so the "primary + diffuse" workload spawns its bounce rays
+// here, straight from the vt_attr records K2 wrote:
+//
+//   direction = T * (sinTheta cos phi) + B' * (sinTheta sin phi) + N' * z,
+//               z = sqrt(r1), sinTheta = sqrt(1 - r1), phi = 2 pi r2          (hemisphere_cos)
+//   origin    = CalcRayOrigin(pos, geometric normal on the viewer's side)
+//
+// N', B' are the shading normal / binormal flipped to the viewer's side for back-face hits.
+// r1, r2 come from a counter-based hash of (slot, dimension, seed) — the reference's Sampler is a
+// sequential mt19937 (source/objects/Sampler.cpp:5-20) and cannot be evaluated in parallel.
+// Slot j = i * spp + s belongs to primary ray i (the hash counter is slot_offset + j, so a batch
+// traced in tiles draws the same numbers as the batch traced whole); hits that spawn nothing (miss, sky) leave a
+// MASKED slot (tmax < 0) that K1 reports as a miss without counting it as an invalid ray.
+#include "vt_kernels.h"
+#include "vt_math.cuh"
+
+namespace {
+
+VT_DEV uint32_t mix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x7feb352du;
+    h ^= h >> 15;
+    h *= 0x846ca68bu;
+    h ^= h >> 16;
+    return h;
+}
+VT_DEV float uniform01(unsigned long long slot, uint32_t dim, unsigned long long seed) {
+    uint32_t h = mix32((uint32_t)slot ^ mix32((uint32_t)(slot >> 32) + 0x9e3779b9u * (dim + 1u)));
+    h = mix32(h ^ (uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + dim));
+    return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+// vistrace.CalcRayOrigin — source/VisTrace.cpp:1495-1517, one component
+VT_DEV float ray_origin_1(float pos, float nrm) {
+    const float origin = 1.f / 32.f, fScale = 1.f / 65536.f, iScale = 256.f;
+    const int iOff = (int)(nrm * iScale);
+    const float iPos = __int_as_float(__float_as_int(pos) + (pos < 0.f ? -iOff : iOff));
+    return fabsf(pos) < origin ? pos + nrm * fScale : iPos;
+}
+
+__global__ void __launch_bounds__(256)
+k_bounce_rays(const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t spp, unsigned long long seed,
+              unsigned long long slot_offset, vt_ray *__restrict__ out, unsigned long long *__restrict__ live) {
+    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long total = n * spp;
+    bool spawned = false;
+    if (j < total) {
+        const unsigned long long i = j / spp;
+        const float4 *a = reinterpret_cast<const float4 *>(attrs + i);
+        const float4 q7 = __ldg(a + 7);  // tex_uv, flags, prim
+        const uint32_t flags = __float_as_uint(q7.z), prim = __float_as_uint(q7.w);
+        float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 0.f, -1.f);  // masked slot
+        if (prim != VT_MISS && !(flags & VT_ATTR_HIT_SKY)) {
+            const float4 q0 = __ldg(a), q1 = __ldg(a + 1), q2 = __ldg(a + 2), q3 = __ldg(a + 3), q4 = __ldg(a + 4);
+            const float sgn = (flags & VT_ATTR_FRONT_FACING) ? 1.f : -1.f;
+            const V3 pos = mk3(q0.x, q0.y, q0.z);
+            const V3 N = mk3(q1.x, q1.y, q1.z) * sgn, T = mk3(q2.x, q2.y, q2.z), B = mk3(q3.x, q3.y, q3.z) * sgn;
+            const V3 gN = mk3(q4.x, q4.y, q4.z) * sgn;
+            const float r1 = uniform01(slot_offset + j, 0, seed), r2 = uniform01(slot_offset + j, 1, seed);
+            const float z = sqrtf(r1), sinTheta = sqrtf(1.f - r1), phi = 6.2831853071795864769f * r2;
+            float sp, cp;
+            sincosf(phi, &sp, &cp);
+            const V3 d = T * (sinTheta * cp) + B * (sinTheta * sp) + N * z;
+            if (isfinite(d.x) && isfinite(d.y) && isfinite(d.z) && (d.x != 0.f || d.y != 0.f || d.z != 0.f)) {
+                ro = make_float4(ray_origin_1(pos.x, gN.x), ray_origin_1(pos.y, gN.y), ray_origin_1(pos.z, gN.z), 0.f);
+                rd = make_float4(d.x, d.y, d.z, FLT_MAX);
+                spawned = true;
+            }
+        }
+        float4 *o = reinterpret_cast<float4 *>(out + j);
+        o[0] = ro;
+        o[1] = rd;
+    }
+    if (live) {
+        const unsigned m = __ballot_sync(0xffffffffu, spawned);
+        if ((threadIdx.x & 31u) == 0 && m) atomicAdd(live, (unsigned long long)__popc(m));
+    }
+}
+
+// Pinhole primary rays, pixel-centre sampling, row-major (index = width * j + i) — the loop of
+// libs/bvh/test/benchmark.cpp:129-150.  cam = {eye, image_u, image_v, dir} (already scaled).
+__global__ void __launch_bounds__(256)
+k_pinhole_rays(const float *__restrict__ cam, uint32_t width, uint32_t height, vt_ray *__restrict__ out) {
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned long long)width * height) return;
+    const uint32_t i = (uint32_t)(idx % width), j = (uint32_t)(idx / width);
+    const float u = 2.f * ((float)i + 0.5f) / (float)width - 1.f;
+    const float v = 2.f * ((float)j + 0.5f) / (float)height - 1.f;
+    const V3 eye = mk3(cam[0], cam[1], cam[2]), iu = mk3(cam[3], cam[4], cam[5]), iv = mk3(cam[6], cam[7], cam[8]),
+             dir = mk3(cam[9], cam[10], cam[11]);
+    V3 d = iu * u + iv * v + dir;
+    d = d * (1.0f / sqrtf(bvh_dot(d, d)));  // bvh::normalize, vector.hpp:149-153
+    float4 *o = reinterpret_cast<float4 *>(out + idx);
+    o[0] = make_float4(eye.x, eye.y, eye.z, 0.f);
+    o[1] = make_float4(d.x, d.y, d.z, FLT_MAX);
+}
+
+}  // namespace
+
+cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, uint64_t slot_offset,
+                                  vt_ray *out, unsigned long long *live, cudaStream_t stream) {
+    const unsigned long long total = (unsigned long long)n * spp;
+    if (total == 0) return cudaSuccess;
+    const unsigned block = 256;
+    k_bounce_rays<<<(unsigned)((total + block - 1) / block), block, 0, stream>>>(attrs, n, spp, seed, slot_offset, out, live);
+    return cudaGetLastError();
+}
+
+cudaError_t vt_launch_pinhole_rays(const float *cam12, uint32_t width, uint32_t height, vt_ray *out, cudaStream_t stream) {
+    const unsigned long long total = (unsigned long long)width * height;
+    if (total == 0) return cudaSuccess;
+    const unsigned block = 256;
+    k_pinhole_rays<<<(unsigned)((total + block - 1) / block), block, 0, stream>>>(cam12, width, height, out);
+    return cudaGetLastError();
+}

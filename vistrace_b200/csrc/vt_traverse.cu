@@ -8,15 +8,19 @@
 //
 // Execution model: persistent warps.  The grid is sized to the machine (SMs x resident CTAs),
 // every warp pulls rays from a global counter and REFILLS idle lanes whenever too few of its 32
-// lanes are still traversing (warp-level compaction by replacement: finished lanes never ride
-// along for the longest ray of their batch).  Each lane runs the reference's loop verbatim —
-// both children of a pair are slab-tested BEFORE any leaf shrinks tmax, left leaf then right
-// leaf, near child first with ties going left, far child pushed — so the visit order, the
-// tmax-shrink order and therefore exact-tie winners are those of the reference.
+// lanes are still busy (warp-level compaction by replacement: finished lanes never ride along
+// for the longest ray of their batch).  Each lane runs the reference's loop verbatim — both
+// children of a pair are slab-tested BEFORE any leaf shrinks tmax, left leaf then right leaf,
+// near child first with ties going left, far child pushed — so the visit order, the tmax-shrink
+// order and therefore exact-tie winners are those of the reference.  The warp schedules that
+// per-lane automaton in ROUNDS (all-node or all-triangle, see k_traverse) so the long
+// triangle test is never executed for one or two lanes at a time: the first version of this
+// kernel ran it inline and spent half of its issued instructions at ~1.5 live lanes
+// (profiles/r1_k_traverse_v1_bounce5m.md).
 //
 // Memory: one traversal step = one 64-byte VtPair = four LDG.128 from a single 128-byte line;
 // the first n_smem_pairs pairs (the top of the tree in breadth-first order) are staged in shared
-// memory per CTA; a leaf is a contiguous run of 48-byte VtTriRec (three LDG.128 each).  The
+// memory per CTA; a leaf is a contiguous run of 64-byte VtTriRec (four LDG.128 each).  The
 // 64-entry traversal stack lives in local memory (lane-interleaved, L1-resident).
 #include "vt_kernels.h"
 #include "vt_math.cuh"
@@ -27,8 +31,7 @@ struct RayState {
     V3 o, d;
     float tmin, tmax;
     V3 inv, so;      // safe_inverse(d), -o * inv    (node_intersectors.hpp:89-94)
-    uint32_t oct;    // bit i = signbit(d[i])        (node_intersectors.hpp:20-26)
-    float t, u, v;   // best hit
+    float u, v;      // best hit; its t is tmax (single_ray_traverser.hpp:59)
     uint32_t prim;   // original triangle index or VT_MISS
 };
 
@@ -42,10 +45,10 @@ VT_DEV float safe_inverse(float d) {
 template <bool ALPHA>
 VT_DEV bool intersect_triangle(const VtSceneView &S, uint32_t slot, RayState &r) {
     const float4 *tp = reinterpret_cast<const float4 *>(S.tris + slot);
-    const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+    const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2), q3 = __ldg(tp + 3);
     const V3 p0 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
-    const uint32_t matflags = __float_as_uint(q2.y);
-    const V3 n = bvh_cross(e1, e2);  // ComputeNormalAndLoD, Primitives.h:93 (LeftHandedNormal)
+    const V3 n = mk3(q2.y, q2.z, q2.w);  // cross(e1, e2) as stored by the Triangle ctor (Primitives.h:93)
+    const uint32_t matflags = __float_as_uint(q3.x);
     const float nDotDir = bvh_dot(n, r.d);
     if ((matflags & VT_TRI_FLAG_CULL) && nDotDir > 0.f) return false;  // :173-174
     const V3 c = p0 - r.o;
@@ -68,11 +71,10 @@ VT_DEV bool intersect_triangle(const VtSceneView &S, uint32_t slot, RayState &r)
                 const float alpha = sample_alpha_mip0(S.texs[ti], S.texels, texUV.x, texUV.y);
                 if (alpha < m.alphatest_reference) return false;
             }
-            r.t = t;
             r.u = u;
             r.v = v;
-            r.prim = __float_as_uint(q2.z);
-            r.tmax = t;  // single_ray_traverser.hpp:59
+            r.prim = __float_as_uint(q3.y);
+            r.tmax = t;  // single_ray_traverser.hpp:59; the best t IS the shrunk tmax
             return true;
         }
     }
@@ -85,7 +87,9 @@ VT_DEV bool intersect_triangle(const VtSceneView &S, uint32_t slot, RayState &r)
 // guarantee; they differ at most in the sign of a zero, which no comparison observes.
 VT_DEV void slab_pair(const float4 &a, const float4 &b, const float4 &c, const float4 &d, const RayState &r, float &le,
                       float &lx, float &re, float &rx) {
-    const bool ox = r.oct & 1u, oy = r.oct & 2u, oz = r.oct & 4u;
+    // octant[i] = signbit(d[i]) (node_intersectors.hpp:20-26) == signbit(inv[i]): safe_inverse keeps the sign
+    // of d, including -0.0 -> -1/eps, and is never zero.
+    const bool ox = signbit(r.inv.x), oy = signbit(r.inv.y), oz = signbit(r.inv.z);
     // left child: a = {minx,maxx,miny,maxy}, b = {minz,maxz,count,first}
     float e0 = fmaf(ox ? a.y : a.x, r.inv.x, r.so.x);
     float e1 = fmaf(oy ? a.w : a.z, r.inv.y, r.so.y);
@@ -112,35 +116,58 @@ VT_DEV void init_ray(const vt_ray &in, RayState &r) {
     r.tmax = in.tmax;
     r.inv = mk3(safe_inverse(r.d.x), safe_inverse(r.d.y), safe_inverse(r.d.z));
     r.so = mk3(-r.o.x * r.inv.x, -r.o.y * r.inv.y, -r.o.z * r.inv.z);
-    r.oct = (signbit(r.d.x) ? 1u : 0u) | (signbit(r.d.y) ? 2u : 0u) | (signbit(r.d.z) ? 4u : 0u);
-    r.t = r.u = r.v = 0.f;
+    r.u = r.v = 0.f;
     r.prim = VT_MISS;
 }
 
+// Result record: t = tmax of the best hit, or zeros + VT_MISS.
+VT_DEV void write_hit(vt_hit *hits, unsigned long long idx, const RayState &r) {
+    const bool hit = r.prim != VT_MISS;
+    reinterpret_cast<float4 *>(hits)[idx] = make_float4(hit ? r.tmax : 0.f, r.u, r.v, __uint_as_float(r.prim));
+}
+
+// Per-lane ray automaton.  A ray alternates between two kinds of work:
+//   * a NODE step: slab-test the two children of pair `cur` against the tmax of step entry, queue the
+//     leaf children that were hit (left first, then right) and decide the next pair right away —
+//     descend / push far / pop do not depend on what the leaves will return;
+//   * TRIANGLE tests: drain the queued leaf triangles one by one, in order, shrinking tmax.
+// A ray never takes its next node step before its queue is empty, so every ray sees exactly the
+// reference's sequence of box tests and triangle tests (single_ray_traverser.hpp:82-123).  What the
+// warp is free to choose is WHICH kind of work it executes next: it runs a triangle round when
+// enough lanes have a candidate queued (or nobody can walk), a node round otherwise.  Lanes that
+// cannot take part in the chosen round wait; this trades a little idling for never running the
+// ~100-instruction triangle test with one or two live lanes.
 template <bool ANY_HIT, bool ALPHA>
 __global__ void __launch_bounds__(VT_TRAVERSE_BLOCK, VT_TRAVERSE_MIN_BLOCKS)
 k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restrict__ hits, unsigned long long n,
-           unsigned long long *__restrict__ counters, int persistent, int refill_threshold) {
+           unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold) {
     extern __shared__ float4 s_pairs[];
     for (uint32_t i = threadIdx.x; i < S.n_smem_pairs * 4u; i += blockDim.x)
         s_pairs[i] = __ldg(reinterpret_cast<const float4 *>(S.pairs) + i);
-    __syncthreads();
+    if (S.n_smem_pairs) __syncthreads();
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t stack[VT_STACK_SIZE];
     int sp = 0;
     uint32_t cur = 0;
-    bool active = false;
+    bool alive = false;      // lane owns a ray whose result is not written yet
+    bool walking = false;    // that ray still has pairs to visit
+    uint32_t qa = 0, na = 0, qb = 0, nb = 0;  // queued leaf runs: tris[qa, qa+na) then tris[qb, qb+nb)
     bool exhausted = false;  // warp-uniform: the ray queue has run dry
     unsigned long long ray_idx = 0;
     RayState r;
     unsigned long long n_invalid = 0;
 
     for (;;) {
-        // ---- refill idle lanes from the global queue
-        const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle && !exhausted) {
+        // ---- retire finished rays, refill idle lanes from the global queue
+        if (alive && !walking && na == 0) {
+            write_hit(hits, ray_idx, r);
+            alive = false;
+        }
+        const unsigned idle = __ballot_sync(0xffffffffu, !alive);
+        if (idle == 0xffffffffu && exhausted) break;
+        if (idle && !exhausted && __popc(idle) >= 32 - refill_threshold) {
             const int n_idle = __popc(idle);
             const int leader = __ffs(idle) - 1;
             unsigned long long base = 0;
@@ -152,43 +179,55 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
                 exhausted = true;  // one batch per warp
             }
             if (base + n_idle >= n) exhausted = true;
-            if (!active) {
+            if (!alive) {
                 ray_idx = base + __popc(idle & lt_mask);
                 if (ray_idx < n) {
                     const float4 *rp = reinterpret_cast<const float4 *>(rays + ray_idx);
                     const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
                     vt_ray in{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                     init_ray(in, r);
+                    alive = true;
+                    walking = false;
+                    na = nb = 0;
+                    sp = 0;
                     // argument rules of AccelStruct::Traverse (source/objects/AccelStruct.cpp:805-806):
                     // tMin < 0 or tMax <= tMin is an error there; here the ray becomes a counted miss.
                     if (!(in.tmin >= 0.f) || !(in.tmax > in.tmin)) {
-                        n_invalid++;
-                        reinterpret_cast<float4 *>(hits)[ray_idx] = make_float4(0.f, 0.f, 0.f, __uint_as_float(VT_MISS));
+                        if (!(in.tmax < 0.f)) n_invalid++;  // tmax < 0 marks a masked slot of a ray wave: silent miss
                     } else if (S.root_leaf_count) {
-                        // root is a leaf: intersect it directly, no slab test (single_ray_traverser.hpp:72-73)
-                        for (uint32_t i = 0; i < S.root_leaf_count; i++)
-                            if (intersect_triangle<ALPHA>(S, i, r) && ANY_HIT) break;
-                        reinterpret_cast<float4 *>(hits)[ray_idx] = make_float4(r.t, r.u, r.v, __uint_as_float(r.prim));
-                    } else if (S.n_pairs == 0) {
-                        reinterpret_cast<float4 *>(hits)[ray_idx] = make_float4(0.f, 0.f, 0.f, __uint_as_float(VT_MISS));
-                    } else {
-                        active = true;
+                        // root is a leaf: its triangles are tested directly, no slab test (single_ray_traverser.hpp:72-73)
+                        qa = 0;
+                        na = S.root_leaf_count;
+                    } else if (S.n_pairs) {
+                        walking = true;
                         cur = 0;  // pair 0 = children of the root (nodes[nodes[0].first], +1)
-                        sp = 0;
                     }
                 }
             }
+            continue;  // retire degenerate rays / re-evaluate before doing work
         }
-        const unsigned act0 = __ballot_sync(0xffffffffu, active);
-        if (act0 == 0) {
-            if (exhausted) break;
-            continue;
-        }
-        const int keep_going = exhausted ? 0 : refill_threshold;
 
-        // ---- traverse until too few lanes remain busy
-        for (;;) {
-            if (active) {
+        // ---- choose the round
+        const unsigned want_tri = __ballot_sync(0xffffffffu, alive && na != 0);
+        const unsigned want_node = __ballot_sync(0xffffffffu, alive && na == 0 && walking);
+        if (want_tri && (want_node == 0 || __popc(want_tri) >= tri_threshold)) {
+            // ---- triangle round: one queued candidate per lane (intersect_leaf loop body, :53-61)
+            if (alive && na != 0) {
+                const bool hit = intersect_triangle<ALPHA>(S, qa, r);
+                qa++;
+                na--;
+                if (ANY_HIT && hit) {  // any_hit: first accepted candidate ends the ray (:57-58, :91-93)
+                    na = nb = 0;
+                    walking = false;
+                } else if (na == 0) {
+                    qa = qb;
+                    na = nb;
+                    nb = 0;
+                }
+            }
+        } else if (want_node) {
+            // ---- node round (:82-123)
+            if (alive && na == 0 && walking) {
                 float4 a, b, c, d;
                 if (cur < S.n_smem_pairs) {
                     const float4 *p = s_pairs + cur * 4u;
@@ -202,43 +241,39 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
                 const uint32_t lcount = __float_as_uint(b.z), lfirst = __float_as_uint(b.w);
                 const uint32_t rcount = __float_as_uint(d.z), rfirst = __float_as_uint(d.w);
                 bool go_l = le <= lx, go_r = re <= rx;
-                bool done = false;
-                if (go_l && lcount) {  // left leaf first (:89-97)
-                    for (uint32_t i = lfirst; i < lfirst + lcount; i++)
-                        if (intersect_triangle<ALPHA>(S, i, r) && ANY_HIT) { done = true; break; }
+                if (go_l && lcount) {  // left leaf is tested first (:89-97) ...
+                    qa = lfirst;
+                    na = lcount;
                     go_l = false;
                 }
-                if (!done && go_r && rcount) {  // then right leaf (:99-107)
-                    for (uint32_t i = rfirst; i < rfirst + rcount; i++)
-                        if (intersect_triangle<ALPHA>(S, i, r) && ANY_HIT) { done = true; break; }
+                if (go_r && rcount) {  // ... then the right leaf (:99-107)
+                    if (na) {
+                        qb = rfirst;
+                        nb = rcount;
+                    } else {
+                        qa = rfirst;
+                        na = rcount;
+                    }
                     go_r = false;
                 }
-                if (!done) {
-                    if (go_l) {
-                        if (go_r) {
-                            uint32_t near_ = lfirst, far_ = rfirst;
-                            if (le > re) { near_ = rfirst; far_ = lfirst; }  // :111-112, ties keep left first
-                            if (sp < VT_STACK_SIZE) stack[sp] = far_;       // reference: unchecked (UB past 64)
-                            sp++;
-                            cur = near_;
-                        } else
-                            cur = lfirst;
-                    } else if (go_r) {
-                        cur = rfirst;
-                    } else if (sp == 0) {
-                        done = true;
-                    } else {
-                        sp--;
-                        cur = stack[sp < VT_STACK_SIZE ? sp : VT_STACK_SIZE - 1];
-                    }
-                }
-                if (done) {
-                    reinterpret_cast<float4 *>(hits)[ray_idx] = make_float4(r.t, r.u, r.v, __uint_as_float(r.prim));
-                    active = false;
+                if (go_l) {
+                    if (go_r) {
+                        uint32_t near_ = lfirst, far_ = rfirst;
+                        if (le > re) { near_ = rfirst; far_ = lfirst; }  // :111-112, ties keep left first
+                        if (sp < VT_STACK_SIZE) stack[sp] = far_;       // reference: unchecked (UB past 64)
+                        sp++;
+                        cur = near_;
+                    } else
+                        cur = lfirst;
+                } else if (go_r) {
+                    cur = rfirst;
+                } else if (sp == 0) {
+                    walking = false;
+                } else {
+                    sp--;
+                    cur = stack[sp < VT_STACK_SIZE ? sp : VT_STACK_SIZE - 1];
                 }
             }
-            const unsigned act = __ballot_sync(0xffffffffu, active);
-            if (__popc(act) <= keep_going) break;
         }
     }
     if (n_invalid) atomicAdd(&counters[1], n_invalid);
@@ -261,7 +296,7 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         kernel<<<grid, VT_TRAVERSE_BLOCK, smem, stream>>>(S, rays, hits, (unsigned long long)n, counters,
-                                                          cfg.persistent ? 1 : 0, cfg.refill_threshold);
+                                                          cfg.persistent ? 1 : 0, cfg.refill_threshold, cfg.tri_threshold);
         return cudaGetLastError();
     };
     if (any_hit) return alpha ? launch(k_traverse<true, true>) : launch(k_traverse<true, false>);
