@@ -241,6 +241,14 @@ int vt_accel_trace_diffuse_wave(vt_accel *accel, const vt_ray *rays, uint64_t n,
                                 vt_hit *hits, vt_attr *attrs, vt_ray *bounce_rays, vt_hit *bounce_hits,
                                 uint64_t *live_out, uint32_t flags, void *stream);
 
+/* Fold one diffuse wave into an RGBFFF framebuffer — tightly packed 3 x f32 per pixel, the memory
+ * an IRenderTarget of format RGBFFF exposes through GetRawData(0) (include/vistrace/IRenderTarget.h:40):
+ *   fb[i] += weight * albedo_i * (bounce rays of pixel i that escape to the sky) / spp.
+ * DEVICE pointers only; enqueued on `stream`.  This per-GPU partial image is what the multi-GPU path
+ * sums with its single NCCL collective. */
+int vt_accel_accumulate_sky(vt_accel *accel, const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n,
+                            uint32_t spp, float weight, float *framebuffer_rgb, void *stream);
+
 /* Rays rejected by the argument rules during the last synchronous traverse. */
 uint64_t vt_accel_invalid_rays(const vt_accel *accel);
 

@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path():
-    return os.path.join(HERE, "libvistrace_b200.so")
+    # VT_LIB: alternative build of the same library (kernel tuning experiments); default = the in-tree build
+    return os.environ.get("VT_LIB") or os.path.join(HERE, "libvistrace_b200.so")
 
 
 _lib = None
@@ -29,6 +30,7 @@ SYMBOLS = {
     "vt_accel_trace_result": (_i32, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "vt_accel_bounce_rays": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
+    "vt_accel_accumulate_sky": (_i32, [_vp, _vp, _vp, _u64, _u32, C.c_float, _vp, _vp]),
     "vt_accel_invalid_rays": (_u64, [_vp]),
     "vt_accel_launch_count": (_u64, [_vp]),
     "vt_accel_stats": (_i32, [_vp, _vp, _vp, _vp]),
@@ -226,6 +228,10 @@ class Accel:
         _check(self.L.vt_accel_trace_diffuse_wave(self.h, _ptr(d_rays), n, spp, seed, _ptr(d_hits), _ptr(d_attrs), _ptr(d_bounce_rays),
                                                   _ptr(d_bounce_hits), None, abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)),
                "vt_accel_trace_diffuse_wave")
+
+    def accumulate_sky_device(self, d_attrs, d_bounce_hits, n, spp, weight, d_fb, stream=None):
+        _check(self.L.vt_accel_accumulate_sky(self.h, _ptr(d_attrs), _ptr(d_bounce_hits), n, spp, weight, _ptr(d_fb), _ptr(stream)),
+               "vt_accel_accumulate_sky")
 
     @property
     def invalid_rays(self):

@@ -575,6 +575,16 @@ void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp,
     }
 }
 
+void AccelStruct::AccumulateSky(const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n, uint32_t spp, float weight,
+                                float *fb, void *stream_) {
+    check_built(mAccelBuilt);
+    if (n == 0) return;
+    if (!attrs || !bounce_hits || !fb) throw std::runtime_error("accumulate_sky: null argument");
+    VT_CUDA(cudaSetDevice(mDevice));
+    VT_CUDA(vt_launch_accumulate_sky(mpDevice->view, attrs, bounce_hits, n, spp, weight, fb, (cudaStream_t)stream_));
+    mLaunches++;
+}
+
 TraceResult *AccelStruct::Traverse(const float origin[3], const float direction[3], float tMin, float tMax, float coneWidth,
                                    float coneAngle) {
     check_built(mAccelBuilt);
@@ -704,6 +714,15 @@ int vt_accel_trace_diffuse_wave(vt_accel *a, const vt_ray *rays, uint64_t n, uin
     VT_TRY
     if (!a) throw std::runtime_error("null argument");
     a->impl.TraceDiffuseWave(rays, n, spp, seed, hits, attrs, bounce_rays, bounce_hits, live_out, flags, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_accumulate_sky(vt_accel *a, const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n, uint32_t spp,
+                            float weight, float *framebuffer_rgb, void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.AccumulateSky(attrs, bounce_hits, n, spp, weight, framebuffer_rgb, stream);
     return 0;
     VT_CATCH(1)
 }

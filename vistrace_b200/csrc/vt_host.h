@@ -124,6 +124,10 @@ public:
     void TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, vt_hit *hits, vt_attr *attrs,
                           vt_ray *bounce_rays, vt_hit *bounce_hits, uint64_t *live_out, uint32_t flags, void *stream);
 
+    // Fold a diffuse wave into an RGBFFF framebuffer (device pointers only): see k_accumulate_sky.
+    void AccumulateSky(const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n, uint32_t spp, float weight, float *fb,
+                       void *stream);
+
     // Single-ray Traverse with the reference's argument rules and messages
     // (source/objects/AccelStruct.cpp:778-838).  Returns nullptr on a miss; the caller owns the result.
     TraceResult *Traverse(const float origin[3], const float direction[3], float tMin = 0.f,

@@ -100,7 +100,55 @@ k_pinhole_rays(const float *__restrict__ cam, uint32_t width, uint32_t height, v
     o[1] = make_float4(d.x, d.y, d.z, FLT_MAX);
 }
 
+// K4 — fold one diffuse wave into an RGBFFF framebuffer (tightly packed 3 x f32 per pixel, the layout
+// of IRenderTarget format RGBFFF: include/vistrace/IRenderTarget.h:40, source/objects/RenderTarget.cpp:61-97):
+//   fb[i] += weight * albedo_i * (number of the spp bounce rays of pixel i that escape to the sky) / spp
+// A bounce ray "escapes" when it misses everything or its closest hit is a sky brush
+// (TraceResult::hitSky, source/objects/TraceResult.cpp:83).  This is the per-rank partial image that the
+// multi-GPU path sums with ONE collective; it is harness-level shading, not part of accel:Traverse.
+__global__ void __launch_bounds__(256)
+k_accumulate_sky(const VtSceneView S, const vt_attr *__restrict__ attrs, const vt_hit *__restrict__ bounce_hits,
+                 unsigned long long n, uint32_t spp, float weight, float *__restrict__ fb) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *a = reinterpret_cast<const float4 *>(attrs + i);
+    const float4 q7 = __ldg(a + 7);
+    const uint32_t flags = __float_as_uint(q7.z), prim = __float_as_uint(q7.w);
+    float r = 0.f, g = 0.f, b = 0.f;
+    if (prim != VT_MISS) {
+        const float4 q5 = __ldg(a + 5);  // albedo, ent_id
+        if (flags & VT_ATTR_HIT_SKY) {
+            r = q5.x, g = q5.y, b = q5.z;  // looking straight at the sky
+        } else {
+            uint32_t escaped = 0;
+            for (uint32_t s = 0; s < spp; s++) {
+                const float4 h = __ldg(reinterpret_cast<const float4 *>(bounce_hits) + i * spp + s);
+                const uint32_t bp = __float_as_uint(h.w);
+                if (bp == VT_MISS || bp >= S.n_tris) {
+                    escaped++;
+                } else {
+                    const uint32_t m = S.attrs[bp].material;
+                    escaped += (S.mats[m].surf_flags & VT_SURF_SKY) ? 1u : 0u;
+                }
+            }
+            const float vis = (float)escaped / (float)spp;
+            r = q5.x * vis, g = q5.y * vis, b = q5.z * vis;
+        }
+    }
+    fb[3 * i + 0] += weight * r;
+    fb[3 * i + 1] += weight * g;
+    fb[3 * i + 2] += weight * b;
+}
+
 }  // namespace
+
+cudaError_t vt_launch_accumulate_sky(const VtSceneView &S, const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n,
+                                     uint32_t spp, float weight, float *fb, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned block = 256;
+    k_accumulate_sky<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(S, attrs, bounce_hits, n, spp, weight, fb);
+    return cudaGetLastError();
+}
 
 cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, uint64_t slot_offset,
                                   vt_ray *out, unsigned long long *live, cudaStream_t stream) {

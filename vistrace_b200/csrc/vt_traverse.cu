@@ -35,6 +35,16 @@ struct RayState {
     uint32_t prim;   // original triangle index or VT_MISS
 };
 
+// 256-bit read-only load (sm_100+: LDG.E.256): one 32-byte sector per lane per instruction.  A pair
+// or a triangle record (64 B, 64-byte aligned) is two of these instead of four LDG.128 — half the
+// per-lane requests through the L1 data stage, which is what limits this kernel once its
+// instruction count is down (profiles/r1_k_traverse_v3_bounce5m.md: l1tex throughput 84 %).
+VT_DEV void ldg256(const void *p, float4 &lo, float4 &hi) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+
 VT_DEV float safe_inverse(float d) {
     // libs/bvh/include/bvh/vector.hpp:69-74
     return 1.0f / (fabsf(d) < FLT_EPSILON ? copysignf(FLT_EPSILON, d) : d);
@@ -44,8 +54,9 @@ VT_DEV float safe_inverse(float d) {
 // hit and tmax when the candidate is accepted (`t <= tmax`: a later equal-t candidate replaces).
 template <bool ALPHA>
 VT_DEV bool intersect_triangle(const VtSceneView &S, uint32_t slot, RayState &r) {
-    const float4 *tp = reinterpret_cast<const float4 *>(S.tris + slot);
-    const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2), q3 = __ldg(tp + 3);
+    float4 q0, q1, q2, q3;
+    ldg256(S.tris + slot, q0, q1);
+    ldg256(reinterpret_cast<const char *>(S.tris + slot) + 32, q2, q3);
     const V3 p0 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
     const V3 n = mk3(q2.y, q2.z, q2.w);  // cross(e1, e2) as stored by the Triangle ctor (Primitives.h:93)
     const uint32_t matflags = __float_as_uint(q3.x);
@@ -137,14 +148,16 @@ VT_DEV void write_hit(vt_hit *hits, unsigned long long idx, const RayState &r) {
 // enough lanes have a candidate queued (or nobody can walk), a node round otherwise.  Lanes that
 // cannot take part in the chosen round wait; this trades a little idling for never running the
 // ~100-instruction triangle test with one or two live lanes.
-template <bool ANY_HIT, bool ALPHA>
+template <bool ANY_HIT, bool ALPHA, bool SMEM>
 __global__ void __launch_bounds__(VT_TRAVERSE_BLOCK, VT_TRAVERSE_MIN_BLOCKS)
 k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restrict__ hits, unsigned long long n,
            unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold) {
     extern __shared__ float4 s_pairs[];
-    for (uint32_t i = threadIdx.x; i < S.n_smem_pairs * 4u; i += blockDim.x)
-        s_pairs[i] = __ldg(reinterpret_cast<const float4 *>(S.pairs) + i);
-    if (S.n_smem_pairs) __syncthreads();
+    if (SMEM) {  // optional: stage the top of the tree (the first n_smem_pairs pairs, breadth-first) per CTA
+        for (uint32_t i = threadIdx.x; i < S.n_smem_pairs * 4u; i += blockDim.x)
+            s_pairs[i] = __ldg(reinterpret_cast<const float4 *>(S.pairs) + i);
+        __syncthreads();
+    }
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -159,6 +172,7 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
     RayState r;
     unsigned long long n_invalid = 0;
 
+    // invariant: a lane without a ray has walking == false and na == 0
     for (;;) {
         // ---- retire finished rays, refill idle lanes from the global queue
         if (alive && !walking && na == 0) {
@@ -187,8 +201,6 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
                     vt_ray in{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                     init_ray(in, r);
                     alive = true;
-                    walking = false;
-                    na = nb = 0;
                     sp = 0;
                     // argument rules of AccelStruct::Traverse (source/objects/AccelStruct.cpp:805-806):
                     // tMin < 0 or tMax <= tMin is an error there; here the ray becomes a counted miss.
@@ -204,74 +216,68 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
                     }
                 }
             }
-            continue;  // retire degenerate rays / re-evaluate before doing work
         }
+        const int keep = exhausted ? 0 : refill_threshold;
 
-        // ---- choose the round
-        const unsigned want_tri = __ballot_sync(0xffffffffu, alive && na != 0);
-        const unsigned want_node = __ballot_sync(0xffffffffu, alive && na == 0 && walking);
-        if (want_tri && (want_node == 0 || __popc(want_tri) >= tri_threshold)) {
-            // ---- triangle round: one queued candidate per lane (intersect_leaf loop body, :53-61)
-            if (alive && na != 0) {
-                const bool hit = intersect_triangle<ALPHA>(S, qa, r);
-                qa++;
-                na--;
-                if (ANY_HIT && hit) {  // any_hit: first accepted candidate ends the ray (:57-58, :91-93)
-                    na = nb = 0;
-                    walking = false;
-                } else if (na == 0) {
-                    qa = qb;
-                    na = nb;
-                    nb = 0;
+        // ---- rounds, until too few lanes have work left
+        for (;;) {
+            const unsigned want_tri = __ballot_sync(0xffffffffu, na != 0);
+            const unsigned want_node = __ballot_sync(0xffffffffu, na == 0 && walking);
+            if (__popc(want_tri | want_node) <= keep) break;
+            if (want_tri && (want_node == 0 || __popc(want_tri) >= tri_threshold)) {
+                // ---- triangle round: one queued candidate per lane (intersect_leaf loop body, :53-61)
+                if (na != 0) {
+                    const bool hit = intersect_triangle<ALPHA>(S, qa, r);
+                    qa++;
+                    na--;
+                    if (ANY_HIT && hit) {  // any_hit: first accepted candidate ends the ray (:57-58, :91-93)
+                        na = nb = 0;
+                        walking = false;
+                    } else if (na == 0) {
+                        qa = qb;
+                        na = nb;
+                        nb = 0;
+                    }
                 }
-            }
-        } else if (want_node) {
-            // ---- node round (:82-123)
-            if (alive && na == 0 && walking) {
+            } else if (na == 0 && walking) {
+                // ---- node round (:82-123), written branch-free: everything below is selects and
+                // predicated stack accesses, so lanes that take different exits do not serialise.
                 float4 a, b, c, d;
-                if (cur < S.n_smem_pairs) {
+                if (SMEM && cur < S.n_smem_pairs) {
                     const float4 *p = s_pairs + cur * 4u;
                     a = p[0], b = p[1], c = p[2], d = p[3];
                 } else {
-                    const float4 *p = reinterpret_cast<const float4 *>(S.pairs + cur);
-                    a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+                    ldg256(S.pairs + cur, a, b);
+                    ldg256(reinterpret_cast<const char *>(S.pairs + cur) + 32, c, d);
                 }
                 float le, lx, re, rx;
                 slab_pair(a, b, c, d, r, le, lx, re, rx);  // both boxes against the tmax of step entry (:86-87)
                 const uint32_t lcount = __float_as_uint(b.z), lfirst = __float_as_uint(b.w);
                 const uint32_t rcount = __float_as_uint(d.z), rfirst = __float_as_uint(d.w);
-                bool go_l = le <= lx, go_r = re <= rx;
-                if (go_l && lcount) {  // left leaf is tested first (:89-97) ...
-                    qa = lfirst;
-                    na = lcount;
-                    go_l = false;
+                const bool hit_l = le <= lx, hit_r = re <= rx;
+                const bool leaf_l = hit_l && lcount != 0, leaf_r = hit_r && rcount != 0;
+                const bool in_l = hit_l && lcount == 0, in_r = hit_r && rcount == 0;
+                // leaf children: the left run is tested first (:89-97), then the right run (:99-107)
+                qa = leaf_l ? lfirst : rfirst;
+                na = leaf_l ? lcount : (leaf_r ? rcount : 0u);
+                qb = rfirst;
+                nb = (leaf_l && leaf_r) ? rcount : 0u;
+                // inner children: near first, far pushed; `le > re` swaps, ties keep the left child first (:109-115)
+                const bool both = in_l && in_r;
+                const bool take_r = both ? (le > re) : in_r;
+                const uint32_t next = take_r ? rfirst : lfirst;
+                const uint32_t far_ = take_r ? lfirst : rfirst;
+                if (both) {
+                    stack[sp & (VT_STACK_SIZE - 1)] = far_;  // reference: unchecked, UB past 64 entries; depth is validated at populate
+                    sp++;
                 }
-                if (go_r && rcount) {  // ... then the right leaf (:99-107)
-                    if (na) {
-                        qb = rfirst;
-                        nb = rcount;
-                    } else {
-                        qa = rfirst;
-                        na = rcount;
-                    }
-                    go_r = false;
-                }
-                if (go_l) {
-                    if (go_r) {
-                        uint32_t near_ = lfirst, far_ = rfirst;
-                        if (le > re) { near_ = rfirst; far_ = lfirst; }  // :111-112, ties keep left first
-                        if (sp < VT_STACK_SIZE) stack[sp] = far_;       // reference: unchecked (UB past 64)
-                        sp++;
-                        cur = near_;
-                    } else
-                        cur = lfirst;
-                } else if (go_r) {
-                    cur = rfirst;
-                } else if (sp == 0) {
-                    walking = false;
-                } else {
+                const bool pop = !(in_l || in_r);
+                if (pop && sp > 0) {
                     sp--;
-                    cur = stack[sp < VT_STACK_SIZE ? sp : VT_STACK_SIZE - 1];
+                    cur = stack[sp & (VT_STACK_SIZE - 1)];
+                } else {
+                    cur = next;
+                    walking = !pop;
                 }
             }
         }
@@ -299,12 +305,16 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
                                                           cfg.persistent ? 1 : 0, cfg.refill_threshold, cfg.tri_threshold);
         return cudaGetLastError();
     };
-    if (any_hit) return alpha ? launch(k_traverse<true, true>) : launch(k_traverse<true, false>);
-    return alpha ? launch(k_traverse<false, true>) : launch(k_traverse<false, false>);
+    if (S.n_smem_pairs) {
+        if (any_hit) return alpha ? launch(k_traverse<true, true, true>) : launch(k_traverse<true, false, true>);
+        return alpha ? launch(k_traverse<false, true, true>) : launch(k_traverse<false, false, true>);
+    }
+    if (any_hit) return alpha ? launch(k_traverse<true, true, false>) : launch(k_traverse<true, false, false>);
+    return alpha ? launch(k_traverse<false, true, false>) : launch(k_traverse<false, false, false>);
 }
 
 cudaError_t vt_traverse_occupancy(int *blocks_per_sm, size_t smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(k_traverse<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_traverse<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_traverse<false, true>, VT_TRAVERSE_BLOCK, smem_bytes);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_traverse<false, true, true>, VT_TRAVERSE_BLOCK, smem_bytes);
 }
