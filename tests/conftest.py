@@ -73,3 +73,20 @@ def attr_max_rel_err(a, b):
         else:
             out[f] = int((x != y).sum())
     return out
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    """tests/golden/<name>.npz -> (SceneData, dict of arrays); fixtures come from the unmodified
+    reference (tests/golden/make_golden.py)."""
+    from vistrace_b200 import abi
+
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    texs = []
+    for i in range(int(z["n_textures"])):
+        w, h, m, fl = (int(v) for v in z[f"tex{i}_hdr"])
+        texs.append((w, h, m, fl, z[f"tex{i}_px"]))
+    scene = abi.SceneData(z["tris"], z["materials"], z["entities"], texs)
+    return scene, z

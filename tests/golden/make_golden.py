@@ -1,0 +1,83 @@
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference -> oracle/_ref/libvt_ref.so):
+
+    python tests/golden/make_golden.py
+
+Every array in the .npz files is either an input (scene, hierarchy, rays) or an output of the
+reference's own code run through oracle/ref_harness.cpp.  The fixtures travel to the GPU box, where
+/root/reference does not exist; tests compare the C restatement (oracle/vt_oracle.c) and the CUDA
+path against them bit for bit.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import oracle  # noqa: E402
+from vistrace_b200 import abi, scenes  # noqa: E402
+
+
+def pack_scene(sc):
+    d = {"tris": sc.tris, "materials": sc.materials, "entities": sc.entities, "n_textures": np.array(len(sc.textures))}
+    for i, (w, h, m, fl, px) in enumerate(sc.textures):
+        d[f"tex{i}_hdr"] = np.array([w, h, m, fl], np.int64)
+        d[f"tex{i}_px"] = px
+    return d
+
+
+def golden_scene(name, sc, rays, extra_rays=None):
+    ref = oracle.CpuScene(sc, "reference")
+    nodes, prims = ref.get_bvh()
+    out = pack_scene(sc)
+    out.update(nodes=nodes, prim_indices=prims, tri_derived=ref.tri_derived())
+    r = ref.traverse(rays, want_attrs=True, want_stats=True)
+    out.update(rays=rays, hits=r["hits"], attrs=r["attrs"], stats=np.array([r["steps"], r["isects"]], np.uint64))
+    bounce, _ = scenes.bounce_rays(r["attrs"], spp=2, key=11)
+    rb = ref.traverse(bounce, want_attrs=True)
+    out.update(bounce_rays=bounce, bounce_hits=rb["hits"], bounce_attrs=rb["attrs"])
+    if extra_rays is not None:
+        re = ref.traverse(extra_rays, want_attrs=True)
+        out.update(extra_rays=extra_rays, extra_hits=re["hits"], extra_attrs=re["attrs"])
+    if sc.textures:
+        rng = np.random.default_rng(5)
+        uvm = np.concatenate([rng.uniform(-2.5, 2.5, (4000, 2)), rng.uniform(-1.0, 9.0, (4000, 1))], 1).astype(np.float32)
+        uvm[:500, 2] = 0.0
+        uvm[500:600, :2] = np.array([[0.0, 0.0], [1.0, 1.0], [-1e-9, 0.5], [0.5, -1e-9], [0.9999, 0.9999]] * 20, np.float32)
+        out["tex_uvm"] = uvm
+        for i in range(len(sc.textures)):
+            out[f"tex{i}_samples"] = ref.sample(i, uvm)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: (v.shape, str(v.dtype)[:12]) for k, v in out.items() if hasattr(v, "shape")})
+
+
+def main():
+    assert oracle.available("reference"), "build oracle/_ref first: make -C oracle ref"
+    # foliage: alpha test (wrap + clamp textures), two-sided cards, one-sided ground, sky room
+    sc = scenes.scene_foliage(n_cards=400, tex_size=32, ground_quads=8, seed=7)
+    rays = scenes.pinhole_rays(96, 54, (0, -48, 20), (0, 0, 8))
+    rnd = scenes.random_rays(3000, (-45, -45, -3), (45, 45, 50), seed=2)
+    rnd["tmax"][::3] = 30.0
+    rnd["tmin"][::4] = 2.0
+    rnd["d"][::5] *= 2.5
+    golden_scene("foliage_small", sc, rays, rnd)
+    # props: multi-entity, per-entity colours and ids, shadow-style rays
+    sc = scenes.scene_props(6, 15, 9, 8)
+    rays = scenes.pinhole_rays(96, 54, (0, -95, 40), (0, 0, 10))
+    golden_scene("props_small", sc, rays)
+    # known answers of the vendored bvh tests
+    # libs/bvh/test/node_intersectors.cpp:18-36 — flat box z in [2.1, 2.1], direction (0, -0, 1): must intersect
+    node = np.zeros(1, abi.NODE)
+    node["bounds"] = (-1, 1, -1, 1, 2.1, 2.1)
+    ray = np.zeros(1, abi.RAY)
+    ray["o"], ray["d"], ray["tmin"], ray["tmax"] = (0.25, 0.25, 0.0), (0.0, -0.0, 1.0), 0.0, 100.0
+    entry, exit_ = oracle.node_intersect(node, ray, "reference")
+    np.savez(os.path.join(HERE, "kat_node_intersect.npz"), node=node, ray=ray, entry_exit=np.array([entry, exit_], np.float32))
+    print("kat node", entry, exit_)
+
+
+if __name__ == "__main__":
+    main()

@@ -198,3 +198,110 @@ def test_large_batch_properties(vt):
     half = len(rays) // 2
     again = np.concatenate([accel.traverse(rays[:half]), accel.traverse(rays[half:])])
     assert again.tobytes() == hits.tobytes()
+
+
+@pytest.mark.parametrize("name", ["foliage_small", "props_small"])
+def test_cuda_matches_reference_golden_vectors(vt, name):
+    """The committed fixtures are outputs of the UNMODIFIED reference (tests/golden/make_golden.py): its own
+    PLOC + LeafCollapser tree, its hits, its TraceResult values.  The CUDA path must reproduce them."""
+    from conftest import load_golden
+
+    scene, z = load_golden(name)
+    accel = vt.Accel(0).populate(scene, bvh=(z["nodes"], z["prim_indices"]))
+    np.testing.assert_array_equal(accel.tri_derived().view(np.uint32), z["tri_derived"].view(np.uint32))
+    for rays_k, hits_k, attrs_k in (("rays", "hits", "attrs"), ("bounce_rays", "bounce_hits", "bounce_attrs"), ("extra_rays", "extra_hits", "extra_attrs")):
+        if rays_k not in z:
+            continue
+        hits, attrs = accel.traverse(z[rays_k], want_attrs=True)
+        assert hits.tobytes() == z[hits_k].tobytes(), (name, rays_k)
+        err = attr_max_rel_err(attrs, z[attrs_k])
+        for f in ATTR_FLOAT_FIELDS:
+            assert err[f] <= 1e-5, (name, rays_k, f, err[f])
+        for f in ATTR_INT_FIELDS:
+            assert err[f] == 0, (name, rays_k, f)
+
+
+def test_bounce_ray_generation_and_diffuse_wave(vt, oracle_mod):
+    """K3 + the one-call wave: the generated rays follow hemisphere_cos / CalcRayOrigin, the wave equals the
+    piecewise calls, tiling does not change a bit, and the oracle agrees on every generated ray."""
+    import os
+
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_heightfield(64)
+    rays = scenes.pinhole_rays(320, 180, (0, -80, 60), (0, 0, 5))
+    accel = vt.Accel(0).populate(scene)
+    hits, attrs = accel.traverse(rays, want_attrs=True)
+    spp = 3
+    brays, live = accel.bounce_rays(attrs, spp, seed=42)
+    masked = brays["tmax"] < 0
+    spawn = (attrs["prim"] != abi.VT_MISS) & ((attrs["flags"] & abi.VT_ATTR_HIT_SKY) == 0)
+    np.testing.assert_array_equal(~masked, np.repeat(spawn, spp))
+    assert live == int((~masked).sum()) and 0 < live < len(brays)
+    a = np.repeat(attrs, spp)[~masked]
+    b = brays[~masked]
+    sgn = np.where((a["flags"] & abi.VT_ATTR_FRONT_FACING) != 0, 1.0, -1.0)[:, None].astype(np.float32)
+    np.testing.assert_allclose(np.linalg.norm(b["d"], axis=1), 1.0, atol=2e-5)       # unit directions ...
+    assert ((b["d"] * a["normal"] * sgn).sum(-1) >= -1e-5).all()                      # ... in the viewer-side hemisphere
+    np.testing.assert_array_equal(b["o"], scenes.calc_ray_origin(a["pos"], a["geometric_normal"] * sgn))  # CalcRayOrigin, bit-exact
+    cosines = (b["d"] * a["normal"] * sgn).sum(-1)
+    assert abs(cosines.mean() - 2.0 / 3.0) < 0.01                                     # cosine-weighted: E[cos] = 2/3
+    # traversal of the generated rays is bit-exact against the oracle
+    cpu = oracle_mod.CpuScene(scene, "port", build_bvh=False)
+    cpu.set_bvh(*accel.get_bvh())
+    bhits = accel.traverse(brays)
+    want = cpu.traverse(b)["hits"]
+    assert bhits[~masked].tobytes() == want.tobytes()
+    assert (bhits["prim"][masked] == abi.VT_MISS).all() and accel.invalid_rays == 0   # masked slots: silent misses
+    # the one-call wave, whole and tiled
+    whole = accel.trace_diffuse_wave(rays, spp, seed=42, want_attrs=True, want_bounce_rays=True)
+    os.environ["VT_WAVE_TILE"] = "5000"
+    tiled = accel.trace_diffuse_wave(rays, spp, seed=42, want_attrs=True, want_bounce_rays=True)
+    del os.environ["VT_WAVE_TILE"]
+    for k, ref in (("hits", hits), ("attrs", attrs), ("bounce_rays", brays), ("bounce_hits", bhits)):
+        assert whole[k].tobytes() == ref.tobytes(), k
+        assert tiled[k].tobytes() == ref.tobytes(), k
+    assert whole["live_bounce"] == live == tiled["live_bounce"]
+
+
+def test_accumulate_sky_framebuffer(vt):
+    import torch
+
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_heightfield(48)
+    rays = scenes.pinhole_rays(160, 90, (0, -80, 60), (0, 0, 5))
+    accel = vt.Accel(0).populate(scene)
+    spp = 4
+    w = accel.trace_diffuse_wave(rays, spp, seed=3, want_attrs=True)
+    to_dev = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).cuda()
+    d_attrs, d_bh = to_dev(w["attrs"]), to_dev(w["bounce_hits"])
+    fb = torch.zeros(len(rays) * 3, dtype=torch.float32, device="cuda")
+    accel.accumulate_sky_device(d_attrs.data_ptr(), d_bh.data_ptr(), len(rays), spp, 0.5, fb.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = fb.cpu().numpy().reshape(-1, 3)
+    a, bh = w["attrs"], w["bounce_hits"].reshape(-1, spp)
+    sky_mat = (scene.materials["surf_flags"] & abi.VT_SURF_SKY) != 0
+    esc = (bh["prim"] == abi.VT_MISS) | sky_mat[scene.tris["material"][np.minimum(bh["prim"], scene.n_tris - 1)]]
+    vis = esc.sum(1).astype(np.float32) / np.float32(spp)
+    is_sky = (a["flags"] & abi.VT_ATTR_HIT_SKY) != 0
+    want = np.where(is_sky[:, None], a["albedo"], a["albedo"] * vis[:, None]) * np.float32(0.5)
+    want[a["prim"] == abi.VT_MISS] = 0
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+
+
+def test_two_gpu_sharded_trace_nccl(vt):
+    """Real multi-GPU plumbing when the box has >= 2 GPUs (gpurun --gpus 2): replicated hierarchy, ray shards, NCCL gather."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import ROOT
+
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29571", f"{ROOT}/tests/multi_gpu_worker.py"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MULTI_GPU_OK" in r.stdout

@@ -1,0 +1,188 @@
+"""CPU tests of the host side of the product: the C-ABI library loads and exports every symbol the
+header declares, the hierarchy builder and the flattening step are correct (checked by running the
+ORACLE's traverser over the product's tree), and nothing computes on a machine without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, compare_hits
+
+
+def test_library_exports_every_declared_symbol(built):
+    import vistrace_b200 as vt
+    from vistrace_b200 import binding
+
+    header = open(os.path.join(ROOT, "include", "vistrace_b200.h")).read()
+    declared = set(re.findall(r"\b(vt_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    L = vt.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/vistrace_b200.h but not exported"
+    assert declared == set(binding.SYMBOLS), declared ^ set(binding.SYMBOLS)
+
+
+def test_record_sizes_match_header(built):
+    from vistrace_b200 import abi
+
+    assert (abi.RAY.itemsize, abi.HIT.itemsize, abi.NODE.itemsize, abi.TRI_IN.itemsize, abi.ATTR.itemsize) == (32, 16, 32, 152, 128)
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device the engine refuses to work instead of detouring through a CPU path."""
+    import vistrace_b200 as vt
+
+    if vt.lib().vt_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        vt.Accel(0)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "vistrace_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "oracle/" not in src and "vt_oracle" not in src and "vtref_" not in src, f
+
+
+@pytest.mark.parametrize("scene_name", ["heightfield", "foliage", "props"])
+def test_builder_tree_is_valid_and_equivalent(oracle_mod, scene_name):
+    """The product builder emits a well-formed bvh::Bvh<float>-form tree; the oracle traversing it finds the same
+    closest t as over the brute-force single-leaf tree for every ray (primitive may differ only on exact ties)."""
+    import vistrace_b200 as vt
+    from vistrace_b200 import abi, scenes
+
+    scene = {"heightfield": lambda: scenes.scene_heightfield(48), "foliage": lambda: scenes.scene_foliage(1200, tex_size=32),
+             "props": lambda: scenes.scene_props(5, 15, 9, 12)}[scene_name]()
+    nodes, prims = vt.build_bvh(scene)
+    n = scene.n_tris
+    assert len(nodes) % 2 == 1 and sorted(prims.tolist()) == list(range(n))
+    leaves = nodes[nodes["prim_count"] > 0]
+    assert leaves["prim_count"].sum() == n and leaves["prim_count"].max() <= 4
+    inner = nodes[nodes["prim_count"] == 0]
+    assert (inner["first"] % 2 == 1).all() and len(set(inner["first"].tolist())) == len(inner)
+    # children are inside their parent
+    for i in np.random.default_rng(0).choice(len(inner), min(300, len(inner)), replace=False):
+        p = inner[i]
+        for c in (nodes[p["first"]], nodes[p["first"] + 1]):
+            assert (c["bounds"][0::2] >= p["bounds"][0::2]).all() and (c["bounds"][1::2] <= p["bounds"][1::2]).all()
+    rays = scenes.random_rays(4000, (-45, -45, -2), (45, 45, 40), seed=5)
+    cpu = oracle_mod.CpuScene(scene, "port", build_bvh=False)
+    cpu.set_bvh(nodes, prims)
+    got = cpu.traverse(rays)["hits"]
+    brute = np.zeros(1, abi.NODE)
+    brute["bounds"], brute["prim_count"] = (-1e30, 1e30, -1e30, 1e30, -1e30, 1e30), n
+    cpu.set_bvh(brute, np.arange(n, dtype=np.uint64))
+    want = cpu.traverse(rays)["hits"]
+    rep = compare_hits(got, want)
+    assert rep["hit_miss_mismatch"] == 0 and rep["prim_mismatch"] == rep["prim_mismatch_exact_tie"], rep
+    np.testing.assert_array_equal(got["t"], want["t"])
+    # deterministic: same input -> same tree
+    nodes2, prims2 = vt.build_bvh(scene)
+    assert nodes.tobytes() == nodes2.tobytes() and prims.tobytes() == prims2.tobytes()
+
+
+def _emulate_pairs(flat, tris_derived, rays):
+    """Tiny numpy traverser over the FLATTENED layout (pairs + leaf order) — checks the structure the GPU walks."""
+    pairs, order = flat["pairs"], flat["leaf_order"]
+    out = np.full(len(rays), 0xFFFFFFFF, np.uint32)
+    for ri, r in enumerate(rays):
+        o, d = r["o"].astype(np.float64), r["d"].astype(np.float64)
+        best_t, best = float(r["tmax"]), 0xFFFFFFFF
+        stack = [0] if len(pairs) else []
+        runs = [(0, flat["root_leaf_count"])] if flat["root_leaf_count"] else []
+        while stack or runs:
+            for first, cnt in runs:
+                for s in range(first, first + cnt):
+                    t = tris_derived[order[s]].astype(np.float64)
+                    p0, e1, e2, n = t[0:3], t[3:6], t[6:9], t[9:12]
+                    nd = n @ d
+                    if nd == 0:
+                        continue
+                    c = p0 - o
+                    rr = np.cross(d, c)
+                    u, v = (rr @ e2) / nd, (rr @ e1) / nd
+                    tt = (n @ c) / nd
+                    if u >= 0 and v >= 0 and 1 - u - v >= 0 and r["tmin"] <= tt <= best_t:
+                        best_t, best = tt, order[s]
+            runs = []
+            if not stack:
+                break
+            p = pairs[stack.pop()]
+            for b, cnt, first in ((p["l_bounds"], p["l_count"], p["l_first"]), (p["r_bounds"], p["r_count"], p["r_first"])):
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    t0 = (b[0::2] - o) / d
+                    t1 = (b[1::2] - o) / d
+                lo, hi = np.nanmax(np.minimum(t0, t1)), np.nanmin(np.maximum(t0, t1))
+                if max(lo, r["tmin"]) <= min(hi, best_t) * (1 + 1e-6) + 1e-6:
+                    if cnt:
+                        runs.append((int(first), int(cnt)))
+                    else:
+                        stack.append(int(first))
+        out[ri] = best
+    return out
+
+
+@pytest.mark.parametrize("bfs_pairs", [0, 7, 100000])
+def test_flatten_preserves_the_tree(oracle_mod, bfs_pairs):
+    import vistrace_b200 as vt
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_props(3, 11, 7, 6)
+    nodes, prims = vt.build_bvh(scene)
+    flat = vt.flatten_bvh(nodes, prims, bfs_pairs)
+    n_pairs = (len(nodes) - 1) // 2
+    assert len(flat["pairs"]) == n_pairs and sorted(flat["leaf_order"].tolist()) == list(range(scene.n_tris))
+    assert 1 <= flat["max_depth"] <= 60
+    p = flat["pairs"]
+    inner_refs = np.concatenate([p["l_first"][p["l_count"] == 0], p["r_first"][p["r_count"] == 0]])
+    assert sorted(inner_refs.tolist()) == list(range(1, n_pairs))  # every pair but the root pair is referenced exactly once
+    # pair 0 holds the children of the root, bounds copied verbatim
+    assert p[0]["l_bounds"].tobytes() == nodes[nodes[0]["first"]]["bounds"].tobytes()
+    cpu = oracle_mod.CpuScene(scene, "port", build_bvh=False)
+    cpu.set_bvh(nodes, prims)
+    rays = scenes.random_rays(150, (-80, -80, 0), (80, 80, 60), seed=9)
+    want = cpu.traverse(rays)["hits"]
+    got = _emulate_pairs(flat, cpu.tri_derived(), rays)
+    assert (got == want["prim"]).mean() > 0.98  # float64 emulation vs float32 oracle: only grazing rays may differ
+    assert ((got == abi.VT_MISS) == (want["prim"] == abi.VT_MISS)).mean() > 0.98
+
+
+def test_flatten_rejects_malformed_trees(built):
+    import vistrace_b200 as vt
+    from vistrace_b200 import abi
+
+    nodes = np.zeros(3, abi.NODE)
+    nodes[0]["first"] = 2  # children must sit at an odd index
+    nodes[1]["prim_count"] = nodes[2]["prim_count"] = 1
+    with pytest.raises(RuntimeError, match="child index"):
+        vt.flatten_bvh(nodes, np.arange(2, dtype=np.uint64))
+    nodes[0]["first"] = 1
+    nodes[2]["first"] = 1
+    with pytest.raises(RuntimeError, match="cover|past the end"):
+        vt.flatten_bvh(nodes, np.arange(3, dtype=np.uint64))
+    chain = np.zeros(2 * 70 + 1, abi.NODE)  # a 70-deep degenerate chain overflows the 64-entry stack
+    for d in range(70):
+        parent = 0 if d == 0 else 2 * d - 1
+        chain[parent]["first"] = 2 * d + 1
+        chain[2 * d + 2]["prim_count"], chain[2 * d + 2]["first"] = 1, d
+    chain[2 * 69 + 1]["prim_count"], chain[2 * 69 + 1]["first"] = 1, 70
+    with pytest.raises(RuntimeError, match="deeper"):
+        vt.flatten_bvh(chain, np.arange(71, dtype=np.uint64))
+
+
+def test_scene_generators_are_deterministic_and_oriented():
+    from vistrace_b200 import scenes
+
+    a, b = scenes.scene_heightfield(16), scenes.scene_heightfield(16)
+    assert a.tris.tobytes() == b.tris.tobytes()
+    n = scenes.reference_normal(a.tris[:-12])
+    assert (n[:, 2] > 0).all()  # terrain front faces look up (n = cross(p0-p1, p2-p0), Primitives.h:82,93)
+    rays = scenes.pinhole_rays(8, 4, (0, -80, 60), (0, 0, 5))
+    np.testing.assert_allclose(np.linalg.norm(rays["d"], axis=1), 1.0, atol=1e-6)
+    pos = np.array([[10.0, -0.01, 300.0]], np.float32)
+    nrm = np.array([[0.0, 0.0, 1.0]], np.float32)
+    o = scenes.calc_ray_origin(pos, nrm)  # source/VisTrace.cpp:1495-1517
+    assert o[0, 2] > pos[0, 2] and o[0, 0] == pos[0, 0] and o[0, 1] == pos[0, 1]

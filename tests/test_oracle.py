@@ -1,0 +1,140 @@
+"""CPU tests of the oracle: the plain-C restatement (oracle/vt_oracle.c) against
+  (a) golden vectors generated from the UNMODIFIED reference (tests/golden/*.npz),
+  (b) the known-answer tests the vendored bvh library ships, and
+  (c) the reference itself (oracle/_ref/libvt_ref.so) when it is present.
+Everything is compared bit for bit: the restatement follows the reference's arithmetic order."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+FLT_MAX = np.finfo(np.float32).max
+
+
+def _port_scene(oracle_mod, scene, z):
+    cpu = oracle_mod.CpuScene(scene, "port", build_bvh=False)
+    cpu.set_bvh(z["nodes"], z["prim_indices"])
+    return cpu
+
+
+@pytest.mark.parametrize("name", ["foliage_small", "props_small"])
+def test_port_matches_golden_hits_and_attrs(oracle_mod, name):
+    scene, z = load_golden(name)
+    cpu = _port_scene(oracle_mod, scene, z)
+    np.testing.assert_array_equal(cpu.tri_derived().view(np.uint32), z["tri_derived"].view(np.uint32))
+    for rays_k, hits_k, attrs_k in (("rays", "hits", "attrs"), ("bounce_rays", "bounce_hits", "bounce_attrs"), ("extra_rays", "extra_hits", "extra_attrs")):
+        if rays_k not in z:
+            continue
+        got = cpu.traverse(z[rays_k], want_attrs=True, want_stats=True)
+        assert got["hits"].tobytes() == z[hits_k].tobytes(), (name, rays_k)
+        assert got["attrs"].tobytes() == z[attrs_k].tobytes(), (name, rays_k)
+        if rays_k == "rays":  # SingleRayTraverser::Statistics of the reference run
+            assert [got["steps"], got["isects"]] == [int(v) for v in z["stats"]]
+        # the attribute stage on its own reproduces the same records from the golden hits
+        assert cpu.trace_result(z[rays_k], z[hits_k]).tobytes() == z[attrs_k].tobytes()
+
+
+def test_port_texture_sampler_matches_golden(oracle_mod):
+    scene, z = load_golden("foliage_small")
+    cpu = _port_scene(oracle_mod, scene, z)
+    for i in range(int(z["n_textures"])):  # texture 0 wraps, texture 1 clamps; mips 0..5 incl. fractional levels
+        got = cpu.sample(i, z["tex_uvm"])
+        np.testing.assert_array_equal(got.view(np.uint32), z[f"tex{i}_samples"].view(np.uint32))
+
+
+def test_kat_node_intersector_flat_box_negative_zero(oracle_mod):
+    """libs/bvh/test/node_intersectors.cpp:18-36 — box flat in z, ray direction (0, -0, 1): must be hit."""
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "kat_node_intersect.npz"))
+    entry, exit_ = oracle_mod.node_intersect(z["node"], z["ray"], "port")
+    assert entry <= exit_
+    assert [np.float32(entry), np.float32(exit_)] == list(z["entry_exit"])
+
+
+def test_kat_simple_example_quad(oracle_mod):
+    """libs/bvh/test/simple_example.cpp:63-83 — ray (0,0,0)->+Z, t in [0,100] must hit the 2-triangle quad at z = 1.
+    (VisTrace's primitive is two-sided here: oneSided = false, so winding does not matter.)"""
+    from vistrace_b200 import abi
+
+    tris = np.zeros(2, abi.TRI_IN)
+    tris["p"][0] = [[1, -1, 1], [1, 1, 1], [-1, 1, 1]]
+    tris["p"][1] = [[1, -1, 1], [-1, -1, 1], [-1, 1, 1]]
+    tris["normals"], tris["tangents"], tris["alphas"] = (0, 0, 1), (1, 0, 0), 1.0
+    tris["uvs"] = [[0, 0], [1, 0], [1, 1]]
+    scene = abi.SceneData(tris)
+    cpu = oracle_mod.CpuScene(scene, "port", build_bvh=False)
+    nodes = np.zeros(1, abi.NODE)  # a single leaf root (single_ray_traverser.hpp:72-73)
+    nodes["bounds"], nodes["prim_count"], nodes["first"] = (-1, 1, -1, 1, 1, 1), 2, 0
+    cpu.set_bvh(nodes, np.arange(2, dtype=np.uint64))
+    ray = np.zeros(1, abi.RAY)
+    ray["d"], ray["tmax"] = (0, 0, 1), 100.0
+    hit = cpu.traverse(ray)["hits"][0]
+    assert hit["prim"] != abi.VT_MISS and hit["t"] == np.float32(1.0)
+    ray["tmax"] = 0.5  # closed interval [tmin, tmax] (Primitives.h:189)
+    assert cpu.traverse(ray)["hits"][0]["prim"] == abi.VT_MISS
+    ray["tmax"] = 1.0
+    assert cpu.traverse(ray)["hits"][0]["prim"] != abi.VT_MISS
+
+
+def test_exact_tie_is_won_by_the_later_candidate(oracle_mod):
+    """`t <= tmax` + tmax = t (single_ray_traverser.hpp:55-60): of two coplanar duplicates the one tested later wins."""
+    from vistrace_b200 import abi
+
+    tris = np.zeros(2, abi.TRI_IN)
+    tris["p"][:] = [[-1, -1, 2], [1, -1, 2], [0, 1, 2]]
+    tris["normals"], tris["tangents"], tris["alphas"] = (0, 0, 1), (1, 0, 0), 1.0
+    tris["uvs"] = [[0, 0], [1, 0], [0, 1]]
+    cpu = oracle_mod.CpuScene(abi.SceneData(tris), "port", build_bvh=False)
+    nodes = np.zeros(1, abi.NODE)
+    nodes["bounds"], nodes["prim_count"] = (-1, 1, -1, 1, 2, 2), 2
+    ray = np.zeros(1, abi.RAY)
+    ray["d"], ray["tmax"] = (0, 0, 1), FLT_MAX
+    for order in ([0, 1], [1, 0]):
+        cpu.set_bvh(nodes, np.array(order, np.uint64))
+        assert cpu.traverse(ray)["hits"][0]["prim"] == order[1]
+
+
+def test_backface_cull_and_nocull(oracle_mod):
+    """oneSided && !nocull && dot(n, d) > 0 rejects (Primitives.h:173-174)."""
+    from vistrace_b200 import abi
+
+    tris = np.zeros(1, abi.TRI_IN)
+    tris["p"][0] = [[-1, -1, 0], [1, -1, 0], [0, 1, 0]]
+    tris["normals"], tris["tangents"], tris["alphas"], tris["one_sided"] = (0, 0, 1), (1, 0, 0), 1.0, 1
+    tris["uvs"] = [[0, 0], [1, 0], [0, 1]]
+    nodes = np.zeros(1, abi.NODE)
+    nodes["bounds"], nodes["prim_count"] = (-1, 1, -1, 1, 0, 0), 1
+    rays = np.zeros(2, abi.RAY)
+    rays["o"], rays["d"], rays["tmax"] = [(0, 0, 1), (0, 0, -1)], [(0, 0, -1), (0, 0, 1)], FLT_MAX
+    mats = abi.default_materials(1)
+    cpu = oracle_mod.CpuScene(abi.SceneData(tris, mats), "port", build_bvh=False)
+    cpu.set_bvh(nodes, np.zeros(1, np.uint64))
+    hit = cpu.traverse(rays)["hits"]["prim"] != abi.VT_MISS
+    assert hit.sum() == 1  # exactly one side is culled
+    mats["flags"] = abi.VT_MATFLAG_NOCULL
+    cpu = oracle_mod.CpuScene(abi.SceneData(tris, mats), "port", build_bvh=False)
+    cpu.set_bvh(nodes, np.zeros(1, np.uint64))
+    assert (cpu.traverse(rays)["hits"]["prim"] != abi.VT_MISS).all()
+
+
+def test_port_matches_live_reference(oracle_mod):
+    """With /root/reference compiled (oracle/_ref): restatement == reference on a fresh seeded scene, both hierarchies."""
+    import vistrace_b200 as vt
+    from vistrace_b200 import scenes
+
+    if not oracle_mod.available("reference"):
+        pytest.skip("oracle/_ref/libvt_ref.so not built (needs /root/reference)")
+    scene = scenes.scene_foliage(n_cards=1500, tex_size=64, seed=31)
+    rays = scenes.pinhole_rays(200, 120, (0, -48, 20), (0, 0, 8))
+    ref = oracle_mod.CpuScene(scene, "reference")
+    port = oracle_mod.CpuScene(scene, "port", build_bvh=False)
+    np.testing.assert_array_equal(ref.tri_derived().view(np.uint32), port.tri_derived().view(np.uint32))
+    for bvh in (ref.get_bvh(), vt.build_bvh(scene)):  # the reference's PLOC tree, then the product builder's tree
+        ref.set_bvh(*bvh)
+        port.set_bvh(*bvh)
+        a = ref.traverse(rays, want_attrs=True, want_stats=True)
+        b = port.traverse(rays, want_attrs=True, want_stats=True)
+        assert a["hits"].tobytes() == b["hits"].tobytes() and a["attrs"].tobytes() == b["attrs"].tobytes()
+        assert (a["steps"], a["isects"]) == (b["steps"], b["isects"])
+    uvm = np.random.default_rng(1).uniform(-3, 3, (5000, 3)).astype(np.float32)
+    for i in range(2):
+        np.testing.assert_array_equal(ref.sample(i, uvm).view(np.uint32), port.sample(i, uvm).view(np.uint32))
