@@ -39,6 +39,7 @@ CAMERA = ((0.0, -330.0, 200.0), (0.0, 0.0, 10.0))
 METRIC = "Mrays/s closest-hit (primary+diffuse)"
 WORKLOAD = f"config3: {2 * QUADS * QUADS + 12}-tri closed terrain scene, {WIDTH}x{HEIGHT} primary + {SPP} spp cosine diffuse bounce"
 PAIR_BYTES, TRI_BYTES, RAY_BYTES, HIT_BYTES = 64, 64, 32, 16
+_OUT = sys.stdout
 
 
 def log(*a):
@@ -156,7 +157,7 @@ def run_reference(args):
     from vistrace_b200 import abi, scenes
 
     if not (oracle.available("reference") or oracle.available("port")):
-        print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/libvt_ref.so nor oracle/libvt_oracle.so is built"}))
+        print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/libvt_ref.so nor oracle/libvt_oracle.so is built"}), file=_OUT, flush=True)
         return 0
     scene = make_scene()
     rays = primary_rays()
@@ -193,7 +194,7 @@ def run_reference(args):
         "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cpu.max_threads, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=_OUT, flush=True)
     return 0
 
 
@@ -367,13 +368,17 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": round(cpu["mrays"], 3), "unit": "Mrays/s", "cores": cpu["cores"], "kind": cpu["kind"],
                                 "sample": f"one full step on the host: {len(rays)} primary rays incl. TraceResult + {len(bounce_live)} bounce rays, best of 2, "
                                           f"{'reference PLOC+LeafCollapser hierarchy' if cpu['kind'] == 'reference' else 'product hierarchy'} (build {cpu['build_s']:.1f}s excluded)"}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
