@@ -211,12 +211,14 @@ class Accel:
         rays = rays if isinstance(rays, np.ndarray) and rays.dtype == abi.RAY and rays.flags.c_contiguous else np.ascontiguousarray(rays, abi.RAY)
         n = len(rays)
         out = dict(out or {})
-        out.setdefault("hits", np.zeros(n, abi.HIT))
-        out.setdefault("bounce_hits", np.zeros(n * spp, abi.HIT))
-        if want_attrs:
-            out.setdefault("attrs", np.zeros(n, abi.ATTR))
-        if want_bounce_rays:
-            out.setdefault("bounce_rays", np.zeros(n * spp, abi.RAY))
+        if "hits" not in out:
+            out["hits"] = np.zeros(n, abi.HIT)
+        if "bounce_hits" not in out:
+            out["bounce_hits"] = np.zeros(n * spp, abi.HIT)
+        if want_attrs and "attrs" not in out:
+            out["attrs"] = np.zeros(n, abi.ATTR)
+        if want_bounce_rays and "bounce_rays" not in out:
+            out["bounce_rays"] = np.zeros(n * spp, abi.RAY)
         live = C.c_uint64(0)
         _check(self.L.vt_accel_trace_diffuse_wave(self.h, rays.ctypes.data, n, spp, seed, out["hits"].ctypes.data, _ptr(out.get("attrs")),
                                                   _ptr(out.get("bounce_rays")), out["bounce_hits"].ctypes.data, C.addressof(live), 0, None),
