@@ -210,6 +210,14 @@ int vt_accel_get_bvh(const vt_accel *accel, vt_node *nodes, uint64_t *node_count
 int vt_accel_traverse(vt_accel *accel, const vt_ray *rays, uint64_t n, vt_hit *hits,
                       vt_attr *attrs, uint32_t flags, void *stream);
 
+/* The opt-in statistics overload of the reference traverser (SingleRayTraverser::Statistics,
+ * libs/bvh/include/bvh/single_ray_traverser.hpp:132-135,158-163) summed over a batch of closest-hit
+ * queries: *steps = traversal steps (sibling-pair visits), *tests = primitive intersections.
+ * Synchronous; rays are host pointers unless VT_TRAVERSE_DEVICE_PTRS.  On the exact layout the totals
+ * equal the reference's; on the compact layout steps is slightly larger (conservative boxes). */
+int vt_accel_traverse_stats(vt_accel *accel, const vt_ray *rays, uint64_t n, uint32_t flags,
+                            uint64_t *steps, uint64_t *tests);
+
 /* Same with per-ray texture-LOD cones: cones = n x {coneWidth, coneAngle}, the 5th and 6th
  * arguments of accel:Traverse (source/objects/AccelStruct.cpp:795-803).  NULL = (-1, -1) = mip 0. */
 int vt_accel_traverse_cones(vt_accel *accel, const vt_ray *rays, const float *cones, uint64_t n,
@@ -249,6 +257,23 @@ int vt_accel_trace_diffuse_wave(vt_accel *accel, const vt_ray *rays, uint64_t n,
 int vt_accel_accumulate_sky(vt_accel *accel, const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n,
                             uint32_t spp, float weight, float *framebuffer_rgb, void *stream);
 
+/* Node layout of the device-resident hierarchy, applied by the next populate call.
+ *   VT_LAYOUT_COMPACT (default): each sibling pair — the two Bvh::Node records one traversal step
+ *     reads (libs/bvh/include/bvh/single_ray_traverser.hpp:85-87) — is stored in 32 bytes with
+ *     conservatively quantised boxes.  Every node FastNodeIntersector (node_intersectors.hpp:35-47)
+ *     accepts is still visited, the triangle test is the exact one, so t/u/v/prim are bit-identical to
+ *     the reference whenever the closest hit is unique; only the winner among candidates whose t is
+ *     equal (or differs by float rounding) can differ, because equal-distance subtrees may be
+ *     visited in another order.  Trees it cannot hold (a leaf of > 15 triangles, non-finite bounds)
+ *     fall back to the exact layout: query vt_accel_get_layout() after populate.
+ *   VT_LAYOUT_EXACT: the 2 x 32-byte nodes verbatim; visit order and exact-tie winners are the
+ *     reference's (single_ray_traverser.hpp:55-60,109-115). */
+#define VT_LAYOUT_EXACT   0
+#define VT_LAYOUT_COMPACT 1
+#define VT_LAYOUT_QUAD    2
+int vt_accel_set_layout(vt_accel *accel, int layout);
+int vt_accel_get_layout(const vt_accel *accel);
+
 /* Rays rejected by the argument rules during the last synchronous traverse. */
 uint64_t vt_accel_invalid_rays(const vt_accel *accel);
 
@@ -275,6 +300,20 @@ int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, ui
 int vt_flatten_bvh(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris,
                    uint32_t bfs_pairs, void *pairs_out, uint32_t *leaf_order_out,
                    uint32_t *root_leaf_count, uint32_t *max_depth);
+
+/* Host-only: 64-byte sibling pairs in depth-first order (vt_flatten_bvh with bfs_pairs = 0) ->
+ * n_pairs 32-byte compact pairs: per axis {origin_adj f32} x3, {biased exponent u8} x3,
+ * counts u8 (lcount | rcount << 4), q[axis][l.lo, l.hi, r.lo, r.hi] u8, ref u32.
+ * plane = (2^23 + q) * 2^E + origin_adj, exactly, with lo' <= lo and hi' >= hi. */
+int vt_compact_pairs(const void *pairs, uint64_t n_pairs, void *cpairs_out);
+
+/* Host-only: bvh::Bvh<float>-form hierarchy -> quad nodes (64 bytes each, depth-first order; layout in
+ * vistrace_b200/csrc/vt_device.h: VtQuad) + the leaf-order permutation of the triangles.  Call with
+ * quads_out == NULL to get the count; *n_quads is the capacity on entry, the count on return.
+ * *max_stack = worst-case number of pending child references during traversal (<= 64). */
+int vt_build_quads(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris,
+                   void *quads_out, uint64_t *n_quads, uint32_t *leaf_order_out, uint32_t *root_leaf_count,
+                   uint32_t *max_stack);
 
 /* Last error message of the calling thread ("" if none). */
 const char *vt_last_error(void);

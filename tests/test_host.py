@@ -186,3 +186,147 @@ def test_scene_generators_are_deterministic_and_oriented():
     nrm = np.array([[0.0, 0.0, 1.0]], np.float32)
     o = scenes.calc_ray_origin(pos, nrm)  # source/VisTrace.cpp:1495-1517
     assert o[0, 2] > pos[0, 2] and o[0, 0] == pos[0, 0] and o[0, 1] == pos[0, 1]
+
+
+def _decode_cpairs(c):
+    """numpy restatement of slab_cpair's decode (vt_traverse.cu): float32 fma-free because every step is exact."""
+    scale = (c["exp"].astype(np.uint32) << 23).view(np.float32)                      # 2^E
+    magic = (np.uint32(0x4B000000) | c["q"].astype(np.uint32)).view(np.float32)      # 2^23 + q
+    plane = magic.astype(np.float64) * scale.astype(np.float64)[:, :, None] + c["origin_adj"].astype(np.float64)[:, :, None]
+    assert (plane.astype(np.float32).astype(np.float64) == plane).all()              # (k + q) * 2^E is an exact float
+    return plane.astype(np.float32)  # [pair, axis, {l.lo, l.hi, r.lo, r.hi}]
+
+
+@pytest.mark.parametrize("scene_name", ["heightfield", "foliage", "props", "far_from_origin"])
+def test_compact_pairs_are_conservative_and_address_the_same_children(built, scene_name):
+    import vistrace_b200 as vt
+    from vistrace_b200 import scenes
+
+    if scene_name == "heightfield":
+        scene = scenes.scene_heightfield(48)
+    elif scene_name == "foliage":
+        scene = scenes.scene_foliage(n_cards=1500, tex_size=16, ground_quads=8)
+    elif scene_name == "props":
+        scene = scenes.scene_props(5, 15, 9, 8)
+    else:  # Source-engine map scale: coordinates of +-16384 with sub-unit triangles
+        scene = scenes.scene_props(5, 15, 9, 8)
+        scene.tris["p"] = scene.tris["p"] * np.float32(0.02) + np.array([16000.0, -15900.0, 8000.0], np.float32)
+    nodes, prims = vt.build_bvh(scene)
+    flat = vt.flatten_bvh(nodes, prims, 0)
+    p = flat["pairs"]
+    c = vt.compact_pairs(p)
+    plane = _decode_cpairs(c)
+    for a in range(3):
+        assert (plane[:, a, 0] <= p["l_bounds"][:, 2 * a]).all() and (plane[:, a, 1] >= p["l_bounds"][:, 2 * a + 1]).all()
+        assert (plane[:, a, 2] <= p["r_bounds"][:, 2 * a]).all() and (plane[:, a, 3] >= p["r_bounds"][:, 2 * a + 1]).all()
+        # ... and tight: never more than one grid cell of slack per plane
+        cell = (c["exp"][:, a].astype(np.uint32) << 23).view(np.float32)
+        assert (p["l_bounds"][:, 2 * a] - plane[:, a, 0] < cell).all() and (plane[:, a, 3] - p["r_bounds"][:, 2 * a + 1] < cell).all()
+        # the grid is as fine as 8 bits allow: the pair spans more than 127 cells unless float resolution binds
+        lo = np.minimum(p["l_bounds"][:, 2 * a], p["r_bounds"][:, 2 * a]).astype(np.float64)
+        hi = np.maximum(p["l_bounds"][:, 2 * a + 1], p["r_bounds"][:, 2 * a + 1]).astype(np.float64)
+        ulp_bound = np.maximum(np.abs(lo), np.abs(hi)) / 2.0**22 >= cell
+        assert (((hi - lo) / cell > 127) | ulp_bound | (hi == lo)).all()
+    lcount, rcount = c["counts"] & 15, c["counts"] >> 4
+    nxt = np.arange(1, len(c) + 1, dtype=np.uint32)
+    lfirst = np.where(lcount == 0, nxt, c["ref"])
+    rfirst = np.where(lcount == 0, c["ref"], np.where(rcount == 0, nxt, c["ref"] + lcount))
+    assert (lcount == p["l_count"]).all() and (rcount == p["r_count"]).all()
+    assert (lfirst == p["l_first"]).all() and (rfirst == p["r_first"]).all()
+
+
+def test_compact_pairs_reject_what_they_cannot_hold(built):
+    import vistrace_b200 as vt
+    from vistrace_b200.binding import PAIR
+
+    p = np.zeros(1, PAIR)
+    p["l_count"], p["r_count"], p["l_first"], p["r_first"] = 16, 1, 0, 16
+    with pytest.raises(RuntimeError, match="more than 15"):
+        vt.compact_pairs(p)
+    p["l_count"] = 1
+    p["r_first"] = 1
+    p["l_bounds"][0, 1] = np.inf
+    with pytest.raises(RuntimeError, match="non-finite"):
+        vt.compact_pairs(p)
+    p["l_bounds"][0, 1] = 0
+    p["r_first"] = 5  # both leaves: the right run must follow the left one
+    with pytest.raises(RuntimeError, match="depth-first"):
+        vt.compact_pairs(p)
+
+
+def _tri_hit(t, o, d, tmin, best_t):
+    p0, e1, e2, n = t[0:3], t[3:6], t[6:9], t[9:12]
+    nd = n @ d
+    if nd == 0:
+        return None
+    c = p0 - o
+    rr = np.cross(d, c)
+    u, v = (rr @ e2) / nd, (rr @ e1) / nd
+    tt = (n @ c) / nd
+    return tt if (u >= 0 and v >= 0 and 1 - u - v >= 0 and tmin <= tt <= best_t) else None
+
+
+@pytest.mark.parametrize("scene_name", ["heightfield", "props"])
+def test_quad_layout_structure_and_walk(oracle_mod, scene_name):
+    """The 4-wide layout: every triangle in exactly one leaf run, every quad referenced once, decoded boxes contain
+    the boxes of the binary nodes they replace, and a numpy walk over the quads finds the oracle's hits."""
+    import vistrace_b200 as vt
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_heightfield(40) if scene_name == "heightfield" else scenes.scene_props(4, 13, 9, 8)
+    nodes, prims = vt.build_bvh(scene)
+    qb = vt.build_quads(nodes, prims)
+    quads, order = qb["quads"], qb["leaf_order"]
+    assert sorted(order.tolist()) == list(range(scene.n_tris)) and qb["root_leaf_count"] == 0
+    assert 0 < qb["max_stack"] <= 64 and len(quads) < (len(nodes) - 1) // 2  # fewer, wider nodes
+    valid = (quads["valid"][:, None] >> np.arange(4)) & 1
+    refs = quads["ref"]
+    count, idx = refs >> 28, refs & 0x0FFFFFFF
+    assert (refs[valid == 0] == 0xFFFFFFFF).all() and valid.sum(1).min() >= 2
+    inner = (valid == 1) & (count == 0)
+    assert sorted(idx[inner].tolist()) == list(range(1, len(quads)))  # a tree: each quad but the root referenced once
+    leaf = (valid == 1) & (count > 0)
+    runs = sorted(zip(idx[leaf].tolist(), count[leaf].tolist()))
+    assert runs[0][0] == 0 and all(a + n == b for (a, n), (b, _) in zip(runs, runs[1:])) and runs[-1][0] + runs[-1][1] == scene.n_tris
+    # decoded planes: exact floats on the power-of-two grid
+    scale = (quads["exp"].astype(np.uint32) << 23).view(np.float32).astype(np.float64)                    # [quad, axis]
+    magic = (np.uint32(0x4B000000) | quads["q"].astype(np.uint32)).view(np.float32).astype(np.float64)   # [quad, axis, lo/hi, child]
+    plane = magic * scale[:, :, None, None] + quads["origin_adj"].astype(np.float64)[:, :, None, None]
+    assert (plane.astype(np.float32).astype(np.float64) == plane).all()
+    # leaf children: the decoded box contains every vertex of the run's triangles
+    cpu = oracle_mod.CpuScene(scene, "port", build_bvh=False)
+    cpu.set_bvh(nodes, prims)
+    td = cpu.tri_derived().astype(np.float64)
+    verts = np.stack([td[:, 0:3], td[:, 0:3] - td[:, 3:6], td[:, 0:3] + td[:, 6:9]], 1)                    # p0, p0 - e1, p0 + e2
+    for qi, ci in zip(*np.nonzero(leaf)):
+        v = verts[order[idx[qi, ci]: idx[qi, ci] + count[qi, ci]]].reshape(-1, 3)
+        assert (plane[qi, :, 0, ci] <= v.min(0)).all() and (plane[qi, :, 1, ci] >= v.max(0)).all()
+    # inner children: the decoded box contains the child quad's own decoded children (nesting)
+    for qi, ci in zip(*np.nonzero(inner)):
+        c = idx[qi, ci]
+        cv = valid[c] == 1
+        assert (plane[qi, :, 0, ci] <= plane[c, :, 0][:, cv].min(1)).all() and (plane[qi, :, 1, ci] >= plane[c, :, 1][:, cv].max(1)).all()
+    # walk
+    rays = scenes.random_rays(120, (-45, -45, 0), (45, 45, 40), seed=4)
+    want = cpu.traverse(rays)["hits"]
+    got = np.full(len(rays), 0xFFFFFFFF, np.uint32)
+    for ri, r in enumerate(rays):
+        o, d = r["o"].astype(np.float64), r["d"].astype(np.float64)
+        best_t, stack = float(r["tmax"]), [0]
+        while stack:
+            ref = stack.pop()
+            if ref >> 28:
+                for s in range(ref & 0x0FFFFFFF, (ref & 0x0FFFFFFF) + (ref >> 28)):
+                    tt = _tri_hit(td[order[s]], o, d, r["tmin"], best_t)
+                    if tt is not None:
+                        best_t, got[ri] = tt, order[s]
+                continue
+            for ci in range(4):
+                if not valid[ref, ci]:
+                    continue
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    t0, t1 = (plane[ref, :, 0, ci] - o) / d, (plane[ref, :, 1, ci] - o) / d
+                lo, hi = np.nanmax(np.minimum(t0, t1)), np.nanmin(np.maximum(t0, t1))
+                if max(lo, r["tmin"]) <= min(hi, best_t) * (1 + 1e-6) + 1e-6:
+                    stack.append(int(refs[ref, ci]))
+    assert (got == want["prim"]).mean() > 0.98 and ((got == abi.VT_MISS) == (want["prim"] == abi.VT_MISS)).mean() > 0.98

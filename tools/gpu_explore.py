@@ -75,11 +75,14 @@ def main():
             d_rays, d_bounce = to_dev(rays), to_dev(bounce)
             d_hits = torch.empty(max(len(rays), len(bounce)) * 16, dtype=torch.uint8, device="cuda")
             d_attrs = torch.empty(len(rays) * 128, dtype=torch.uint8, device="cuda")
+        st_p = accel.traverse_stats(d_rays.data_ptr(), len(rays))
+        st_b = accel.traverse_stats(d_bounce.data_ptr(), len(bounce))
         ms_p = time_traverse(accel, d_rays, len(rays), d_hits)
         ms_b = time_traverse(accel, d_bounce, len(bounce), d_hits)
         ms_a = time_traverse(accel, d_bounce, len(bounce), d_hits, any_hit=True)
         ms_pa = time_traverse(accel, d_rays, len(rays), d_hits, d_attrs=d_attrs)
-        print(json.dumps({"knobs": knobs, "upload_s": round(t_up, 2), "primary_Mrays": round(len(rays) / ms_p / 1e3, 1),
+        print(json.dumps({"knobs": knobs, "layout": accel.layout, "S_I_primary": [round(st_p[0] / len(rays), 2), round(st_p[1] / len(rays), 2)],
+                          "S_I_bounce": [round(st_b[0] / len(bounce), 2), round(st_b[1] / len(bounce), 2)], "upload_s": round(t_up, 2), "primary_Mrays": round(len(rays) / ms_p / 1e3, 1),
                           "bounce_Mrays": round(len(bounce) / ms_b / 1e3, 1), "bounce_anyhit_Mrays": round(len(bounce) / ms_a / 1e3, 1),
                           "primary+attrs_Mrays": round(len(rays) / ms_pa / 1e3, 1), "ms": [round(ms_p, 3), round(ms_b, 3), round(ms_a, 3), round(ms_pa, 3)]}), flush=True)
         accel.close()

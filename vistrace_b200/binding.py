@@ -26,11 +26,16 @@ SYMBOLS = {
     "vt_accel_populate_with_bvh": (_i32, [_vp, _vp, _vp, _u64, _vp]),
     "vt_accel_get_bvh": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "vt_accel_traverse": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32, _vp]),
+    "vt_accel_traverse_stats": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp]),
     "vt_accel_traverse_cones": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_result": (_i32, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "vt_accel_bounce_rays": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "vt_accel_accumulate_sky": (_i32, [_vp, _vp, _vp, _u64, _u32, C.c_float, _vp, _vp]),
+    "vt_accel_set_layout": (_i32, [_vp, _i32]),
+    "vt_accel_get_layout": (_i32, [_vp]),
+    "vt_compact_pairs": (_i32, [_vp, _u64, _vp]),
+    "vt_build_quads": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_invalid_rays": (_u64, [_vp]),
     "vt_accel_launch_count": (_u64, [_vp]),
     "vt_accel_stats": (_i32, [_vp, _vp, _vp, _vp]),
@@ -118,15 +123,56 @@ def flatten_bvh(nodes, prim_indices, bfs_pairs=384):
     return {"pairs": pairs, "leaf_order": order, "root_leaf_count": rl.value, "max_depth": md.value}
 
 
+CPAIR = np.dtype([("origin_adj", np.float32, 3), ("exp", np.uint8, 3), ("counts", np.uint8), ("q", np.uint8, (3, 4)), ("ref", np.uint32)])
+assert PAIR.itemsize == 64 and CPAIR.itemsize == 32
+
+
+def compact_pairs(pairs):
+    """Host-only: depth-first 64-byte pairs -> 32-byte conservative compact pairs."""
+    pairs = np.ascontiguousarray(pairs, PAIR)
+    out = np.zeros(len(pairs), CPAIR)
+    _check(lib().vt_compact_pairs(pairs.ctypes.data, len(pairs), out.ctypes.data), "vt_compact_pairs")
+    return out
+
+
+QUAD = np.dtype([("origin_adj", np.float32, 3), ("exp", np.uint8, 3), ("valid", np.uint8), ("q", np.uint8, (3, 2, 4)), ("pad", np.uint32, 2),
+                 ("ref", np.uint32, 4)])
+assert QUAD.itemsize == 64
+
+
+def build_quads(nodes, prim_indices):
+    """Host-only: binary hierarchy -> dict(quads, leaf_order, root_leaf_count, max_stack) of the 4-wide layout."""
+    L = lib()
+    nodes = np.ascontiguousarray(nodes, abi.NODE)
+    prim_indices = np.ascontiguousarray(prim_indices, np.uint64)
+    cnt = C.c_uint64(0)
+    args = (nodes.ctypes.data, len(nodes), prim_indices.ctypes.data, len(prim_indices))
+    _check(L.vt_build_quads(*args, None, C.addressof(cnt), None, None, None), "vt_build_quads")
+    quads = np.zeros(cnt.value, QUAD)
+    order = np.zeros(len(prim_indices), np.uint32)
+    rl, ms = C.c_uint32(0), C.c_uint32(0)
+    _check(L.vt_build_quads(*args, quads.ctypes.data, C.addressof(cnt), order.ctypes.data, C.addressof(rl), C.addressof(ms)), "vt_build_quads")
+    return {"quads": quads, "leaf_order": order, "root_leaf_count": rl.value, "max_stack": ms.value}
+
+
 class Accel:
     """vt_accel handle: the AccelStruct of source/objects/AccelStruct.h:61-86 bound to one GPU."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, layout=None):
+        """layout: "compact" (32-byte conservative pairs, default), "exact" (the reference's nodes verbatim), or
+        None = the library default (VT_LAYOUT in the environment, else compact)."""
         self.L = lib()
         self.h = self.L.vt_accel_create(device)
         if not self.h:
             raise RuntimeError(f"vt_accel_create: {_err()}")
         self.scene = None
+        if layout is not None:
+            _check(self.L.vt_accel_set_layout(self.h, {"exact": 0, "compact": 1, "quad": 2}[layout]), "vt_accel_set_layout")
+
+    @property
+    def layout(self):
+        """Layout resident after populate ("compact" falls back to "exact" for trees it cannot hold)."""
+        return ("exact", "compact", "quad")[self.L.vt_accel_get_layout(self.h)]
 
     def close(self):
         if getattr(self, "h", None):
@@ -177,6 +223,17 @@ class Accel:
                                                 _ptr(attrs), flags, None)
         _check(rc, "vt_accel_traverse")
         return (hits, attrs) if want_attrs else hits
+
+    def traverse_stats(self, rays, n=None):
+        """(pair visits, triangle tests) summed over the batch; rays = numpy array or (device pointer, n)."""
+        steps, tests = C.c_uint64(0), C.c_uint64(0)
+        if isinstance(rays, np.ndarray):
+            rays = np.ascontiguousarray(rays, abi.RAY)
+            n, flags = len(rays), 0
+        else:
+            flags = abi.VT_TRAVERSE_DEVICE_PTRS
+        _check(self.L.vt_accel_traverse_stats(self.h, _ptr(rays), n, flags, C.addressof(steps), C.addressof(tests)), "vt_accel_traverse_stats")
+        return steps.value, tests.value
 
     def traverse_device(self, d_rays, n, d_hits, d_attrs=None, any_hit=False, stream=None):
         """Device-pointer call (ints = CUDA device addresses): enqueues on `stream` and returns."""

@@ -96,7 +96,9 @@ struct DevBuf {
 constexpr int kCounterSlots = 256;  // 16-byte {queue head, invalid rays} records, one per in-flight call
 
 struct DeviceScene {
-    DevBuf<VtPair> pairs;
+    DevBuf<VtPair> pairs;    // exact layout  \ one of the two is resident
+    DevBuf<VtCPair> cpairs;  // compact layout  | exactly one of the three is resident
+    DevBuf<VtQuad> quads;    // quad layout    /
     DevBuf<VtTriRec> tris;
     DevBuf<float> tri_uv;
     DevBuf<VtTriAttr> attrs;
@@ -105,6 +107,7 @@ struct DeviceScene {
     DevBuf<VtDevTexture> texs;
     DevBuf<uint8_t> texels;
     DevBuf<unsigned long long> counters;
+    DevBuf<unsigned long long> stat_counters;
     // staging for host-pointer calls
     DevBuf<vt_ray> s_rays;
     DevBuf<vt_hit> s_hits;
@@ -126,6 +129,8 @@ struct DeviceScene {
 
     ~DeviceScene() {
         pairs.release();
+        cpairs.release();
+        quads.release();
         tris.release();
         tri_uv.release();
         attrs.release();
@@ -134,6 +139,7 @@ struct DeviceScene {
         texs.release();
         texels.release();
         counters.release();
+        stat_counters.release();
         s_rays.release();
         s_hits.release();
         s_attrs.release();
@@ -150,13 +156,20 @@ struct DeviceScene {
         if (own_stream) cudaStreamDestroy(own_stream);
     }
     uint64_t scene_bytes() const {
-        return pairs.bytes() + tris.bytes() + tri_uv.bytes() + attrs.bytes() + mats.bytes() + ents.bytes() + texs.bytes() +
+        return pairs.bytes() + cpairs.bytes() + quads.bytes() + tris.bytes() + tri_uv.bytes() + attrs.bytes() + mats.bytes() + ents.bytes() + texs.bytes() +
                texels.bytes();
     }
 };
 
 // ----------------------------------------------------------------------------- AccelStruct
 AccelStruct::AccelStruct(int device) : mDevice(device) {
+    if (const char *v = std::getenv("VT_LAYOUT")) {  // default for handles that do not call SetLayout
+        const std::string l(v);
+        if (l == "exact") mWantLayout = VT_LAYOUT_EXACT;
+        else if (l == "compact") mWantLayout = VT_LAYOUT_COMPACT;
+        else if (l == "quad") mWantLayout = VT_LAYOUT_QUAD;
+        else if (!l.empty()) throw std::runtime_error("VT_LAYOUT must be 'exact', 'compact' or 'quad'");
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -230,12 +243,29 @@ void AccelStruct::Upload(const vt_scene &scene) {
     D.cfg.tri_threshold = env_int("VT_TRI_ROUND", D.cfg.tri_threshold);
     const size_t n = mTriangles.size();
 
-    // how many leading pairs fit the shared-memory budget of one CTA
-    uint32_t smem_pairs = (uint32_t)env_int("VT_SMEM_PAIRS", 0);
+    // Node layout (include/vistrace_b200.h: VT_LAYOUT_*).  A tree the quantised layouts cannot hold (a leaf of
+    // more than 15 triangles, non-finite bounds, too deep) falls back to the exact layout.
+    int layout = mWantLayout;
+    uint32_t smem_pairs = layout == VT_LAYOUT_EXACT ? (uint32_t)env_int("VT_SMEM_PAIRS", 0) : 0u;  // exact only: breadth-first prefix staged in smem
     FlatBvh flat;
+    QuadBvh quad;
+    std::vector<VtCPair> cpairs;
     std::string err;
-    if (!flatten_bvh(mAccel, n, smem_pairs, flat, err)) throw std::runtime_error(err);
-    smem_pairs = (uint32_t)std::min<size_t>(smem_pairs, flat.pairs.size());
+    if (layout == VT_LAYOUT_QUAD && !build_quads(mAccel, n, quad, err)) layout = VT_LAYOUT_EXACT;
+    if (layout != VT_LAYOUT_QUAD) {
+        if (!flatten_bvh(mAccel, n, smem_pairs, flat, err)) throw std::runtime_error(err);
+        smem_pairs = (uint32_t)std::min<size_t>(smem_pairs, flat.pairs.size());
+        // tagged references (vt_traverse.cu): 4 bits of leaf count + 28 bits of pair index / triangle slot
+        if (n >= (1u << 28) - 16 || flat.pairs.size() >= (1u << 28) - 16 || flat.root_leaf_count > 15) layout = VT_LAYOUT_EXACT;
+        if (layout == VT_LAYOUT_COMPACT && !compact_pairs(flat.pairs, cpairs, err)) {
+            layout = VT_LAYOUT_EXACT;
+            cpairs.clear();
+        }
+    }
+    mLayout = layout;
+    const std::vector<uint32_t> &leaf_order = layout == VT_LAYOUT_QUAD ? quad.leaf_order : flat.leaf_order;
+    const uint32_t root_leaf_count = layout == VT_LAYOUT_QUAD ? quad.root_leaf_count : flat.root_leaf_count;
+    const uint32_t n_inner = layout == VT_LAYOUT_QUAD ? (uint32_t)quad.quads.size() : (uint32_t)flat.pairs.size();
 
     // leaf-order geometry records + UVs; original-order attribute records
     std::vector<VtTriRec> recs(n);
@@ -244,7 +274,7 @@ void AccelStruct::Upload(const vt_scene &scene) {
     uint32_t any_alpha = 0;
 #pragma omp parallel for reduction(| : any_alpha)
     for (int64_t s = 0; s < (int64_t)n; s++) {
-        const uint32_t orig = flat.leaf_order[s];
+        const uint32_t orig = leaf_order[s];
         const Triangle &t = mTriangles[orig];
         const Material &m = mMaterials[t.material];
         VtTriRec &r = recs[s];
@@ -342,7 +372,12 @@ void AccelStruct::Upload(const vt_scene &scene) {
     const uint8_t white[4] = {255, 255, 255, 255};
     add_texture(dt[scene.n_textures], 1, 1, 1, 0, white, 4);
 
-    D.pairs.upload(flat.pairs.data(), flat.pairs.size());
+    D.pairs.release();
+    D.cpairs.release();
+    D.quads.release();
+    if (layout == VT_LAYOUT_QUAD) D.quads.upload(quad.quads.data(), quad.quads.size());
+    else if (layout == VT_LAYOUT_COMPACT) D.cpairs.upload(cpairs.data(), cpairs.size());
+    else D.pairs.upload(flat.pairs.data(), flat.pairs.size());
     D.tris.upload(recs.data(), n);
     D.tri_uv.upload(uv.data(), uv.size());
     D.attrs.upload(attrs.data(), n);
@@ -352,7 +387,9 @@ void AccelStruct::Upload(const vt_scene &scene) {
     D.texels.upload(texels.data(), texels.size());
 
     VtSceneView &V = D.view;
-    V.pairs = D.pairs.p;
+    V.pairs = layout == VT_LAYOUT_EXACT ? D.pairs.p : nullptr;
+    V.cpairs = layout == VT_LAYOUT_COMPACT ? D.cpairs.p : nullptr;
+    V.quads = layout == VT_LAYOUT_QUAD ? D.quads.p : nullptr;
     V.tris = D.tris.p;
     V.tri_uv = D.tri_uv.p;
     V.attrs = D.attrs.p;
@@ -360,15 +397,16 @@ void AccelStruct::Upload(const vt_scene &scene) {
     V.ents = D.ents.p;
     V.texs = D.texs.p;
     V.texels = D.texels.p;
-    V.n_pairs = (uint32_t)flat.pairs.size();
+    V.n_pairs = n_inner;
     V.n_tris = (uint32_t)n;
-    V.root_leaf_count = flat.root_leaf_count;
+    V.root_leaf_count = root_leaf_count;
     V.n_smem_pairs = smem_pairs;
     V.has_alphatest = any_alpha ? 1u : 0u;
     V.fallback_tex = scene.n_textures;
+    V.magic = 0x4B000000u;
 
     int blocks = 0;
-    VT_CUDA(vt_traverse_occupancy(&blocks, (size_t)smem_pairs * sizeof(VtPair)));
+    VT_CUDA(vt_traverse_occupancy(&blocks, (size_t)smem_pairs * sizeof(VtPair), layout));
     if (blocks < 1) blocks = 1;
     const int mult = env_int("VT_GRID_BLOCKS_PER_SM", blocks);
     D.cfg.grid = D.sm_count * std::max(1, std::min(mult, blocks));
@@ -404,6 +442,8 @@ void AccelStruct::TraverseBatch(const vt_ray *rays, uint64_t n, vt_hit *hits, vt
     DeviceScene &D = *mpDevice;
     const bool dev_ptrs = (flags & VT_TRAVERSE_DEVICE_PTRS) != 0;
     const bool any_hit = (flags & VT_TRAVERSE_ANY_HIT) != 0;
+    if (dev_ptrs && (((uintptr_t)rays & 31) || ((uintptr_t)hits & 15)))
+        throw std::runtime_error("traverse: device ray buffers must be 32-byte aligned and hit buffers 16-byte aligned");
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : (dev_ptrs ? (cudaStream_t) nullptr : D.own_stream);
     const uint32_t slot = D.next_slot.fetch_add(1) % kCounterSlots;
     unsigned long long *ctr = D.counters.p + 2 * slot;
@@ -443,6 +483,36 @@ void AccelStruct::TraverseBatch(const vt_ray *rays, uint64_t n, vt_hit *hits, vt
         VT_CUDA(cudaStreamSynchronize(stream));
         mInvalidRays = invalid[1];
     }
+}
+
+void AccelStruct::TraverseStats(const vt_ray *rays, uint64_t n, uint32_t flags, uint64_t *steps, uint64_t *tests) {
+    check_built(mAccelBuilt);
+    if (steps) *steps = 0;
+    if (tests) *tests = 0;
+    if (n == 0) return;
+    if (!rays) throw std::runtime_error("traverse_stats: rays must not be null");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    if (D.view.n_smem_pairs) throw std::runtime_error("traverse_stats: not available with VT_SMEM_PAIRS");
+    cudaStream_t stream = D.own_stream;
+    D.stat_counters.ensure(4);
+    VT_CUDA(cudaMemsetAsync(D.stat_counters.p, 0, 4 * sizeof(unsigned long long), stream));
+    const vt_ray *d_rays = rays;
+    D.s_hits.ensure(n);
+    if (!(flags & VT_TRAVERSE_DEVICE_PTRS)) {
+        D.s_rays.ensure(n);
+        VT_CUDA(cudaMemcpyAsync(D.s_rays.p, rays, n * sizeof(vt_ray), cudaMemcpyHostToDevice, stream));
+        d_rays = D.s_rays.p;
+    } else {
+        VT_CUDA(cudaDeviceSynchronize());  // the caller's stream may still be producing the rays
+    }
+    VT_CUDA(vt_launch_traverse(D.view, d_rays, D.s_hits.p, n, false, D.stat_counters.p, D.cfg, stream, true));
+    mLaunches++;
+    unsigned long long c[4];
+    VT_CUDA(cudaMemcpyAsync(c, D.stat_counters.p, sizeof(c), cudaMemcpyDeviceToHost, stream));
+    VT_CUDA(cudaStreamSynchronize(stream));
+    if (steps) *steps = c[2];
+    if (tests) *tests = c[3];
 }
 
 void AccelStruct::TraceResultBatch(const vt_ray *rays, const vt_hit *hits, uint64_t n, vt_attr *attrs, const float *cones,
@@ -727,6 +797,25 @@ int vt_accel_accumulate_sky(vt_accel *a, const vt_attr *attrs, const vt_hit *bou
     VT_CATCH(1)
 }
 
+int vt_accel_set_layout(vt_accel *a, int layout) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    if (layout != VT_LAYOUT_EXACT && layout != VT_LAYOUT_COMPACT && layout != VT_LAYOUT_QUAD) throw std::runtime_error("unknown layout");
+    a->impl.SetLayout(layout);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_get_layout(const vt_accel *a) { return a ? a->impl.Layout() : VT_LAYOUT_EXACT; }
+
+int vt_accel_traverse_stats(vt_accel *a, const vt_ray *rays, uint64_t n, uint32_t flags, uint64_t *steps, uint64_t *tests) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.TraverseStats(rays, n, flags, steps, tests);
+    return 0;
+    VT_CATCH(1)
+}
+
 uint64_t vt_accel_invalid_rays(const vt_accel *a) { return a ? a->impl.InvalidRays() : 0; }
 uint64_t vt_accel_launch_count(const vt_accel *a) { return a ? a->impl.Launches() : 0; }
 
@@ -800,6 +889,40 @@ int vt_flatten_bvh(const vt_node *nodes, uint64_t node_count, const uint64_t *pr
     if (leaf_order_out) std::memcpy(leaf_order_out, flat.leaf_order.data(), flat.leaf_order.size() * sizeof(uint32_t));
     if (root_leaf_count) *root_leaf_count = flat.root_leaf_count;
     if (max_depth) *max_depth = flat.max_depth;
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_build_quads(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris, void *quads_out,
+                   uint64_t *n_quads, uint32_t *leaf_order_out, uint32_t *root_leaf_count, uint32_t *max_stack) {
+    VT_TRY
+    if (!nodes || !prim_indices || !n_quads) throw std::runtime_error("null argument");
+    vt::HostBvh bvh;
+    bvh.nodes.assign(nodes, nodes + node_count);
+    bvh.prim_indices.assign(prim_indices, prim_indices + n_tris);
+    vt::QuadBvh q;
+    std::string err;
+    if (!vt::build_quads(bvh, n_tris, q, err)) throw std::runtime_error(err);
+    if (quads_out) {
+        if (*n_quads < q.quads.size()) throw std::runtime_error("quad buffer too small");
+        std::memcpy(quads_out, q.quads.data(), q.quads.size() * sizeof(VtQuad));
+        if (leaf_order_out) std::memcpy(leaf_order_out, q.leaf_order.data(), q.leaf_order.size() * sizeof(uint32_t));
+    }
+    *n_quads = q.quads.size();
+    if (root_leaf_count) *root_leaf_count = q.root_leaf_count;
+    if (max_stack) *max_stack = q.max_stack;
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_compact_pairs(const void *pairs, uint64_t n_pairs, void *cpairs_out) {
+    VT_TRY
+    if (!pairs || !cpairs_out) throw std::runtime_error("null argument");
+    std::vector<VtPair> in((const VtPair *)pairs, (const VtPair *)pairs + n_pairs);
+    std::vector<VtCPair> out;
+    std::string err;
+    if (!vt::compact_pairs(in, out, err)) throw std::runtime_error(err);
+    std::memcpy(cpairs_out, out.data(), out.size() * sizeof(VtCPair));
     return 0;
     VT_CATCH(1)
 }

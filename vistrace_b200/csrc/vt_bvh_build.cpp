@@ -388,4 +388,264 @@ bool flatten_bvh(const HostBvh &bvh, uint64_t n_tris, uint32_t bfs_pairs, FlatBv
     return true;
 }
 
+// ------------------------------------------------------------------------------------ compact
+// VtPair[] (depth-first order, bfs_pairs = 0) -> VtCPair[]: see vt_device.h.  Returns false (with a
+// reason) when the tree cannot be represented: a leaf of more than 15 triangles, a non-finite
+// bound, or a child reference that is not where the depth-first order puts it.
+namespace {
+
+// Smallest power-of-two grid 2^E on which [lo, hi] spans <= 255 cells from k = floor(lo / 2^E), with
+// |k| small enough that (k - 2^23) * 2^E and (k + q) * 2^E are exact floats.
+bool choose_grid(double lo, double hi, int &E, int64_t &k) {
+    const double kmax = 8388608.0 - 512.0;
+    const double mag = std::max(std::fabs(lo), std::fabs(hi));
+    int e = -149;
+    if (hi > lo) e = std::max(e, (int)std::ceil(std::log2((hi - lo) / 255.0)) - 1);
+    if (mag > 0) e = std::max(e, (int)std::floor(std::log2(mag)) - 23);
+    e = std::max(e, -126);  // 2^E must be a normal float (biased exponent 1..254)
+    for (; e <= 100; e++) {  // (2^23 + q) * 2^E must stay finite
+        const double s = std::ldexp(1.0, e);
+        const double kl = std::floor(lo / s), kh = std::ceil(hi / s);
+        if (kh - kl <= 255.0 && std::fabs(kl) <= kmax && std::fabs(kh) <= kmax) {
+            E = e;
+            k = (int64_t)kl;
+            return true;
+        }
+    }
+    return false;
+}
+
+}  // namespace
+
+bool compact_pairs(const std::vector<VtPair> &pairs, std::vector<VtCPair> &out, std::string &err) {
+    out.resize(pairs.size());
+    std::atomic<int> fail{0};
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)pairs.size(); i++) {
+        const VtPair &p = pairs[i];
+        VtCPair &c = out[i];
+        if (p.l.count > 15 || p.r.count > 15) {
+            fail = 1;
+            continue;
+        }
+        bool ok = true;
+        for (int a = 0; a < 3 && ok; a++) {
+            const float llo = p.l.bounds[2 * a], lhi = p.l.bounds[2 * a + 1];
+            const float rlo = p.r.bounds[2 * a], rhi = p.r.bounds[2 * a + 1];
+            if (!(std::isfinite(llo) && std::isfinite(lhi) && std::isfinite(rlo) && std::isfinite(rhi)) || lhi < llo || rhi < rlo) {
+                ok = false;
+                break;
+            }
+            int E;
+            int64_t k;
+            if (!choose_grid(std::min(llo, rlo), std::max(lhi, rhi), E, k)) {
+                ok = false;
+                break;
+            }
+            const double s = std::ldexp(1.0, E);
+            c.origin_adj[a] = (float)((double)(k - 8388608) * s);  // exact: |k - 2^23| < 2^24
+            c.exp[a] = (uint8_t)(E + 127);
+            c.q[a][0] = (uint8_t)((int64_t)std::floor(llo / s) - k);
+            c.q[a][1] = (uint8_t)((int64_t)std::ceil(lhi / s) - k);
+            c.q[a][2] = (uint8_t)((int64_t)std::floor(rlo / s) - k);
+            c.q[a][3] = (uint8_t)((int64_t)std::ceil(rhi / s) - k);
+        }
+        if (!ok) {
+            fail = 2;
+            continue;
+        }
+        c.counts = (uint8_t)(p.l.count | (p.r.count << 4));
+        const bool li = p.l.count == 0, ri = p.r.count == 0;
+        const uint32_t next = (uint32_t)i + 1;
+        if (li) {
+            if (p.l.first != next) fail = 3;
+            c.ref = p.r.first;
+        } else {
+            c.ref = p.l.first;
+            if (ri ? p.r.first != next : p.r.first != p.l.first + p.l.count) fail = 3;
+        }
+    }
+    switch (fail.load()) {
+        case 1: err = "compact layout: a leaf holds more than 15 triangles"; return false;
+        case 2: err = "compact layout: non-finite or inverted bounds, or coordinates out of float grid range"; return false;
+        case 3: err = "compact layout: pairs are not in depth-first order"; return false;
+    }
+    return true;
+}
+
+// --------------------------------------------------------------------------------------- quads
+namespace {
+
+struct QuadBuilder {
+    const HostBvh &bvh;
+    uint64_t n_tris;
+    QuadBvh &out;
+    std::string &err;
+    bool ok = true;
+
+    static float half_area(const vt_node &n) {
+        const float dx = n.bounds[1] - n.bounds[0], dy = n.bounds[3] - n.bounds[2], dz = n.bounds[5] - n.bounds[4];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    bool fail(const char *why) {
+        if (ok) err = why;
+        ok = false;
+        return false;
+    }
+
+    // Emit the quad that replaces binary inner node `ni`; returns its index, *need = worst-case stack entries below it.
+    uint32_t emit(uint32_t ni, uint32_t depth, uint32_t *need) {
+        const size_t node_count = bvh.nodes.size();
+        uint32_t kids[4];
+        int nk = 2;
+        kids[0] = bvh.nodes[ni].first;
+        kids[1] = kids[0] + 1;
+        if (kids[0] == 0 || (size_t)kids[1] >= node_count || depth > 64) {
+            fail("quad layout: malformed hierarchy");
+            *need = 0;
+            return 0;
+        }
+        while (nk < 4) {  // adopt the children of the inner child with the largest box
+            int best = -1;
+            float best_area = -1.f;
+            for (int i = 0; i < nk; i++) {
+                const vt_node &c = bvh.nodes[kids[i]];
+                if (c.prim_count == 0 && half_area(c) > best_area) {
+                    best_area = half_area(c);
+                    best = i;
+                }
+            }
+            if (best < 0) break;
+            const uint32_t f = bvh.nodes[kids[best]].first;
+            if (f == 0 || (size_t)f + 1 >= node_count) {
+                fail("quad layout: malformed hierarchy");
+                break;
+            }
+            for (int i = nk; i > best + 1; i--) kids[i] = kids[i - 1];  // keep left-to-right order
+            kids[best] = f;
+            kids[best + 1] = f + 1;
+            nk++;
+        }
+        const uint32_t qi = (uint32_t)out.quads.size();
+        if (out.quads.size() > bvh.nodes.size()) {  // not a tree: a node is reachable twice
+            fail("BVH is not a tree (a node pair is referenced twice)");
+            *need = 0;
+            return 0;
+        }
+        out.quads.emplace_back();
+        VtQuad q;
+        std::memset(&q, 0, sizeof(q));
+        // shared grid over the union of the children
+        for (int a = 0; a < 3 && ok; a++) {
+            double lo = 1e300, hi = -1e300;
+            for (int i = 0; i < nk; i++) {
+                const vt_node &c = bvh.nodes[kids[i]];
+                if (!(std::isfinite(c.bounds[2 * a]) && std::isfinite(c.bounds[2 * a + 1])) || c.bounds[2 * a + 1] < c.bounds[2 * a])
+                    fail("quad layout: non-finite or inverted bounds");
+                lo = std::min(lo, (double)c.bounds[2 * a]);
+                hi = std::max(hi, (double)c.bounds[2 * a + 1]);
+            }
+            int E = 0;
+            int64_t k = 0;
+            if (ok && !choose_grid(lo, hi, E, k)) fail("quad layout: coordinates out of float grid range");
+            if (!ok) break;
+            const double s = std::ldexp(1.0, E);
+            q.origin_adj[a] = (float)((double)(k - 8388608) * s);
+            q.exp[a] = (uint8_t)(E + 127);
+            for (int i = 0; i < 4; i++) {
+                if (i < nk) {
+                    const vt_node &c = bvh.nodes[kids[i]];
+                    q.q[a][0][i] = (uint8_t)((int64_t)std::floor(c.bounds[2 * a] / s) - k);
+                    q.q[a][1][i] = (uint8_t)((int64_t)std::ceil(c.bounds[2 * a + 1] / s) - k);
+                } else {
+                    q.q[a][0][i] = 255;  // empty slot: inverted box (and valid bit clear)
+                    q.q[a][1][i] = 0;
+                }
+            }
+        }
+        // leaves first (their triangles sit next to each other), then the inner children, depth-first
+        for (int i = 0; i < 4; i++) q.ref[i] = 0xFFFFFFFFu;
+        for (int i = 0; i < nk && ok; i++) {
+            const vt_node &c = bvh.nodes[kids[i]];
+            q.valid |= (uint8_t)(1u << i);
+            if (c.prim_count == 0) continue;
+            if (c.prim_count > 15) {
+                fail("quad layout: a leaf holds more than 15 triangles");
+                break;
+            }
+            if ((uint64_t)c.first + c.prim_count > n_tris) {
+                fail("BVH leaf addresses primitives past the end of prim_indices");
+                break;
+            }
+            q.ref[i] = (c.prim_count << 28) | (uint32_t)out.leaf_order.size();
+            for (uint32_t t = 0; t < c.prim_count; t++) {
+                const uint64_t p = bvh.prim_indices[c.first + t];
+                if (p >= n_tris) {
+                    fail("BVH primitive index out of range");
+                    break;
+                }
+                out.leaf_order.push_back((uint32_t)p);
+            }
+        }
+        uint32_t below = 0;
+        for (int i = 0; i < nk && ok; i++) {
+            if (bvh.nodes[kids[i]].prim_count != 0) continue;
+            uint32_t n = 0;
+            q.ref[i] = emit(kids[i], depth + 1, &n);
+            below = std::max(below, n);
+        }
+        *need = (uint32_t)(nk - 1) + below;  // while a child is being walked, up to nk - 1 siblings are pending
+        out.quads[qi] = q;
+        return qi;
+    }
+};
+
+}  // namespace
+
+bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string &err) {
+    out.quads.clear();
+    out.leaf_order.clear();
+    out.root_leaf_count = 0;
+    out.max_stack = 0;
+    if (bvh.nodes.empty() || n_tris == 0) return true;
+    if (n_tris >= (1ull << 28) - 16 || bvh.nodes.size() >= (1ull << 28) - 16) {
+        err = "quad layout: more than 2^28 triangles or nodes";
+        return false;
+    }
+    const vt_node &root = bvh.nodes[0];
+    out.leaf_order.reserve(n_tris);
+    if (root.prim_count != 0) {
+        if (root.prim_count > 15 || (uint64_t)root.first + root.prim_count > n_tris) {
+            err = "quad layout: the root leaf holds more than 15 triangles";
+            return false;
+        }
+        for (uint32_t t = 0; t < root.prim_count; t++) out.leaf_order.push_back((uint32_t)bvh.prim_indices[root.first + t]);
+        out.root_leaf_count = root.prim_count;
+        return out.leaf_order.size() == n_tris;
+    }
+    out.quads.reserve(bvh.nodes.size() / 3 + 1);
+    QuadBuilder b{bvh, n_tris, out, err};
+    uint32_t need = 0;
+    b.emit(0, 0, &need);
+    if (!b.ok) return false;
+    out.max_stack = need;
+    if (out.leaf_order.size() != n_tris) {
+        err = "BVH leaves do not cover every primitive exactly once";
+        return false;
+    }
+    std::vector<uint8_t> seen(n_tris, 0);
+    for (uint32_t p : out.leaf_order) {
+        if (seen[p]) {
+            err = "BVH leaves do not cover every primitive exactly once";
+            return false;
+        }
+        seen[p] = 1;
+    }
+    if (need > VT_STACK_SIZE) {
+        err = "quad layout: worst-case traversal stack deeper than 64 entries";
+        return false;
+    }
+    return true;
+}
+
 }  // namespace vt

@@ -32,6 +32,40 @@ struct alignas(64) VtPair {
 };
 static_assert(sizeof(VtPair) == 64, "pair layout");
 
+// Compact sibling pair: the same two children in ONE 32-byte sector (one LDG.E.256 per traversal
+// step instead of two).  The boxes are quantised to 8 bits per plane on a per-pair power-of-two grid
+// and are CONSERVATIVE: plane' = (k + q) * 2^E with lo' <= lo and hi' >= hi, decoded exactly (no
+// rounding) by ONE fma:  fmaf(as_float(0x4B000000 | q), 2^E, origin_adj),  origin_adj = (k - 2^23) * 2^E.
+// Because fmaf(plane, inv_dir, scaled_origin) is monotone in `plane`, every node the reference's
+// FastNodeIntersector accepts (node_intersectors.hpp:35-47) is accepted here too; only the ORDER of
+// equal-distance visits can differ, i.e. which of two exactly tied candidates wins.
+// Needs the depth-first pair order of flatten_bvh (bfs_pairs = 0) and leaves of <= 15 triangles:
+//   left child inner  -> its pair is cur + 1, `ref` belongs to the right child (pair index or triangle slot)
+//   left child leaf   -> `ref` is its triangle slot; right child = pair cur + 1 (inner) or slot ref + lcount (leaf)
+struct alignas(32) VtCPair {
+    float origin_adj[3];  // (k - 2^23) * 2^E per axis
+    uint8_t exp[3];       // biased exponent of 2^E per axis
+    uint8_t counts;       // lcount | rcount << 4; 0 = inner child
+    uint8_t q[3][4];      // per axis: {l.lo, l.hi, r.lo, r.hi}
+    uint32_t ref;
+};
+static_assert(sizeof(VtCPair) == 32, "compact pair layout");
+
+// Quad node: a 4-wide hierarchy obtained by collapsing the binary tree (each node adopts its
+// grandchildren, largest box first), so a ray needs about half as many dependent node fetches.  Same
+// conservative power-of-two grid as VtCPair, shared by the four children; 64 bytes = two LDG.E.256.
+// Children are TAGGED references: bits 28-31 = triangle count (0 = inner quad), bits 0-27 = quad index
+// or first triangle slot; empty slots have valid bit 0 and ref 0xFFFFFFFF.
+struct alignas(64) VtQuad {
+    float origin_adj[3];  // (k - 2^23) * 2^E per axis
+    uint8_t exp[3];       // biased exponent of 2^E per axis
+    uint8_t valid;        // bit i: child i exists
+    uint8_t q[3][2][4];   // [axis][lo, hi][child]
+    uint32_t pad[2];
+    uint32_t ref[4];
+};
+static_assert(sizeof(VtQuad) == 64, "quad layout");
+
 struct alignas(64) VtTriRec {
     float p0[3];
     float e1[3];
@@ -84,7 +118,9 @@ struct VtDevEntity {
 
 // Kernel argument block (passed by value).
 struct VtSceneView {
-    const VtPair *pairs;
+    const VtPair *pairs;     // exact layout (nullptr when the compact layout is resident)
+    const VtCPair *cpairs;   // compact layout (nullptr when the exact layout is resident)
+    const VtQuad *quads;     // quad layout (nullptr unless resident)
     const VtTriRec *tris;
     const float *tri_uv;  // 6 floats per leaf-order triangle
     const VtTriAttr *attrs;
@@ -98,4 +134,5 @@ struct VtSceneView {
     uint32_t n_smem_pairs;     // leading pairs staged in shared memory by the traversal kernel
     uint32_t has_alphatest;    // any triangle carries VT_TRI_FLAG_ALPHATEST
     uint32_t fallback_tex;     // index of the 1x1 white stand-in for a null baseTexture
+    uint32_t magic;            // 0x4B000000 (2^23 as float bits), a constant-bank operand of the compact decode
 };

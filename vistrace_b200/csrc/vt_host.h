@@ -49,6 +49,18 @@ struct FlatBvh {
 
 void build_bvh(const std::vector<Triangle> &tris, HostBvh &out, int max_leaf, float trav_cost);
 bool flatten_bvh(const HostBvh &bvh, uint64_t n_tris, uint32_t bfs_pairs, FlatBvh &out, std::string &err);
+// bvh::Bvh<float> form -> 4-wide quantised nodes (vt_device.h: VtQuad) in depth-first order + the leaf-order
+// permutation of the triangles.  False (with a reason) when the tree cannot be held: a leaf of more than 15
+// triangles, non-finite bounds, or a worst-case traversal stack deeper than VT_STACK_SIZE.
+struct QuadBvh {
+    std::vector<VtQuad> quads;
+    std::vector<uint32_t> leaf_order;
+    uint32_t root_leaf_count = 0;
+    uint32_t max_stack = 0;  // worst-case number of pending references
+};
+bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string &err);
+// 64-byte pairs in depth-first order -> 32-byte conservative compact pairs (vt_device.h: VtCPair)
+bool compact_pairs(const std::vector<VtPair> &pairs, std::vector<VtCPair> &out, std::string &err);
 
 struct DeviceScene;  // HBM-resident copy, vt_accel.cu
 
@@ -86,6 +98,8 @@ public:
 class AccelStruct {
     int mDevice;
     bool mAccelBuilt = false;
+    int mWantLayout = VT_LAYOUT_QUAD;  // layout requested for the next Populate (VT_LAYOUT_*)
+    int mLayout = VT_LAYOUT_EXACT;     // node layout resident on the device
     HostBvh mAccel;
     std::vector<Triangle> mTriangles;
     std::vector<Entity> mEntities;
@@ -111,6 +125,9 @@ public:
     // Batched Traverse (the entry the north star adds behind the same object).
     void TraverseBatch(const vt_ray *rays, uint64_t n, vt_hit *hits, vt_attr *attrs, const float *cones, uint32_t flags,
                        void *stream);
+    // SingleRayTraverser::Statistics (single_ray_traverser.hpp:132-135,158-163) summed over the batch:
+    // traversal steps (pair visits) and primitive intersections.  Synchronous, closest hit.
+    void TraverseStats(const vt_ray *rays, uint64_t n, uint32_t flags, uint64_t *steps, uint64_t *tests);
     void TraceResultBatch(const vt_ray *rays, const vt_hit *hits, uint64_t n, vt_attr *attrs, const float *cones,
                           uint32_t flags, void *stream);
 
@@ -137,6 +154,8 @@ public:
     const std::vector<Triangle> &Triangles() const { return mTriangles; }
     const HostBvh &Bvh() const { return mAccel; }
     bool Built() const { return mAccelBuilt; }
+    int Layout() const { return mLayout; }
+    void SetLayout(int layout) { mWantLayout = layout; }
     uint64_t InvalidRays() const { return mInvalidRays; }
     uint64_t Launches() const { return mLaunches; }
     uint64_t DeviceBytes() const;

@@ -13,6 +13,10 @@
 #define VT_TRAVERSE_MIN_BLOCKS 8
 #endif
 
+#ifndef VT_COMPACT_MIN_BLOCKS
+#define VT_COMPACT_MIN_BLOCKS 8
+#endif
+
 struct VtLaunchConfig {
     int persistent = 1;         // 1: machine-sized grid pulling rays from a counter; 0: one ray per thread
     int grid = 0;               // CTAs for the persistent launch (SMs x resident CTAs)
@@ -21,10 +25,11 @@ struct VtLaunchConfig {
 };
 
 // K1 — closest hit (or any hit) for n rays.  counters[0] = ray queue head (must be 0 on entry),
-// counters[1] += rays rejected by the argument rules.
+// counters[1] += rays rejected by the argument rules; with stats: counters[2] += traversal steps,
+// counters[3] += triangle tests (SingleRayTraverser::Statistics, single_ray_traverser.hpp:132-135).
 cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit *hits, uint64_t n, bool any_hit,
-                               unsigned long long *counters, const VtLaunchConfig &cfg, cudaStream_t stream);
-cudaError_t vt_traverse_occupancy(int *blocks_per_sm, size_t smem_bytes);
+                               unsigned long long *counters, const VtLaunchConfig &cfg, cudaStream_t stream, bool stats = false);
+cudaError_t vt_traverse_occupancy(int *blocks_per_sm, size_t smem_bytes, int layout);
 
 // K2 — eager TraceResult for n (ray, hit) records; cones = n x {coneWidth, coneAngle} or nullptr.
 cudaError_t vt_launch_trace_result(const VtSceneView &S, const vt_ray *rays, const vt_hit *hits, const float *cones,

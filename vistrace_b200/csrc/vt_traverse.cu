@@ -39,12 +39,33 @@ struct RayState {
 // or a triangle record (64 B, 64-byte aligned) is two of these instead of four LDG.128 — half the
 // per-lane requests through the L1 data stage, which is what limits this kernel once its
 // instruction count is down (profiles/r1_k_traverse_v3_bounce5m.md: l1tex throughput 84 %).
+// Cache-eviction qualifiers (PTX: ld.global.nc{.L1::x}{.L2::y}.v8): the hierarchy is the data every ray
+// re-reads, triangles are touched a few times per ray, rays are read once.
+#ifndef VT_QUAL_NODE
+#define VT_QUAL_NODE ""
+#endif
+#ifndef VT_QUAL_TRI
+#define VT_QUAL_TRI ""
+#endif
+#ifndef VT_QUAL_RAY
+#define VT_QUAL_RAY ""
+#endif
 VT_DEV void ldg256(const void *p, float4 &lo, float4 &hi) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc" VT_QUAL_NODE ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
                  : "l"(p));
 }
 
+VT_DEV void ldg256_tri(const void *p, float4 &lo, float4 &hi) {
+    asm volatile("ld.global.nc" VT_QUAL_TRI ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+VT_DEV void ldg256_ray(const void *p, float4 &lo, float4 &hi) {
+    asm volatile("ld.global.nc" VT_QUAL_RAY ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
 VT_DEV float safe_inverse(float d) {
     // libs/bvh/include/bvh/vector.hpp:69-74
     return 1.0f / (fabsf(d) < FLT_EPSILON ? copysignf(FLT_EPSILON, d) : d);
@@ -55,8 +76,8 @@ VT_DEV float safe_inverse(float d) {
 template <bool ALPHA>
 VT_DEV bool intersect_triangle(const VtSceneView &S, uint32_t slot, RayState &r) {
     float4 q0, q1, q2, q3;
-    ldg256(S.tris + slot, q0, q1);
-    ldg256(reinterpret_cast<const char *>(S.tris + slot) + 32, q2, q3);
+    ldg256_tri(S.tris + slot, q0, q1);
+    ldg256_tri(reinterpret_cast<const char *>(S.tris + slot) + 32, q2, q3);
     const V3 p0 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
     const V3 n = mk3(q2.y, q2.z, q2.w);  // cross(e1, e2) as stored by the Triangle ctor (Primitives.h:93)
     const uint32_t matflags = __float_as_uint(q3.x);
@@ -120,6 +141,114 @@ VT_DEV void slab_pair(const float4 &a, const float4 &b, const float4 &c, const f
     rx = fminf(x0, fminf(x1, fminf(x2, r.tmax)));
 }
 
+VT_DEV void ldg256u(const void *p, uint4 &lo, uint4 &hi) {
+    asm volatile("ld.global.nc" VT_QUAL_NODE ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+
+// One step over a COMPACT pair (vt_device.h: VtCPair): a single 32-byte load, exact decode of the
+// conservative planes ((k + q) * 2^E through one fma on the 2^23 + q float), then the reference's slab
+// arithmetic fmaf(plane, inv, so) on them.  fmaf is monotone in `plane`, so entry' <= entry and
+// exit' >= exit of the exact box: every node FastNodeIntersector accepts is accepted here.
+// Children come back as TAGGED references: bits 28-31 = triangle count (0 = inner), bits 0-27 = pair
+// index or first triangle slot.  `magic` is 0x4B000000 read from the kernel parameter block, so PRMT
+// takes it as a constant-bank operand and its selector stays an immediate.
+#define VT_REF_SHIFT 28
+#define VT_REF_MASK 0x0FFFFFFFu
+#define VT_REF_DONE 0xFFFFFFFFu
+VT_DEV void slab_cpair(const VtCPair *cpairs, uint32_t cur, uint32_t magic, const RayState &r, float &le, float &lx, float &re,
+                       float &rx, uint32_t &lref, uint32_t &rref) {
+    uint4 w0, w1;
+    ldg256u(cpairs + cur, w0, w1);
+    const float sx = __uint_as_float((w0.w & 0xffu) << 23);
+    const float sy = __uint_as_float((w0.w << 15) & 0x7f800000u);
+    const float sz = __uint_as_float((w0.w << 7) & 0x7f800000u);
+    const float ax = __uint_as_float(w0.x), ay = __uint_as_float(w0.y), az = __uint_as_float(w0.z);
+    // per axis the word holds {l.lo, l.hi, r.lo, r.hi}; with a negative direction the near plane is hi
+    // (node_intersectors.hpp:20-26): swap inside the byte pairs so the word reads {l.near, l.far, r.near, r.far}
+    const uint32_t qx = __byte_perm(w1.x, 0u, signbit(r.inv.x) ? 0x2301u : 0x3210u);
+    const uint32_t qy = __byte_perm(w1.y, 0u, signbit(r.inv.y) ? 0x2301u : 0x3210u);
+    const uint32_t qz = __byte_perm(w1.z, 0u, signbit(r.inv.z) ? 0x2301u : 0x3210u);
+#define VT_PLANE(q, sel, s, a) fmaf(__uint_as_float(__byte_perm(q, magic, sel)), s, a)
+    float e0 = fmaf(VT_PLANE(qx, 0x7650u, sx, ax), r.inv.x, r.so.x);
+    float e1 = fmaf(VT_PLANE(qy, 0x7650u, sy, ay), r.inv.y, r.so.y);
+    float e2 = fmaf(VT_PLANE(qz, 0x7650u, sz, az), r.inv.z, r.so.z);
+    float x0 = fmaf(VT_PLANE(qx, 0x7651u, sx, ax), r.inv.x, r.so.x);
+    float x1 = fmaf(VT_PLANE(qy, 0x7651u, sy, ay), r.inv.y, r.so.y);
+    float x2 = fmaf(VT_PLANE(qz, 0x7651u, sz, az), r.inv.z, r.so.z);
+    le = fmaxf(e0, fmaxf(e1, fmaxf(e2, r.tmin)));
+    lx = fminf(x0, fminf(x1, fminf(x2, r.tmax)));
+    e0 = fmaf(VT_PLANE(qx, 0x7652u, sx, ax), r.inv.x, r.so.x);
+    e1 = fmaf(VT_PLANE(qy, 0x7652u, sy, ay), r.inv.y, r.so.y);
+    e2 = fmaf(VT_PLANE(qz, 0x7652u, sz, az), r.inv.z, r.so.z);
+    x0 = fmaf(VT_PLANE(qx, 0x7653u, sx, ax), r.inv.x, r.so.x);
+    x1 = fmaf(VT_PLANE(qy, 0x7653u, sy, ay), r.inv.y, r.so.y);
+    x2 = fmaf(VT_PLANE(qz, 0x7653u, sz, az), r.inv.z, r.so.z);
+#undef VT_PLANE
+    re = fmaxf(e0, fmaxf(e1, fmaxf(e2, r.tmin)));
+    rx = fminf(x0, fminf(x1, fminf(x2, r.tmax)));
+    const uint32_t lcount = (w0.w >> 24) & 15u, rcount = w0.w >> 28;
+    const uint32_t ref = w1.w, next = cur + 1u;
+    const uint32_t lleaf = (lcount << VT_REF_SHIFT) | ref;                // left leaf: `ref` is its slot
+    const uint32_t rleaf_after_inner = (rcount << VT_REF_SHIFT) | ref;    // left inner: `ref` belongs to the right child
+    const uint32_t rleaf_after_leaf = (rcount << VT_REF_SHIFT) | (ref + lcount);
+    lref = lcount == 0 ? next : lleaf;
+    rref = lcount == 0 ? rleaf_after_inner : (rcount == 0 ? next : rleaf_after_leaf);
+}
+
+// One step over a QUAD (vt_device.h: VtQuad): two 32-byte loads, the four boxes decoded and slab-tested
+// exactly like slab_cpair, then the children that were hit are ordered near-to-far by entry distance.
+// Out: k[i] ascending sort keys (0x7FFFFFFF = no hit) and the matching tagged references r[i].
+VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const RayState &ray, int (&k)[4], uint32_t (&r)[4]) {
+    uint4 a0, a1, b0, b1;
+    ldg256u(quads + cur, a0, a1);
+    ldg256u(reinterpret_cast<const char *>(quads + cur) + 32, b0, b1);
+    const float sx = __uint_as_float((a0.w & 0xffu) << 23);
+    const float sy = __uint_as_float((a0.w << 15) & 0x7f800000u);
+    const float sz = __uint_as_float((a0.w << 7) & 0x7f800000u);
+    const float ax = __uint_as_float(a0.x), ay = __uint_as_float(a0.y), az = __uint_as_float(a0.z);
+    // words: a1 = {lo_x[4], hi_x[4], lo_y[4], hi_y[4]}, b0.x = lo_z[4], b0.y = hi_z[4]; a negative direction
+    // makes hi the near plane (node_intersectors.hpp:20-26)
+    const bool ox = signbit(ray.inv.x), oy = signbit(ray.inv.y), oz = signbit(ray.inv.z);
+    const uint32_t nx = ox ? a1.y : a1.x, fx = ox ? a1.x : a1.y;
+    const uint32_t ny = oy ? a1.w : a1.z, fy = oy ? a1.z : a1.w;
+    const uint32_t nz = oz ? b0.y : b0.x, fz = oz ? b0.x : b0.y;
+    r[0] = b1.x, r[1] = b1.y, r[2] = b1.z, r[3] = b1.w;
+#define VT_PLANE(q, sel, s, a) fmaf(__uint_as_float(__byte_perm(q, magic, sel)), s, a)
+#define VT_CHILD(i, sel)                                                                   \
+    {                                                                                      \
+        const float e0 = fmaf(VT_PLANE(nx, sel, sx, ax), ray.inv.x, ray.so.x);             \
+        const float e1 = fmaf(VT_PLANE(ny, sel, sy, ay), ray.inv.y, ray.so.y);             \
+        const float e2 = fmaf(VT_PLANE(nz, sel, sz, az), ray.inv.z, ray.so.z);             \
+        const float x0 = fmaf(VT_PLANE(fx, sel, sx, ax), ray.inv.x, ray.so.x);             \
+        const float x1 = fmaf(VT_PLANE(fy, sel, sy, ay), ray.inv.y, ray.so.y);             \
+        const float x2 = fmaf(VT_PLANE(fz, sel, sz, az), ray.inv.z, ray.so.z);             \
+        const float en = fmaxf(e0, fmaxf(e1, fmaxf(e2, ray.tmin)));                        \
+        const float ex = fminf(x0, fminf(x1, fminf(x2, ray.tmax)));                        \
+        const bool hit = en <= ex && (a0.w & (1u << (24 + i)));                            \
+        /* en >= tmin >= 0: its bit pattern orders like the value (-0.0 sorts first) */    \
+        k[i] = hit ? (int)((__float_as_uint(en) & ~3u) | (unsigned)i) : 0x7FFFFFFF;        \
+    }
+    VT_CHILD(0, 0x7650u)
+    VT_CHILD(1, 0x7651u)
+    VT_CHILD(2, 0x7652u)
+    VT_CHILD(3, 0x7653u)
+#undef VT_CHILD
+#undef VT_PLANE
+#define VT_CE(a, b)                       \
+    if (k[a] > k[b]) {                    \
+        const int tk = k[a];              \
+        k[a] = k[b];                      \
+        k[b] = tk;                        \
+        const uint32_t tr = r[a];         \
+        r[a] = r[b];                      \
+        r[b] = tr;                        \
+    }
+    VT_CE(0, 1) VT_CE(2, 3) VT_CE(0, 2) VT_CE(1, 3) VT_CE(1, 2)
+#undef VT_CE
+}
+
 VT_DEV void init_ray(const vt_ray &in, RayState &r) {
     r.o = mk3(in.ox, in.oy, in.oz);
     r.d = mk3(in.dx, in.dy, in.dz);
@@ -148,7 +277,7 @@ VT_DEV void write_hit(vt_hit *hits, unsigned long long idx, const RayState &r) {
 // enough lanes have a candidate queued (or nobody can walk), a node round otherwise.  Lanes that
 // cannot take part in the chosen round wait; this trades a little idling for never running the
 // ~100-instruction triangle test with one or two live lanes.
-template <bool ANY_HIT, bool ALPHA, bool SMEM>
+template <bool ANY_HIT, bool ALPHA, bool SMEM, bool STATS = false>
 __global__ void __launch_bounds__(VT_TRAVERSE_BLOCK, VT_TRAVERSE_MIN_BLOCKS)
 k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restrict__ hits, unsigned long long n,
            unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold) {
@@ -171,6 +300,7 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
     unsigned long long ray_idx = 0;
     RayState r;
     unsigned long long n_invalid = 0;
+    unsigned long long n_steps = 0, n_tests = 0;  // STATS: SingleRayTraverser::Statistics (single_ray_traverser.hpp:132-135)
 
     // invariant: a lane without a ray has walking == false and na == 0
     for (;;) {
@@ -196,8 +326,8 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
             if (!alive) {
                 ray_idx = base + __popc(idle & lt_mask);
                 if (ray_idx < n) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(rays + ray_idx);
-                    const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
+                    float4 ra, rb;
+                    ldg256_ray(rays + ray_idx, ra, rb);
                     vt_ray in{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                     init_ray(in, r);
                     alive = true;
@@ -227,6 +357,7 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
             if (want_tri && (want_node == 0 || __popc(want_tri) >= tri_threshold)) {
                 // ---- triangle round: one queued candidate per lane (intersect_leaf loop body, :53-61)
                 if (na != 0) {
+                    if (STATS) n_tests++;
                     const bool hit = intersect_triangle<ALPHA>(S, qa, r);
                     qa++;
                     na--;
@@ -242,18 +373,22 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
             } else if (na == 0 && walking) {
                 // ---- node round (:82-123), written branch-free: everything below is selects and
                 // predicated stack accesses, so lanes that take different exits do not serialise.
-                float4 a, b, c, d;
-                if (SMEM && cur < S.n_smem_pairs) {
-                    const float4 *p = s_pairs + cur * 4u;
-                    a = p[0], b = p[1], c = p[2], d = p[3];
-                } else {
-                    ldg256(S.pairs + cur, a, b);
-                    ldg256(reinterpret_cast<const char *>(S.pairs + cur) + 32, c, d);
-                }
                 float le, lx, re, rx;
-                slab_pair(a, b, c, d, r, le, lx, re, rx);  // both boxes against the tmax of step entry (:86-87)
-                const uint32_t lcount = __float_as_uint(b.z), lfirst = __float_as_uint(b.w);
-                const uint32_t rcount = __float_as_uint(d.z), rfirst = __float_as_uint(d.w);
+                uint32_t lcount, lfirst, rcount, rfirst;
+                if (STATS) n_steps++;
+                {
+                    float4 a, b, c, d;
+                    if (SMEM && cur < S.n_smem_pairs) {
+                        const float4 *p = s_pairs + cur * 4u;
+                        a = p[0], b = p[1], c = p[2], d = p[3];
+                    } else {
+                        ldg256(S.pairs + cur, a, b);
+                        ldg256(reinterpret_cast<const char *>(S.pairs + cur) + 32, c, d);
+                    }
+                    slab_pair(a, b, c, d, r, le, lx, re, rx);  // both boxes against the tmax of step entry (:86-87)
+                    lcount = __float_as_uint(b.z), lfirst = __float_as_uint(b.w);
+                    rcount = __float_as_uint(d.z), rfirst = __float_as_uint(d.w);
+                }
                 const bool hit_l = le <= lx, hit_r = re <= rx;
                 const bool leaf_l = hit_l && lcount != 0, leaf_r = hit_r && rcount != 0;
                 const bool in_l = hit_l && lcount == 0, in_r = hit_r && rcount == 0;
@@ -283,14 +418,152 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
         }
     }
     if (n_invalid) atomicAdd(&counters[1], n_invalid);
+    if (STATS) {
+        atomicAdd(&counters[2], n_steps);
+        atomicAdd(&counters[3], n_tests);
+    }
+}
+
+// K1 on the COMPACT layout.  Same persistent-warp / refill / warp-round machinery; the per-lane automaton
+// is simpler because this layout does not promise the reference's visit order (only its result, see
+// vt_device.h): a lane holds ONE tagged reference `cur` — an inner pair to step through, or a leaf run
+// whose remaining count and next slot are both encoded in it — leaves are ordered against inner siblings
+// by entry distance like any other child (ties: left first), and the far child of either kind is pushed.
+template <bool ANY_HIT, bool ALPHA, bool STATS, bool QUAD>
+__global__ void __launch_bounds__(VT_TRAVERSE_BLOCK, VT_COMPACT_MIN_BLOCKS)
+k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restrict__ hits, unsigned long long n,
+                   unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t stack[VT_STACK_SIZE];
+    int sp = 0;
+    uint32_t cur = VT_REF_DONE;  // VT_REF_DONE: nothing left to visit
+    bool alive = false;          // lane owns a ray whose result is not written yet
+    bool exhausted = false;      // warp-uniform: the ray queue has run dry
+    unsigned long long ray_idx = 0;
+    RayState r;
+    unsigned long long n_invalid = 0, n_steps = 0, n_tests = 0;
+    const uint32_t magic = S.magic;
+
+    for (;;) {
+        if (alive && cur == VT_REF_DONE) {
+            write_hit(hits, ray_idx, r);
+            alive = false;
+        }
+        const unsigned idle = __ballot_sync(0xffffffffu, !alive);
+        if (idle == 0xffffffffu && exhausted) break;
+        if (idle && !exhausted && __popc(idle) >= 32 - refill_threshold) {
+            const int n_idle = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if (persistent) {
+                if ((int)lane == leader) base = atomicAdd(&counters[0], (unsigned long long)n_idle);
+                base = __shfl_sync(0xffffffffu, base, leader);
+            } else {
+                base = ((unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u));
+                exhausted = true;
+            }
+            if (base + n_idle >= n) exhausted = true;
+            if (!alive) {
+                ray_idx = base + __popc(idle & lt_mask);
+                if (ray_idx < n) {
+                    float4 ra, rb;
+                    ldg256_ray(rays + ray_idx, ra, rb);
+                    vt_ray in{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                    init_ray(in, r);
+                    alive = true;
+                    sp = 0;
+                    if (!(in.tmin >= 0.f) || !(in.tmax > in.tmin)) {  // AccelStruct.cpp:805-806 -> counted miss; tmax < 0: masked slot
+                        if (!(in.tmax < 0.f)) n_invalid++;
+                    } else if (S.root_leaf_count) {
+                        cur = S.root_leaf_count << VT_REF_SHIFT;  // the root is a leaf over tris[0, count)
+                    } else if (S.n_pairs) {
+                        cur = 0;  // pair 0 / quad 0: the children of the root
+                    }
+                }
+            }
+        }
+        const int keep = exhausted ? 0 : refill_threshold;
+
+        for (;;) {
+            const bool has = cur != VT_REF_DONE;
+            const bool is_leaf = has && (cur >> VT_REF_SHIFT) != 0;
+            const unsigned want_tri = __ballot_sync(0xffffffffu, is_leaf);
+            const unsigned want_node = __ballot_sync(0xffffffffu, has && !is_leaf);
+            if (__popc(want_tri | want_node) <= keep) break;
+            if (want_tri && (want_node == 0 || __popc(want_tri) >= tri_threshold)) {
+                if (is_leaf) {
+                    if (STATS) n_tests++;
+                    const bool hit = intersect_triangle<ALPHA>(S, cur & VT_REF_MASK, r);
+                    if (ANY_HIT && hit) {
+                        cur = VT_REF_DONE;
+                        sp = 0;
+                    } else if ((cur >> VT_REF_SHIFT) == 1u) {  // run finished: pop
+                        if (sp > 0) {
+                            sp--;
+                            cur = stack[sp & (VT_STACK_SIZE - 1)];
+                        } else {
+                            cur = VT_REF_DONE;
+                        }
+                    } else {
+                        cur -= VT_REF_MASK;  // count - 1, slot + 1
+                    }
+                }
+            } else if (has && !is_leaf) {
+                if (STATS) n_steps++;
+                if (QUAD) {
+                    int k[4];
+                    uint32_t cr[4];
+                    slab_quad(S.quads, cur, magic, r, k, cr);
+                    // farthest first, so the nearest pending child is popped first
+                    if (k[3] != 0x7FFFFFFF) stack[(sp++) & (VT_STACK_SIZE - 1)] = cr[3];
+                    if (k[2] != 0x7FFFFFFF) stack[(sp++) & (VT_STACK_SIZE - 1)] = cr[2];
+                    if (k[1] != 0x7FFFFFFF) stack[(sp++) & (VT_STACK_SIZE - 1)] = cr[1];
+                    if (k[0] != 0x7FFFFFFF) {
+                        cur = cr[0];
+                    } else if (sp > 0) {
+                        sp--;
+                        cur = stack[sp & (VT_STACK_SIZE - 1)];
+                    } else {
+                        cur = VT_REF_DONE;
+                    }
+                    continue;
+                }
+                float le, lx, re, rx;
+                uint32_t lref, rref;
+                slab_cpair(S.cpairs, cur, magic, r, le, lx, re, rx, lref, rref);
+                const bool hit_l = le <= lx, hit_r = re <= rx;
+                const bool take_r = hit_r && (!hit_l || le > re);  // near child first; ties keep the left child first
+                const uint32_t next = take_r ? rref : lref;
+                const uint32_t far_ = take_r ? lref : rref;
+                if (hit_l && hit_r) {
+                    stack[sp & (VT_STACK_SIZE - 1)] = far_;
+                    sp++;
+                }
+                if (hit_l || hit_r) {
+                    cur = next;
+                } else if (sp > 0) {
+                    sp--;
+                    cur = stack[sp & (VT_STACK_SIZE - 1)];
+                } else {
+                    cur = VT_REF_DONE;
+                }
+            }
+        }
+    }
+    if (n_invalid) atomicAdd(&counters[1], n_invalid);
+    if (STATS) {
+        atomicAdd(&counters[2], n_steps);
+        atomicAdd(&counters[3], n_tests);
+    }
 }
 
 }  // namespace
 
 cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit *hits, uint64_t n, bool any_hit,
-                               unsigned long long *counters, const VtLaunchConfig &cfg, cudaStream_t stream) {
+                               unsigned long long *counters, const VtLaunchConfig &cfg, cudaStream_t stream, bool stats) {
     if (n == 0) return cudaSuccess;
-    const size_t smem = (size_t)S.n_smem_pairs * sizeof(VtPair);
+    const size_t smem = (S.cpairs || S.quads) ? 0 : (size_t)S.n_smem_pairs * sizeof(VtPair);
     int grid;
     if (cfg.persistent) {
         grid = cfg.grid;
@@ -305,6 +578,26 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
                                                           cfg.persistent ? 1 : 0, cfg.refill_threshold, cfg.tri_threshold);
         return cudaGetLastError();
     };
+    if (S.quads) {
+        if (stats) {  // closest hit only; counters[2] += traversal steps, counters[3] += triangle tests
+            if (any_hit) return cudaErrorInvalidValue;
+            return alpha ? launch(k_traverse_compact<false, true, true, true>) : launch(k_traverse_compact<false, false, true, true>);
+        }
+        if (any_hit) return alpha ? launch(k_traverse_compact<true, true, false, true>) : launch(k_traverse_compact<true, false, false, true>);
+        return alpha ? launch(k_traverse_compact<false, true, false, true>) : launch(k_traverse_compact<false, false, false, true>);
+    }
+    if (S.cpairs) {
+        if (stats) {
+            if (any_hit) return cudaErrorInvalidValue;
+            return alpha ? launch(k_traverse_compact<false, true, true, false>) : launch(k_traverse_compact<false, false, true, false>);
+        }
+        if (any_hit) return alpha ? launch(k_traverse_compact<true, true, false, false>) : launch(k_traverse_compact<true, false, false, false>);
+        return alpha ? launch(k_traverse_compact<false, true, false, false>) : launch(k_traverse_compact<false, false, false, false>);
+    }
+    if (stats) {
+        if (any_hit || S.n_smem_pairs) return cudaErrorInvalidValue;
+        return alpha ? launch(k_traverse<false, true, false, true>) : launch(k_traverse<false, false, false, true>);
+    }
     if (S.n_smem_pairs) {
         if (any_hit) return alpha ? launch(k_traverse<true, true, true>) : launch(k_traverse<true, false, true>);
         return alpha ? launch(k_traverse<false, true, true>) : launch(k_traverse<false, false, true>);
@@ -313,7 +606,11 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
     return alpha ? launch(k_traverse<false, true, false>) : launch(k_traverse<false, false, false>);
 }
 
-cudaError_t vt_traverse_occupancy(int *blocks_per_sm, size_t smem_bytes) {
+cudaError_t vt_traverse_occupancy(int *blocks_per_sm, size_t smem_bytes, int layout) {
+    if (layout == VT_LAYOUT_QUAD)
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_traverse_compact<false, true, false, true>, VT_TRAVERSE_BLOCK, 0);
+    if (layout == VT_LAYOUT_COMPACT)
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_traverse_compact<false, true, false, false>, VT_TRAVERSE_BLOCK, 0);
     cudaError_t e = cudaFuncSetAttribute(k_traverse<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_traverse<false, true, true>, VT_TRAVERSE_BLOCK, smem_bytes);
