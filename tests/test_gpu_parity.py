@@ -279,6 +279,28 @@ def test_large_batch_properties(vt):
     assert again.tobytes() == hits.tobytes()
 
 
+def test_full_size_scene_layouts_agree(vt):
+    """BASELINE config 3 at full size (5 005 460 triangles, 1920x1080 primary + 4 spp bounce rays, ~7.7 M rays): the
+    quantised layouts against the exact layout (which the tests above pin to the oracle bit for bit).  Records may
+    differ only as ties — the axis-aligned room has edges where two triangles give the same t — and are counted."""
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_terrain_closed(1582)
+    rays = scenes.pinhole_rays(1920, 1080, (0.0, -330.0, 200.0), (0.0, 0.0, 10.0))
+    exact = vt.Accel(0, layout="exact").populate(scene)
+    bvh = exact.get_bvh()
+    want = exact.trace_diffuse_wave(rays, 4, seed=11, want_bounce_rays=True)
+    assert (want["hits"]["prim"] != abi.VT_MISS).all()  # closed scene
+    live = want["bounce_rays"]["tmax"] >= 0
+    exact.close()
+    for layout in ("quad", "compact"):
+        accel = vt.Accel(0, layout=layout).populate(scene, bvh=bvh)
+        assert accel.layout == layout
+        assert same_hits(accel.traverse(rays), want["hits"], layout)
+        assert same_hits(accel.traverse(want["bounce_rays"][live]), want["bounce_hits"][live], layout)
+        accel.close()
+
+
 @pytest.mark.parametrize("name", ["foliage_small", "props_small"])
 def test_cuda_matches_reference_golden_vectors(vt, name, layout):
     """The committed fixtures are outputs of the UNMODIFIED reference (tests/golden/make_golden.py): its own

@@ -154,6 +154,9 @@ VT_DEV void ldg256u(const void *p, uint4 &lo, uint4 &hi) {
 // Children come back as TAGGED references: bits 28-31 = triangle count (0 = inner), bits 0-27 = pair
 // index or first triangle slot.  `magic` is 0x4B000000 read from the kernel parameter block, so PRMT
 // takes it as a constant-bank operand and its selector stays an immediate.
+#ifndef VT_LEAF_RUN_PER_ROUND
+#define VT_LEAF_RUN_PER_ROUND 1
+#endif
 #define VT_REF_SHIFT 28
 #define VT_REF_MASK 0x0FFFFFFFu
 #define VT_REF_DONE 0xFFFFFFFFu
@@ -493,6 +496,27 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
             if (__popc(want_tri | want_node) <= keep) break;
             if (want_tri && (want_node == 0 || __popc(want_tri) >= tri_threshold)) {
                 if (is_leaf) {
+                    // the whole leaf run in one round, in order (tmax shrinks between candidates exactly as in
+                    // intersect_leaf, single_ray_traverser.hpp:41-63); the run is contiguous, so after the first
+                    // record the next ones mostly come from the same 128-byte line
+#if VT_LEAF_RUN_PER_ROUND
+                    bool any = false;
+                    for (;;) {
+                        if (STATS) n_tests++;
+                        any |= intersect_triangle<ALPHA>(S, cur & VT_REF_MASK, r);
+                        if ((ANY_HIT && any) || (cur >> VT_REF_SHIFT) == 1u) break;
+                        cur -= VT_REF_MASK;  // count - 1, slot + 1
+                    }
+                    if (ANY_HIT && any) {
+                        cur = VT_REF_DONE;
+                        sp = 0;
+                    } else if (sp > 0) {
+                        sp--;
+                        cur = stack[sp & (VT_STACK_SIZE - 1)];
+                    } else {
+                        cur = VT_REF_DONE;
+                    }
+#else
                     if (STATS) n_tests++;
                     const bool hit = intersect_triangle<ALPHA>(S, cur & VT_REF_MASK, r);
                     if (ANY_HIT && hit) {
@@ -508,6 +532,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     } else {
                         cur -= VT_REF_MASK;  // count - 1, slot + 1
                     }
+#endif
                 }
             } else if (has && !is_leaf) {
                 if (STATS) n_steps++;
