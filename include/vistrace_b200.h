@@ -67,6 +67,16 @@ typedef struct vt_tri_in {
     uint8_t pad;
 } vt_tri_in;
 
+/* Per-triangle skinning data, the fields Model.cpp leaves in a Triangle for SkinTriangle
+ * (source/objects/Primitives.h:68-70): per vertex up to three (bone, weight) influences. 52 bytes. */
+typedef struct vt_tri_skin {
+    uint8_t num_bones[3];   /* Triangle::numBones */
+    uint8_t pad;
+    int8_t bone_ids[3][3];  /* Triangle::boneIds */
+    uint8_t pad2[3];
+    float weights[3][3];    /* Triangle::weights */
+} vt_tri_skin;
+
 /* Texture: decoded RGBA8888 mip chain exactly as VTFTexture keeps it in memory,
  * i.e. SMALLEST mip first (libs/VTFParser/VTFParser.cpp:44-78,178-188), one
  * frame, one face, depth 1.  flags are VTF TEXTURE_FLAGS (CLAMPS 0x4, CLAMPT 0x8). */
@@ -274,6 +284,15 @@ int vt_accel_accumulate_sky(vt_accel *accel, const vt_attr *attrs, const vt_hit 
 int vt_accel_set_layout(vt_accel *accel, int layout);
 int vt_accel_get_layout(const vt_accel *accel);
 
+/* The diffuse wave with the framebuffer as its only result: HOST rays[n] in, HOST framebuffer_rgb[3n] out —
+ * the memory of an RGBFFF IRenderTarget (include/vistrace/IRenderTarget.h:40; GetRawData(0)), written, not
+ * accumulated: fb[i] = weight * albedo_i * (escaped fraction of pixel i's spp bounce rays), sky pixels =
+ * weight * albedo.  Runs vt_accel_trace_diffuse_wave + vt_accel_accumulate_sky per tile on several CUDA streams,
+ * so the ray upload, the kernels and the image download overlap; returns when the image is on the host.
+ * live_out (nullable) receives the number of bounce rays spawned. */
+int vt_accel_render_diffuse_wave(vt_accel *accel, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed,
+                                 float weight, float *framebuffer_rgb, uint64_t *live_out);
+
 /* Rays rejected by the argument rules during the last synchronous traverse. */
 uint64_t vt_accel_invalid_rays(const vt_accel *accel);
 
@@ -300,6 +319,16 @@ int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, ui
 int vt_flatten_bvh(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris,
                    uint32_t bfs_pairs, void *pairs_out, uint32_t *leaf_order_out,
                    uint32_t *root_leaf_count, uint32_t *max_depth);
+
+/* Host-only: SkinTriangle (source/objects/AccelStruct.cpp:66-108) over n triangles, in place — what
+ * PopulateAccel runs per entity triangle before the build (AccelStruct.cpp:742-749): positions
+ * {p0, p0 - e1, p0 + e2} (e1 = p0 - p1, e2 = p2 - p0 as rounded by the Triangle constructor), normals and
+ * tangents become sum_i bones[b_i] * binds[b_i] * vec4(v, w) * weight_i (w = 1 for positions, 0 for
+ * directions; glm::mat4 arithmetic order), then p = the new vertices; e1/e2/n/nNorm/lod are re-derived by
+ * vt_accel_populate.  bones/binds: n_bones glm::mat4 each, 16 floats, column-major.  skin == NULL applies
+ * the one-bone overload (AccelStruct.cpp:103-108): every vertex bound to bone 0 with weight 1. */
+int vt_skin_triangles(vt_tri_in *tris, const vt_tri_skin *skin, uint64_t n, const float *bones,
+                      const float *binds, uint32_t n_bones);
 
 /* Host-only: 64-byte sibling pairs in depth-first order (vt_flatten_bvh with bfs_pairs = 0) ->
  * n_pairs 32-byte compact pairs: per axis {origin_adj f32} x3, {biased exponent u8} x3,

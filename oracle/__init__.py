@@ -59,6 +59,7 @@ def _lib(kind):
         "sample": (None, [vp, i32, vp, u64, vp]),
         "node_intersect": (None, [vp, vp, vp]),
         "tri_intersect": (i32, [vp, u64, vp, vp]),
+        "skin_triangles": (None, [vp, vp, u64, vp, vp, C.c_uint32, vp]),
     }
     ns = type("ns", (), {})()
     for name, (res, args) in sig.items():
@@ -169,3 +170,15 @@ def node_intersect(node, ray, kind="reference"):
     out = np.zeros(2, np.float32)
     _lib(kind).node_intersect(node.ctypes.data, ray.ctypes.data, out.ctypes.data)
     return float(out[0]), float(out[1])
+
+
+def skin_triangles(tris, skin, bones, binds, kind="reference"):
+    """SkinTriangle (source/objects/AccelStruct.cpp:66-108) over vt_tri_in records -> float32 [n, 27] =
+    {p0, e1, e2, normals[3], tangents[3]} as the reference leaves them.  skin=None: the one-bone overload."""
+    tris = np.ascontiguousarray(tris, abi.TRI_IN)
+    bones = np.ascontiguousarray(bones, np.float32).reshape(-1, 16)
+    binds = np.ascontiguousarray(binds, np.float32).reshape(-1, 16)
+    out = np.zeros((len(tris), 27), np.float32)
+    _lib(kind).skin_triangles(tris.ctypes.data, None if skin is None else np.ascontiguousarray(skin, abi.TRI_SKIN).ctypes.data, len(tris),
+                              bones.ctypes.data, binds.ctypes.data, len(bones), out.ctypes.data)
+    return out

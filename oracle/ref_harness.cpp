@@ -44,6 +44,10 @@
 
 #include "../include/vistrace_b200.h"
 
+// defined in source/objects/AccelStruct.cpp:66 (no header declares it)
+void SkinTriangle(Triangle &tri, const std::vector<glm::mat4> &bones, const std::vector<glm::mat4> &binds);
+void SkinTriangle(Triangle &tri, const glm::mat4 bone, glm::mat4 bind);
+
 namespace {
 
 // In-memory IVTFTexture over the reference's VTFTexture parser/sampler.
@@ -402,6 +406,43 @@ int vtref_tri_intersect(void *h, uint64_t prim, const vt_ray *r, float *tuv) {
     tuv[1] = hit->u;
     tuv[2] = hit->v;
     return 1;
+}
+
+// The reference's own SkinTriangle (source/objects/AccelStruct.cpp:66-101; external linkage, no header) over
+// vt_tri_in records: construct the Triangle as Model.cpp does, attach the skinning fields, skin.
+// out27[i] = {p0, e1, e2, normals[3], tangents[3]} as SkinTriangle left them (the fields the build reads next).
+void vtref_skin_triangles(const vt_tri_in *tris, const vt_tri_skin *skin, uint64_t n, const float *bones, const float *binds,
+                          uint32_t n_bones, float *out27) {
+    std::vector<glm::mat4> vb(n_bones), vbind(n_bones);
+    std::memcpy((void *)vb.data(), bones, n_bones * sizeof(glm::mat4));
+    std::memcpy((void *)vbind.data(), binds, n_bones * sizeof(glm::mat4));
+    for (uint64_t i = 0; i < n; i++) {
+        const vt_tri_in &in = tris[i];
+        glm::vec2 uvs[3] = {{in.uvs[0][0], in.uvs[0][1]}, {in.uvs[1][0], in.uvs[1][1]}, {in.uvs[2][0], in.uvs[2][1]}};
+        Triangle tri(Vector3(in.p[0][0], in.p[0][1], in.p[0][2]), Vector3(in.p[1][0], in.p[1][1], in.p[1][2]),
+                     Vector3(in.p[2][0], in.p[2][1], in.p[2][2]), in.material, uvs, in.one_sided != 0);
+        for (int v = 0; v < 3; v++) {
+            tri.normals[v] = glm::vec3(in.normals[v][0], in.normals[v][1], in.normals[v][2]);
+            tri.tangents[v] = glm::vec3(in.tangents[v][0], in.tangents[v][1], in.tangents[v][2]);
+            tri.numBones[v] = skin ? skin[i].num_bones[v] : 1;
+            for (int k = 0; k < 3; k++) {
+                tri.weights[v][k] = skin ? skin[i].weights[v][k] : (k == 0 ? 1.f : 0.f);
+                tri.boneIds[v][k] = skin ? skin[i].bone_ids[v][k] : 0;
+            }
+        }
+        if (skin) SkinTriangle(tri, vb, vbind);
+        else SkinTriangle(tri, vb[0], vbind[0]);  // the one-bone overload, AccelStruct.cpp:103-108
+        float *o = out27 + 27 * i;
+        for (int k = 0; k < 3; k++) {
+            o[k] = tri.p0[k];
+            o[3 + k] = tri.e1[k];
+            o[6 + k] = tri.e2[k];
+            for (int v = 0; v < 3; v++) {
+                o[9 + 3 * v + k] = tri.normals[v][k];
+                o[18 + 3 * v + k] = tri.tangents[v][k];
+            }
+        }
+    }
 }
 
 } // extern "C"

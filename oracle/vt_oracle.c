@@ -762,3 +762,57 @@ int vto_tri_intersect(void *h, uint64_t prim, const vt_ray *r, float *tuv) {
     ORay ray = {{r->ox, r->oy, r->oz}, {r->dx, r->dy, r->dz}, r->tmin, r->tmax};
     return tri_intersect(s, &s->tris[prim], &ray, &tuv[0], &tuv[1], &tuv[2]);
 }
+
+/* ---- SkinTriangle: source/objects/AccelStruct.cpp:33-47 (TransformToBone) and :66-101 (SkinTriangle), with
+ * glm::mat4 * mat4 (libs/glm/glm/detail/type_mat4x4.inl:630-648) and mat4 * vec4 (:561-572) in glm's operation order.
+ * out27[i] = {p0, e1, e2, normals[3], tangents[3]} as SkinTriangle leaves them. */
+static void m4_mul(const float *a, const float *b, float *r) { /* column-major: m[col*4 + row] */
+    for (int j = 0; j < 4; j++)
+        for (int k = 0; k < 4; k++)
+            r[j * 4 + k] = ((a[0 * 4 + k] * b[j * 4 + 0] + a[1 * 4 + k] * b[j * 4 + 1]) + a[2 * 4 + k] * b[j * 4 + 2]) + a[3 * 4 + k] * b[j * 4 + 3];
+}
+static void m4_mul_v(const float *m, const float *v, float *o) {
+    for (int k = 0; k < 4; k++) o[k] = (m[0 * 4 + k] * v[0] + m[1 * 4 + k] * v[1]) + (m[2 * 4 + k] * v[2] + m[3 * 4 + k] * v[3]);
+}
+static void transform_to_bone(const float *vec, const float *bones, const float *binds, unsigned num, const float *w, const int8_t *ids,
+                              int angle_only, float *out) {
+    float fin[4] = {0.f, 0.f, 0.f, 0.f};
+    const float vertex[4] = {vec[0], vec[1], vec[2], angle_only ? 0.f : 1.f};
+    for (unsigned i = 0; i < num; i++) {
+        float bb[16], t[4];
+        m4_mul(bones + 16 * ids[i], binds + 16 * ids[i], bb);
+        m4_mul_v(bb, vertex, t);
+        for (int k = 0; k < 4; k++) fin[k] += t[k] * w[i];
+    }
+    out[0] = fin[0], out[1] = fin[1], out[2] = fin[2];
+}
+void vto_skin_triangles(const vt_tri_in *tris, const vt_tri_skin *skin, uint64_t n, const float *bones, const float *binds,
+                        uint32_t n_bones, float *out27) {
+    (void)n_bones;
+    static const float one_w[3] = {1.f, 0.f, 0.f};
+    static const int8_t one_id[3] = {0, 0, 0};
+    for (uint64_t i = 0; i < n; i++) {
+        const vt_tri_in *in = &tris[i];
+        float pos[3][3], *o = out27 + 27 * i;
+        for (int k = 0; k < 3; k++) { /* p0, p0 - e1, p0 + e2 with the constructor's rounded edges (Primitives.h:82) */
+            const float e1 = in->p[0][k] - in->p[1][k], e2 = in->p[2][k] - in->p[0][k];
+            pos[0][k] = in->p[0][k];
+            pos[1][k] = in->p[0][k] - e1;
+            pos[2][k] = in->p[0][k] + e2;
+        }
+        float v[3][3];
+        for (int vi = 0; vi < 3; vi++) {
+            const unsigned num = skin ? skin[i].num_bones[vi] : 1u;
+            const float *w = skin ? skin[i].weights[vi] : one_w;
+            const int8_t *ids = skin ? skin[i].bone_ids[vi] : one_id;
+            transform_to_bone(pos[vi], bones, binds, num, w, ids, 0, v[vi]);
+            transform_to_bone(in->normals[vi], bones, binds, num, w, ids, 1, o + 9 + 3 * vi);
+            transform_to_bone(in->tangents[vi], bones, binds, num, w, ids, 1, o + 18 + 3 * vi);
+        }
+        for (int k = 0; k < 3; k++) {
+            o[k] = v[0][k];
+            o[3 + k] = v[0][k] - v[1][k]; /* e1 = v0 - v1, e2 = v2 - v0 (AccelStruct.cpp:96-98) */
+            o[6 + k] = v[2][k] - v[0][k];
+        }
+    }
+}

@@ -54,8 +54,20 @@ def golden_scene(name, sc, rays, extra_rays=None):
     print(name, {k: (v.shape, str(v.dtype)[:12]) for k, v in out.items() if hasattr(v, "shape")})
 
 
+def golden_skin():
+    """SkinTriangle (source/objects/AccelStruct.cpp:66-108): weighted multi-bone case + the one-bone overload."""
+    tris, skin, bones, binds = scenes.skin_case()
+    out = {"tris": tris, "skin": skin, "bones": bones, "binds": binds,
+           "skinned": oracle.skin_triangles(tris, skin, bones, binds, "reference"),
+           "skinned_one_bone": oracle.skin_triangles(tris, None, bones[:1], binds[:1], "reference")}
+    np.savez_compressed(os.path.join(HERE, "skin_small.npz"), **out)
+    print("skin_small", {k: v.shape for k, v in out.items()})
+
+
 def main():
     assert oracle.available("reference"), "build oracle/_ref first: make -C oracle ref"
+    if sys.argv[1:] == ["skin"]:
+        return golden_skin()
     # foliage: alpha test (wrap + clamp textures), two-sided cards, one-sided ground, sky room
     sc = scenes.scene_foliage(n_cards=400, tex_size=32, ground_quads=8, seed=7)
     rays = scenes.pinhole_rays(96, 54, (0, -48, 20), (0, 0, 8))
@@ -77,6 +89,7 @@ def main():
     entry, exit_ = oracle.node_intersect(node, ray, "reference")
     np.savez(os.path.join(HERE, "kat_node_intersect.npz"), node=node, ray=ray, entry_exit=np.array([entry, exit_], np.float32))
     print("kat node", entry, exit_)
+    golden_skin()
 
 
 if __name__ == "__main__":

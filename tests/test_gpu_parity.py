@@ -110,7 +110,7 @@ def test_config1_heightfield_primary_and_bounce(vt, oracle_mod, kind, bvh_from, 
 def test_config2_props_primary_and_shadow(vt, oracle_mod, kind, layout):
     from vistrace_b200 import abi, scenes
 
-    scene = scenes.scene_props(24, 31, 15, 24)
+    scene = scenes.scene_props_skinned(24, 31, 15, 24)  # props baked to world space by SkinTriangle (vt_skin_triangles)
     rays = scenes.pinhole_rays(480, 270, (0, -95, 40), (0, 0, 10))
     accel, cpu, hits, attrs, want = _check_against(vt, oracle_mod, scene, rays, kind, "product", layout)
     assert len(np.unique(attrs["ent_id"][hits["prim"] != abi.VT_MISS])) > 5  # several entities visible
@@ -391,6 +391,16 @@ def test_accumulate_sky_framebuffer(vt):
     want = np.where(is_sky[:, None], a["albedo"], a["albedo"] * vis[:, None]) * np.float32(0.5)
     want[a["prim"] == abi.VT_MISS] = 0
     np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+    # the one-call render (host rays in, host RGBFFF image out), whole and tiled, is the same image bit for bit
+    import os
+
+    img, live = accel.render_diffuse_wave(rays, spp, seed=3, weight=0.5)
+    assert live == spp * int((~is_sky & (a["prim"] != abi.VT_MISS)).sum())
+    np.testing.assert_array_equal(img, got)
+    os.environ["VT_WAVE_TILE"] = "3000"
+    img2, _ = accel.render_diffuse_wave(rays, spp, seed=3, weight=0.5)
+    del os.environ["VT_WAVE_TILE"]
+    np.testing.assert_array_equal(img2, got)
 
 
 def test_two_gpu_sharded_trace_nccl(vt):

@@ -138,3 +138,35 @@ def test_port_matches_live_reference(oracle_mod):
     uvm = np.random.default_rng(1).uniform(-3, 3, (5000, 3)).astype(np.float32)
     for i in range(2):
         np.testing.assert_array_equal(ref.sample(i, uvm).view(np.uint32), port.sample(i, uvm).view(np.uint32))
+
+
+def _skinned27(out):
+    """{p0, e1, e2, normals, tangents} from skinned vt_tri_in records, with the constructor's e1 = p0 - p1, e2 = p2 - p0."""
+    p = out["p"]
+    return np.concatenate([p[:, 0], p[:, 0] - p[:, 1], p[:, 2] - p[:, 0], out["normals"].reshape(-1, 9), out["tangents"].reshape(-1, 9)], 1).astype(np.float32)
+
+
+def test_skin_triangles_port_and_product_match_reference_golden(oracle_mod):
+    """SkinTriangle (source/objects/AccelStruct.cpp:66-108): the committed outputs of the reference's own function vs the
+    C restatement and the product's host code (vt_skin_triangles), bit for bit; live reference too when present."""
+    import os
+
+    import vistrace_b200 as vt
+    from conftest import GOLDEN
+
+    z = np.load(os.path.join(GOLDEN, "skin_small.npz"))
+    for skin, bones, binds, key in ((z["skin"], z["bones"], z["binds"], "skinned"), (None, z["bones"][:1], z["binds"][:1], "skinned_one_bone")):
+        want = z[key]
+        port = oracle_mod.skin_triangles(z["tris"], skin, bones, binds, "port")
+        np.testing.assert_array_equal(port.view(np.uint32), want.view(np.uint32))
+        got = _skinned27(vt.skin_triangles(z["tris"], skin, bones, binds))
+        np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+        if oracle_mod.available("reference"):
+            live = oracle_mod.skin_triangles(z["tris"], skin, bones, binds, "reference")
+            np.testing.assert_array_equal(live.view(np.uint32), want.view(np.uint32))
+    # the transform really moved things, and a bad bone id is an error, not a crash
+    assert np.abs(z["skinned"][:, :3] - z["tris"]["p"][:, 0]).max() > 1.0
+    bad = z["skin"].copy()
+    bad["bone_ids"][0, 0, 0] = 99
+    with pytest.raises(RuntimeError, match="bone id"):
+        vt.skin_triangles(z["tris"], bad, z["bones"], z["binds"])

@@ -39,6 +39,7 @@ TRI_IN = np.dtype(
     ],
     align=False,
 )
+TRI_SKIN = np.dtype([("num_bones", u1, 3), ("pad", u1), ("bone_ids", np.int8, (3, 3)), ("pad2", u1, 3), ("weights", f4, (3, 3))], align=False)
 ATTR = np.dtype(
     [
         ("pos", f4, 3),
@@ -96,6 +97,7 @@ MATERIAL = np.dtype(
 ENTITY = np.dtype([("id", u4), ("colour", f4, 4)], align=False)
 
 assert RAY.itemsize == 32 and HIT.itemsize == 16 and NODE.itemsize == 32
+assert TRI_SKIN.itemsize == 52
 assert TRI_IN.itemsize == 152 and ATTR.itemsize == 128 and ENTITY.itemsize == 20
 assert MATERIAL.itemsize == 280
 

@@ -31,10 +31,12 @@ SYMBOLS = {
     "vt_accel_trace_result": (_i32, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "vt_accel_bounce_rays": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
+    "vt_accel_render_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, C.c_float, _vp, _vp]),
     "vt_accel_accumulate_sky": (_i32, [_vp, _vp, _vp, _u64, _u32, C.c_float, _vp, _vp]),
     "vt_accel_set_layout": (_i32, [_vp, _i32]),
     "vt_accel_get_layout": (_i32, [_vp]),
     "vt_compact_pairs": (_i32, [_vp, _u64, _vp]),
+    "vt_skin_triangles": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32]),
     "vt_build_quads": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_invalid_rays": (_u64, [_vp]),
     "vt_accel_launch_count": (_u64, [_vp]),
@@ -92,6 +94,19 @@ def build_bvh(scene):
     cap = C.c_uint64(len(nodes))
     _check(L.vt_build_bvh(C.cast(scene.ptr(), _vp), nodes.ctypes.data, C.addressof(cap), prims.ctypes.data), "vt_build_bvh")
     return nodes, prims
+
+
+def skin_triangles(tris, skin, bones, binds):
+    """Host-only SkinTriangle (source/objects/AccelStruct.cpp:66-108): returns a skinned COPY of the vt_tri_in records.
+    bones/binds: [n_bones, 16] glm::mat4 (column-major); skin: abi.TRI_SKIN records or None (one-bone overload)."""
+    out = np.ascontiguousarray(tris, abi.TRI_IN).copy()
+    bones = np.ascontiguousarray(bones, np.float32).reshape(-1, 16)
+    binds = np.ascontiguousarray(binds, np.float32).reshape(-1, 16)
+    if len(bones) != len(binds):
+        raise ValueError("bones and binds must have the same length")
+    sk = None if skin is None else np.ascontiguousarray(skin, abi.TRI_SKIN)
+    _check(lib().vt_skin_triangles(out.ctypes.data, _ptr(sk), len(out), bones.ctypes.data, binds.ctypes.data, len(bones)), "vt_skin_triangles")
+    return out
 
 
 PAIR = np.dtype(
@@ -287,6 +302,15 @@ class Accel:
         _check(self.L.vt_accel_trace_diffuse_wave(self.h, _ptr(d_rays), n, spp, seed, _ptr(d_hits), _ptr(d_attrs), _ptr(d_bounce_rays),
                                                   _ptr(d_bounce_hits), None, abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)),
                "vt_accel_trace_diffuse_wave")
+
+    def render_diffuse_wave(self, rays, spp, seed=0, weight=1.0, out=None):
+        """Host rays in, host RGBFFF framebuffer out (numpy float32 [n, 3]); returns (framebuffer, bounce rays spawned)."""
+        rays = rays if isinstance(rays, np.ndarray) and rays.dtype == abi.RAY and rays.flags.c_contiguous else np.ascontiguousarray(rays, abi.RAY)
+        fb = np.empty((len(rays), 3), np.float32) if out is None else out
+        live = C.c_uint64(0)
+        _check(self.L.vt_accel_render_diffuse_wave(self.h, rays.ctypes.data, len(rays), spp, seed, weight, fb.ctypes.data, C.addressof(live)),
+               "vt_accel_render_diffuse_wave")
+        return fb, live.value
 
     def accumulate_sky_device(self, d_attrs, d_bounce_hits, n, spp, weight, d_fb, stream=None):
         _check(self.L.vt_accel_accumulate_sky(self.h, _ptr(d_attrs), _ptr(d_bounce_hits), n, spp, weight, _ptr(d_fb), _ptr(stream)),

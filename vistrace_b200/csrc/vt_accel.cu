@@ -68,6 +68,81 @@ void Triangle::ComputeNormalAndLoD() {
     for (int k = 0; k < 3; k++) nNorm[k] = n[k] / len;
 }
 
+// ------------------------------------------------------------------------------ SkinTriangle
+// glm::mat4 arithmetic in glm's operation order (libs/glm/glm/detail/type_mat4x4.inl), host side,
+// compiled with -ffp-contract=off so every product and sum rounds separately as in the reference build.
+namespace {
+struct M4 {
+    float c[4][4];  // c[column][row]
+};
+// operator*(mat4, mat4), type_mat4x4.inl:630-648: Result[j] = ((A0*B[j][0] + A1*B[j][1]) + A2*B[j][2]) + A3*B[j][3]
+M4 mul(const M4 &a, const M4 &b) {
+    M4 r;
+    for (int j = 0; j < 4; j++)
+        for (int k = 0; k < 4; k++) r.c[j][k] = ((a.c[0][k] * b.c[j][0] + a.c[1][k] * b.c[j][1]) + a.c[2][k] * b.c[j][2]) + a.c[3][k] * b.c[j][3];
+    return r;
+}
+// operator*(mat4, vec4), type_mat4x4.inl:561-572: (m[0]*v0 + m[1]*v1) + (m[2]*v2 + m[3]*v3)
+void mul(const M4 &m, const float v[4], float out[4]) {
+    for (int k = 0; k < 4; k++) out[k] = (m.c[0][k] * v[0] + m.c[1][k] * v[1]) + (m.c[2][k] * v[2] + m.c[3][k] * v[3]);
+}
+// TransformToBone, source/objects/AccelStruct.cpp:33-47
+void transform_to_bone(const float vec[3], const M4 *bones, const M4 *binds, uint32_t n_bones, uint8_t num, const float *weights,
+                       const int8_t *ids, bool angle_only, float out[3]) {
+    float fin[4] = {0.f, 0.f, 0.f, 0.f};
+    const float vertex[4] = {vec[0], vec[1], vec[2], angle_only ? 0.f : 1.f};
+    for (uint8_t i = 0; i < num; i++) {
+        const int8_t b = ids[i];
+        if (b < 0 || (uint32_t)b >= n_bones) throw std::runtime_error("skin_triangles: bone id out of range");
+        float t[4];
+        mul(mul(bones[b], binds[b]), vertex, t);  // (bones * binds) * vertex ...
+        for (int k = 0; k < 4; k++) fin[k] += t[k] * weights[i];  // ... * weight, accumulated
+    }
+    out[0] = fin[0], out[1] = fin[1], out[2] = fin[2];
+}
+}  // namespace
+
+void SkinTriangles(vt_tri_in *tris, const vt_tri_skin *skin, uint64_t n, const float *bones_, const float *binds_, uint32_t n_bones) {
+    if (n == 0) return;
+    if (!tris || !bones_ || !binds_ || n_bones == 0) throw std::runtime_error("skin_triangles: null argument");
+    const M4 *bones = reinterpret_cast<const M4 *>(bones_), *binds = reinterpret_cast<const M4 *>(binds_);
+    vt_tri_skin one;
+    std::memset(&one, 0, sizeof(one));
+    for (int v = 0; v < 3; v++) {
+        one.num_bones[v] = 1;
+        one.weights[v][0] = 1.f;
+    }
+    std::string error;
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        vt_tri_in &t = tris[i];
+        const vt_tri_skin &sk = skin ? skin[i] : one;
+        // the vertices SkinTriangle sees: p0, p0 - e1, p0 + e2 with the constructor's rounded edges (AccelStruct.cpp:68-72)
+        float pos[3][3];
+        for (int k = 0; k < 3; k++) {
+            const float e1 = t.p[0][k] - t.p[1][k], e2 = t.p[2][k] - t.p[0][k];
+            pos[0][k] = t.p[0][k];
+            pos[1][k] = t.p[0][k] - e1;
+            pos[2][k] = t.p[0][k] + e2;
+        }
+        try {
+            for (int v = 0; v < 3; v++) {
+                float o[3];
+                transform_to_bone(pos[v], bones, binds, n_bones, sk.num_bones[v], sk.weights[v], sk.bone_ids[v], false, o);
+                std::memcpy(t.p[v], o, 12);
+                transform_to_bone(t.normals[v], bones, binds, n_bones, sk.num_bones[v], sk.weights[v], sk.bone_ids[v], true, o);
+                std::memcpy(t.normals[v], o, 12);
+                transform_to_bone(t.tangents[v], bones, binds, n_bones, sk.num_bones[v], sk.weights[v], sk.bone_ids[v], true, o);
+                std::memcpy(t.tangents[v], o, 12);
+            }
+        } catch (const std::exception &e) {
+#pragma omp critical
+            error = e.what();
+        }
+    }
+    if (!error.empty()) throw std::runtime_error(error);
+}
+
 // --------------------------------------------------------------------------- DeviceScene
 template <typename T>
 struct DevBuf {
@@ -119,6 +194,7 @@ struct DeviceScene {
         DevBuf<vt_ray> rays, brays;
         DevBuf<vt_hit> hits, bhits;
         DevBuf<vt_attr> attrs;
+        DevBuf<float> fb;
     } lanes[3];
     DevBuf<unsigned long long> live;
     VtSceneView view{};
@@ -151,6 +227,7 @@ struct DeviceScene {
             l.hits.release();
             l.bhits.release();
             l.attrs.release();
+            l.fb.release();
             if (l.stream) cudaStreamDestroy(l.stream);
         }
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -608,14 +685,15 @@ void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp,
         return;
     }
     // host pointers: tiles round-robin over three streams — H2D(rays) | K1 K2 K3 K1 | D2H(results) overlap across tiles
-    const uint64_t tile = (uint64_t)std::max(1, env_int("VT_WAVE_TILE", 1 << 18));
+    const uint64_t tile = (uint64_t)std::max(1, env_int("VT_WAVE_TILE", 1 << 19));
     VT_CUDA(cudaMemsetAsync(D.live.p, 0, sizeof(unsigned long long), D.own_stream));
     VT_CUDA(cudaStreamSynchronize(D.own_stream));
     for (auto &l : D.lanes)
         if (!l.stream) VT_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     int li = 0;
-    for (uint64_t base = 0; base < n; base += tile, li = (li + 1) % 3) {
-        const uint64_t m = std::min(tile, n - base);
+    uint64_t cur_tile = std::max<uint64_t>(1, tile / 8);  // small first tiles, doubling up to `tile`
+    for (uint64_t base = 0, m = 0; base < n; base += m, li = (li + 1) % 3, cur_tile = std::min(tile, cur_tile * 2)) {
+        m = std::min(cur_tile, n - base);
         DeviceScene::WaveLane &l = D.lanes[li];
         l.rays.ensure(tile);
         l.hits.ensure(tile);
@@ -636,6 +714,55 @@ void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp,
         if (attrs) VT_CUDA(cudaMemcpyAsync(attrs + base, l.attrs.p, m * sizeof(vt_attr), cudaMemcpyDeviceToHost, l.stream));
         if (bounce_rays)
             VT_CUDA(cudaMemcpyAsync(bounce_rays + base * spp, l.brays.p, m * spp * sizeof(vt_ray), cudaMemcpyDeviceToHost, l.stream));
+    }
+    for (auto &l : D.lanes) VT_CUDA(cudaStreamSynchronize(l.stream));
+    if (live_out) {
+        unsigned long long v = 0;
+        VT_CUDA(cudaMemcpy(&v, D.live.p, sizeof(v), cudaMemcpyDeviceToHost));
+        *live_out = v;
+    }
+}
+
+void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb,
+                                    uint64_t *live_out) {
+    check_built(mAccelBuilt);
+    if (live_out) *live_out = 0;
+    if (n == 0) return;
+    if (!rays || !fb) throw std::runtime_error("render_diffuse_wave: rays and framebuffer must not be null");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    D.live.ensure(1);
+    auto next_counter = [&]() { return D.counters.p + 2 * (D.next_slot.fetch_add(1) % kCounterSlots); };
+    // tiles round-robin over three streams: H2D(rays) | K1 K2 K3 K1 K4 | D2H(framebuffer tile) overlap across tiles
+    const uint64_t tile = (uint64_t)std::max(1, env_int("VT_WAVE_TILE", 1 << 19));
+    VT_CUDA(cudaMemsetAsync(D.live.p, 0, sizeof(unsigned long long), D.own_stream));
+    VT_CUDA(cudaStreamSynchronize(D.own_stream));
+    for (auto &l : D.lanes)
+        if (!l.stream) VT_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    int li = 0;
+    // the first tiles are small so the first kernel starts after a short upload; sizes double up to `tile`
+    uint64_t cur_tile = std::max<uint64_t>(1, tile / 8);
+    for (uint64_t base = 0, m = 0; base < n; base += m, li = (li + 1) % 3, cur_tile = std::min(tile, cur_tile * 2)) {
+        m = std::min(cur_tile, n - base);
+        DeviceScene::WaveLane &l = D.lanes[li];
+        l.rays.ensure(tile);
+        l.hits.ensure(tile);
+        l.attrs.ensure(tile);
+        l.brays.ensure(tile * spp);
+        l.bhits.ensure(tile * spp);
+        l.fb.ensure(tile * 3);
+        unsigned long long *c0 = next_counter(), *c1 = next_counter();
+        VT_CUDA(cudaMemsetAsync(c0, 0, 16, l.stream));
+        VT_CUDA(cudaMemsetAsync(c1, 0, 16, l.stream));
+        VT_CUDA(cudaMemsetAsync(l.fb.p, 0, m * 3 * sizeof(float), l.stream));
+        VT_CUDA(cudaMemcpyAsync(l.rays.p, rays + base, m * sizeof(vt_ray), cudaMemcpyHostToDevice, l.stream));
+        VT_CUDA(vt_launch_traverse(D.view, l.rays.p, l.hits.p, m, false, c0, D.cfg, l.stream));
+        VT_CUDA(vt_launch_trace_result(D.view, l.rays.p, l.hits.p, nullptr, l.attrs.p, m, l.stream));
+        VT_CUDA(vt_launch_bounce_rays(l.attrs.p, m, spp, seed, base * spp, l.brays.p, live_out ? D.live.p : nullptr, l.stream));
+        VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, m * spp, false, c1, D.cfg, l.stream));
+        VT_CUDA(vt_launch_accumulate_sky(D.view, l.attrs.p, l.bhits.p, m, spp, weight, l.fb.p, l.stream));
+        mLaunches += 5;
+        VT_CUDA(cudaMemcpyAsync(fb + base * 3, l.fb.p, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, l.stream));
     }
     for (auto &l : D.lanes) VT_CUDA(cudaStreamSynchronize(l.stream));
     if (live_out) {
@@ -788,6 +915,15 @@ int vt_accel_trace_diffuse_wave(vt_accel *a, const vt_ray *rays, uint64_t n, uin
     VT_CATCH(1)
 }
 
+int vt_accel_render_diffuse_wave(vt_accel *a, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight,
+                                 float *framebuffer_rgb, uint64_t *live_out) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.RenderDiffuseWave(rays, n, spp, seed, weight, framebuffer_rgb, live_out);
+    return 0;
+    VT_CATCH(1)
+}
+
 int vt_accel_accumulate_sky(vt_accel *a, const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n, uint32_t spp,
                             float weight, float *framebuffer_rgb, void *stream) {
     VT_TRY
@@ -911,6 +1047,13 @@ int vt_build_quads(const vt_node *nodes, uint64_t node_count, const uint64_t *pr
     *n_quads = q.quads.size();
     if (root_leaf_count) *root_leaf_count = q.root_leaf_count;
     if (max_stack) *max_stack = q.max_stack;
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_skin_triangles(vt_tri_in *tris, const vt_tri_skin *skin, uint64_t n, const float *bones, const float *binds, uint32_t n_bones) {
+    VT_TRY
+    vt::SkinTriangles(tris, skin, n, bones, binds, n_bones);
     return 0;
     VT_CATCH(1)
 }

@@ -62,6 +62,9 @@ bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string 
 // 64-byte pairs in depth-first order -> 32-byte conservative compact pairs (vt_device.h: VtCPair)
 bool compact_pairs(const std::vector<VtPair> &pairs, std::vector<VtCPair> &out, std::string &err);
 
+// SkinTriangle over a batch (source/objects/AccelStruct.cpp:66-108): bakes bone * bind * weight into world space.
+void SkinTriangles(vt_tri_in *tris, const vt_tri_skin *skin, uint64_t n, const float *bones, const float *binds, uint32_t n_bones);
+
 struct DeviceScene;  // HBM-resident copy, vt_accel.cu
 
 // Eager TraceResult for one hit (source/objects/TraceResult.h:54-111): the batched path fills
@@ -140,6 +143,10 @@ public:
     // on several streams so the PCIe copies overlap the kernels.
     void TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, vt_hit *hits, vt_attr *attrs,
                           vt_ray *bounce_rays, vt_hit *bounce_hits, uint64_t *live_out, uint32_t flags, void *stream);
+
+    // The same wave with the framebuffer as its only result: HOST rays in, HOST RGBFFF image out
+    // (fb[i] = weight * albedo_i * escaped fraction of pixel i's bounce rays), tiled over streams like TraceDiffuseWave.
+    void RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb, uint64_t *live_out);
 
     // Fold a diffuse wave into an RGBFFF framebuffer (device pointers only): see k_accumulate_sky.
     void AccumulateSky(const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n, uint32_t spp, float weight, float *fb,

@@ -186,6 +186,59 @@ def _random_rotations(rng, n):
         np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], 1)
 
 
+def rigid_mat4(rot, trans, scale=1.0):
+    """glm::mat4 (column-major, 16 floats) of x -> scale * rot @ x + trans."""
+    m = np.zeros((4, 4), np.float64)
+    m[:3, :3] = np.asarray(rot, np.float64) * scale
+    m[:3, 3] = trans
+    m[3, 3] = 1.0
+    return m.T.astype(f4).reshape(16)  # element [col*4 + row]
+
+
+def skin_case(n_tris=600, n_bones=5, seed=77):
+    """Deterministic input for SkinTriangle (source/objects/AccelStruct.cpp:66-101): object-space triangles with
+    normals/tangents, 1-3 weighted bones per vertex, random bone and bind-pose matrices."""
+    rng = np.random.default_rng(seed)
+    tris = torus(25, 12, seed=seed)[:n_tris].copy()
+    n = len(tris)
+    skin = np.zeros(n, abi.TRI_SKIN)
+    skin["num_bones"] = rng.integers(1, 4, (n, 3))
+    skin["bone_ids"] = rng.integers(0, n_bones, (n, 3, 3))
+    w = rng.uniform(0.05, 1.0, (n, 3, 3))
+    w *= np.arange(3)[None, None, :] < skin["num_bones"][:, :, None]
+    skin["weights"] = (w / w.sum(-1, keepdims=True)).astype(f4)
+    rots = _random_rotations(rng, 2 * n_bones)
+    bones = np.stack([rigid_mat4(rots[b], rng.uniform(-50, 50, 3), rng.uniform(0.5, 3.0)) for b in range(n_bones)])
+    binds = np.stack([rigid_mat4(rots[n_bones + b], rng.uniform(-2, 2, 3)) for b in range(n_bones)])
+    return tris, skin, bones, binds
+
+
+def scene_props_skinned(n_props=256, nu=63, nv=31, ground_quads=64, seed=4321, extent=200.0):
+    """Config 2 the way PopulateAccel builds it: every prop is an object-space mesh baked to world space by
+    SkinTriangle with its entity's bone matrix (the one-bone overload, source/objects/AccelStruct.cpp:103-108, as for
+    a rigid prop) through vt_skin_triangles; entity 0 = one-sided world (ground + room)."""
+    from . import binding
+
+    rng = np.random.default_rng(seed)
+    parts = [heightfield(ground_quads, extent, 2.0, seed, 0.03), box([-extent / 2, -extent / 2, -8.0], [extent / 2, extent / 2, 80.0], True, material=1)]
+    rots = _random_rotations(rng, n_props)
+    pos = np.stack([rng.uniform(-extent * 0.45, extent * 0.45, n_props), rng.uniform(-extent * 0.45, extent * 0.45, n_props),
+                    rng.uniform(4.0, 40.0, n_props)], -1)
+    scl = rng.uniform(2.0, 6.0, n_props)
+    ident = rigid_mat4(np.eye(3), (0, 0, 0))
+    for e in range(n_props):
+        obj = torus(nu, nv, seed=seed + e, material=2 + (e % 6), ent_idx=e + 1)
+        parts.append(binding.skin_triangles(obj, None, rigid_mat4(rots[e], pos[e], scl[e])[None], ident[None]))
+    mats = abi.default_materials(8)
+    mats["surf_flags"][1] = abi.VT_SURF_SKY
+    mats["colour"][2:, :3] = rng.uniform(0.2, 1.0, (6, 3))
+    ents = np.zeros(n_props + 1, abi.ENTITY)
+    ents["id"] = np.concatenate([[0], 100 + np.arange(n_props)])
+    ents["colour"] = 1.0
+    ents["colour"][1:, :3] = rng.uniform(0.5, 1.0, (n_props, 3))
+    return abi.SceneData(np.concatenate(parts), mats, ents)
+
+
 def leaf_texture(size=256, seed=5, clamp=False):
     """Synthetic RGBA8888 'leaf' texture with a full mip chain, returned in VTF memory
     order (smallest mip first, libs/VTFParser/VTFParser.cpp:44-78)."""
