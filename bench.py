@@ -28,7 +28,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 for multi-rank launches; the host side of this engine (triangle set-up, hierarchy
+# build, flatten) is OpenMP code, so give every rank its share of the host cores before any OpenMP runtime loads.
+_world = int(os.environ.get("WORLD_SIZE", "1"))
+if _world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _world))
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -213,16 +219,21 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — vistrace_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
 
     t0 = time.time()
     scene = make_scene()
     rays = primary_rays()
     n = len(rays)
     accel = vt.Accel(local_rank)
-    accel.populate(scene)
+    if world > 1:  # the hierarchy is built once (rank 0) and replicated over NCCL; every GPU holds the whole scene
+        from vistrace_b200 import shard
+
+        accel.populate(scene, bvh=shard.replicate_bvh(vt.build_bvh(scene) if rank == 0 else None, device=dev))
+    else:
+        accel.populate(scene)
     st = accel.stats()
     if rank == 0:
         log(f"[bench] scene {st['n_tris']} tris, {st['node_count']} nodes, {st['device_bytes'] / 1e6:.0f} MB resident, setup {time.time() - t0:.1f}s")

@@ -16,7 +16,9 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 scene = scenes.scene_props(8, 31, 15, 16)
 rays = scenes.pinhole_rays(401, 203, (0, -95, 40), (0, 0, 10))
-accel = vt.Accel(local).populate(scene)
+dev = torch.device("cuda", local)
+bvh = shard.replicate_bvh(vt.build_bvh(scene) if rank == 0 else None, device=dev)  # built once, replicated over NCCL
+accel = vt.Accel(local).populate(scene, bvh=bvh)
 full = shard.trace_sharded(lambda r: accel.traverse(r), rays, device=torch.device("cuda", local))
 single = accel.traverse(rays)
 assert full.tobytes() == single.tobytes(), "sharded result differs from the single-GPU result"

@@ -31,7 +31,10 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     scene, z = load_golden("props_small")
     cpu = oracle.CpuScene(scene, "port", build_bvh=False)
-    cpu.set_bvh(z["nodes"], z["prim_indices"])
+    # the hierarchy exists on rank 0 only and is replicated by broadcast (as bench.py --gpus N does over NCCL)
+    nodes, prims = shard.replicate_bvh((z["nodes"], z["prim_indices"]) if rank == 0 else None)
+    assert nodes.tobytes() == z["nodes"].tobytes() and prims.tobytes() == z["prim_indices"].astype(np.uint64).tobytes()
+    cpu.set_bvh(nodes, prims)
     rays = z["rays"][:5001]  # odd size: ragged shards
     full = shard.trace_sharded(lambda r: cpu.traverse(r, threads=1)["hits"], rays)
     # per-rank partial framebuffers summed with one reduce (the bench's collective)

@@ -1,5 +1,6 @@
-mkdir -p gpurun_out/c10
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/c10/pytest.log
-timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/c10/bench.json 2> gpurun_out/c10/bench.err
-for t in 131072 524288 1048576; do VT_WAVE_TILE=$t timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('tile',$t, d['e2e'])" ; done > gpurun_out/c10/tiles.log 2>&1
-cat gpurun_out/c10/pytest.log; cat gpurun_out/c10/bench.json; tail -n 3 gpurun_out/c10/bench.err; cat gpurun_out/c10/tiles.log
+mkdir -p gpurun_out/m2
+nvidia-smi -L > gpurun_out/m2/smi.txt; nproc >> gpurun_out/m2/smi.txt
+timeout 600 python -m pytest tests -m gpu -x -q -k "two_gpu or accumulate or config2" 2>&1 | tail -5 > gpurun_out/m2/pytest.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/m2/bench2.json 2> gpurun_out/m2/bench2.err
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu > gpurun_out/m2/bench1.json 2> gpurun_out/m2/bench1.err
+cat gpurun_out/m2/smi.txt gpurun_out/m2/pytest.log; cat gpurun_out/m2/bench2.json gpurun_out/m2/bench1.json | cut -c1-900; tail -n 4 gpurun_out/m2/bench2.err

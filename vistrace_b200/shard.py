@@ -42,3 +42,29 @@ def trace_sharded(trace_fn, rays, group=None, device=None):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     b, e = shard_range(len(rays), rank, world)
     return gather_hits(trace_fn(rays[b:e]), len(rays), group, device)
+
+
+def replicate_bvh(bvh, group=None, device=None, src=0):
+    """Rank `src` built the hierarchy (bvh = (nodes, prim_indices) in bvh::Bvh<float> form); every other rank passes
+    None and receives a bit-identical replica through two broadcasts (NCCL over NVLink when `device` is a GPU) —
+    the hierarchy is built ONCE per job, not once per GPU."""
+    rank = dist.get_rank(group)
+    dev = device if device is not None else torch.device("cpu")
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    if rank == src:
+        nodes = np.ascontiguousarray(bvh[0], abi.NODE)
+        prims = np.ascontiguousarray(bvh[1], np.uint64)
+        counts = torch.tensor([len(nodes), len(prims)], dtype=torch.int64, device=dev)
+    dist.broadcast(counts, src=src, group=group)
+    n_nodes, n_prims = (int(v) for v in counts.cpu())
+    if rank == src:
+        t_nodes = torch.from_numpy(nodes.view(np.uint8).reshape(-1).copy()).to(dev)
+        t_prims = torch.from_numpy(prims.view(np.int64).copy()).to(dev)
+    else:
+        t_nodes = torch.empty(n_nodes * abi.NODE.itemsize, dtype=torch.uint8, device=dev)
+        t_prims = torch.empty(n_prims, dtype=torch.int64, device=dev)
+    dist.broadcast(t_nodes, src=src, group=group)
+    dist.broadcast(t_prims, src=src, group=group)
+    if rank == src:
+        return nodes, prims
+    return np.frombuffer(t_nodes.cpu().numpy().tobytes(), abi.NODE), t_prims.cpu().numpy().view(np.uint64)
