@@ -249,6 +249,15 @@ int vt_accel_trace_result(vt_accel *accel, const vt_ray *rays, const vt_hit *hit
 int vt_accel_bounce_rays(vt_accel *accel, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed,
                          vt_ray *out_rays, uint64_t *live_out, uint32_t flags, void *stream);
 
+/* Shadow-ray generation on the device ("primary + shadow rays"): for every non-sky hit in attrs[0, n) one ray from
+ * vistrace.CalcRayOrigin(pos, geometric normal on the viewer's side) (source/VisTrace.cpp:1478-1519) into out_rays[i]:
+ *   point_light == 0: direction = light (a sun direction, used as given), tMax = tmax;
+ *   point_light != 0: direction = light - origin, tMax = 1 (t is parametric, source/objects/AccelStruct.cpp:810-815).
+ * Misses and sky hits leave MASKED slots (tmax < 0).  Trace the result with VT_TRAVERSE_ANY_HIT for an occlusion
+ * query.  live_out (nullable, host pointer) receives the number of rays spawned and makes the call synchronous. */
+int vt_accel_shadow_rays(vt_accel *accel, const vt_attr *attrs, uint64_t n, const float light[3], int point_light,
+                         float tmax, vt_ray *out_rays, uint64_t *live_out, uint32_t flags, void *stream);
+
 /* The "primary + diffuse" wave of the headline benchmark in one call: traverse rays[0, n), build
  * the TraceResult of every hit, spawn spp bounce rays per hit (as vt_accel_bounce_rays) and
  * traverse those.  Out: hits[n], bounce_hits[n*spp]; optional attrs[n], bounce_rays[n*spp]

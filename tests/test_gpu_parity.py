@@ -114,7 +114,17 @@ def test_config2_props_primary_and_shadow(vt, oracle_mod, kind, layout):
     rays = scenes.pinhole_rays(480, 270, (0, -95, 40), (0, 0, 10))
     accel, cpu, hits, attrs, want = _check_against(vt, oracle_mod, scene, rays, kind, "product", layout)
     assert len(np.unique(attrs["ent_id"][hits["prim"] != abi.VT_MISS])) > 5  # several entities visible
-    shadow, _ = scenes.shadow_rays(attrs)
+    shadow, parent = scenes.shadow_rays(attrs)
+    # the device-side generator (K3b) writes the same rays into their parents' slots, masked slots elsewhere
+    sun = np.array((0.3, 0.2, 0.93), np.float32)
+    sun = (sun / np.sqrt((sun * sun).sum(dtype=np.float32))).astype(np.float32)
+    dev_rays, live = accel.shadow_rays(attrs, sun)
+    assert live == len(shadow) and (dev_rays["tmax"] < 0).sum() == len(attrs) - live
+    assert dev_rays[parent].tobytes() == shadow.tobytes()
+    light = np.array((10.0, -20.0, 60.0), np.float32)
+    pt_rays, _ = accel.shadow_rays(attrs, light, point_light=True)
+    np.testing.assert_array_equal(pt_rays["d"][parent], (light[None, :] - shadow["o"]).astype(np.float32))
+    assert (pt_rays["tmax"][parent] == 1.0).all()
     got = accel.traverse(shadow)
     assert same_hits(got, cpu.traverse(shadow)["hits"], layout)
     occl = accel.traverse(shadow, any_hit=True)  # early-out variant: only hit / no-hit is defined

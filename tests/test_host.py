@@ -279,8 +279,8 @@ def test_quad_layout_structure_and_walk(oracle_mod, scene_name):
     quads, order = qb["quads"], qb["leaf_order"]
     assert sorted(order.tolist()) == list(range(scene.n_tris)) and qb["root_leaf_count"] == 0
     assert 0 < qb["max_stack"] <= 64 and len(quads) < (len(nodes) - 1) // 2  # fewer, wider nodes
-    valid = (quads["valid"][:, None] >> np.arange(4)) & 1
     refs = quads["ref"]
+    valid = (refs != 0xFFFFFFFF).astype(np.uint8)
     count, idx = refs >> 28, refs & 0x0FFFFFFF
     assert (refs[valid == 0] == 0xFFFFFFFF).all() and valid.sum(1).min() >= 2
     inner = (valid == 1) & (count == 0)
@@ -289,7 +289,8 @@ def test_quad_layout_structure_and_walk(oracle_mod, scene_name):
     runs = sorted(zip(idx[leaf].tolist(), count[leaf].tolist()))
     assert runs[0][0] == 0 and all(a + n == b for (a, n), (b, _) in zip(runs, runs[1:])) and runs[-1][0] + runs[-1][1] == scene.n_tris
     # decoded planes: exact floats on the power-of-two grid
-    scale = (quads["exp"].astype(np.uint32) << 23).view(np.float32).astype(np.float64)                    # [quad, axis]
+    scale = quads["scale"].astype(np.float64)                                                            # [quad, axis], powers of two
+    assert ((quads["scale"].view(np.uint32) & 0x007FFFFF) == 0).all()
     magic = (np.uint32(0x4B000000) | quads["q"].astype(np.uint32)).view(np.float32).astype(np.float64)   # [quad, axis, lo/hi, child]
     plane = magic * scale[:, :, None, None] + quads["origin_adj"].astype(np.float64)[:, :, None, None]
     assert (plane.astype(np.float32).astype(np.float64) == plane).all()

@@ -30,6 +30,7 @@ SYMBOLS = {
     "vt_accel_traverse_cones": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_result": (_i32, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "vt_accel_bounce_rays": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _u32, _vp]),
+    "vt_accel_shadow_rays": (_i32, [_vp, _vp, _u64, _vp, _i32, C.c_float, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "vt_accel_render_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, C.c_float, _vp, _vp]),
     "vt_accel_accumulate_sky": (_i32, [_vp, _vp, _vp, _u64, _u32, C.c_float, _vp, _vp]),
@@ -150,8 +151,7 @@ def compact_pairs(pairs):
     return out
 
 
-QUAD = np.dtype([("origin_adj", np.float32, 3), ("exp", np.uint8, 3), ("valid", np.uint8), ("q", np.uint8, (3, 2, 4)), ("pad", np.uint32, 2),
-                 ("ref", np.uint32, 4)])
+QUAD = np.dtype([("origin_adj", np.float32, 3), ("scale", np.float32, 3), ("q", np.uint8, (3, 2, 4)), ("ref", np.uint32, 4)])
 assert QUAD.itemsize == 64
 
 
@@ -273,6 +273,21 @@ class Accel:
         _check(self.L.vt_accel_bounce_rays(self.h, attrs.ctypes.data, len(attrs), spp, seed, out.ctypes.data, C.addressof(live), 0, None),
                "vt_accel_bounce_rays")
         return out, live.value
+
+    def shadow_rays(self, attrs, light, point_light=False, tmax=3.4028234663852886e38):
+        """Host-buffer shadow-ray generation: (rays[n] with masked slots, number spawned)."""
+        attrs = np.ascontiguousarray(attrs, abi.ATTR)
+        out = np.zeros(len(attrs), abi.RAY)
+        live = C.c_uint64(0)
+        lv = (C.c_float * 3)(*[float(v) for v in light])
+        _check(self.L.vt_accel_shadow_rays(self.h, attrs.ctypes.data, len(attrs), C.cast(lv, _vp), int(point_light), tmax, out.ctypes.data,
+                                           C.addressof(live), 0, None), "vt_accel_shadow_rays")
+        return out, live.value
+
+    def shadow_rays_device(self, d_attrs, n, light, d_out, point_light=False, tmax=3.4028234663852886e38, stream=None):
+        lv = (C.c_float * 3)(*[float(v) for v in light])
+        _check(self.L.vt_accel_shadow_rays(self.h, _ptr(d_attrs), n, C.cast(lv, _vp), int(point_light), tmax, _ptr(d_out), None,
+                                           abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)), "vt_accel_shadow_rays")
 
     def bounce_rays_device(self, d_attrs, n, spp, seed, d_out, stream=None):
         _check(self.L.vt_accel_bounce_rays(self.h, _ptr(d_attrs), n, spp, seed, _ptr(d_out), None, abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)),

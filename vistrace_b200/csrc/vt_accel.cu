@@ -658,6 +658,39 @@ void AccelStruct::BounceRays(const vt_attr *attrs, uint64_t n, uint32_t spp, uin
     }
 }
 
+void AccelStruct::ShadowRays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out_rays,
+                             uint64_t *live_out, uint32_t flags, void *stream_) {
+    if (live_out) *live_out = 0;
+    if (n == 0) return;
+    if (!attrs || !out_rays || !light) throw std::runtime_error("shadow_rays: null argument");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    const bool dev_ptrs = (flags & VT_TRAVERSE_DEVICE_PTRS) != 0;
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : (dev_ptrs ? (cudaStream_t) nullptr : D.own_stream);
+    D.live.ensure(1);
+    if (live_out) VT_CUDA(cudaMemsetAsync(D.live.p, 0, sizeof(unsigned long long), stream));
+    const vt_attr *d_attrs = attrs;
+    vt_ray *d_out = out_rays;
+    if (!dev_ptrs) {
+        D.s_attrs.ensure(n);
+        D.s_rays.ensure(n);
+        VT_CUDA(cudaMemcpyAsync(D.s_attrs.p, attrs, n * sizeof(vt_attr), cudaMemcpyHostToDevice, stream));
+        d_attrs = D.s_attrs.p;
+        d_out = D.s_rays.p;
+    }
+    VT_CUDA(vt_launch_shadow_rays(d_attrs, n, light, point_light, tmax, d_out, live_out ? D.live.p : nullptr, stream));
+    mLaunches++;
+    if (!dev_ptrs) VT_CUDA(cudaMemcpyAsync(out_rays, d_out, n * sizeof(vt_ray), cudaMemcpyDeviceToHost, stream));
+    if (live_out) {
+        unsigned long long v = 0;
+        VT_CUDA(cudaMemcpyAsync(&v, D.live.p, sizeof(v), cudaMemcpyDeviceToHost, stream));
+        VT_CUDA(cudaStreamSynchronize(stream));
+        *live_out = v;
+    } else if (!dev_ptrs) {
+        VT_CUDA(cudaStreamSynchronize(stream));
+    }
+}
+
 void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, vt_hit *hits, vt_attr *attrs,
                                    vt_ray *bounce_rays, vt_hit *bounce_hits, uint64_t *live_out, uint32_t flags,
                                    void *stream_) {
@@ -901,6 +934,15 @@ int vt_accel_bounce_rays(vt_accel *a, const vt_attr *attrs, uint64_t n, uint32_t
     VT_TRY
     if (!a) throw std::runtime_error("null argument");
     a->impl.BounceRays(attrs, n, spp, seed, out_rays, live_out, flags, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_shadow_rays(vt_accel *a, const vt_attr *attrs, uint64_t n, const float light[3], int point_light, float tmax,
+                         vt_ray *out_rays, uint64_t *live_out, uint32_t flags, void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.ShadowRays(attrs, n, light, point_light != 0, tmax, out_rays, live_out, flags, stream);
     return 0;
     VT_CATCH(1)
 }

@@ -551,7 +551,7 @@ struct QuadBuilder {
             if (!ok) break;
             const double s = std::ldexp(1.0, E);
             q.origin_adj[a] = (float)((double)(k - 8388608) * s);
-            q.exp[a] = (uint8_t)(E + 127);
+            q.scale[a] = (float)s;
             for (int i = 0; i < 4; i++) {
                 if (i < nk) {
                     const vt_node &c = bvh.nodes[kids[i]];
@@ -567,7 +567,6 @@ struct QuadBuilder {
         for (int i = 0; i < 4; i++) q.ref[i] = 0xFFFFFFFFu;
         for (int i = 0; i < nk && ok; i++) {
             const vt_node &c = bvh.nodes[kids[i]];
-            q.valid |= (uint8_t)(1u << i);
             if (c.prim_count == 0) continue;
             if (c.prim_count > 15) {
                 fail("quad layout: a leaf holds more than 15 triangles");

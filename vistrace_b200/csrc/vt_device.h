@@ -55,14 +55,12 @@ static_assert(sizeof(VtCPair) == 32, "compact pair layout");
 // grandchildren, largest box first), so a ray needs about half as many dependent node fetches.  Same
 // conservative power-of-two grid as VtCPair, shared by the four children; 64 bytes = two LDG.E.256.
 // Children are TAGGED references: bits 28-31 = triangle count (0 = inner quad), bits 0-27 = quad index
-// or first triangle slot; empty slots have valid bit 0 and ref 0xFFFFFFFF.
+// or first triangle slot; empty slots have ref 0xFFFFFFFF.
 struct alignas(64) VtQuad {
     float origin_adj[3];  // (k - 2^23) * 2^E per axis
-    uint8_t exp[3];       // biased exponent of 2^E per axis
-    uint8_t valid;        // bit i: child i exists
+    float scale[3];       // 2^E per axis, as a float
     uint8_t q[3][2][4];   // [axis][lo, hi][child]
-    uint32_t pad[2];
-    uint32_t ref[4];
+    uint32_t ref[4];      // tagged child references; 0xFFFFFFFF = empty slot (its box is inverted: q_lo = 255, q_hi = 0)
 };
 static_assert(sizeof(VtQuad) == 64, "quad layout");
 

@@ -138,6 +138,9 @@ public:
     // spp cosine-weighted bounce rays per non-sky hit, slot i*spp+s; *live_out = rays spawned.
     void BounceRays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays, uint64_t *live_out,
                     uint32_t flags, void *stream);
+    // One shadow ray per non-sky hit: origin = CalcRayOrigin(pos, geometric normal), toward a directional or point light.
+    void ShadowRays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out_rays,
+                    uint64_t *live_out, uint32_t flags, void *stream);
     // "primary + diffuse" wave in one call: traverse the primary rays, build their TraceResults, spawn
     // spp bounce rays per hit on the device and traverse those.  Host pointers are processed in tiles
     // on several streams so the PCIe copies overlap the kernels.

@@ -14,7 +14,7 @@
 #endif
 
 #ifndef VT_COMPACT_MIN_BLOCKS
-#define VT_COMPACT_MIN_BLOCKS 8
+#define VT_COMPACT_MIN_BLOCKS 9
 #endif
 
 struct VtLaunchConfig {
@@ -39,6 +39,8 @@ cudaError_t vt_launch_trace_result(const VtSceneView &S, const vt_ray *rays, con
 // masked slots (tmax < 0) elsewhere; *live += spawned rays.  And a pinhole primary-ray generator.
 cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, uint64_t slot_offset,
                                   vt_ray *out, unsigned long long *live, cudaStream_t stream);
+cudaError_t vt_launch_shadow_rays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out,
+                                  unsigned long long *live, cudaStream_t stream);
 cudaError_t vt_launch_pinhole_rays(const float *cam12, uint32_t width, uint32_t height, vt_ray *out, cudaStream_t stream);
 
 // K4 — fb[i] += weight * albedo_i * (escaped bounce rays of pixel i) / spp, RGBFFF framebuffer.

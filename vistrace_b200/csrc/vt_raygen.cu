@@ -82,6 +82,38 @@ k_bounce_rays(const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t 
     }
 }
 
+// Shadow rays (config 2 / 5: "primary + shadow"): one ray per non-sky hit from CalcRayOrigin(pos, geometric normal on
+// the viewer's side) along a fixed direction (a sun) with the given tmax, or toward a point light (dir = light - origin,
+// tmax = 1: t is parametric, source/objects/AccelStruct.cpp:810-815).  Misses and sky hits leave masked slots.
+__global__ void __launch_bounds__(256)
+k_shadow_rays(const vt_attr *__restrict__ attrs, unsigned long long n, float lx, float ly, float lz, int point_light, float tmax,
+              vt_ray *__restrict__ out, unsigned long long *__restrict__ live) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool spawned = false;
+    if (i < n) {
+        const float4 *a = reinterpret_cast<const float4 *>(attrs + i);
+        const float4 q7 = __ldg(a + 7);
+        const uint32_t flags = __float_as_uint(q7.z), prim = __float_as_uint(q7.w);
+        float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 0.f, -1.f);  // masked slot
+        if (prim != VT_MISS && !(flags & VT_ATTR_HIT_SKY)) {
+            const float4 q0 = __ldg(a), q4 = __ldg(a + 4);
+            const float sgn = (flags & VT_ATTR_FRONT_FACING) ? 1.f : -1.f;
+            const V3 o = mk3(ray_origin_1(q0.x, q4.x * sgn), ray_origin_1(q0.y, q4.y * sgn), ray_origin_1(q0.z, q4.z * sgn));
+            const V3 d = point_light ? mk3(lx - o.x, ly - o.y, lz - o.z) : mk3(lx, ly, lz);
+            ro = make_float4(o.x, o.y, o.z, 0.f);
+            rd = make_float4(d.x, d.y, d.z, point_light ? 1.f : tmax);
+            spawned = true;
+        }
+        float4 *o4 = reinterpret_cast<float4 *>(out + i);
+        o4[0] = ro;
+        o4[1] = rd;
+    }
+    if (live) {
+        const unsigned m = __ballot_sync(0xffffffffu, spawned);
+        if ((threadIdx.x & 31u) == 0 && m) atomicAdd(live, (unsigned long long)__popc(m));
+    }
+}
+
 // Pinhole primary rays, pixel-centre sampling, row-major (index = width * j + i) — the loop of
 // libs/bvh/test/benchmark.cpp:129-150.  cam = {eye, image_u, image_v, dir} (already scaled).
 __global__ void __launch_bounds__(256)
@@ -156,6 +188,15 @@ cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp
     if (total == 0) return cudaSuccess;
     const unsigned block = 256;
     k_bounce_rays<<<(unsigned)((total + block - 1) / block), block, 0, stream>>>(attrs, n, spp, seed, slot_offset, out, live);
+    return cudaGetLastError();
+}
+
+cudaError_t vt_launch_shadow_rays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out,
+                                  unsigned long long *live, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned block = 256;
+    k_shadow_rays<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(attrs, n, light[0], light[1], light[2], point_light ? 1 : 0,
+                                                                            tmax, out, live);
     return cudaGetLastError();
 }
 

@@ -154,6 +154,36 @@ VT_DEV void ldg256u(const void *p, uint4 &lo, uint4 &hi) {
 // Children come back as TAGGED references: bits 28-31 = triangle count (0 = inner), bits 0-27 = pair
 // index or first triangle slot.  `magic` is 0x4B000000 read from the kernel parameter block, so PRMT
 // takes it as a constant-bank operand and its selector stays an immediate.
+// Software prefetch of records whose address is known a round or more before they are read: the first triangle of
+// a leaf the lane just selected, and the children it pushed.  0 = off, 1 = prefetch.global.L2, 2 = prefetch.global.L1.
+#ifndef VT_PREFETCH
+#define VT_PREFETCH 0
+#endif
+VT_DEV void vt_prefetch(const void *p) {
+#if VT_PREFETCH == 1
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#elif VT_PREFETCH == 2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+VT_DEV void vt_prefetch_ref(const VtSceneView &S, uint32_t ref, bool quad) {
+#if VT_PREFETCH
+    const uint32_t idx = ref & 0x0FFFFFFFu;
+    if (ref >> 28) vt_prefetch(S.tris + idx);
+    else if (quad) vt_prefetch(S.quads + idx);
+    else vt_prefetch(S.cpairs + idx);
+#else
+    (void)S, (void)ref, (void)quad;
+#endif
+}
+#ifndef VT_PREFETCH_LEAF
+#define VT_PREFETCH_LEAF 1
+#endif
+#ifndef VT_PREFETCH_FAR
+#define VT_PREFETCH_FAR 1
+#endif
 #ifndef VT_LEAF_RUN_PER_ROUND
 #define VT_LEAF_RUN_PER_ROUND 1
 #endif
@@ -207,16 +237,14 @@ VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const R
     uint4 a0, a1, b0, b1;
     ldg256u(quads + cur, a0, a1);
     ldg256u(reinterpret_cast<const char *>(quads + cur) + 32, b0, b1);
-    const float sx = __uint_as_float((a0.w & 0xffu) << 23);
-    const float sy = __uint_as_float((a0.w << 15) & 0x7f800000u);
-    const float sz = __uint_as_float((a0.w << 7) & 0x7f800000u);
+    // words: a0 = {origin_adj.xyz, scale.x}, a1 = {scale.y, scale.z, lo_x[4], hi_x[4]}, b0 = {lo_y[4], hi_y[4], lo_z[4], hi_z[4]}, b1 = refs
     const float ax = __uint_as_float(a0.x), ay = __uint_as_float(a0.y), az = __uint_as_float(a0.z);
-    // words: a1 = {lo_x[4], hi_x[4], lo_y[4], hi_y[4]}, b0.x = lo_z[4], b0.y = hi_z[4]; a negative direction
-    // makes hi the near plane (node_intersectors.hpp:20-26)
+    const float sx = __uint_as_float(a0.w), sy = __uint_as_float(a1.x), sz = __uint_as_float(a1.y);
+    // a negative direction makes hi the near plane (node_intersectors.hpp:20-26)
     const bool ox = signbit(ray.inv.x), oy = signbit(ray.inv.y), oz = signbit(ray.inv.z);
-    const uint32_t nx = ox ? a1.y : a1.x, fx = ox ? a1.x : a1.y;
-    const uint32_t ny = oy ? a1.w : a1.z, fy = oy ? a1.z : a1.w;
-    const uint32_t nz = oz ? b0.y : b0.x, fz = oz ? b0.x : b0.y;
+    const uint32_t nx = ox ? a1.w : a1.z, fx = ox ? a1.z : a1.w;
+    const uint32_t ny = oy ? b0.y : b0.x, fy = oy ? b0.x : b0.y;
+    const uint32_t nz = oz ? b0.w : b0.z, fz = oz ? b0.z : b0.w;
     r[0] = b1.x, r[1] = b1.y, r[2] = b1.z, r[3] = b1.w;
 #define VT_PLANE(q, sel, s, a) fmaf(__uint_as_float(__byte_perm(q, magic, sel)), s, a)
 #define VT_CHILD(i, sel)                                                                   \
@@ -229,7 +257,8 @@ VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const R
         const float x2 = fmaf(VT_PLANE(fz, sel, sz, az), ray.inv.z, ray.so.z);             \
         const float en = fmaxf(e0, fmaxf(e1, fmaxf(e2, ray.tmin)));                        \
         const float ex = fminf(x0, fminf(x1, fminf(x2, ray.tmax)));                        \
-        const bool hit = en <= ex && (a0.w & (1u << (24 + i)));                            \
+        /* an empty slot's inverted box can look hit after rounding when the node is tiny and far: test the ref too */ \
+        const bool hit = r[i] != VT_REF_DONE && en <= ex;                                  \
         /* en >= tmin >= 0: its bit pattern orders like the value (-0.0 sorts first) */    \
         k[i] = hit ? (int)((__float_as_uint(en) & ~3u) | (unsigned)i) : 0x7FFFFFFF;        \
     }
@@ -438,8 +467,10 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                    unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
+    // the layouts served by this kernel validate the worst-case stack depth on the host (<= VT_STACK_SIZE), so
+    // the stack is a bare pointer: push = store + increment, pop = decrement + load
     uint32_t stack[VT_STACK_SIZE];
-    int sp = 0;
+    uint32_t *sp = stack;
     uint32_t cur = VT_REF_DONE;  // VT_REF_DONE: nothing left to visit
     bool alive = false;          // lane owns a ray whose result is not written yet
     bool exhausted = false;      // warp-uniform: the ray queue has run dry
@@ -475,7 +506,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     vt_ray in{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                     init_ray(in, r);
                     alive = true;
-                    sp = 0;
+                    sp = stack;
                     if (!(in.tmin >= 0.f) || !(in.tmax > in.tmin)) {  // AccelStruct.cpp:805-806 -> counted miss; tmax < 0: masked slot
                         if (!(in.tmax < 0.f)) n_invalid++;
                     } else if (S.root_leaf_count) {
@@ -509,10 +540,9 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     }
                     if (ANY_HIT && any) {
                         cur = VT_REF_DONE;
-                        sp = 0;
-                    } else if (sp > 0) {
-                        sp--;
-                        cur = stack[sp & (VT_STACK_SIZE - 1)];
+                        sp = stack;
+                    } else if (sp != stack) {
+                        cur = *--sp;
                     } else {
                         cur = VT_REF_DONE;
                     }
@@ -521,11 +551,10 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     const bool hit = intersect_triangle<ALPHA>(S, cur & VT_REF_MASK, r);
                     if (ANY_HIT && hit) {
                         cur = VT_REF_DONE;
-                        sp = 0;
+                        sp = stack;
                     } else if ((cur >> VT_REF_SHIFT) == 1u) {  // run finished: pop
-                        if (sp > 0) {
-                            sp--;
-                            cur = stack[sp & (VT_STACK_SIZE - 1)];
+                        if (sp != stack) {
+                            cur = *--sp;
                         } else {
                             cur = VT_REF_DONE;
                         }
@@ -541,14 +570,17 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     uint32_t cr[4];
                     slab_quad(S.quads, cur, magic, r, k, cr);
                     // farthest first, so the nearest pending child is popped first
-                    if (k[3] != 0x7FFFFFFF) stack[(sp++) & (VT_STACK_SIZE - 1)] = cr[3];
-                    if (k[2] != 0x7FFFFFFF) stack[(sp++) & (VT_STACK_SIZE - 1)] = cr[2];
-                    if (k[1] != 0x7FFFFFFF) stack[(sp++) & (VT_STACK_SIZE - 1)] = cr[1];
+                    if (k[3] != 0x7FFFFFFF) *sp++ = cr[3];
+                    if (k[2] != 0x7FFFFFFF) *sp++ = cr[2];
+                    if (k[1] != 0x7FFFFFFF) {
+                        *sp++ = cr[1];
+                        if (VT_PREFETCH_FAR) vt_prefetch_ref(S, cr[1], true);  // the next one to be popped
+                    }
                     if (k[0] != 0x7FFFFFFF) {
                         cur = cr[0];
-                    } else if (sp > 0) {
-                        sp--;
-                        cur = stack[sp & (VT_STACK_SIZE - 1)];
+                        if (VT_PREFETCH_LEAF && (cur >> VT_REF_SHIFT)) vt_prefetch(S.tris + (cur & VT_REF_MASK));
+                    } else if (sp != stack) {
+                        cur = *--sp;
                     } else {
                         cur = VT_REF_DONE;
                     }
@@ -561,15 +593,11 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                 const bool take_r = hit_r && (!hit_l || le > re);  // near child first; ties keep the left child first
                 const uint32_t next = take_r ? rref : lref;
                 const uint32_t far_ = take_r ? lref : rref;
-                if (hit_l && hit_r) {
-                    stack[sp & (VT_STACK_SIZE - 1)] = far_;
-                    sp++;
-                }
+                if (hit_l && hit_r) *sp++ = far_;
                 if (hit_l || hit_r) {
                     cur = next;
-                } else if (sp > 0) {
-                    sp--;
-                    cur = stack[sp & (VT_STACK_SIZE - 1)];
+                } else if (sp != stack) {
+                    cur = *--sp;
                 } else {
                     cur = VT_REF_DONE;
                 }
