@@ -56,6 +56,7 @@ def _lib(kind):
         "set_bvh": (None, [vp, vp, u64, vp]),
         "traverse": (C.c_double, [vp, vp, u64, vp, vp, i32, vp]),
         "trace_result": (None, [vp, vp, vp, u64, vp, i32]),
+        "trace_result_cones": (None, [vp, vp, vp, vp, u64, vp, i32]),
         "sample": (None, [vp, i32, vp, u64, vp]),
         "node_intersect": (None, [vp, vp, vp]),
         "tri_intersect": (i32, [vp, u64, vp, vp]),
@@ -143,10 +144,15 @@ class CpuScene:
             best = min(best, self.lib.traverse(self.h, rays.ctypes.data, len(rays), hits.ctypes.data, None, threads, None))
         return best
 
-    def trace_result(self, rays, hits, threads=0):
+    def trace_result(self, rays, hits, threads=0, cones=None):
+        """TraceResult records for given hits; cones = [n, 2] {coneWidth, coneAngle} or None (mip 0)."""
         rays = np.ascontiguousarray(rays, abi.RAY)
         hits = np.ascontiguousarray(hits, abi.HIT)
         attrs = np.zeros(len(rays), abi.ATTR)
+        if cones is not None:
+            cones = np.ascontiguousarray(cones, np.float32).reshape(len(rays), 2)
+            self.lib.trace_result_cones(self.h, rays.ctypes.data, hits.ctypes.data, cones.ctypes.data, len(rays), attrs.ctypes.data, threads)
+            return attrs
         self.lib.trace_result(self.h, rays.ctypes.data, hits.ctypes.data, len(rays), attrs.ctypes.data, threads)
         return attrs
 

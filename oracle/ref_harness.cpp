@@ -371,6 +371,23 @@ void vtref_trace_result(void *h, const vt_ray *rays, const vt_hit *hits, uint64_
     }
 }
 
+// Same with per-ray texture-LOD cones {coneWidth, coneAngle} (source/objects/AccelStruct.cpp:795-803, :827).
+void vtref_trace_result_cones(void *h, const vt_ray *rays, const vt_hit *hits, const float *cones, uint64_t n, vt_attr *attrs,
+                              int threads) {
+    AccelStruct &a = static_cast<RefScene *>(h)->accel;
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+    for (int64_t i = 0; i < static_cast<int64_t>(n); i++) {
+        if (hits[i].prim == VT_MISS) {
+            std::memset(&attrs[i], 0, sizeof(vt_attr));
+            attrs[i].prim = VT_MISS;
+        } else {
+            fill_attr(a, rays[i], hits[i].prim, hits[i].t, hits[i].u, hits[i].v, cones ? cones[2 * i] : -1.f,
+                      cones ? cones[2 * i + 1] : -1.f, attrs[i]);
+        }
+    }
+}
+
 // IVTFTexture::Sample(u, v, mip) through the reference sampler: in = n × (u, v, mip), out = n × rgba.
 void vtref_sample(void *h, int tex, const float *uvm, uint64_t n, float *rgba) {
     auto *rs = static_cast<RefScene *>(h);

@@ -739,6 +739,23 @@ void vto_trace_result(void *h, const vt_ray *rays, const vt_hit *hits, uint64_t 
     }
 }
 
+/* Same with per-ray texture-LOD cones {coneWidth, coneAngle} (the 5th/6th arguments of accel:Traverse,
+ * source/objects/AccelStruct.cpp:795-803); cones == NULL -> (-1, -1). */
+void vto_trace_result_cones(void *h, const vt_ray *rays, const vt_hit *hits, const float *cones, uint64_t n, vt_attr *attrs, int threads) {
+    OScene *s = (OScene *)h;
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        if (hits[i].prim == VT_MISS) {
+            memset(&attrs[i], 0, sizeof(vt_attr));
+            attrs[i].prim = VT_MISS;
+        } else {
+            trace_result(s, &rays[i], hits[i].prim, hits[i].t, hits[i].u, hits[i].v, cones ? cones[2 * i] : -1.f,
+                         cones ? cones[2 * i + 1] : -1.f, &attrs[i]);
+        }
+    }
+}
+
 void vto_sample(void *h, int tex, const float *uvm, uint64_t n, float *rgba) {
     OScene *s = (OScene *)h;
     for (uint64_t i = 0; i < n; i++) {

@@ -240,6 +240,32 @@ def test_traversal_statistics_match_the_reference_counters(vt, oracle_mod):
     print(f"[stats] exact {want['steps']} steps / {want['isects']} tests; compact {steps} / {tests}; quad {qsteps} / {qtests}")
 
 
+@pytest.mark.parametrize("kind", oracle_kinds())
+def test_every_shading_branch_and_cone_lod(vt, oracle_mod, kind):
+    """K2 on a scene that reaches every TraceResult branch (source/objects/TraceResult.cpp:11-43, 89-253): one and two
+    normal maps, vertex-transition blending (smoothstep and masked), second base texture, the twelve detail blend
+    modes, MRAO, UV transforms / texScale, water — without cones (mip 0) and with per-ray cones (trilinear LOD from
+    CalcFootprint + TriUVInfoToTexLOD, source/Utils.h:75-78)."""
+    from test_oracle import _material_case
+    from vistrace_b200 import abi
+
+    scene, rays, cones = _material_case()
+    accel = vt.Accel(0).populate(scene)
+    cpu = oracle_mod.CpuScene(scene, kind, build_bvh=False)
+    cpu.set_bvh(*accel.get_bvh())
+    want = cpu.traverse(rays, want_attrs=True)
+    hits, attrs = accel.traverse(rays, want_attrs=True)
+    assert same_hits(hits, want["hits"], accel.layout)
+    for got_attrs, want_attrs in ((attrs, want["attrs"]), (accel.traverse(rays, want_attrs=True, cones=cones)[1], cpu.trace_result(rays, hits, cones=cones))):
+        err = attr_max_rel_err(got_attrs, want_attrs)
+        for f in ATTR_FLOAT_FIELDS:
+            assert err[f] <= 1e-5, (f, err[f])
+        for f in ATTR_INT_FIELDS:
+            assert err[f] == 0, (f, err[f])
+    hit = hits["prim"] != abi.VT_MISS
+    assert len(np.unique(scene.tris["material"][hits["prim"][hit]])) >= 17
+
+
 def test_trace_result_stage_alone(vt, oracle_mod):
     """K2 on its own: attributes for hits produced elsewhere (here: by the oracle)."""
     from vistrace_b200 import scenes

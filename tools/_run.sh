@@ -1,6 +1,7 @@
-mkdir -p gpurun_out/c12
-free -g | head -2 > gpurun_out/c12/mem.txt
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/c12/pytest.log
-timeout 1500 python tools/config_sweep.py --configs 1,2,4,3 --out gpurun_out/c12/sweep.jsonl > gpurun_out/c12/sweep.log 2>&1
-timeout 1500 python tools/config_sweep.py --configs 5 --out gpurun_out/c12/sweep.jsonl > gpurun_out/c12/sweep5.log 2>&1
-cat gpurun_out/c12/mem.txt gpurun_out/c12/pytest.log; tail -n 5 gpurun_out/c12/sweep.log | cut -c1-1500; tail -n 3 gpurun_out/c12/sweep5.log | cut -c1-2500
+mkdir -p gpurun_out/c13
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12 > gpurun_out/c13/pytest.log
+timeout 600 python tools/gpu_explore.py --quads 1582 --knobs "VT_LAYOUT=quad" > gpurun_out/c13/explore.log 2>&1
+for v in pfL2 pfL1 pfL2leaf pfL2far; do
+VT_LIB=$PWD/build/variants/lib_$v.so timeout 600 python tools/gpu_explore.py --quads 1582 --knobs "VT_LAYOUT=quad" > gpurun_out/c13/explore_$v.log 2>&1
+done
+cat gpurun_out/c13/pytest.log; grep -H knobs gpurun_out/c13/explore*.log | cut -c1-440

@@ -262,6 +262,77 @@ def leaf_texture(size=256, seed=5, clamp=False):
     return (size, size, len(mips), flags, np.concatenate(chain))
 
 
+def noise_texture(size=64, seed=1, clamp=False, kind="colour"):
+    """Synthetic RGBA8888 texture with a full mip chain in VTF memory order (smallest mip first).
+    kind: "colour" (smooth RGBA noise), "normal" (tangent-space normals around +Z), "blend" (r,g in the ranges
+    WorldVertexTransition blend modulate textures use)."""
+    lin = (np.arange(size) + 0.5) / size
+    x, y = np.meshgrid(lin, lin, indexing="xy")
+    ch = [value_noise(x * (5 + k), y * (5 + k), seed * 7 + k, 4) * 0.5 + 0.5 for k in range(4)]
+    if kind == "normal":
+        nx, ny = (ch[0] - 0.5) * 1.2, (ch[1] - 0.5) * 1.2
+        nz = np.sqrt(np.clip(1.0 - nx * nx - ny * ny, 0.05, 1.0))
+        img = np.stack([nx * 0.5 + 0.5, ny * 0.5 + 0.5, nz * 0.5 + 0.5, ch[3]], -1)
+    elif kind == "blend":
+        img = np.stack([ch[0] * 0.4, 0.3 + 0.5 * ch[1], ch[2], ch[3]], -1)
+    else:
+        img = np.stack(ch, -1)
+    mips = [np.clip(img, 0, 1)]
+    while mips[-1].shape[0] > 1:
+        m = mips[-1]
+        mips.append(0.25 * (m[0::2, 0::2] + m[1::2, 0::2] + m[0::2, 1::2] + m[1::2, 1::2]))
+    chain = [np.round(m * 255.0).astype(np.uint8).reshape(-1) for m in reversed(mips)]
+    flags = (abi.VT_TEXFLAG_CLAMPS | abi.VT_TEXFLAG_CLAMPT) if clamp else 0
+    return (size, size, len(mips), flags, np.concatenate(chain))
+
+
+def scene_materials(ground_quads=24, n_props=12, seed=31, extent=100.0):
+    """Every TraceResult shading-input branch (source/objects/TraceResult.cpp:89-253): normal maps (one and two,
+    blended), WorldVertexTransition blending (smoothstep and masked), second base texture, all detail blend modes of
+    TextureCombine (:11-43), MRAO (one and two), UV transforms and texScale, a water material.  Ground triangles
+    cycle through the materials and carry random vertex alphas (the blend factor, :72); props reuse them."""
+    rng = np.random.default_rng(seed)
+    texs = [noise_texture(64, 1), noise_texture(32, 2, clamp=True), noise_texture(32, 3, kind="blend"), noise_texture(64, 4, kind="normal"),
+            noise_texture(32, 5, kind="normal", clamp=True), noise_texture(32, 6), noise_texture(16, 7), noise_texture(64, 8)]
+    BASE, BASE2, BLEND, NORM, NORM2, MRAO, MRAO2, DETAIL = range(8)
+    n_detail_modes = 12  # DetailBlendMode 0..11 (Material.h:12-26); 10 and 11 fall through to the base colour
+    mats = abi.default_materials(6 + n_detail_modes)
+    mats["surf_flags"][1] = abi.VT_SURF_SKY
+    skew = (0.9, 0.2, 0.0, 0.13, -0.15, 1.1, 0.0, 0.37)  # mat2x4: col0 = (a, b, ., tx) drives u, col1 drives v
+    m = mats[0]  # blended ground: everything at once
+    m["base_texture"], m["base_texture2"], m["blend_texture"] = BASE, BASE2, BLEND
+    m["normal_map"], m["normal_map2"], m["mrao"], m["mrao2"] = NORM, NORM2, MRAO, MRAO2
+    m["base_tex_mat"], m["base_tex_mat2"], m["normal_map_mat"], m["blend_tex_mat"] = skew, abi._IDENT, skew, abi._IDENT
+    m["tex_scale"], m["colour"] = 2.0, (0.9, 0.8, 0.7, 0.95)
+    m = mats[2]  # masked blending (blendFactor = blend texture's green, :121-122)
+    m["base_texture"], m["base_texture2"], m["blend_texture"], m["masked_blending"] = BASE, BASE2, BLEND, 1
+    m = mats[3]  # single normal map + MRAO, no blending
+    m["base_texture"], m["normal_map"], m["mrao"], m["normal_map_mat"] = BASE, NORM, MRAO, skew
+    m = mats[4]  # masked blending WITHOUT a blend texture (blendFactor = 0.5, :110), two normal maps
+    m["base_texture"], m["base_texture2"], m["normal_map"], m["normal_map2"], m["masked_blending"] = BASE, BASE2, NORM, NORM2, 1
+    m = mats[5]  # water, no textures at all (fallback base texture)
+    m["water"], m["colour"] = 1, (0.2, 0.4, 0.8, 0.5)
+    for k in range(n_detail_modes):
+        m = mats[6 + k]
+        m["base_texture"], m["detail"], m["detail_blend_mode"] = BASE, DETAIL, k
+        m["detail_scale"], m["detail_blend_factor"], m["detail_mat"] = 3.0, 0.35 + 0.05 * k, skew
+    ground = heightfield(ground_quads, extent, 4.0, seed, 0.05)
+    usable = np.array([0, 2, 3, 4, 5] + list(range(6, 6 + n_detail_modes)))
+    ground["material"] = usable[np.arange(len(ground)) % len(usable)]
+    ground["alphas"] = rng.uniform(0, 1, (len(ground), 3))
+    parts = [ground, box([-extent / 2, -extent / 2, -9.0], [extent / 2, extent / 2, 50.0], True, material=1)]
+    rots = _random_rotations(rng, n_props)
+    for e in range(n_props):
+        obj = torus(21, 11, seed=seed + e, material=int(usable[e % len(usable)]), ent_idx=e + 1)
+        obj["alphas"] = rng.uniform(0, 1, (len(obj), 3))
+        parts.append(transform_tris(obj, rots[e], (rng.uniform(-35, 35), rng.uniform(-35, 35), rng.uniform(6, 25)), rng.uniform(2.0, 5.0)))
+    ents = np.zeros(n_props + 1, abi.ENTITY)
+    ents["id"] = np.concatenate([[0], 200 + np.arange(n_props)])
+    ents["colour"] = 1.0
+    ents["colour"][1:] = rng.uniform(0.4, 1.0, (n_props, 4))
+    return abi.SceneData(np.concatenate(parts), mats, ents, texs)
+
+
 # ---------------------------------------------------------------------- scenes
 def scene_heightfield(n_quads=224, seed=1234, closed=True, extent=100.0, amp=8.0):
     """Config 1: 2*n_quads^2 terrain triangles (+12 for the enclosing room when closed)."""
