@@ -37,23 +37,42 @@ def layout(request):
 
 
 TIES = {"quad": 0, "compact": 0, "exact": 0}
+LEAKS = {"quad": 0, "compact": 0, "exact": 0}
 
 
-def same_hits(got, want, layout):
-    """Hit buffers agree: byte for byte ("exact"), or up to counted ties ("compact")."""
+def same_hits(got, want, layout, rays=None, cpu=None):
+    """Hit buffers agree: byte for byte ("exact"), or — quantised layouts — up to COUNTED exceptions of two kinds:
+
+    * tie: both hit and |dt| <= 1e-6 t (two triangles at the same distance; the visit order picks the winner);
+    * reference leak (only checked when the caller passes `rays` and a CPU checker): the quantised layout returns a
+      CLOSER hit than the reference traversal (or a hit where it misses), and the checker's own triangle test
+      (TriangleBackfaceCull::intersect through oracle.tri_intersect) accepts exactly that (t, u, v) for that primitive.
+      The triangle is then a genuine hit under the reference's arithmetic which its traverser never tested because a
+      FastNodeIntersector box test rounded the ray out of an ancestor box — the quantised boxes contain the
+      reference's boxes, so they cannot lose a candidate, but they can keep one the reference
+      drops.  Seen once in 5.6 M bounce rays of the closed 5 M-triangle scene (a ray through the shared edge of two
+      wall triangles: the reference reports a MISS inside a closed room).
+
+    The opposite direction (the reference finds something closer than we do) is always a failure."""
     if got.tobytes() == want.tobytes():
         return True
     if layout == "exact":
         return False
     from vistrace_b200 import abi
 
-    diff = (got.view(np.uint32).reshape(-1, 4) != want.view(np.uint32).reshape(-1, 4)).any(1)
+    diff = np.nonzero((got.view(np.uint32).reshape(-1, 4) != want.view(np.uint32).reshape(-1, 4)).any(1))[0]
     g, w = got[diff], want[diff]
-    both_hit = (g["prim"] != abi.VT_MISS) & (w["prim"] != abi.VT_MISS)
-    tie = both_hit & (np.abs(g["t"].astype(np.float64) - w["t"]) <= 1e-6 * np.abs(w["t"].astype(np.float64)))
+    g_hit, w_hit = g["prim"] != abi.VT_MISS, w["prim"] != abi.VT_MISS
+    tie = g_hit & w_hit & (np.abs(g["t"].astype(np.float64) - w["t"]) <= 1e-6 * np.abs(w["t"].astype(np.float64)))
+    leak = np.zeros(len(diff), bool)
+    if rays is not None and cpu is not None:
+        for j in np.nonzero(~tie & g_hit & (~w_hit | (g["t"] < w["t"])))[0]:
+            ok, tuv = cpu.tri_intersect(int(g["prim"][j]), rays[diff[j]])
+            leak[j] = ok and tuv.tobytes() == np.array([g["t"][j], g["u"][j], g["v"][j]], np.float32).tobytes()
     TIES[layout] += int(tie.sum())
-    print(f"[parity] {int(diff.sum())} of {len(got)} records differ, {int(tie.sum())} of them ties")
-    return bool(tie.all())
+    LEAKS[layout] += int(leak.sum())
+    print(f"[parity] {len(diff)} of {len(got)} records differ: {int(tie.sum())} ties, {int(leak.sum())} reference leaks")
+    return bool((tie | leak).all()) and int(leak.sum()) <= max(1, len(got) // 1000000)
 
 
 def _check_against(vt, oracle_mod, scene, rays, kind, bvh_from, layout, any_hit=False):
@@ -78,7 +97,7 @@ def _check_against(vt, oracle_mod, scene, rays, kind, bvh_from, layout, any_hit=
     rep = compare_hits(hits, want["hits"])
     assert rep["hit_miss_mismatch"] == 0 and rep["tuv_bit_mismatch"] == 0, rep
     assert rep["prim_mismatch"] == 0 or layout != "exact", rep
-    assert same_hits(hits, want["hits"], layout), rep
+    assert same_hits(hits, want["hits"], layout, rays, cpu), rep
     err = attr_max_rel_err(attrs, want["attrs"])
     for f in ATTR_FLOAT_FIELDS:
         assert err[f] <= 1e-5, (f, err[f])  # tolerance from BASELINE.json north_star
@@ -103,7 +122,7 @@ def test_config1_heightfield_primary_and_bounce(vt, oracle_mod, kind, bvh_from, 
     bounce, _ = scenes.bounce_rays(attrs, spp=2)
     assert len(bounce) > 1000
     got = accel.traverse(bounce)
-    assert same_hits(got, cpu.traverse(bounce)["hits"], layout)
+    assert same_hits(got, cpu.traverse(bounce)["hits"], layout, bounce, cpu)
 
 
 @pytest.mark.parametrize("kind", oracle_kinds())
@@ -126,7 +145,7 @@ def test_config2_props_primary_and_shadow(vt, oracle_mod, kind, layout):
     np.testing.assert_array_equal(pt_rays["d"][parent], (light[None, :] - shadow["o"]).astype(np.float32))
     assert (pt_rays["tmax"][parent] == 1.0).all()
     got = accel.traverse(shadow)
-    assert same_hits(got, cpu.traverse(shadow)["hits"], layout)
+    assert same_hits(got, cpu.traverse(shadow)["hits"], layout, shadow, cpu)
     occl = accel.traverse(shadow, any_hit=True)  # early-out variant: only hit / no-hit is defined
     np.testing.assert_array_equal(occl["prim"] == abi.VT_MISS, got["prim"] == abi.VT_MISS)
 
@@ -145,7 +164,7 @@ def test_config4_foliage_alpha_test_and_attrs(vt, oracle_mod, kind, bvh_from, la
     assert (mats >= 2).sum() > 1000  # alpha-tested cards are actually being hit ...
     assert (attrs["alpha"][hits["prim"] != abi.VT_MISS][mats >= 2] >= 0.5 - 1e-6).all()  # ... and only where opaque
     bounce, _ = scenes.bounce_rays(attrs, spp=1)
-    assert same_hits(accel.traverse(bounce), cpu.traverse(bounce)["hits"], layout)
+    assert same_hits(accel.traverse(bounce), cpu.traverse(bounce)["hits"], layout, bounce, cpu)
 
 
 @pytest.mark.parametrize("kind", oracle_kinds())
@@ -191,6 +210,18 @@ def test_edge_cases(vt, oracle_mod, layout):
     ax["d"] = np.tile(dirs, (500, 1))
     ax["tmax"] = FLT_MAX
     _check_against(vt, oracle_mod, scene, ax, "port", "product", layout)
+    # (f) un-normalised directions of extreme magnitude (t is parametric, AccelStruct.cpp:810-815): |d| ~ 2^70 and
+    # 2^100 send a warp of the quad kernel down its two-fma plane form (slab_quad: |inv| < 2^-60), |d| ~ 2^-30 hits
+    # safe_inverse's clamp (vector.hpp:69-74); mixed into ordinary rays so both forms run side by side
+    wild = scenes.pinhole_rays(96, 54, (0, -80, 60), (0, 0, 5))
+    scale = np.ones(len(wild), np.float32)
+    scale[::7] = 2.0**70
+    scale[3::11] = 2.0**100
+    scale[5::13] = 2.0**-30
+    wild["d"] *= scale[:, None]
+    _check_against(vt, oracle_mod, scene, wild, "port", "product", layout)
+    wild["d"][::5, 0] = np.float32(2.0**90)  # one huge component only
+    _check_against(vt, oracle_mod, scene, wild, "port", "product", layout)
 
 
 def test_exact_ties_duplicate_geometry(vt, oracle_mod, layout):
@@ -315,10 +346,11 @@ def test_large_batch_properties(vt):
     assert again.tobytes() == hits.tobytes()
 
 
-def test_full_size_scene_layouts_agree(vt):
+def test_full_size_scene_layouts_agree(vt, oracle_mod):
     """BASELINE config 3 at full size (5 005 460 triangles, 1920x1080 primary + 4 spp bounce rays, ~7.7 M rays): the
     quantised layouts against the exact layout (which the tests above pin to the oracle bit for bit).  Records may
-    differ only as ties — the axis-aligned room has edges where two triangles give the same t — and are counted."""
+    differ only as ties — the axis-aligned room has edges where two triangles give the same t — or as verified
+    reference leaks (same_hits); both are counted."""
     from vistrace_b200 import abi, scenes
 
     scene = scenes.scene_terrain_closed(1582)
@@ -329,11 +361,13 @@ def test_full_size_scene_layouts_agree(vt):
     assert (want["hits"]["prim"] != abi.VT_MISS).all()  # closed scene
     live = want["bounce_rays"]["tmax"] >= 0
     exact.close()
+    cpu = oracle_mod.CpuScene(scene, "reference" if oracle_mod.available("reference") else "port", build_bvh=False)  # triangle test only
+    bounce = want["bounce_rays"][live]
     for layout in ("quad", "compact"):
         accel = vt.Accel(0, layout=layout).populate(scene, bvh=bvh)
         assert accel.layout == layout
-        assert same_hits(accel.traverse(rays), want["hits"], layout)
-        assert same_hits(accel.traverse(want["bounce_rays"][live]), want["bounce_hits"][live], layout)
+        assert same_hits(accel.traverse(rays), want["hits"], layout, rays, cpu)
+        assert same_hits(accel.traverse(bounce), want["bounce_hits"][live], layout, bounce, cpu)
         accel.close()
 
 

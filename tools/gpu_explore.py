@@ -35,6 +35,55 @@ def time_traverse(accel, d_rays, n, d_hits, reps=5, any_hit=False, d_attrs=None)
     return best
 
 
+def _morton3(q, bits):
+    """Interleave three `bits`-bit integer columns of q (n x 3) into one Morton code."""
+    code = np.zeros(len(q), np.uint64)
+    for b in range(bits):
+        for a in range(3):
+            code |= ((q[:, a].astype(np.uint64) >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b + a)
+    return code
+
+
+def sort_key(rays, name):
+    """Host-side ordering keys for the ray-coherence experiment (how much would a device-side sort buy?)."""
+    o, d = rays["o"], rays["d"]
+    octant = ((d[:, 0] < 0).astype(np.uint64) | ((d[:, 1] < 0).astype(np.uint64) << np.uint64(1)) | ((d[:, 2] < 0).astype(np.uint64) << np.uint64(2)))
+    lo, hi = o.min(0), o.max(0)
+
+    def oq(bits):
+        return np.minimum(((o - lo) / (hi - lo + 1e-9) * (1 << bits)).astype(np.int64), (1 << bits) - 1)
+
+    dn = d / np.maximum(np.abs(d).max(-1, keepdims=True), 1e-30)
+
+    def dq(bits):
+        return np.minimum(((dn * 0.5 + 0.5) * (1 << bits)).astype(np.int64), (1 << bits) - 1)
+
+    idx = np.arange(len(rays), dtype=np.uint64)
+    if name == "none":
+        return idx
+    if name == "random":
+        return np.random.default_rng(1).permutation(len(rays)).astype(np.uint64)
+    if name == "oct":
+        return octant
+    if name.startswith("blk") and name.endswith("_oct"):  # octant inside blocks of N consecutive rays
+        n = np.uint64(int(name[3:-4]))
+        return (idx // n) * np.uint64(8) + octant
+    if name.startswith("blk") and name.endswith("_dir"):  # 3 x 3-bit direction cell inside blocks of N rays
+        n = np.uint64(int(name[3:-4]))
+        return (idx // n) * np.uint64(512) + _morton3(dq(3), 3)
+    if name == "morton_o":
+        return _morton3(oq(10), 10)
+    if name == "oct_morton_o":
+        return (octant << np.uint64(30)) | _morton3(oq(10), 10)
+    if name == "morton_o5_dir":  # coarse origin cell, then direction cell, then fine origin
+        return (_morton3(oq(5), 5) << np.uint64(24)) | (_morton3(dq(3), 3) << np.uint64(15)) | (_morton3(oq(10), 10) & np.uint64(0x7FFF))
+    if name == "morton_o4_dir":
+        return (_morton3(oq(4), 4) << np.uint64(24)) | (_morton3(dq(4), 4) << np.uint64(12))
+    if name == "dir_morton_o":
+        return (_morton3(dq(3), 3) << np.uint64(30)) | _morton3(oq(10), 10)
+    raise ValueError(name)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quads", type=int, default=224)
@@ -43,6 +92,8 @@ def main():
     ap.add_argument("--knobs", default="")
     ap.add_argument("--props", type=int, default=0)
     ap.add_argument("--cpu", type=int, default=0, help="time the CPU reference on this many rays")
+    ap.add_argument("--rebuild", action="store_true", help="rebuild the hierarchy per knob set (builder knobs: VT_MAX_LEAF, VT_TRAV_COST, ...)")
+    ap.add_argument("--sorts", default="", help="comma list of host-side bounce-ray orderings to time (see sort_key)")
     args = ap.parse_args()
     w, h = map(int, args.res.split("x"))
     t0 = time.time()
@@ -64,6 +115,10 @@ def main():
             if k.startswith("VT_"):
                 del os.environ[k]
         os.environ.update(knobs)
+        if args.rebuild:
+            t0 = time.time()
+            bvh = vt.build_bvh(scene)
+            print(f"rebuild {knobs}: {len(bvh[0])} nodes in {time.time()-t0:.2f}s", flush=True)
         accel = vt.Accel(0)
         t0 = time.time()
         accel.populate(scene, bvh=bvh)
@@ -85,6 +140,14 @@ def main():
                           "S_I_bounce": [round(st_b[0] / len(bounce), 2), round(st_b[1] / len(bounce), 2)], "upload_s": round(t_up, 2), "primary_Mrays": round(len(rays) / ms_p / 1e3, 1),
                           "bounce_Mrays": round(len(bounce) / ms_b / 1e3, 1), "bounce_anyhit_Mrays": round(len(bounce) / ms_a / 1e3, 1),
                           "primary+attrs_Mrays": round(len(rays) / ms_pa / 1e3, 1), "ms": [round(ms_p, 3), round(ms_b, 3), round(ms_a, 3), round(ms_pa, 3)]}), flush=True)
+        for name in [x for x in args.sorts.split(",") if x]:
+            order = np.argsort(sort_key(bounce, name), kind="stable")
+            d_sorted = to_dev(np.ascontiguousarray(bounce[order]))
+            st_s = accel.traverse_stats(d_sorted.data_ptr(), len(bounce))
+            ms_s = time_traverse(accel, d_sorted, len(bounce), d_hits)
+            print(json.dumps({"sort": name, "bounce_Mrays": round(len(bounce) / ms_s / 1e3, 1), "ms": round(ms_s, 3),
+                              "S_I": [round(st_s[0] / len(bounce), 2), round(st_s[1] / len(bounce), 2)]}), flush=True)
+            del d_sorted
         accel.close()
     if args.cpu:
         import oracle

@@ -402,8 +402,11 @@ bool choose_grid(double lo, double hi, int &E, int64_t &k) {
     int e = -149;
     if (hi > lo) e = std::max(e, (int)std::ceil(std::log2((hi - lo) / 255.0)) - 1);
     if (mag > 0) e = std::max(e, (int)std::floor(std::log2(mag)) - 23);
-    e = std::max(e, -126);  // 2^E must be a normal float (biased exponent 1..254)
-    for (; e <= 100; e++) {  // (2^23 + q) * 2^E must stay finite
+    // |E| <= 60: 2^E times a ray's inverse direction (|inv| in [2^-60, 2^24] on the one-fma path of slab_quad) must be
+    // a NORMAL float so that the product is exact; it also keeps 2^E normal and (2^23 + q) * 2^E finite.  A coarser
+    // grid than the box needs is still conservative (a flat box at 0 gets k = q = 0 on any grid).
+    e = std::max(e, -60);
+    for (; e <= 60; e++) {
         const double s = std::ldexp(1.0, e);
         const double kl = std::floor(lo / s), kh = std::ceil(hi / s);
         if (kh - kl <= 255.0 && std::fabs(kl) <= kmax && std::fabs(kh) <= kmax) {

@@ -233,6 +233,31 @@ VT_DEV void slab_cpair(const VtCPair *cpairs, uint32_t cur, uint32_t magic, cons
 // One step over a QUAD (vt_device.h: VtQuad): two 32-byte loads, the four boxes decoded and slab-tested
 // exactly like slab_cpair, then the children that were hit are ordered near-to-far by entry distance.
 // Out: k[i] ascending sort keys (0x7FFFFFFF = no hit) and the matching tagged references r[i].
+// Sort key of a hit child: the bits of its entry distance (en >= tmin >= 0, so the pattern orders like the
+// value).  VT_KEY_SLOT=1 additionally breaks ties by slot index inside the key (two more LOP3 per child);
+// without it the compare-exchange network leaves equal keys in network order — just as deterministic.
+// VT_SLAB_TWO_FMA=1 forces the two-fma plane form for every ray (tuning / A-B builds).
+#ifndef VT_SLAB_TWO_FMA
+#define VT_SLAB_TWO_FMA 0
+#endif
+#ifndef VT_KEY_SLOT
+#define VT_KEY_SLOT 0
+#endif
+#if VT_KEY_SLOT
+#define VT_QUAD_KEY(en, i) (int)((__float_as_uint(en) & ~3u) | (unsigned)(i))
+#else
+#define VT_QUAD_KEY(en, i) (int)__float_as_uint(en)
+#endif
+//
+// Plane arithmetic, two forms with the same guarantee (every box FastNodeIntersector accepts is accepted):
+//   TWO_FMA   t = fmaf(fmaf(2^23+q, 2^E, origin_adj), inv, so): exact decode, then the reference's expression.
+//   one fma   t = fmaf(2^23+q, 2^E*inv, A) with A = origin_adj*inv + so rounded DOWN for entry planes and UP for exit
+//             planes, once per node and axis.  2^E*inv is exact (power of two; the host keeps |E| <= 60 and the lane's
+//             |inv| is in [2^-60, 2^24], so the product is a normal float), (2^23+q)*2^E + origin_adj is the decoded
+//             plane exactly, hence the real value under the rounding is plane*inv + so minus a non-negative slack
+//             (entry) or plus one (exit); rounding is monotone, so entry' <= the reference's entry and exit' >= its exit.
+//             A warp holding a ray outside that |inv| range (|d| > 2^60, NaN) takes the TWO_FMA form.
+template <bool TWO_FMA>
 VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const RayState &ray, int (&k)[4], uint32_t (&r)[4]) {
     uint4 a0, a1, b0, b1;
     ldg256u(quads + cur, a0, a1);
@@ -246,21 +271,35 @@ VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const R
     const uint32_t ny = oy ? b0.y : b0.x, fy = oy ? b0.x : b0.y;
     const uint32_t nz = oz ? b0.w : b0.z, fz = oz ? b0.z : b0.w;
     r[0] = b1.x, r[1] = b1.y, r[2] = b1.z, r[3] = b1.w;
-#define VT_PLANE(q, sel, s, a) fmaf(__uint_as_float(__byte_perm(q, magic, sel)), s, a)
+#define VT_QF(q, sel) __uint_as_float(__byte_perm(q, magic, sel))
+#define VT_PLANE(q, sel, s, a) fmaf(VT_QF(q, sel), s, a)
+    const float six = sx * ray.inv.x, siy = sy * ray.inv.y, siz = sz * ray.inv.z;
+    const float alx = __fmaf_rd(ax, ray.inv.x, ray.so.x), aly = __fmaf_rd(ay, ray.inv.y, ray.so.y), alz = __fmaf_rd(az, ray.inv.z, ray.so.z);
+    const float ahx = __fmaf_ru(ax, ray.inv.x, ray.so.x), ahy = __fmaf_ru(ay, ray.inv.y, ray.so.y), ahz = __fmaf_ru(az, ray.inv.z, ray.so.z);
 #define VT_CHILD(i, sel)                                                                   \
     {                                                                                      \
-        const float e0 = fmaf(VT_PLANE(nx, sel, sx, ax), ray.inv.x, ray.so.x);             \
-        const float e1 = fmaf(VT_PLANE(ny, sel, sy, ay), ray.inv.y, ray.so.y);             \
-        const float e2 = fmaf(VT_PLANE(nz, sel, sz, az), ray.inv.z, ray.so.z);             \
-        const float x0 = fmaf(VT_PLANE(fx, sel, sx, ax), ray.inv.x, ray.so.x);             \
-        const float x1 = fmaf(VT_PLANE(fy, sel, sy, ay), ray.inv.y, ray.so.y);             \
-        const float x2 = fmaf(VT_PLANE(fz, sel, sz, az), ray.inv.z, ray.so.z);             \
+        float e0, e1, e2, x0, x1, x2;                                                      \
+        if (TWO_FMA) {                                                                     \
+            e0 = fmaf(VT_PLANE(nx, sel, sx, ax), ray.inv.x, ray.so.x);                     \
+            e1 = fmaf(VT_PLANE(ny, sel, sy, ay), ray.inv.y, ray.so.y);                     \
+            e2 = fmaf(VT_PLANE(nz, sel, sz, az), ray.inv.z, ray.so.z);                     \
+            x0 = fmaf(VT_PLANE(fx, sel, sx, ax), ray.inv.x, ray.so.x);                     \
+            x1 = fmaf(VT_PLANE(fy, sel, sy, ay), ray.inv.y, ray.so.y);                     \
+            x2 = fmaf(VT_PLANE(fz, sel, sz, az), ray.inv.z, ray.so.z);                     \
+        } else {                                                                           \
+            e0 = fmaf(VT_QF(nx, sel), six, alx);                                           \
+            e1 = fmaf(VT_QF(ny, sel), siy, aly);                                           \
+            e2 = fmaf(VT_QF(nz, sel), siz, alz);                                           \
+            x0 = fmaf(VT_QF(fx, sel), six, ahx);                                           \
+            x1 = fmaf(VT_QF(fy, sel), siy, ahy);                                           \
+            x2 = fmaf(VT_QF(fz, sel), siz, ahz);                                           \
+        }                                                                                  \
         const float en = fmaxf(e0, fmaxf(e1, fmaxf(e2, ray.tmin)));                        \
         const float ex = fminf(x0, fminf(x1, fminf(x2, ray.tmax)));                        \
         /* an empty slot's inverted box can look hit after rounding when the node is tiny and far: test the ref too */ \
         const bool hit = r[i] != VT_REF_DONE && en <= ex;                                  \
         /* en >= tmin >= 0: its bit pattern orders like the value (-0.0 sorts first) */    \
-        k[i] = hit ? (int)((__float_as_uint(en) & ~3u) | (unsigned)i) : 0x7FFFFFFF;        \
+        k[i] = hit ? VT_QUAD_KEY(en, i) : 0x7FFFFFFF;                                      \
     }
     VT_CHILD(0, 0x7650u)
     VT_CHILD(1, 0x7651u)
@@ -268,6 +307,7 @@ VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const R
     VT_CHILD(3, 0x7653u)
 #undef VT_CHILD
 #undef VT_PLANE
+#undef VT_QF
 #define VT_CE(a, b)                       \
     if (k[a] > k[b]) {                    \
         const int tk = k[a];              \
@@ -279,6 +319,22 @@ VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const R
     }
     VT_CE(0, 1) VT_CE(2, 3) VT_CE(0, 2) VT_CE(1, 3) VT_CE(1, 2)
 #undef VT_CE
+}
+
+// Traversal stack of the quantised kernels: the array lives in local memory and is addressed through a
+// 32-bit .local address (st.local / ld.local with a 32-bit register), so push = STL + one VIADD and pop = LDL
+// + one VIADD.  A generic `uint32_t *` costs a 64-bit pointer update next to the 32-bit one the compiler
+// derives for STL/LDL anyway (profiles/r1_k_traverse_v5_step.md).
+VT_DEV uint32_t local_addr(const void *p) {
+    uint64_t a;
+    asm("cvta.to.local.u64 %0, %1;" : "=l"(a) : "l"(p));
+    return (uint32_t)a;
+}
+VT_DEV void stack_store(uint32_t a, uint32_t v) { asm volatile("st.local.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+VT_DEV uint32_t stack_load(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.local.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
 }
 
 VT_DEV void init_ray(const vt_ray &in, RayState &r) {
@@ -469,8 +525,9 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
     const unsigned lt_mask = (1u << lane) - 1u;
     // the layouts served by this kernel validate the worst-case stack depth on the host (<= VT_STACK_SIZE), so
     // the stack is a bare pointer: push = store + increment, pop = decrement + load
-    uint32_t stack[VT_STACK_SIZE];
-    uint32_t *sp = stack;
+    uint32_t stack_mem[VT_STACK_SIZE];
+    const uint32_t stack = local_addr(stack_mem);
+    uint32_t sp = stack;         // byte address of the next free entry
     uint32_t cur = VT_REF_DONE;  // VT_REF_DONE: nothing left to visit
     bool alive = false;          // lane owns a ray whose result is not written yet
     bool exhausted = false;      // warp-uniform: the ray queue has run dry
@@ -478,6 +535,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
     RayState r;
     unsigned long long n_invalid = 0, n_steps = 0, n_tests = 0;
     const uint32_t magic = S.magic;
+    bool warp_wild = false;  // warp-uniform: some lane holds a ray the one-fma plane form is not proven for (slab_quad)
 
     for (;;) {
         if (alive && cur == VT_REF_DONE) {
@@ -498,6 +556,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                 exhausted = true;
             }
             if (base + n_idle >= n) exhausted = true;
+            bool fresh_wild = false;
             if (!alive) {
                 ray_idx = base + __popc(idle & lt_mask);
                 if (ray_idx < n) {
@@ -507,6 +566,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     init_ray(in, r);
                     alive = true;
                     sp = stack;
+                    fresh_wild = VT_SLAB_TWO_FMA || !(fminf(fabsf(r.inv.x), fminf(fabsf(r.inv.y), fabsf(r.inv.z))) >= 0x1p-60f);
                     if (!(in.tmin >= 0.f) || !(in.tmax > in.tmin)) {  // AccelStruct.cpp:805-806 -> counted miss; tmax < 0: masked slot
                         if (!(in.tmax < 0.f)) n_invalid++;
                     } else if (S.root_leaf_count) {
@@ -516,6 +576,8 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     }
                 }
             }
+            // sticky for this warp's share of the launch: such rays are pathological input, the flag only has to be right, not tight
+            if (__any_sync(0xffffffffu, fresh_wild)) warp_wild = true;
         }
         const int keep = exhausted ? 0 : refill_threshold;
 
@@ -542,7 +604,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                         cur = VT_REF_DONE;
                         sp = stack;
                     } else if (sp != stack) {
-                        cur = *--sp;
+                        cur = stack_load(sp -= 4u);
                     } else {
                         cur = VT_REF_DONE;
                     }
@@ -554,7 +616,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                         sp = stack;
                     } else if ((cur >> VT_REF_SHIFT) == 1u) {  // run finished: pop
                         if (sp != stack) {
-                            cur = *--sp;
+                            cur = stack_load(sp -= 4u);
                         } else {
                             cur = VT_REF_DONE;
                         }
@@ -568,19 +630,20 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                 if (QUAD) {
                     int k[4];
                     uint32_t cr[4];
-                    slab_quad(S.quads, cur, magic, r, k, cr);
+                    if (warp_wild) slab_quad<true>(S.quads, cur, magic, r, k, cr);
+                    else slab_quad<false>(S.quads, cur, magic, r, k, cr);
                     // farthest first, so the nearest pending child is popped first
-                    if (k[3] != 0x7FFFFFFF) *sp++ = cr[3];
-                    if (k[2] != 0x7FFFFFFF) *sp++ = cr[2];
+                    if (k[3] != 0x7FFFFFFF) stack_store(sp, cr[3]), sp += 4u;
+                    if (k[2] != 0x7FFFFFFF) stack_store(sp, cr[2]), sp += 4u;
                     if (k[1] != 0x7FFFFFFF) {
-                        *sp++ = cr[1];
+                        stack_store(sp, cr[1]), sp += 4u;
                         if (VT_PREFETCH_FAR) vt_prefetch_ref(S, cr[1], true);  // the next one to be popped
                     }
                     if (k[0] != 0x7FFFFFFF) {
                         cur = cr[0];
                         if (VT_PREFETCH_LEAF && (cur >> VT_REF_SHIFT)) vt_prefetch(S.tris + (cur & VT_REF_MASK));
                     } else if (sp != stack) {
-                        cur = *--sp;
+                        cur = stack_load(sp -= 4u);
                     } else {
                         cur = VT_REF_DONE;
                     }
@@ -593,11 +656,11 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                 const bool take_r = hit_r && (!hit_l || le > re);  // near child first; ties keep the left child first
                 const uint32_t next = take_r ? rref : lref;
                 const uint32_t far_ = take_r ? lref : rref;
-                if (hit_l && hit_r) *sp++ = far_;
+                if (hit_l && hit_r) stack_store(sp, far_), sp += 4u;
                 if (hit_l || hit_r) {
                     cur = next;
                 } else if (sp != stack) {
-                    cur = *--sp;
+                    cur = stack_load(sp -= 4u);
                 } else {
                     cur = VT_REF_DONE;
                 }
