@@ -66,7 +66,7 @@ def primary_rays():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed regions (resident and e2e) run."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -74,9 +74,9 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
-    def __enter__(self):
+    def __enter__(self):  # re-enterable: rows accumulate over every timed region
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -220,6 +220,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — vistrace_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from vistrace_b200 import shard
+
+    numa = shard.bind_to_gpu_numa_node(local_rank)  # before any pinned buffer or OpenMP thread exists
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -229,8 +232,6 @@ def run_ours(args):
     n = len(rays)
     accel = vt.Accel(local_rank)
     if world > 1:  # the hierarchy is built once (rank 0) and replicated over NCCL; every GPU holds the whole scene
-        from vistrace_b200 import shard
-
         accel.populate(scene, bvh=shard.replicate_bvh(vt.build_bvh(scene) if rank == 0 else None, device=dev))
     else:
         accel.populate(scene)
@@ -311,15 +312,42 @@ def run_ours(args):
     h_rays[:] = rays
     h_fb = h_fb_t.numpy().view(np.float32).reshape(n, 3)
     e2e_steps = max(1, args.steps)
+    if world == 1 or os.environ.get("VT_BENCH_E2E") == "tiled":
+        e2e_call = "vt_accel_render_diffuse_wave: host rays in, host RGBFFF framebuffer out"
+        h2d_step, d2h_step = n * 32, n * 12
+
+        def e2e_step(it):
+            return accel.render_diffuse_wave(h_rays, SPP, seed=seed0 + it, weight=1.0, out=h_fb)[1]
+    else:
+        # N GPUs: every rank uploads 1/N of the ray array and downloads 1/N of the finished image; the rest moves over
+        # NVLink (one all_gather of the rays, one all_reduce of the partial images) — shard.ShardedFrame
+        frame = shard.ShardedFrame(n, dev)
+        h_rays_f32 = h_rays_t.view(torch.float32)
+        e2e_call = "shard.ShardedFrame.step: 1/N of the host rays in per rank, all_gather, trace own samples, all_reduce, 1/N of the host RGBFFF image out per rank"
+        h2d_step, d2h_step = frame.h2d_bytes, frame.d2h_bytes
+
+        def e2e_step(it):
+            def trace(d_rays_full):
+                p = d_rays_full.data_ptr()
+                accel.traverse_device(p, n, d_hits.data_ptr(), d_attrs.data_ptr(), stream=sh)
+                accel.bounce_rays_device(d_attrs.data_ptr(), n, SPP, seed0 + it, d_brays.data_ptr(), stream=sh)
+                accel.traverse_device(d_brays.data_ptr(), n * SPP, d_bhits.data_ptr(), stream=sh)
+                d_fb.zero_()
+                accel.accumulate_sky_device(d_attrs.data_ptr(), d_bhits.data_ptr(), n, SPP, 1.0 / world, d_fb.data_ptr(), stream=sh)
+                return d_fb
+
+            frame.step(h_rays_f32, trace)  # the finished chunk lands in the frame's own pinned buffer
+            return live
     for it in range(min(2, args.warmup)):
-        accel.render_diffuse_wave(h_rays, SPP, seed=seed0 + it, weight=1.0, out=h_fb)
+        e2e_step(it)
     sync_all()
     launches_e2e0 = accel.launch_count
-    t0 = time.perf_counter()
-    for it in range(e2e_steps):
-        _, live_e2e = accel.render_diffuse_wave(h_rays, SPP, seed=seed0 + args.warmup + it, weight=1.0, out=h_fb)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    with clocks:
+        t0 = time.perf_counter()
+        for it in range(e2e_steps):
+            live_e2e = e2e_step(args.warmup + it)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
     launches += accel.launch_count - launches_e2e0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -328,18 +356,22 @@ def run_ours(args):
     e2e_rays = n + int(live_e2e)
     e2e_value = world * e2e_rays / (e2e_s / e2e_steps) / 1e6
 
-    # ---- the same wave returning every hit record instead of the image (vt_accel_trace_diffuse_wave): reported beside e2e
-    h_hits_t, h_bhits_t = pinned(n * 16), pinned(n * SPP * 16)
-    out = {"hits": h_hits_t.numpy().view(abi.HIT), "bounce_hits": h_bhits_t.numpy().view(abi.HIT)}
-    hit_steps = max(1, min(5, args.steps))
-    accel.trace_diffuse_wave(h_rays, SPP, seed=seed0, out=out)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for it in range(hit_steps):
-        res = accel.trace_diffuse_wave(h_rays, SPP, seed=seed0 + args.warmup + it, out=out)
-    torch.cuda.synchronize()
-    e2e_hits_ms = 1e3 * (time.perf_counter() - t0) / hit_steps
-    e2e_hits_value = (n + int(res["live_bounce"])) / (e2e_hits_ms * 1e-3) / 1e6
+    # ---- the same wave returning every hit record instead of the image (vt_accel_trace_diffuse_wave): reported beside
+    # e2e at N = 1 (at N > 1 every rank would pull 166 MB per step through shared PCIe uplinks: not the sharded design)
+    hits_variant = None
+    if world == 1:
+        h_hits_t, h_bhits_t = pinned(n * 16), pinned(n * SPP * 16)
+        out = {"hits": h_hits_t.numpy().view(abi.HIT), "bounce_hits": h_bhits_t.numpy().view(abi.HIT)}
+        hit_steps = max(1, min(5, args.steps))
+        accel.trace_diffuse_wave(h_rays, SPP, seed=seed0, out=out)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for it in range(hit_steps):
+            res = accel.trace_diffuse_wave(h_rays, SPP, seed=seed0 + args.warmup + it, out=out)
+        torch.cuda.synchronize()
+        e2e_hits_ms = 1e3 * (time.perf_counter() - t0) / hit_steps
+        hits_variant = {"call": "vt_accel_trace_diffuse_wave", "value": round((n + int(res["live_bounce"])) / (e2e_hits_ms * 1e-3) / 1e6, 2),
+                        "ms_per_step": round(e2e_hits_ms, 3), "d2h_bytes_per_step": n * 16 + n * SPP * 16}
 
     if rank != 0:
         if world > 1:
@@ -376,14 +408,12 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": rays_per_step, "parallelism": f"replicated hierarchy, {world} x ray/sample shard",
+        "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": rays_per_step, "parallelism": f"replicated hierarchy, {world} x ray/sample shard", "numa_node": numa,
                    "l2": "no explicit flush: one step streams ~0.6 GB of ray/hit/attribute buffers and walks a 0.5 GB hierarchy, both > 126 MB L2",
                    "hierarchy": f"product builder (binned SAH), {accel.layout} node layout"},
         "clocks": clocks.summary(),
-        "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 12,
-                "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3), "call": "vt_accel_render_diffuse_wave: host rays in, host RGBFFF framebuffer out",
-                "all_hit_records_variant": {"call": "vt_accel_trace_diffuse_wave", "value": round(e2e_hits_value, 2), "ms_per_step": round(e2e_hits_ms, 3),
-                                            "d2h_bytes_per_step": n * 16 + n * SPP * 16}},
+        "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3), "call": e2e_call, "all_hit_records_variant": hits_variant},
         "gpu_launches": int(launches),
     }
     if roof:

@@ -42,6 +42,25 @@ def _worker(rank, world, port, out_dir):
     fb = torch.zeros(len(rays), dtype=torch.float64)
     fb[b:e] = torch.from_numpy(full["t"][b:e].astype(np.float64))
     dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)
+    # the N-GPU end-to-end step (shard.ShardedFrame): 1/N of the rays in per rank, all_gather, every rank traces the whole
+    # frame for its own sample set, all_reduce, 1/N of the finished image out per rank
+    from vistrace_b200 import abi
+
+    frame = shard.ShardedFrame(len(rays), torch.device("cpu"))
+    h_rays = torch.from_numpy(np.ascontiguousarray(rays).view(np.float32).reshape(-1).copy())
+    if rank != 0:
+        h_rays[: frame.begin * 8] = 0  # a rank may only read its own chunk of the host array
+        h_rays[frame.end * 8:] = 0
+
+    def trace(d_rays):
+        got = np.frombuffer(d_rays.numpy().tobytes(), abi.RAY)
+        assert got.tobytes() == np.ascontiguousarray(rays).tobytes()  # the gathered frame is the whole ray array
+        h = cpu.traverse(got, threads=1)["hits"]
+        img = np.stack([h["t"], h["u"], h["v"]], 1).astype(np.float32) * np.float32(rank + 1)  # "this rank's samples"
+        return torch.from_numpy(img.reshape(-1).copy())
+
+    b, e, img = frame.step(h_rays, trace)
+    np.save(os.path.join(out_dir, f"frame{rank}.npy"), np.concatenate([[b, e], img.reshape(-1)]))
     if rank == 0:
         np.savez(os.path.join(out_dir, "out.npz"), hits=full, fb=fb.numpy())
     else:
@@ -70,3 +89,13 @@ def test_two_rank_gloo_shard_and_gather(built, tmp_path):
     assert out["hits"].tobytes() == want.tobytes()
     assert np.load(tmp_path / "hits1.npy").tobytes() == want.tobytes()  # every rank holds the full buffer
     np.testing.assert_allclose(out["fb"], want["t"].astype(np.float64))
+    # ShardedFrame: the two chunks tile the frame and hold (1 + 2) x the single-rank image
+    img = np.stack([want["t"], want["u"], want["v"]], 1).astype(np.float32)
+    total = img * np.float32(1) + img * np.float32(2)
+    spans = []
+    for r in range(2):
+        f = np.load(tmp_path / f"frame{r}.npy")
+        b, e = int(f[0]), int(f[1])
+        spans.append((b, e))
+        np.testing.assert_array_equal(f[2:].astype(np.float32).reshape(-1, 3), total[b:e])
+    assert spans == [(0, 2501), (2501, 5001)]
