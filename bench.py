@@ -246,20 +246,35 @@ def run_ours(args):
     d_hits, d_attrs = dev_bytes(n * 16), dev_bytes(n * 128)
     d_brays, d_bhits = dev_bytes(n * SPP * 32), dev_bytes(n * SPP * 16)
     d_fb = torch.zeros(n * 3, dtype=torch.float32, device=dev)
+    # ray queue: K3 lists the slots that received a bounce ray, K1 visits only those (VT_BENCH_QUEUE=0: trace every slot)
+    use_queue = os.environ.get("VT_BENCH_QUEUE", "1") != "0"
+    d_queue, d_qcount = dev_bytes(n * SPP * 4), torch.zeros(1, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
     seed0 = 1000 + rank * 7919  # every rank traces its own samples of the frame
 
     ev_pairs = []
 
+    def bounce_wave(seed, before_k1=None):
+        if use_queue:
+            accel.bounce_rays_queued_device(d_attrs.data_ptr(), n, SPP, seed, d_brays.data_ptr(), d_queue.data_ptr(), d_qcount.data_ptr(),
+                                            d_bhits.data_ptr(), stream=sh)                                     # K3 (+ queue, miss records)
+            if before_k1:
+                before_k1()
+            accel.traverse_queued_device(d_brays.data_ptr(), d_queue.data_ptr(), d_qcount.data_ptr(), n * SPP, d_bhits.data_ptr(), stream=sh)
+        else:
+            accel.bounce_rays_device(d_attrs.data_ptr(), n, SPP, seed, d_brays.data_ptr(), stream=sh)          # K3
+            if before_k1:
+                before_k1()
+            accel.traverse_device(d_brays.data_ptr(), n * SPP, d_bhits.data_ptr(), stream=sh)                  # K1 (dominant)
+
     def step(it, timed):
         seed = seed0 + it
         accel.traverse_device(d_rays.data_ptr(), n, d_hits.data_ptr(), d_attrs.data_ptr(), stream=sh)          # K1 + K2
-        accel.bounce_rays_device(d_attrs.data_ptr(), n, SPP, seed, d_brays.data_ptr(), stream=sh)              # K3
+        e0 = e1 = None
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-        accel.traverse_device(d_brays.data_ptr(), n * SPP, d_bhits.data_ptr(), stream=sh)                      # K1 (dominant)
+        bounce_wave(seed, (lambda: e0.record(stream)) if timed else None)
         if timed:
             e1.record(stream)
             ev_pairs.append((e0, e1))
@@ -330,8 +345,7 @@ def run_ours(args):
             def trace(d_rays_full):
                 p = d_rays_full.data_ptr()
                 accel.traverse_device(p, n, d_hits.data_ptr(), d_attrs.data_ptr(), stream=sh)
-                accel.bounce_rays_device(d_attrs.data_ptr(), n, SPP, seed0 + it, d_brays.data_ptr(), stream=sh)
-                accel.traverse_device(d_brays.data_ptr(), n * SPP, d_bhits.data_ptr(), stream=sh)
+                bounce_wave(seed0 + it)
                 d_fb.zero_()
                 accel.accumulate_sky_device(d_attrs.data_ptr(), d_bhits.data_ptr(), n, SPP, 1.0 / world, d_fb.data_ptr(), stream=sh)
                 return d_fb
@@ -397,10 +411,13 @@ def run_ours(args):
     roof = None
     if S is not None:
         n_live, n_masked = int(live_mask.sum()), int((~live_mask).sum())
-        algo_bytes = n_live * (NODE_BYTES[accel.layout] * S + TRI_BYTES * I + RAY_BYTES + HIT_BYTES) + n_masked * (RAY_BYTES + HIT_BYTES)
+        if use_queue:  # K1 reads one 4-byte queue entry per live ray and never touches a masked slot
+            algo_bytes = n_live * (NODE_BYTES[accel.layout] * S + TRI_BYTES * I + RAY_BYTES + HIT_BYTES + 4)
+        else:
+            algo_bytes = n_live * (NODE_BYTES[accel.layout] * S + TRI_BYTES * I + RAY_BYTES + HIT_BYTES) + n_masked * (RAY_BYTES + HIT_BYTES)
         achieved = algo_bytes / (k1_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": recorded_traffic(), "kernel": "k_traverse (closest hit, bounce wave)", "kernel_ms": round(k1_ms, 4),
+                "traffic": recorded_traffic(), "kernel": "k_traverse (closest hit, bounce wave" + (", ray queue)" if use_queue else ")"), "kernel_ms": round(k1_ms, 4),
                 "algorithmic_bytes_per_launch": int(algo_bytes), "node_layout": accel.layout, "node_bytes": NODE_BYTES[accel.layout],
                 "node_visits_per_ray": round(S, 2), "tri_tests_per_ray": round(I, 2),
                 "peak_source": peak_src}

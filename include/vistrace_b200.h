@@ -258,6 +258,23 @@ int vt_accel_bounce_rays(vt_accel *accel, const vt_attr *attrs, uint64_t n, uint
 int vt_accel_shadow_rays(vt_accel *accel, const vt_attr *attrs, uint64_t n, const float light[3], int point_light,
                          float tmax, vt_ray *out_rays, uint64_t *live_out, uint32_t flags, void *stream);
 
+/* Ray queue — wavefront compaction between two accel:Traverse waves.  A generator call with a queue also LISTS the
+ * slots it filled: queue[0, *queue_count) (u32 slot indices; *queue_count is zeroed by the call and counted on the
+ * device) and writes the miss record of every slot it masked into miss_hits[slot].  vt_accel_traverse_queued then
+ * traces rays[queue[k]] -> hits[queue[k]] for k < min(capacity, *queue_count) and touches nothing else, so masked
+ * slots never occupy a lane, yet hits[0, capacity) is complete in slot order when miss_hits == hits (required when
+ * attrs are requested: the TraceResult stage reads every slot's hit record).  Same per-ray
+ * semantics as vt_accel_traverse (source/objects/AccelStruct.cpp:778-838); the order of the queue is unspecified, the
+ * hit buffer does not depend on it.  DEVICE pointers only, everything is enqueued on `stream`; at most 2^32 slots. */
+int vt_accel_bounce_rays_queued(vt_accel *accel, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed,
+                                vt_ray *out_rays, uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream);
+int vt_accel_shadow_rays_queued(vt_accel *accel, const vt_attr *attrs, uint64_t n, const float light[3], int point_light,
+                                float tmax, vt_ray *out_rays, uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits,
+                                void *stream);
+int vt_accel_traverse_queued(vt_accel *accel, const vt_ray *rays, const uint32_t *queue, const uint64_t *queue_count,
+                             uint64_t capacity, vt_hit *hits, vt_attr *attrs /* nullable: TraceResult of all `capacity` slots */,
+                             uint32_t flags /* VT_TRAVERSE_ANY_HIT */, void *stream);
+
 /* The "primary + diffuse" wave of the headline benchmark in one call: traverse rays[0, n), build
  * the TraceResult of every hit, spawn spp bounce rays per hit (as vt_accel_bounce_rays) and
  * traverse those.  Out: hits[n], bounce_hits[n*spp]; optional attrs[n], bounce_rays[n*spp]

@@ -473,6 +473,58 @@ def test_accumulate_sky_framebuffer(vt):
     np.testing.assert_array_equal(img2, got)
 
 
+def test_ray_queue_generators_and_queued_traversal(vt, layout):
+    """Ray queue: the queued generators list exactly the slots they filled, write the miss record of every masked slot, and
+    the queued traversal (closest hit after bounce rays, any hit after shadow rays) leaves the same hit buffer, byte for
+    byte, as tracing every slot — including when the hit buffer starts out as garbage."""
+    import torch
+
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_heightfield(64)
+    rays = scenes.pinhole_rays(320, 180, (0, -80, 60), (0, 0, 5))
+    accel = vt.Accel(0, layout=layout).populate(scene)
+    hits, attrs = accel.traverse(rays, want_attrs=True)
+    n, spp = len(rays), 3
+    spawn = (attrs["prim"] != abi.VT_MISS) & ((attrs["flags"] & abi.VT_ATTR_HIT_SKY) == 0)
+    assert 0 < spawn.sum() < n  # the open height field leaves sky pixels: masked slots exist
+    to_dev = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).cuda()
+    sh = torch.cuda.current_stream().cuda_stream
+    d_attrs = to_dev(attrs)
+    # --- bounce rays, closest hit
+    brays, live = accel.bounce_rays(attrs, spp, seed=42)
+    want_hits = accel.traverse(brays)
+    d_brays = torch.zeros(n * spp * 32, dtype=torch.uint8, device="cuda")
+    d_bhits = torch.full((n * spp * 16,), 0xAB, dtype=torch.uint8, device="cuda")  # garbage: every slot must be written
+    d_queue = torch.full((n * spp,), -1, dtype=torch.int32, device="cuda")
+    d_count = torch.full((1,), 12345, dtype=torch.int64, device="cuda")            # the call zeroes it
+    accel.bounce_rays_queued_device(d_attrs.data_ptr(), n, spp, 42, d_brays.data_ptr(), d_queue.data_ptr(), d_count.data_ptr(),
+                                    d_bhits.data_ptr(), stream=sh)
+    accel.traverse_queued_device(d_brays.data_ptr(), d_queue.data_ptr(), d_count.data_ptr(), n * spp, d_bhits.data_ptr(), stream=sh)
+    torch.cuda.synchronize()
+    assert int(d_count.item()) == live
+    queue = d_queue.cpu().numpy().view(np.uint32)
+    np.testing.assert_array_equal(np.sort(queue[:live]), np.flatnonzero(np.repeat(spawn, spp)))
+    assert (queue[live:] == 0xFFFFFFFF).all()
+    assert d_brays.cpu().numpy().tobytes() == brays.tobytes()
+    assert d_bhits.cpu().numpy().tobytes() == want_hits.tobytes()
+    # --- shadow rays, any hit (only hit / miss is defined for an occlusion query)
+    sun = (0.3, -0.2, 0.9)
+    srays, slive = accel.shadow_rays(attrs, sun)
+    want_occ = accel.traverse(srays, any_hit=True)["prim"] != abi.VT_MISS
+    d_srays = torch.zeros(n * 32, dtype=torch.uint8, device="cuda")
+    d_shits = torch.full((n * 16,), 0xCD, dtype=torch.uint8, device="cuda")
+    accel.shadow_rays_queued_device(d_attrs.data_ptr(), n, sun, d_srays.data_ptr(), d_queue.data_ptr(), d_count.data_ptr(),
+                                    d_shits.data_ptr(), stream=sh)
+    accel.traverse_queued_device(d_srays.data_ptr(), d_queue.data_ptr(), d_count.data_ptr(), n, d_shits.data_ptr(), any_hit=True, stream=sh)
+    torch.cuda.synchronize()
+    assert int(d_count.item()) == slive == int(spawn.sum())
+    assert d_srays.cpu().numpy().tobytes() == srays.tobytes()
+    got_occ = np.frombuffer(d_shits.cpu().numpy().tobytes(), abi.HIT)["prim"] != abi.VT_MISS
+    np.testing.assert_array_equal(got_occ, want_occ)
+    assert accel.invalid_rays == 0
+
+
 def test_two_gpu_sharded_trace_nccl(vt):
     """Real multi-GPU plumbing when the box has >= 2 GPUs (gpurun --gpus 2): replicated hierarchy, ray shards, NCCL gather."""
     import subprocess

@@ -43,6 +43,7 @@ class Wave:
         self.hits, self.attrs = dev(n * 16), dev(n * 128)
         self.srays, self.shits = dev(n * 32), dev(n * 16)
         self.brays, self.bhits = dev(n * spp * 32), dev(n * spp * 16)
+        self.queue, self.qcount = dev(n * spp * 4), torch.zeros(1, dtype=torch.int64, device="cuda")  # ray queue of the secondary wave
 
 
 def timed(fn, reps=3):
@@ -132,9 +133,28 @@ def run_config(cfg, args):
     d_rays = to_dev(rays)
     spp = 4 if cfg == 3 else 1
     w = Wave(n, spp)
-    res = {"config": cfg, "name": name, "n_tris": scene.n_tris, "layout": accel.layout, "gen_s": round(gen_s, 1), "build_s": round(build_s, 1),
+    res = {"config": cfg, "name": name, "n_tris": scene.n_tris, "layout": accel.layout, "ray_queue": not args.no_queue, "gen_s": round(gen_s, 1), "build_s": round(build_s, 1),
            "device_MB": round(accel.stats()["device_bytes"] / 1e6)}
     P = lambda t: t.data_ptr()
+    Q = not args.no_queue  # ray queue: generators list the live slots, traversal visits only those
+
+    def shadow_wave(src_attrs, wv):
+        if Q:
+            accel.shadow_rays_queued_device(P(src_attrs), n, SUN, P(wv.srays), P(wv.queue), P(wv.qcount), P(wv.shits), stream=s)
+            accel.traverse_queued_device(P(wv.srays), P(wv.queue), P(wv.qcount), n, P(wv.shits), any_hit=True, stream=s)
+        else:
+            accel.shadow_rays_device(P(src_attrs), n, SUN, P(wv.srays), stream=s)
+            accel.traverse_device(P(wv.srays), n, P(wv.shits), any_hit=True, stream=s)
+
+    def bounce_wave_k(src, k_spp, seed, d_hits, d_attrs=None):
+        if Q:
+            accel.bounce_rays_queued_device(P(src.attrs), n, k_spp, seed, P(src.brays), P(src.queue), P(src.qcount), P(d_hits), stream=s)
+            accel.traverse_queued_device(P(src.brays), P(src.queue), P(src.qcount), n * k_spp, P(d_hits), P(d_attrs) if d_attrs is not None else None,
+                                         stream=s)
+        else:
+            accel.bounce_rays_device(P(src.attrs), n, k_spp, seed, P(src.brays), stream=s)
+            accel.traverse_device(P(src.brays), n * k_spp, P(d_hits), P(d_attrs) if d_attrs is not None else None, stream=s)
+
     stages = {}
     samples = [rays]
     # primary (+ TraceResult)
@@ -145,8 +165,7 @@ def run_config(cfg, args):
         accel.shadow_rays_device(P(w.attrs), n, SUN, P(w.srays), stream=s)
         torch.cuda.synchronize()
         ls = live_count(w.srays, n)
-        ms = timed(lambda: (accel.shadow_rays_device(P(w.attrs), n, SUN, P(w.srays), stream=s),
-                            accel.traverse_device(P(w.srays), n, P(w.shits), any_hit=True, stream=s)))
+        ms = timed(lambda: shadow_wave(w.attrs, w))
         stages["shadow K3b+K1 any-hit"] = (ms, ls)
         total_ms, total_rays = total_ms + ms, total_rays + ls
         sr = to_host(w.srays, abi.RAY, n)
@@ -155,8 +174,7 @@ def run_config(cfg, args):
         accel.bounce_rays_device(P(w.attrs), n, spp, 17, P(w.brays), stream=s)
         torch.cuda.synchronize()
         lb = live_count(w.brays, n * spp)
-        ms = timed(lambda: (accel.bounce_rays_device(P(w.attrs), n, spp, 17, P(w.brays), stream=s),
-                            accel.traverse_device(P(w.brays), n * spp, P(w.bhits), stream=s)))
+        ms = timed(lambda: bounce_wave_k(w, spp, 17, w.bhits))
         stages[f"bounce K3+K1 ({spp} spp)"] = (ms, lb)
         total_ms, total_rays = total_ms + ms, total_rays + lb
         br = to_host(w.brays, abi.RAY, n * spp)
@@ -171,10 +189,8 @@ def run_config(cfg, args):
             lb = live_count(src.brays, n)
 
             def bounce_wave(src=src, dst=dst, k=k):
-                accel.bounce_rays_device(P(src.attrs), n, 1, 100 + k, P(src.brays), stream=s)
-                accel.traverse_device(P(src.brays), n, P(dst.hits), P(dst.attrs), stream=s)
-                accel.shadow_rays_device(P(dst.attrs), n, SUN, P(dst.srays), stream=s)
-                accel.traverse_device(P(dst.srays), n, P(dst.shits), any_hit=True, stream=s)
+                bounce_wave_k(src, 1, 100 + k, dst.hits, dst.attrs)
+                shadow_wave(dst.attrs, dst)
 
             ms = timed(bounce_wave, reps=2)
             ls = live_count(dst.srays, n)
@@ -205,6 +221,7 @@ def main():
     ap.add_argument("--configs", default="1,2,3,4,5")
     ap.add_argument("--cpu-rays", type=int, default=200000)
     ap.add_argument("--no-agreement", action="store_true")
+    ap.add_argument("--no-queue", action="store_true", help="trace every slot of a secondary wave instead of the generator's ray queue")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     for cfg in (int(c) for c in args.configs.split(",")):

@@ -31,6 +31,9 @@ SYMBOLS = {
     "vt_accel_trace_result": (_i32, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "vt_accel_bounce_rays": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_shadow_rays": (_i32, [_vp, _vp, _u64, _vp, _i32, C.c_float, _vp, _vp, _u32, _vp]),
+    "vt_accel_bounce_rays_queued": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "vt_accel_shadow_rays_queued": (_i32, [_vp, _vp, _u64, _vp, _i32, C.c_float, _vp, _vp, _vp, _vp, _vp]),
+    "vt_accel_traverse_queued": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "vt_accel_render_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, C.c_float, _vp, _vp]),
     "vt_accel_accumulate_sky": (_i32, [_vp, _vp, _vp, _u64, _u32, C.c_float, _vp, _vp]),
@@ -292,6 +295,22 @@ class Accel:
     def bounce_rays_device(self, d_attrs, n, spp, seed, d_out, stream=None):
         _check(self.L.vt_accel_bounce_rays(self.h, _ptr(d_attrs), n, spp, seed, _ptr(d_out), None, abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)),
                "vt_accel_bounce_rays")
+
+    # ---- ray queue (device pointers): the generator lists the slots it filled, the traversal visits only those
+    def bounce_rays_queued_device(self, d_attrs, n, spp, seed, d_out, d_queue, d_queue_count, d_miss_hits, stream=None):
+        _check(self.L.vt_accel_bounce_rays_queued(self.h, _ptr(d_attrs), n, spp, seed, _ptr(d_out), _ptr(d_queue), _ptr(d_queue_count),
+                                                  _ptr(d_miss_hits), _ptr(stream)), "vt_accel_bounce_rays_queued")
+
+    def shadow_rays_queued_device(self, d_attrs, n, light, d_out, d_queue, d_queue_count, d_miss_hits, point_light=False,
+                                  tmax=3.4028234663852886e38, stream=None):
+        lv = (C.c_float * 3)(*[float(x) for x in light])
+        _check(self.L.vt_accel_shadow_rays_queued(self.h, _ptr(d_attrs), n, C.cast(lv, _vp), int(point_light), tmax, _ptr(d_out),
+                                                  _ptr(d_queue), _ptr(d_queue_count), _ptr(d_miss_hits), _ptr(stream)),
+               "vt_accel_shadow_rays_queued")
+
+    def traverse_queued_device(self, d_rays, d_queue, d_queue_count, capacity, d_hits, d_attrs=None, any_hit=False, stream=None):
+        _check(self.L.vt_accel_traverse_queued(self.h, _ptr(d_rays), _ptr(d_queue), _ptr(d_queue_count), capacity, _ptr(d_hits), _ptr(d_attrs),
+                                               abi.VT_TRAVERSE_ANY_HIT if any_hit else 0, _ptr(stream)), "vt_accel_traverse_queued")
 
     def trace_diffuse_wave(self, rays, spp, seed=0, want_attrs=False, want_bounce_rays=False, out=None):
         """Host-buffer wave.  `out` may carry preallocated (e.g. pinned) numpy views: hits, bounce_hits, attrs, bounce_rays."""

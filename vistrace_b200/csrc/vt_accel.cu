@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 
@@ -195,7 +196,16 @@ struct DeviceScene {
         DevBuf<vt_hit> hits, bhits;
         DevBuf<vt_attr> attrs;
         DevBuf<float> fb;
+        DevBuf<uint32_t> queue;                // live bounce slots of the tile (ray queue)
+        DevBuf<unsigned long long> queue_count;
     } lanes[3];
+    // ray-queue scratch of the device-pointer wave, one per caller stream
+    struct WaveScratch {
+        DevBuf<uint32_t> queue;
+        DevBuf<unsigned long long> queue_count;
+    };
+    std::map<cudaStream_t, WaveScratch> wave_scratch;
+    std::mutex wave_mutex;
     DevBuf<unsigned long long> live;
     VtSceneView view{};
     VtLaunchConfig cfg;
@@ -228,7 +238,13 @@ struct DeviceScene {
             l.bhits.release();
             l.attrs.release();
             l.fb.release();
+            l.queue.release();
+            l.queue_count.release();
             if (l.stream) cudaStreamDestroy(l.stream);
+        }
+        for (auto &kv : wave_scratch) {
+            kv.second.queue.release();
+            kv.second.queue_count.release();
         }
         if (own_stream) cudaStreamDestroy(own_stream);
     }
@@ -691,6 +707,53 @@ void AccelStruct::ShadowRays(const vt_attr *attrs, uint64_t n, const float light
     }
 }
 
+void AccelStruct::BounceRaysQueued(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays, uint32_t *queue,
+                                   uint64_t *queue_count, vt_hit *miss_hits, void *stream_) {
+    if (!attrs || !out_rays || !queue || !queue_count || !miss_hits) throw std::runtime_error("bounce_rays_queued: null argument");
+    if (spp == 0) throw std::runtime_error("bounce_rays_queued: spp must be positive");
+    if (n * spp > 0xFFFFFFFFull) throw std::runtime_error("bounce_rays_queued: more than 2^32 slots");
+    VT_CUDA(cudaSetDevice(mDevice));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VT_CUDA(cudaMemsetAsync(queue_count, 0, sizeof(uint64_t), stream));
+    if (n == 0) return;
+    VT_CUDA(vt_launch_bounce_rays(attrs, n, spp, seed, 0, out_rays, nullptr, stream, queue, (unsigned long long *)queue_count, miss_hits));
+    mLaunches++;
+}
+
+void AccelStruct::ShadowRaysQueued(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax,
+                                   vt_ray *out_rays, uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream_) {
+    if (!attrs || !out_rays || !light || !queue || !queue_count || !miss_hits) throw std::runtime_error("shadow_rays_queued: null argument");
+    if (n > 0xFFFFFFFFull) throw std::runtime_error("shadow_rays_queued: more than 2^32 slots");
+    VT_CUDA(cudaSetDevice(mDevice));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VT_CUDA(cudaMemsetAsync(queue_count, 0, sizeof(uint64_t), stream));
+    if (n == 0) return;
+    VT_CUDA(vt_launch_shadow_rays(attrs, n, light, point_light, tmax, out_rays, nullptr, stream, queue, (unsigned long long *)queue_count,
+                                  miss_hits));
+    mLaunches++;
+}
+
+void AccelStruct::TraverseQueued(const vt_ray *rays, const uint32_t *queue, const uint64_t *queue_count, uint64_t capacity,
+                                 vt_hit *hits, vt_attr *attrs, uint32_t flags, void *stream_) {
+    check_built(mAccelBuilt);
+    if (capacity == 0) return;
+    if (!rays || !hits || !queue || !queue_count) throw std::runtime_error("traverse_queued: null argument");
+    if (((uintptr_t)rays & 31) || ((uintptr_t)hits & 15))
+        throw std::runtime_error("traverse_queued: device ray buffers must be 32-byte aligned and hit buffers 16-byte aligned");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long *ctr = D.counters.p + 2 * (D.next_slot.fetch_add(1) % kCounterSlots);
+    VT_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), stream));
+    VT_CUDA(vt_launch_traverse(D.view, rays, hits, capacity, (flags & VT_TRAVERSE_ANY_HIT) != 0, ctr, D.cfg, stream, false, queue,
+                               (const unsigned long long *)queue_count));
+    mLaunches++;
+    if (attrs) {  // eager TraceResult of every slot: hits[] is complete once the generator has written its miss records
+        VT_CUDA(vt_launch_trace_result(D.view, rays, hits, nullptr, attrs, capacity, stream));
+        mLaunches++;
+    }
+}
+
 void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, vt_hit *hits, vt_attr *attrs,
                                    vt_ray *bounce_rays, vt_hit *bounce_hits, uint64_t *live_out, uint32_t flags,
                                    void *stream_) {
@@ -708,12 +771,21 @@ void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp,
         if (!attrs || !bounce_rays) throw std::runtime_error("diffuse_wave (device pointers): attrs and bounce_rays scratch required");
         cudaStream_t stream = (cudaStream_t)stream_;
         unsigned long long *c0 = next_counter(), *c1 = next_counter();
+        DeviceScene::WaveScratch *ws;
+        {
+            std::lock_guard<std::mutex> lock(D.wave_mutex);
+            ws = &D.wave_scratch[stream];
+        }
+        ws->queue.ensure(n * spp);
+        ws->queue_count.ensure(1);
         VT_CUDA(cudaMemsetAsync(c0, 0, 16, stream));
         VT_CUDA(cudaMemsetAsync(c1, 0, 16, stream));
+        VT_CUDA(cudaMemsetAsync(ws->queue_count.p, 0, sizeof(unsigned long long), stream));
         VT_CUDA(vt_launch_traverse(D.view, rays, hits, n, false, c0, D.cfg, stream));
         VT_CUDA(vt_launch_trace_result(D.view, rays, hits, nullptr, attrs, n, stream));
-        VT_CUDA(vt_launch_bounce_rays(attrs, n, spp, seed, 0, bounce_rays, nullptr, stream));
-        VT_CUDA(vt_launch_traverse(D.view, bounce_rays, bounce_hits, n * spp, false, c1, D.cfg, stream));
+        VT_CUDA(vt_launch_bounce_rays(attrs, n, spp, seed, 0, bounce_rays, nullptr, stream, ws->queue.p, ws->queue_count.p, bounce_hits));
+        VT_CUDA(vt_launch_traverse(D.view, bounce_rays, bounce_hits, n * spp, false, c1, D.cfg, stream, false, ws->queue.p,
+                                   ws->queue_count.p));
         mLaunches += 4;
         return;
     }
@@ -733,14 +805,19 @@ void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp,
         l.attrs.ensure(tile);
         l.brays.ensure(tile * spp);
         l.bhits.ensure(tile * spp);
+        l.queue.ensure(tile * spp);
+        l.queue_count.ensure(1);
         unsigned long long *c0 = next_counter(), *c1 = next_counter();
         VT_CUDA(cudaMemsetAsync(c0, 0, 16, l.stream));
         VT_CUDA(cudaMemsetAsync(c1, 0, 16, l.stream));
+        VT_CUDA(cudaMemsetAsync(l.queue_count.p, 0, sizeof(unsigned long long), l.stream));
         VT_CUDA(cudaMemcpyAsync(l.rays.p, rays + base, m * sizeof(vt_ray), cudaMemcpyHostToDevice, l.stream));
         VT_CUDA(vt_launch_traverse(D.view, l.rays.p, l.hits.p, m, false, c0, D.cfg, l.stream));
         VT_CUDA(vt_launch_trace_result(D.view, l.rays.p, l.hits.p, nullptr, l.attrs.p, m, l.stream));
-        VT_CUDA(vt_launch_bounce_rays(l.attrs.p, m, spp, seed, base * spp, l.brays.p, D.live.p, l.stream));
-        VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, m * spp, false, c1, D.cfg, l.stream));
+        VT_CUDA(vt_launch_bounce_rays(l.attrs.p, m, spp, seed, base * spp, l.brays.p, D.live.p, l.stream, l.queue.p, l.queue_count.p,
+                                      l.bhits.p));
+        VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, m * spp, false, c1, D.cfg, l.stream, false, l.queue.p,
+                                   l.queue_count.p));
         mLaunches += 4;
         VT_CUDA(cudaMemcpyAsync(hits + base, l.hits.p, m * sizeof(vt_hit), cudaMemcpyDeviceToHost, l.stream));
         VT_CUDA(cudaMemcpyAsync(bounce_hits + base * spp, l.bhits.p, m * spp * sizeof(vt_hit), cudaMemcpyDeviceToHost, l.stream));
@@ -784,15 +861,20 @@ void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp
         l.brays.ensure(tile * spp);
         l.bhits.ensure(tile * spp);
         l.fb.ensure(tile * 3);
+        l.queue.ensure(tile * spp);
+        l.queue_count.ensure(1);
         unsigned long long *c0 = next_counter(), *c1 = next_counter();
         VT_CUDA(cudaMemsetAsync(c0, 0, 16, l.stream));
         VT_CUDA(cudaMemsetAsync(c1, 0, 16, l.stream));
+        VT_CUDA(cudaMemsetAsync(l.queue_count.p, 0, sizeof(unsigned long long), l.stream));
         VT_CUDA(cudaMemsetAsync(l.fb.p, 0, m * 3 * sizeof(float), l.stream));
         VT_CUDA(cudaMemcpyAsync(l.rays.p, rays + base, m * sizeof(vt_ray), cudaMemcpyHostToDevice, l.stream));
         VT_CUDA(vt_launch_traverse(D.view, l.rays.p, l.hits.p, m, false, c0, D.cfg, l.stream));
         VT_CUDA(vt_launch_trace_result(D.view, l.rays.p, l.hits.p, nullptr, l.attrs.p, m, l.stream));
-        VT_CUDA(vt_launch_bounce_rays(l.attrs.p, m, spp, seed, base * spp, l.brays.p, live_out ? D.live.p : nullptr, l.stream));
-        VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, m * spp, false, c1, D.cfg, l.stream));
+        VT_CUDA(vt_launch_bounce_rays(l.attrs.p, m, spp, seed, base * spp, l.brays.p, live_out ? D.live.p : nullptr, l.stream, l.queue.p,
+                                      l.queue_count.p, l.bhits.p));
+        VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, m * spp, false, c1, D.cfg, l.stream, false, l.queue.p,
+                                   l.queue_count.p));
         VT_CUDA(vt_launch_accumulate_sky(D.view, l.attrs.p, l.bhits.p, m, spp, weight, l.fb.p, l.stream));
         mLaunches += 5;
         VT_CUDA(cudaMemcpyAsync(fb + base * 3, l.fb.p, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, l.stream));
@@ -943,6 +1025,33 @@ int vt_accel_shadow_rays(vt_accel *a, const vt_attr *attrs, uint64_t n, const fl
     VT_TRY
     if (!a) throw std::runtime_error("null argument");
     a->impl.ShadowRays(attrs, n, light, point_light != 0, tmax, out_rays, live_out, flags, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_bounce_rays_queued(vt_accel *a, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays,
+                                uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.BounceRaysQueued(attrs, n, spp, seed, out_rays, queue, queue_count, miss_hits, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_shadow_rays_queued(vt_accel *a, const vt_attr *attrs, uint64_t n, const float light[3], int point_light, float tmax,
+                                vt_ray *out_rays, uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.ShadowRaysQueued(attrs, n, light, point_light != 0, tmax, out_rays, queue, queue_count, miss_hits, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_traverse_queued(vt_accel *a, const vt_ray *rays, const uint32_t *queue, const uint64_t *queue_count, uint64_t capacity,
+                             vt_hit *hits, vt_attr *attrs, uint32_t flags, void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.TraverseQueued(rays, queue, queue_count, capacity, hits, attrs, flags, stream);
     return 0;
     VT_CATCH(1)
 }

@@ -141,6 +141,15 @@ public:
     // One shadow ray per non-sky hit: origin = CalcRayOrigin(pos, geometric normal), toward a directional or point light.
     void ShadowRays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out_rays,
                     uint64_t *live_out, uint32_t flags, void *stream);
+    // Ray-queue variants (DEVICE pointers only, enqueued on `stream`): the generator also lists the slots it filled —
+    // queue[0, *queue_count), *queue_count zeroed here — and writes the miss record of every masked slot into
+    // miss_hits; TraverseQueued then traces the listed slots only.  spp == 0 selects the shadow-ray generator.
+    void BounceRaysQueued(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays, uint32_t *queue,
+                          uint64_t *queue_count, vt_hit *miss_hits, void *stream);
+    void ShadowRaysQueued(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out_rays,
+                          uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream);
+    void TraverseQueued(const vt_ray *rays, const uint32_t *queue, const uint64_t *queue_count, uint64_t capacity, vt_hit *hits,
+                        vt_attr *attrs, uint32_t flags, void *stream);
     // "primary + diffuse" wave in one call: traverse the primary rays, build their TraceResults, spawn
     // spp bounce rays per hit on the device and traverse those.  Host pointers are processed in tiles
     // on several streams so the PCIe copies overlap the kernels.

@@ -27,8 +27,11 @@ struct VtLaunchConfig {
 // K1 — closest hit (or any hit) for n rays.  counters[0] = ray queue head (must be 0 on entry),
 // counters[1] += rays rejected by the argument rules; with stats: counters[2] += traversal steps,
 // counters[3] += triangle tests (SingleRayTraverser::Statistics, single_ray_traverser.hpp:132-135).
+// Ray queue (both or neither): queue[0, min(n, *queue_count)) names the slots of rays/hits to trace — what a
+// generator (K3) listed as live; every other slot is left untouched.
 cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit *hits, uint64_t n, bool any_hit,
-                               unsigned long long *counters, const VtLaunchConfig &cfg, cudaStream_t stream, bool stats = false);
+                               unsigned long long *counters, const VtLaunchConfig &cfg, cudaStream_t stream, bool stats = false,
+                               const uint32_t *queue = nullptr, const unsigned long long *queue_count = nullptr);
 cudaError_t vt_traverse_occupancy(int *blocks_per_sm, size_t smem_bytes, int layout);
 
 // K2 — eager TraceResult for n (ray, hit) records; cones = n x {coneWidth, coneAngle} or nullptr.
@@ -37,10 +40,15 @@ cudaError_t vt_launch_trace_result(const VtSceneView &S, const vt_ray *rays, con
 
 // K3 — secondary-ray generation: spp cosine-weighted bounce rays per (non-sky) hit into slot i*spp+s,
 // masked slots (tmax < 0) elsewhere; *live += spawned rays.  And a pinhole primary-ray generator.
+// Ray queue (optional, all three or none): queue[pos] = slot of every ray spawned, pos handed out from *queue_count
+// (must be 0 on entry), and miss_hits[slot] = a miss record for every masked slot — so the traversal that follows
+// only has to visit the queue and the hit buffer is complete in slot order all the same.
 cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, uint64_t slot_offset,
-                                  vt_ray *out, unsigned long long *live, cudaStream_t stream);
+                                  vt_ray *out, unsigned long long *live, cudaStream_t stream, uint32_t *queue = nullptr,
+                                  unsigned long long *queue_count = nullptr, vt_hit *miss_hits = nullptr);
 cudaError_t vt_launch_shadow_rays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out,
-                                  unsigned long long *live, cudaStream_t stream);
+                                  unsigned long long *live, cudaStream_t stream, uint32_t *queue = nullptr,
+                                  unsigned long long *queue_count = nullptr, vt_hit *miss_hits = nullptr);
 cudaError_t vt_launch_pinhole_rays(const float *cam12, uint32_t width, uint32_t height, vt_ray *out, cudaStream_t stream);
 
 // K4 — fb[i] += weight * albedo_i * (escaped bounce rays of pixel i) / spp, RGBFFF framebuffer.

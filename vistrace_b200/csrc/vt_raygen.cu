@@ -16,6 +16,11 @@
 // Slot j = i * spp + s belongs to primary ray i (the hash counter is slot_offset + j, so a batch
 // traced in tiles draws the same numbers as the batch traced whole); hits that spawn nothing (miss, sky) leave a
 // MASKED slot (tmax < 0) that K1 reports as a miss without counting it as an invalid ray.
+//
+// Ray queue: a generator can also LIST the slots it filled (queue[pos] = slot, pos from a device counter, one
+// warp-aggregated atomic per warp) and write the miss record of every masked slot itself.  K1 then walks the queue
+// only — masked slots never occupy a lane — and the hit buffer still comes out complete, in slot order.  The order of
+// the queue depends on warp scheduling; the hit buffer does not (rays are independent).
 #include "vt_kernels.h"
 #include "vt_math.cuh"
 
@@ -43,9 +48,39 @@ VT_DEV float ray_origin_1(float pos, float nrm) {
     return fabsf(pos) < origin ? pos + nrm * fScale : iPos;
 }
 
+// Block-level tail shared by the generators: count the spawned rays, append their slots to the queue, write the
+// miss record of the masked ones.  Must be reached by every thread of the (256-thread) block.  ONE atomic per block and
+// counter: a warp-aggregated atomic per warp is 260 k same-address atomics for a 1080p x 4 spp wave — they serialise
+// in L2 and cost as much as the generator itself (measured: K3 0.08 -> 0.16 ms).
+VT_DEV void publish_slot(bool in_range, bool spawned, unsigned long long slot, unsigned long long *live, uint32_t *queue,
+                         unsigned long long *queue_count, vt_hit *miss_hits) {
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned long long s_base;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, spawned);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    unsigned before = 0, total = 0;
+#pragma unroll
+    for (unsigned w = 0; w < 8; w++) {
+        const unsigned c = s_warp[w];
+        before += w < warp ? c : 0u;
+        total += c;
+    }
+    if (threadIdx.x == 0 && total) {
+        if (live) atomicAdd(live, (unsigned long long)total);
+        if (queue) s_base = atomicAdd(queue_count, (unsigned long long)total);
+    }
+    if (!queue) return;
+    __syncthreads();
+    if (spawned) queue[s_base + before + __popc(m & ((1u << lane) - 1u))] = (uint32_t)slot;
+    else if (in_range) reinterpret_cast<float4 *>(miss_hits)[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(VT_MISS));
+}
+
 __global__ void __launch_bounds__(256)
 k_bounce_rays(const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t spp, unsigned long long seed,
-              unsigned long long slot_offset, vt_ray *__restrict__ out, unsigned long long *__restrict__ live) {
+              unsigned long long slot_offset, vt_ray *__restrict__ out, unsigned long long *__restrict__ live,
+              uint32_t *__restrict__ queue, unsigned long long *__restrict__ queue_count, vt_hit *__restrict__ miss_hits) {
     const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long total = n * spp;
     bool spawned = false;
@@ -76,10 +111,7 @@ k_bounce_rays(const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t 
         o[0] = ro;
         o[1] = rd;
     }
-    if (live) {
-        const unsigned m = __ballot_sync(0xffffffffu, spawned);
-        if ((threadIdx.x & 31u) == 0 && m) atomicAdd(live, (unsigned long long)__popc(m));
-    }
+    if (live || queue) publish_slot(j < total, spawned, j, live, queue, queue_count, miss_hits);
 }
 
 // Shadow rays (config 2 / 5: "primary + shadow"): one ray per non-sky hit from CalcRayOrigin(pos, geometric normal on
@@ -87,7 +119,8 @@ k_bounce_rays(const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t 
 // tmax = 1: t is parametric, source/objects/AccelStruct.cpp:810-815).  Misses and sky hits leave masked slots.
 __global__ void __launch_bounds__(256)
 k_shadow_rays(const vt_attr *__restrict__ attrs, unsigned long long n, float lx, float ly, float lz, int point_light, float tmax,
-              vt_ray *__restrict__ out, unsigned long long *__restrict__ live) {
+              vt_ray *__restrict__ out, unsigned long long *__restrict__ live, uint32_t *__restrict__ queue,
+              unsigned long long *__restrict__ queue_count, vt_hit *__restrict__ miss_hits) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool spawned = false;
     if (i < n) {
@@ -108,10 +141,7 @@ k_shadow_rays(const vt_attr *__restrict__ attrs, unsigned long long n, float lx,
         o4[0] = ro;
         o4[1] = rd;
     }
-    if (live) {
-        const unsigned m = __ballot_sync(0xffffffffu, spawned);
-        if ((threadIdx.x & 31u) == 0 && m) atomicAdd(live, (unsigned long long)__popc(m));
-    }
+    if (live || queue) publish_slot(i < n, spawned, i, live, queue, queue_count, miss_hits);
 }
 
 // Pinhole primary rays, pixel-centre sampling, row-major (index = width * j + i) — the loop of
@@ -183,20 +213,25 @@ cudaError_t vt_launch_accumulate_sky(const VtSceneView &S, const vt_attr *attrs,
 }
 
 cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, uint64_t slot_offset,
-                                  vt_ray *out, unsigned long long *live, cudaStream_t stream) {
+                                  vt_ray *out, unsigned long long *live, cudaStream_t stream, uint32_t *queue,
+                                  unsigned long long *queue_count, vt_hit *miss_hits) {
     const unsigned long long total = (unsigned long long)n * spp;
     if (total == 0) return cudaSuccess;
+    if (queue && (!queue_count || !miss_hits || total > 0xFFFFFFFFull)) return cudaErrorInvalidValue;
     const unsigned block = 256;
-    k_bounce_rays<<<(unsigned)((total + block - 1) / block), block, 0, stream>>>(attrs, n, spp, seed, slot_offset, out, live);
+    k_bounce_rays<<<(unsigned)((total + block - 1) / block), block, 0, stream>>>(attrs, n, spp, seed, slot_offset, out, live, queue,
+                                                                                queue_count, miss_hits);
     return cudaGetLastError();
 }
 
 cudaError_t vt_launch_shadow_rays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out,
-                                  unsigned long long *live, cudaStream_t stream) {
+                                  unsigned long long *live, cudaStream_t stream, uint32_t *queue, unsigned long long *queue_count,
+                                  vt_hit *miss_hits) {
     if (n == 0) return cudaSuccess;
+    if (queue && (!queue_count || !miss_hits || n > 0xFFFFFFFFull)) return cudaErrorInvalidValue;
     const unsigned block = 256;
     k_shadow_rays<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(attrs, n, light[0], light[1], light[2], point_light ? 1 : 0,
-                                                                            tmax, out, live);
+                                                                            tmax, out, live, queue, queue_count, miss_hits);
     return cudaGetLastError();
 }
 

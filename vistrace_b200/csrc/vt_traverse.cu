@@ -368,8 +368,10 @@ VT_DEV void write_hit(vt_hit *hits, unsigned long long idx, const RayState &r) {
 template <bool ANY_HIT, bool ALPHA, bool SMEM, bool STATS = false>
 __global__ void __launch_bounds__(VT_TRAVERSE_BLOCK, VT_TRAVERSE_MIN_BLOCKS)
 k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restrict__ hits, unsigned long long n,
-           unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold) {
+           unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold,
+           const uint32_t *__restrict__ queue, const unsigned long long *__restrict__ queue_count) {
     extern __shared__ float4 s_pairs[];
+    if (queue_count) n = min(n, *queue_count);  // ray queue: only the slots the generator listed are traced
     if (SMEM) {  // optional: stage the top of the tree (the first n_smem_pairs pairs, breadth-first) per CTA
         for (uint32_t i = threadIdx.x; i < S.n_smem_pairs * 4u; i += blockDim.x)
             s_pairs[i] = __ldg(reinterpret_cast<const float4 *>(S.pairs) + i);
@@ -414,6 +416,7 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
             if (!alive) {
                 ray_idx = base + __popc(idle & lt_mask);
                 if (ray_idx < n) {
+                    if (queue) ray_idx = __ldg(queue + ray_idx);  // queued launch: the slot this entry names
                     float4 ra, rb;
                     ldg256_ray(rays + ray_idx, ra, rb);
                     vt_ray in{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
@@ -520,7 +523,9 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
 template <bool ANY_HIT, bool ALPHA, bool STATS, bool QUAD>
 __global__ void __launch_bounds__(VT_TRAVERSE_BLOCK, VT_COMPACT_MIN_BLOCKS)
 k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restrict__ hits, unsigned long long n,
-                   unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold) {
+                   unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold,
+                   const uint32_t *__restrict__ queue, const unsigned long long *__restrict__ queue_count) {
+    if (queue_count) n = min(n, *queue_count);  // ray queue: only the slots the generator listed are traced
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     // the layouts served by this kernel validate the worst-case stack depth on the host (<= VT_STACK_SIZE), so
@@ -560,6 +565,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
             if (!alive) {
                 ray_idx = base + __popc(idle & lt_mask);
                 if (ray_idx < n) {
+                    if (queue) ray_idx = __ldg(queue + ray_idx);  // queued launch: the slot this entry names
                     float4 ra, rb;
                     ldg256_ray(rays + ray_idx, ra, rb);
                     vt_ray in{ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
@@ -677,8 +683,10 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
 }  // namespace
 
 cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit *hits, uint64_t n, bool any_hit,
-                               unsigned long long *counters, const VtLaunchConfig &cfg, cudaStream_t stream, bool stats) {
+                               unsigned long long *counters, const VtLaunchConfig &cfg, cudaStream_t stream, bool stats,
+                               const uint32_t *queue, const unsigned long long *queue_count) {
     if (n == 0) return cudaSuccess;
+    if ((queue == nullptr) != (queue_count == nullptr)) return cudaErrorInvalidValue;
     const size_t smem = (S.cpairs || S.quads) ? 0 : (size_t)S.n_smem_pairs * sizeof(VtPair);
     int grid;
     if (cfg.persistent) {
@@ -691,7 +699,7 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         kernel<<<grid, VT_TRAVERSE_BLOCK, smem, stream>>>(S, rays, hits, (unsigned long long)n, counters,
-                                                          cfg.persistent ? 1 : 0, cfg.refill_threshold, cfg.tri_threshold);
+                                                          cfg.persistent ? 1 : 0, cfg.refill_threshold, cfg.tri_threshold, queue, queue_count);
         return cudaGetLastError();
     };
     if (S.quads) {
