@@ -193,6 +193,17 @@ void vt_accel_destroy(vt_accel *accel);
  * it to the device layout and upload.  Rebuild = call again. */
 int vt_accel_populate(vt_accel *accel, const vt_scene *scene);
 
+/* AccelStruct:Rebuild (source/VisTrace.cpp:798-818) for MOVED geometry of unchanged topology — the same triangles in
+ * the same order with new vertices, e.g. props that moved: keeps the structure of the resident hierarchy and refits
+ * its boxes bottom-up as bvh::HierarchyRefitter does (libs/bvh/include/bvh/hierarchy_refitter.hpp:20-31, leaf update of
+ * libs/bvh/test/refit_bvh.cpp:79-89) instead of the full rebuild the reference performs, then re-derives the resident
+ * node layout and uploads.  Fails when nothing was populated or scene->n_tris differs. */
+int vt_accel_refit(vt_accel *accel, const vt_scene *scene);
+
+/* Host-only: the refit step alone — `nodes` (bvh::Bvh<float> form, node_count entries) are updated in place for the
+ * triangles of `scene`; prim_indices has scene->n_tris entries. */
+int vt_refit_bvh(const vt_scene *scene, vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices);
+
 /* Same, but with a hierarchy the caller already built, in bvh::Bvh<float> form
  * (`mAccel.nodes`, `mAccel.primitive_indices`, `mAccel.node_count`;
  * libs/bvh/include/bvh/bvh.hpp:96-99).  This is what the reference's own
@@ -365,7 +376,10 @@ int vt_compact_pairs(const void *pairs, uint64_t n_pairs, void *cpairs_out);
 /* Host-only: bvh::Bvh<float>-form hierarchy -> quad nodes (64 bytes each, depth-first order; layout in
  * vistrace_b200/csrc/vt_device.h: VtQuad) + the leaf-order permutation of the triangles.  Call with
  * quads_out == NULL to get the count; *n_quads is the capacity on entry, the count on return.
- * *max_stack = worst-case number of pending child references during traversal (<= 64). */
+ * *max_stack = worst-case number of pending child references during traversal (<= 64).
+ * plane = (OFFSET + q) * scale + origin_adj exactly, OFFSET = vt_quad_plane_offset() (the float the kernel
+ * forms from a quantised byte: 1024 through the fp16 pattern 0x6400 | q, or 2^23 through 0x4B000000 | q). */
+uint32_t vt_quad_plane_offset(void);
 int vt_build_quads(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris,
                    void *quads_out, uint64_t *n_quads, uint32_t *leaf_order_out, uint32_t *root_leaf_count,
                    uint32_t *max_stack);

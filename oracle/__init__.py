@@ -54,6 +54,7 @@ def _lib(kind):
         "get_tri_derived": (None, [vp, vp]),
         "get_bvh": (None, [vp, vp, vp, vp, vp]),
         "set_bvh": (None, [vp, vp, u64, vp]),
+        "refit": (None, [vp, vp]),
         "traverse": (C.c_double, [vp, vp, u64, vp, vp, i32, vp]),
         "trace_result": (None, [vp, vp, vp, u64, vp, i32]),
         "trace_result_cones": (None, [vp, vp, vp, vp, u64, vp, i32]),
@@ -118,6 +119,13 @@ class CpuScene:
         prim_indices = np.ascontiguousarray(prim_indices, np.uint64)
         assert len(prim_indices) == self.n_tris
         self.lib.set_bvh(self.h, nodes.ctypes.data, len(nodes), prim_indices.ctypes.data)
+
+    def refit(self, scene):
+        """Same topology, moved vertices: the checker's own bottom-up refit of its current hierarchy
+        (reference kind: bvh::HierarchyRefitter itself)."""
+        assert scene.n_tris == self.n_tris
+        self.scene = scene
+        self.lib.refit(self.h, C.cast(scene.ptr(), C.c_void_p))
 
     def traverse(self, rays, want_attrs=False, threads=0, want_stats=False):
         """Returns dict(hits, attrs?, seconds, steps?, isects?)."""

@@ -38,6 +38,7 @@
 #undef private
 
 #include "VTFParser.h"
+#include "bvh/hierarchy_refitter.hpp"
 #include "bvh/leaf_collapser.hpp"
 #include "bvh/locally_ordered_clustering_builder.hpp"
 #include "bvh/node_intersectors.hpp"
@@ -113,6 +114,29 @@ glm::mat2x4 to_mat(const float m[8]) {
     r[0] = glm::vec4(m[0], m[1], m[2], m[3]);
     r[1] = glm::vec4(m[4], m[5], m[6], m[7]);
     return r;
+}
+
+// mTriangles from the caller's vertices through the reference constructor (source/objects/Primitives.h:75-89)
+void fill_triangles(AccelStruct &a, const vt_scene *s) {
+    a.mTriangles.resize(s->n_tris);
+#pragma omp parallel for
+    for (int64_t i = 0; i < static_cast<int64_t>(s->n_tris); i++) {
+        const vt_tri_in &t = s->tris[i];
+        glm::vec2 uvs[3] = {glm::vec2(t.uvs[0][0], t.uvs[0][1]), glm::vec2(t.uvs[1][0], t.uvs[1][1]),
+                            glm::vec2(t.uvs[2][0], t.uvs[2][1])};
+        // Reference constructor: source/objects/Primitives.h:75-89
+        Triangle tri(Vector3(t.p[0][0], t.p[0][1], t.p[0][2]), Vector3(t.p[1][0], t.p[1][1], t.p[1][2]),
+                     Vector3(t.p[2][0], t.p[2][1], t.p[2][2]), 0, uvs, t.one_sided != 0);
+        tri.material = t.material; // ctor takes int16_t; ingestion overwrites it with the global index anyway
+        tri.entIdx = t.ent_idx;
+        for (int k = 0; k < 3; k++) {
+            tri.normals[k] = glm::vec3(t.normals[k][0], t.normals[k][1], t.normals[k][2]);
+            tri.tangents[k] = glm::vec3(t.tangents[k][0], t.tangents[k][1], t.tangents[k][2]);
+            tri.alphas[k] = t.alphas[k];
+            tri.numBones[k] = 0;
+        }
+        a.mTriangles[i] = tri;
+    }
 }
 
 void build_reference_sequence(AccelStruct &a) {
@@ -203,25 +227,7 @@ void *vtref_create(const vt_scene *s, int build) {
                              s->entities[i].colour[3]);
     }
 
-    a.mTriangles.resize(s->n_tris);
-#pragma omp parallel for
-    for (int64_t i = 0; i < static_cast<int64_t>(s->n_tris); i++) {
-        const vt_tri_in &t = s->tris[i];
-        glm::vec2 uvs[3] = {glm::vec2(t.uvs[0][0], t.uvs[0][1]), glm::vec2(t.uvs[1][0], t.uvs[1][1]),
-                            glm::vec2(t.uvs[2][0], t.uvs[2][1])};
-        // Reference constructor: source/objects/Primitives.h:75-89
-        Triangle tri(Vector3(t.p[0][0], t.p[0][1], t.p[0][2]), Vector3(t.p[1][0], t.p[1][1], t.p[1][2]),
-                     Vector3(t.p[2][0], t.p[2][1], t.p[2][2]), 0, uvs, t.one_sided != 0);
-        tri.material = t.material; // ctor takes int16_t; ingestion overwrites it with the global index anyway
-        tri.entIdx = t.ent_idx;
-        for (int k = 0; k < 3; k++) {
-            tri.normals[k] = glm::vec3(t.normals[k][0], t.normals[k][1], t.normals[k][2]);
-            tri.tangents[k] = glm::vec3(t.tangents[k][0], t.tangents[k][1], t.tangents[k][2]);
-            tri.alphas[k] = t.alphas[k];
-            tri.numBones[k] = 0;
-        }
-        a.mTriangles[i] = tri;
-    }
+    fill_triangles(a, s);
 
     if (build) build_reference_sequence(a);
     return rs;
@@ -254,6 +260,27 @@ void vtref_get_bvh(void *h, vt_node *nodes, uint64_t *node_count, uint64_t *prim
     if (nodes) std::memcpy(nodes, a.mAccel.nodes.get(), a.mAccel.node_count * sizeof(vt_node));
     if (prim_indices)
         for (size_t i = 0; i < a.mTriangles.size(); i++) prim_indices[i] = a.mAccel.primitive_indices[i];
+}
+
+// Moved geometry, same topology: rebuild mTriangles from `s` and refit the CURRENT hierarchy with the reference
+// library's own bvh::HierarchyRefitter, leaf update exactly as its test drives it (libs/bvh/test/refit_bvh.cpp:79-89).
+void vtref_refit(void *h, const vt_scene *s) {
+    AccelStruct &a = static_cast<RefScene *>(h)->accel;
+    if (s->n_tris != a.mTriangles.size() || !a.mAccelBuilt) throw std::runtime_error("vtref_refit: topology changed / nothing built");
+    fill_triangles(a, s);
+    bvh::HierarchyRefitter<BVH> refitter(a.mAccel);
+    refitter.refit([&](BVH::Node &leaf) {
+        auto bbox = bvh::BoundingBox<float>::empty();
+        for (size_t i = 0; i < leaf.primitive_count; ++i) {
+            auto &triangle = a.mTriangles[a.mAccel.primitive_indices[leaf.first_child_or_primitive + i]];
+            bbox.extend(triangle.bounding_box());
+        }
+        leaf.bounding_box_proxy() = bbox;
+    });
+    delete a.mpIntersector;
+    delete a.mpTraverser;
+    a.mpIntersector = new Intersector(a.mAccel, a.mTriangles.data());
+    a.mpTraverser = new Traverser(a.mAccel);
 }
 
 // Replace the hierarchy with one built elsewhere (same bvh::Bvh<float> form) so the

@@ -676,6 +676,60 @@ void vto_set_bvh(void *h, const vt_node *nodes, uint64_t node_count, const uint6
     s->built = 1;
 }
 
+/* bvh::HierarchyRefitter::refit (libs/bvh/include/bvh/hierarchy_refitter.hpp:20-31) over moved geometry of the same
+ * topology, leaf update as the library's own test drives it (libs/bvh/test/refit_bvh.cpp:79-89): a leaf's box is the
+ * union of Triangle::bounding_box() (source/objects/Primitives.h:107-113: p0, p1() = p0 - e1, p2() = p0 + e2) of its
+ * primitives, an inner node's box the union of its two children.  BoundingBox::extend is a per-component min / max
+ * (bounding_box.hpp), so any bottom-up order gives the same bits; the parallel schedule of bottom_up_algorithm.hpp is
+ * not restated, a reverse pre-order walk is used instead. */
+void vto_refit(void *h, const vt_scene *sc) {
+    OScene *s = (OScene *)h;
+    if (!s->built || sc->n_tris != s->n_tris) return;
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)sc->n_tris; i++) derive_triangle(&sc->tris[i], &s->tris[i]);
+    uint64_t *order = (uint64_t *)malloc(sizeof(uint64_t) * s->node_count), n_order = 0;
+    uint64_t *stack = (uint64_t *)malloc(sizeof(uint64_t) * s->node_count), sp = 0;
+    stack[sp++] = 0;
+    while (sp) { /* pre-order: parents before children */
+        uint64_t i = stack[--sp];
+        order[n_order++] = i;
+        if (s->nodes[i].prim_count == 0) {
+            stack[sp++] = s->nodes[i].first;
+            stack[sp++] = (uint64_t)s->nodes[i].first + 1;
+        }
+    }
+    for (uint64_t k = n_order; k-- > 0;) { /* children before parents */
+        vt_node *nd = &s->nodes[order[k]];
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}; /* BoundingBox::empty() */
+        if (nd->prim_count) {
+            for (uint32_t t = 0; t < nd->prim_count; t++) {
+                const OTri *tr = &s->tris[s->prim_indices[nd->first + t]];
+                for (int a = 0; a < 3; a++) {
+                    const float v[3] = {tr->p0[a], tr->p0[a] - tr->e1[a], tr->p0[a] + tr->e2[a]};
+                    for (int j = 0; j < 3; j++) {
+                        lo[a] = fminf(lo[a], v[j]);
+                        hi[a] = fmaxf(hi[a], v[j]);
+                    }
+                }
+            }
+        } else {
+            for (int c = 0; c < 2; c++) {
+                const vt_node *ch = &s->nodes[nd->first + c];
+                for (int a = 0; a < 3; a++) {
+                    lo[a] = fminf(lo[a], ch->bounds[2 * a]);
+                    hi[a] = fmaxf(hi[a], ch->bounds[2 * a + 1]);
+                }
+            }
+        }
+        for (int a = 0; a < 3; a++) {
+            nd->bounds[2 * a] = lo[a];
+            nd->bounds[2 * a + 1] = hi[a];
+        }
+    }
+    free(order);
+    free(stack);
+}
+
 static double now_s(void) {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);

@@ -291,7 +291,7 @@ def test_quad_layout_structure_and_walk(oracle_mod, scene_name):
     # decoded planes: exact floats on the power-of-two grid
     scale = quads["scale"].astype(np.float64)                                                            # [quad, axis], powers of two
     assert ((quads["scale"].view(np.uint32) & 0x007FFFFF) == 0).all()
-    magic = (np.uint32(0x4B000000) | quads["q"].astype(np.uint32)).view(np.float32).astype(np.float64)   # [quad, axis, lo/hi, child]
+    magic = float(vt.quad_plane_offset()) + quads["q"].astype(np.float64)                                 # [quad, axis, lo/hi, child]
     plane = magic * scale[:, :, None, None] + quads["origin_adj"].astype(np.float64)[:, :, None, None]
     assert (plane.astype(np.float32).astype(np.float64) == plane).all()
     # leaf children: the decoded box contains every vertex of the run's triangles
@@ -331,3 +331,67 @@ def test_quad_layout_structure_and_walk(oracle_mod, scene_name):
                 if max(lo, r["tmin"]) <= min(hi, best_t) * (1 + 1e-6) + 1e-6:
                     stack.append(int(refs[ref, ci]))
     assert (got == want["prim"]).mean() > 0.98 and ((got == abi.VT_MISS) == (want["prim"] == abi.VT_MISS)).mean() > 0.98
+
+
+def _moved_props(scene, seed=9):
+    """Same triangles, same order, new vertices: every prop (entity >= 1) gets its own rigid shift + a little jitter."""
+    from vistrace_b200 import abi
+
+    rng = np.random.default_rng(seed)
+    tris = scene.tris.copy()
+    n_ent = len(scene.entities)
+    shift = rng.uniform(-6.0, 6.0, (n_ent, 3)).astype(np.float32)
+    shift[0] = 0.0  # the world stays where it is
+    tris["p"] = tris["p"] + shift[tris["ent_idx"]][:, None, :] + rng.uniform(-0.05, 0.05, tris["p"].shape).astype(np.float32) * (tris["ent_idx"] > 0)[:, None, None]
+    return abi.SceneData(tris, scene.materials, scene.entities)
+
+
+@pytest.mark.parametrize("tree", ["product", "reference"])
+def test_refit_matches_the_reference_hierarchy_refitter(built, oracle_mod, tree):
+    """vt_refit_bvh against bvh::HierarchyRefitter itself (oracle/_ref, leaf update of libs/bvh/test/refit_bvh.cpp:79-89)
+    and against the C restatement: same boxes for every node, structure untouched, boxes nested and tight."""
+    import vistrace_b200 as vt
+    from vistrace_b200 import scenes
+
+    scene = scenes.scene_props(6, 15, 9, 8)
+    moved = _moved_props(scene)
+    kinds = [k for k in ("reference", "port") if oracle_mod.available(k)]
+    if tree == "reference" and "reference" not in kinds:
+        pytest.skip("the reference-built tree needs oracle/_ref")
+    if tree == "reference":
+        nodes, prims = oracle_mod.CpuScene(scene, "reference", build_bvh=True).get_bvh()
+    else:
+        nodes, prims = vt.build_bvh(scene)
+    got = vt.refit_bvh(moved, nodes, prims)
+    assert (got["first"] == nodes["first"]).all() and (got["prim_count"] == nodes["prim_count"]).all()
+    assert (got["bounds"] != nodes["bounds"]).any()
+    for kind in kinds:
+        cpu = oracle_mod.CpuScene(scene, kind, build_bvh=False)
+        cpu.set_bvh(nodes, prims)
+        cpu.refit(moved)
+        want, _ = cpu.get_bvh()
+        assert np.array_equal(got["bounds"], want["bounds"]), kind  # numeric equality: +0 == -0
+        assert (want["first"] == nodes["first"]).all()
+    # leaves hold their triangles exactly; parents are the union of their children
+    p = moved.tris["p"]
+    leaf = np.nonzero(got["prim_count"] > 0)[0]
+    for i in leaf[:: max(1, len(leaf) // 200)]:
+        v = p[prims[got["first"][i]: got["first"][i] + got["prim_count"][i]].astype(np.int64)].reshape(-1, 3)
+        b = got["bounds"][i]
+        assert np.allclose(b[0::2], v.min(0), rtol=0, atol=1e-4) and np.allclose(b[1::2], v.max(0), rtol=0, atol=1e-4)
+        assert (b[0::2] <= v.min(0) + 1e-4).all() and (b[1::2] >= v.max(0) - 1e-4).all()
+    inner = np.nonzero(got["prim_count"] == 0)[0]
+    l, r = got["bounds"][got["first"][inner]], got["bounds"][got["first"][inner] + 1]
+    assert np.array_equal(got["bounds"][inner][:, 0::2], np.minimum(l[:, 0::2], r[:, 0::2]))
+    assert np.array_equal(got["bounds"][inner][:, 1::2], np.maximum(l[:, 1::2], r[:, 1::2]))
+
+
+def test_refit_rejects_a_changed_topology(built):
+    import vistrace_b200 as vt
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_heightfield(12)
+    nodes, prims = vt.build_bvh(scene)
+    fewer = abi.SceneData(scene.tris[:-2], scene.materials, scene.entities)
+    with pytest.raises(RuntimeError):
+        vt.refit_bvh(fewer, nodes, prims[:-2])  # leaves address primitives past the end

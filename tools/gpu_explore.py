@@ -93,6 +93,7 @@ def main():
     ap.add_argument("--props", type=int, default=0)
     ap.add_argument("--cpu", type=int, default=0, help="time the CPU reference on this many rays")
     ap.add_argument("--rebuild", action="store_true", help="rebuild the hierarchy per knob set (builder knobs: VT_MAX_LEAF, VT_TRAV_COST, ...)")
+    ap.add_argument("--ref-hits", default="", help="npz path: saved on first use, compared (records differing) on later runs — A/B of library builds")
     ap.add_argument("--sorts", default="", help="comma list of host-side bounce-ray orderings to time (see sort_key)")
     args = ap.parse_args()
     w, h = map(int, args.res.split("x"))
@@ -140,6 +141,21 @@ def main():
                           "S_I_bounce": [round(st_b[0] / len(bounce), 2), round(st_b[1] / len(bounce), 2)], "upload_s": round(t_up, 2), "primary_Mrays": round(len(rays) / ms_p / 1e3, 1),
                           "bounce_Mrays": round(len(bounce) / ms_b / 1e3, 1), "bounce_anyhit_Mrays": round(len(bounce) / ms_a / 1e3, 1),
                           "primary+attrs_Mrays": round(len(rays) / ms_pa / 1e3, 1), "ms": [round(ms_p, 3), round(ms_b, 3), round(ms_a, 3), round(ms_pa, 3)]}), flush=True)
+        if args.ref_hits:
+            accel.traverse_device(d_rays.data_ptr(), len(rays), d_hits.data_ptr(), None)
+            torch.cuda.synchronize()
+            hp = d_hits[: len(rays) * 16].cpu().numpy().copy()
+            accel.traverse_device(d_bounce.data_ptr(), len(bounce), d_hits.data_ptr(), None)
+            torch.cuda.synchronize()
+            hb = d_hits[: len(bounce) * 16].cpu().numpy().copy()
+            if os.path.exists(args.ref_hits):
+                ref = np.load(args.ref_hits)
+                dp = (hp.reshape(-1, 16) != ref["hp"].reshape(-1, 16)).any(1).sum()
+                db = (hb.reshape(-1, 16) != ref["hb"].reshape(-1, 16)).any(1).sum()
+                print(json.dumps({"vs_ref_hits": args.ref_hits, "primary_records_differing": int(dp), "bounce_records_differing": int(db)}), flush=True)
+            else:
+                np.savez(args.ref_hits, hp=hp, hb=hb)
+                print(json.dumps({"saved_ref_hits": args.ref_hits}), flush=True)
         for name in [x for x in args.sorts.split(",") if x]:
             order = np.argsort(sort_key(bounce, name), kind="stable")
             d_sorted = to_dev(np.ascontiguousarray(bounce[order]))

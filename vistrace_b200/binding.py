@@ -24,6 +24,8 @@ SYMBOLS = {
     "vt_accel_destroy": (None, [_vp]),
     "vt_accel_populate": (_i32, [_vp, _vp]),
     "vt_accel_populate_with_bvh": (_i32, [_vp, _vp, _vp, _u64, _vp]),
+    "vt_accel_refit": (_i32, [_vp, _vp]),
+    "vt_refit_bvh": (_i32, [_vp, _vp, _u64, _vp]),
     "vt_accel_get_bvh": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "vt_accel_traverse": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_traverse_stats": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp]),
@@ -41,6 +43,7 @@ SYMBOLS = {
     "vt_accel_get_layout": (_i32, [_vp]),
     "vt_compact_pairs": (_i32, [_vp, _u64, _vp]),
     "vt_skin_triangles": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32]),
+    "vt_quad_plane_offset": (_u32, []),
     "vt_build_quads": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_invalid_rays": (_u64, [_vp]),
     "vt_accel_launch_count": (_u64, [_vp]),
@@ -98,6 +101,14 @@ def build_bvh(scene):
     cap = C.c_uint64(len(nodes))
     _check(L.vt_build_bvh(C.cast(scene.ptr(), _vp), nodes.ctypes.data, C.addressof(cap), prims.ctypes.data), "vt_build_bvh")
     return nodes, prims
+
+
+def refit_bvh(scene, nodes, prim_indices):
+    """Host-only bvh::HierarchyRefitter step: a refitted COPY of `nodes` for the (moved) triangles of `scene`."""
+    out = np.ascontiguousarray(nodes, abi.NODE).copy()
+    prims = np.ascontiguousarray(prim_indices, np.uint64)
+    _check(lib().vt_refit_bvh(C.cast(scene.ptr(), _vp), out.ctypes.data, len(out), prims.ctypes.data), "vt_refit_bvh")
+    return out
 
 
 def skin_triangles(tris, skin, bones, binds):
@@ -158,6 +169,11 @@ QUAD = np.dtype([("origin_adj", np.float32, 3), ("scale", np.float32, 3), ("q", 
 assert QUAD.itemsize == 64
 
 
+def quad_plane_offset():
+    """OFFSET of the quad layout's plane decode: plane = (OFFSET + q) * scale + origin_adj."""
+    return int(lib().vt_quad_plane_offset())
+
+
 def build_quads(nodes, prim_indices):
     """Host-only: binary hierarchy -> dict(quads, leaf_order, root_leaf_count, max_stack) of the 4-wide layout."""
     L = lib()
@@ -212,6 +228,12 @@ class Accel:
                 self.L.vt_accel_populate_with_bvh(self.h, C.cast(scene.ptr(), _vp), nodes.ctypes.data, len(nodes), prims.ctypes.data),
                 "vt_accel_populate_with_bvh",
             )
+        return self
+
+    def refit(self, scene):
+        """accel:Rebuild for moved geometry of unchanged topology: keep the hierarchy, refit its boxes, re-upload."""
+        self.scene = scene
+        _check(self.L.vt_accel_refit(self.h, C.cast(scene.ptr(), _vp)), "vt_accel_refit")
         return self
 
     def get_bvh(self):

@@ -2,6 +2,7 @@
 //
 // Host code stays C++ (as in the reference); the kernels are reached only from here.  There is
 // NO CPU fallback: without a CUDA device vt_accel_create fails and every later call errors out.
+#include <limits>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -361,8 +362,22 @@ void AccelStruct::Upload(const vt_scene &scene) {
     const uint32_t n_inner = layout == VT_LAYOUT_QUAD ? (uint32_t)quad.quads.size() : (uint32_t)flat.pairs.size();
 
     // leaf-order geometry records + UVs; original-order attribute records
-    std::vector<VtTriRec> recs(n);
-    std::vector<float> uv(n * 6);
+    // quad layout: one extra all-NaN record behind the last triangle, the target of empty child slots (vt_device.h)
+    const bool sentinel = VT_EMPTY_SENTINEL && layout == VT_LAYOUT_QUAD;
+    std::vector<VtTriRec> recs(n + (sentinel ? 1 : 0));
+    std::vector<float> uv((n + (sentinel ? 1 : 0)) * 6);
+    if (sentinel) {
+        VtTriRec &r = recs[n];
+        const float nan = std::numeric_limits<float>::quiet_NaN();
+        for (int k = 0; k < 3; k++) r.p0[k] = r.e1[k] = r.e2[k] = r.n[k] = nan;  // every accept test is NaN-rejecting (Primitives.h:184-189)
+        r.matflags = 0;
+        r.orig = VT_MISS;
+        r.pad[0] = r.pad[1] = 0;
+        const uint32_t ref = (1u << 28) | (uint32_t)n;
+        for (VtQuad &q : quad.quads)
+            for (int i = 0; i < 4; i++)
+                if (q.ref[i] == 0xFFFFFFFFu) q.ref[i] = ref;
+    }
     std::vector<VtTriAttr> attrs(n);
     uint32_t any_alpha = 0;
 #pragma omp parallel for reduction(| : any_alpha)
@@ -471,7 +486,7 @@ void AccelStruct::Upload(const vt_scene &scene) {
     if (layout == VT_LAYOUT_QUAD) D.quads.upload(quad.quads.data(), quad.quads.size());
     else if (layout == VT_LAYOUT_COMPACT) D.cpairs.upload(cpairs.data(), cpairs.size());
     else D.pairs.upload(flat.pairs.data(), flat.pairs.size());
-    D.tris.upload(recs.data(), n);
+    D.tris.upload(recs.data(), recs.size());
     D.tri_uv.upload(uv.data(), uv.size());
     D.attrs.upload(attrs.data(), n);
     D.mats.upload(dm.data(), dm.size());
@@ -497,6 +512,7 @@ void AccelStruct::Upload(const vt_scene &scene) {
     V.has_alphatest = any_alpha ? 1u : 0u;
     V.fallback_tex = scene.n_textures;
     V.magic = 0x4B000000u;
+    V.magic_h = 0x64646464u;
 
     int blocks = 0;
     VT_CUDA(vt_traverse_occupancy(&blocks, (size_t)smem_pairs * sizeof(VtPair), layout));
@@ -518,6 +534,15 @@ void AccelStruct::PopulateWithBvh(const vt_scene &scene, const vt_node *nodes, u
     if (!nodes || !prim_indices || node_count == 0) throw std::runtime_error("populate_with_bvh: null hierarchy");
     mAccel.nodes.assign(nodes, nodes + node_count);
     mAccel.prim_indices.assign(prim_indices, prim_indices + scene.n_tris);
+    Upload(scene);
+}
+
+void AccelStruct::Refit(const vt_scene &scene) {
+    if (!mAccelBuilt) throw std::runtime_error("refit: nothing built yet (use Populate)");
+    if (scene.n_tris != mAccel.prim_indices.size()) throw std::runtime_error("refit: triangle count changed (use Populate to rebuild)");
+    Ingest(scene);  // clears mAccelBuilt; mAccel keeps the structure
+    std::string err;
+    if (!refit_bvh(mTriangles, mAccel, err)) throw std::runtime_error(err);
     Upload(scene);
 }
 
@@ -973,6 +998,33 @@ int vt_accel_populate_with_bvh(vt_accel *a, const vt_scene *scene, const vt_node
     VT_CATCH(1)
 }
 
+int vt_accel_refit(vt_accel *a, const vt_scene *scene) {
+    VT_TRY
+    if (!a || !scene) throw std::runtime_error("null argument");
+    a->impl.Refit(*scene);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_refit_bvh(const vt_scene *scene, vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices) {
+    VT_TRY
+    if (!scene || !nodes || !prim_indices) throw std::runtime_error("null argument");
+    std::vector<vt::Triangle> tris(scene->n_tris);
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)scene->n_tris; i++) {
+        const vt_tri_in &in = scene->tris[i];
+        tris[i] = vt::Triangle(in.p[0], in.p[1], in.p[2], in.material, in.uvs, in.one_sided != 0);
+    }
+    vt::HostBvh bvh;
+    bvh.nodes.assign(nodes, nodes + node_count);
+    bvh.prim_indices.assign(prim_indices, prim_indices + scene->n_tris);
+    std::string err;
+    if (!vt::refit_bvh(tris, bvh, err)) throw std::runtime_error(err);
+    std::memcpy(nodes, bvh.nodes.data(), node_count * sizeof(vt_node));
+    return 0;
+    VT_CATCH(1)
+}
+
 int vt_accel_get_bvh(const vt_accel *a, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices, uint64_t *n_tris) {
     VT_TRY
     if (!a) throw std::runtime_error("null argument");
@@ -1179,6 +1231,8 @@ int vt_flatten_bvh(const vt_node *nodes, uint64_t node_count, const uint64_t *pr
     return 0;
     VT_CATCH(1)
 }
+
+uint32_t vt_quad_plane_offset(void) { return (uint32_t)VT_QUAD_OFFSET; }
 
 int vt_build_quads(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris, void *quads_out,
                    uint64_t *n_quads, uint32_t *leaf_order_out, uint32_t *root_leaf_count, uint32_t *max_stack) {

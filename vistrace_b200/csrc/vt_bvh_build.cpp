@@ -247,6 +247,82 @@ void build_bvh(const std::vector<Triangle> &tris, HostBvh &out, int max_leaf, fl
     for (size_t i = 0; i < n; i++) out.prim_indices[i] = idx[i];
 }
 
+// ------------------------------------------------------------------------------------ refit
+// bvh::HierarchyRefitter::refit (libs/bvh/include/bvh/hierarchy_refitter.hpp:20-31) for moved geometry of unchanged
+// topology — what `accel:Rebuild` of moving props needs instead of a full build.  Leaf boxes are
+// recomputed from Triangle::bounding_box (source/objects/Primitives.h:107-113) of their primitives, the way the library's
+// refit test updates leaves (libs/bvh/test/refit_bvh.cpp:79-89), in parallel; inner boxes are the union of their two
+// children, children first.  The reference library walks up from every leaf with per-node arrival flags
+// (bottom_up_algorithm.hpp:52-80); min/max are exact, so this level-free reverse pre-order pass gives the same boxes.
+bool refit_bvh(const std::vector<Triangle> &tris, HostBvh &bvh, std::string &err) {
+    const size_t node_count = bvh.nodes.size();
+    if (node_count == 0) return true;
+    if (bvh.prim_indices.size() != tris.size()) {
+        err = "refit: triangle count differs from the hierarchy's";
+        return false;
+    }
+    std::vector<uint32_t> order;
+    order.reserve(node_count);
+    std::vector<uint32_t> stack{0u};
+    while (!stack.empty()) {  // pre-order: parents before children
+        const uint32_t i = stack.back();
+        stack.pop_back();
+        order.push_back(i);
+        if (order.size() > node_count) {
+            err = "refit: hierarchy is not a tree";
+            return false;
+        }
+        const vt_node &nd = bvh.nodes[i];
+        if (nd.prim_count == 0) {
+            if (nd.first == 0 || (size_t)nd.first + 1 >= node_count) {
+                err = "refit: malformed hierarchy";
+                return false;
+            }
+            stack.push_back(nd.first);
+            stack.push_back(nd.first + 1);
+        } else if ((size_t)nd.first + nd.prim_count > tris.size()) {
+            err = "refit: leaf addresses primitives past the end of prim_indices";
+            return false;
+        }
+    }
+    bool bad = false;
+#pragma omp parallel for schedule(static) reduction(|| : bad)
+    for (int64_t k = 0; k < (int64_t)order.size(); k++) {
+        vt_node &nd = bvh.nodes[order[k]];
+        if (nd.prim_count == 0) continue;
+        Box b;
+        b.reset();
+        for (uint32_t t = 0; t < nd.prim_count; t++) {
+            const uint64_t p = bvh.prim_indices[nd.first + t];
+            if (p >= tris.size()) {
+                bad = true;
+                break;
+            }
+            const Triangle &tr = tris[p];
+            float v[3][3];
+            for (int a = 0; a < 3; a++) v[0][a] = tr.p0[a], v[1][a] = tr.p0[a] - tr.e1[a], v[2][a] = tr.p0[a] + tr.e2[a];
+            b.grow_pt(v[0]);
+            b.grow_pt(v[1]);
+            b.grow_pt(v[2]);
+        }
+        set_bounds(nd, b);
+    }
+    if (bad) {
+        err = "refit: primitive index out of range";
+        return false;
+    }
+    for (size_t k = order.size(); k-- > 0;) {  // children before parents
+        vt_node &nd = bvh.nodes[order[k]];
+        if (nd.prim_count != 0) continue;
+        const vt_node &l = bvh.nodes[nd.first], &r = bvh.nodes[nd.first + 1];
+        for (int a = 0; a < 3; a++) {
+            nd.bounds[2 * a] = std::min(l.bounds[2 * a], r.bounds[2 * a]);
+            nd.bounds[2 * a + 1] = std::max(l.bounds[2 * a + 1], r.bounds[2 * a + 1]);
+        }
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------------------------ flatten
 // bvh::Bvh<float> form -> VtPair array + leaf-order triangle permutation.
 // Pair order: breadth-first for the first `bfs_pairs` pairs (the part the traversal kernel stages
@@ -553,7 +629,7 @@ struct QuadBuilder {
             if (ok && !choose_grid(lo, hi, E, k)) fail("quad layout: coordinates out of float grid range");
             if (!ok) break;
             const double s = std::ldexp(1.0, E);
-            q.origin_adj[a] = (float)((double)(k - 8388608) * s);
+            q.origin_adj[a] = (float)((double)(k - VT_QUAD_OFFSET) * s);
             q.scale[a] = (float)s;
             for (int i = 0; i < 4; i++) {
                 if (i < nk) {

@@ -19,6 +19,18 @@
 #define VT_TRI_FLAG_CULL 1u       // oneSided && !(mat.flags & nocull)   (Primitives.h:174)
 #define VT_TRI_FLAG_ALPHATEST 2u  // mat.flags & alphatest               (Primitives.h:195)
 #define VT_LEAF_BIT 0x80000000u
+// Quad layout: empty child slots reference a one-triangle leaf whose record (slot n_tris, behind the last real
+// triangle) is all NaN and can never be hit, instead of carrying a "slot in use" test through every node step.
+#ifndef VT_EMPTY_SENTINEL
+#define VT_EMPTY_SENTINEL 1
+#endif
+// Quad layout: the kernel forms the float OFFSET + q from a quantised byte q and decodes a plane as
+// fmaf(OFFSET + q, 2^E, origin_adj) with origin_adj = (k - OFFSET) * 2^E.  OFFSET = 2^23 when the float is built by
+// OR-ing q into the mantissa of 0x4B000000, 1024 when it comes from the fp16 0x6400 | q (VT_DECODE_HALF, vt_traverse.cu).
+#ifndef VT_DECODE_HALF
+#define VT_DECODE_HALF 1
+#endif
+#define VT_QUAD_OFFSET (VT_DECODE_HALF ? 1024 : 8388608)
 
 // One child inside a pair: bounds in bvh order {minx,maxx,miny,maxy,minz,maxz}; count != 0 marks a
 // leaf.  `first` = pair index of the child's own children (inner) or first slot in `tris` (leaf).
@@ -133,4 +145,5 @@ struct VtSceneView {
     uint32_t has_alphatest;    // any triangle carries VT_TRI_FLAG_ALPHATEST
     uint32_t fallback_tex;     // index of the 1x1 white stand-in for a null baseTexture
     uint32_t magic;            // 0x4B000000 (2^23 as float bits), a constant-bank operand of the compact decode
+    uint32_t magic_h;          // 0x64646464 (fp16 1024 = 0x6400): the half2 decode of the quad planes (VT_DECODE_HALF)
 };

@@ -48,6 +48,8 @@ struct FlatBvh {
 };
 
 void build_bvh(const std::vector<Triangle> &tris, HostBvh &out, int max_leaf, float trav_cost);
+// bvh::HierarchyRefitter over moved geometry of unchanged topology (hierarchy_refitter.hpp:20-31): node boxes only.
+bool refit_bvh(const std::vector<Triangle> &tris, HostBvh &bvh, std::string &err);
 bool flatten_bvh(const HostBvh &bvh, uint64_t n_tris, uint32_t bfs_pairs, FlatBvh &out, std::string &err);
 // bvh::Bvh<float> form -> 4-wide quantised nodes (vt_device.h: VtQuad) in depth-first order + the leaf-order
 // permutation of the triangles.  False (with a reason) when the tree cannot be held: a leaf of more than 15
@@ -124,6 +126,11 @@ public:
     void Populate(const vt_scene &scene);
     // Same, with a hierarchy built by the caller (e.g. the reference's PLOC + LeafCollapser).
     void PopulateWithBvh(const vt_scene &scene, const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices);
+
+    // `accel:Rebuild` for moved geometry of unchanged topology (same triangle count and order, e.g. props that moved):
+    // keeps the hierarchy's structure and refits its boxes bottom-up (bvh::HierarchyRefitter, hierarchy_refitter.hpp:20-31)
+    // instead of rebuilding, then re-derives the resident layout.  Throws if nothing was built or the count differs.
+    void Refit(const vt_scene &scene);
 
     // Batched Traverse (the entry the north star adds behind the same object).
     void TraverseBatch(const vt_ray *rays, uint64_t n, vt_hit *hits, vt_attr *attrs, const float *cones, uint32_t flags,

@@ -24,6 +24,18 @@
 // 64-entry traversal stack lives in local memory (lane-interleaved, L1-resident).
 #include "vt_kernels.h"
 #include "vt_math.cuh"
+#include <cuda_fp16.h>
+
+// Build-time knobs of the ALU-pipe diet (A/B builds: make EXTRA=-DVT_...=0); see the notes at slab_quad.
+#ifndef VT_SCHED2
+#define VT_SCHED2 1
+#endif
+#ifndef VT_TRI_ADDR_WIDE
+#define VT_TRI_ADDR_WIDE 1
+#endif
+#ifndef VT_STACK_DIST
+#define VT_STACK_DIST 0  // measured: -7 % node visits / -22 % triangle tests on primary rays (+3 %), but -5.6 % on the bounce wave
+#endif
 
 namespace {
 
@@ -76,8 +88,16 @@ VT_DEV float safe_inverse(float d) {
 template <bool ALPHA>
 VT_DEV bool intersect_triangle(const VtSceneView &S, uint32_t slot, RayState &r) {
     float4 q0, q1, q2, q3;
+#if VT_TRI_ADDR_WIDE
+    // one IMAD.WIDE (FMA pipe) instead of the shift/mask/add-with-carry chain the compiler derives from the tagged reference
+    uint64_t rec;
+    asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(rec) : "r"(slot), "l"(S.tris));
+    ldg256_tri(reinterpret_cast<const char *>(rec), q0, q1);
+    ldg256_tri(reinterpret_cast<const char *>(rec) + 32, q2, q3);
+#else
     ldg256_tri(S.tris + slot, q0, q1);
     ldg256_tri(reinterpret_cast<const char *>(S.tris + slot) + 32, q2, q3);
+#endif
     const V3 p0 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
     const V3 n = mk3(q2.y, q2.z, q2.w);  // cross(e1, e2) as stored by the Triangle ctor (Primitives.h:93)
     const uint32_t matflags = __float_as_uint(q3.x);
@@ -243,6 +263,22 @@ VT_DEV void slab_cpair(const VtCPair *cpairs, uint32_t cur, uint32_t magic, cons
 #ifndef VT_KEY_SLOT
 #define VT_KEY_SLOT 0
 #endif
+// ALU-pipe diet (profiles/r1_k1_alu_diet.md: the half-rate ALU pipe — PRMT/SEL/ISETP/FMNMX/VIMNMX — is the busiest unit
+// of this kernel, the FMA pipes idle at 20 %):
+//   VT_EMPTY_SENTINEL  empty quad slots reference an all-NaN triangle record behind the last real one (vt_accel.cu), so
+//                      the step needs no per-child "slot in use" test: a false positive costs one rejected triangle test.
+//   VT_SORT_CE         compare-exchanges of the child ordering network: 5 = full sort, 4 = nearest and farthest exact,
+//                      the middle two in network order, 3 = nearest exact only.  Any order is correct; order only prunes.
+//   VT_DECODE_HALF     planes are decoded two at a time: one PRMT builds the half2 {1024 + q_a, 1024 + q_b} (bytes q, 0x64),
+//                      two HADD2.F32 (FMA pipe) widen it — 12 PRMT + 24 conversions instead of 24 PRMT per step.  The host
+//                      then stores origin_adj = (k - 1024) * 2^E (vt_device.h).  Measured: IMAD.HI is quarter rate on
+//                      B200 (tools/ubench/pipes.cu), so the byte-3 decode through IMAD.HI was slower and is gone.
+#ifndef VT_SORT_CE
+#define VT_SORT_CE 5
+#endif
+#if VT_KEY_SLOT && VT_STACK_DIST
+#error "VT_KEY_SLOT alters the low key bits; the stack's distance test (VT_STACK_DIST) needs exact entry distances"
+#endif
 #if VT_KEY_SLOT
 #define VT_QUAD_KEY(en, i) (int)((__float_as_uint(en) & ~3u) | (unsigned)(i))
 #else
@@ -257,6 +293,13 @@ VT_DEV void slab_cpair(const VtCPair *cpairs, uint32_t cur, uint32_t magic, cons
 //             plane exactly, hence the real value under the rounding is plane*inv + so minus a non-negative slack
 //             (entry) or plus one (exit); rounding is monotone, so entry' <= the reference's entry and exit' >= its exit.
 //             A warp holding a ray outside that |inv| range (|d| > 2^60, NaN) takes the TWO_FMA form.
+#if VT_DECODE_HALF
+// {1024 + byte a, 1024 + byte b} of q as two floats: PRMT interleaves the bytes with 0x64 (fp16 1024 = 0x6400, ulp 1)
+VT_DEV float2 decode_half_pair(uint32_t q, uint32_t magic_h, uint32_t sel) {
+    const uint32_t h = __byte_perm(q, magic_h, sel);
+    return __half22float2(*reinterpret_cast<const __half2 *>(&h));
+}
+#endif
 template <bool TWO_FMA>
 VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const RayState &ray, int (&k)[4], uint32_t (&r)[4]) {
     uint4 a0, a1, b0, b1;
@@ -271,7 +314,18 @@ VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const R
     const uint32_t ny = oy ? b0.y : b0.x, fy = oy ? b0.x : b0.y;
     const uint32_t nz = oz ? b0.w : b0.z, fz = oz ? b0.z : b0.w;
     r[0] = b1.x, r[1] = b1.y, r[2] = b1.z, r[3] = b1.w;
+#if VT_DECODE_HALF
+    // `magic` is 0x64646464 here; children 0,1 from selector 0x4140, children 2,3 from 0x4342
+    const float2 nx_a = decode_half_pair(nx, magic, 0x4140u), nx_b = decode_half_pair(nx, magic, 0x4342u);
+    const float2 ny_a = decode_half_pair(ny, magic, 0x4140u), ny_b = decode_half_pair(ny, magic, 0x4342u);
+    const float2 nz_a = decode_half_pair(nz, magic, 0x4140u), nz_b = decode_half_pair(nz, magic, 0x4342u);
+    const float2 fx_a = decode_half_pair(fx, magic, 0x4140u), fx_b = decode_half_pair(fx, magic, 0x4342u);
+    const float2 fy_a = decode_half_pair(fy, magic, 0x4140u), fy_b = decode_half_pair(fy, magic, 0x4342u);
+    const float2 fz_a = decode_half_pair(fz, magic, 0x4140u), fz_b = decode_half_pair(fz, magic, 0x4342u);
+#define VT_QF(q, sel) ((sel) == 0x7650u ? q##_a.x : (sel) == 0x7651u ? q##_a.y : (sel) == 0x7652u ? q##_b.x : q##_b.y)
+#else
 #define VT_QF(q, sel) __uint_as_float(__byte_perm(q, magic, sel))
+#endif
 #define VT_PLANE(q, sel, s, a) fmaf(VT_QF(q, sel), s, a)
     const float six = sx * ray.inv.x, siy = sy * ray.inv.y, siz = sz * ray.inv.z;
     const float alx = __fmaf_rd(ax, ray.inv.x, ray.so.x), aly = __fmaf_rd(ay, ray.inv.y, ray.so.y), alz = __fmaf_rd(az, ray.inv.z, ray.so.z);
@@ -296,8 +350,9 @@ VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const R
         }                                                                                  \
         const float en = fmaxf(e0, fmaxf(e1, fmaxf(e2, ray.tmin)));                        \
         const float ex = fminf(x0, fminf(x1, fminf(x2, ray.tmax)));                        \
-        /* an empty slot's inverted box can look hit after rounding when the node is tiny and far: test the ref too */ \
-        const bool hit = r[i] != VT_REF_DONE && en <= ex;                                  \
+        /* an empty slot's inverted box can look hit after rounding when the node is tiny and far: either test the   \
+           ref too, or let the slot reference the all-NaN sentinel triangle (VT_EMPTY_SENTINEL) */                     \
+        const bool hit = (VT_EMPTY_SENTINEL || r[i] != VT_REF_DONE) && en <= ex;           \
         /* en >= tmin >= 0: its bit pattern orders like the value (-0.0 sorts first) */    \
         k[i] = hit ? VT_QUAD_KEY(en, i) : 0x7FFFFFFF;                                      \
     }
@@ -317,7 +372,13 @@ VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const R
         r[a] = r[b];                      \
         r[b] = tr;                        \
     }
-    VT_CE(0, 1) VT_CE(2, 3) VT_CE(0, 2) VT_CE(1, 3) VT_CE(1, 2)
+    VT_CE(0, 1) VT_CE(2, 3) VT_CE(0, 2)
+#if VT_SORT_CE >= 4
+    VT_CE(1, 3)
+#endif
+#if VT_SORT_CE >= 5
+    VT_CE(1, 2)
+#endif
 #undef VT_CE
 }
 
@@ -335,6 +396,38 @@ VT_DEV uint32_t stack_load(uint32_t a) {
     uint32_t v;
     asm volatile("ld.local.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
+}
+
+// Stack entries with the entry distance of the pushed child (VT_STACK_DIST, closest hit only): a pop discards every
+// entry whose box starts beyond the CURRENT tmax — the ray found something nearer since the push — instead of fetching
+// the node (or testing the whole leaf run) just to see every child fail.  The reference's traverser does not carry
+// distances (single_ray_traverser.hpp:109-121) and re-tests such nodes; the result is the same: a discarded box cannot
+// hold a candidate with t <= tmax, equal t included, because its conservative entry is <= the t of anything inside.
+VT_DEV void stack_store2(uint32_t a, uint32_t ref, uint32_t key) {
+    asm volatile("st.local.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(ref), "r"(key) : "memory");
+}
+VT_DEV void stack_load2(uint32_t a, uint32_t &ref, uint32_t &key) {
+    asm volatile("ld.local.v2.u32 {%0, %1}, [%2];" : "=r"(ref), "=r"(key) : "r"(a) : "memory");
+}
+template <bool DIST>
+VT_DEV void stack_push(uint32_t &sp, uint32_t ref, uint32_t key) {
+    if (DIST) stack_store2(sp, ref, key), sp += 8u;
+    else stack_store(sp, ref), sp += 4u;
+}
+// next reference to visit, or VT_REF_DONE when the stack is empty
+template <bool DIST>
+VT_DEV uint32_t stack_pop(uint32_t &sp, uint32_t stack, float tmax) {
+    if constexpr (!DIST) {
+        if (sp == stack) return 0xFFFFFFFFu;
+        return stack_load(sp -= 4u);
+    } else {
+        while (sp != stack) {
+            uint32_t ref, key;
+            stack_load2(sp -= 8u, ref, key);
+            if (__uint_as_float(key) <= tmax) return ref;  // keys are entry distances >= tmin >= 0 (or -0.0)
+        }
+        return 0xFFFFFFFFu;
+    }
 }
 
 VT_DEV void init_ray(const vt_ray &in, RayState &r) {
@@ -530,7 +623,8 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
     const unsigned lt_mask = (1u << lane) - 1u;
     // the layouts served by this kernel validate the worst-case stack depth on the host (<= VT_STACK_SIZE), so
     // the stack is a bare pointer: push = store + increment, pop = decrement + load
-    uint32_t stack_mem[VT_STACK_SIZE];
+    constexpr bool DIST = VT_STACK_DIST && !ANY_HIT;  // any-hit rays never shrink tmax before they end
+    uint64_t stack_mem[DIST ? VT_STACK_SIZE : VT_STACK_SIZE / 2];
     const uint32_t stack = local_addr(stack_mem);
     uint32_t sp = stack;         // byte address of the next free entry
     uint32_t cur = VT_REF_DONE;  // VT_REF_DONE: nothing left to visit
@@ -539,7 +633,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
     unsigned long long ray_idx = 0;
     RayState r;
     unsigned long long n_invalid = 0, n_steps = 0, n_tests = 0;
-    const uint32_t magic = S.magic;
+    const uint32_t magic = (QUAD && VT_DECODE_HALF) ? S.magic_h : S.magic;
     bool warp_wild = false;  // warp-uniform: some lane holds a ray the one-fma plane form is not proven for (slab_quad)
 
     for (;;) {
@@ -588,11 +682,22 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
         const int keep = exhausted ? 0 : refill_threshold;
 
         for (;;) {
+#if VT_SCHED2
+            // one compare per class: inner references are < 2^28, VT_REF_DONE is the only value that is neither
+            const bool has = cur != VT_REF_DONE;
+            const bool is_node = cur < (1u << VT_REF_SHIFT);
+            const bool is_leaf = has && !is_node;
+            const unsigned want_node = __ballot_sync(0xffffffffu, is_node);
+            const unsigned want_any = __ballot_sync(0xffffffffu, has);
+            const unsigned want_tri = want_any & ~want_node;
+            if (__popc(want_any) <= keep) break;
+#else
             const bool has = cur != VT_REF_DONE;
             const bool is_leaf = has && (cur >> VT_REF_SHIFT) != 0;
             const unsigned want_tri = __ballot_sync(0xffffffffu, is_leaf);
             const unsigned want_node = __ballot_sync(0xffffffffu, has && !is_leaf);
             if (__popc(want_tri | want_node) <= keep) break;
+#endif
             if (want_tri && (want_node == 0 || __popc(want_tri) >= tri_threshold)) {
                 if (is_leaf) {
                     // the whole leaf run in one round, in order (tmax shrinks between candidates exactly as in
@@ -609,10 +714,8 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     if (ANY_HIT && any) {
                         cur = VT_REF_DONE;
                         sp = stack;
-                    } else if (sp != stack) {
-                        cur = stack_load(sp -= 4u);
                     } else {
-                        cur = VT_REF_DONE;
+                        cur = stack_pop<DIST>(sp, stack, r.tmax);
                     }
 #else
                     if (STATS) n_tests++;
@@ -621,11 +724,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                         cur = VT_REF_DONE;
                         sp = stack;
                     } else if ((cur >> VT_REF_SHIFT) == 1u) {  // run finished: pop
-                        if (sp != stack) {
-                            cur = stack_load(sp -= 4u);
-                        } else {
-                            cur = VT_REF_DONE;
-                        }
+                        cur = stack_pop<DIST>(sp, stack, r.tmax);
                     } else {
                         cur -= VT_REF_MASK;  // count - 1, slot + 1
                     }
@@ -639,19 +738,17 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     if (warp_wild) slab_quad<true>(S.quads, cur, magic, r, k, cr);
                     else slab_quad<false>(S.quads, cur, magic, r, k, cr);
                     // farthest first, so the nearest pending child is popped first
-                    if (k[3] != 0x7FFFFFFF) stack_store(sp, cr[3]), sp += 4u;
-                    if (k[2] != 0x7FFFFFFF) stack_store(sp, cr[2]), sp += 4u;
+                    if (k[3] != 0x7FFFFFFF) stack_push<DIST>(sp, cr[3], (uint32_t)k[3]);
+                    if (k[2] != 0x7FFFFFFF) stack_push<DIST>(sp, cr[2], (uint32_t)k[2]);
                     if (k[1] != 0x7FFFFFFF) {
-                        stack_store(sp, cr[1]), sp += 4u;
+                        stack_push<DIST>(sp, cr[1], (uint32_t)k[1]);
                         if (VT_PREFETCH_FAR) vt_prefetch_ref(S, cr[1], true);  // the next one to be popped
                     }
                     if (k[0] != 0x7FFFFFFF) {
                         cur = cr[0];
                         if (VT_PREFETCH_LEAF && (cur >> VT_REF_SHIFT)) vt_prefetch(S.tris + (cur & VT_REF_MASK));
-                    } else if (sp != stack) {
-                        cur = stack_load(sp -= 4u);
                     } else {
-                        cur = VT_REF_DONE;
+                        cur = stack_pop<DIST>(sp, stack, r.tmax);
                     }
                     continue;
                 }
@@ -662,13 +759,11 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                 const bool take_r = hit_r && (!hit_l || le > re);  // near child first; ties keep the left child first
                 const uint32_t next = take_r ? rref : lref;
                 const uint32_t far_ = take_r ? lref : rref;
-                if (hit_l && hit_r) stack_store(sp, far_), sp += 4u;
+                if (hit_l && hit_r) stack_push<DIST>(sp, far_, __float_as_uint(take_r ? le : re));
                 if (hit_l || hit_r) {
                     cur = next;
-                } else if (sp != stack) {
-                    cur = stack_load(sp -= 4u);
                 } else {
-                    cur = VT_REF_DONE;
+                    cur = stack_pop<DIST>(sp, stack, r.tmax);
                 }
             }
         }
