@@ -526,13 +526,18 @@ def test_ray_queue_generators_and_queued_traversal(vt, layout):
 
 
 @pytest.mark.parametrize("kind", oracle_kinds())
-def test_refit_moved_props(vt, oracle_mod, kind, layout):
-    """accel:Rebuild through vt_accel_refit: props move, the hierarchy keeps its structure, boxes are refitted.  The GPU
-    result on the refitted tree equals the checker's on the SAME refitted tree (its own refit: bvh::HierarchyRefitter for
-    the reference kind) and — up to counted ties — a from-scratch build of the moved scene."""
+@pytest.mark.parametrize("path", ["device", "host"])
+def test_refit_moved_props(vt, oracle_mod, kind, layout, path, monkeypatch):
+    """accel:Rebuild through vt_accel_refit: props move, the hierarchy keeps its structure, boxes are refitted — by K5 on
+    the device for the quad layout (path "device"), on the host otherwise.  The GPU result on the refitted tree equals the
+    checker's on the SAME refitted tree (its own refit: bvh::HierarchyRefitter for the reference kind) and — up to counted
+    ties — a from-scratch build of the moved scene; the device-refitted quads prune like the host-derived ones."""
     from test_host import _moved_props
     from vistrace_b200 import abi, scenes
 
+    if path == "device" and layout != "quad":
+        pytest.skip("K5 refits the quad layout; the other layouts take the host path")
+    monkeypatch.setenv("VT_REFIT_DEVICE", "1" if path == "device" else "0")
     scene = scenes.scene_props(8, 21, 11, 12)
     moved = _moved_props(scene)
     rays = np.concatenate([scenes.pinhole_rays(320, 180, (0, -95, 40), (0, 0, 10)), scenes.random_rays(20000, (-90, -90, -5), (90, 90, 60), seed=12)])
@@ -554,6 +559,16 @@ def test_refit_moved_props(vt, oracle_mod, kind, layout):
     err = attr_max_rel_err(attrs, want["attrs"])
     assert max(err[f] for f in ATTR_FLOAT_FIELDS) <= 1e-5
     assert (hits["prim"] != before["prim"]).sum() + (hits["t"] != before["t"]).sum() > 100  # the props really moved
+    if path == "device":  # second refit on the prepared state (back to the start), then forward again: same records
+        accel.refit(scene)
+        assert same_hits(accel.traverse(rays), before, layout)
+        accel.refit(moved)
+        assert accel.traverse(rays).tobytes() == hits.tobytes()
+        monkeypatch.setenv("VT_REFIT_DEVICE", "0")
+        host = vt.Accel(0, layout=layout).populate(scene).refit(moved)
+        assert same_hits(host.traverse(rays), hits, layout)
+        s_dev, s_host = accel.traverse_stats(rays), host.traverse_stats(rays)
+        assert abs(s_dev[0] - s_host[0]) <= 0.03 * s_host[0], (s_dev, s_host)  # same pruning power: node visits within 3 %
     fresh = vt.Accel(0, layout=layout).populate(moved).traverse(rays)
     rep = compare_hits(hits, fresh)
     # two different trees over the same triangles: same answer but for exact ties / a verified reference leak (same_hits)

@@ -208,6 +208,11 @@ struct DeviceScene {
     std::map<cudaStream_t, WaveScratch> wave_scratch;
     std::mutex wave_mutex;
     DevBuf<unsigned long long> live;
+    // K5 (device refit) state, built on the first refit of a resident quad hierarchy
+    DevBuf<vt_tri_in> refit_in;
+    DevBuf<uint32_t> refit_parent, refit_n_inner, refit_slot_of, refit_arrive, refit_error;
+    DevBuf<float> refit_qbox;  // 6 floats per quad
+    bool refit_ready = false;
     VtSceneView view{};
     VtLaunchConfig cfg;
     std::atomic<uint32_t> next_slot{0};
@@ -232,6 +237,13 @@ struct DeviceScene {
         s_attrs.release();
         s_cones.release();
         live.release();
+        refit_in.release();
+        refit_parent.release();
+        refit_n_inner.release();
+        refit_slot_of.release();
+        refit_arrive.release();
+        refit_error.release();
+        refit_qbox.release();
         for (auto &l : lanes) {
             l.rays.release();
             l.brays.release();
@@ -480,6 +492,8 @@ void AccelStruct::Upload(const vt_scene &scene) {
     const uint8_t white[4] = {255, 255, 255, 255};
     add_texture(dt[scene.n_textures], 1, 1, 1, 0, white, 4);
 
+    D.refit_ready = false;
+    mBvhStale = false;
     D.pairs.release();
     D.cpairs.release();
     D.quads.release();
@@ -537,10 +551,58 @@ void AccelStruct::PopulateWithBvh(const vt_scene &scene, const vt_node *nodes, u
     Upload(scene);
 }
 
+const HostBvh &AccelStruct::Bvh() const {
+    if (mBvhStale) {
+        std::string err;
+        if (!refit_bvh(mTriangles, mAccel, err)) throw std::runtime_error(err);
+        mBvhStale = false;
+    }
+    return mAccel;
+}
+
 void AccelStruct::Refit(const vt_scene &scene) {
     if (!mAccelBuilt) throw std::runtime_error("refit: nothing built yet (use Populate)");
     if (scene.n_tris != mAccel.prim_indices.size()) throw std::runtime_error("refit: triangle count changed (use Populate to rebuild)");
-    Ingest(scene);  // clears mAccelBuilt; mAccel keeps the structure
+    if (scene.n_materials != mMaterials.size() || scene.n_entities != mEntities.size())
+        throw std::runtime_error("refit: material or entity count changed (use Populate to rebuild)");
+    const bool on_device = mLayout == VT_LAYOUT_QUAD && mpDevice->view.n_pairs != 0 && env_int("VT_REFIT_DEVICE", 1) != 0;
+    if (on_device) {
+        // K5: new vertices up, Triangle constructor + bottom-up quad refit on the device (vt_refit.cu); the host copies
+        // (mTriangles now, the bvh::Bvh-form boxes on demand) are brought up to date while the GPU works.
+        VT_CUDA(cudaSetDevice(mDevice));
+        DeviceScene &D = *mpDevice;
+        const VtSceneView &V = D.view;
+        cudaStream_t stream = D.own_stream;
+        D.refit_in.ensure(scene.n_tris);
+        VT_CUDA(cudaMemcpyAsync(D.refit_in.p, scene.tris, scene.n_tris * sizeof(vt_tri_in), cudaMemcpyHostToDevice, stream));
+        if (!D.refit_ready) {
+            D.refit_parent.ensure(V.n_pairs);
+            D.refit_n_inner.ensure(V.n_pairs);
+            D.refit_arrive.ensure(V.n_pairs);
+            D.refit_qbox.ensure((size_t)V.n_pairs * 6);
+            D.refit_slot_of.ensure(V.n_tris);
+            D.refit_error.ensure(1);
+            VT_CUDA(vt_launch_refit_prepare(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_slot_of.p, stream));
+            mLaunches++;
+            D.refit_ready = true;
+        }
+        VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
+        VT_CUDA(vt_launch_refit_tris(V, D.refit_in.p, D.refit_slot_of.p, stream));
+        VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
+        mLaunches += 2;
+        Ingest(scene);  // host copies of the containers (clears mAccelBuilt; mAccel keeps the structure)
+        uint32_t failed = 0;
+        VT_CUDA(cudaMemcpyAsync(&failed, D.refit_error.p, sizeof(failed), cudaMemcpyDeviceToHost, stream));
+        VT_CUDA(cudaStreamSynchronize(stream));
+        if (!failed) {
+            mBvhStale = true;
+            mAccelBuilt = true;
+            return;
+        }
+        // a box left the float grid the quantised layout can hold: re-derive the layout on the host (may fall back to exact)
+    } else {
+        Ingest(scene);
+    }
     std::string err;
     if (!refit_bvh(mTriangles, mAccel, err)) throw std::runtime_error(err);
     Upload(scene);

@@ -105,7 +105,8 @@ class AccelStruct {
     bool mAccelBuilt = false;
     int mWantLayout = VT_LAYOUT_QUAD;  // layout requested for the next Populate (VT_LAYOUT_*)
     int mLayout = VT_LAYOUT_EXACT;     // node layout resident on the device
-    HostBvh mAccel;
+    mutable HostBvh mAccel;
+    mutable bool mBvhStale = false;  // a device-side refit moved the boxes; the host copy is refitted on demand
     std::vector<Triangle> mTriangles;
     std::vector<Entity> mEntities;
     std::vector<Material> mMaterials;
@@ -178,7 +179,7 @@ public:
 
     const Material &GetMaterial(size_t i) const { return mMaterials[i]; }  // AccelStruct.cpp:840-843
     const std::vector<Triangle> &Triangles() const { return mTriangles; }
-    const HostBvh &Bvh() const { return mAccel; }
+    const HostBvh &Bvh() const;  // boxes refreshed lazily after a device-side refit
     bool Built() const { return mAccelBuilt; }
     int Layout() const { return mLayout; }
     void SetLayout(int layout) { mWantLayout = layout; }

@@ -54,3 +54,12 @@ cudaError_t vt_launch_pinhole_rays(const float *cam12, uint32_t width, uint32_t 
 // K4 — fb[i] += weight * albedo_i * (escaped bounce rays of pixel i) / spp, RGBFFF framebuffer.
 cudaError_t vt_launch_accumulate_sky(const VtSceneView &S, const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n,
                                      uint32_t spp, float weight, float *fb, cudaStream_t stream);
+
+// K5 — device-side refit of the resident quad hierarchy (vt_refit.cu).  prepare: once per resident hierarchy
+// (parent / inner-child count per quad, original triangle -> leaf slot).  refit_tris: Triangle constructor over the
+// caller's new vertices into the resident triangle / attribute records.  refit_quads: bottom-up boxes + requantisation;
+// qbox = n_quads x 24 bytes of scratch, *error != 0 afterwards when a box could not be held on the float grid.
+cudaError_t vt_launch_refit_prepare(const VtSceneView &S, uint32_t *parent, uint32_t *n_inner, uint32_t *slot_of, cudaStream_t stream);
+cudaError_t vt_launch_refit_tris(const VtSceneView &S, const vt_tri_in *in, const uint32_t *slot_of, cudaStream_t stream);
+cudaError_t vt_launch_refit_quads(const VtSceneView &S, const uint32_t *parent, const uint32_t *n_inner, uint32_t *arrive, void *qbox,
+                                  unsigned int *error, cudaStream_t stream);

@@ -1,0 +1,216 @@
+// vt_refit.cu — K5: device-side refit of the resident QUAD hierarchy for moved geometry of unchanged topology.
+//
+// What `accel:Rebuild` (source/VisTrace.cpp:798-818) needs when props merely moved: the reference rebuilds from
+// scratch (PopulateAccel); the bvh library it builds with offers bvh::HierarchyRefitter
+// (libs/bvh/include/bvh/hierarchy_refitter.hpp:20-31: leaf boxes from their primitives, inner boxes = union of the
+// children, bottom-up with per-node arrival flags, bottom_up_algorithm.hpp:52-80).  This file is that algorithm on
+// the device, over the 4-wide quantised nodes the traversal kernel reads:
+//
+//   k_refit_prepare   once per resident hierarchy: parent[] and inner-child counts from the quad references,
+//                     slot_of[] (original triangle -> leaf-order slot) from the triangle records.
+//   k_refit_tris      per ORIGINAL triangle: the Triangle constructor + ComputeNormalAndLoD
+//                     (source/objects/Primitives.h:75-102) on the caller's new vertices, written straight into the
+//                     resident leaf-order VtTriRec / tri_uv and original-order VtTriAttr records.
+//   k_refit_quads     bottom-up: a thread starts at every quad whose children are all leaves, computes the exact child
+//                     boxes (Triangle::bounding_box, Primitives.h:107-113, over p0, p0 - e1, p0 + e2), re-derives the
+//                     quad's power-of-two grid and conservative plane bytes exactly as the host's build_quads does
+//                     (vt_bvh_build.cpp: choose_grid), stores the quad's exact union box, and walks up: the LAST
+//                     child to arrive at a parent (atomic arrival counter) processes it.
+//
+// HBM-bound streaming: 152 B in + 264 B out per triangle, 64 B in/out + 24 B per quad.  Arithmetic is IEEE, uncontracted
+// (--fmad=false), so p0/e1/e2/n/nNorm equal the host constructor's bit for bit; `lod` goes through log2f, whose device
+// and glibc implementations may differ in the last place (it only selects a texture LOD; parity bar 1e-5 relative).
+#include <cfloat>
+
+#include "vt_kernels.h"
+
+namespace {
+
+#define VT_REF_SHIFT 28
+#define VT_REF_MASK 0x0FFFFFFFu
+
+__global__ void k_refit_prepare(const VtQuad *__restrict__ quads, uint32_t n_quads, const VtTriRec *__restrict__ tris, uint32_t n_tris,
+                                uint32_t *__restrict__ parent, uint32_t *__restrict__ n_inner, uint32_t *__restrict__ slot_of) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_quads) {
+        uint32_t inner = 0;
+        for (int c = 0; c < 4; c++) {
+            const uint32_t ref = quads[i].ref[c];
+            if (ref != 0xFFFFFFFFu && (ref >> VT_REF_SHIFT) == 0) {
+                parent[ref] = i;
+                inner++;
+            }
+        }
+        n_inner[i] = inner;
+        if (i == 0) parent[0] = 0xFFFFFFFFu;
+    }
+    if (i < n_tris) slot_of[tris[i].orig] = i;
+}
+
+__global__ void k_refit_tris(const vt_tri_in *__restrict__ in, uint32_t n_tris, const uint32_t *__restrict__ slot_of,
+                             const VtDevMaterial *__restrict__ mats, VtTriRec *__restrict__ recs, float *__restrict__ tri_uv,
+                             VtTriAttr *__restrict__ attrs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tris) return;
+    const vt_tri_in t = in[i];
+    float p0[3], e1[3], e2[3], n[3], nn[3];
+    for (int k = 0; k < 3; k++) {
+        p0[k] = t.p[0][k];
+        e1[k] = t.p[0][k] - t.p[1][k];  // e1 = p0 - p1, e2 = p2 - p0 (Primitives.h:82)
+        e2[k] = t.p[2][k] - t.p[0][k];
+    }
+    n[0] = e1[1] * e2[2] - e1[2] * e2[1];  // ComputeNormalAndLoD, Primitives.h:91-102
+    n[1] = e1[2] * e2[0] - e1[0] * e2[2];
+    n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+    const float uv10x = t.uvs[1][0] - t.uvs[0][0], uv10y = t.uvs[1][1] - t.uvs[0][1];
+    const float uv20x = t.uvs[2][0] - t.uvs[0][0], uv20y = t.uvs[2][1] - t.uvs[0][1];
+    const float area = fabsf(uv10x * uv20y - uv20x * uv10y);
+    float d = n[0] * n[0];
+    d += n[1] * n[1];
+    d += n[2] * n[2];
+    const float len = sqrtf(d);
+    const float lod = 0.5f * log2f(area / len);
+    for (int k = 0; k < 3; k++) nn[k] = n[k] / len;
+
+    const uint32_t s = slot_of[i];
+    VtTriRec r;
+    for (int k = 0; k < 3; k++) r.p0[k] = p0[k], r.e1[k] = e1[k], r.e2[k] = e2[k], r.n[k] = n[k];
+    const uint32_t mflags = mats[t.material].flags;
+    uint32_t fl = 0;
+    if (t.one_sided && (mflags & VT_MATFLAG_NOCULL) == 0) fl |= VT_TRI_FLAG_CULL;  // Primitives.h:174
+    if (mflags & VT_MATFLAG_ALPHATEST) fl |= VT_TRI_FLAG_ALPHATEST;               // Primitives.h:195
+    r.matflags = (t.material << 2) | fl;
+    r.orig = i;
+    r.pad[0] = r.pad[1] = 0;
+    recs[s] = r;
+    for (int k = 0; k < 6; k++) tri_uv[(size_t)s * 6 + k] = (&t.uvs[0][0])[k];
+    VtTriAttr a;
+    for (int k = 0; k < 3; k++) a.p0[k] = p0[k], a.e1[k] = e1[k], a.e2[k] = e2[k], a.nNorm[k] = nn[k], a.alphas[k] = t.alphas[k];
+    for (int k = 0; k < 9; k++) (&a.normals[0][0])[k] = (&t.normals[0][0])[k], (&a.tangents[0][0])[k] = (&t.tangents[0][0])[k];
+    for (int k = 0; k < 6; k++) (&a.uvs[0][0])[k] = (&t.uvs[0][0])[k];
+    a.lod = lod;
+    a.material = t.material;
+    a.ent_idx = t.ent_idx;
+    attrs[i] = a;
+}
+
+// choose_grid of vt_bvh_build.cpp: the smallest power-of-two cell 2^E on which [lo, hi] spans <= 255 cells from
+// k = floor(lo / 2^E) with |k| small enough that (k - OFFSET) * 2^E and (k + q) * 2^E are exact floats; |E| <= 60.
+__device__ bool choose_grid_dev(double lo, double hi, int &E, long long &k) {
+    const double kmax = 8388608.0 - 512.0;
+    const double mag = fmax(fabs(lo), fabs(hi));
+    int e = -149;
+    if (hi > lo) e = max(e, (int)ceil(log2((hi - lo) / 255.0)) - 1);
+    if (mag > 0) e = max(e, (int)floor(log2(mag)) - 23);
+    e = max(e, -60);
+    for (; e <= 60; e++) {
+        const double s = ldexp(1.0, e);
+        const double kl = floor(lo / s), kh = ceil(hi / s);
+        if (kh - kl <= 255.0 && fabs(kl) <= kmax && fabs(kh) <= kmax) {
+            E = e;
+            k = (long long)kl;
+            return true;
+        }
+    }
+    return false;
+}
+
+struct Box6 {
+    float lo[3], hi[3];
+};
+
+__global__ void k_refit_quads(VtQuad *quads, uint32_t n_quads, const VtTriRec *__restrict__ tris, uint32_t n_tris,
+                              const uint32_t *__restrict__ parent, const uint32_t *__restrict__ n_inner, uint32_t *arrive,
+                              Box6 *qbox, unsigned int *error) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_quads || n_inner[q] != 0) return;  // start at the quads all of whose children are leaves
+    for (;;) {
+        VtQuad node = quads[q];
+        Box6 cb[4], un;
+        bool used[4];
+        for (int a = 0; a < 3; a++) un.lo[a] = FLT_MAX, un.hi[a] = -FLT_MAX;
+        for (int c = 0; c < 4; c++) {
+            const uint32_t ref = node.ref[c];
+            const uint32_t count = ref >> VT_REF_SHIFT, idx = ref & VT_REF_MASK;
+            used[c] = ref != 0xFFFFFFFFu && !(count != 0 && idx >= n_tris);  // 0xFFFFFFFF or the sentinel leaf: empty slot
+            if (!used[c]) continue;
+            Box6 b;
+            if (count == 0) {
+                // written by the thread that finished that child before it signalled arrival (threadfence + atomic below)
+                const volatile Box6 *src = qbox + idx;
+                for (int a = 0; a < 3; a++) b.lo[a] = src->lo[a], b.hi[a] = src->hi[a];
+            } else {
+                for (int a = 0; a < 3; a++) b.lo[a] = FLT_MAX, b.hi[a] = -FLT_MAX;
+                for (uint32_t t = 0; t < count; t++) {
+                    const VtTriRec &tr = tris[idx + t];
+                    for (int a = 0; a < 3; a++) {
+                        const float v0 = tr.p0[a], v1 = tr.p0[a] - tr.e1[a], v2 = tr.p0[a] + tr.e2[a];
+                        b.lo[a] = fminf(b.lo[a], fminf(v0, fminf(v1, v2)));
+                        b.hi[a] = fmaxf(b.hi[a], fmaxf(v0, fmaxf(v1, v2)));
+                    }
+                }
+            }
+            cb[c] = b;
+            for (int a = 0; a < 3; a++) un.lo[a] = fminf(un.lo[a], b.lo[a]), un.hi[a] = fmaxf(un.hi[a], b.hi[a]);
+        }
+        bool ok = true;
+        for (int a = 0; a < 3; a++) {
+            int E = 0;
+            long long k = 0;
+            if (!(isfinite(un.lo[a]) && isfinite(un.hi[a])) || un.hi[a] < un.lo[a] || !choose_grid_dev(un.lo[a], un.hi[a], E, k)) {
+                ok = false;
+                break;
+            }
+            const double s = ldexp(1.0, E);
+            node.origin_adj[a] = (float)((double)(k - VT_QUAD_OFFSET) * s);
+            node.scale[a] = (float)s;
+            for (int c = 0; c < 4; c++) {
+                if (used[c]) {
+                    node.q[a][0][c] = (uint8_t)((long long)floor((double)cb[c].lo[a] / s) - k);
+                    node.q[a][1][c] = (uint8_t)((long long)ceil((double)cb[c].hi[a] / s) - k);
+                } else {
+                    node.q[a][0][c] = 255;  // empty slot: inverted box
+                    node.q[a][1][c] = 0;
+                }
+            }
+        }
+        if (!ok) {
+            atomicExch(error, 1u);  // non-finite geometry or coordinates out of float grid range: the host re-derives the layout
+            return;
+        }
+        quads[q] = node;
+        qbox[q] = un;
+        const uint32_t p = parent[q];
+        if (p == 0xFFFFFFFFu) return;  // the root
+        __threadfence();               // box and node visible before the arrival is counted
+        if (atomicAdd(&arrive[p], 1u) + 1u < n_inner[p]) return;  // a sibling subtree is still being refitted
+        __threadfence();
+        q = p;
+    }
+}
+
+}  // namespace
+
+cudaError_t vt_launch_refit_prepare(const VtSceneView &S, uint32_t *parent, uint32_t *n_inner, uint32_t *slot_of, cudaStream_t stream) {
+    const uint32_t n = S.n_pairs > S.n_tris ? S.n_pairs : S.n_tris;
+    if (n == 0) return cudaSuccess;
+    k_refit_prepare<<<(n + 255) / 256, 256, 0, stream>>>(S.quads, S.n_pairs, S.tris, S.n_tris, parent, n_inner, slot_of);
+    return cudaGetLastError();
+}
+
+cudaError_t vt_launch_refit_tris(const VtSceneView &S, const vt_tri_in *in, const uint32_t *slot_of, cudaStream_t stream) {
+    if (S.n_tris == 0) return cudaSuccess;
+    k_refit_tris<<<(S.n_tris + 127) / 128, 128, 0, stream>>>(in, S.n_tris, slot_of, S.mats, const_cast<VtTriRec *>(S.tris),
+                                                             const_cast<float *>(S.tri_uv), const_cast<VtTriAttr *>(S.attrs));
+    return cudaGetLastError();
+}
+
+cudaError_t vt_launch_refit_quads(const VtSceneView &S, const uint32_t *parent, const uint32_t *n_inner, uint32_t *arrive, void *qbox,
+                                  unsigned int *error, cudaStream_t stream) {
+    if (S.n_pairs == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(arrive, 0, (size_t)S.n_pairs * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    k_refit_quads<<<(S.n_pairs + 127) / 128, 128, 0, stream>>>(const_cast<VtQuad *>(S.quads), S.n_pairs, S.tris, S.n_tris, parent, n_inner,
+                                                               arrive, static_cast<Box6 *>(qbox), error);
+    return cudaGetLastError();
+}
