@@ -1,6 +1,6 @@
 #!/bin/bash
-# session G: K5 device refit — tests, timing at 6 M triangles, PCIe probe
-O=gpurun_out/sG; mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -x -q -k "refit" > $O/pytest_refit.log 2>&1; echo "pytest rc=$?"; tail -15 $O/pytest_refit.log
-timeout 600 python tools/refit_time.py > $O/refit.log 2>&1; tail -3 $O/refit.log
-timeout 300 python tools/pcie_probe.py > $O/pcie.log 2>&1; head -12 $O/pcie.log
+# session I (2 GPUs): NCCL test + bench at N=2 as the driver launches it
+O=gpurun_out/sI; mkdir -p $O
+nvidia-smi -L > $O/gpus.txt
+timeout 600 python -m pytest tests -m gpu -x -q -k "two_gpu" > $O/pytest_2gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_2gpu.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 3 > $O/bench_n2.json 2> $O/bench_n2.err; echo "bench rc=$?"; cat $O/bench_n2.json; tail -3 $O/bench_n2.err
