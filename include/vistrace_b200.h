@@ -92,6 +92,27 @@ typedef struct vt_texture {
     uint64_t nbytes;
 } vt_texture;
 
+/* VTF file -> the RGBA8888 mip chain of a vt_texture (host only).  Restates libs/VTFParser: header and image-data
+ * location (FileFormat/Parser.cpp:99-155, FileFormat/Structs.h:21-75), DXT1/3/5 decompressed at load
+ * (VTFParser.cpp:26-84, DXTn/DXT1.cpp, DXT3.cpp, DXT5.cpp), the 8-bit-per-channel formats swizzled as ParsePixel
+ * reads them (Parser.cpp:157-298) — every output byte b satisfies b / 255.f == the channel VTFTexture::GetPixel
+ * returns.  Formats that arithmetic cannot express in 8 bits (RGB565, BGR565, BGRX5551, BGRA5551, BGRA4444,
+ * RGBA16161616(F), P8) are rejected: vt_vtf_info.supported = 0 and vt_vtf_decode fails. */
+typedef struct vt_vtf_info {
+    uint32_t width, height; /* mip 0 */
+    uint32_t mip_count;
+    uint32_t flags;         /* VTF TEXTURE_FLAGS: pass on as vt_texture.flags (CLAMPS / CLAMPT) */
+    int32_t format;         /* IMAGE_FORMAT of the file (FileFormat/Enums.h:5-35) */
+    uint32_t frames, faces, depth;
+    uint32_t supported;     /* 1 when vt_vtf_decode can produce the chain */
+    uint32_t pad;
+    uint64_t rgba_bytes;    /* size of the decoded chain of ONE frame / face / z-slice 0, smallest mip first */
+} vt_vtf_info;
+int vt_vtf_read_info(const uint8_t *file, uint64_t size, vt_vtf_info *info);
+/* rgba_out: capacity >= info.rgba_bytes; the chain is in VTF order (smallest mip first), ready for vt_texture.rgba. */
+int vt_vtf_decode(const uint8_t *file, uint64_t size, uint32_t frame, uint32_t face, uint8_t *rgba_out, uint64_t capacity,
+                  vt_vtf_info *info_or_null);
+
 /* Material subset on the path (source/objects/Material.h:74-125).  Texture slots
  * are indices into the texture array, -1 = nullptr.  *_mat are glm::mat2x4 in
  * memory order: [0..3] = column 0 (drives u), [4..7] = column 1 (drives v)

@@ -63,6 +63,8 @@ def _lib(kind):
         "tri_intersect": (i32, [vp, u64, vp, vp]),
         "skin_triangles": (None, [vp, vp, u64, vp, vp, C.c_uint32, vp]),
     }
+    if kind != "port":  # reference only: its VTF parser is not restated in the C port (the product's decoder is checked against it)
+        sig["vtf_pixels"] = (C.c_int64, [vp, u64, C.c_uint32, C.c_uint32, vp, u64])
     ns = type("ns", (), {})()
     for name, (res, args) in sig.items():
         fn = getattr(lib, pre + name)
@@ -195,4 +197,17 @@ def skin_triangles(tris, skin, bones, binds, kind="reference"):
     out = np.zeros((len(tris), 27), np.float32)
     _lib(kind).skin_triangles(tris.ctypes.data, None if skin is None else np.ascontiguousarray(skin, abi.TRI_SKIN).ctypes.data, len(tris),
                               bones.ctypes.data, binds.ctypes.data, len(bones), out.ctypes.data)
+    return out
+
+
+def vtf_pixels(data, n_texels, frame=0, face=0):
+    """Reference VTFTexture over the VTF file bytes `data`: (n_texels, 4) float32 of GetPixel in storage order
+    (smallest mip first), or None when the reference parser rejects the file."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    out = np.zeros((n_texels, 4), np.float32)
+    n = _lib("reference").vtf_pixels(buf.ctypes.data, len(buf), frame, face, out.ctypes.data, n_texels)
+    if n == -1:
+        return None
+    if n != n_texels:
+        raise RuntimeError(f"vtf_pixels: reference reports {n} texels, expected {n_texels}")
     return out

@@ -262,6 +262,27 @@ void vtref_get_bvh(void *h, vt_node *nodes, uint64_t *node_count, uint64_t *prim
         for (size_t i = 0; i < a.mTriangles.size(); i++) prim_indices[i] = a.mAccel.primitive_indices[i];
 }
 
+// Every texel of one frame / face (z slice 0) of a VTF file as the reference's own VTFTexture reports it
+// (libs/VTFParser/VTFParser.cpp: constructor :13-96 incl. DXT decompression, GetPixel :166-205), in VTF storage order
+// (smallest mip first, rows top to bottom).  Returns the number of texels written, -1 when the parser rejects the file,
+// -2 when `capacity` (in texels) is too small.
+int64_t vtref_vtf_pixels(const uint8_t *file, uint64_t size, uint32_t frame, uint32_t face, float *rgba, uint64_t capacity) {
+    VTFTexture tex(file, size);
+    if (!tex.IsValid()) return -1;
+    uint64_t n = 0;
+    for (int m = (int)tex.GetMIPLevels() - 1; m >= 0; m--) {
+        const uint32_t w = tex.GetWidth((uint8_t)m), h = tex.GetHeight((uint8_t)m);
+        for (uint32_t y = 0; y < h; y++)
+            for (uint32_t x = 0; x < w; x++) {
+                if (n >= capacity) return -2;
+                const VTFPixel p = tex.GetPixel((uint16_t)x, (uint16_t)y, 0, (uint8_t)m, (uint16_t)frame, (uint8_t)face);
+                rgba[4 * n + 0] = p.r, rgba[4 * n + 1] = p.g, rgba[4 * n + 2] = p.b, rgba[4 * n + 3] = p.a;
+                n++;
+            }
+    }
+    return (int64_t)n;
+}
+
 // Moved geometry, same topology: rebuild mTriangles from `s` and refit the CURRENT hierarchy with the reference
 // library's own bvh::HierarchyRefitter, leaf update exactly as its test drives it (libs/bvh/test/refit_bvh.cpp:79-89).
 void vtref_refit(void *h, const vt_scene *s) {

@@ -64,10 +64,33 @@ def golden_skin():
     print("skin_small", {k: v.shape for k, v in out.items()})
 
 
+def golden_vtf():
+    """Synthetic VTF files (tests/test_vtf.py: make_vtf) and every texel of them as the reference's VTFTexture reports it."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_vtf import make_vtf
+
+    cases = {"dxt1_low": ("DXT1", 32, 32, 6, {"low": (16, 16)}), "dxt3_odd": ("DXT3", 20, 12, 3, {"seed": 4}),
+             "dxt5_res": ("DXT5", 16, 16, 5, {"minor": 3, "resources": True, "low": (16, 16), "seed": 9}),
+             "dxt1a_tiny": ("DXT1_ONEBITALPHA", 4, 4, 3, {"seed": 6}), "bgr888": ("BGR888", 16, 8, 5, {}),
+             "ia88_v71": ("IA88", 8, 4, 4, {"minor": 1}), "argb8888": ("ARGB8888", 8, 8, 4, {}), "a8": ("A8", 8, 8, 4, {})}
+    out = {}
+    for name, (fmt, w, h, mips, kw) in cases.items():
+        data = make_vtf(fmt, w, h, mips, **kw)
+        n_tex = sum(max(1, w >> m) * max(1, h >> m) for m in range(mips))
+        want = oracle.vtf_pixels(data, n_tex)
+        assert want is not None, name
+        out["file_" + name] = np.frombuffer(data, np.uint8)
+        out["want_" + name] = want
+    np.savez_compressed(os.path.join(HERE, "vtf_small.npz"), **out)
+    print("vtf_small", {k: v.shape for k, v in out.items() if k.startswith("want_")})
+
+
 def main():
     assert oracle.available("reference"), "build oracle/_ref first: make -C oracle ref"
     if sys.argv[1:] == ["skin"]:
         return golden_skin()
+    if sys.argv[1:] == ["vtf"]:
+        return golden_vtf()
     # foliage: alpha test (wrap + clamp textures), two-sided cards, one-sided ground, sky room
     sc = scenes.scene_foliage(n_cards=400, tex_size=32, ground_quads=8, seed=7)
     rays = scenes.pinhole_rays(96, 54, (0, -48, 20), (0, 0, 8))
@@ -90,6 +113,7 @@ def main():
     np.savez(os.path.join(HERE, "kat_node_intersect.npz"), node=node, ray=ray, entry_exit=np.array([entry, exit_], np.float32))
     print("kat node", entry, exit_)
     golden_skin()
+    golden_vtf()
 
 
 if __name__ == "__main__":

@@ -1,6 +1,7 @@
 #!/bin/bash
-# session I (2 GPUs): NCCL test + bench at N=2 as the driver launches it
-O=gpurun_out/sI; mkdir -p $O
-nvidia-smi -L > $O/gpus.txt
-timeout 600 python -m pytest tests -m gpu -x -q -k "two_gpu" > $O/pytest_2gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_2gpu.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 3 > $O/bench_n2.json 2> $O/bench_n2.err; echo "bench rc=$?"; cat $O/bench_n2.json; tail -3 $O/bench_n2.err
+# session L: e2e lanes (streams in flight) x tile size
+O=gpurun_out/sL; mkdir -p $O
+for cfg in "3 524288 65536" "4 524288 65536" "5 524288 65536" "6 524288 65536" "6 262144 32768" "8 262144 65536" "5 393216 131072" "2 524288 65536"; do
+  set -- $cfg
+  echo "== lanes=$1 tile=$2 first=$3"; VT_WAVE_LANES=$1 VT_WAVE_TILE=$2 VT_WAVE_FIRST=$3 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['e2e']['all_hit_records_variant']['ms_per_step'])"
+done

@@ -44,6 +44,8 @@ SYMBOLS = {
     "vt_compact_pairs": (_i32, [_vp, _u64, _vp]),
     "vt_skin_triangles": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32]),
     "vt_quad_plane_offset": (_u32, []),
+    "vt_vtf_read_info": (_i32, [_vp, _u64, _vp]),
+    "vt_vtf_decode": (_i32, [_vp, _u64, _u32, _u32, _vp, _u64, _vp]),
     "vt_build_quads": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_invalid_rays": (_u64, [_vp]),
     "vt_accel_launch_count": (_u64, [_vp]),
@@ -167,6 +169,28 @@ def compact_pairs(pairs):
 
 QUAD = np.dtype([("origin_adj", np.float32, 3), ("scale", np.float32, 3), ("q", np.uint8, (3, 2, 4)), ("ref", np.uint32, 4)])
 assert QUAD.itemsize == 64
+
+
+VTF_INFO = np.dtype([("width", np.uint32), ("height", np.uint32), ("mip_count", np.uint32), ("flags", np.uint32), ("format", np.int32),
+                     ("frames", np.uint32), ("faces", np.uint32), ("depth", np.uint32), ("supported", np.uint32), ("pad", np.uint32),
+                     ("rgba_bytes", np.uint64)])
+
+
+def vtf_info(data):
+    """Header of a VTF file held in `data` (bytes): a VTF_INFO record."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    info = np.zeros(1, VTF_INFO)
+    _check(lib().vt_vtf_read_info(buf.ctypes.data, len(buf), info.ctypes.data), "vt_vtf_read_info")
+    return info[0]
+
+
+def vtf_decode(data, frame=0, face=0):
+    """VTF file -> (width, height, mip_count, flags, rgba uint8 chain, smallest mip first): a SceneData texture tuple."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    info = vtf_info(data)
+    out = np.zeros(int(info["rgba_bytes"]), np.uint8)
+    _check(lib().vt_vtf_decode(buf.ctypes.data, len(buf), frame, face, out.ctypes.data, len(out), None), "vt_vtf_decode")
+    return int(info["width"]), int(info["height"]), int(info["mip_count"]), int(info["flags"]), out
 
 
 def quad_plane_offset():

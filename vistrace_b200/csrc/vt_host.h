@@ -67,6 +67,10 @@ bool compact_pairs(const std::vector<VtPair> &pairs, std::vector<VtCPair> &out, 
 // SkinTriangle over a batch (source/objects/AccelStruct.cpp:66-108): bakes bone * bind * weight into world space.
 void SkinTriangles(vt_tri_in *tris, const vt_tri_skin *skin, uint64_t n, const float *bones, const float *binds, uint32_t n_bones);
 
+// VTF file -> RGBA8888 mip chain (vt_vtf.cpp; libs/VTFParser restated).  Throw std::runtime_error on malformed / unsupported files.
+void VtfInfo(const uint8_t *file, uint64_t size, vt_vtf_info *out);
+void VtfDecode(const uint8_t *file, uint64_t size, uint32_t frame, uint32_t face, uint8_t *rgba, uint64_t capacity, vt_vtf_info *info_out);
+
 struct DeviceScene;  // HBM-resident copy, vt_accel.cu
 
 // Eager TraceResult for one hit (source/objects/TraceResult.h:54-111): the batched path fills
