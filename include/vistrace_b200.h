@@ -92,7 +92,7 @@ typedef struct vt_texture {
     uint64_t nbytes;
 } vt_texture;
 
-/* VTF file -> the RGBA8888 mip chain of a vt_texture (host only).  Restates libs/VTFParser: header and image-data
+/* VTF file -> the RGBA8888 mip chain of a vt_texture; host only.  Restates libs/VTFParser: header and image-data
  * location (FileFormat/Parser.cpp:99-155, FileFormat/Structs.h:21-75), DXT1/3/5 decompressed at load
  * (VTFParser.cpp:26-84, DXTn/DXT1.cpp, DXT3.cpp, DXT5.cpp), the 8-bit-per-channel formats swizzled as ParsePixel
  * reads them (Parser.cpp:157-298) — every output byte b satisfies b / 255.f == the channel VTFTexture::GetPixel
