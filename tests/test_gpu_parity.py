@@ -577,6 +577,26 @@ def test_refit_moved_props(vt, oracle_mod, kind, layout, path, monkeypatch):
         accel.refit(abi.SceneData(moved.tris[:-1], moved.materials, moved.entities))
 
 
+@pytest.mark.parametrize("kind", oracle_kinds())
+def test_alpha_test_through_dxt_compressed_vtf_files(vt, oracle_mod, kind, layout):
+    """The ingestion row end to end: the foliage scene's base textures arrive as DXT5 / DXT1-one-bit-alpha VTF FILES,
+    go through vt_vtf_decode (pinned to the reference's parser in tests/test_vtf.py) and drive the alpha test and the
+    TraceResult albedo/alpha of both the GPU path and the checker."""
+    from test_vtf import make_vtf
+    from vistrace_b200 import abi, scenes
+
+    base = scenes.scene_foliage(n_cards=1500, tex_size=32, ground_quads=8)
+    files = [make_vtf("DXT5", 64, 64, 7, low=(16, 16), seed=21), make_vtf("DXT1_ONEBITALPHA", 32, 32, 6, flags=0x4 | 0x8, seed=22)]
+    texs = [vt.vtf_decode(f) for f in files]
+    assert len(base.textures) == len(texs)
+    scene = abi.SceneData(base.tris, base.materials, base.entities, textures=texs)
+    rays = np.concatenate([scenes.pinhole_rays(320, 180, (0, -48, 20), (0, 0, 8)), scenes.random_rays(15000, (-45, -45, -3), (45, 45, 50), seed=5)])
+    accel, cpu, hits, attrs, want = _check_against(vt, oracle_mod, scene, rays, kind, "product", layout)
+    hit = hits["prim"] != abi.VT_MISS
+    alpha_tested = (scene.materials["flags"][scene.tris["material"][hits["prim"][hit]]] & abi.VT_MATFLAG_ALPHATEST) != 0
+    assert alpha_tested.sum() > 1000 and len(np.unique(attrs["alpha"][hit][alpha_tested])) > 20  # texels really sampled
+
+
 def test_two_gpu_sharded_trace_nccl(vt):
     """Real multi-GPU plumbing when the box has >= 2 GPUs (gpurun --gpus 2): replicated hierarchy, ray shards, NCCL gather."""
     import subprocess
