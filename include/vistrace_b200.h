@@ -218,7 +218,10 @@ int vt_accel_populate(vt_accel *accel, const vt_scene *scene);
  * the same order with new vertices, e.g. props that moved: keeps the structure of the resident hierarchy and refits
  * its boxes bottom-up as bvh::HierarchyRefitter does (libs/bvh/include/bvh/hierarchy_refitter.hpp:20-31, leaf update of
  * libs/bvh/test/refit_bvh.cpp:79-89) instead of the full rebuild the reference performs, then re-derives the resident
- * node layout and uploads.  Fails when nothing was populated or scene->n_tris differs. */
+ * node layout and uploads.  Fails when nothing was populated or scene->n_tris / n_materials / n_entities differ; materials,
+ * entities and textures are taken to be unchanged.  Synchronous; no traversal of this handle may be in flight.  With the
+ * default (quad) layout the work runs on the device (K5, vt_refit.cu): the vt_tri_in array is uploaded, the Triangle
+ * constructor and the bottom-up requantisation run as kernels; VT_REFIT_DEVICE=0 forces the host path. */
 int vt_accel_refit(vt_accel *accel, const vt_scene *scene);
 
 /* Host-only: the refit step alone — `nodes` (bvh::Bvh<float> form, node_count entries) are updated in place for the

@@ -577,6 +577,31 @@ def test_refit_moved_props(vt, oracle_mod, kind, layout, path, monkeypatch):
         accel.refit(abi.SceneData(moved.tris[:-1], moved.materials, moved.entities))
 
 
+def test_refit_falls_back_when_a_box_leaves_the_float_grid(vt, oracle_mod):
+    """K5 cannot requantise a box whose coordinates exceed the grid range (|E| <= 60): it reports that, vt_accel_refit
+    re-derives the layout on the host, which drops to the exact layout — results still equal the checker's."""
+    from test_host import _moved_props
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_props(4, 13, 9, 8)
+    moved = _moved_props(scene)
+    far = np.nonzero(moved.tris["ent_idx"] == 2)[0][0]
+    moved.tris["p"][far, 1] = (1.0e30, -1.0e30, 1.0e30)  # one vertex far outside any representable grid
+    rays = scenes.pinhole_rays(200, 120, (0, -95, 40), (0, 0, 10))
+    accel = vt.Accel(0, layout="quad").populate(scene)
+    assert accel.layout == "quad"
+    accel.refit(moved)
+    assert accel.layout == "exact"
+    kind = "reference" if oracle_mod.available("reference") else "port"
+    cpu = oracle_mod.CpuScene(moved, kind, build_bvh=False)
+    cpu.set_bvh(*accel.get_bvh())
+    assert accel.traverse(rays).tobytes() == cpu.traverse(rays)["hits"].tobytes()
+    accel.refit(scene)  # and back: the exact layout is refitted on the host
+    cpu = oracle_mod.CpuScene(scene, kind, build_bvh=False)
+    cpu.set_bvh(*accel.get_bvh())
+    assert accel.traverse(rays).tobytes() == cpu.traverse(rays)["hits"].tobytes()
+
+
 @pytest.mark.parametrize("kind", oracle_kinds())
 def test_alpha_test_through_dxt_compressed_vtf_files(vt, oracle_mod, kind, layout):
     """The ingestion row end to end: the foliage scene's base textures arrive as DXT5 / DXT1-one-bit-alpha VTF FILES,

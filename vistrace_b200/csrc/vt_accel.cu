@@ -569,6 +569,12 @@ void AccelStruct::Refit(const vt_scene &scene) {
     if (on_device) {
         // K5: new vertices up, Triangle constructor + bottom-up quad refit on the device (vt_refit.cu); the host copies
         // (mTriangles now, the bvh::Bvh-form boxes on demand) are brought up to date while the GPU works.
+        // the kernel indexes the resident material table with the caller's indices: check them before anything is launched
+        bool bad = false;
+#pragma omp parallel for reduction(|| : bad)
+        for (int64_t i = 0; i < (int64_t)scene.n_tris; i++)
+            bad = bad || scene.tris[i].material >= scene.n_materials || scene.tris[i].ent_idx >= scene.n_entities;
+        if (bad) throw std::runtime_error("triangle references a material or entity out of range");
         VT_CUDA(cudaSetDevice(mDevice));
         DeviceScene &D = *mpDevice;
         const VtSceneView &V = D.view;
@@ -594,6 +600,7 @@ void AccelStruct::Refit(const vt_scene &scene) {
         uint32_t failed = 0;
         VT_CUDA(cudaMemcpyAsync(&failed, D.refit_error.p, sizeof(failed), cudaMemcpyDeviceToHost, stream));
         VT_CUDA(cudaStreamSynchronize(stream));
+        D.refit_in.release();  // 152 B per triangle of staging: not part of the resident scene
         if (!failed) {
             mBvhStale = true;
             mAccelBuilt = true;
