@@ -224,6 +224,12 @@ int vt_accel_populate(vt_accel *accel, const vt_scene *scene);
  * constructor and the bottom-up requantisation run as kernels; VT_REFIT_DEVICE=0 forces the host path. */
 int vt_accel_refit(vt_accel *accel, const vt_scene *scene);
 
+/* The same for ONE contiguous range of the triangle array — the triangles [first, first + count) of the populated scene get
+ * the vertices and attributes of tris[0 .. count) (an entity that moved: its triangles are contiguous after ingestion,
+ * source/objects/AccelStruct.cpp:561-760); only those records are uploaded.  Needs the resident quad layout.  On failure
+ * after the upload (a box left the float grid) the handle is invalid until vt_accel_refit / vt_accel_populate. */
+int vt_accel_refit_range(vt_accel *accel, const vt_tri_in *tris, uint64_t first, uint64_t count);
+
 /* Host-only: the refit step alone — `nodes` (bvh::Bvh<float> form, node_count entries) are updated in place for the
  * triangles of `scene`; prim_indices has scene->n_tris entries. */
 int vt_refit_bvh(const vt_scene *scene, vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices);

@@ -577,6 +577,37 @@ def test_refit_moved_props(vt, oracle_mod, kind, layout, path, monkeypatch):
         accel.refit(abi.SceneData(moved.tris[:-1], moved.materials, moved.entities))
 
 
+def test_refit_range_one_moved_entity(vt, oracle_mod):
+    """vt_accel_refit_range: only the moved entities' triangles go up; the resident scene ends up byte-identical in effect to a
+    whole-scene refit — same hit records, same derived triangles, same refitted host boxes — and equal to the checker."""
+    from test_host import _moved_props
+    from vistrace_b200 import scenes
+
+    scene = scenes.scene_props(8, 21, 11, 12)
+    moved = _moved_props(scene)
+    rays = np.concatenate([scenes.pinhole_rays(320, 180, (0, -95, 40), (0, 0, 10)), scenes.random_rays(20000, (-90, -90, -5), (90, 90, 60), seed=12)])
+    whole = vt.Accel(0, layout="quad").populate(scene).refit(moved)
+    part = vt.Accel(0, layout="quad").populate(scene)
+    for ent in range(1, len(scene.entities)):  # entity by entity, each a contiguous run of the triangle array
+        idx = np.nonzero(scene.tris["ent_idx"] == ent)[0]
+        assert idx[-1] - idx[0] + 1 == len(idx)
+        part.refit_range(moved.tris[idx[0]: idx[-1] + 1], int(idx[0]))
+    assert part.layout == "quad"
+    h_whole, a_whole = whole.traverse(rays, want_attrs=True)
+    h_part, a_part = part.traverse(rays, want_attrs=True)
+    assert h_part.tobytes() == h_whole.tobytes() and a_part.tobytes() == a_whole.tobytes()
+    np.testing.assert_array_equal(part.tri_derived().view(np.uint32), whole.tri_derived().view(np.uint32))
+    assert np.array_equal(part.get_bvh()[0]["bounds"], whole.get_bvh()[0]["bounds"])
+    kind = "reference" if oracle_mod.available("reference") else "port"
+    cpu = oracle_mod.CpuScene(moved, kind, build_bvh=False)
+    cpu.set_bvh(*part.get_bvh())
+    assert same_hits(h_part, cpu.traverse(rays)["hits"], "quad", rays, cpu)
+    with pytest.raises(RuntimeError):
+        part.refit_range(moved.tris[:4], scene.n_tris - 2)  # past the end
+    with pytest.raises(RuntimeError):
+        vt.Accel(0, layout="exact").populate(scene).refit_range(moved.tris[:4], 0)  # quad layout only
+
+
 def test_refit_falls_back_when_a_box_leaves_the_float_grid(vt, oracle_mod):
     """K5 cannot requantise a box whose coordinates exceed the grid range (|E| <= 60): it reports that, vt_accel_refit
     re-derives the layout on the host, which drops to the exact layout — results still equal the checker's."""

@@ -1,5 +1,4 @@
 #!/bin/bash
-# session N (8 GPUs): bench at N=8 exactly as the driver launches it
-O=gpurun_out/sN; mkdir -p $O
-nvidia-smi -L > $O/gpus.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 20 --warmup 3 > $O/bench_n8.json 2> $O/bench_n8.err; echo "bench rc=$?"; cat $O/bench_n8.json; tail -3 $O/bench_n8.err
+# session O: every BASELINE config at full size on the final library
+O=gpurun_out/sO; mkdir -p $O
+timeout 1700 python tools/config_sweep.py --configs 1,2,3,4,5 --out $O/sweep.jsonl > $O/sweep.log 2>&1; echo "rc=$?"; tail -30 $O/sweep.log

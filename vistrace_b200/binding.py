@@ -26,6 +26,7 @@ SYMBOLS = {
     "vt_accel_populate_with_bvh": (_i32, [_vp, _vp, _vp, _u64, _vp]),
     "vt_accel_refit": (_i32, [_vp, _vp]),
     "vt_refit_bvh": (_i32, [_vp, _vp, _u64, _vp]),
+    "vt_accel_refit_range": (_i32, [_vp, _vp, _u64, _u64]),
     "vt_accel_get_bvh": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "vt_accel_traverse": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_traverse_stats": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp]),
@@ -258,6 +259,13 @@ class Accel:
         """accel:Rebuild for moved geometry of unchanged topology: keep the hierarchy, refit its boxes, re-upload."""
         self.scene = scene
         _check(self.L.vt_accel_refit(self.h, C.cast(scene.ptr(), _vp)), "vt_accel_refit")
+        return self
+
+    def refit_range(self, tris, first):
+        """New vertices / attributes for the triangles [first, first + len(tris)) of the populated scene (quad layout)."""
+        tris = np.ascontiguousarray(tris, abi.TRI_IN)
+        _check(self.L.vt_accel_refit_range(self.h, tris.ctypes.data, first, len(tris)), "vt_accel_refit_range")
+        self.scene.tris[first:first + len(tris)] = tris  # keep the Python-side copy in step (tri_derived sizes, later refits)
         return self
 
     def get_bvh(self):

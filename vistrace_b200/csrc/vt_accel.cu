@@ -593,7 +593,7 @@ void AccelStruct::Refit(const vt_scene &scene) {
             D.refit_ready = true;
         }
         VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
-        VT_CUDA(vt_launch_refit_tris(V, D.refit_in.p, D.refit_slot_of.p, stream));
+        VT_CUDA(vt_launch_refit_tris(V, D.refit_in.p, 0, (uint32_t)scene.n_tris, D.refit_slot_of.p, stream));
         VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
         mLaunches += 2;
         Ingest(scene);  // host copies of the containers (clears mAccelBuilt; mAccel keeps the structure)
@@ -613,6 +613,59 @@ void AccelStruct::Refit(const vt_scene &scene) {
     std::string err;
     if (!refit_bvh(mTriangles, mAccel, err)) throw std::runtime_error(err);
     Upload(scene);
+}
+
+void AccelStruct::RefitRange(const vt_tri_in *tris, uint64_t first, uint64_t count) {
+    if (!mAccelBuilt) throw std::runtime_error("refit: nothing built yet (use Populate)");
+    if (count == 0) return;
+    if (!tris) throw std::runtime_error("refit_range: null triangles");
+    if (first + count > mTriangles.size()) throw std::runtime_error("refit_range: range past the end of the triangle array");
+    if (mLayout != VT_LAYOUT_QUAD || mpDevice->view.n_pairs == 0)
+        throw std::runtime_error("refit_range: needs the resident quad layout (use vt_accel_refit with the whole scene)");
+    bool bad = false;
+#pragma omp parallel for reduction(|| : bad)
+    for (int64_t i = 0; i < (int64_t)count; i++) bad = bad || tris[i].material >= mMaterials.size() || tris[i].ent_idx >= mEntities.size();
+    if (bad) throw std::runtime_error("triangle references a material or entity out of range");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    const VtSceneView &V = D.view;
+    cudaStream_t stream = D.own_stream;
+    D.refit_in.ensure(count);
+    VT_CUDA(cudaMemcpyAsync(D.refit_in.p, tris, count * sizeof(vt_tri_in), cudaMemcpyHostToDevice, stream));
+    if (!D.refit_ready) {
+        D.refit_parent.ensure(V.n_pairs);
+        D.refit_n_inner.ensure(V.n_pairs);
+        D.refit_arrive.ensure(V.n_pairs);
+        D.refit_qbox.ensure((size_t)V.n_pairs * 6);
+        D.refit_slot_of.ensure(V.n_tris);
+        D.refit_error.ensure(1);
+        VT_CUDA(vt_launch_refit_prepare(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_slot_of.p, stream));
+        mLaunches++;
+        D.refit_ready = true;
+    }
+    VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
+    VT_CUDA(vt_launch_refit_tris(V, D.refit_in.p, (uint32_t)first, (uint32_t)count, D.refit_slot_of.p, stream));
+    VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
+    mLaunches += 2;
+    mAccelBuilt = false;  // until the device reports success
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)count; i++) {  // the host copy of the containers, as Ingest fills them
+        const vt_tri_in &in = tris[i];
+        Triangle t(in.p[0], in.p[1], in.p[2], in.material, in.uvs, in.one_sided != 0);
+        std::memcpy(t.normals, in.normals, sizeof(t.normals));
+        std::memcpy(t.tangents, in.tangents, sizeof(t.tangents));
+        std::memcpy(t.alphas, in.alphas, sizeof(t.alphas));
+        t.entIdx = in.ent_idx;
+        mTriangles[first + i] = t;
+    }
+    uint32_t failed = 0;
+    VT_CUDA(cudaMemcpyAsync(&failed, D.refit_error.p, sizeof(failed), cudaMemcpyDeviceToHost, stream));
+    VT_CUDA(cudaStreamSynchronize(stream));
+    D.refit_in.release();
+    mBvhStale = true;
+    if (failed)  // the resident records are half updated: the handle stays invalid until the caller rebuilds
+        throw std::runtime_error("refit_range: a box left the float grid of the quad layout; rebuild with vt_accel_refit or vt_accel_populate");
+    mAccelBuilt = true;
 }
 
 static void check_built(bool built) {
@@ -1073,6 +1126,14 @@ int vt_accel_refit(vt_accel *a, const vt_scene *scene) {
     VT_TRY
     if (!a || !scene) throw std::runtime_error("null argument");
     a->impl.Refit(*scene);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_refit_range(vt_accel *a, const vt_tri_in *tris, uint64_t first, uint64_t count) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.RefitRange(tris, first, count);
     return 0;
     VT_CATCH(1)
 }

@@ -136,6 +136,8 @@ public:
     // keeps the hierarchy's structure and refits its boxes bottom-up (bvh::HierarchyRefitter, hierarchy_refitter.hpp:20-31)
     // instead of rebuilding, then re-derives the resident layout.  Throws if nothing was built or the count differs.
     void Refit(const vt_scene &scene);
+    // The same for a contiguous range of the triangle array (one moved entity): only those records go up.  Quad layout only.
+    void RefitRange(const vt_tri_in *tris, uint64_t first, uint64_t count);
 
     // Batched Traverse (the entry the north star adds behind the same object).
     void TraverseBatch(const vt_ray *rays, uint64_t n, vt_hit *hits, vt_attr *attrs, const float *cones, uint32_t flags,

@@ -60,6 +60,7 @@ cudaError_t vt_launch_accumulate_sky(const VtSceneView &S, const vt_attr *attrs,
 // caller's new vertices into the resident triangle / attribute records.  refit_quads: bottom-up boxes + requantisation;
 // qbox = n_quads x 24 bytes of scratch, *error != 0 afterwards when a box could not be held on the float grid.
 cudaError_t vt_launch_refit_prepare(const VtSceneView &S, uint32_t *parent, uint32_t *n_inner, uint32_t *slot_of, cudaStream_t stream);
-cudaError_t vt_launch_refit_tris(const VtSceneView &S, const vt_tri_in *in, const uint32_t *slot_of, cudaStream_t stream);
+cudaError_t vt_launch_refit_tris(const VtSceneView &S, const vt_tri_in *in, uint32_t first, uint32_t count, const uint32_t *slot_of,
+                                 cudaStream_t stream);  // in[j] = new vertices of original triangle first + j
 cudaError_t vt_launch_refit_quads(const VtSceneView &S, const uint32_t *parent, const uint32_t *n_inner, uint32_t *arrive, void *qbox,
                                   unsigned int *error, cudaStream_t stream);

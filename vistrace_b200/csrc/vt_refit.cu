@@ -47,12 +47,14 @@ __global__ void k_refit_prepare(const VtQuad *__restrict__ quads, uint32_t n_qua
     if (i < n_tris) slot_of[tris[i].orig] = i;
 }
 
-__global__ void k_refit_tris(const vt_tri_in *__restrict__ in, uint32_t n_tris, const uint32_t *__restrict__ slot_of,
+// in[j] holds the new vertices of ORIGINAL triangle first + j, j < count
+__global__ void k_refit_tris(const vt_tri_in *__restrict__ in, uint32_t first, uint32_t count, const uint32_t *__restrict__ slot_of,
                              const VtDevMaterial *__restrict__ mats, VtTriRec *__restrict__ recs, float *__restrict__ tri_uv,
                              VtTriAttr *__restrict__ attrs) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_tris) return;
-    const vt_tri_in t = in[i];
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const uint32_t i = first + j;
+    const vt_tri_in t = in[j];
     float p0[3], e1[3], e2[3], n[3], nn[3];
     for (int k = 0; k < 3; k++) {
         p0[k] = t.p[0][k];
@@ -198,10 +200,12 @@ cudaError_t vt_launch_refit_prepare(const VtSceneView &S, uint32_t *parent, uint
     return cudaGetLastError();
 }
 
-cudaError_t vt_launch_refit_tris(const VtSceneView &S, const vt_tri_in *in, const uint32_t *slot_of, cudaStream_t stream) {
-    if (S.n_tris == 0) return cudaSuccess;
-    k_refit_tris<<<(S.n_tris + 127) / 128, 128, 0, stream>>>(in, S.n_tris, slot_of, S.mats, const_cast<VtTriRec *>(S.tris),
-                                                             const_cast<float *>(S.tri_uv), const_cast<VtTriAttr *>(S.attrs));
+cudaError_t vt_launch_refit_tris(const VtSceneView &S, const vt_tri_in *in, uint32_t first, uint32_t count, const uint32_t *slot_of,
+                                 cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    if ((uint64_t)first + count > S.n_tris) return cudaErrorInvalidValue;
+    k_refit_tris<<<(count + 127) / 128, 128, 0, stream>>>(in, first, count, slot_of, S.mats, const_cast<VtTriRec *>(S.tris),
+                                                          const_cast<float *>(S.tri_uv), const_cast<VtTriAttr *>(S.attrs));
     return cudaGetLastError();
 }
 
