@@ -69,7 +69,7 @@ static_assert(sizeof(VtCPair) == 32, "compact pair layout");
 // Children are TAGGED references: bits 28-31 = triangle count (0 = inner quad), bits 0-27 = quad index
 // or first triangle slot; empty slots have ref 0xFFFFFFFF.
 struct alignas(64) VtQuad {
-    float origin_adj[3];  // (k - 2^23) * 2^E per axis
+    float origin_adj[3];  // (k - VT_QUAD_OFFSET) * 2^E per axis
     float scale[3];       // 2^E per axis, as a float
     uint8_t q[3][2][4];   // [axis][lo, hi][child]
     uint32_t ref[4];      // tagged child references; 0xFFFFFFFF = empty slot (its box is inverted: q_lo = 255, q_hi = 0)

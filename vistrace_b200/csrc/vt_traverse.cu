@@ -289,10 +289,11 @@ VT_DEV void slab_cpair(const VtCPair *cpairs, uint32_t cur, uint32_t magic, cons
 #endif
 //
 // Plane arithmetic, two forms with the same guarantee (every box FastNodeIntersector accepts is accepted):
-//   TWO_FMA   t = fmaf(fmaf(2^23+q, 2^E, origin_adj), inv, so): exact decode, then the reference's expression.
-//   one fma   t = fmaf(2^23+q, 2^E*inv, A) with A = origin_adj*inv + so rounded DOWN for entry planes and UP for exit
+//   (OFF = VT_QUAD_OFFSET: 1024 with the half2 decode, 2^23 with the PRMT decode; origin_adj = (k - OFF) * 2^E)
+//   TWO_FMA   t = fmaf(fmaf(OFF+q, 2^E, origin_adj), inv, so): exact decode, then the reference's expression.
+//   one fma   t = fmaf(OFF+q, 2^E*inv, A) with A = origin_adj*inv + so rounded DOWN for entry planes and UP for exit
 //             planes, once per node and axis.  2^E*inv is exact (power of two; the host keeps |E| <= 60 and the lane's
-//             |inv| is in [2^-60, 2^24], so the product is a normal float), (2^23+q)*2^E + origin_adj is the decoded
+//             |inv| is in [2^-60, 2^24], so the product is a normal float), (OFF+q)*2^E + origin_adj is the decoded
 //             plane exactly, hence the real value under the rounding is plane*inv + so minus a non-negative slack
 //             (entry) or plus one (exit); rounding is monotone, so entry' <= the reference's entry and exit' >= its exit.
 //             A warp holding a ray outside that |inv| range (|d| > 2^60, NaN) takes the TWO_FMA form.
