@@ -33,9 +33,6 @@
 #ifndef VT_TRI_ADDR_WIDE
 #define VT_TRI_ADDR_WIDE 1
 #endif
-#ifndef VT_POSTPONE
-#define VT_POSTPONE 0
-#endif
 #ifndef VT_STACK_DIST
 #define VT_STACK_DIST 0  // measured: -7 % node visits / -22 % triangle tests on primary rays (+3 %), but -5.6 % on the bounce wave
 #endif
@@ -632,20 +629,6 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
     const uint32_t stack = local_addr(stack_mem);
     uint32_t sp = stack;         // byte address of the next free entry
     uint32_t cur = VT_REF_DONE;  // VT_REF_DONE: nothing left to visit
-#if VT_POSTPONE
-    // one leaf run put aside while the lane keeps walking (speculative traversal): triangle rounds then start with
-    // many more lanes than the few that happen to reach a leaf in the same round.  Invariant: `cur` is a leaf only
-    // while `pend` is occupied (the lane then waits for the next triangle round).
-    uint32_t pend = VT_REF_DONE;
-#define VT_IS_LEAF(c) ((c) - (1u << VT_REF_SHIFT) < VT_REF_DONE - (1u << VT_REF_SHIFT))
-#define VT_SETTLE()                                           \
-    if (VT_IS_LEAF(cur) && pend == VT_REF_DONE) {             \
-        pend = cur;                                           \
-        cur = stack_pop<DIST>(sp, stack, r.tmax);             \
-    }
-#else
-#define VT_SETTLE()
-#endif
     bool alive = false;          // lane owns a ray whose result is not written yet
     bool exhausted = false;      // warp-uniform: the ray queue has run dry
     unsigned long long ray_idx = 0;
@@ -655,11 +638,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
     bool warp_wild = false;  // warp-uniform: some lane holds a ray the one-fma plane form is not proven for (slab_quad)
 
     for (;;) {
-#if VT_POSTPONE
-        if (alive && cur == VT_REF_DONE && pend == VT_REF_DONE) {
-#else
         if (alive && cur == VT_REF_DONE) {
-#endif
             write_hit(hits, ray_idx, r);
             alive = false;
         }
@@ -693,7 +672,6 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                         if (!(in.tmax < 0.f)) n_invalid++;
                     } else if (S.root_leaf_count) {
                         cur = S.root_leaf_count << VT_REF_SHIFT;  // the root is a leaf over tris[0, count)
-                        VT_SETTLE()
                     } else if (S.n_pairs) {
                         cur = 0;  // pair 0 / quad 0: the children of the root
                     }
@@ -705,13 +683,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
         const int keep = exhausted ? 0 : refill_threshold;
 
         for (;;) {
-#if VT_POSTPONE
-            const bool is_node = cur < (1u << VT_REF_SHIFT);
-            const bool is_leaf = pend != VT_REF_DONE;  // a run is waiting for a triangle round
-            const unsigned want_node = __ballot_sync(0xffffffffu, is_node);
-            const unsigned want_tri = __ballot_sync(0xffffffffu, is_leaf);
-            if (__popc(want_node | want_tri) <= keep) break;
-#elif VT_SCHED2
+#if VT_SCHED2
             // one compare per class: inner references are < 2^28, VT_REF_DONE is the only value that is neither
             const bool has = cur != VT_REF_DONE;
             const bool is_node = cur < (1u << VT_REF_SHIFT);
@@ -732,21 +704,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     // the whole leaf run in one round, in order (tmax shrinks between candidates exactly as in
                     // intersect_leaf, single_ray_traverser.hpp:41-63); the run is contiguous, so after the first
                     // record the next ones mostly come from the same 128-byte line
-#if VT_POSTPONE
-                    bool any = false;
-                    for (;;) {
-                        if (STATS) n_tests++;
-                        any |= intersect_triangle<ALPHA>(S, pend & VT_REF_MASK, r);
-                        if ((ANY_HIT && any) || (pend >> VT_REF_SHIFT) == 1u) break;
-                        pend -= VT_REF_MASK;  // count - 1, slot + 1
-                    }
-                    pend = VT_REF_DONE;
-                    if (ANY_HIT && any) {
-                        cur = VT_REF_DONE;
-                        sp = stack;
-                    }
-                    VT_SETTLE()  // a leaf that was blocked behind this one takes its place
-#elif VT_LEAF_RUN_PER_ROUND
+#if VT_LEAF_RUN_PER_ROUND
                     bool any = false;
                     for (;;) {
                         if (STATS) n_tests++;
@@ -773,11 +731,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     }
 #endif
                 }
-#if VT_POSTPONE
-            } else if (is_node) {
-#else
             } else if (has && !is_leaf) {
-#endif
                 if (STATS) n_steps++;
                 if (QUAD) {
                     int k[4];
@@ -797,7 +751,6 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     } else {
                         cur = stack_pop<DIST>(sp, stack, r.tmax);
                     }
-                    VT_SETTLE()
                     continue;
                 }
                 float le, lx, re, rx;
@@ -813,7 +766,6 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                 } else {
                     cur = stack_pop<DIST>(sp, stack, r.tmax);
                 }
-                VT_SETTLE()
             }
         }
     }
