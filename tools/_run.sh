@@ -1,4 +1,5 @@
 #!/bin/bash
-# session O: every BASELINE config at full size on the final library
-O=gpurun_out/sO; mkdir -p $O
-timeout 1700 python tools/config_sweep.py --configs 1,2,3,4,5 --out $O/sweep.jsonl > $O/sweep.log 2>&1; echo "rc=$?"; tail -30 $O/sweep.log
+# session P: range-refit + fallback tests; split-step experiment
+O=gpurun_out/sP; mkdir -p $O
+timeout 600 python -m pytest tests -m gpu -x -q -k "refit" > $O/pytest_refit.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_refit.log
+timeout 600 python tools/split_step.py --parts 1,2,3,4,6 > $O/split.log 2>&1; cat $O/split.log | tail -8
