@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -193,7 +194,7 @@ struct DeviceScene {
     // per-stream tile staging of the host-pointer diffuse wave
     struct WaveLane {
         cudaStream_t stream = nullptr;
-        DevBuf<vt_ray> rays, brays;
+        DevBuf<vt_ray> brays;
         DevBuf<vt_hit> hits, bhits;
         DevBuf<vt_attr> attrs;
         DevBuf<float> fb;
@@ -208,6 +209,11 @@ struct DeviceScene {
     std::map<cudaStream_t, WaveScratch> wave_scratch;
     std::mutex wave_mutex;
     DevBuf<unsigned long long> live;
+    // host-pointer waves: the whole frame's rays are staged here by ONE copy stream, tile after tile, so an upload never
+    // waits for the lane (stream) its tile will run on; upload_done[k] gates tile k's kernels
+    DevBuf<vt_ray> wave_rays;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> upload_done;
     // K5 (device refit) state, built on the first refit of a resident quad hierarchy
     DevBuf<vt_tri_in> refit_in;
     DevBuf<uint32_t> refit_parent, refit_n_inner, refit_slot_of, refit_arrive, refit_error;
@@ -237,6 +243,9 @@ struct DeviceScene {
         s_attrs.release();
         s_cones.release();
         live.release();
+        wave_rays.release();
+        for (cudaEvent_t e : upload_done) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         refit_in.release();
         refit_parent.release();
         refit_n_inner.release();
@@ -245,7 +254,6 @@ struct DeviceScene {
         refit_error.release();
         refit_qbox.release();
         for (auto &l : lanes) {
-            l.rays.release();
             l.brays.release();
             l.hits.release();
             l.bhits.release();
@@ -943,28 +951,52 @@ void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp,
     const int n_lanes = std::max(1, std::min(8, env_int("VT_WAVE_LANES", 4)));
     for (int i = 0; i < n_lanes; i++)
         if (!D.lanes[i].stream) VT_CUDA(cudaStreamCreateWithFlags(&D.lanes[i].stream, cudaStreamNonBlocking));
+    // VT_WAVE_CTAS_PER_SM: persistent-grid size of the tiles' K1 launches.  Several tiles are in flight, so a tile's K1 takes
+    // 6 of the 9 CTA slots per SM and leaves room for another tile's kernels to start (3.08 vs 3.15 ms per e2e step; 3: 3.38)
+    VtLaunchConfig tile_cfg = D.cfg;
+    {
+        const int per_sm = env_int("VT_WAVE_CTAS_PER_SM", 6);
+        if (per_sm > 0) tile_cfg.grid = std::min(D.cfg.grid, D.sm_count * per_sm);
+    }
+    // uploads go through one copy stream into a frame-sized staging buffer (see DeviceScene::wave_rays)
+    D.wave_rays.ensure(n);
+    if (!D.copy_stream) VT_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
+    size_t n_uploads = 0;
+    auto upload_tile = [&](uint64_t base, uint64_t m, cudaStream_t consumer) -> const vt_ray * {
+        if (n_uploads == D.upload_done.size()) {
+            cudaEvent_t e;
+            VT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            D.upload_done.push_back(e);
+        }
+        cudaEvent_t done = D.upload_done[n_uploads++];
+        VT_CUDA(cudaMemcpyAsync(D.wave_rays.p + base, rays + base, m * sizeof(vt_ray), cudaMemcpyHostToDevice, D.copy_stream));
+        VT_CUDA(cudaEventRecord(done, D.copy_stream));
+        VT_CUDA(cudaStreamWaitEvent(consumer, done, 0));
+        return D.wave_rays.p + base;
+    };
     int li = 0;
     uint64_t cur_tile = std::max<uint64_t>(1, std::min<uint64_t>(tile, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)(tile / 8)))));  // small first tiles, doubling up to `tile`
     for (uint64_t base = 0, m = 0; base < n; base += m, li = (li + 1) % n_lanes, cur_tile = std::min(tile, cur_tile * 2)) {
         m = std::min(cur_tile, n - base);
+        if (n - base - m < cur_tile / 2) m = n - base;  // no small tail tile: its launch-latency chain would run alone at the end
         DeviceScene::WaveLane &l = D.lanes[li];
-        l.rays.ensure(tile);
-        l.hits.ensure(tile);
-        l.attrs.ensure(tile);
-        l.brays.ensure(tile * spp);
-        l.bhits.ensure(tile * spp);
-        l.queue.ensure(tile * spp);
+        const uint64_t cap = tile + tile / 2;
+        l.hits.ensure(cap);
+        l.attrs.ensure(cap);
+        l.brays.ensure(cap * spp);
+        l.bhits.ensure(cap * spp);
+        l.queue.ensure(cap * spp);
         l.queue_count.ensure(1);
         unsigned long long *c0 = next_counter(), *c1 = next_counter();
         VT_CUDA(cudaMemsetAsync(c0, 0, 16, l.stream));
         VT_CUDA(cudaMemsetAsync(c1, 0, 16, l.stream));
         VT_CUDA(cudaMemsetAsync(l.queue_count.p, 0, sizeof(unsigned long long), l.stream));
-        VT_CUDA(cudaMemcpyAsync(l.rays.p, rays + base, m * sizeof(vt_ray), cudaMemcpyHostToDevice, l.stream));
-        VT_CUDA(vt_launch_traverse(D.view, l.rays.p, l.hits.p, m, false, c0, D.cfg, l.stream));
-        VT_CUDA(vt_launch_trace_result(D.view, l.rays.p, l.hits.p, nullptr, l.attrs.p, m, l.stream));
+        const vt_ray *d_tile = upload_tile(base, m, l.stream);
+        VT_CUDA(vt_launch_traverse(D.view, d_tile, l.hits.p, m, false, c0, tile_cfg, l.stream));
+        VT_CUDA(vt_launch_trace_result(D.view, d_tile, l.hits.p, nullptr, l.attrs.p, m, l.stream));
         VT_CUDA(vt_launch_bounce_rays(l.attrs.p, m, spp, seed, base * spp, l.brays.p, D.live.p, l.stream, l.queue.p, l.queue_count.p,
                                       l.bhits.p));
-        VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, m * spp, false, c1, D.cfg, l.stream, false, l.queue.p,
+        VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, m * spp, false, c1, tile_cfg, l.stream, false, l.queue.p,
                                    l.queue_count.p));
         mLaunches += 4;
         VT_CUDA(cudaMemcpyAsync(hits + base, l.hits.p, m * sizeof(vt_hit), cudaMemcpyDeviceToHost, l.stream));
@@ -998,37 +1030,99 @@ void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp
     const int n_lanes = std::max(1, std::min(8, env_int("VT_WAVE_LANES", 4)));
     for (int i = 0; i < n_lanes; i++)
         if (!D.lanes[i].stream) VT_CUDA(cudaStreamCreateWithFlags(&D.lanes[i].stream, cudaStreamNonBlocking));
+    // VT_WAVE_TRACE=1: one line per tile with the stream-time (ms since the first submission) at which each stage finished
+    const bool trace = env_int("VT_WAVE_TRACE", 0) != 0;
+    struct TileTrace {
+        uint64_t base, m;
+        int lane;
+        cudaEvent_t ev[6];  // after H2D, K1 primary, K2+K3, K1 bounce, K4, D2H
+    };
+    std::vector<TileTrace> tiles;
+    cudaEvent_t ev_begin = nullptr;
+    if (trace) {
+        VT_CUDA(cudaEventCreate(&ev_begin));
+        VT_CUDA(cudaEventRecord(ev_begin, D.lanes[0].stream));
+    }
+    auto mark = [&](TileTrace &t, int k, cudaStream_t st) {
+        if (!trace) return;
+        VT_CUDA(cudaEventCreate(&t.ev[k]));
+        VT_CUDA(cudaEventRecord(t.ev[k], st));
+    };
+    // VT_WAVE_CTAS_PER_SM: persistent-grid size of the tiles' K1 launches.  Several tiles are in flight, so a tile's K1 takes
+    // 6 of the 9 CTA slots per SM and leaves room for another tile's kernels to start (3.08 vs 3.15 ms per e2e step; 3: 3.38)
+    VtLaunchConfig tile_cfg = D.cfg;
+    {
+        const int per_sm = env_int("VT_WAVE_CTAS_PER_SM", 6);
+        if (per_sm > 0) tile_cfg.grid = std::min(D.cfg.grid, D.sm_count * per_sm);
+    }
+    // uploads go through one copy stream into a frame-sized staging buffer (see DeviceScene::wave_rays)
+    D.wave_rays.ensure(n);
+    if (!D.copy_stream) VT_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
+    size_t n_uploads = 0;
+    auto upload_tile = [&](uint64_t base, uint64_t m, cudaStream_t consumer) -> const vt_ray * {
+        if (n_uploads == D.upload_done.size()) {
+            cudaEvent_t e;
+            VT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            D.upload_done.push_back(e);
+        }
+        cudaEvent_t done = D.upload_done[n_uploads++];
+        VT_CUDA(cudaMemcpyAsync(D.wave_rays.p + base, rays + base, m * sizeof(vt_ray), cudaMemcpyHostToDevice, D.copy_stream));
+        VT_CUDA(cudaEventRecord(done, D.copy_stream));
+        VT_CUDA(cudaStreamWaitEvent(consumer, done, 0));
+        return D.wave_rays.p + base;
+    };
     int li = 0;
     // the first tiles are small so the first kernel starts after a short upload; sizes double up to `tile`
     uint64_t cur_tile = std::max<uint64_t>(1, std::min<uint64_t>(tile, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)(tile / 8)))));
     for (uint64_t base = 0, m = 0; base < n; base += m, li = (li + 1) % n_lanes, cur_tile = std::min(tile, cur_tile * 2)) {
         m = std::min(cur_tile, n - base);
+        if (n - base - m < cur_tile / 2) m = n - base;  // no small tail tile: its launch-latency chain would run alone at the end
         DeviceScene::WaveLane &l = D.lanes[li];
-        l.rays.ensure(tile);
-        l.hits.ensure(tile);
-        l.attrs.ensure(tile);
-        l.brays.ensure(tile * spp);
-        l.bhits.ensure(tile * spp);
-        l.fb.ensure(tile * 3);
-        l.queue.ensure(tile * spp);
+        const uint64_t cap = tile + tile / 2;
+        l.hits.ensure(cap);
+        l.attrs.ensure(cap);
+        l.brays.ensure(cap * spp);
+        l.bhits.ensure(cap * spp);
+        l.fb.ensure(cap * 3);
+        l.queue.ensure(cap * spp);
         l.queue_count.ensure(1);
         unsigned long long *c0 = next_counter(), *c1 = next_counter();
         VT_CUDA(cudaMemsetAsync(c0, 0, 16, l.stream));
         VT_CUDA(cudaMemsetAsync(c1, 0, 16, l.stream));
         VT_CUDA(cudaMemsetAsync(l.queue_count.p, 0, sizeof(unsigned long long), l.stream));
         VT_CUDA(cudaMemsetAsync(l.fb.p, 0, m * 3 * sizeof(float), l.stream));
-        VT_CUDA(cudaMemcpyAsync(l.rays.p, rays + base, m * sizeof(vt_ray), cudaMemcpyHostToDevice, l.stream));
-        VT_CUDA(vt_launch_traverse(D.view, l.rays.p, l.hits.p, m, false, c0, D.cfg, l.stream));
-        VT_CUDA(vt_launch_trace_result(D.view, l.rays.p, l.hits.p, nullptr, l.attrs.p, m, l.stream));
+        TileTrace tt{base, m, li, {}};
+        const vt_ray *d_tile = upload_tile(base, m, l.stream);
+        mark(tt, 0, l.stream);
+        VT_CUDA(vt_launch_traverse(D.view, d_tile, l.hits.p, m, false, c0, tile_cfg, l.stream));
+        mark(tt, 1, l.stream);
+        VT_CUDA(vt_launch_trace_result(D.view, d_tile, l.hits.p, nullptr, l.attrs.p, m, l.stream));
         VT_CUDA(vt_launch_bounce_rays(l.attrs.p, m, spp, seed, base * spp, l.brays.p, live_out ? D.live.p : nullptr, l.stream, l.queue.p,
                                       l.queue_count.p, l.bhits.p));
-        VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, m * spp, false, c1, D.cfg, l.stream, false, l.queue.p,
+        mark(tt, 2, l.stream);
+        VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, m * spp, false, c1, tile_cfg, l.stream, false, l.queue.p,
                                    l.queue_count.p));
+        mark(tt, 3, l.stream);
         VT_CUDA(vt_launch_accumulate_sky(D.view, l.attrs.p, l.bhits.p, m, spp, weight, l.fb.p, l.stream));
+        mark(tt, 4, l.stream);
         mLaunches += 5;
         VT_CUDA(cudaMemcpyAsync(fb + base * 3, l.fb.p, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, l.stream));
+        mark(tt, 5, l.stream);
+        if (trace) tiles.push_back(tt);
     }
     for (int i = 0; i < n_lanes; i++) VT_CUDA(cudaStreamSynchronize(D.lanes[i].stream));
+    if (trace) {
+        for (TileTrace &t : tiles) {
+            float ms[6];
+            for (int k = 0; k < 6; k++) {
+                VT_CUDA(cudaEventElapsedTime(&ms[k], ev_begin, t.ev[k]));
+                cudaEventDestroy(t.ev[k]);
+            }
+            std::fprintf(stderr, "[wave] tile base %8llu rays %7llu lane %d: H2D %.3f  K1p %.3f  K2K3 %.3f  K1b %.3f  K4 %.3f  D2H %.3f ms\n",
+                         (unsigned long long)t.base, (unsigned long long)t.m, t.lane, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5]);
+        }
+        cudaEventDestroy(ev_begin);
+    }
     if (live_out) {
         unsigned long long v = 0;
         VT_CUDA(cudaMemcpy(&v, D.live.p, sizeof(v), cudaMemcpyDeviceToHost));
