@@ -23,6 +23,40 @@ def test_library_exports_every_declared_symbol(built):
     assert declared == set(binding.SYMBOLS), declared ^ set(binding.SYMBOLS)
 
 
+def test_header_is_plain_c_and_links_against_the_library(built, tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and as C++11 with pedantic warnings as errors, and a C program that
+    calls into the library links and runs (no compute: vt_device_count, vt_last_error, a VTF header probe)."""
+    import shutil
+    import subprocess
+
+    import vistrace_b200 as vt
+
+    if not shutil.which("gcc"):
+        pytest.skip("no C compiler")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "vistrace_b200.h"\n'
+        "int main(void) {\n"
+        "    vt_ray r; vt_hit h; vt_vtf_info info;\n"
+        "    unsigned char junk[16];\n"
+        "    memset(&r, 0, sizeof r); memset(&h, 0, sizeof h); memset(junk, 0, sizeof junk);\n"
+        '    if (vt_vtf_read_info(junk, sizeof junk, &info) == 0) return 2; /* bad signature must fail ... */\n'
+        '    if (vt_last_error()[0] == 0) return 3;                        /* ... and say why */\n'
+        '    printf("%d %u %u %u\\n", vt_device_count() >= 0, (unsigned)sizeof(vt_ray), (unsigned)sizeof(vt_hit), (unsigned)sizeof(vt_tri_in));\n'
+        "    return 0;\n}\n")
+    inc = os.path.join(ROOT, "include")
+    lib = vt.library_path()
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
+        if not shutil.which(cc):
+            continue
+        subprocess.check_call([cc, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c" if cc == "gcc" else "c++", "-I", inc, str(src)])
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), lib, "-Wl,-rpath," + os.path.dirname(lib)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out
+    assert out.stdout.split() == ["1", "32", "16", "152"]
+
+
 def test_record_sizes_match_header(built):
     from vistrace_b200 import abi
 
