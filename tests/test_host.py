@@ -42,7 +42,7 @@ def test_header_is_plain_c_and_links_against_the_library(built, tmp_path):
         "    memset(&r, 0, sizeof r); memset(&h, 0, sizeof h); memset(junk, 0, sizeof junk);\n"
         '    if (vt_vtf_read_info(junk, sizeof junk, &info) == 0) return 2; /* bad signature must fail ... */\n'
         '    if (vt_last_error()[0] == 0) return 3;                        /* ... and say why */\n'
-        '    printf("%d %u %u %u\\n", vt_device_count() >= 0, (unsigned)sizeof(vt_ray), (unsigned)sizeof(vt_hit), (unsigned)sizeof(vt_tri_in));\n'
+        '    printf("%d %u %u %u\\n", vt_device_count() >= -1, (unsigned)sizeof(vt_ray), (unsigned)sizeof(vt_hit), (unsigned)sizeof(vt_tri_in));\n'
         "    return 0;\n}\n")
     inc = os.path.join(ROOT, "include")
     lib = vt.library_path()
