@@ -80,7 +80,10 @@ VT_DEV float tex_lod(const VtDevTexture &t, V2 info) { return info.x + 0.5f * lo
 
 VT_DEV void st4(float *dst, float a, float b, float c, float d) { *reinterpret_cast<float4 *>(dst) = make_float4(a, b, c, d); }
 
-__global__ void __launch_bounds__(128)
+#ifndef VT_K2_MIN_BLOCKS
+#define VT_K2_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, VT_K2_MIN_BLOCKS)
 k_trace_result(const VtSceneView S, const vt_ray *__restrict__ rays, const vt_hit *__restrict__ hits,
                const float *__restrict__ cones, vt_attr *__restrict__ attrs, unsigned long long n) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
