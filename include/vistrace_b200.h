@@ -379,6 +379,14 @@ int vt_accel_get_tri_derived(const vt_accel *accel, float *out16);
  * entry and the node count on return; prim_indices has scene->n_tris entries. */
 int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices);
 
+/* Host-only: the REFERENCE's hierarchy for the scene, rebuilt from its algorithm — bvh::LocallyOrderedClusteringBuilder
+ * <BVH, uint32_t> (libs/bvh/include/bvh/locally_ordered_clustering_builder.hpp: search radius 14, 30-bit Morton codes) and,
+ * with collapse != 0, bvh::LeafCollapser (leaf_collapser.hpp) — the sequence of source/objects/AccelStruct.cpp:762-770.
+ * Nodes and primitive indices equal the reference's arrays bit for bit, so the exact node layout then reproduces the
+ * reference's winners among exactly tied candidates.  Same calling convention as vt_build_bvh; VT_BUILDER=ploc makes
+ * vt_accel_populate use it. */
+int vt_build_bvh_ploc(const vt_scene *scene, int collapse, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices);
+
 /* Host-only: flatten a bvh::Bvh<float>-form hierarchy to the device layout — (node_count-1)/2
  * 64-byte sibling pairs (the first bfs_pairs in breadth-first order, depth-first below) and the
  * leaf-order permutation of the triangles.  Validates the tree (adjacent odd child pairs, every

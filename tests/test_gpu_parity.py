@@ -577,6 +577,33 @@ def test_refit_moved_props(vt, oracle_mod, kind, layout, path, monkeypatch):
         accel.refit(abi.SceneData(moved.tris[:-1], moved.materials, moved.entities))
 
 
+@pytest.mark.parametrize("scene_name", ["props", "duplicates"])
+def test_ploc_builder_gives_the_reference_answers_ties_included(vt, oracle_mod, scene_name, monkeypatch):
+    """VT_BUILDER=ploc + exact layout: the engine builds the reference's own hierarchy (vt_bvh_ploc.cpp) and, with the reference's
+    visit order, returns its hit buffer byte for byte — exact ties between duplicated triangles included — while the
+    reference runs on the tree IT built; nothing is handed over."""
+    from vistrace_b200 import abi, scenes
+
+    if not oracle_mod.available("reference"):
+        pytest.skip("needs oracle/_ref")
+    base = scenes.scene_props(6, 15, 9, 8)
+    scene = base if scene_name == "props" else abi.SceneData(np.concatenate([base.tris, base.tris]), base.materials, base.entities)
+    rays = np.concatenate([scenes.pinhole_rays(320, 180, (0, -95, 40), (0, 0, 10)), scenes.random_rays(20000, (-90, -90, -5), (90, 90, 60), seed=3)])
+    monkeypatch.setenv("VT_BUILDER", "ploc")
+    accel = vt.Accel(0, layout="exact").populate(scene)
+    cpu = oracle_mod.CpuScene(scene, "reference", build_bvh=True)
+    want_nodes, want_prims = cpu.get_bvh()
+    nodes, prims = accel.get_bvh()
+    assert nodes.tobytes() == want_nodes.tobytes() and prims.tobytes() == want_prims.tobytes()
+    hits, attrs = accel.traverse(rays, want_attrs=True)
+    want = cpu.traverse(rays, want_attrs=True)
+    assert hits.tobytes() == want["hits"].tobytes()
+    err = attr_max_rel_err(attrs, want["attrs"])
+    assert max(err[f] for f in ATTR_FLOAT_FIELDS) <= 1e-5
+    quad = vt.Accel(0, layout="quad").populate(scene)  # the quantised layout over the same tree: same records up to counted ties
+    assert same_hits(quad.traverse(rays), want["hits"], "quad", rays, cpu)
+
+
 def test_refit_range_one_moved_entity(vt, oracle_mod):
     """vt_accel_refit_range: only the moved entities' triangles go up; the resident scene ends up byte-identical in effect to a
     whole-scene refit — same hit records, same derived triangles, same refitted host boxes — and equal to the checker."""

@@ -429,3 +429,49 @@ def test_refit_rejects_a_changed_topology(built):
     fewer = abi.SceneData(scene.tris[:-2], scene.materials, scene.entities)
     with pytest.raises(RuntimeError):
         vt.refit_bvh(fewer, nodes, prims[:-2])  # leaves address primitives past the end
+
+
+@pytest.mark.parametrize("name", ["props_small", "foliage_small"])
+def test_ploc_builder_reproduces_the_golden_reference_hierarchy(built, name):
+    """vt_build_bvh_ploc against the hierarchy the UNMODIFIED reference built for the golden scenes (PLOC + LeafCollapser,
+    stored by tests/golden/make_golden.py): node array and primitive indices bit for bit."""
+    import vistrace_b200 as vt
+    from conftest import load_golden
+
+    scene, z = load_golden(name)
+    nodes, prims = vt.build_bvh_ploc(scene)
+    assert nodes.tobytes() == np.ascontiguousarray(z["nodes"]).tobytes()
+    assert prims.tobytes() == np.ascontiguousarray(z["prim_indices"], np.uint64).tobytes()
+
+
+@pytest.mark.parametrize("scene_name", ["heightfield", "props", "far_from_origin", "two_triangles", "one_triangle", "duplicates"])
+def test_ploc_builder_reproduces_the_reference_hierarchy(built, oracle_mod, scene_name):
+    """The same against the reference run here (oracle/_ref): ordinary scenes, map-scale coordinates, the degenerate sizes where
+    the collapser turns the root into a leaf, and duplicated geometry (equal Morton codes and equal merge distances: every
+    tie-break of the stable sort and of the neighbour search is exercised)."""
+    import vistrace_b200 as vt
+    from vistrace_b200 import abi, scenes
+
+    if not oracle_mod.available("reference"):
+        pytest.skip("needs oracle/_ref")
+    if scene_name == "heightfield":
+        scene = scenes.scene_heightfield(64)
+    elif scene_name == "props":
+        scene = scenes.scene_props(9, 21, 11, 12)
+    elif scene_name == "far_from_origin":
+        scene = scenes.scene_props(5, 15, 9, 8)
+        scene.tris["p"] = scene.tris["p"] * np.float32(0.02) + np.array([16000.0, -15900.0, 8000.0], np.float32)
+    elif scene_name == "duplicates":
+        base = scenes.scene_props(3, 9, 7, 6)
+        scene = abi.SceneData(np.concatenate([base.tris, base.tris, base.tris[::3]]), base.materials, base.entities)
+    else:
+        base = scenes.scene_heightfield(4)
+        scene = abi.SceneData(base.tris[: 2 if scene_name == "two_triangles" else 1], base.materials, base.entities)
+    ref = oracle_mod.CpuScene(scene, "reference", build_bvh=True)
+    want_nodes, want_prims = ref.get_bvh()
+    nodes, prims = vt.build_bvh_ploc(scene)
+    assert len(nodes) == len(want_nodes) and nodes.tobytes() == want_nodes.tobytes()
+    assert prims.tobytes() == want_prims.tobytes()
+    if scene.n_tris > 2:  # and it is a hierarchy the engine accepts: every triangle once, depth within the stack
+        flat = vt.flatten_bvh(nodes, prims, 0)
+        assert sorted(flat["leaf_order"].tolist()) == list(range(scene.n_tris))

@@ -47,6 +47,7 @@ SYMBOLS = {
     "vt_quad_plane_offset": (_u32, []),
     "vt_vtf_read_info": (_i32, [_vp, _u64, _vp]),
     "vt_vtf_decode": (_i32, [_vp, _u64, _u32, _u32, _vp, _u64, _vp]),
+    "vt_build_bvh_ploc": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "vt_build_quads": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_invalid_rays": (_u64, [_vp]),
     "vt_accel_launch_count": (_u64, [_vp]),
@@ -103,6 +104,18 @@ def build_bvh(scene):
     prims = np.zeros(scene.n_tris, np.uint64)
     cap = C.c_uint64(len(nodes))
     _check(L.vt_build_bvh(C.cast(scene.ptr(), _vp), nodes.ctypes.data, C.addressof(cap), prims.ctypes.data), "vt_build_bvh")
+    return nodes, prims
+
+
+def build_bvh_ploc(scene, collapse=True):
+    """Host-only: the reference's own PLOC (+ LeafCollapser) hierarchy rebuilt from its algorithm -> (nodes, prim_indices)."""
+    L = lib()
+    cnt = C.c_uint64(0)
+    _check(L.vt_build_bvh_ploc(C.cast(scene.ptr(), _vp), int(collapse), None, C.addressof(cnt), None), "vt_build_bvh_ploc")
+    nodes = np.zeros(cnt.value, abi.NODE)
+    prims = np.zeros(scene.n_tris, np.uint64)
+    cap = C.c_uint64(len(nodes))
+    _check(L.vt_build_bvh_ploc(C.cast(scene.ptr(), _vp), int(collapse), nodes.ctypes.data, C.addressof(cap), prims.ctypes.data), "vt_build_bvh_ploc")
     return nodes, prims
 
 

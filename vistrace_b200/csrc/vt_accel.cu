@@ -546,8 +546,15 @@ void AccelStruct::Upload(const vt_scene &scene) {
 
 void AccelStruct::Populate(const vt_scene &scene) {
     Ingest(scene);
-    // the build step of source/objects/AccelStruct.cpp:762-770, host side
-    build_bvh(mTriangles, mAccel, env_int("VT_MAX_LEAF", 4), env_float("VT_TRAV_COST", 1.0f));
+    // the build step of source/objects/AccelStruct.cpp:762-770, host side: the product's binned-SAH builder, or (VT_BUILDER=ploc)
+    // the reference's own PLOC + LeafCollapser tree, node for node (vt_bvh_ploc.cpp)
+    const char *builder = std::getenv("VT_BUILDER");
+    if (builder && std::string(builder) == "ploc") {
+        build_bvh_ploc(mTriangles, mAccel);
+        collapse_leaves(mAccel);
+    } else {
+        build_bvh(mTriangles, mAccel, env_int("VT_MAX_LEAF", 4), env_float("VT_TRAV_COST", 1.0f));
+    }
     Upload(scene);
 }
 
@@ -1429,6 +1436,28 @@ int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, ui
     }
     vt::HostBvh bvh;
     vt::build_bvh(tris, bvh, vt::env_int("VT_MAX_LEAF", 4), vt::env_float("VT_TRAV_COST", 1.0f));
+    if (nodes) {
+        if (*node_count < bvh.nodes.size()) throw std::runtime_error("node buffer too small");
+        std::memcpy(nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(vt_node));
+        if (prim_indices) std::memcpy(prim_indices, bvh.prim_indices.data(), bvh.prim_indices.size() * sizeof(uint64_t));
+    }
+    *node_count = bvh.nodes.size();
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_build_bvh_ploc(const vt_scene *scene, int collapse, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices) {
+    VT_TRY
+    if (!scene || !node_count) throw std::runtime_error("null argument");
+    std::vector<vt::Triangle> tris(scene->n_tris);
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)scene->n_tris; i++) {
+        const vt_tri_in &in = scene->tris[i];
+        tris[i] = vt::Triangle(in.p[0], in.p[1], in.p[2], in.material, in.uvs, in.one_sided != 0);
+    }
+    vt::HostBvh bvh;
+    vt::build_bvh_ploc(tris, bvh);
+    if (collapse) vt::collapse_leaves(bvh);
     if (nodes) {
         if (*node_count < bvh.nodes.size()) throw std::runtime_error("node buffer too small");
         std::memcpy(nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(vt_node));

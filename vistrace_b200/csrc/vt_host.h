@@ -48,6 +48,10 @@ struct FlatBvh {
 };
 
 void build_bvh(const std::vector<Triangle> &tris, HostBvh &out, int max_leaf, float trav_cost);
+// The reference's own hierarchy rebuilt from its algorithm (vt_bvh_ploc.cpp): bvh::LocallyOrderedClusteringBuilder<BVH, uint32_t>
+// (search radius 14, 30-bit Morton codes) and bvh::LeafCollapser, the sequence of source/objects/AccelStruct.cpp:762-770.
+void build_bvh_ploc(const std::vector<Triangle> &tris, HostBvh &out);
+bool collapse_leaves(HostBvh &bvh);
 // bvh::HierarchyRefitter over moved geometry of unchanged topology (hierarchy_refitter.hpp:20-31): node boxes only.
 bool refit_bvh(const std::vector<Triangle> &tris, HostBvh &bvh, std::string &err);
 bool flatten_bvh(const HostBvh &bvh, uint64_t n_tris, uint32_t bfs_pairs, FlatBvh &out, std::string &err);
