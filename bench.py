@@ -231,8 +231,11 @@ def run_ours(args):
     rays = primary_rays()
     n = len(rays)
     accel = vt.Accel(local_rank)
+    build = vt.build_bvh_ploc if args.builder == "ploc" else vt.build_bvh
     if world > 1:  # the hierarchy is built once (rank 0) and replicated over NCCL; every GPU holds the whole scene
-        accel.populate(scene, bvh=shard.replicate_bvh(vt.build_bvh(scene) if rank == 0 else None, device=dev))
+        accel.populate(scene, bvh=shard.replicate_bvh(build(scene) if rank == 0 else None, device=dev))
+    elif args.builder == "ploc":
+        accel.populate(scene, bvh=build(scene))
     else:
         accel.populate(scene)
     st = accel.stats()
@@ -427,7 +430,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": rays_per_step, "parallelism": f"replicated hierarchy, {world} x ray/sample shard", "numa_node": numa,
                    "l2": "no explicit flush: one step streams ~0.6 GB of ray/hit/attribute buffers and walks a 0.5 GB hierarchy, both > 126 MB L2",
-                   "hierarchy": f"product builder (binned SAH), {accel.layout} node layout"},
+                   "hierarchy": ("reference-identical PLOC + LeafCollapser (vt_build_bvh_ploc)" if args.builder == "ploc" else "product builder (binned SAH)")
+                                + f", {accel.layout} node layout"},
         "clocks": clocks.summary(),
         "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                 "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3), "call": e2e_call, "all_hit_records_variant": hits_variant},
@@ -457,6 +461,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-stride", type=int, default=1, help="reference arm: trace every n-th pixel per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--builder", default="product", choices=["product", "ploc"],
+                    help="hierarchy of our arm: the product's binned-SAH builder (default, the headline) or the bit-identical "
+                         "restatement of the reference's PLOC + LeafCollapser build (the tree the reference arm traverses)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
