@@ -1,6 +1,4 @@
 #!/bin/bash
-O=gpurun_out/sZ; mkdir -p $O
-for lay in quad exact; do
-  echo "== builder=ploc layout=$lay"; VT_LAYOUT=$lay timeout 600 python bench.py --builder ploc --steps 10 --warmup 3 --no-cpu 2> $O/err_$lay.log | tee $O/bench_ploc_$lay.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['roofline']['node_visits_per_ray'], d['roofline']['tri_tests_per_ray'], d['roofline']['kernel_ms'], d['config']['hierarchy'])"
-  tail -1 $O/err_$lay.log
-done
+O=gpurun_out/s12; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
+timeout 600 python bench.py --steps 20 --warmup 3 > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; python -c "import json; d=json.load(open('$O/bench.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['cpu_baseline']['value'], d['config']['hierarchy'])"

@@ -26,6 +26,7 @@
 #include <cstring>
 #include <limits>
 #include <numeric>
+#include <parallel/algorithm>
 
 #include "vt_host.h"
 
@@ -110,9 +111,13 @@ void build_bvh_ploc(const std::vector<Triangle> &tris, HostBvh &out) {
         }
         codes[i] = morton_split(c[0]) | (morton_split(c[1]) << 1) | (morton_split(c[2]) << 2);
     }
+    // stable by code = plain sort of the unique keys (code << 32 | original index); libstdc++'s OpenMP parallel sort
     std::vector<uint64_t> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return codes[a] < codes[b]; });
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; i++) order[i] = ((uint64_t)codes[i] << 32) | (uint64_t)i;
+    __gnu_parallel::sort(order.begin(), order.end());
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; i++) order[i] &= 0xFFFFFFFFull;
 
     // ---- leaves at the end of the array, then level after level of clustering towards index 0
     const size_t node_count = 2 * n - 1;
