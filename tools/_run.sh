@@ -1,3 +1,5 @@
 #!/bin/bash
-O=gpurun_out/parity; mkdir -p $O; rm -f $O/parity.jsonl
-timeout 200 python tools/parity_report.py --configs 1,2,4,3,5 --out $O/parity.jsonl > $O/parity.log 2>&1; echo "rc=$?"; tail -3 $O/parity.log | cut -c1-400
+# Scratch driver for one-off gpurun sessions (the sessions of this round are summarised in profiles/).
+# Standard session: tools/gpu_session.sh <tag>; A/B of -D builds: tools/build_variants.sh + tools/ab_variants.sh;
+# full-size correctness report: tools/parity_report.py; per-config timings: tools/config_sweep.py.
+bash tools/gpu_session.sh "${1:-scratch}"
