@@ -567,6 +567,7 @@ void AccelStruct::PopulateWithBvh(const vt_scene &scene, const vt_node *nodes, u
 }
 
 const HostBvh &AccelStruct::Bvh() const {
+    std::lock_guard<std::mutex> lock(mBvhMutex);
     if (mBvhStale) {
         std::string err;
         if (!refit_bvh(mTriangles, mAccel, err)) throw std::runtime_error(err);

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "../../include/vistrace_b200.h"
@@ -114,7 +115,8 @@ class AccelStruct {
     int mWantLayout = VT_LAYOUT_QUAD;  // layout requested for the next Populate (VT_LAYOUT_*)
     int mLayout = VT_LAYOUT_EXACT;     // node layout resident on the device
     mutable HostBvh mAccel;
-    mutable bool mBvhStale = false;  // a device-side refit moved the boxes; the host copy is refitted on demand
+    mutable bool mBvhStale = false;
+    mutable std::mutex mBvhMutex;  // guards the lazy host-side refit in Bvh()  // a device-side refit moved the boxes; the host copy is refitted on demand
     std::vector<Triangle> mTriangles;
     std::vector<Entity> mEntities;
     std::vector<Material> mMaterials;
