@@ -90,3 +90,63 @@ def load_golden(name):
         texs.append((w, h, m, fl, z[f"tex{i}_px"]))
     scene = abi.SceneData(z["tris"], z["materials"], z["entities"], texs)
     return scene, z
+
+
+def cornell_box():
+    """The bvh library's golden-image known answer (libs/bvh/test/CMakeLists.txt:57-82, benchmark.cpp:121-176,451-463):
+    (SceneData of the 36 Cornell-box triangles, the 1080 x 720 camera rays of `--eye 0 0.9 2.5 --dir 0 0.001 -1 --up 0 1 0 --fov 60`
+    in the benchmark's float arithmetic, a function hits -> uint8 image, the reference picture)."""
+    from vistrace_b200 import abi
+
+    f4 = np.float32
+    g = np.load(os.path.join(GOLDEN, "cornell_box.npz"))
+    tris = np.zeros(len(g["p"]), abi.TRI_IN)
+    tris["p"] = g["p"]
+    tris["normals"][:, :, 2] = 1.0
+    tris["tangents"][:, :, 0] = 1.0
+    scene = abi.SceneData(tris)  # two-sided, one flag-free material: TriangleBackfaceCull degenerates to bvh::Triangle::intersect
+
+    def dot(a, b):
+        d = a[..., 0] * b[..., 0]
+        d = d + a[..., 1] * b[..., 1]
+        return d + a[..., 2] * b[..., 2]
+
+    def normalize(v):  # vector.hpp:151-154: v * (1 / sqrt(dot))
+        return (v * (f4(1) / np.sqrt(dot(v, v)))[..., None]).astype(f4)
+
+    def cross(a, b):  # vector.hpp:159-167
+        return np.stack([a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1], a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2],
+                         a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]], -1).astype(f4)
+
+    W, H = 1080, 720
+    eye, cdir, up, fov = np.array([0, 0.9, 2.5], f4), np.array([0, 0.001, -1], f4), np.array([0, 1, 0], f4), f4(60)
+    d = normalize(cdir)
+    iu = normalize(cross(d, up))
+    iv = normalize(cross(iu, d))
+    iw = f4(np.tan(np.float64(fov * f4(3.14159265 * (1.0 / 180.0) * 0.5))))
+    ratio = f4(H) / f4(W)
+    iu = (iu * iw).astype(f4)
+    iv = ((iv * iw).astype(f4) * ratio).astype(f4)
+    i = np.arange(W, dtype=f4)[None, :]
+    j = np.arange(H, dtype=f4)[:, None]
+    u = (f4(2) * (i + f4(0.5)) / f4(W) - f4(1)).astype(f4) + np.zeros((H, 1), f4)
+    v = (f4(2) * (j + f4(0.5)) / f4(H) - f4(1)).astype(f4) + np.zeros((1, W), f4)
+    dirs = normalize(((iu[None, None, :] * u[..., None]).astype(f4) + (iv[None, None, :] * v[..., None]).astype(f4)).astype(f4) + d[None, None, :])
+    rays = np.zeros(W * H, abi.RAY)  # index = W * j + i
+    rays["o"] = eye
+    rays["d"] = dirs.reshape(-1, 3)
+    rays["tmin"] = 0.0
+    rays["tmax"] = np.finfo(f4).max
+
+    p = g["p"]
+    n = cross(p[:, 0] - p[:, 1], p[:, 2] - p[:, 0])  # Triangle: e1 = p0 - p1, e2 = p2 - p0, n = cross(e1, e2)
+    shade = np.abs(normalize(n))
+
+    def to_image(hits):
+        px = np.zeros((W * H, 3), f4)
+        hit = hits["prim"] != abi.VT_MISS
+        px[hit] = shade[hits["prim"][hit]]
+        img = np.maximum(np.minimum(px * f4(255), f4(255)), f4(0)).astype(np.uint8).reshape(H, W, 3)
+        return img[::-1]  # the benchmark writes row j = height - 1 first
+
+    return scene, rays, to_image, g["image"]

@@ -85,8 +85,35 @@ def golden_vtf():
     print("vtf_small", {k: v.shape for k, v in out.items() if k.startswith("want_")})
 
 
+def golden_cornell():
+    """The bvh library's own golden-image test (libs/bvh/test/CMakeLists.txt:57-82): the Cornell box of libs/bvh/test/scene,
+    triangulated as libs/bvh/test/obj.hpp:57-95 does (fans), and the reference picture every builder must reproduce."""
+    from PIL import Image
+
+    root = "/root/reference/libs/bvh/test/scene"
+    verts, tris = [], []
+    for line in open(os.path.join(root, "cornell_box.obj")):
+        tok = line.split()
+        if not tok or tok[0].startswith("#"):
+            continue
+        if tok[0] == "v":
+            verts.append([np.float32(x) for x in tok[1:4]])
+        elif tok[0] == "f":
+            idx = [int(t.split("/")[0]) for t in tok[1:]]
+            pts = [verts[len(verts) + i if i < 0 else i - 1] for i in idx]
+            p0, p1 = pts[0], pts[1]
+            for v in pts[2:]:
+                tris.append([p0, p1, v])
+                p1 = v
+    image = np.asarray(Image.open(os.path.join(root, "cornell_box_reference.png")).convert("RGB"), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "cornell_box.npz"), p=np.asarray(tris, np.float32), image=image)
+    print("cornell_box", len(tris), "triangles, image", image.shape)
+
+
 def main():
     assert oracle.available("reference"), "build oracle/_ref first: make -C oracle ref"
+    if sys.argv[1:] == ["cornell"]:
+        return golden_cornell()
     if sys.argv[1:] == ["skin"]:
         return golden_skin()
     if sys.argv[1:] == ["vtf"]:
@@ -114,6 +141,7 @@ def main():
     print("kat node", entry, exit_)
     golden_skin()
     golden_vtf()
+    golden_cornell()
 
 
 if __name__ == "__main__":

@@ -577,6 +577,23 @@ def test_refit_moved_props(vt, oracle_mod, kind, layout, path, monkeypatch):
         accel.refit(abi.SceneData(moved.tris[:-1], moved.materials, moved.entities))
 
 
+@pytest.mark.parametrize("builder", ["product", "ploc"])
+def test_cornell_box_golden_image_of_the_bvh_library(vt, layout, builder, monkeypatch):
+    """The bvh library's golden-image test (libs/bvh/test/CMakeLists.txt:57-82: every builder must reproduce
+    scene/cornell_box_reference.png with the benchmark's camera) through the CUDA path, on every node layout, over the product's
+    tree and over the rebuilt PLOC + LeafCollapser tree.  tests/test_oracle.py holds the same check for the CPU checkers."""
+    from conftest import cornell_box
+
+    scene, rays, to_image, want = cornell_box()
+    if builder == "ploc":
+        monkeypatch.setenv("VT_BUILDER", "ploc")
+    accel = vt.Accel(0, layout=layout).populate(scene)
+    assert accel.layout == layout
+    img = to_image(accel.traverse(rays))
+    differing = int((img != want).any(-1).sum())
+    assert differing <= 8, f"{differing} of {want.shape[0] * want.shape[1]} pixels differ from the golden image"
+
+
 @pytest.mark.parametrize("scene_name", ["props", "duplicates"])
 def test_ploc_builder_gives_the_reference_answers_ties_included(vt, oracle_mod, scene_name, monkeypatch):
     """VT_BUILDER=ploc + exact layout: the engine builds the reference's own hierarchy (vt_bvh_ploc.cpp) and, with the reference's

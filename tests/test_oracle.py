@@ -204,3 +204,26 @@ def test_port_matches_reference_on_every_shading_branch(oracle_mod):
     lod = a["base_mip"][hit & (cones[:, 0] >= 0)]
     assert (lod > 0).any() and not (a["albedo"] == want["attrs"]["albedo"]).all()  # the cones change the sampled mip
     assert len(np.unique(a["metalness"][hit])) > 10 and (a["flags"][hit] & 4).any()  # MRAO sampled, water hit
+
+
+@pytest.mark.parametrize("kind", ["reference", "port"])
+def test_cornell_box_golden_image_of_the_bvh_library(built, oracle_mod, kind):
+    """libs/bvh/test/CMakeLists.txt:57-82: every builder of the library must reproduce scene/cornell_box_reference.png with the
+    benchmark's camera (shading = |normalised triangle normal|).  Both checkers do, over the reference's PLOC + LeafCollapser tree
+    (reference kind: built by the library itself; port: the product's bit-identical rebuild of it) and over the product's SAH tree."""
+    import vistrace_b200 as vt
+    from conftest import cornell_box
+
+    if not oracle_mod.available(kind):
+        pytest.skip(f"oracle kind {kind} not built")
+    scene, rays, to_image, want = cornell_box()
+    trees = [vt.build_bvh_ploc(scene), vt.build_bvh(scene)]
+    if kind == "reference":
+        trees.insert(0, None)  # the library's own build
+    for tree in trees:
+        cpu = oracle_mod.CpuScene(scene, kind, build_bvh=tree is None)
+        if tree is not None:
+            cpu.set_bvh(*tree)
+        img = to_image(cpu.traverse(rays)["hits"])
+        differing = int((img != want).any(-1).sum())
+        assert differing <= 8, f"{differing} of {want.shape[0] * want.shape[1]} pixels differ from the golden image"
