@@ -65,6 +65,7 @@ def _lib(kind):
     }
     if kind != "port":  # reference only: its VTF parser is not restated in the C port (the product's decoder is checked against it)
         sig["vtf_pixels"] = (C.c_int64, [vp, u64, C.c_uint32, C.c_uint32, vp, u64])
+        sig["reinsertion_optimize"] = (None, [vp, vp])
     ns = type("ns", (), {})()
     for name, (res, args) in sig.items():
         fn = getattr(lib, pre + name)
@@ -128,6 +129,12 @@ class CpuScene:
         assert scene.n_tris == self.n_tris
         self.scene = scene
         self.lib.refit(self.h, C.cast(scene.ptr(), C.c_void_p))
+
+    def reinsertion_optimize(self):
+        """Reference kind only: bvh::ParallelReinsertionOptimizer over the current hierarchy -> (SAH cost before, after)."""
+        c = np.zeros(2, np.float64)
+        self.lib.reinsertion_optimize(self.h, c.ctypes.data)
+        return float(c[0]), float(c[1])
 
     def traverse(self, rays, want_attrs=False, threads=0, want_stats=False):
         """Returns dict(hits, attrs?, seconds, steps?, isects?)."""

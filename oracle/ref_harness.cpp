@@ -42,6 +42,7 @@
 #include "bvh/leaf_collapser.hpp"
 #include "bvh/locally_ordered_clustering_builder.hpp"
 #include "bvh/node_intersectors.hpp"
+#include "bvh/parallel_reinsertion_optimizer.hpp"
 
 #include "../include/vistrace_b200.h"
 
@@ -281,6 +282,29 @@ int64_t vtref_vtf_pixels(const uint8_t *file, uint64_t size, uint32_t frame, uin
             }
     }
     return (int64_t)n;
+}
+
+// Experiment hook (tools/reinsertion_probe.py): the library's bvh::ParallelReinsertionOptimizer over the CURRENT hierarchy — how
+// much traversal work would a reinsertion pass in the product's builder save?  Returns the SAH cost before and after.
+void vtref_reinsertion_optimize(void *h, double *cost_before_after) {
+    AccelStruct &a = static_cast<RefScene *>(h)->accel;
+    if (!a.mAccelBuilt) throw std::runtime_error("vtref_reinsertion_optimize: nothing built");
+    auto sah_cost = [&]() {  // SahBasedAlgorithm::compute_cost (sah_based_algorithm.hpp:20-35; protected there), traversal cost 1
+        double cost = 0;
+        for (size_t i = 0; i < a.mAccel.node_count; i++) {
+            const auto &n = a.mAccel.nodes[i];
+            cost += (double)n.bounding_box_proxy().half_area() * (n.is_leaf() ? (double)n.primitive_count : 1.0);
+        }
+        return cost / (double)a.mAccel.nodes[0].bounding_box_proxy().half_area();
+    };
+    bvh::ParallelReinsertionOptimizer<BVH> optimizer(a.mAccel);
+    if (cost_before_after) cost_before_after[0] = sah_cost();
+    optimizer.optimize();
+    if (cost_before_after) cost_before_after[1] = sah_cost();
+    delete a.mpIntersector;
+    delete a.mpTraverser;
+    a.mpIntersector = new Intersector(a.mAccel, a.mTriangles.data());
+    a.mpTraverser = new Traverser(a.mAccel);
 }
 
 // Moved geometry, same topology: rebuild mTriangles from `s` and refit the CURRENT hierarchy with the reference
