@@ -475,3 +475,44 @@ def test_ploc_builder_reproduces_the_reference_hierarchy(built, oracle_mod, scen
     if scene.n_tris > 2:  # and it is a hierarchy the engine accepts: every triangle once, depth within the stack
         flat = vt.flatten_bvh(nodes, prims, 0)
         assert sorted(flat["leaf_order"].tolist()) == list(range(scene.n_tris))
+
+
+def test_ploc_builder_random_scenes(built, oracle_mod):
+    """Seeded fuzz against the reference's build: triangle soups, duplicated and degenerate triangles, far-apart clusters, huge
+    coordinates — identical arrays.  A scene with a zero-extent axis makes the REFERENCE convert NaN to unsigned (undefined
+    behaviour, morton.hpp:52-57), so there only validity and determinism of our tree are checked."""
+    import vistrace_b200 as vt
+    from vistrace_b200 import abi
+
+    rng = np.random.default_rng(123)
+    kinds = ["soup", "duplicates", "degenerate", "clustered", "huge", "flat"]
+    for it in range(90):
+        kind = kinds[it % len(kinds)]
+        n = int(rng.integers(1, 300))
+        p = rng.uniform(-50, 50, (n, 3, 3)).astype(np.float32)
+        if kind == "duplicates":
+            p = np.concatenate([p, p[: n // 2], p[: n // 3]])
+        elif kind == "degenerate":
+            p[::3, 1] = p[::3, 0]
+            p[::5, 2] = p[::5, 0]
+        elif kind == "clustered":
+            p = (p * 0.001 + rng.integers(0, 3, (len(p), 1, 1)) * 1000).astype(np.float32)
+        elif kind == "huge":
+            p = (p * 1e6).astype(np.float32)
+        elif kind == "flat":
+            p[:, :, 2] = 3.0
+        tris = np.zeros(len(p), abi.TRI_IN)
+        tris["p"] = p
+        scene = abi.SceneData(tris)
+        nodes, prims = vt.build_bvh_ploc(scene)
+        if kind == "flat":
+            again = vt.build_bvh_ploc(scene)
+            assert nodes.tobytes() == again[0].tobytes() and prims.tobytes() == again[1].tobytes()
+            assert sorted(prims.tolist()) == list(range(len(p)))
+            leaves = nodes[nodes["prim_count"] > 0]
+            assert int(leaves["prim_count"].sum()) == len(p)
+            continue
+        if not oracle_mod.available("reference"):
+            continue
+        want_nodes, want_prims = oracle_mod.CpuScene(scene, "reference", build_bvh=True).get_bvh()
+        assert nodes.tobytes() == want_nodes.tobytes() and prims.tobytes() == want_prims.tobytes(), (it, kind, len(p))
