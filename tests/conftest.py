@@ -150,3 +150,45 @@ def cornell_box():
         return img[::-1]  # the benchmark writes row j = height - 1 first
 
     return scene, rays, to_image, g["image"]
+
+
+def hostile_case(it, rng, n_rays=3000):
+    """One seeded hostile scene + ray set (kind = it % 6: soup, zero-area, grid-aligned, duplicated, coplanar layers, soup again):
+    rays with zero / negative-zero / tiny / huge direction components, grid-aligned origins and directions for the grid kind,
+    finite and infinite intervals.  Shared by the oracle fuzz (tests/test_oracle.py) and the GPU fuzz (tests/test_gpu_parity.py)."""
+    from vistrace_b200 import abi
+
+    n = int(rng.integers(1, 300))
+    p = rng.uniform(-20, 20, (n, 3, 3)).astype(np.float32)
+    kind = it % 6
+    if kind == 1:
+        p[::3, 1] = p[::3, 0]
+    elif kind == 2:
+        p = np.round(p)
+    elif kind == 3:
+        p = np.concatenate([p, p])
+    elif kind == 4:
+        p[:, :, 2] = np.round(p[:, :, 2] / 10) * 10
+    tris = np.zeros(len(p), abi.TRI_IN)
+    tris["p"] = p
+    tris["normals"] = rng.normal(size=(len(p), 3, 3))
+    tris["tangents"] = rng.normal(size=(len(p), 3, 3))
+    tris["uvs"] = rng.uniform(-2, 2, (len(p), 3, 2))
+    tris["alphas"] = rng.uniform(0, 1, (len(p), 3))
+    tris["one_sided"] = rng.integers(0, 2, len(p))
+    scene = abi.SceneData(tris)
+    m = n_rays
+    rays = np.zeros(m, abi.RAY)
+    rays["o"] = rng.uniform(-25, 25, (m, 3))
+    rays["d"] = rng.normal(size=(m, 3))
+    if kind == 2:
+        rays["o"] = np.round(rays["o"])
+        rays["d"] = np.round(rays["d"] * 2) / 2
+    rays["d"][::7, 0] = 0.0
+    rays["d"][::11, 1] = -0.0
+    rays["d"][::13] *= 1e-3
+    rays["d"][::17] *= 1e4
+    rays["tmin"] = np.where(rng.random(m) < 0.3, rng.uniform(0, 5, m), 0)
+    rays["tmax"] = np.where(rng.random(m) < 0.3, rng.uniform(5, 60, m), np.finfo(np.float32).max)
+    rays["d"][(rays["d"] == 0).all(1), 2] = 1.0
+    return scene, rays, kind

@@ -577,6 +577,42 @@ def test_refit_moved_props(vt, oracle_mod, kind, layout, path, monkeypatch):
         accel.refit(abi.SceneData(moved.tris[:-1], moved.materials, moved.entities))
 
 
+def test_hostile_random_inputs(vt, oracle_mod, layout):
+    """The seeded hostile scenes of tests/test_oracle.py through the CUDA path: zero-area, grid-aligned, duplicated and coplanar
+    triangles; rays with zero / -0.0 / tiny / huge direction components, through vertices and along edges.  Exact layout: the
+    checker's hit buffer byte for byte; quantised layouts: up to counted ties / verified reference leaks (same_hits)."""
+    from conftest import hostile_case
+    from vistrace_b200 import abi
+
+    kind_name = "reference" if oracle_mod.available("reference") else "port"
+    rng = np.random.default_rng(99)
+    for it in range(12):
+        scene, rays, kind = hostile_case(it, rng)
+        tree = vt.build_bvh_ploc(scene) if it % 2 else vt.build_bvh(scene)
+        accel = vt.Accel(0, layout=layout).populate(scene, bvh=tree)
+        cpu = oracle_mod.CpuScene(scene, kind_name, build_bvh=False)
+        cpu.set_bvh(*tree)
+        got, want = accel.traverse(rays), cpu.traverse(rays)["hits"]
+        if accel.layout == "exact":  # also where a quantised layout fell back to exact (e.g. a root leaf it cannot hold)
+            assert got.tobytes() == want.tobytes(), (it, kind)
+        else:
+            rep = compare_hits(got, want)
+            assert rep["tuv_bit_mismatch"] == 0, (it, kind, rep)
+            # every differing record is a tie, or a candidate the checker's own triangle test accepts with exactly these
+            # (t, u, v) but its traverser never reached (a box test rounded the ray out: see same_hits) — any number of them here,
+            # the inputs are built to sit on edges and vertices
+            diff = np.nonzero((got.view(np.uint32).reshape(-1, 4) != want.view(np.uint32).reshape(-1, 4)).any(1))[0]
+            for j in diff:
+                g, w = got[j], want[j]
+                g_hit, w_hit = g["prim"] != abi.VT_MISS, w["prim"] != abi.VT_MISS
+                if g_hit and w_hit and abs(float(g["t"]) - float(w["t"])) <= 1e-6 * abs(float(w["t"])):
+                    continue
+                assert g_hit and (not w_hit or g["t"] < w["t"]), (it, kind, j, g, w)  # never the other way round
+                ok, tuv = cpu.tri_intersect(int(g["prim"]), rays[j])
+                assert ok and tuv.tobytes() == np.array([g["t"], g["u"], g["v"]], np.float32).tobytes(), (it, kind, j, g, w)
+        accel.close()
+
+
 @pytest.mark.parametrize("builder", ["product", "ploc"])
 def test_cornell_box_golden_image_of_the_bvh_library(vt, layout, builder, monkeypatch):
     """The bvh library's golden-image test (libs/bvh/test/CMakeLists.txt:57-82: every builder must reproduce

@@ -234,46 +234,15 @@ def test_port_equals_reference_on_random_hostile_inputs(built, oracle_mod):
     one- and two-sided; rays with zero / negative-zero / tiny / huge direction components, through vertices and along edges,
     finite and infinite intervals.  Hit records, TraceResult records (NaNs included) and both statistics counters: byte for byte."""
     import vistrace_b200 as vt
-    from vistrace_b200 import abi
 
     if not (oracle_mod.available("reference") and oracle_mod.available("port")):
         pytest.skip("needs both checkers")
+    from conftest import hostile_case
+
     rng = np.random.default_rng(99)
     for it in range(18):
-        n = int(rng.integers(1, 300))
-        p = rng.uniform(-20, 20, (n, 3, 3)).astype(np.float32)
-        kind = it % 6
-        if kind == 1:
-            p[::3, 1] = p[::3, 0]
-        elif kind == 2:
-            p = np.round(p)
-        elif kind == 3:
-            p = np.concatenate([p, p])
-        elif kind == 4:
-            p[:, :, 2] = np.round(p[:, :, 2] / 10) * 10
-        tris = np.zeros(len(p), abi.TRI_IN)
-        tris["p"] = p
-        tris["normals"] = rng.normal(size=(len(p), 3, 3))
-        tris["tangents"] = rng.normal(size=(len(p), 3, 3))
-        tris["uvs"] = rng.uniform(-2, 2, (len(p), 3, 2))
-        tris["alphas"] = rng.uniform(0, 1, (len(p), 3))
-        tris["one_sided"] = rng.integers(0, 2, len(p))
-        scene = abi.SceneData(tris)
+        scene, rays, kind = hostile_case(it, rng)
         tree = vt.build_bvh_ploc(scene) if it % 2 else vt.build_bvh(scene)
-        m = 3000
-        rays = np.zeros(m, abi.RAY)
-        rays["o"] = rng.uniform(-25, 25, (m, 3))
-        rays["d"] = rng.normal(size=(m, 3))
-        if kind == 2:
-            rays["o"] = np.round(rays["o"])
-            rays["d"] = np.round(rays["d"] * 2) / 2
-        rays["d"][::7, 0] = 0.0
-        rays["d"][::11, 1] = -0.0
-        rays["d"][::13] *= 1e-3
-        rays["d"][::17] *= 1e4
-        rays["tmin"] = np.where(rng.random(m) < 0.3, rng.uniform(0, 5, m), 0)
-        rays["tmax"] = np.where(rng.random(m) < 0.3, rng.uniform(5, 60, m), np.finfo(np.float32).max)
-        rays["d"][(rays["d"] == 0).all(1), 2] = 1.0
         out = {}
         for k in ("reference", "port"):
             cpu = oracle_mod.CpuScene(scene, k, build_bvh=False)
