@@ -198,6 +198,11 @@ typedef struct vt_attr {
 
 typedef struct vt_accel vt_accel; /* opaque; replaces AccelStruct (source/objects/AccelStruct.h:61-86) */
 
+/* Threading contract.  The reference object is used from one thread (the game's Lua thread, source/VisTrace.cpp:831-836).
+ * Here: a handle may be used from ONE thread at a time for every call that takes HOST pointers (they share per-handle
+ * staging buffers) and for populate / refit; calls with VT_TRAVERSE_DEVICE_PTRS may be issued concurrently from several
+ * threads when each uses its own stream.  Different handles are independent. */
+
 /* Number of CUDA devices visible; <0 on error. */
 int vt_device_count(void);
 
@@ -421,6 +426,66 @@ uint32_t vt_quad_plane_offset(void);
 int vt_build_quads(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris,
                    void *quads_out, uint64_t *n_quads, uint32_t *leaf_order_out, uint32_t *root_leaf_count,
                    uint32_t *max_stack);
+
+/* ------------------------------------------------------------------ multi-GPU
+ * The reference is single-threaded CPU code with no multi-device notion; the north star shards ray
+ * batches over the GPUs of one box behind the same object: the hierarchy is built ONCE, its device image is replicated on
+ * every GPU (the scene is read-only and far smaller than 180 GB), rays are partitioned, and the only communication is the
+ * final gather of hit-buffer slices or framebuffer tiles.  vt_group stands for "one AccelStruct
+ * (source/objects/AccelStruct.h:61-86) resident on several GPUs".
+ *
+ *   vt_group_create(devices, n)        one process drives n local GPUs (a worker thread per GPU; every GPU reads its share of
+ *                                      the caller's host buffers and writes its results straight back over its own PCIe link;
+ *                                      replication by cudaMemcpyPeer).
+ *   vt_group_create_rank(dev, r, w, id)  one process per GPU (torchrun / MPI style): `id` is the 128-byte ncclUniqueId that
+ *                                      rank 0 obtained from vt_group_unique_id() and the launcher distributed.  Rank 0 builds,
+ *                                      the image is ncclBroadcast, results are gathered on rank 0 over NVLink (ncclSend / ncclRecv).
+ *                                      NCCL is bound at run time (libnccl.so.2 via dlopen; VT_NCCL_LIB overrides the name).
+ * Every call on a multi-process group is COLLECTIVE: all ranks call it with the same n / spp / seed / flags. */
+typedef struct vt_group vt_group;
+int vt_group_unique_id(uint8_t id[128]);
+vt_group *vt_group_create(const int *devices, int n);
+vt_group *vt_group_create_rank(int device, int rank, int world, const uint8_t id[128]);
+void vt_group_destroy(vt_group *group);
+int vt_group_size(const vt_group *group);          /* GPUs in the group (world size) */
+int vt_group_rank(const vt_group *group);          /* global rank of this process's first member */
+int vt_group_local_members(const vt_group *group); /* members driven by this process */
+vt_accel *vt_group_accel(vt_group *group, int local_member); /* borrowed; members other than the builder are replicas (no refit / get_bvh) */
+
+/* AccelStruct::PopulateAccel (source/objects/AccelStruct.cpp:533-776) for the whole group: ingest + build + flatten once,
+ * replicate the device image.  Multi-process groups: only rank 0 reads `scene` (the others may pass NULL). */
+int vt_group_populate(vt_group *group, const vt_scene *scene);
+
+/* Batched AccelStruct::Traverse (source/objects/AccelStruct.cpp:778-838) over the group: contiguous, balanced slices of
+ * rays[0, n) — rank r traces [r * n / w ...) — HOST pointers.  Single process: hits / attrs are complete on return.
+ * Multi-process: every rank passes frame-sized arrays and reads only its own slice of `rays`; the slices are gathered on
+ * rank 0 over NVLink and downloaded there (rank 0: complete arrays; other ranks: their own slice). */
+int vt_group_traverse(vt_group *group, const vt_ray *rays, uint64_t n, vt_hit *hits, vt_attr *attrs, uint32_t flags);
+
+/* Frame sharding used by vt_group_render_diffuse_wave: the frame of n pixels is cut into tiles of *tile pixels dealt
+ * round-robin to the ranks (tile g belongs to rank g % w); *local_count = pixels of `rank`, stored compactly in tile order. */
+int vt_group_shard(const vt_group *group, uint64_t n, int rank, uint64_t *tile, uint64_t *local_count);
+
+/* Host-only (no GPU touched): the same geometry for any (world, rank, tile) — what a launcher needs to lay out per-rank buffers. */
+int vt_shard_geometry(uint64_t n, int world, int rank, uint64_t tile, uint64_t *local_count, uint64_t *local_tiles);
+
+/* vt_accel_render_diffuse_wave over the group, STRONG scaling of one frame: every pixel is traced exactly once, by the rank
+ * that owns its tile, and the image equals the single-GPU image bit for bit (the bounce rays' random-number counters come
+ * from global pixel indices).  flags = 0: HOST rays[n] in, HOST RGBFFF framebuffer_rgb[3n] out (include/vistrace/IRenderTarget.h:40),
+ * complete on return in a single-process group and on rank 0 of a multi-process group (other ranks receive their own tiles);
+ * *live_out (nullable) = bounce rays spawned by THIS process's GPUs.
+ * flags = VT_TRAVERSE_DEVICE_PTRS (multi-process groups): rays = this rank's COMPACT shard already resident on its GPU
+ * (vt_group_shard: local_count records in tile order), framebuffer_rgb = frame-sized DEVICE image, complete on rank 0; everything
+ * is enqueued on `stream` and the call returns without synchronising; live_out must be NULL. */
+int vt_group_render_diffuse_wave(vt_group *group, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight,
+                                 float *framebuffer_rgb, uint64_t *live_out, uint32_t flags, void *stream);
+
+/* Sample-index sharding (every rank renders the whole frame for its own samples): sum the per-rank DEVICE images into
+ * rank 0's, in place — one ncclReduce over NVLink, enqueued on `stream`.  Multi-process groups. */
+int vt_group_reduce_device(vt_group *group, float *buf, uint64_t count, void *stream);
+
+/* Kernel launches + collectives issued through the group so far. */
+uint64_t vt_group_launch_count(const vt_group *group);
 
 /* Last error message of the calling thread ("" if none). */
 const char *vt_last_error(void);

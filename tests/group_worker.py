@@ -1,0 +1,62 @@
+"""torchrun worker for test_multi_process_group_two_ranks_nccl: one process per GPU, native vt_group in rank mode."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import vistrace_b200 as vt  # noqa: E402
+from vistrace_b200 import scenes  # noqa: E402
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+uid = torch.from_numpy(vt.group_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+dist.broadcast(uid, src=0)  # the launcher's job: hand rank 0's ncclUniqueId to everybody
+group = vt.Group(device=local, rank=rank, world=world, unique_id=uid.cpu().numpy())
+scene = scenes.scene_heightfield(64)
+rays = scenes.pinhole_rays(333, 187, (0, -80, 60), (0, 0, 5))
+group.populate(scene if rank == 0 else None)  # rank 0 builds; everybody else receives the device image over NCCL
+n, spp = len(rays), 3
+
+hits, attrs = group.traverse(rays, want_attrs=True)
+os.environ["VT_GROUP_TILE"] = "1000"
+img, live = group.render_diffuse_wave(rays, spp, seed=9, weight=0.5)
+live_t = torch.tensor([live], dtype=torch.int64, device=dev)
+dist.all_reduce(live_t)
+
+# device-resident shards -> frame-sized device image on rank 0
+idx = group.shard_indices(n)
+d_rays = torch.from_numpy(np.ascontiguousarray(rays[idx]).view(np.uint8).reshape(-1).copy()).to(dev)
+d_fb = torch.full((n * 3,), -1.0, dtype=torch.float32, device=dev)
+group.render_diffuse_wave_device(d_rays.data_ptr(), n, spp, 9, 0.5, d_fb.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+
+# sample-index sharding: per-rank partial images summed on rank 0 with one ncclReduce
+part = torch.full((1000,), float(rank + 1), dtype=torch.float32, device=dev)
+group.reduce_device(part.data_ptr(), 1000, stream=torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+
+single = vt.Accel(local).populate(scene)  # each rank checks what it holds against its own single-GPU run
+want_hits, want_attrs = single.traverse(rays, want_attrs=True)
+want_img, want_live = single.render_diffuse_wave(rays, spp, seed=9, weight=0.5)
+if rank == 0:
+    assert hits.tobytes() == want_hits.tobytes() and attrs.tobytes() == want_attrs.tobytes(), "gathered hit buffer differs"
+    np.testing.assert_array_equal(img, want_img)
+    np.testing.assert_array_equal(d_fb.cpu().numpy().reshape(-1, 3), want_img)
+    assert int(live_t.item()) == want_live
+    assert float(part[0].item()) == sum(range(1, world + 1))
+else:  # a non-root rank holds its own slice / tiles
+    b = rank * (n // world) + min(rank, n % world)
+    e = b + n // world + (1 if rank < n % world else 0)
+    assert hits[b:e].tobytes() == want_hits[b:e].tobytes()
+    np.testing.assert_array_equal(img[idx], want_img[idx])
+dist.barrier()
+if rank == 0:
+    print("GROUP_OK", n, int(live_t.item()))
+group.close()
+dist.destroy_process_group()

@@ -99,3 +99,61 @@ def test_two_rank_gloo_shard_and_gather(built, tmp_path):
         spans.append((b, e))
         np.testing.assert_array_equal(f[2:].astype(np.float32).reshape(-1, 3), total[b:e])
     assert spans == [(0, 2501), (2501, 5001)]
+
+
+def _tile_worker(rank, world, port, out_dir):
+    """The frame sharding of the native group (vt_group.cu: tiles dealt round-robin, compact shards, gather on rank 0) with the
+    C port as the tracer and gloo as the fabric: the assembled frame must equal the frame traced whole."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    import vistrace_b200 as vt
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    scene, z = load_golden("props_small")
+    cpu = oracle.CpuScene(scene, "port", build_bvh=False)
+    cpu.set_bvh(z["nodes"], z["prim_indices"])
+    rays = z["rays"][:5001]
+    n, tile = len(rays), 512  # 10 tiles, the last one ragged (393 rays) and owned by rank 1
+    idx = vt.shard_indices(n, world, rank, tile)
+    mine = cpu.traverse(np.ascontiguousarray(rays[idx]), threads=1)["hits"]  # the compact shard, traced on its own
+    counts = [len(vt.shard_indices(n, world, r, tile)) for r in range(world)]
+    t = torch.from_numpy(mine.view(np.uint8).reshape(-1).copy())
+    if rank == 0:
+        frame = np.zeros(n, mine.dtype)
+        frame[idx] = mine
+        for r in range(1, world):
+            buf = torch.empty(counts[r] * mine.dtype.itemsize, dtype=torch.uint8)
+            dist.recv(buf, src=r)
+            frame[vt.shard_indices(n, world, r, tile)] = np.frombuffer(buf.numpy().tobytes(), mine.dtype)
+        np.save(os.path.join(out_dir, "tile_frame.npy"), frame.view(np.uint8))
+    else:
+        dist.send(t, dst=0)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_geometry_covers_every_record_once(built):
+    import vistrace_b200 as vt
+
+    for n in (0, 1, 511, 512, 513, 5001, 2073600):
+        for world in (1, 2, 3, 8):
+            for tile in (64, 512, 8192):
+                parts = [vt.shard_indices(n, world, r, tile) for r in range(world)]
+                allidx = np.concatenate(parts) if parts else np.zeros(0, np.int64)
+                assert np.array_equal(np.sort(allidx), np.arange(n)), (n, world, tile)
+                if n >= world * tile * 4:  # round-robin tiles: shards differ by at most one tile
+                    assert max(map(len, parts)) - min(map(len, parts)) <= tile
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_tile_sharded_frame(built, tmp_path):
+    port = _free_port()
+    mp.spawn(_tile_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    scene, z = load_golden("props_small")
+    want = z["hits"][:5001]
+    assert np.load(tmp_path / "tile_frame.npy").tobytes() == want.tobytes()

@@ -23,18 +23,19 @@ from vistrace_b200 import abi, scenes  # noqa: E402
 FLOAT_FIELDS = [f for f in abi.ATTR.names if abi.ATTR[f].base == np.float32 or abi.ATTR[f].subdtype and abi.ATTR[f].subdtype[0] == np.float32]
 
 
-def compare(got, want):
+def compare(got, want, rays=None, cpu=None):
+    """classify_hits (vistrace_b200/report.py) + the column names of SURVEY.md section 8d."""
+    from vistrace_b200.report import classify_hits
+
+    rep = classify_hits(got, want, rays, cpu.tri_intersect if cpu is not None else None)
     miss_g, miss_w = got["prim"] == abi.VT_MISS, want["prim"] == abi.VT_MISS
     both = ~miss_g & ~miss_w
-    diff = both & (got["prim"] != want["prim"])
-    tg, tw = got["t"].astype(np.float64), want["t"].astype(np.float64)
-    exact_tie = diff & (got["t"] == want["t"])
-    near_tie = diff & ~exact_tie & (np.abs(tg - tw) <= 1e-6 * np.abs(tw))
-    same = both & ~diff
-    bits = lambda f: got[f].view(np.uint32) != want[f].view(np.uint32)
-    return {"rays": int(len(got)), "hits": int((~miss_w).sum()), "hit_miss_mismatch": int((miss_g != miss_w).sum()), "prim_mismatch": int(diff.sum()),
-            "exact_tie": int(exact_tie.sum()), "near_tie": int(near_tie.sum()), "other": int((diff & ~exact_tie & ~near_tie).sum()),
-            "tuv_bit_mismatch_same_prim": int((same & (bits("t") | bits("u") | bits("v"))).sum())}
+    rep["hit_miss_mismatch"] = int((miss_g != miss_w).sum())
+    rep["prim_mismatch"] = int((both & (got["prim"] != want["prim"])).sum())
+    # "other" = a primitive / hit-miss difference that is neither an exact tie nor a checker-verified leak: a bug if non-zero
+    rep["other"] = rep["lost"] + rep["unverified"]
+    rep["tuv_bit_mismatch_same_prim"] = rep["tuv_bits"]
+    return rep
 
 
 def attr_err(got, want):
@@ -58,19 +59,29 @@ def config(cfg):
     return "config5 20M terrain + props, 4K: primary + shadow + bounce", scenes.scene_terrain_closed(2980, n_props=143), (3840, 2160), ((0.0, -330.0, 200.0), (0.0, 0.0, 10.0)), "shadow+bounce1"
 
 
-def run(cfg, engine_factory, kind, small=False):
+def run(cfg, engine_factory, kind, small=False, builder="product"):
+    """builder = "product": the engine's own tree, handed to the checker as well (same hierarchy on both sides);
+    builder = "ploc": the engine rebuilds the reference's PLOC + LeafCollapser tree (vt_build_bvh_ploc) while the reference
+    checker builds ITS OWN — nothing is handed over."""
     t0 = time.time()
     name, scene, (W, H), cam, secondary = config(cfg)
     if small:
         W, H = W // 8, H // 8
-    bvh = vt.build_bvh(scene)
+    if builder == "ploc":
+        bvh = vt.build_bvh_ploc(scene)
+        cpu = oracle.CpuScene(scene, kind, build_bvh=(kind == "reference"))
+        if kind != "reference":
+            cpu.set_bvh(*bvh)
+    else:
+        bvh = vt.build_bvh(scene)
+        cpu = oracle.CpuScene(scene, kind, build_bvh=False)
+        cpu.set_bvh(*bvh)
     engine = engine_factory(scene, bvh)
-    cpu = oracle.CpuScene(scene, kind, build_bvh=False)
-    cpu.set_bvh(*bvh)
     rays = scenes.pinhole_rays(W, H, *cam)
     hits, attrs = engine(rays, True)
     want = cpu.traverse(rays, want_attrs=True)
-    res = {"config": cfg, "name": name, "n_tris": int(scene.n_tris), "checker": kind, "primary": compare(hits, want["hits"]), "primary_attrs": attr_err(attrs, want["attrs"])}
+    res = {"config": cfg, "name": name, "n_tris": int(scene.n_tris), "checker": kind, "builder": builder, "primary": compare(hits, want["hits"], rays, cpu),
+           "primary_attrs": attr_err(attrs, want["attrs"]), "byte_identical": hits.tobytes() == want["hits"].tobytes()}
     waves = []
     if secondary:
         for part in secondary.split("+"):
@@ -82,7 +93,8 @@ def run(cfg, engine_factory, kind, small=False):
             sec = np.ascontiguousarray(sec[sec["tmax"] >= 0])
             g = engine(sec, False)
             w = cpu.traverse(sec)["hits"]
-            waves.append({part: compare(g, w)})  # shadow rays too are traced closest-hit here: every field is defined
+            waves.append({part: compare(g, w, sec, cpu)})  # shadow rays too are traced closest-hit here: every field is defined
+            res["byte_identical"] = res["byte_identical"] and g.tobytes() == w.tobytes()
     res["secondary"] = waves
     res["seconds"] = round(time.time() - t0, 1)
     cpu.close()

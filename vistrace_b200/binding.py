@@ -55,6 +55,21 @@ SYMBOLS = {
     "vt_accel_get_tri_derived": (_i32, [_vp, _vp]),
     "vt_build_bvh": (_i32, [_vp, _vp, _vp, _vp]),
     "vt_flatten_bvh": (_i32, [_vp, _u64, _vp, _u64, _u32, _vp, _vp, _vp, _vp]),
+    "vt_group_unique_id": (_i32, [_vp]),
+    "vt_group_create": (_vp, [_vp, _i32]),
+    "vt_group_create_rank": (_vp, [_i32, _i32, _i32, _vp]),
+    "vt_group_destroy": (None, [_vp]),
+    "vt_group_size": (_i32, [_vp]),
+    "vt_group_rank": (_i32, [_vp]),
+    "vt_group_local_members": (_i32, [_vp]),
+    "vt_group_accel": (_vp, [_vp, _i32]),
+    "vt_group_populate": (_i32, [_vp, _vp]),
+    "vt_group_traverse": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32]),
+    "vt_group_shard": (_i32, [_vp, _u64, _i32, _vp, _vp]),
+    "vt_shard_geometry": (_i32, [_u64, _i32, _i32, _u64, _vp, _vp]),
+    "vt_group_render_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, C.c_float, _vp, _vp, _u32, _vp]),
+    "vt_group_reduce_device": (_i32, [_vp, _vp, _u64, _vp]),
+    "vt_group_launch_count": (_u64, [_vp]),
     "vt_last_error": (C.c_char_p, []),
 }
 
@@ -241,6 +256,13 @@ class Accel:
         if layout is not None:
             _check(self.L.vt_accel_set_layout(self.h, {"exact": 0, "compact": 1, "quad": 2}[layout]), "vt_accel_set_layout")
 
+    @classmethod
+    def borrowed(cls, handle, scene=None):
+        """Wrap a vt_accel* owned by something else (a vt_group member): never destroyed from here."""
+        self = cls.__new__(cls)
+        self.L, self.h, self.scene, self._borrowed = lib(), handle, scene, True
+        return self
+
     @property
     def layout(self):
         """Layout resident after populate ("compact" falls back to "exact" for trees it cannot hold)."""
@@ -248,7 +270,8 @@ class Accel:
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.vt_accel_destroy(self.h)
+            if not getattr(self, "_borrowed", False):
+                self.L.vt_accel_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -429,3 +452,120 @@ class Accel:
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         _check(self.L.vt_accel_stats(self.h, C.addressof(a), C.addressof(b), C.addressof(c)), "vt_accel_stats")
         return {"n_tris": a.value, "node_count": b.value, "device_bytes": c.value}
+
+
+def shard_indices(n, world, rank, tile):
+    """Host-only: global record indices of `rank`'s shard of an n-record frame cut into `tile`-record tiles dealt round-robin,
+    in the shard's compact order (vt_shard_geometry gives the count; the order is tile by tile)."""
+    cnt, lt = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().vt_shard_geometry(n, world, rank, tile, C.addressof(cnt), C.addressof(lt)), "vt_shard_geometry")
+    tiles = np.arange(rank, rank + lt.value * world, world, dtype=np.int64)
+    idx = (tiles[:, None] * tile + np.arange(tile, dtype=np.int64)[None, :]).reshape(-1)
+    idx = idx[idx < n]
+    assert len(idx) == cnt.value
+    return idx
+
+
+def group_unique_id():
+    """128-byte ncclUniqueId (numpy uint8) for vt_group_create_rank: rank 0 calls this, the launcher distributes it."""
+    out = np.zeros(128, np.uint8)
+    _check(lib().vt_group_unique_id(out.ctypes.data), "vt_group_unique_id")
+    return out
+
+
+class Group:
+    """vt_group handle: one AccelStruct resident on several GPUs (include/vistrace_b200.h, multi-GPU section).
+
+    Group(devices=[0, 1, ...])                       one process drives the listed local GPUs
+    Group(device=d, rank=r, world=w, unique_id=id)   one process per GPU; `id` from group_unique_id() on rank 0
+    """
+
+    def __init__(self, devices=None, device=None, rank=None, world=None, unique_id=None):
+        self.L = lib()
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self.h = self.L.vt_group_create(C.cast(arr, _vp), len(devices))
+        else:
+            uid = None if unique_id is None else np.ascontiguousarray(unique_id, np.uint8)
+            self.h = self.L.vt_group_create_rank(int(device), int(rank), int(world), _ptr(uid))
+        if not self.h:
+            raise RuntimeError(f"vt_group_create: {_err()}")
+        self.scene = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vt_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def world(self):
+        return int(self.L.vt_group_size(self.h))
+
+    @property
+    def rank(self):
+        return int(self.L.vt_group_rank(self.h))
+
+    @property
+    def local_members(self):
+        return int(self.L.vt_group_local_members(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.vt_group_launch_count(self.h))
+
+    def accel(self, local_member=0):
+        h = self.L.vt_group_accel(self.h, local_member)
+        if not h:
+            raise RuntimeError("vt_group_accel: no such member")
+        return Accel.borrowed(h, self.scene)
+
+    def populate(self, scene):
+        """Build once, replicate the device image (multi-process groups: only rank 0 passes the scene; others pass None)."""
+        self.scene = scene
+        _check(self.L.vt_group_populate(self.h, None if scene is None else C.cast(scene.ptr(), _vp)), "vt_group_populate")
+        return self
+
+    def shard(self, n, rank=None):
+        """(tile, local_count) of `rank`'s shard of an n-pixel frame."""
+        tile, cnt = C.c_uint64(0), C.c_uint64(0)
+        _check(self.L.vt_group_shard(self.h, n, self.rank if rank is None else rank, C.addressof(tile), C.addressof(cnt)), "vt_group_shard")
+        return tile.value, cnt.value
+
+    def shard_indices(self, n, rank=None):
+        """Global pixel indices of `rank`'s shard, in its compact (tile) order."""
+        r = self.rank if rank is None else rank
+        tile, cnt = self.shard(n, r)
+        tiles = np.arange(r, (n + tile - 1) // tile, self.world, dtype=np.int64)
+        idx = (tiles[:, None] * tile + np.arange(tile, dtype=np.int64)[None, :]).reshape(-1)
+        idx = idx[idx < n]
+        assert len(idx) == cnt
+        return idx
+
+    def traverse(self, rays, want_attrs=False, any_hit=False, out=None):
+        rays = rays if isinstance(rays, np.ndarray) and rays.dtype == abi.RAY and rays.flags.c_contiguous else np.ascontiguousarray(rays, abi.RAY)
+        out = dict(out or {})
+        hits = out.get("hits") if "hits" in out else np.zeros(len(rays), abi.HIT)
+        attrs = (out.get("attrs") if "attrs" in out else np.zeros(len(rays), abi.ATTR)) if want_attrs else None
+        _check(self.L.vt_group_traverse(self.h, rays.ctypes.data, len(rays), hits.ctypes.data, _ptr(attrs), abi.VT_TRAVERSE_ANY_HIT if any_hit else 0),
+               "vt_group_traverse")
+        return (hits, attrs) if want_attrs else hits
+
+    def render_diffuse_wave(self, rays, spp, seed=0, weight=1.0, out=None, want_live=True):
+        """Host rays (frame-sized array) in, host RGBFFF framebuffer out; returns (framebuffer, bounce rays spawned by this process)."""
+        rays = rays if isinstance(rays, np.ndarray) and rays.dtype == abi.RAY and rays.flags.c_contiguous else np.ascontiguousarray(rays, abi.RAY)
+        fb = np.zeros((len(rays), 3), np.float32) if out is None else out
+        live = C.c_uint64(0)
+        _check(self.L.vt_group_render_diffuse_wave(self.h, rays.ctypes.data, len(rays), spp, seed, weight, fb.ctypes.data,
+                                                   C.addressof(live) if want_live else None, 0, None), "vt_group_render_diffuse_wave")
+        return fb, live.value
+
+    def render_diffuse_wave_device(self, d_rays_shard, n, spp, seed, weight, d_fb, stream=None):
+        """Device-resident shard in, frame-sized device image out (complete on rank 0); enqueued on `stream`."""
+        _check(self.L.vt_group_render_diffuse_wave(self.h, _ptr(d_rays_shard), n, spp, seed, weight, _ptr(d_fb), None,
+                                                   abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)), "vt_group_render_diffuse_wave")
+
+    def reduce_device(self, d_buf, count, stream=None):
+        _check(self.L.vt_group_reduce_device(self.h, _ptr(d_buf), count, _ptr(stream)), "vt_group_reduce_device")

@@ -15,28 +15,11 @@
 #include <mutex>
 #include <string>
 
-#include "vt_host.h"
-#include "vt_kernels.h"
+#include "vt_accel_internal.h"
 
 namespace vt {
 
-static thread_local std::string g_last_error;
-
-#define VT_CUDA(expr)                                                                                   \
-    do {                                                                                                \
-        cudaError_t _e = (expr);                                                                        \
-        if (_e != cudaSuccess)                                                                          \
-            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr); \
-    } while (0)
-
-static int env_int(const char *name, int def) {
-    const char *v = std::getenv(name);
-    return (v && *v) ? std::atoi(v) : def;
-}
-static float env_float(const char *name, float def) {
-    const char *v = std::getenv(name);
-    return (v && *v) ? (float)std::atof(v) : def;
-}
+thread_local std::string g_last_error;
 
 // ------------------------------------------------------------------------------ Triangle
 Triangle::Triangle(const float p0_[3], const float p1[3], const float p2[3], uint32_t material_, const float uvs_[3][2],
@@ -146,136 +129,12 @@ void SkinTriangles(vt_tri_in *tris, const vt_tri_skin *skin, uint64_t n, const f
     if (!error.empty()) throw std::runtime_error(error);
 }
 
-// --------------------------------------------------------------------------- DeviceScene
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t cap = 0;  // elements
-    void ensure(size_t n) {
-        if (n <= cap) return;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        VT_CUDA(cudaMalloc(&p, n * sizeof(T)));
-        cap = n;
-    }
-    void upload(const T *src, size_t n) {
-        ensure(n ? n : 1);
-        if (n) VT_CUDA(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    size_t bytes() const { return cap * sizeof(T); }
-};
-
-constexpr int kCounterSlots = 256;  // 16-byte {queue head, invalid rays} records, one per in-flight call
-
-struct DeviceScene {
-    DevBuf<VtPair> pairs;    // exact layout  \ one of the two is resident
-    DevBuf<VtCPair> cpairs;  // compact layout  | exactly one of the three is resident
-    DevBuf<VtQuad> quads;    // quad layout    /
-    DevBuf<VtTriRec> tris;
-    DevBuf<float> tri_uv;
-    DevBuf<VtTriAttr> attrs;
-    DevBuf<VtDevMaterial> mats;
-    DevBuf<VtDevEntity> ents;
-    DevBuf<VtDevTexture> texs;
-    DevBuf<uint8_t> texels;
-    DevBuf<unsigned long long> counters;
-    DevBuf<unsigned long long> stat_counters;
-    // staging for host-pointer calls
-    DevBuf<vt_ray> s_rays;
-    DevBuf<vt_hit> s_hits;
-    DevBuf<vt_attr> s_attrs;
-    DevBuf<float> s_cones;
-    // per-stream tile staging of the host-pointer diffuse wave
-    struct WaveLane {
-        cudaStream_t stream = nullptr;
-        DevBuf<vt_ray> brays;
-        DevBuf<vt_hit> hits, bhits;
-        DevBuf<vt_attr> attrs;
-        DevBuf<float> fb;
-        DevBuf<uint32_t> queue;                // live bounce slots of the tile (ray queue)
-        DevBuf<unsigned long long> queue_count;
-    } lanes[8];  // VT_WAVE_LANES of them are used (default 4: measured 3.26 / 3.08 / 3.15 / 3.16 ms per e2e step with 3 / 4 / 5 / 6)
-    // ray-queue scratch of the device-pointer wave, one per caller stream
-    struct WaveScratch {
-        DevBuf<uint32_t> queue;
-        DevBuf<unsigned long long> queue_count;
-    };
-    std::map<cudaStream_t, WaveScratch> wave_scratch;
-    std::mutex wave_mutex;
-    DevBuf<unsigned long long> live;
-    // host-pointer waves: the whole frame's rays are staged here by ONE copy stream, tile after tile, so an upload never
-    // waits for the lane (stream) its tile will run on; upload_done[k] gates tile k's kernels
-    DevBuf<vt_ray> wave_rays;
-    cudaStream_t copy_stream = nullptr;
-    std::vector<cudaEvent_t> upload_done;
-    // K5 (device refit) state, built on the first refit of a resident quad hierarchy
-    DevBuf<vt_tri_in> refit_in;
-    DevBuf<uint32_t> refit_parent, refit_n_inner, refit_slot_of, refit_arrive, refit_error;
-    DevBuf<float> refit_qbox;  // 6 floats per quad
-    bool refit_ready = false;
-    VtSceneView view{};
-    VtLaunchConfig cfg;
-    std::atomic<uint32_t> next_slot{0};
-    int sm_count = 0;
-    cudaStream_t own_stream = nullptr;
-
-    ~DeviceScene() {
-        pairs.release();
-        cpairs.release();
-        quads.release();
-        tris.release();
-        tri_uv.release();
-        attrs.release();
-        mats.release();
-        ents.release();
-        texs.release();
-        texels.release();
-        counters.release();
-        stat_counters.release();
-        s_rays.release();
-        s_hits.release();
-        s_attrs.release();
-        s_cones.release();
-        live.release();
-        wave_rays.release();
-        for (cudaEvent_t e : upload_done) cudaEventDestroy(e);
-        if (copy_stream) cudaStreamDestroy(copy_stream);
-        refit_in.release();
-        refit_parent.release();
-        refit_n_inner.release();
-        refit_slot_of.release();
-        refit_arrive.release();
-        refit_error.release();
-        refit_qbox.release();
-        for (auto &l : lanes) {
-            l.brays.release();
-            l.hits.release();
-            l.bhits.release();
-            l.attrs.release();
-            l.fb.release();
-            l.queue.release();
-            l.queue_count.release();
-            if (l.stream) cudaStreamDestroy(l.stream);
-        }
-        for (auto &kv : wave_scratch) {
-            kv.second.queue.release();
-            kv.second.queue_count.release();
-        }
-        if (own_stream) cudaStreamDestroy(own_stream);
-    }
-    uint64_t scene_bytes() const {
-        return pairs.bytes() + cpairs.bytes() + quads.bytes() + tris.bytes() + tri_uv.bytes() + attrs.bytes() + mats.bytes() + ents.bytes() + texs.bytes() +
-               texels.bytes();
-    }
-};
-
 // ----------------------------------------------------------------------------- AccelStruct
+static void check_built(bool built) {
+    // source/objects/AccelStruct.cpp:780
+    if (!built) throw std::runtime_error("Unable to perform traversal, acceleration structure invalid (use AccelStruct:Rebuild to rebuild it)");
+}
+
 AccelStruct::AccelStruct(int device) : mDevice(device) {
     if (const char *v = std::getenv("VT_LAYOUT")) {  // default for handles that do not call SetLayout
         const std::string l(v);
@@ -502,6 +361,7 @@ void AccelStruct::Upload(const vt_scene &scene) {
 
     D.refit_ready = false;
     mBvhStale = false;
+    mReplica = false;
     D.pairs.release();
     D.cpairs.release();
     D.quads.release();
@@ -566,7 +426,81 @@ void AccelStruct::PopulateWithBvh(const vt_scene &scene, const vt_node *nodes, u
     Upload(scene);
 }
 
+// ---- replicas (multi-GPU): the device image of a populated handle, copied GPU to GPU by vt_group.cu
+void AccelStruct::ExportReplica(ReplicaImage &img, const void *bufs[10]) const {
+    check_built(mAccelBuilt);
+    const DeviceScene &D = *mpDevice;
+    const VtSceneView &V = D.view;
+    std::memset(&img, 0, sizeof(img));
+    const size_t n_inner = V.n_pairs, n_tri_recs = (size_t)V.n_tris + ((VT_EMPTY_SENTINEL && mLayout == VT_LAYOUT_QUAD) ? 1 : 0);
+    const uint64_t bytes[10] = {V.pairs ? n_inner * sizeof(VtPair) : 0,
+                                V.cpairs ? n_inner * sizeof(VtCPair) : 0,
+                                V.quads ? n_inner * sizeof(VtQuad) : 0,
+                                n_tri_recs * sizeof(VtTriRec),
+                                n_tri_recs * 6 * sizeof(float),
+                                (size_t)V.n_tris * sizeof(VtTriAttr),
+                                D.mats.cap * sizeof(VtDevMaterial),
+                                D.ents.cap * sizeof(VtDevEntity),
+                                D.texs.cap * sizeof(VtDevTexture),
+                                D.texels.cap};
+    const void *ptrs[10] = {D.pairs.p, D.cpairs.p, D.quads.p, D.tris.p, D.tri_uv.p, D.attrs.p, D.mats.p, D.ents.p, D.texs.p, D.texels.p};
+    for (int i = 0; i < 10; i++) img.bytes[i] = bytes[i], bufs[i] = bytes[i] ? ptrs[i] : nullptr;
+    img.n_pairs = V.n_pairs, img.n_tris = V.n_tris, img.root_leaf_count = V.root_leaf_count, img.n_smem_pairs = V.n_smem_pairs;
+    img.has_alphatest = V.has_alphatest, img.fallback_tex = V.fallback_tex;
+    img.layout = mLayout;
+    img.n_materials = (uint32_t)D.mats.cap;
+}
+
+void AccelStruct::AllocReplica(const ReplicaImage &img, void *bufs[10]) {
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    mAccelBuilt = false;
+    mTriangles.clear();
+    mEntities.clear();
+    mMaterials.clear();
+    mAccel = HostBvh();
+    D.refit_ready = false;
+    D.pairs.release();
+    D.cpairs.release();
+    D.quads.release();
+    if (img.bytes[0]) D.pairs.ensure(img.bytes[0] / sizeof(VtPair));
+    if (img.bytes[1]) D.cpairs.ensure(img.bytes[1] / sizeof(VtCPair));
+    if (img.bytes[2]) D.quads.ensure(img.bytes[2] / sizeof(VtQuad));
+    D.tris.ensure(std::max<size_t>(1, img.bytes[3] / sizeof(VtTriRec)));
+    D.tri_uv.ensure(std::max<size_t>(1, img.bytes[4] / sizeof(float)));
+    D.attrs.ensure(std::max<size_t>(1, img.bytes[5] / sizeof(VtTriAttr)));
+    D.mats.ensure(std::max<size_t>(1, img.bytes[6] / sizeof(VtDevMaterial)));
+    D.ents.ensure(std::max<size_t>(1, img.bytes[7] / sizeof(VtDevEntity)));
+    D.texs.ensure(std::max<size_t>(1, img.bytes[8] / sizeof(VtDevTexture)));
+    D.texels.ensure(std::max<size_t>(1, img.bytes[9]));
+    void *ptrs[10] = {D.pairs.p, D.cpairs.p, D.quads.p, D.tris.p, D.tri_uv.p, D.attrs.p, D.mats.p, D.ents.p, D.texs.p, D.texels.p};
+    for (int i = 0; i < 10; i++) bufs[i] = img.bytes[i] ? ptrs[i] : nullptr;
+    mLayout = mWantLayout = img.layout;
+    VtSceneView &V = D.view;
+    V = VtSceneView{};
+    V.pairs = img.layout == VT_LAYOUT_EXACT ? D.pairs.p : nullptr;
+    V.cpairs = img.layout == VT_LAYOUT_COMPACT ? D.cpairs.p : nullptr;
+    V.quads = img.layout == VT_LAYOUT_QUAD ? D.quads.p : nullptr;
+    V.tris = D.tris.p, V.tri_uv = D.tri_uv.p, V.attrs = D.attrs.p, V.mats = D.mats.p, V.ents = D.ents.p, V.texs = D.texs.p, V.texels = D.texels.p;
+    V.n_pairs = img.n_pairs, V.n_tris = img.n_tris, V.root_leaf_count = img.root_leaf_count, V.n_smem_pairs = img.n_smem_pairs;
+    V.has_alphatest = img.has_alphatest, V.fallback_tex = img.fallback_tex;
+    V.magic = 0x4B000000u;
+    V.magic_h = 0x64646464u;
+    D.cfg.persistent = env_int("VT_PERSISTENT", 1);
+    D.cfg.refill_threshold = env_int("VT_REFILL", D.cfg.refill_threshold);
+    D.cfg.tri_threshold = env_int("VT_TRI_ROUND", D.cfg.tri_threshold);
+    int blocks = 0;
+    VT_CUDA(vt_traverse_occupancy(&blocks, (size_t)V.n_smem_pairs * sizeof(VtPair), img.layout));
+    if (blocks < 1) blocks = 1;
+    const int mult = env_int("VT_GRID_BLOCKS_PER_SM", blocks);
+    D.cfg.grid = D.sm_count * std::max(1, std::min(mult, blocks));
+    mReplica = true;
+    mBvhStale = false;
+    mAccelBuilt = true;  // valid once the caller has filled the buffers (it does so before anything is enqueued)
+}
+
 const HostBvh &AccelStruct::Bvh() const {
+    if (mReplica) throw std::runtime_error("this handle is a replica (vt_group): the host-side hierarchy lives in the group's first member");
     std::lock_guard<std::mutex> lock(mBvhMutex);
     if (mBvhStale) {
         std::string err;
@@ -577,6 +511,7 @@ const HostBvh &AccelStruct::Bvh() const {
 }
 
 void AccelStruct::Refit(const vt_scene &scene) {
+    if (mReplica) throw std::runtime_error("refit: this handle is a replica (vt_group): refit the group");
     if (!mAccelBuilt) throw std::runtime_error("refit: nothing built yet (use Populate)");
     if (scene.n_tris != mAccel.prim_indices.size()) throw std::runtime_error("refit: triangle count changed (use Populate to rebuild)");
     if (scene.n_materials != mMaterials.size() || scene.n_entities != mEntities.size())
@@ -586,13 +521,19 @@ void AccelStruct::Refit(const vt_scene &scene) {
         // K5: new vertices up, Triangle constructor + bottom-up quad refit on the device (vt_refit.cu); the host copies
         // (mTriangles now, the bvh::Bvh-form boxes on demand) are brought up to date while the GPU works.
         // the kernel indexes the resident material table with the caller's indices: check them before anything is launched
-        bool bad = false;
-#pragma omp parallel for reduction(|| : bad)
-        for (int64_t i = 0; i < (int64_t)scene.n_tris; i++)
-            bad = bad || scene.tris[i].material >= scene.n_materials || scene.tris[i].ent_idx >= scene.n_entities;
+        bool bad = false, any_alpha = false;
+#pragma omp parallel for reduction(|| : bad, any_alpha)
+        for (int64_t i = 0; i < (int64_t)scene.n_tris; i++) {
+            const bool oob = scene.tris[i].material >= scene.n_materials || scene.tris[i].ent_idx >= scene.n_entities;
+            bad = bad || oob;
+            // k_refit_tris rebuilds the CULL / ALPHATEST bits from the RESIDENT material table (materials are unchanged by a refit)
+            any_alpha = any_alpha || (!oob && (mMaterials[scene.tris[i].material].flags & VT_MATFLAG_ALPHATEST) != 0);
+        }
         if (bad) throw std::runtime_error("triangle references a material or entity out of range");
         VT_CUDA(cudaSetDevice(mDevice));
         DeviceScene &D = *mpDevice;
+        // K1's ALPHA template is chosen from this flag: a refit may move a triangle onto (or off) an alpha-tested material
+        D.view.has_alphatest = any_alpha ? 1u : 0u;
         const VtSceneView &V = D.view;
         cudaStream_t stream = D.own_stream;
         D.refit_in.ensure(scene.n_tris);
@@ -632,18 +573,25 @@ void AccelStruct::Refit(const vt_scene &scene) {
 }
 
 void AccelStruct::RefitRange(const vt_tri_in *tris, uint64_t first, uint64_t count) {
+    if (mReplica) throw std::runtime_error("refit: this handle is a replica (vt_group): refit the group");
     if (!mAccelBuilt) throw std::runtime_error("refit: nothing built yet (use Populate)");
     if (count == 0) return;
     if (!tris) throw std::runtime_error("refit_range: null triangles");
     if (first + count > mTriangles.size()) throw std::runtime_error("refit_range: range past the end of the triangle array");
     if (mLayout != VT_LAYOUT_QUAD || mpDevice->view.n_pairs == 0)
         throw std::runtime_error("refit_range: needs the resident quad layout (use vt_accel_refit with the whole scene)");
-    bool bad = false;
-#pragma omp parallel for reduction(|| : bad)
-    for (int64_t i = 0; i < (int64_t)count; i++) bad = bad || tris[i].material >= mMaterials.size() || tris[i].ent_idx >= mEntities.size();
+    bool bad = false, any_alpha = false;
+#pragma omp parallel for reduction(|| : bad, any_alpha)
+    for (int64_t i = 0; i < (int64_t)count; i++) {
+        const bool oob = tris[i].material >= mMaterials.size() || tris[i].ent_idx >= mEntities.size();
+        bad = bad || oob;
+        any_alpha = any_alpha || (!oob && (mMaterials[tris[i].material].flags & VT_MATFLAG_ALPHATEST) != 0);
+    }
     if (bad) throw std::runtime_error("triangle references a material or entity out of range");
     VT_CUDA(cudaSetDevice(mDevice));
     DeviceScene &D = *mpDevice;
+    // a range can only ADD alpha-tested triangles as far as this call can tell; the ALPHA template is correct for scenes without any
+    if (any_alpha) D.view.has_alphatest = 1u;
     const VtSceneView &V = D.view;
     cudaStream_t stream = D.own_stream;
     D.refit_in.ensure(count);
@@ -684,10 +632,6 @@ void AccelStruct::RefitRange(const vt_tri_in *tris, uint64_t first, uint64_t cou
     mAccelBuilt = true;
 }
 
-static void check_built(bool built) {
-    // source/objects/AccelStruct.cpp:780
-    if (!built) throw std::runtime_error("Unable to perform traversal, acceleration structure invalid (use AccelStruct:Rebuild to rebuild it)");
-}
 
 void AccelStruct::TraverseBatch(const vt_ray *rays, uint64_t n, vt_hit *hits, vt_attr *attrs, const float *cones,
                                 uint32_t flags, void *stream_) {
@@ -982,7 +926,7 @@ void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp,
         VT_CUDA(cudaStreamWaitEvent(consumer, done, 0));
         return D.wave_rays.p + base;
     };
-    int li = 0;
+    int li = 0, tiles_since_fence = 0;
     uint64_t cur_tile = std::max<uint64_t>(1, std::min<uint64_t>(tile, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)(tile / 8)))));  // small first tiles, doubling up to `tile`
     for (uint64_t base = 0, m = 0; base < n; base += m, li = (li + 1) % n_lanes, cur_tile = std::min(tile, cur_tile * 2)) {
         m = std::min(cur_tile, n - base);
@@ -995,6 +939,11 @@ void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp,
         l.bhits.ensure(cap * spp);
         l.queue.ensure(cap * spp);
         l.queue_count.ensure(1);
+        // the counter ring has kCounterSlots entries and a tile takes two: drain the lanes before a live slot could be reused
+        if (++tiles_since_fence >= kCounterSlots / 2 - 16) {
+            for (int i = 0; i < n_lanes; i++) VT_CUDA(cudaStreamSynchronize(D.lanes[i].stream));
+            tiles_since_fence = 0;
+        }
         unsigned long long *c0 = next_counter(), *c1 = next_counter();
         VT_CUDA(cudaMemsetAsync(c0, 0, 16, l.stream));
         VT_CUDA(cudaMemsetAsync(c1, 0, 16, l.stream));
@@ -1079,7 +1028,7 @@ void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp
         VT_CUDA(cudaStreamWaitEvent(consumer, done, 0));
         return D.wave_rays.p + base;
     };
-    int li = 0;
+    int li = 0, tiles_since_fence = 0;
     // the first tiles are small so the first kernel starts after a short upload; sizes double up to `tile`
     uint64_t cur_tile = std::max<uint64_t>(1, std::min<uint64_t>(tile, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)(tile / 8)))));
     for (uint64_t base = 0, m = 0; base < n; base += m, li = (li + 1) % n_lanes, cur_tile = std::min(tile, cur_tile * 2)) {
@@ -1094,6 +1043,10 @@ void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp
         l.fb.ensure(cap * 3);
         l.queue.ensure(cap * spp);
         l.queue_count.ensure(1);
+        if (++tiles_since_fence >= kCounterSlots / 2 - 16) {  // see TraceDiffuseWave: the counter ring must not wrap onto a live slot
+            for (int i = 0; i < n_lanes; i++) VT_CUDA(cudaStreamSynchronize(D.lanes[i].stream));
+            tiles_since_fence = 0;
+        }
         unsigned long long *c0 = next_counter(), *c1 = next_counter();
         VT_CUDA(cudaMemsetAsync(c0, 0, 16, l.stream));
         VT_CUDA(cudaMemsetAsync(c1, 0, 16, l.stream));
@@ -1168,22 +1121,6 @@ TraceResult *AccelStruct::Traverse(const float origin[3], const float direction[
 }  // namespace vt
 
 // ================================================================================ C ABI
-struct vt_accel {
-    vt::AccelStruct impl;
-    explicit vt_accel(int device) : impl(device) {}
-};
-
-#define VT_TRY try {
-#define VT_CATCH(ret)                     \
-    }                                     \
-    catch (const std::exception &e) {     \
-        vt::g_last_error = e.what();      \
-        return ret;                       \
-    }                                     \
-    catch (...) {                         \
-        vt::g_last_error = "unknown error"; \
-        return ret;                       \
-    }
 
 extern "C" {
 

@@ -672,7 +672,10 @@ struct QuadBuilder {
             q.ref[i] = emit(kids[i], depth + 1, &n);
             below = std::max(below, n);
         }
-        *need = (uint32_t)(nk - 1) + below;  // while a child is being walked, up to nk - 1 siblings are pending
+        // while a child is being walked, up to nk - 1 siblings are pending — and with VT_EMPTY_SENTINEL the kernel does not test
+        // "slot in use": an empty slot's inverted box can pass the rounded slab test (vt_traverse.cu, slab_quad) and its sentinel
+        // leaf is then pushed like any other child, so every level is budgeted with all 3 non-nearest slots
+        *need = (uint32_t)(VT_EMPTY_SENTINEL ? 3 : nk - 1) + below;
         out.quads[qi] = q;
         return qi;
     }

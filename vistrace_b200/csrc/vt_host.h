@@ -124,10 +124,26 @@ class AccelStruct {
     uint64_t mInvalidRays = 0;
     uint64_t mLaunches = 0;
 
+    bool mReplica = false;  // device arrays copied from another handle (vt_group.cu): no host containers, no refit / get_bvh
+
     void Ingest(const vt_scene &scene);
     void Upload(const vt_scene &scene);
+    friend class Group;
 
 public:
+    // What a replica on another GPU needs besides the bytes of the ten device arrays (multi-GPU, vt_group.cu): the hierarchy is
+    // built and flattened ONCE and its device image is copied GPU to GPU (cudaMemcpyPeer in one process, ncclBroadcast across
+    // processes); every GPU then holds the whole scene (replicate, never partition).
+    struct ReplicaImage {
+        uint64_t bytes[10];  // pairs, cpairs, quads, tris, tri_uv, attrs, mats, ents, texs, texels
+        uint32_t n_pairs, n_tris, root_leaf_count, n_smem_pairs, has_alphatest, fallback_tex;
+        int32_t layout;
+        uint32_t n_materials;
+    };
+    void ExportReplica(ReplicaImage &img, const void *bufs[10]) const;
+    void AllocReplica(const ReplicaImage &img, void *bufs[10]);  // the caller fills bufs[i] (img.bytes[i] each), then the handle is usable
+    bool IsReplica() const { return mReplica; }
+
     explicit AccelStruct(int device);
     ~AccelStruct();
     AccelStruct(const AccelStruct &) = delete;

@@ -43,9 +43,19 @@ cudaError_t vt_launch_trace_result(const VtSceneView &S, const vt_ray *rays, con
 // Ray queue (optional, all three or none): queue[pos] = slot of every ray spawned, pos handed out from *queue_count
 // (must be 0 on entry), and miss_hits[slot] = a miss record for every masked slot — so the traversal that follows
 // only has to visit the queue and the hit buffer is complete in slot order all the same.
+// Pixel map of a SHARD of a frame (multi-GPU, vt_group.cu): the frame is cut into tiles of `tile` pixels, the shard owns every
+// `stride`-th tile starting at tile `phase`, stored compactly; local pixel i (after adding local_base, the offset of the batch
+// inside the shard) is global pixel ((i / tile) * stride + phase) * tile + i % tile.  The random-number counter of a bounce ray is
+// taken from the GLOBAL pixel, so a frame traced in shards draws the same numbers — and gives the same image bit for bit — as the
+// frame traced whole.  tile == 0: identity.
+struct VtSlotMap {
+    unsigned long long local_base = 0;
+    unsigned long long tile = 0;
+    uint32_t stride = 1, phase = 0;
+};
 cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, uint64_t slot_offset,
                                   vt_ray *out, unsigned long long *live, cudaStream_t stream, uint32_t *queue = nullptr,
-                                  unsigned long long *queue_count = nullptr, vt_hit *miss_hits = nullptr);
+                                  unsigned long long *queue_count = nullptr, vt_hit *miss_hits = nullptr, const VtSlotMap *map = nullptr);
 cudaError_t vt_launch_shadow_rays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out,
                                   unsigned long long *live, cudaStream_t stream, uint32_t *queue = nullptr,
                                   unsigned long long *queue_count = nullptr, vt_hit *miss_hits = nullptr);

@@ -80,12 +80,20 @@ VT_DEV void publish_slot(bool in_range, bool spawned, unsigned long long slot, u
 __global__ void __launch_bounds__(256)
 k_bounce_rays(const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t spp, unsigned long long seed,
               unsigned long long slot_offset, vt_ray *__restrict__ out, unsigned long long *__restrict__ live,
-              uint32_t *__restrict__ queue, unsigned long long *__restrict__ queue_count, vt_hit *__restrict__ miss_hits) {
+              uint32_t *__restrict__ queue, unsigned long long *__restrict__ queue_count, vt_hit *__restrict__ miss_hits,
+              const VtSlotMap map) {
     const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long total = n * spp;
     bool spawned = false;
     if (j < total) {
         const unsigned long long i = j / spp;
+        // counter of the random-number hash: slot of the GLOBAL pixel (VtSlotMap, vt_kernels.h); identity map: slot_offset + j
+        unsigned long long ctr = slot_offset + j;
+        if (map.tile) {
+            const unsigned long long li = map.local_base + i;
+            const unsigned long long gi = ((li / map.tile) * map.stride + map.phase) * map.tile + li % map.tile;
+            ctr = slot_offset + gi * spp + (j - i * spp);
+        }
         const float4 *a = reinterpret_cast<const float4 *>(attrs + i);
         const float4 q7 = __ldg(a + 7);  // tex_uv, flags, prim
         const uint32_t flags = __float_as_uint(q7.z), prim = __float_as_uint(q7.w);
@@ -96,7 +104,7 @@ k_bounce_rays(const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t 
             const V3 pos = mk3(q0.x, q0.y, q0.z);
             const V3 N = mk3(q1.x, q1.y, q1.z) * sgn, T = mk3(q2.x, q2.y, q2.z), B = mk3(q3.x, q3.y, q3.z) * sgn;
             const V3 gN = mk3(q4.x, q4.y, q4.z) * sgn;
-            const float r1 = uniform01(slot_offset + j, 0, seed), r2 = uniform01(slot_offset + j, 1, seed);
+            const float r1 = uniform01(ctr, 0, seed), r2 = uniform01(ctr, 1, seed);
             const float z = sqrtf(r1), sinTheta = sqrtf(1.f - r1), phi = 6.2831853071795864769f * r2;
             float sp, cp;
             sincosf(phi, &sp, &cp);
@@ -214,13 +222,13 @@ cudaError_t vt_launch_accumulate_sky(const VtSceneView &S, const vt_attr *attrs,
 
 cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, uint64_t slot_offset,
                                   vt_ray *out, unsigned long long *live, cudaStream_t stream, uint32_t *queue,
-                                  unsigned long long *queue_count, vt_hit *miss_hits) {
+                                  unsigned long long *queue_count, vt_hit *miss_hits, const VtSlotMap *map) {
     const unsigned long long total = (unsigned long long)n * spp;
     if (total == 0) return cudaSuccess;
     if (queue && (!queue_count || !miss_hits || total > 0xFFFFFFFFull)) return cudaErrorInvalidValue;
     const unsigned block = 256;
     k_bounce_rays<<<(unsigned)((total + block - 1) / block), block, 0, stream>>>(attrs, n, spp, seed, slot_offset, out, live, queue,
-                                                                                queue_count, miss_hits);
+                                                                                queue_count, miss_hits, map ? *map : VtSlotMap());
     return cudaGetLastError();
 }
 

@@ -246,8 +246,12 @@ void VtfDecode(const uint8_t *file, uint64_t size, uint32_t frame, uint32_t face
     uint64_t total = 0;
     for (uint32_t m = 0; m < h.mips; m++)
         total += image_size(std::max(1, h.width >> m), std::max(1, h.height >> m), std::max<uint32_t>(1u, info.depth >> m), h.format);
-    total *= (uint64_t)h.frames * info.faces;
-    if (h.data_offset + total > size) throw std::runtime_error("vtf: image data runs past the end of the file");
+    // untrusted header: every factor is checked against the file size BEFORE it is multiplied in, so the product cannot wrap
+    // (16384 x 16384 x depth 65535 x 65535 frames is ~2^65 bytes)
+    if (h.data_offset > size || total > size - h.data_offset) throw std::runtime_error("vtf: image data runs past the end of the file");
+    const uint64_t copies = (uint64_t)h.frames * info.faces;  // <= 65535 * 7
+    if (total != 0 && copies > (size - h.data_offset) / total) throw std::runtime_error("vtf: image data runs past the end of the file");
+    total *= copies;
     // storage order: mips smallest first; inside a mip frames -> faces -> z slices (VTFParser.cpp:44-78,178-205)
     const uint8_t *src = file + h.data_offset;
     uint8_t *dst = rgba;
@@ -255,6 +259,7 @@ void VtfDecode(const uint8_t *file, uint64_t size, uint32_t frame, uint32_t face
         const uint32_t w = std::max(1, h.width >> m), hh = std::max(1, h.height >> m), d = std::max<uint32_t>(1u, info.depth >> m);
         const uint64_t slice = image_size(w, hh, 1, h.format);
         const uint8_t *img = src + ((uint64_t)frame * info.faces + face) * slice * d;  // z slice 0
+        if (img < file || slice > size || (uint64_t)(img - file) > size - slice) throw std::runtime_error("vtf: image data runs past the end of the file");
         if (is_dxt(h.format)) {
             decode_dxt(img, dst, w, hh, h.format);
         } else {
