@@ -194,6 +194,16 @@ typedef struct vt_attr {
     uint32_t prim;             /* original triangle index, VT_MISS on a miss (rest zero) */
 } vt_attr;
 
+/* One BSDF sample: BSDFSample (source/libraries/BSDF.h:112-118).  32 bytes. */
+#define VT_LOBE_NONE               0u
+#define VT_LOBE_DIFFUSE_REFLECTION 1u /* LobeType::DiffuseReflection (BSDF.h:13) */
+typedef struct vt_bsdf_sample {
+    float scattered[3]; /* world-space direction of the scattered ray */
+    float pdf;
+    float weight[3];    /* BSDF * cos / pdf of the chosen lobe, over the lobe's selection probability */
+    uint32_t lobe;      /* VT_LOBE_* */
+} vt_bsdf_sample;
+
 /* --------------------------------------------------------------- entry points */
 
 typedef struct vt_accel vt_accel; /* opaque; replaces AccelStruct (source/objects/AccelStruct.h:61-86) */
@@ -295,6 +305,27 @@ int vt_accel_trace_result(vt_accel *accel, const vt_ray *rays, const vt_hit *hit
 int vt_accel_bounce_rays(vt_accel *accel, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed,
                          vt_ray *out_rays, uint64_t *live_out, uint32_t flags, void *stream);
 
+/* Batched SampleBSDF, DIFFUSE LOBE (source/libraries/BSDF.cpp:770-825, SampleDiffuse :252-278, hemisphere_cos :69-77) — the
+ * other call a GLua path tracer makes per hit between two accel:Traverse calls.  For every non-sky hit in attrs[0, n) and every
+ * sample s < spp: a BSDFMaterial whose activeLobes is LobeType::DiffuseReflection (the remaining fields at their defaults,
+ * BSDF.h:58-92) is prepared by PrepShadingData(albedo, metalness, roughness) (BSDF.cpp:11-21) from the TraceResult record;
+ * incident = TraceResult's wo = -normalize(direction of rays[i]) (source/objects/AccelStruct.cpp:826); the three numbers the
+ * reference draws from its ISampler — lobeSelect, then r1, r2 of hemisphere_cos — are vt_sample_uniform01(i*spp+s, 0 / 1 / 2, seed).
+ * out_samples[i*spp+s] = the BSDFSample (scattered in world space, pdf, weight, lobe); out_rays[i*spp+s] = the ray along
+ * `scattered` from vistrace.CalcRayOrigin(pos, geometric normal on the side `scattered` leaves through)
+ * (source/VisTrace.cpp:1478-1519), tMax = FLT_MAX.  Slots that spawn nothing — miss, sky, or lobeSelect >= pDiffuse (a fully
+ * metallic hit: SampleBSDF returns with the zero vector, weight 0, pdf 0, lobe None) — are MASKED rays (tmax < 0).
+ * The specular / transmission lobes are not restated (SURVEY.md section 8 f2 names the diffuse lobe).
+ * Host pointers unless VT_TRAVERSE_DEVICE_PTRS; live_out (nullable, host) = rays spawned, makes the call synchronous;
+ * queue / queue_count / miss_hits (all or none; device pointers only) as in vt_accel_bounce_rays_queued. */
+int vt_accel_sample_bsdf_rays(vt_accel *accel, const vt_ray *rays, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed,
+                              vt_ray *out_rays, vt_bsdf_sample *out_samples, uint64_t *live_out, uint32_t *queue,
+                              uint64_t *queue_count, vt_hit *miss_hits, uint32_t flags, void *stream);
+
+/* Host-only: the counter-based random number the generators draw for (slot, dimension, seed), in [0, 1) — the stand-in for the
+ * reference's sequential mt19937 Sampler (source/objects/Sampler.cpp:5-20), exposed so that a caller can reproduce a wave. */
+float vt_sample_uniform01(uint64_t slot, uint32_t dim, uint64_t seed);
+
 /* Shadow-ray generation on the device ("primary + shadow rays"): for every non-sky hit in attrs[0, n) one ray from
  * vistrace.CalcRayOrigin(pos, geometric normal on the viewer's side) (source/VisTrace.cpp:1478-1519) into out_rays[i]:
  *   point_light == 0: direction = light (a sun direction, used as given), tMax = tmax;
@@ -320,6 +351,37 @@ int vt_accel_shadow_rays_queued(vt_accel *accel, const vt_attr *attrs, uint64_t 
 int vt_accel_traverse_queued(vt_accel *accel, const vt_ray *rays, const uint32_t *queue, const uint64_t *queue_count,
                              uint64_t capacity, vt_hit *hits, vt_attr *attrs /* nullable: TraceResult of all `capacity` slots */,
                              uint32_t flags /* VT_TRAVERSE_ANY_HIT */, void *stream);
+
+/* Wave compaction for multi-bounce paths (path tracing: primary, then bounce after bounce, each with its shadow rays).  After
+ * the first bounce most slots of a wave are dead — the path left through the sky — and a wave that still visits every slot
+ * spends its time on them.  The requeued generators visit only the parents the PREVIOUS wave's queue lists
+ * (attrs[in_queue[k]], k < min(n, *in_count)): slot = parent * spp + sample as before, slots they do not visit are not
+ * written at all.  With VT_TRAVERSE_QUEUE_ATTRS vt_accel_traverse_queued likewise builds the TraceResult only of the slots
+ * its queue lists.  Everything downstream of a compacted wave must therefore go through the queues; the per-ray results are
+ * those of the uncompacted calls (same rays, same random-number counters, same hits).  in_queue must differ from queue.
+ * DEVICE pointers, enqueued on `stream`. */
+#define VT_TRAVERSE_QUEUE_ATTRS 4u
+int vt_accel_bounce_rays_requeued(vt_accel *accel, const vt_attr *attrs, const uint32_t *in_queue, const uint64_t *in_count,
+                                  uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays, uint32_t *queue,
+                                  uint64_t *queue_count, vt_hit *miss_hits, void *stream);
+int vt_accel_shadow_rays_requeued(vt_accel *accel, const vt_attr *attrs, const uint32_t *in_queue, const uint64_t *in_count,
+                                  uint64_t n, const float light[3], int point_light, float tmax, vt_ray *out_rays,
+                                  uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream);
+
+/* Path waves in one call (BASELINE.json configs[4]: "per sample primary + shadow + up to K diffuse bounces each with a shadow ray"):
+ * rays[0, n) are the primary rays of n paths (slot = pixel).  Wave 0 = accel:Traverse + TraceResult of every ray; wave k + 1 =
+ * one cosine-weighted bounce ray (vt_accel_bounce_rays) per vertex of wave k that is still alive (hit something that is not the
+ * sky), traversed closest-hit + TraceResult; at every vertex one shadow ray toward sun_dir, traversed any-hit.  From wave 1 on
+ * every kernel walks the queue of live paths only (requeued generators, VT_TRAVERSE_QUEUE_ATTRS) unless VT_PATHS_NO_COMPACTION.
+ * Harness-level shading folds the result into the RGBFFF framebuffer: fb[i] += weight * (sum over vertices of throughput * sun_rgb
+ * where the shadow ray is unoccluded  +  throughput * albedo where the path leaves through a sky brush), throughput = product of
+ * the albedos along the path.  ray_counts (nullable, HOST, 2 + 2 * bounces entries; makes the call synchronous): rays traced per
+ * wave — [0] primary, [1] its shadow rays, [2 + 2k], [3 + 2k] bounce k + 1 and its shadow rays.
+ * DEVICE pointers (VT_TRAVERSE_DEVICE_PTRS required), enqueued on `stream`; at most 8 bounces. */
+#define VT_PATHS_NO_COMPACTION 8u
+int vt_accel_trace_paths(vt_accel *accel, const vt_ray *rays, uint64_t n, uint32_t bounces, const float sun_dir[3],
+                         const float sun_rgb[3], uint64_t seed, float weight, float *framebuffer_rgb, uint64_t *ray_counts,
+                         uint32_t flags, void *stream);
 
 /* The "primary + diffuse" wave of the headline benchmark in one call: traverse rays[0, n), build
  * the TraceResult of every hit, spawn spp bounce rays per hit (as vt_accel_bounce_rays) and

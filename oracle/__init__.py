@@ -62,6 +62,7 @@ def _lib(kind):
         "node_intersect": (None, [vp, vp, vp]),
         "tri_intersect": (i32, [vp, u64, vp, vp]),
         "skin_triangles": (None, [vp, vp, u64, vp, vp, C.c_uint32, vp]),
+        "sample_bsdf_diffuse": (None, [vp, vp, vp, u64, vp, vp]),
     }
     if kind != "port":  # reference only: its VTF parser is not restated in the C port (the product's decoder is checked against it)
         sig["vtf_pixels"] = (C.c_int64, [vp, u64, C.c_uint32, C.c_uint32, vp, u64])
@@ -218,3 +219,16 @@ def vtf_pixels(data, n_texels, frame=0, face=0):
     if n != n_texels:
         raise RuntimeError(f"vtf_pixels: reference reports {n} texels, expected {n_texels}")
     return out
+
+
+def sample_bsdf_diffuse(attrs, wo, rnd, kind="reference"):
+    """SampleBSDF (source/libraries/BSDF.cpp:770-825) with only the diffuse lobe active, per TraceResult record: BSDFMaterial
+    prepared by PrepShadingData(albedo, metalness, roughness); wo = incident direction [n, 3]; rnd = [n, 3] the numbers the
+    ISampler hands out (lobeSelect, r1, r2).  Returns (abi.BSDF_SAMPLE records, returned flags)."""
+    attrs = np.ascontiguousarray(attrs, abi.ATTR)
+    wo = np.ascontiguousarray(wo, np.float32).reshape(len(attrs), 3)
+    rnd = np.ascontiguousarray(rnd, np.float32).reshape(len(attrs), 3)
+    out = np.zeros(len(attrs), abi.BSDF_SAMPLE)
+    ret = np.zeros(len(attrs), np.int32)
+    _lib(kind).sample_bsdf_diffuse(attrs.ctypes.data, wo.ctypes.data, rnd.ctypes.data, len(attrs), out.ctypes.data, ret.ctypes.data)
+    return out, ret

@@ -13,6 +13,7 @@
 //     (bvh::SingleRayTraverser + ClosestPrimitiveIntersector + Triangle::intersect)
 //   * TraceResult ctor and getters                  source/objects/TraceResult.cpp:45-262
 //   * VTFTexture(const uint8_t*, size_t)::Sample    libs/VTFParser/VTFParser.cpp:311-330
+//   * SampleBSDF + BSDFMaterial::PrepShadingData    source/libraries/BSDF.cpp:11-21,770-825 (diffuse lobe)
 // The ingestion paths (Lua, engine filesystem) are bypassed by filling the
 // private containers directly, which is why `private` is opened up below.
 #include <algorithm>
@@ -37,6 +38,7 @@
 #include "TraceResult.h"
 #undef private
 
+#include "BSDF.h"
 #include "VTFParser.h"
 #include "bvh/hierarchy_refitter.hpp"
 #include "bvh/leaf_collapser.hpp"
@@ -534,4 +536,36 @@ void vtref_skin_triangles(const vt_tri_in *tris, const vt_tri_skin *skin, uint64
     }
 }
 
+
+// SampleBSDF (source/libraries/BSDF.cpp:770-825) for a BSDFMaterial restricted to the diffuse lobe, prepared per hit by
+// PrepShadingData (BSDF.cpp:11-21) from the TraceResult values; the ISampler hands out the caller's numbers in call order.
+namespace {
+class ScriptedSampler final : public VisTrace::ISampler {
+    const float *v;
+    int i = 0;
+
+public:
+    explicit ScriptedSampler(const float *values) : v(values) {}
+    float GetFloat() override { return v[i++]; }
+    void GetFloat2D(float &r1, float &r2) override { r1 = v[i++], r2 = v[i++]; }
+};
+}  // namespace
+void vtref_sample_bsdf_diffuse(const vt_attr *attrs, const float *wo3, const float *rnd3, uint64_t n, vt_bsdf_sample *out, int32_t *returned) {
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const vt_attr &a = attrs[i];
+        BSDFMaterial mat;
+        mat.activeLobes = LobeType::DiffuseReflection;
+        mat.PrepShadingData(glm::vec3(a.albedo[0], a.albedo[1], a.albedo[2]), a.metalness, a.roughness);
+        ScriptedSampler sg(rnd3 + 3 * i);
+        BSDFSample res;
+        const bool ok = SampleBSDF(mat, &sg, glm::vec3(a.normal[0], a.normal[1], a.normal[2]), glm::vec3(a.tangent[0], a.tangent[1], a.tangent[2]),
+                                   glm::vec3(a.binormal[0], a.binormal[1], a.binormal[2]), glm::vec3(wo3[3 * i], wo3[3 * i + 1], wo3[3 * i + 2]), res);
+        returned[i] = ok ? 1 : 0;
+        out[i].scattered[0] = res.scattered.x, out[i].scattered[1] = res.scattered.y, out[i].scattered[2] = res.scattered.z;
+        out[i].pdf = res.pdf;
+        out[i].weight[0] = res.weight.x, out[i].weight[1] = res.weight.y, out[i].weight[2] = res.weight.z;
+        out[i].lobe = (uint32_t)res.lobe;
+    }
+}
 } // extern "C"

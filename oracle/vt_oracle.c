@@ -887,3 +887,61 @@ void vto_skin_triangles(const vt_tri_in *tris, const vt_tri_skin *skin, uint64_t
         }
     }
 }
+
+/* SampleBSDF restricted to the diffuse lobe — source/libraries/BSDF.cpp:770-825 with a BSDFMaterial whose activeLobes is
+ * LobeType::DiffuseReflection (BSDF.h:13), prepared per hit by BSDFMaterial::PrepShadingData (BSDF.cpp:11-21) with the defaults of
+ * BSDF.h:58-92 (dielectricInput = 1, specularTransmission = 0, anisotropicRotation = 0).  rnd3 = the three numbers the reference
+ * draws from its ISampler, in call order: lobeSelect (:780), then r1, r2 of hemisphere_cos (:69-77).
+ * glm::rotate(v, 0, n) (to_local / from_local, :760-767) is the identity for finite vectors: cos 0 = 1, sin 0 = 0. */
+typedef struct { float scattered[3]; float pdf; float weight[3]; uint32_t lobe; } vto_bsdf_sample;
+static inline float schlick_dielectric(float f0, float cosTheta, float f90) { return f0 + (f90 - f0) * powf(1.f - cosTheta, 5.f); } /* :157-160 */
+void vto_sample_bsdf_diffuse(const vt_attr *attrs, const float *wo3, const float *rnd3, uint64_t n, vto_bsdf_sample *out, int32_t *returned) {
+    const float pi = 3.14159265358979323846264338327950288f; /* glm::pi<float>() */
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const vt_attr *a = &attrs[i];
+        /* PrepShadingData, :11-21 */
+        const float metallic = gclamp(a->metalness, 0.f, 1.f);
+        const float linearRoughness = gclamp(a->roughness, 0.f, 1.f);
+        const v3 dielectric = V3(gclamp(1.f * a->albedo[0], 0.f, 1.f), gclamp(1.f * a->albedo[1], 0.f, 1.f), gclamp(1.f * a->albedo[2], 0.f, 1.f));
+        /* CalculateLobePDFs, :23-56: only the diffuse lobe is active */
+        float pDiffuse = (1.f - metallic) * (1.f - 0.f);
+        float normFactor = pDiffuse + 0.f + 0.f + 0.f;
+        if (normFactor > 0.f) {
+            normFactor = 1.f / normFactor;
+            pDiffuse *= normFactor;
+        }
+        const float lobeSelect = rnd3[3 * i];
+        const v3 N = V3(a->normal[0], a->normal[1], a->normal[2]), T = V3(a->tangent[0], a->tangent[1], a->tangent[2]),
+                 B = V3(a->binormal[0], a->binormal[1], a->binormal[2]), wo = V3(wo3[3 * i], wo3[3 * i + 1], wo3[3 * i + 2]);
+        const int entering = gdot(wo, N) >= 0.f; /* :782 */
+        const v3 Ns = entering ? N : V3(-N.x, -N.y, -N.z);
+        const v3 incident = V3(gdot(wo, T), gdot(wo, B), gdot(wo, Ns)); /* to_local, :783 */
+        v3 scattered = V3(0.f, 0.f, 0.f), weight = V3(0.f, 0.f, 0.f);
+        float pdf = 0.f;
+        uint32_t lobe = 0;
+        if (lobeSelect < pDiffuse) { /* :785-793, SampleDiffuse :252-278 */
+            lobe = 1;
+            const float r1 = rnd3[3 * i + 1];
+            const float z = sqrtf(r1), sinTheta = sqrtf(1.f - r1), phi = 2.f * pi * rnd3[3 * i + 2];
+            scattered = V3(sinTheta * cosf(phi), sinTheta * sinf(phi), z);
+            pdf = (scattered.z > 0.f) ? (scattered.z / pi) : 0.f;
+            const v3 halfway = gnormalize(v3add(incident, scattered));
+            const float iDotN = incident.z, sDotH = gdot(scattered, halfway), sDotN = scattered.z;
+            const float energyBias = lerp1(0.f, 0.5f, linearRoughness);
+            const float energyFactor = lerp1(1.f, 1.f / 1.51f, linearRoughness);
+            const float fd90 = energyBias + 2.f * sDotH * sDotH * linearRoughness;
+            const float lightScatter = schlick_dielectric(1.f, sDotN, fd90), viewScatter = schlick_dielectric(1.f, iDotN, fd90);
+            weight = v3s(v3s(v3s(dielectric, lightScatter), viewScatter), energyFactor);
+            weight = v3s(weight, (1.f - metallic) * (1.f - 0.f) / pDiffuse); /* :788 */
+            pdf *= pDiffuse;                                                 /* :790; the other lobes' probabilities are 0 */
+        }
+        /* from_local, :824: T * x + B * y + N * z */
+        const v3 world = v3add(v3add(v3s(T, scattered.x), v3s(B, scattered.y)), v3s(Ns, scattered.z));
+        out[i].scattered[0] = world.x, out[i].scattered[1] = world.y, out[i].scattered[2] = world.z;
+        out[i].pdf = pdf;
+        out[i].weight[0] = weight.x, out[i].weight[1] = weight.y, out[i].weight[2] = weight.z;
+        out[i].lobe = lobe;
+        returned[i] = 1;
+    }
+}

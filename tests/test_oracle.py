@@ -252,3 +252,40 @@ def test_port_equals_reference_on_random_hostile_inputs(built, oracle_mod):
         assert a["hits"].tobytes() == b["hits"].tobytes(), (it, kind)
         assert (a["steps"], a["isects"]) == (b["steps"], b["isects"]), (it, kind)
         assert a["attrs"].tobytes() == b["attrs"].tobytes(), (it, kind)
+
+
+def _bsdf_case(n=20000, seed=3):
+    """TraceResult-like records with every kind of frame: front / back facing, metallic 0 .. 1 (incl. exactly 1), rough 0 .. 1."""
+    from vistrace_b200 import abi
+
+    rng = np.random.default_rng(seed)
+    f4 = np.float32
+    a = np.zeros(n, abi.ATTR)
+    nrm = rng.normal(size=(n, 3)).astype(f4)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True).astype(f4)
+    t = np.cross(nrm, rng.normal(size=(n, 3))).astype(f4)
+    t /= np.linalg.norm(t, axis=1, keepdims=True).astype(f4)
+    a["normal"], a["tangent"], a["binormal"] = nrm, t, np.cross(t, nrm).astype(f4)
+    a["albedo"] = rng.uniform(0, 1.2, (n, 3)).astype(f4)  # > 1 exercises the clamp of PrepShadingData
+    a["metalness"] = rng.uniform(-0.1, 1.0, n).astype(f4)
+    a["metalness"][::17] = 1.0  # pDiffuse = 0: SampleBSDF falls through every branch
+    a["roughness"] = rng.uniform(-0.1, 1.1, n).astype(f4)
+    wo = rng.normal(size=(n, 3)).astype(f4)
+    wo /= np.linalg.norm(wo, axis=1, keepdims=True).astype(f4)
+    rnd = rng.uniform(0, 1, (n, 3)).astype(f4)
+    rnd[::13, 1] = 0.0  # r1 = 0: a sample in the tangent plane, pdf 0
+    return a, wo, rnd
+
+
+def test_bsdf_diffuse_port_equals_reference(oracle_mod):
+    """The C port's restatement of SampleBSDF (diffuse lobe) against the reference's own function driven by a scripted ISampler."""
+    if not oracle_mod.available("reference"):
+        pytest.skip("needs oracle/_ref")
+    a, wo, rnd = _bsdf_case()
+    want, wret = oracle_mod.sample_bsdf_diffuse(a, wo, rnd, "reference")
+    got, gret = oracle_mod.sample_bsdf_diffuse(a, wo, rnd, "port")
+    assert (wret == 1).all() and (gret == 1).all()
+    np.testing.assert_array_equal(got["lobe"], want["lobe"])
+    assert (want["lobe"][::17] == 0).all() and (want["lobe"] == 1).sum() > 0.9 * len(a)
+    for f in ("scattered", "pdf", "weight"):
+        np.testing.assert_array_equal(got[f].view(np.uint32), want[f].view(np.uint32), err_msg=f)  # same libm, same order: bit-identical

@@ -19,11 +19,15 @@ VT_ATTR_HIT_SKY = 2
 VT_ATTR_HIT_WATER = 4
 VT_TRAVERSE_DEVICE_PTRS = 1
 VT_TRAVERSE_ANY_HIT = 2
+VT_TRAVERSE_QUEUE_ATTRS = 4
+VT_PATHS_NO_COMPACTION = 8
+VT_LOBE_NONE, VT_LOBE_DIFFUSE_REFLECTION = 0, 1
 
 f4, u4, i4, u2, u1 = np.float32, np.uint32, np.int32, np.uint16, np.uint8
 
 RAY = np.dtype([("o", f4, 3), ("tmin", f4), ("d", f4, 3), ("tmax", f4)], align=False)
 HIT = np.dtype([("t", f4), ("u", f4), ("v", f4), ("prim", u4)], align=False)
+BSDF_SAMPLE = np.dtype([("scattered", f4, 3), ("pdf", f4), ("weight", f4, 3), ("lobe", u4)], align=False)  # vt_bsdf_sample = BSDFSample
 NODE = np.dtype([("bounds", f4, 6), ("prim_count", u4), ("first", u4)], align=False)
 TRI_IN = np.dtype(
     [

@@ -33,12 +33,17 @@ SYMBOLS = {
     "vt_accel_traverse_cones": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_result": (_i32, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "vt_accel_bounce_rays": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _u32, _vp]),
+    "vt_accel_sample_bsdf_rays": (_i32, [_vp, _vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
+    "vt_sample_uniform01": (C.c_float, [_u64, _u32, _u64]),
     "vt_accel_shadow_rays": (_i32, [_vp, _vp, _u64, _vp, _i32, C.c_float, _vp, _vp, _u32, _vp]),
     "vt_accel_bounce_rays_queued": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_shadow_rays_queued": (_i32, [_vp, _vp, _u64, _vp, _i32, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_traverse_queued": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
+    "vt_accel_bounce_rays_requeued": (_i32, [_vp, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "vt_accel_shadow_rays_requeued": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _i32, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_trace_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "vt_accel_render_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, C.c_float, _vp, _vp]),
+    "vt_accel_trace_paths": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _u64, C.c_float, _vp, _vp, _u32, _vp]),
     "vt_accel_accumulate_sky": (_i32, [_vp, _vp, _vp, _u64, _u32, C.c_float, _vp, _vp]),
     "vt_accel_set_layout": (_i32, [_vp, _i32]),
     "vt_accel_get_layout": (_i32, [_vp]),
@@ -367,6 +372,21 @@ class Accel:
                "vt_accel_bounce_rays")
         return out, live.value
 
+    def sample_bsdf_rays(self, rays, attrs, spp, seed=0):
+        """Host-buffer batched SampleBSDF (diffuse lobe): (rays[n*spp] with masked slots, BSDF_SAMPLE records[n*spp], number spawned)."""
+        rays = np.ascontiguousarray(rays, abi.RAY)
+        attrs = np.ascontiguousarray(attrs, abi.ATTR)
+        out = np.zeros(len(attrs) * spp, abi.RAY)
+        samples = np.zeros(len(attrs) * spp, abi.BSDF_SAMPLE)
+        live = C.c_uint64(0)
+        _check(self.L.vt_accel_sample_bsdf_rays(self.h, rays.ctypes.data, attrs.ctypes.data, len(attrs), spp, seed, out.ctypes.data, samples.ctypes.data,
+                                                C.addressof(live), None, None, None, 0, None), "vt_accel_sample_bsdf_rays")
+        return out, samples, live.value
+
+    def sample_bsdf_rays_device(self, d_rays, d_attrs, n, spp, seed, d_out, d_samples, d_queue=None, d_queue_count=None, d_miss_hits=None, stream=None):
+        _check(self.L.vt_accel_sample_bsdf_rays(self.h, _ptr(d_rays), _ptr(d_attrs), n, spp, seed, _ptr(d_out), _ptr(d_samples), None, _ptr(d_queue),
+                                                _ptr(d_queue_count), _ptr(d_miss_hits), abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)), "vt_accel_sample_bsdf_rays")
+
     def shadow_rays(self, attrs, light, point_light=False, tmax=3.4028234663852886e38):
         """Host-buffer shadow-ray generation: (rays[n] with masked slots, number spawned)."""
         attrs = np.ascontiguousarray(attrs, abi.ATTR)
@@ -398,9 +418,23 @@ class Accel:
                                                   _ptr(d_queue), _ptr(d_queue_count), _ptr(d_miss_hits), _ptr(stream)),
                "vt_accel_shadow_rays_queued")
 
-    def traverse_queued_device(self, d_rays, d_queue, d_queue_count, capacity, d_hits, d_attrs=None, any_hit=False, stream=None):
+    def traverse_queued_device(self, d_rays, d_queue, d_queue_count, capacity, d_hits, d_attrs=None, any_hit=False, stream=None, queue_attrs=False):
+        """queue_attrs: TraceResult only of the slots the queue lists (wave compaction)."""
+        flags = (abi.VT_TRAVERSE_ANY_HIT if any_hit else 0) | (abi.VT_TRAVERSE_QUEUE_ATTRS if queue_attrs else 0)
         _check(self.L.vt_accel_traverse_queued(self.h, _ptr(d_rays), _ptr(d_queue), _ptr(d_queue_count), capacity, _ptr(d_hits), _ptr(d_attrs),
-                                               abi.VT_TRAVERSE_ANY_HIT if any_hit else 0, _ptr(stream)), "vt_accel_traverse_queued")
+                                               flags, _ptr(stream)), "vt_accel_traverse_queued")
+
+    # ---- wave compaction: generators driven by the previous wave's queue
+    def bounce_rays_requeued_device(self, d_attrs, d_in_queue, d_in_count, n, spp, seed, d_out, d_queue, d_queue_count, d_miss_hits, stream=None):
+        _check(self.L.vt_accel_bounce_rays_requeued(self.h, _ptr(d_attrs), _ptr(d_in_queue), _ptr(d_in_count), n, spp, seed, _ptr(d_out), _ptr(d_queue),
+                                                    _ptr(d_queue_count), _ptr(d_miss_hits), _ptr(stream)), "vt_accel_bounce_rays_requeued")
+
+    def shadow_rays_requeued_device(self, d_attrs, d_in_queue, d_in_count, n, light, d_out, d_queue, d_queue_count, d_miss_hits, point_light=False,
+                                    tmax=3.4028234663852886e38, stream=None):
+        lv = (C.c_float * 3)(*[float(x) for x in light])
+        _check(self.L.vt_accel_shadow_rays_requeued(self.h, _ptr(d_attrs), _ptr(d_in_queue), _ptr(d_in_count), n, C.cast(lv, _vp), int(point_light), tmax,
+                                                    _ptr(d_out), _ptr(d_queue), _ptr(d_queue_count), _ptr(d_miss_hits), _ptr(stream)),
+               "vt_accel_shadow_rays_requeued")
 
     def trace_diffuse_wave(self, rays, spp, seed=0, want_attrs=False, want_bounce_rays=False, out=None):
         """Host-buffer wave.  `out` may carry preallocated (e.g. pinned) numpy views: hits, bounce_hits, attrs, bounce_rays."""
@@ -436,6 +470,16 @@ class Accel:
                "vt_accel_render_diffuse_wave")
         return fb, live.value
 
+    def trace_paths_device(self, d_rays, n, bounces, sun_dir, sun_rgb, seed, weight, d_fb, want_counts=False, compact=True, stream=None):
+        """Path waves with compaction over device-resident primary rays; returns the per-wave ray counts when asked (synchronous then)."""
+        sd = (C.c_float * 3)(*[float(x) for x in sun_dir])
+        sc = (C.c_float * 3)(*[float(x) for x in sun_rgb])
+        counts = np.zeros(2 + 2 * bounces, np.uint64) if want_counts else None
+        flags = abi.VT_TRAVERSE_DEVICE_PTRS | (0 if compact else abi.VT_PATHS_NO_COMPACTION)
+        _check(self.L.vt_accel_trace_paths(self.h, _ptr(d_rays), n, bounces, C.cast(sd, _vp), C.cast(sc, _vp), seed, weight, _ptr(d_fb), _ptr(counts),
+                                           flags, _ptr(stream)), "vt_accel_trace_paths")
+        return counts
+
     def accumulate_sky_device(self, d_attrs, d_bounce_hits, n, spp, weight, d_fb, stream=None):
         _check(self.L.vt_accel_accumulate_sky(self.h, _ptr(d_attrs), _ptr(d_bounce_hits), n, spp, weight, _ptr(d_fb), _ptr(stream)),
                "vt_accel_accumulate_sky")
@@ -464,6 +508,12 @@ def shard_indices(n, world, rank, tile):
     idx = idx[idx < n]
     assert len(idx) == cnt.value
     return idx
+
+
+def sample_uniform01(slots, dim, seed):
+    """The generators' counter-based random numbers for an array of slots (host-only)."""
+    L = lib()
+    return np.array([L.vt_sample_uniform01(int(s), dim, seed) for s in np.asarray(slots).reshape(-1)], np.float32)
 
 
 def group_unique_id():

@@ -16,6 +16,7 @@
 #include <string>
 
 #include "vt_accel_internal.h"
+#include "vt_math.cuh"
 
 namespace vt {
 
@@ -401,6 +402,8 @@ void AccelStruct::Upload(const vt_scene &scene) {
     if (blocks < 1) blocks = 1;
     const int mult = env_int("VT_GRID_BLOCKS_PER_SM", blocks);
     D.cfg.grid = D.sm_count * std::max(1, std::min(mult, blocks));
+    D.cfg.sm_count = D.sm_count;
+    D.cfg.min_rays_per_lane = env_int("VT_K1_RAYS_PER_LANE", D.cfg.min_rays_per_lane);
     mAccelBuilt = true;
 }
 
@@ -494,6 +497,8 @@ void AccelStruct::AllocReplica(const ReplicaImage &img, void *bufs[10]) {
     if (blocks < 1) blocks = 1;
     const int mult = env_int("VT_GRID_BLOCKS_PER_SM", blocks);
     D.cfg.grid = D.sm_count * std::max(1, std::min(mult, blocks));
+    D.cfg.sm_count = D.sm_count;
+    D.cfg.min_rays_per_lane = env_int("VT_K1_RAYS_PER_LANE", D.cfg.min_rays_per_lane);
     mReplica = true;
     mBvhStale = false;
     mAccelBuilt = true;  // valid once the caller has filled the buffers (it does so before anything is enqueued)
@@ -781,6 +786,51 @@ void AccelStruct::BounceRays(const vt_attr *attrs, uint64_t n, uint32_t spp, uin
     }
 }
 
+void AccelStruct::SampleBsdfRays(const vt_ray *rays, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays,
+                                 vt_bsdf_sample *samples, uint64_t *live_out, uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits,
+                                 uint32_t flags, void *stream_) {
+    if (live_out) *live_out = 0;
+    if (n == 0 || spp == 0) return;
+    if (!rays || !attrs || !out_rays || !samples) throw std::runtime_error("sample_bsdf_rays: null argument");
+    const bool dev_ptrs = (flags & VT_TRAVERSE_DEVICE_PTRS) != 0;
+    if ((queue || queue_count || miss_hits) && !(queue && queue_count && miss_hits && dev_ptrs))
+        throw std::runtime_error("sample_bsdf_rays: the queue needs queue, queue_count and miss_hits, as device pointers");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : (dev_ptrs ? (cudaStream_t) nullptr : D.own_stream);
+    D.live.ensure(1);
+    if (live_out) VT_CUDA(cudaMemsetAsync(D.live.p, 0, sizeof(unsigned long long), stream));
+    if (queue_count) VT_CUDA(cudaMemsetAsync(queue_count, 0, sizeof(uint64_t), stream));
+    const vt_ray *d_rays = rays;
+    const vt_attr *d_attrs = attrs;
+    vt_ray *d_out = out_rays;
+    vt_bsdf_sample *d_samples = samples;
+    if (!dev_ptrs) {
+        D.s_rays2.ensure(n);
+        D.s_attrs.ensure(n);
+        D.s_rays.ensure(n * spp);
+        D.s_samples.ensure(n * spp);
+        VT_CUDA(cudaMemcpyAsync(D.s_rays2.p, rays, n * sizeof(vt_ray), cudaMemcpyHostToDevice, stream));
+        VT_CUDA(cudaMemcpyAsync(D.s_attrs.p, attrs, n * sizeof(vt_attr), cudaMemcpyHostToDevice, stream));
+        d_rays = D.s_rays2.p, d_attrs = D.s_attrs.p, d_out = D.s_rays.p, d_samples = D.s_samples.p;
+    }
+    VT_CUDA(vt_launch_bsdf_diffuse_rays(d_rays, d_attrs, n, spp, seed, d_out, d_samples, live_out ? D.live.p : nullptr, stream, queue,
+                                        (unsigned long long *)queue_count, miss_hits));
+    mLaunches++;
+    if (!dev_ptrs) {
+        VT_CUDA(cudaMemcpyAsync(out_rays, d_out, n * spp * sizeof(vt_ray), cudaMemcpyDeviceToHost, stream));
+        VT_CUDA(cudaMemcpyAsync(samples, d_samples, n * spp * sizeof(vt_bsdf_sample), cudaMemcpyDeviceToHost, stream));
+    }
+    if (live_out) {
+        unsigned long long v = 0;
+        VT_CUDA(cudaMemcpyAsync(&v, D.live.p, sizeof(v), cudaMemcpyDeviceToHost, stream));
+        VT_CUDA(cudaStreamSynchronize(stream));
+        *live_out = v;
+    } else if (!dev_ptrs) {
+        VT_CUDA(cudaStreamSynchronize(stream));
+    }
+}
+
 void AccelStruct::ShadowRays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out_rays,
                              uint64_t *live_out, uint32_t flags, void *stream_) {
     if (live_out) *live_out = 0;
@@ -815,7 +865,9 @@ void AccelStruct::ShadowRays(const vt_attr *attrs, uint64_t n, const float light
 }
 
 void AccelStruct::BounceRaysQueued(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays, uint32_t *queue,
-                                   uint64_t *queue_count, vt_hit *miss_hits, void *stream_) {
+                                   uint64_t *queue_count, vt_hit *miss_hits, void *stream_, const uint32_t *in_queue, const uint64_t *in_count) {
+    if ((in_queue == nullptr) != (in_count == nullptr)) throw std::runtime_error("bounce_rays_queued: in_queue and in_count go together");
+    if (in_queue && (in_queue == queue || in_count == queue_count)) throw std::runtime_error("bounce_rays_queued: the input queue must not be the output queue");
     if (!attrs || !out_rays || !queue || !queue_count || !miss_hits) throw std::runtime_error("bounce_rays_queued: null argument");
     if (spp == 0) throw std::runtime_error("bounce_rays_queued: spp must be positive");
     if (n * spp > 0xFFFFFFFFull) throw std::runtime_error("bounce_rays_queued: more than 2^32 slots");
@@ -823,12 +875,16 @@ void AccelStruct::BounceRaysQueued(const vt_attr *attrs, uint64_t n, uint32_t sp
     cudaStream_t stream = (cudaStream_t)stream_;
     VT_CUDA(cudaMemsetAsync(queue_count, 0, sizeof(uint64_t), stream));
     if (n == 0) return;
-    VT_CUDA(vt_launch_bounce_rays(attrs, n, spp, seed, 0, out_rays, nullptr, stream, queue, (unsigned long long *)queue_count, miss_hits));
+    VT_CUDA(vt_launch_bounce_rays(attrs, n, spp, seed, 0, out_rays, nullptr, stream, queue, (unsigned long long *)queue_count, miss_hits, nullptr,
+                                  in_queue, (const unsigned long long *)in_count));
     mLaunches++;
 }
 
 void AccelStruct::ShadowRaysQueued(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax,
-                                   vt_ray *out_rays, uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream_) {
+                                   vt_ray *out_rays, uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream_,
+                                   const uint32_t *in_queue, const uint64_t *in_count) {
+    if ((in_queue == nullptr) != (in_count == nullptr)) throw std::runtime_error("shadow_rays_queued: in_queue and in_count go together");
+    if (in_queue && (in_queue == queue || in_count == queue_count)) throw std::runtime_error("shadow_rays_queued: the input queue must not be the output queue");
     if (!attrs || !out_rays || !light || !queue || !queue_count || !miss_hits) throw std::runtime_error("shadow_rays_queued: null argument");
     if (n > 0xFFFFFFFFull) throw std::runtime_error("shadow_rays_queued: more than 2^32 slots");
     VT_CUDA(cudaSetDevice(mDevice));
@@ -836,7 +892,7 @@ void AccelStruct::ShadowRaysQueued(const vt_attr *attrs, uint64_t n, const float
     VT_CUDA(cudaMemsetAsync(queue_count, 0, sizeof(uint64_t), stream));
     if (n == 0) return;
     VT_CUDA(vt_launch_shadow_rays(attrs, n, light, point_light, tmax, out_rays, nullptr, stream, queue, (unsigned long long *)queue_count,
-                                  miss_hits));
+                                  miss_hits, in_queue, (const unsigned long long *)in_count));
     mLaunches++;
 }
 
@@ -855,8 +911,13 @@ void AccelStruct::TraverseQueued(const vt_ray *rays, const uint32_t *queue, cons
     VT_CUDA(vt_launch_traverse(D.view, rays, hits, capacity, (flags & VT_TRAVERSE_ANY_HIT) != 0, ctr, D.cfg, stream, false, queue,
                                (const unsigned long long *)queue_count));
     mLaunches++;
-    if (attrs) {  // eager TraceResult of every slot: hits[] is complete once the generator has written its miss records
-        VT_CUDA(vt_launch_trace_result(D.view, rays, hits, nullptr, attrs, capacity, stream));
+    if (attrs) {
+        // eager TraceResult of every slot (hits[] is complete once the generator has written its miss records), or — wave
+        // compaction, VT_TRAVERSE_QUEUE_ATTRS — only of the slots the queue lists
+        if (flags & VT_TRAVERSE_QUEUE_ATTRS)
+            VT_CUDA(vt_launch_trace_result(D.view, rays, hits, nullptr, attrs, capacity, stream, queue, (const unsigned long long *)queue_count));
+        else
+            VT_CUDA(vt_launch_trace_result(D.view, rays, hits, nullptr, attrs, capacity, stream));
         mLaunches++;
     }
 }
@@ -1091,6 +1152,78 @@ void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp
     }
 }
 
+void AccelStruct::TracePaths(const vt_ray *rays, uint64_t n, uint32_t bounces, const float sun_dir[3], const float sun_rgb[3], uint64_t seed,
+                             float weight, float *fb, uint64_t *ray_counts, bool compact, void *stream_) {
+    check_built(mAccelBuilt);
+    if (n == 0) return;
+    if (!rays || !fb || !sun_dir || !sun_rgb) throw std::runtime_error("trace_paths: null argument");
+    if (bounces > 8) throw std::runtime_error("trace_paths: at most 8 bounces");
+    if (n > 0xFFFFFFFFull) throw std::runtime_error("trace_paths: more than 2^32 paths per call");
+    if (((uintptr_t)rays & 31)) throw std::runtime_error("trace_paths: device ray buffers must be 32-byte aligned");
+    VT_CUDA(cudaSetDevice(mDevice));
+    DeviceScene &D = *mpDevice;
+    DeviceScene::PathScratch &P = D.path;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    for (int i = 0; i < 2; i++) P.hits[i].ensure(n), P.attrs[i].ensure(n);
+    for (int i = 0; i < 3; i++) P.queue[i].ensure(n);
+    P.shits.ensure(n), P.brays.ensure(n), P.srays.ensure(n), P.throughput.ensure(3 * n);
+    P.counts.ensure(32);
+    VT_CUDA(cudaMemsetAsync(P.counts.p, 0, 32 * sizeof(unsigned long long), stream));
+    auto next_counter = [&]() {
+        unsigned long long *c = D.counters.p + 2 * (D.next_slot.fetch_add(1) % kCounterSlots);
+        VT_CUDA(cudaMemsetAsync(c, 0, 16, stream));
+        return c;
+    };
+    auto count = [&](int i) { return P.counts.p + i; };
+    auto record = [&](int slot, const unsigned long long *src) {  // rays of a wave = what its queue counted
+        VT_CUDA(cudaMemcpyAsync(P.counts.p + slot, src, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+    };
+    // ---- primary wave: K1 + K2 over every ray, then one shadow ray per surface hit (any hit), then shading
+    VT_CUDA(vt_launch_traverse(D.view, rays, P.hits[0].p, n, false, next_counter(), D.cfg, stream));
+    VT_CUDA(vt_launch_trace_result(D.view, rays, P.hits[0].p, nullptr, P.attrs[0].p, n, stream));
+    uint32_t *q_live = P.queue[0].p, *q_next = P.queue[1].p, *q_shadow = P.queue[2].p;  // live vertices of this wave / of the next / shadow rays
+    unsigned long long *c_live = count(0), *c_next = count(1), *c_shadow = count(2);
+    VT_CUDA(vt_launch_shadow_rays(P.attrs[0].p, n, sun_dir, false, FLT_MAX, P.srays.p, nullptr, stream, q_shadow, c_shadow, P.shits.p));
+    VT_CUDA(vt_launch_traverse(D.view, P.srays.p, P.shits.p, n, true, next_counter(), D.cfg, stream, false, q_shadow, c_shadow));
+    VT_CUDA(vt_launch_path_shade(P.attrs[0].p, P.shits.p, nullptr, nullptr, n, true, weight, sun_rgb, P.throughput.p, fb, stream));
+    record(9, c_shadow);
+    mLaunches += 5;
+    int cur = 0;
+    bool have_live_queue = false;  // the primary wave has no queue: every slot is a vertex
+    for (uint32_t k = 0; k < bounces; k++) {
+        const int nxt = cur ^ 1;
+        // bounce rays of the live vertices of wave k -> slots of wave k + 1 (slot = pixel), listed in q_next
+        VT_CUDA(cudaMemsetAsync(c_next, 0, sizeof(unsigned long long), stream));
+        const bool from_queue = compact && have_live_queue;
+        VT_CUDA(vt_launch_bounce_rays(P.attrs[cur].p, n, 1, seed + 0x9E3779B97F4A7C15ull * (k + 1), 0, P.brays.p, nullptr, stream, q_next, c_next, P.hits[nxt].p, nullptr,
+                                      from_queue ? q_live : nullptr, from_queue ? c_live : nullptr));
+        VT_CUDA(vt_launch_traverse(D.view, P.brays.p, P.hits[nxt].p, n, false, next_counter(), D.cfg, stream, false, q_next, c_next));
+        if (compact) VT_CUDA(vt_launch_trace_result(D.view, P.brays.p, P.hits[nxt].p, nullptr, P.attrs[nxt].p, n, stream, q_next, c_next));
+        else VT_CUDA(vt_launch_trace_result(D.view, P.brays.p, P.hits[nxt].p, nullptr, P.attrs[nxt].p, n, stream));
+        record(10 + 2 * k, c_next);
+        // shadow rays of wave k + 1's vertices
+        VT_CUDA(cudaMemsetAsync(c_shadow, 0, sizeof(unsigned long long), stream));
+        VT_CUDA(vt_launch_shadow_rays(P.attrs[nxt].p, n, sun_dir, false, FLT_MAX, P.srays.p, nullptr, stream, q_shadow, c_shadow, P.shits.p,
+                                      compact ? q_next : nullptr, compact ? c_next : nullptr));
+        VT_CUDA(vt_launch_traverse(D.view, P.srays.p, P.shits.p, n, true, next_counter(), D.cfg, stream, false, q_shadow, c_shadow));
+        record(11 + 2 * k, c_shadow);
+        VT_CUDA(vt_launch_path_shade(P.attrs[nxt].p, P.shits.p, q_next, c_next, n, false, weight, sun_rgb, P.throughput.p, fb, stream));
+        mLaunches += 6;
+        std::swap(q_live, q_next);
+        std::swap(c_live, c_next);
+        have_live_queue = true;
+        cur = nxt;
+    }
+    if (ray_counts) {  // [0] = primary rays, [1] = their shadow rays, [2 + 2k], [3 + 2k] = bounce k + 1 and its shadow rays
+        unsigned long long h[32];
+        VT_CUDA(cudaMemcpyAsync(h, P.counts.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        VT_CUDA(cudaStreamSynchronize(stream));
+        ray_counts[0] = n;
+        ray_counts[1] = h[9];
+        for (uint32_t k = 0; k < bounces; k++) ray_counts[2 + 2 * k] = h[10 + 2 * k], ray_counts[3 + 2 * k] = h[11 + 2 * k];
+    }
+}
+
 void AccelStruct::AccumulateSky(const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n, uint32_t spp, float weight,
                                 float *fb, void *stream_) {
     check_built(mAccelBuilt);
@@ -1243,6 +1376,18 @@ int vt_accel_bounce_rays(vt_accel *a, const vt_attr *attrs, uint64_t n, uint32_t
     VT_CATCH(1)
 }
 
+int vt_accel_sample_bsdf_rays(vt_accel *a, const vt_ray *rays, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays,
+                              vt_bsdf_sample *out_samples, uint64_t *live_out, uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits,
+                              uint32_t flags, void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.SampleBsdfRays(rays, attrs, n, spp, seed, out_rays, out_samples, live_out, queue, queue_count, miss_hits, flags, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+float vt_sample_uniform01(uint64_t slot, uint32_t dim, uint64_t seed) { return vt_uniform01(slot, dim, seed); }
+
 int vt_accel_shadow_rays(vt_accel *a, const vt_attr *attrs, uint64_t n, const float light[3], int point_light, float tmax,
                          vt_ray *out_rays, uint64_t *live_out, uint32_t flags, void *stream) {
     VT_TRY
@@ -1266,6 +1411,25 @@ int vt_accel_shadow_rays_queued(vt_accel *a, const vt_attr *attrs, uint64_t n, c
     VT_TRY
     if (!a) throw std::runtime_error("null argument");
     a->impl.ShadowRaysQueued(attrs, n, light, point_light != 0, tmax, out_rays, queue, queue_count, miss_hits, stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_bounce_rays_requeued(vt_accel *a, const vt_attr *attrs, const uint32_t *in_queue, const uint64_t *in_count, uint64_t n, uint32_t spp,
+                                  uint64_t seed, vt_ray *out_rays, uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream) {
+    VT_TRY
+    if (!a || !in_queue || !in_count) throw std::runtime_error("null argument");
+    a->impl.BounceRaysQueued(attrs, n, spp, seed, out_rays, queue, queue_count, miss_hits, stream, in_queue, in_count);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_shadow_rays_requeued(vt_accel *a, const vt_attr *attrs, const uint32_t *in_queue, const uint64_t *in_count, uint64_t n,
+                                  const float light[3], int point_light, float tmax, vt_ray *out_rays, uint32_t *queue, uint64_t *queue_count,
+                                  vt_hit *miss_hits, void *stream) {
+    VT_TRY
+    if (!a || !in_queue || !in_count) throw std::runtime_error("null argument");
+    a->impl.ShadowRaysQueued(attrs, n, light, point_light != 0, tmax, out_rays, queue, queue_count, miss_hits, stream, in_queue, in_count);
     return 0;
     VT_CATCH(1)
 }
@@ -1294,6 +1458,16 @@ int vt_accel_render_diffuse_wave(vt_accel *a, const vt_ray *rays, uint64_t n, ui
     VT_TRY
     if (!a) throw std::runtime_error("null argument");
     a->impl.RenderDiffuseWave(rays, n, spp, seed, weight, framebuffer_rgb, live_out);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_trace_paths(vt_accel *a, const vt_ray *rays, uint64_t n, uint32_t bounces, const float sun_dir[3], const float sun_rgb[3],
+                         uint64_t seed, float weight, float *framebuffer_rgb, uint64_t *ray_counts, uint32_t flags, void *stream) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    if (!(flags & VT_TRAVERSE_DEVICE_PTRS)) throw std::runtime_error("vt_accel_trace_paths: device pointers only (VT_TRAVERSE_DEVICE_PTRS)");
+    a->impl.TracePaths(rays, n, bounces, sun_dir, sun_rgb, seed, weight, framebuffer_rgb, ray_counts, !(flags & VT_PATHS_NO_COMPACTION), stream);
     return 0;
     VT_CATCH(1)
 }

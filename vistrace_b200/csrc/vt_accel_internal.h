@@ -78,6 +78,8 @@ struct DeviceScene {
     DevBuf<vt_hit> s_hits;
     DevBuf<vt_attr> s_attrs;
     DevBuf<float> s_cones;
+    DevBuf<vt_bsdf_sample> s_samples;
+    DevBuf<vt_ray> s_rays2;
     // per-stream tile staging of the host-pointer diffuse wave
     struct WaveLane {
         cudaStream_t stream = nullptr;
@@ -95,6 +97,16 @@ struct DeviceScene {
     };
     std::map<cudaStream_t, WaveScratch> wave_scratch;
     std::mutex wave_mutex;
+    // scratch of vt_accel_trace_paths (multi-bounce path waves with compaction): two generations of hit / TraceResult records,
+    // the secondary rays of a wave, three slot queues + their counters, per-pixel path throughput
+    struct PathScratch {
+        DevBuf<vt_hit> hits[2], shits;
+        DevBuf<vt_attr> attrs[2];
+        DevBuf<vt_ray> brays, srays;
+        DevBuf<uint32_t> queue[3];
+        DevBuf<unsigned long long> counts;  // [0..2]: the three queue counters, [8 + 2k], [9 + 2k]: rays of wave k (bounce, shadow)
+        DevBuf<float> throughput;
+    } path;
     DevBuf<unsigned long long> live;
     // host-pointer waves: the whole frame's rays are staged here by ONE copy stream, tile after tile, so an upload never
     // waits for the lane (stream) its tile will run on; upload_done[k] gates tile k's kernels
@@ -129,7 +141,12 @@ struct DeviceScene {
         s_hits.release();
         s_attrs.release();
         s_cones.release();
+        s_samples.release();
+        s_rays2.release();
         live.release();
+        for (int i = 0; i < 2; i++) path.hits[i].release(), path.attrs[i].release();
+        for (int i = 0; i < 3; i++) path.queue[i].release();
+        path.shits.release(), path.brays.release(), path.srays.release(), path.counts.release(), path.throughput.release();
         wave_rays.release();
         for (cudaEvent_t e : upload_done) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);

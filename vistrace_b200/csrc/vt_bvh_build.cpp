@@ -560,6 +560,7 @@ struct QuadBuilder {
     uint64_t n_tris;
     QuadBvh &out;
     std::string &err;
+    const CollapsePlan &plan;
     bool ok = true;
 
     static float half_area(const vt_node &n) {
@@ -576,35 +577,12 @@ struct QuadBuilder {
     uint32_t emit(uint32_t ni, uint32_t depth, uint32_t *need) {
         const size_t node_count = bvh.nodes.size();
         uint32_t kids[4];
-        int nk = 2;
-        kids[0] = bvh.nodes[ni].first;
-        kids[1] = kids[0] + 1;
-        if (kids[0] == 0 || (size_t)kids[1] >= node_count || depth > 64) {
+        if (bvh.nodes[ni].first == 0 || (size_t)bvh.nodes[ni].first + 1 >= node_count || depth > 64) {
             fail("quad layout: malformed hierarchy");
             *need = 0;
             return 0;
         }
-        while (nk < 4) {  // adopt the children of the inner child with the largest box
-            int best = -1;
-            float best_area = -1.f;
-            for (int i = 0; i < nk; i++) {
-                const vt_node &c = bvh.nodes[kids[i]];
-                if (c.prim_count == 0 && half_area(c) > best_area) {
-                    best_area = half_area(c);
-                    best = i;
-                }
-            }
-            if (best < 0) break;
-            const uint32_t f = bvh.nodes[kids[best]].first;
-            if (f == 0 || (size_t)f + 1 >= node_count) {
-                fail("quad layout: malformed hierarchy");
-                break;
-            }
-            for (int i = nk; i > best + 1; i--) kids[i] = kids[i - 1];  // keep left-to-right order
-            kids[best] = f;
-            kids[best + 1] = f + 1;
-            nk++;
-        }
+        const int nk = plan.children(bvh, ni, kids);
         const uint32_t qi = (uint32_t)out.quads.size();
         if (out.quads.size() > bvh.nodes.size()) {  // not a tree: a node is reachable twice
             fail("BVH is not a tree (a node pair is referenced twice)");
@@ -705,7 +683,9 @@ bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string 
         return out.leaf_order.size() == n_tris;
     }
     out.quads.reserve(bvh.nodes.size() / 3 + 1);
-    QuadBuilder b{bvh, n_tris, out, err};
+    CollapsePlan plan;
+    if (!plan_collapse(bvh, 4, plan, err)) return false;
+    QuadBuilder b{bvh, n_tris, out, err, plan};
     uint32_t need = 0;
     b.emit(0, 0, &need);
     if (!b.ok) return false;

@@ -1,0 +1,149 @@
+// vt_bvh_collapse.cpp — choosing the children of the wide (4- / 8-wide) nodes: SAH-optimal collapse of the binary hierarchy by
+// dynamic programming (Ylitie, Karras, Laine, HPG 2017, section 3.1; the published algorithm restated, no code of theirs).
+//
+//   cost(n, 1) = A(n) * c_node + distribute(n, W)              n becomes a wide node with up to W children        (inner n)
+//   cost(n, i) = min(distribute(n, i), cost(n, i - 1))         n's subtree presented as at most i roots, 1 < i < W
+//   distribute(n, j) = min over 0 < k < j of cost(left, k) + cost(right, j - k)
+//   cost(leaf, i) = A(leaf) * triangles * c_prim
+//
+// Leaves are kept as the builder made them (no triangles are merged or moved), so the set of triangles a ray can reach through a
+// given box is unchanged; only how many box tests and dependent fetches it takes to get there.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+#include "vt_host.h"
+
+namespace vt {
+
+namespace {
+float half_area(const vt_node &n) {
+    const float dx = n.bounds[1] - n.bounds[0], dy = n.bounds[3] - n.bounds[2], dz = n.bounds[5] - n.bounds[4];
+    return dx * dy + dy * dz + dz * dx;
+}
+}  // namespace
+
+bool plan_collapse(const HostBvh &bvh, int width, CollapsePlan &plan, std::string &err) {
+    plan.width = width;
+    plan.split.clear();
+    const char *mode = std::getenv("VT_COLLAPSE");
+    plan.greedy = mode && std::string(mode) == "greedy";
+    const size_t n = bvh.nodes.size();
+    if (plan.greedy || n == 0 || bvh.nodes[0].prim_count != 0) return true;
+    if (width < 2 || width > 8) {
+        err = "collapse: width must be 2..8";
+        return false;
+    }
+    const float c_node = 1.0f;
+    const char *cp = std::getenv("VT_COLLAPSE_CPRIM");
+    const float c_prim = (cp && *cp) ? (float)std::atof(cp) : 0.6f;
+    // pre-order, parents before children (children need not have larger indices in a caller's tree)
+    std::vector<uint32_t> order;
+    order.reserve(n);
+    std::vector<uint32_t> stack{0u};
+    while (!stack.empty()) {
+        const uint32_t i = stack.back();
+        stack.pop_back();
+        order.push_back(i);
+        if (order.size() > n) {
+            err = "collapse: hierarchy is not a tree";
+            return false;
+        }
+        const vt_node &nd = bvh.nodes[i];
+        if (nd.prim_count == 0) {
+            if (nd.first == 0 || (size_t)nd.first + 1 >= n) {
+                err = "collapse: malformed hierarchy";
+                return false;
+            }
+            stack.push_back(nd.first);
+            stack.push_back(nd.first + 1);
+        }
+    }
+    const int W = width;
+    std::vector<float> cost(n * (size_t)W);  // cost[node * W + (i - 1)], i = 1 .. W - 1 used; slot W - 1 holds distribute(n, W)
+    plan.split.assign(n * (size_t)W, 0);
+    for (size_t q = order.size(); q-- > 0;) {  // children before parents
+        const uint32_t ni = order[q];
+        const vt_node &nd = bvh.nodes[ni];
+        float *c = &cost[(size_t)ni * W];
+        uint8_t *sp = &plan.split[(size_t)ni * W];
+        if (nd.prim_count != 0) {
+            const float leaf = half_area(nd) * (float)nd.prim_count * c_prim;
+            for (int i = 0; i < W; i++) c[i] = leaf;
+            continue;
+        }
+        const float *cl = &cost[(size_t)nd.first * W], *cr = &cost[((size_t)nd.first + 1) * W];
+        // distribute(n, j) for j = 2 .. W; a child may take 1 .. W - 1 roots
+        float dist[9];
+        uint8_t dk[9];
+        for (int j = 2; j <= W; j++) {
+            float best = std::numeric_limits<float>::max();
+            int bk = 1;
+            for (int k = 1; k < j; k++) {
+                const float v = cl[k - 1] + cr[j - k - 1];
+                if (v < best) best = v, bk = k;
+            }
+            dist[j] = best, dk[j] = (uint8_t)bk;
+        }
+        c[0] = half_area(nd) * c_node + dist[W];
+        sp[0] = dk[W];  // the wide node's own children: forest of W roots split dk[W] : W - dk[W]
+        for (int i = 2; i < W; i++) {
+            if (dist[i] < c[i - 2]) c[i - 1] = dist[i], sp[i - 1] = dk[i];
+            else c[i - 1] = c[i - 2], sp[i - 1] = 0;  // one root fewer is cheaper
+        }
+    }
+    return true;
+}
+
+int CollapsePlan::children(const HostBvh &bvh, uint32_t ni, uint32_t *kids) const {
+    const uint32_t first = bvh.nodes[ni].first;
+    if (greedy || split.empty()) {  // adopt the children of the inner child with the largest box until the node is full
+        int nk = 2;
+        kids[0] = first, kids[1] = first + 1;
+        while (nk < width) {
+            int best = -1;
+            float best_area = -1.f;
+            for (int i = 0; i < nk; i++) {
+                const vt_node &c = bvh.nodes[kids[i]];
+                if (c.prim_count == 0 && half_area(c) > best_area) best_area = half_area(c), best = i;
+            }
+            if (best < 0) break;
+            const uint32_t f = bvh.nodes[kids[best]].first;
+            for (int i = nk; i > best + 1; i--) kids[i] = kids[i - 1];  // keep left-to-right order
+            kids[best] = f, kids[best + 1] = f + 1;
+            nk++;
+        }
+        return nk;
+    }
+    // forest(node, i): the roots that present `node`'s subtree with a budget of i
+    struct Item {
+        uint32_t node;
+        int budget;
+    };
+    Item todo[16];
+    int nt = 0, nk = 0;
+    const int k0 = split[(size_t)ni * width];
+    todo[nt++] = {first + 1, width - k0};
+    todo[nt++] = {first, k0};
+    while (nt) {
+        const Item it = todo[--nt];
+        const vt_node &nd = bvh.nodes[it.node];
+        int b = it.budget;
+        if (nd.prim_count != 0) {
+            kids[nk++] = it.node;
+            continue;
+        }
+        int k = 0;
+        while (b > 1 && (k = split[(size_t)it.node * width + (b - 1)]) == 0) b--;  // "one root fewer" chain
+        if (b <= 1) {
+            kids[nk++] = it.node;  // stays one root: a wide node of its own (or it would have been split)
+            continue;
+        }
+        todo[nt++] = {nd.first + 1, b - k};
+        todo[nt++] = {nd.first, k};
+    }
+    return nk;
+}
+
+}  // namespace vt

@@ -424,20 +424,30 @@ public:
     // One member's share.  Host rays: the shard is cut into chunks that run on the handle's wave lanes, uploads on its copy
     // stream, so copies overlap kernels as in AccelStruct::RenderDiffuseWave.  Device rays (compact shard): ONE chunk on `stream`.
     // The compact shard image is left in m.fb_local; with fb_host it is also written to the caller's frame (tile-strided D2H).
+    // after_chunk(j0, j1, stream): called once the kernels of local tiles [j0, j1) are enqueued on `stream` — the hook the
+    // multi-process path uses to ship a finished chunk to rank 0 while later chunks are still being traced.  The chunk
+    // schedule is computed from geometry `sched` (rank 0's, the longest shard) so that every rank cuts at the same tile indices.
     void member_render(Member &m, const ShardGeom &g, const vt_ray *rays, bool rays_on_device, uint32_t spp, uint64_t seed, float weight,
-                       float *fb_host, bool count_live, cudaStream_t caller_stream) {
+                       float *fb_host, bool count_live, cudaStream_t caller_stream, const ShardGeom *sched = nullptr,
+                       const std::function<void(uint64_t, uint64_t, cudaStream_t)> &after_chunk = nullptr) {
         AccelStruct &A = m.accel->impl;
         if (!A.Built()) throw std::runtime_error("vt_group: populate the group first");
         VT_CUDA(cudaSetDevice(m.device));
         DeviceScene &D = *A.mpDevice;
         const uint64_t lt = g.local_tiles(), L = g.local_records();
+        const uint64_t lt_sched = sched ? sched->local_tiles() : lt;  // >= lt
         m.live = 0;
-        if (L == 0) return;
+        if (L == 0 && !after_chunk) return;
         if (L * spp > 0xFFFFFFFFull) throw std::runtime_error("vt_group: more than 2^32 bounce slots per GPU");
-        m.fb_local.ensure(L * 3);
+        m.fb_local.ensure(std::max<uint64_t>(1, L * 3));
         D.live.ensure(1);
         auto next_counter = [&]() { return D.counters.p + 2 * (D.next_slot.fetch_add(1) % kCounterSlots); };
-        const int n_lanes = rays_on_device ? 1 : std::max(1, std::min(8, env_int("VT_WAVE_LANES", 4)));
+        // device-resident shards may also be cut into chunks on several lanes (VT_GROUP_DEV_LANES > 1): a small shard's K1 launches
+        // are latency-bound (the slowest ray's dependent chain, ~0.1 ms), so one chunk's primary wave overlapping another chunk's
+        // bounce wave keeps the SMs busier; the lanes are fenced against the caller's stream on both sides
+        const int dev_lanes = std::max(1, std::min(8, env_int("VT_GROUP_DEV_LANES", 1)));
+        const int n_lanes = rays_on_device ? dev_lanes : std::max(1, std::min(8, env_int("VT_WAVE_LANES", 4)));
+        const bool on_caller = rays_on_device && n_lanes == 1;  // everything goes straight onto the caller's stream
         for (int i = 0; i < n_lanes; i++)
             if (!D.lanes[i].stream) VT_CUDA(cudaStreamCreateWithFlags(&D.lanes[i].stream, cudaStreamNonBlocking));
         if (count_live) {
@@ -445,28 +455,39 @@ public:
             VT_CUDA(cudaMemsetAsync(D.live.p, 0, sizeof(unsigned long long), s0));
             if (!rays_on_device) VT_CUDA(cudaStreamSynchronize(s0));
         }
+        if (rays_on_device && !on_caller) {  // lanes start after whatever the caller enqueued before this call
+            VT_CUDA(cudaEventRecord(m.caller_done, caller_stream));
+            for (int i = 0; i < n_lanes; i++) VT_CUDA(cudaStreamWaitEvent(D.lanes[i].stream, m.caller_done, 0));
+        }
         VtLaunchConfig cfg = D.cfg;
         if (n_lanes > 1) {  // several chunks in flight: leave CTA slots for the next chunk's kernels (see RenderDiffuseWave)
-            const int per_sm = env_int("VT_WAVE_CTAS_PER_SM", 6);
+            const int per_sm = env_int(rays_on_device ? "VT_GROUP_DEV_CTAS_PER_SM" : "VT_WAVE_CTAS_PER_SM", 6);
             if (per_sm > 0) cfg.grid = std::min(D.cfg.grid, D.sm_count * per_sm);
         }
         const uint64_t chunk_records = (uint64_t)std::max(1, env_int("VT_WAVE_TILE", 1 << 19));
-        const uint64_t chunk_tiles_max = rays_on_device ? lt : std::max<uint64_t>(1, chunk_records / g.tile);
-        uint64_t chunk_tiles = rays_on_device ? lt : std::max<uint64_t>(1, std::min(chunk_tiles_max, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)(chunk_records / 8))) / g.tile));
+        const uint64_t dev_chunks = (uint64_t)std::max(n_lanes, env_int("VT_GROUP_DEV_CHUNKS", n_lanes));
+        const uint64_t chunk_tiles_max = rays_on_device ? std::max<uint64_t>(1, (lt_sched + dev_chunks - 1) / dev_chunks) : std::max<uint64_t>(1, chunk_records / g.tile);
+        uint64_t chunk_tiles = rays_on_device ? chunk_tiles_max
+                                              : std::max<uint64_t>(1, std::min(chunk_tiles_max, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)(chunk_records / 8))) / g.tile));
         if (!rays_on_device) {
-            D.wave_rays.ensure(L);
+            D.wave_rays.ensure(std::max<uint64_t>(1, L));
             if (!D.copy_stream) VT_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
         }
         size_t n_uploads = 0;
         int li = 0, chunks_since_fence = 0;
         bool used[8] = {};
-        for (uint64_t j0 = 0, j1 = 0; j0 < lt; j0 = j1, li = (li + 1) % n_lanes, chunk_tiles = std::min(chunk_tiles_max, chunk_tiles * 2)) {
-            j1 = std::min(lt, j0 + chunk_tiles);
-            if (lt - j1 < chunk_tiles / 2) j1 = lt;  // no small tail chunk
-            const uint64_t cb = j0 * g.tile, mpix = g.local_records(j1) - cb;
+        for (uint64_t s0 = 0, s1 = 0; s0 < lt_sched; s0 = s1, li = (li + 1) % n_lanes, chunk_tiles = std::min(chunk_tiles_max, chunk_tiles * 2)) {
+            s1 = std::min(lt_sched, s0 + chunk_tiles);
+            if (lt_sched - s1 < chunk_tiles / 2) s1 = lt_sched;  // no small tail chunk
+            const uint64_t j0 = std::min(s0, lt), j1 = std::min(s1, lt);  // this rank's part of the chunk (may be empty at the end)
             DeviceScene::WaveLane &l = D.lanes[li];
-            cudaStream_t st = rays_on_device ? caller_stream : l.stream;
+            cudaStream_t st = on_caller ? caller_stream : l.stream;
             used[li] = true;
+            if (j1 <= j0) {
+                if (after_chunk) after_chunk(s0, s1, st);
+                continue;
+            }
+            const uint64_t cb = j0 * g.tile, mpix = g.local_records(j1) - cb;
             l.hits.ensure(mpix);
             l.attrs.ensure(mpix);
             l.brays.ensure(mpix * spp);
@@ -508,12 +529,14 @@ public:
             VT_CUDA(vt_launch_accumulate_sky(D.view, l.attrs.p, l.bhits.p, mpix, spp, weight, d_fb, st));
             A.mLaunches += 5;
             if (fb_host) copy_tiles(g, j0, j1, 3 * sizeof(float), m.fb_local.p, fb_host, true, cudaMemcpyDeviceToHost, st);
+            if (after_chunk) after_chunk(s0, s1, st);
         }
-        if (!rays_on_device) {  // the member's collective stream continues after every lane
+        if (!on_caller) {  // the stream that carries the gather (the member's own, or the caller's) continues after every lane
+            cudaStream_t after = rays_on_device ? caller_stream : m.stream;
             for (int i = 0; i < n_lanes; i++)
                 if (used[i]) {
                     VT_CUDA(cudaEventRecord(m.lane_done[i], D.lanes[i].stream));
-                    VT_CUDA(cudaStreamWaitEvent(m.stream, m.lane_done[i], 0));
+                    VT_CUDA(cudaStreamWaitEvent(after, m.lane_done[i], 0));
                 }
         }
     }
@@ -559,6 +582,50 @@ public:
         if (root && !fb) throw std::runtime_error("vt_group_render_diffuse_wave: rank 0 needs the framebuffer");
         VT_CUDA(cudaSetDevice(m.device));
         cudaStream_t st = dev_ptrs ? stream : m.stream;
+        const bool pipelined = !dev_ptrs && mWorld > 1 && env_int("VT_GROUP_PIPELINE", 1) != 0;
+        if (pipelined) {
+            // host pointers, several ranks: every finished chunk is shipped at once — rank r sends its tiles of the chunk, rank 0
+            // receives them into its staging area and downloads them — while the lanes go on tracing the next chunk, so only the last
+            // chunk's gather + download is exposed instead of the whole frame's (rank 0 lands 12 bytes per pixel through ONE PCIe link)
+            NcclApi &nccl = NcclApi::get();
+            const ShardGeom sched = g0.of(0);
+            std::vector<uint64_t> stage_off(mWorld, 0);
+            if (root) {
+                uint64_t total = 0;
+                for (uint32_t r = 1; r < mWorld; r++) stage_off[r] = total, total += g0.of(r).local_records();
+                m.fb_stage.ensure(std::max<uint64_t>(1, total * 3));
+            }
+            int ev = 0;
+            auto ship = [&](uint64_t s0, uint64_t s1, cudaStream_t lane) {
+                cudaEvent_t done = m.lane_done[ev++ % 8];
+                VT_CUDA(cudaEventRecord(done, lane));
+                VT_CUDA(cudaStreamWaitEvent(m.stream, done, 0));
+                VT_NCCL(nccl.GroupStart());
+                if (root) {
+                    for (uint32_t r = 1; r < mWorld; r++) {
+                        const ShardGeom gr = g0.of(r);
+                        const uint64_t a = std::min(s0, gr.local_tiles()), b = std::min(s1, gr.local_tiles());
+                        if (b > a)
+                            VT_NCCL(nccl.Recv(m.fb_stage.p + (stage_off[r] + a * gr.tile) * 3, (gr.local_records(b) - a * gr.tile) * 3, ncclFloat32, (int)r, m.comm, m.stream));
+                    }
+                } else {
+                    const uint64_t a = std::min(s0, g.local_tiles()), b = std::min(s1, g.local_tiles());
+                    if (b > a) VT_NCCL(nccl.Send(m.fb_local.p + a * g.tile * 3, (g.local_records(b) - a * g.tile) * 3, ncclFloat32, 0, m.comm, m.stream));
+                }
+                VT_NCCL(nccl.GroupEnd());
+                mLaunches++;
+                if (root)
+                    for (uint32_t r = 1; r < mWorld; r++) {
+                        const ShardGeom gr = g0.of(r);
+                        const uint64_t a = std::min(s0, gr.local_tiles()), b = std::min(s1, gr.local_tiles());
+                        copy_tiles(gr, a, b, 3 * sizeof(float), m.fb_stage.p + stage_off[r] * 3, fb, true, cudaMemcpyDeviceToHost, m.stream);
+                    }
+            };
+            member_render(m, g, rays, false, spp, seed, weight, fb, live_out != nullptr, st, &sched, ship);
+            member_finish(m, live_out != nullptr, st);
+            if (live_out) *live_out = m.live;
+            return;
+        }
         // own shard; with host pointers the shard image also goes straight to this process's host frame while later chunks still run
         member_render(m, g, rays, dev_ptrs, spp, seed, weight, (!dev_ptrs && fb) ? fb : nullptr, live_out != nullptr, st);
         if (mWorld > 1) {

@@ -66,6 +66,19 @@ struct QuadBvh {
     uint32_t max_stack = 0;  // worst-case number of pending references
 };
 bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string &err);
+// Which binary nodes become the children of each WIDE node when the binary tree is collapsed to `width` children per node
+// (vt_bvh_collapse.cpp): the SAH-optimal choice by dynamic programming over the subtree costs, after Ylitie, Karras, Laine,
+// "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs" (HPG 2017), section 3.1 — cost(n, i) = cheapest way to
+// present subtree n as at most i roots — instead of greedily adopting the children of the largest child, which leaves wide
+// nodes partly empty near the leaves (measured at 320 k triangles: 2.98 -> 3.46 of 4 quad slots used, 20 % fewer quads).  VT_COLLAPSE=greedy selects the old rule.
+struct CollapsePlan {
+    int width = 0;
+    std::vector<uint8_t> split;  // [node * width + i]: how many of i + 1 roots go to the left child (0: use one root fewer)
+    bool greedy = false;
+    // children of the wide node that replaces binary inner node `ni` -> kids[0 .. return value)
+    int children(const HostBvh &bvh, uint32_t ni, uint32_t *kids) const;
+};
+bool plan_collapse(const HostBvh &bvh, int width, CollapsePlan &plan, std::string &err);
 // 64-byte pairs in depth-first order -> 32-byte conservative compact pairs (vt_device.h: VtCPair)
 bool compact_pairs(const std::vector<VtPair> &pairs, std::vector<VtCPair> &out, std::string &err);
 
@@ -177,13 +190,22 @@ public:
     // One shadow ray per non-sky hit: origin = CalcRayOrigin(pos, geometric normal), toward a directional or point light.
     void ShadowRays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out_rays,
                     uint64_t *live_out, uint32_t flags, void *stream);
+    // Batched SampleBSDF, diffuse lobe only (source/libraries/BSDF.cpp:770-825): spp samples per non-sky hit from the TraceResult
+    // records and the rays that produced them; out_rays[i*spp+s] + samples[i*spp+s].  Host or device pointers as per flags; the
+    // queue arguments (device pointers only, all or none) list the spawned slots as the queued generators do.
+    void SampleBsdfRays(const vt_ray *rays, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays,
+                        vt_bsdf_sample *samples, uint64_t *live_out, uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits,
+                        uint32_t flags, void *stream);
     // Ray-queue variants (DEVICE pointers only, enqueued on `stream`): the generator also lists the slots it filled —
     // queue[0, *queue_count), *queue_count zeroed here — and writes the miss record of every masked slot into
     // miss_hits; TraverseQueued then traces the listed slots only.  spp == 0 selects the shadow-ray generator.
+    // in_queue / in_count (both or neither): wave compaction — only the parents the previous wave's queue lists are visited.
     void BounceRaysQueued(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out_rays, uint32_t *queue,
-                          uint64_t *queue_count, vt_hit *miss_hits, void *stream);
+                          uint64_t *queue_count, vt_hit *miss_hits, void *stream, const uint32_t *in_queue = nullptr,
+                          const uint64_t *in_count = nullptr);
     void ShadowRaysQueued(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out_rays,
-                          uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream);
+                          uint32_t *queue, uint64_t *queue_count, vt_hit *miss_hits, void *stream, const uint32_t *in_queue = nullptr,
+                          const uint64_t *in_count = nullptr);
     void TraverseQueued(const vt_ray *rays, const uint32_t *queue, const uint64_t *queue_count, uint64_t capacity, vt_hit *hits,
                         vt_attr *attrs, uint32_t flags, void *stream);
     // "primary + diffuse" wave in one call: traverse the primary rays, build their TraceResults, spawn
@@ -191,6 +213,11 @@ public:
     // on several streams so the PCIe copies overlap the kernels.
     void TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, vt_hit *hits, vt_attr *attrs,
                           vt_ray *bounce_rays, vt_hit *bounce_hits, uint64_t *live_out, uint32_t flags, void *stream);
+
+    // Path waves with compaction (BASELINE config 5): per primary ray a path of up to `bounces` diffuse bounces, a shadow ray toward
+    // the sun at every vertex; after the primary wave every kernel visits only the paths that are still alive.  DEVICE pointers.
+    void TracePaths(const vt_ray *rays, uint64_t n, uint32_t bounces, const float sun_dir[3], const float sun_rgb[3], uint64_t seed,
+                    float weight, float *fb, uint64_t *ray_counts, bool compact, void *stream);
 
     // The same wave with the framebuffer as its only result: HOST rays in, HOST RGBFFF image out
     // (fb[i] = weight * albedo_i * escaped fraction of pixel i's bounce rays), tiled over streams like TraceDiffuseWave.

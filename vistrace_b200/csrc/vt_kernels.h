@@ -20,6 +20,9 @@
 struct VtLaunchConfig {
     int persistent = 1;         // 1: machine-sized grid pulling rays from a counter; 0: one ray per thread
     int grid = 0;               // CTAs for the persistent launch (SMs x resident CTAs)
+    int sm_count = 0;           // SMs of the device (lower bound of a shrunk grid)
+    int min_rays_per_lane = 0;  // > 0: shrink the persistent grid of a SMALL launch so that every lane gets about this many rays
+                                // (fewer resident warps = shorter rounds = a shorter tail of the slowest rays); 0 = always the full grid
     int refill_threshold = 24;  // refill a warp when <= this many of its lanes still own a ray
     int tri_threshold = 10;     // run a triangle round when >= this many lanes have a candidate queued (6 / 8 / 10: 3.39 / 3.47 / 3.51 Grays/s)
 };
@@ -35,8 +38,10 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
 cudaError_t vt_traverse_occupancy(int *blocks_per_sm, size_t smem_bytes, int layout);
 
 // K2 — eager TraceResult for n (ray, hit) records; cones = n x {coneWidth, coneAngle} or nullptr.
+// Queue (both or neither): only the slots queue[0, min(n, *queue_count)) get a record — wave compaction for multi-bounce paths.
 cudaError_t vt_launch_trace_result(const VtSceneView &S, const vt_ray *rays, const vt_hit *hits, const float *cones,
-                                   vt_attr *attrs, uint64_t n, cudaStream_t stream);
+                                   vt_attr *attrs, uint64_t n, cudaStream_t stream, const uint32_t *queue = nullptr,
+                                   const unsigned long long *queue_count = nullptr);
 
 // K3 — secondary-ray generation: spp cosine-weighted bounce rays per (non-sky) hit into slot i*spp+s,
 // masked slots (tmax < 0) elsewhere; *live += spawned rays.  And a pinhole primary-ray generator.
@@ -55,15 +60,28 @@ struct VtSlotMap {
 };
 cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, uint64_t slot_offset,
                                   vt_ray *out, unsigned long long *live, cudaStream_t stream, uint32_t *queue = nullptr,
-                                  unsigned long long *queue_count = nullptr, vt_hit *miss_hits = nullptr, const VtSlotMap *map = nullptr);
+                                  unsigned long long *queue_count = nullptr, vt_hit *miss_hits = nullptr, const VtSlotMap *map = nullptr,
+                                  const uint32_t *in_queue = nullptr, const unsigned long long *in_count = nullptr);
+// in_queue / in_count (generators, both or neither): wave compaction — the generator visits only the parents the PREVIOUS wave's
+// queue lists (attrs[in_queue[k]], k < min(n, *in_count)) instead of all n slots; slots it does not visit are not written at all
+// (no masked ray, no miss record), so everything downstream must go through the out queue.
 cudaError_t vt_launch_shadow_rays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out,
                                   unsigned long long *live, cudaStream_t stream, uint32_t *queue = nullptr,
-                                  unsigned long long *queue_count = nullptr, vt_hit *miss_hits = nullptr);
+                                  unsigned long long *queue_count = nullptr, vt_hit *miss_hits = nullptr,
+                                  const uint32_t *in_queue = nullptr, const unsigned long long *in_count = nullptr);
+// K3c — batched SampleBSDF, diffuse lobe (source/libraries/BSDF.cpp:770-825): spp samples per non-sky hit; out rays + BSDFSample records.
+cudaError_t vt_launch_bsdf_diffuse_rays(const vt_ray *rays, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out,
+                                        vt_bsdf_sample *samples, unsigned long long *live, cudaStream_t stream, uint32_t *queue = nullptr,
+                                        unsigned long long *queue_count = nullptr, vt_hit *miss_hits = nullptr);
 cudaError_t vt_launch_pinhole_rays(const float *cam12, uint32_t width, uint32_t height, vt_ray *out, cudaStream_t stream);
 
 // K4 — fb[i] += weight * albedo_i * (escaped bounce rays of pixel i) / spp, RGBFFF framebuffer.
 cudaError_t vt_launch_accumulate_sky(const VtSceneView &S, const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n,
                                      uint32_t spp, float weight, float *fb, cudaStream_t stream);
+
+// Path shading between the waves of vt_accel_trace_paths: one thread per live vertex (queue-listed slots, or all n when queue is null).
+cudaError_t vt_launch_path_shade(const vt_attr *attrs, const vt_hit *shadow_hits, const uint32_t *queue, const unsigned long long *queue_count,
+                                 uint64_t n, bool first_wave, float weight, const float sun_rgb[3], float *throughput, float *fb, cudaStream_t stream);
 
 // K5 — device-side refit of the resident quad hierarchy (vt_refit.cu).  prepare: once per resident hierarchy
 // (parent / inner-child count per quad, original triangle -> leaf slot).  refit_tris: Triangle constructor over the

@@ -158,3 +158,20 @@ VT_DEV Px tex_sample(const VtDevTexture &t, const uint8_t *texels, float u, floa
     return Px{low.r * fract + high.r * fractInv, low.g * fract + high.g * fractInv, low.b * fract + high.b * fractInv,
               low.a * fract + high.a * fractInv};
 }
+
+// Counter-based random numbers of the ray generators: a hash of (slot, dimension, seed) — the reference's Sampler is a sequential
+// mt19937 (source/objects/Sampler.cpp:5-20) and cannot be evaluated in parallel.  Host + device, so that a caller (and the parity
+// tests) can reproduce the numbers a kernel drew: vt_sample_uniform01 in the C ABI.
+__host__ __device__ __forceinline__ uint32_t vt_mix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x7feb352du;
+    h ^= h >> 15;
+    h *= 0x846ca68bu;
+    h ^= h >> 16;
+    return h;
+}
+__host__ __device__ __forceinline__ float vt_uniform01(unsigned long long slot, uint32_t dim, unsigned long long seed) {
+    uint32_t h = vt_mix32((uint32_t)slot ^ vt_mix32((uint32_t)(slot >> 32) + 0x9e3779b9u * (dim + 1u)));
+    h = vt_mix32(h ^ (uint32_t)seed ^ vt_mix32((uint32_t)(seed >> 32) + dim));
+    return (float)(h >> 8) * (1.0f / 16777216.0f);
+}

@@ -26,19 +26,7 @@
 
 namespace {
 
-VT_DEV uint32_t mix32(uint32_t h) {
-    h ^= h >> 16;
-    h *= 0x7feb352du;
-    h ^= h >> 15;
-    h *= 0x846ca68bu;
-    h ^= h >> 16;
-    return h;
-}
-VT_DEV float uniform01(unsigned long long slot, uint32_t dim, unsigned long long seed) {
-    uint32_t h = mix32((uint32_t)slot ^ mix32((uint32_t)(slot >> 32) + 0x9e3779b9u * (dim + 1u)));
-    h = mix32(h ^ (uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + dim));
-    return (float)(h >> 8) * (1.0f / 16777216.0f);
-}
+VT_DEV float uniform01(unsigned long long slot, uint32_t dim, unsigned long long seed) { return vt_uniform01(slot, dim, seed); }
 
 // vistrace.CalcRayOrigin — source/VisTrace.cpp:1495-1517, one component
 VT_DEV float ray_origin_1(float pos, float nrm) {
@@ -81,11 +69,17 @@ __global__ void __launch_bounds__(256)
 k_bounce_rays(const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t spp, unsigned long long seed,
               unsigned long long slot_offset, vt_ray *__restrict__ out, unsigned long long *__restrict__ live,
               uint32_t *__restrict__ queue, unsigned long long *__restrict__ queue_count, vt_hit *__restrict__ miss_hits,
-              const VtSlotMap map) {
-    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long total = n * spp;
+              const VtSlotMap map, const uint32_t *__restrict__ in_queue, const unsigned long long *__restrict__ in_count) {
+    unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long total = n * spp;
+    if (in_queue) {  // wave compaction: thread j handles sample j % spp of parent in_queue[j / spp]; whole blocks past the end leave at once
+        total = min(n, *in_count) * spp;
+        if ((unsigned long long)blockIdx.x * blockDim.x >= total) return;
+        if (j < total) j = (unsigned long long)__ldg(in_queue + j / spp) * spp + j % spp;
+        else j = ~0ull;
+    }
     bool spawned = false;
-    if (j < total) {
+    if (j < (in_queue ? ~0ull : total)) {
         const unsigned long long i = j / spp;
         // counter of the random-number hash: slot of the GLOBAL pixel (VtSlotMap, vt_kernels.h); identity map: slot_offset + j
         unsigned long long ctr = slot_offset + j;
@@ -119,6 +113,89 @@ k_bounce_rays(const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t 
         o[0] = ro;
         o[1] = rd;
     }
+    if (live || queue) publish_slot(in_queue ? (j != ~0ull) : (j < total), spawned, j, live, queue, queue_count, miss_hits);
+}
+
+// Batched SampleBSDF restricted to the diffuse lobe (source/libraries/BSDF.cpp:770-825 with activeLobes = LobeType::DiffuseReflection):
+// what a GLua path tracer calls per hit between two accel:Traverse calls.  Per (hit i, sample s):
+//   BSDFMaterial::PrepShadingData(albedo, metalness, roughness)                 BSDF.cpp:11-21  (dielectricInput = 1)
+//   CalculateLobePDFs -> pDiffuse = (1 - metallic), normalised                  :23-56
+//   lobeSelect = rnd(dim 0); entering = dot(wo, N) >= 0; incident = to_local    :780-783  (anisotropicRotation = 0: rotate() is the identity)
+//   SampleDiffuse: hemisphere_cos(rnd(dim 1), rnd(dim 2)), Disney-diffuse weight :252-278, :69-77
+//   weight *= (1 - metallic) / pDiffuse, pdf *= pDiffuse, scattered = from_local :788-790, :824
+// wo = -normalize(ray direction), the incident direction TraceResult keeps (AccelStruct.cpp:826, TraceResult.cpp:56).  The spawned
+// ray starts at CalcRayOrigin(pos, geometric normal on the side the scattered direction leaves through).  Slots that spawn
+// nothing (miss, sky, lobeSelect >= pDiffuse — a fully metallic hit — or a non-finite direction) are masked; their sample record
+// is what SampleBSDF leaves in BSDFSample then: zero vector, weight 0, pdf 0, lobe None.
+__global__ void __launch_bounds__(256)
+k_bsdf_diffuse_rays(const vt_ray *__restrict__ rays, const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t spp,
+                    unsigned long long seed, vt_ray *__restrict__ out, vt_bsdf_sample *__restrict__ samples,
+                    unsigned long long *__restrict__ live, uint32_t *__restrict__ queue, unsigned long long *__restrict__ queue_count,
+                    vt_hit *__restrict__ miss_hits) {
+    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long total = n * spp;
+    bool spawned = false;
+    if (j < total) {
+        const unsigned long long i = j / spp;
+        const float4 *a = reinterpret_cast<const float4 *>(attrs + i);
+        const float4 q7 = __ldg(a + 7);  // tex_uv, flags, prim
+        const uint32_t flags = __float_as_uint(q7.z), prim = __float_as_uint(q7.w);
+        float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 0.f, -1.f);  // masked slot
+        V3 world = mk3(0.f, 0.f, 0.f), weight = mk3(0.f, 0.f, 0.f);
+        float pdf = 0.f;
+        uint32_t lobe = VT_LOBE_NONE;
+        if (prim != VT_MISS && !(flags & VT_ATTR_HIT_SKY)) {
+            const float4 q0 = __ldg(a), q1 = __ldg(a + 1), q2 = __ldg(a + 2), q3 = __ldg(a + 3), q4 = __ldg(a + 4), q5 = __ldg(a + 5);
+            const float4 rdir = __ldg(reinterpret_cast<const float4 *>(rays + i) + 1);
+            const V3 wo = neg(glm_normalize(mk3(rdir.x, rdir.y, rdir.z)));
+            const V3 pos = mk3(q0.x, q0.y, q0.z), N = mk3(q1.x, q1.y, q1.z), T = mk3(q2.x, q2.y, q2.z), B = mk3(q3.x, q3.y, q3.z);
+            const V3 gN = mk3(q4.x, q4.y, q4.z);
+            const float metallic = glm_clamp(q2.w, 0.f, 1.f), linearRoughness = glm_clamp(q3.w, 0.f, 1.f);
+            const V3 dielectric = mk3(glm_clamp(1.f * q5.x, 0.f, 1.f), glm_clamp(1.f * q5.y, 0.f, 1.f), glm_clamp(1.f * q5.z, 0.f, 1.f));
+            float pDiffuse = (1.f - metallic) * (1.f - 0.f);
+            float normFactor = pDiffuse + 0.f + 0.f + 0.f;
+            if (normFactor > 0.f) {
+                normFactor = 1.f / normFactor;
+                pDiffuse *= normFactor;
+            }
+            const float lobeSelect = uniform01(j, 0, seed);
+            const bool entering = glm_dot(wo, N) >= 0.f;
+            const V3 Ns = entering ? N : neg(N);
+            const V3 incident = mk3(glm_dot(wo, T), glm_dot(wo, B), glm_dot(wo, Ns));
+            V3 scattered = mk3(0.f, 0.f, 0.f);
+            if (lobeSelect < pDiffuse) {
+                lobe = VT_LOBE_DIFFUSE_REFLECTION;
+                const float pi = 3.14159265358979323846264338327950288f;
+                const float r1 = uniform01(j, 1, seed);
+                const float z = sqrtf(r1), sinTheta = sqrtf(1.f - r1), phi = 2.f * pi * uniform01(j, 2, seed);
+                scattered = mk3(sinTheta * cosf(phi), sinTheta * sinf(phi), z);
+                pdf = (scattered.z > 0.f) ? (scattered.z / pi) : 0.f;
+                const V3 halfway = glm_normalize(incident + scattered);
+                const float iDotN = incident.z, sDotH = glm_dot(scattered, halfway), sDotN = scattered.z;
+                const float energyBias = glm_lerp(0.f, 0.5f, linearRoughness);
+                const float energyFactor = glm_lerp(1.f, 1.f / 1.51f, linearRoughness);
+                const float fd90 = energyBias + 2.f * sDotH * sDotH * linearRoughness;
+                const float lightScatter = 1.f + (fd90 - 1.f) * powf(1.f - sDotN, 5.f);  // schlick_dielectric(1, cos, f90), BSDF.cpp:157-160
+                const float viewScatter = 1.f + (fd90 - 1.f) * powf(1.f - iDotN, 5.f);
+                weight = dielectric * lightScatter * viewScatter * energyFactor;
+                weight = weight * ((1.f - metallic) * (1.f - 0.f) / pDiffuse);
+                pdf *= pDiffuse;
+            }
+            world = T * scattered.x + B * scattered.y + Ns * scattered.z;
+            if (lobe != VT_LOBE_NONE && isfinite(world.x) && isfinite(world.y) && isfinite(world.z) && (world.x != 0.f || world.y != 0.f || world.z != 0.f)) {
+                const float side = glm_dot(world, gN) >= 0.f ? 1.f : -1.f;
+                ro = make_float4(ray_origin_1(pos.x, gN.x * side), ray_origin_1(pos.y, gN.y * side), ray_origin_1(pos.z, gN.z * side), 0.f);
+                rd = make_float4(world.x, world.y, world.z, FLT_MAX);
+                spawned = true;
+            }
+        }
+        float4 *o = reinterpret_cast<float4 *>(out + j);
+        o[0] = ro;
+        o[1] = rd;
+        float4 *sm = reinterpret_cast<float4 *>(samples + j);
+        sm[0] = make_float4(world.x, world.y, world.z, pdf);
+        sm[1] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(lobe));
+    }
     if (live || queue) publish_slot(j < total, spawned, j, live, queue, queue_count, miss_hits);
 }
 
@@ -128,10 +205,16 @@ k_bounce_rays(const vt_attr *__restrict__ attrs, unsigned long long n, uint32_t 
 __global__ void __launch_bounds__(256)
 k_shadow_rays(const vt_attr *__restrict__ attrs, unsigned long long n, float lx, float ly, float lz, int point_light, float tmax,
               vt_ray *__restrict__ out, unsigned long long *__restrict__ live, uint32_t *__restrict__ queue,
-              unsigned long long *__restrict__ queue_count, vt_hit *__restrict__ miss_hits) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+              unsigned long long *__restrict__ queue_count, vt_hit *__restrict__ miss_hits, const uint32_t *__restrict__ in_queue,
+              const unsigned long long *__restrict__ in_count) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (in_queue) {  // wave compaction: only the parents the previous wave's queue lists
+        const unsigned long long total = min(n, *in_count);
+        if ((unsigned long long)blockIdx.x * blockDim.x >= total) return;
+        i = i < total ? (unsigned long long)__ldg(in_queue + i) : ~0ull;
+    }
     bool spawned = false;
-    if (i < n) {
+    if (i < (in_queue ? ~0ull : n)) {
         const float4 *a = reinterpret_cast<const float4 *>(attrs + i);
         const float4 q7 = __ldg(a + 7);
         const uint32_t flags = __float_as_uint(q7.z), prim = __float_as_uint(q7.w);
@@ -149,7 +232,7 @@ k_shadow_rays(const vt_attr *__restrict__ attrs, unsigned long long n, float lx,
         o4[0] = ro;
         o4[1] = rd;
     }
-    if (live || queue) publish_slot(i < n, spawned, i, live, queue, queue_count, miss_hits);
+    if (live || queue) publish_slot(in_queue ? (i != ~0ull) : (i < n), spawned, i, live, queue, queue_count, miss_hits);
 }
 
 // Pinhole primary rays, pixel-centre sampling, row-major (index = width * j + i) — the loop of
@@ -210,7 +293,54 @@ k_accumulate_sky(const VtSceneView S, const vt_attr *__restrict__ attrs, const v
     fb[3 * i + 2] += weight * b;
 }
 
+// Path shading between two waves of vt_accel_trace_paths (harness-level, like K4: it exists so that a multi-bounce workload has
+// an image to deliver; not part of accel:Traverse).  One thread per LIVE path vertex of the wave — the slots the wave's queue
+// lists, or all n slots of the primary wave (queue == nullptr).  Slot = pixel, so no two threads touch the same pixel:
+//   sky hit (TraceResult::hitSky, source/objects/TraceResult.cpp:83):  fb += weight * throughput * albedo, the path ends;
+//   surface hit:  throughput *= albedo;  if the vertex's shadow ray reached the sun (any-hit miss)  fb += weight * throughput * sun.
+__global__ void __launch_bounds__(256)
+k_path_shade(const vt_attr *__restrict__ attrs, const vt_hit *__restrict__ shadow_hits, const uint32_t *__restrict__ queue,
+             const unsigned long long *__restrict__ queue_count, unsigned long long n, int first_wave, float weight, float sun_r,
+             float sun_g, float sun_b, float *__restrict__ throughput, float *__restrict__ fb) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (queue) {
+        if (i >= min(n, *queue_count)) return;
+        i = __ldg(queue + i);
+    } else if (i >= n) {
+        return;
+    }
+    const float4 *a = reinterpret_cast<const float4 *>(attrs + i);
+    const float4 q7 = __ldg(a + 7);
+    const uint32_t flags = __float_as_uint(q7.z), prim = __float_as_uint(q7.w);
+    if (prim == VT_MISS) return;
+    const float4 q5 = __ldg(a + 5);  // albedo, ent_id
+    float tr = 1.f, tg = 1.f, tb = 1.f;
+    if (!first_wave) tr = throughput[3 * i], tg = throughput[3 * i + 1], tb = throughput[3 * i + 2];
+    tr *= q5.x, tg *= q5.y, tb *= q5.z;
+    float r = 0.f, g = 0.f, b = 0.f;
+    if (flags & VT_ATTR_HIT_SKY) {
+        r = tr, g = tg, b = tb;
+    } else {
+        throughput[3 * i] = tr, throughput[3 * i + 1] = tg, throughput[3 * i + 2] = tb;
+        const uint32_t occluder = __float_as_uint(__ldg(reinterpret_cast<const float4 *>(shadow_hits) + i).w);
+        if (occluder == VT_MISS) r = tr * sun_r, g = tg * sun_g, b = tb * sun_b;
+    }
+    fb[3 * i] += weight * r;
+    fb[3 * i + 1] += weight * g;
+    fb[3 * i + 2] += weight * b;
+}
+
 }  // namespace
+
+cudaError_t vt_launch_path_shade(const vt_attr *attrs, const vt_hit *shadow_hits, const uint32_t *queue, const unsigned long long *queue_count,
+                                 uint64_t n, bool first_wave, float weight, const float sun_rgb[3], float *throughput, float *fb, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    if ((queue == nullptr) != (queue_count == nullptr)) return cudaErrorInvalidValue;
+    const unsigned block = 256;
+    k_path_shade<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(attrs, shadow_hits, queue, queue_count, n, first_wave ? 1 : 0, weight,
+                                                                           sun_rgb[0], sun_rgb[1], sun_rgb[2], throughput, fb);
+    return cudaGetLastError();
+}
 
 cudaError_t vt_launch_accumulate_sky(const VtSceneView &S, const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n,
                                      uint32_t spp, float weight, float *fb, cudaStream_t stream) {
@@ -222,24 +352,39 @@ cudaError_t vt_launch_accumulate_sky(const VtSceneView &S, const vt_attr *attrs,
 
 cudaError_t vt_launch_bounce_rays(const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, uint64_t slot_offset,
                                   vt_ray *out, unsigned long long *live, cudaStream_t stream, uint32_t *queue,
-                                  unsigned long long *queue_count, vt_hit *miss_hits, const VtSlotMap *map) {
+                                  unsigned long long *queue_count, vt_hit *miss_hits, const VtSlotMap *map, const uint32_t *in_queue,
+                                  const unsigned long long *in_count) {
+    const unsigned long long total = (unsigned long long)n * spp;
+    if (total == 0) return cudaSuccess;
+    if (queue && (!queue_count || !miss_hits || total > 0xFFFFFFFFull)) return cudaErrorInvalidValue;
+    if ((in_queue == nullptr) != (in_count == nullptr) || (in_queue && !queue)) return cudaErrorInvalidValue;
+    const unsigned block = 256;
+    k_bounce_rays<<<(unsigned)((total + block - 1) / block), block, 0, stream>>>(attrs, n, spp, seed, slot_offset, out, live, queue,
+                                                                                queue_count, miss_hits, map ? *map : VtSlotMap(), in_queue, in_count);
+    return cudaGetLastError();
+}
+
+cudaError_t vt_launch_bsdf_diffuse_rays(const vt_ray *rays, const vt_attr *attrs, uint64_t n, uint32_t spp, uint64_t seed, vt_ray *out,
+                                        vt_bsdf_sample *samples, unsigned long long *live, cudaStream_t stream, uint32_t *queue,
+                                        unsigned long long *queue_count, vt_hit *miss_hits) {
     const unsigned long long total = (unsigned long long)n * spp;
     if (total == 0) return cudaSuccess;
     if (queue && (!queue_count || !miss_hits || total > 0xFFFFFFFFull)) return cudaErrorInvalidValue;
     const unsigned block = 256;
-    k_bounce_rays<<<(unsigned)((total + block - 1) / block), block, 0, stream>>>(attrs, n, spp, seed, slot_offset, out, live, queue,
-                                                                                queue_count, miss_hits, map ? *map : VtSlotMap());
+    k_bsdf_diffuse_rays<<<(unsigned)((total + block - 1) / block), block, 0, stream>>>(rays, attrs, n, spp, seed, out, samples, live, queue,
+                                                                                      queue_count, miss_hits);
     return cudaGetLastError();
 }
 
 cudaError_t vt_launch_shadow_rays(const vt_attr *attrs, uint64_t n, const float light[3], bool point_light, float tmax, vt_ray *out,
                                   unsigned long long *live, cudaStream_t stream, uint32_t *queue, unsigned long long *queue_count,
-                                  vt_hit *miss_hits) {
+                                  vt_hit *miss_hits, const uint32_t *in_queue, const unsigned long long *in_count) {
     if (n == 0) return cudaSuccess;
     if (queue && (!queue_count || !miss_hits || n > 0xFFFFFFFFull)) return cudaErrorInvalidValue;
+    if ((in_queue == nullptr) != (in_count == nullptr) || (in_queue && !queue)) return cudaErrorInvalidValue;
     const unsigned block = 256;
     k_shadow_rays<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(attrs, n, light[0], light[1], light[2], point_light ? 1 : 0,
-                                                                            tmax, out, live, queue, queue_count, miss_hits);
+                                                                            tmax, out, live, queue, queue_count, miss_hits, in_queue, in_count);
     return cudaGetLastError();
 }
 

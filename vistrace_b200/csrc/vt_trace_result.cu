@@ -85,9 +85,15 @@ VT_DEV void st4(float *dst, float a, float b, float c, float d) { *reinterpret_c
 #endif
 __global__ void __launch_bounds__(128, VT_K2_MIN_BLOCKS)
 k_trace_result(const VtSceneView S, const vt_ray *__restrict__ rays, const vt_hit *__restrict__ hits,
-               const float *__restrict__ cones, vt_attr *__restrict__ attrs, unsigned long long n) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+               const float *__restrict__ cones, vt_attr *__restrict__ attrs, unsigned long long n,
+               const uint32_t *__restrict__ queue, const unsigned long long *__restrict__ queue_count) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (queue) {  // wave compaction: only the slots a generator listed get a TraceResult; everything else stays untouched
+        if (i >= min(n, *queue_count)) return;
+        i = __ldg(queue + i);
+    } else if (i >= n) {
+        return;
+    }
     float *out = reinterpret_cast<float *>(attrs + i);
     const float4 h = __ldg(reinterpret_cast<const float4 *>(hits) + i);
     const uint32_t prim = __float_as_uint(h.w);
@@ -261,10 +267,11 @@ k_trace_result(const VtSceneView S, const vt_ray *__restrict__ rays, const vt_hi
 }  // namespace
 
 cudaError_t vt_launch_trace_result(const VtSceneView &S, const vt_ray *rays, const vt_hit *hits, const float *cones,
-                                   vt_attr *attrs, uint64_t n, cudaStream_t stream) {
+                                   vt_attr *attrs, uint64_t n, cudaStream_t stream, const uint32_t *queue, const unsigned long long *queue_count) {
     if (n == 0) return cudaSuccess;
+    if ((queue == nullptr) != (queue_count == nullptr)) return cudaErrorInvalidValue;
     const unsigned block = 128;
-    const unsigned long long grid = (n + block - 1) / block;
-    k_trace_result<<<(unsigned)grid, block, 0, stream>>>(S, rays, hits, cones, attrs, (unsigned long long)n);
+    const unsigned long long grid = (n + block - 1) / block;  // queued: blocks past *queue_count exit at once
+    k_trace_result<<<(unsigned)grid, block, 0, stream>>>(S, rays, hits, cones, attrs, (unsigned long long)n, queue, queue_count);
     return cudaGetLastError();
 }

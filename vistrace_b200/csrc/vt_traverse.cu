@@ -25,6 +25,8 @@
 #include "vt_kernels.h"
 #include "vt_math.cuh"
 #include <cuda_fp16.h>
+#include <algorithm>
+#include <cstdlib>
 
 // Build-time knobs of the ALU-pipe diet (A/B builds: make EXTRA=-DVT_...=0); see the notes at slab_quad.
 #ifndef VT_SCHED2
@@ -32,6 +34,16 @@
 #endif
 #ifndef VT_TRI_ADDR_WIDE
 #define VT_TRI_ADDR_WIDE 1
+#endif
+// Ray prefetch ring (quantised kernels): a warp pulls VT_RAY_BATCH rays from the global queue at once — ONE atomic, coalesced
+// 32-byte loads — derives safe_inverse / scaled origin for all of them with every lane busy, and parks the prepared ray states in
+// shared memory; a lane that finishes its ray later picks the next state up with four LDS.128, no atomic, no global latency and
+// no per-lane divisions.  That makes a refill cheap enough to run with only a few idle lanes (VT_REFILL 28 instead of 24), so node
+// rounds execute with fuller warps.  0 = the round-1 path (refill straight from global memory).
+// Measured (profiles/r2_k1_experiments.md): SLOWER than the round-1 refill at every threshold (3.33 vs 3.51 Grays/s on the bounce
+// wave; 64-entry rings 3.21) — the 9 KB of shared memory per CTA come out of the L1 that serves half of the node fetches.  Off.
+#ifndef VT_RAY_BATCH
+#define VT_RAY_BATCH 0
 #endif
 #ifndef VT_STACK_DIST
 #define VT_STACK_DIST 0  // measured: -7 % node visits / -22 % triangle tests on primary rays (+3 %), but -5.6 % on the bounce wave
@@ -637,12 +649,87 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
     const uint32_t magic = (QUAD && VT_DECODE_HALF) ? S.magic_h : S.magic;
     bool warp_wild = false;  // warp-uniform: some lane holds a ray the one-fma plane form is not proven for (slab_quad)
 
+#if VT_RAY_BATCH
+    // prepared ray states of this warp: {o.xyz, tmin} {d.xyz, tmax} {inv.xyz, flags} {so.xyz, -} + the slot each belongs to
+    __shared__ float4 s_state[VT_TRAVERSE_BLOCK / 32][VT_RAY_BATCH][4];
+    __shared__ unsigned long long s_slot[VT_TRAVERSE_BLOCK / 32][VT_RAY_BATCH];
+    const unsigned warp_in_cta = threadIdx.x >> 5;
+    int buf_pos = 0, buf_cnt = 0;  // warp-uniform: entries [buf_pos, buf_cnt) of the ring are still to be handed out
+#endif
+
     for (;;) {
         if (alive && cur == VT_REF_DONE) {
             write_hit(hits, ray_idx, r);
             alive = false;
         }
         const unsigned idle = __ballot_sync(0xffffffffu, !alive);
+#if VT_RAY_BATCH
+        if (idle == 0xffffffffu && exhausted && buf_pos == buf_cnt) break;
+        if (idle && !(exhausted && buf_pos == buf_cnt) && __popc(idle) >= 32 - refill_threshold) {
+            const int n_idle = __popc(idle);
+            if (buf_pos == buf_cnt && !exhausted) {
+                // ---- fill the ring: one atomic for the batch, coalesced loads, ray set-up with all lanes busy
+                unsigned long long base = 0;
+                if (persistent) {
+                    if (lane == 0) base = atomicAdd(&counters[0], (unsigned long long)VT_RAY_BATCH);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                } else {
+                    base = ((unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u));
+                    exhausted = true;
+                }
+                if (base + VT_RAY_BATCH >= n) exhausted = true;
+                bool fresh_wild = false;
+                for (unsigned e = lane; e < (unsigned)VT_RAY_BATCH; e += 32u) {
+                    const unsigned long long q = base + e;
+                    if (q < n) {
+                        const unsigned long long slot = queue ? (unsigned long long)__ldg(queue + q) : q;  // queued launch: the slot this entry names
+                        float4 ra, rb;
+                        ldg256_ray(rays + slot, ra, rb);
+                        const float ix = safe_inverse(rb.x), iy = safe_inverse(rb.y), iz = safe_inverse(rb.z);
+                        // argument rules of AccelStruct::Traverse (source/objects/AccelStruct.cpp:805-806) -> counted miss; tmax < 0: masked slot
+                        uint32_t flags = 0;
+                        if (!(ra.w >= 0.f) || !(rb.w > ra.w)) {
+                            flags = 1u;
+                            if (!(rb.w < 0.f)) n_invalid++;
+                        }
+                        fresh_wild |= VT_SLAB_TWO_FMA || !(fminf(fabsf(ix), fminf(fabsf(iy), fabsf(iz))) >= 0x1p-60f);
+                        s_state[warp_in_cta][e][0] = ra;
+                        s_state[warp_in_cta][e][1] = rb;
+                        s_state[warp_in_cta][e][2] = make_float4(ix, iy, iz, __uint_as_float(flags));
+                        s_state[warp_in_cta][e][3] = make_float4(-ra.x * ix, -ra.y * iy, -ra.z * iz, 0.f);
+                        s_slot[warp_in_cta][e] = slot;
+                    }
+                }
+                // sticky for this warp's share of the launch: such rays are pathological input, the flag only has to be right, not tight
+                if (__any_sync(0xffffffffu, fresh_wild)) warp_wild = true;
+                buf_pos = 0;
+                buf_cnt = base < n ? (int)min((unsigned long long)VT_RAY_BATCH, n - base) : 0;
+                __syncwarp();
+            }
+            const int avail = buf_cnt - buf_pos;
+            if (!alive) {
+                const int rank_in_idle = __popc(idle & lt_mask);
+                if (rank_in_idle < avail) {
+                    const int e = buf_pos + rank_in_idle;
+                    const float4 a = s_state[warp_in_cta][e][0], b = s_state[warp_in_cta][e][1], c = s_state[warp_in_cta][e][2], d = s_state[warp_in_cta][e][3];
+                    ray_idx = s_slot[warp_in_cta][e];
+                    r.o = mk3(a.x, a.y, a.z), r.tmin = a.w;
+                    r.d = mk3(b.x, b.y, b.z), r.tmax = b.w;
+                    r.inv = mk3(c.x, c.y, c.z), r.so = mk3(d.x, d.y, d.z);
+                    r.u = r.v = 0.f;
+                    r.prim = VT_MISS;
+                    alive = true;
+                    sp = stack;
+                    if (__float_as_uint(c.w)) cur = VT_REF_DONE;                                             // invalid or masked: a miss
+                    else if (S.root_leaf_count) cur = S.root_leaf_count << VT_REF_SHIFT;                     // the root is a leaf over tris[0, count)
+                    else cur = S.n_pairs ? 0u : VT_REF_DONE;                                                 // pair 0 / quad 0: the children of the root
+                }
+            }
+            buf_pos += min(n_idle, avail);
+            __syncwarp();  // every pick-up has read its entry before a later refill may overwrite the ring
+        }
+        const int keep = (exhausted && buf_pos == buf_cnt) ? 0 : refill_threshold;
+#else
         if (idle == 0xffffffffu && exhausted) break;
         if (idle && !exhausted && __popc(idle) >= 32 - refill_threshold) {
             const int n_idle = __popc(idle);
@@ -681,6 +768,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
             if (__any_sync(0xffffffffu, fresh_wild)) warp_wild = true;
         }
         const int keep = exhausted ? 0 : refill_threshold;
+#endif
 
         for (;;) {
 #if VT_SCHED2
@@ -783,10 +871,20 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
                                const uint32_t *queue, const unsigned long long *queue_count) {
     if (n == 0) return cudaSuccess;
     if ((queue == nullptr) != (queue_count == nullptr)) return cudaErrorInvalidValue;
-    const size_t smem = (S.cpairs || S.quads) ? 0 : (size_t)S.n_smem_pairs * sizeof(VtPair);
+    // VT_K1_DYN_SMEM (bytes, tuning only): unused dynamic shared memory for the quantised kernels — shrinks the L1 carve-out so the
+    // L1-capacity sensitivity of the kernel can be measured in isolation
+    const char *dyn_smem_env = std::getenv("VT_K1_DYN_SMEM");
+    const int dyn_smem_probe = (dyn_smem_env && *dyn_smem_env) ? std::atoi(dyn_smem_env) : 0;
+    const size_t smem = (S.cpairs || S.quads) ? (size_t)dyn_smem_probe : (size_t)S.n_smem_pairs * sizeof(VtPair);
     int grid;
     if (cfg.persistent) {
         grid = cfg.grid;
+        if (cfg.min_rays_per_lane > 0 && cfg.sm_count > 0) {
+            const uint64_t want = (n + (uint64_t)VT_TRAVERSE_BLOCK * cfg.min_rays_per_lane - 1) / ((uint64_t)VT_TRAVERSE_BLOCK * cfg.min_rays_per_lane);
+            // whole multiples of the SM count, at least one CTA per SM, never more than the resident maximum
+            const uint64_t per_sm = std::max<uint64_t>(1, (want + cfg.sm_count - 1) / cfg.sm_count);
+            grid = (int)std::min<uint64_t>((uint64_t)cfg.grid, per_sm * cfg.sm_count);
+        }
     } else {
         grid = (int)((n + VT_TRAVERSE_BLOCK - 1) / VT_TRAVERSE_BLOCK);
     }
