@@ -245,6 +245,16 @@ int vt_accel_refit(vt_accel *accel, const vt_scene *scene);
  * after the upload (a box left the float grid) the handle is invalid until vt_accel_refit / vt_accel_populate. */
 int vt_accel_refit_range(vt_accel *accel, const vt_tri_in *tris, uint64_t first, uint64_t count);
 
+/* Refit quality and the rebuild trigger.  A refit keeps the topology that was built for the ORIGINAL geometry; the further things
+ * move, the looser its boxes.  *area_ratio = (sum of the surface areas of all node boxes now) / (the same sum right after the
+ * build): the SAH's inner-node term, to which the expected number of node visits is proportional
+ * (libs/bvh/include/bvh/sah_based_algorithm.hpp:16-41); 1.0 until the first device-side refit.  vt_accel_set_refit_rebuild_ratio(r),
+ * r > 0 (or VT_REFIT_REBUILD_RATIO in the environment): vt_accel_refit rebuilds the hierarchy from scratch — what accel:Rebuild
+ * always does in the reference (source/VisTrace.cpp:798-818) — whenever the refitted tree exceeds r; *rebuilds counts those.
+ * vt_accel_refit_range cannot rebuild (it does not see the whole scene): the caller polls the ratio and calls vt_accel_populate. */
+int vt_accel_refit_quality(const vt_accel *accel, double *area_ratio, uint64_t *rebuilds);
+int vt_accel_set_refit_rebuild_ratio(vt_accel *accel, double ratio);
+
 /* Host-only: the refit step alone — `nodes` (bvh::Bvh<float> form, node_count entries) are updated in place for the
  * triangles of `scene`; prim_indices has scene->n_tris entries. */
 int vt_refit_bvh(const vt_scene *scene, vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices);

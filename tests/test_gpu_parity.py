@@ -731,3 +731,111 @@ def test_two_gpu_sharded_trace_nccl(vt):
                         "--master-port", "29571", f"{ROOT}/tests/multi_gpu_worker.py"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MULTI_GPU_OK" in r.stdout
+
+
+def test_refit_range_onto_an_alphatest_material_enables_the_alpha_test(vt, oracle_mod):
+    """a scene populated WITHOUT any alpha-tested triangle selects K1's no-alpha template; a refit that moves triangles
+    onto an alpha-tested material must switch the template (has_alphatest) — on the device path as well as on the host path."""
+    from vistrace_b200 import abi, scenes
+
+    base = scenes.scene_foliage(n_cards=800, tex_size=32, ground_quads=8)
+    alpha_mats = np.nonzero((base.materials["flags"] & abi.VT_MATFLAG_ALPHATEST) != 0)[0]
+    plain = int(np.nonzero((base.materials["flags"] & abi.VT_MATFLAG_ALPHATEST) == 0)[0][0])
+    assert len(alpha_mats) > 0
+    cards = np.nonzero(np.isin(base.tris["material"], alpha_mats))[0]
+    rays = np.concatenate([scenes.pinhole_rays(240, 135, (0, -48, 20), (0, 0, 8)), scenes.random_rays(10000, (-45, -45, -3), (45, 45, 50), seed=5)])
+    kind = "reference" if oracle_mod.available("reference") else "port"
+    cpu = oracle_mod.CpuScene(base, kind, build_bvh=False)
+    for path in ("range", "device", "host"):
+        start = base.tris.copy()
+        start["material"][cards] = plain  # nothing alpha-tested at populate time (a fresh copy: refit_range updates the scene it was given)
+        scene0 = abi.SceneData(start, base.materials, base.entities, base.textures)
+        accel = vt.Accel(0, layout="quad").populate(scene0)
+        opaque = accel.traverse(rays)
+        if path == "range":  # contiguous runs of card triangles, one refit_range each
+            runs = np.split(cards, np.nonzero(np.diff(cards) != 1)[0] + 1)
+            for r in runs:
+                accel.refit_range(base.tris[r[0]: r[-1] + 1], int(r[0]))
+        else:
+            import os
+
+            os.environ["VT_REFIT_DEVICE"] = "1" if path == "device" else "0"
+            try:
+                accel.refit(base)
+            finally:
+                del os.environ["VT_REFIT_DEVICE"]
+        cpu.set_bvh(*accel.get_bvh())
+        want = cpu.traverse(rays)["hits"]
+        got = accel.traverse(rays)
+        assert same_hits(got, want, "quad", rays, cpu), path
+        assert (got["prim"] != opaque["prim"]).sum() > 100, path  # rays now pass through the transparent texels
+        accel.close()
+
+
+def test_refit_quality_and_rebuild_trigger(vt):
+    """vt_accel_refit_quality: 1.0 as built, grows when moved geometry loosens the refitted boxes, returns to 1.0 when the geometry
+    moves back; with a rebuild ratio set, vt_accel_refit rebuilds from scratch once the refitted tree exceeds it."""
+    from test_host import _moved_props
+    from vistrace_b200 import scenes
+
+    scene = scenes.scene_props(8, 21, 11, 12)
+    moved = _moved_props(scene)
+    rays = scenes.pinhole_rays(200, 120, (0, -95, 40), (0, 0, 10))
+    accel = vt.Accel(0, layout="quad").populate(scene)
+    assert accel.refit_quality() == (1.0, 0)
+    accel.refit(moved)
+    ratio, rebuilds = accel.refit_quality()
+    assert ratio > 1.02 and rebuilds == 0, ratio  # the props left the places their subtrees were built for
+    refit_hits = accel.traverse(rays)
+    accel.refit(scene)
+    back, _ = accel.refit_quality()
+    assert abs(back - 1.0) < 1e-9, back
+    accel.set_refit_rebuild_ratio(1.0 + (ratio - 1.0) / 2)
+    accel.refit(moved)  # exceeds the tolerance: rebuilt
+    ratio2, rebuilds = accel.refit_quality()
+    assert rebuilds == 1 and ratio2 == 1.0
+    rep = compare_hits(accel.traverse(rays), refit_hits)  # another tree over the same triangles: same answer up to exact ties
+    assert rep["hit_miss_mismatch"] == 0 and rep["tuv_bit_mismatch"] == 0 and rep["prim_mismatch"] <= 3, rep
+    fresh = vt.Accel(0, layout="quad").populate(moved)
+    assert accel.traverse_stats(rays) == fresh.traverse_stats(rays)  # the rebuilt tree IS the tree a fresh populate builds
+
+
+@pytest.mark.parametrize("layout_id,layout_name", [(0, "exact"), (2, "quad")])
+def test_compiled_reference_side_binding(built, oracle_mod, layout_id, layout_name):
+    """INTEGRATION.md sections 2-4 COMPILED (oracle/ref_binding.cpp -> oracle/_ref/libvt_ref_binding.so): the real reference
+    AccelStruct runs its own PopulateAccel build sequence (source/objects/AccelStruct.cpp:762-775), hands its own containers and
+    its own collapsed bvh::Bvh to vt_accel_populate_with_bvh — textures through the public IVTFTexture interface only (GetPixel) —
+    and its own per-ray Traverse statements (:810-831) are compared with the batched GPU entry on the same rays."""
+    import ctypes as C
+    import os
+
+    from conftest import ROOT
+    from vistrace_b200 import abi, scenes
+
+    so = os.path.join(ROOT, "oracle", "_ref", "libvt_ref_binding.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libvt_ref_binding.so is built where /root/reference exists (make -C oracle binding)")
+    lib = C.CDLL(so)
+    lib.vtbind_selfcheck.restype = C.c_int
+    lib.vtbind_selfcheck.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint64]
+    for scene, rays in ((scenes.scene_foliage(n_cards=3000, tex_size=64, ground_quads=16),
+                         np.concatenate([scenes.pinhole_rays(320, 180, (0, -48, 20), (0, 0, 8)), scenes.random_rays(20000, (-45, -45, -3), (45, 45, 50), seed=5)])),
+                        (scenes.scene_props(8, 21, 11, 12),
+                         np.concatenate([scenes.pinhole_rays(320, 180, (0, -95, 40), (0, 0, 10)), scenes.random_rays(20000, (-90, -90, -5), (90, 90, 60), seed=3)]))):
+        rays = np.ascontiguousarray(rays, abi.RAY)
+        report = np.zeros(8, np.uint64)
+        worst = C.c_double(0)
+        err = C.create_string_buffer(512)
+        rc = lib.vtbind_selfcheck(C.cast(scene.ptr(), C.c_void_p), rays.ctypes.data, len(rays), layout_id, report.ctypes.data, C.addressof(worst), err, 512)
+        assert rc == 0, err.value.decode()
+        n, bytes_diff, hit_miss, tuv, prim, compared, n_tex, n_tris = (int(v) for v in report)
+        print(f"[binding] {layout_name}: {n} rays, {bytes_diff} records differ, {hit_miss} hit/miss, {tuv} t/u/v, {prim} prim; {n_tex} textures via GetPixel; attr err {worst.value:.3g}")
+        assert n == len(rays) and n_tris == scene.n_tris and compared > 0.3 * n
+        assert hit_miss == 0 and tuv == 0
+        assert worst.value <= 1e-5  # tolerance from BASELINE.json north_star
+        if layout_name == "exact":
+            assert bytes_diff == 0  # the reference's tree, the reference's visit order: its hit buffer byte for byte
+        else:
+            assert prim <= 3  # quantised layout: exact ties only
+        if len(scene.textures):
+            assert n_tex >= len(scene.textures)

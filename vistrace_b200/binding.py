@@ -54,6 +54,8 @@ SYMBOLS = {
     "vt_vtf_decode": (_i32, [_vp, _u64, _u32, _u32, _vp, _u64, _vp]),
     "vt_build_bvh_ploc": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "vt_build_quads": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "vt_accel_refit_quality": (_i32, [_vp, _vp, _vp]),
+    "vt_accel_set_refit_rebuild_ratio": (_i32, [_vp, C.c_double]),
     "vt_accel_invalid_rays": (_u64, [_vp]),
     "vt_accel_launch_count": (_u64, [_vp]),
     "vt_accel_stats": (_i32, [_vp, _vp, _vp, _vp]),
@@ -118,25 +120,21 @@ def _ptr(x):
 def build_bvh(scene):
     """Host-only hierarchy build -> (nodes, prim_indices) in bvh::Bvh<float> form."""
     L = lib()
-    cnt = C.c_uint64(0)
-    _check(L.vt_build_bvh(C.cast(scene.ptr(), _vp), None, C.addressof(cnt), None), "vt_build_bvh")
-    nodes = np.zeros(cnt.value, abi.NODE)
+    nodes = np.zeros(max(1, 2 * scene.n_tris), abi.NODE)  # a binary tree over n leaves has at most 2n - 1 nodes: ONE build, not two
     prims = np.zeros(scene.n_tris, np.uint64)
     cap = C.c_uint64(len(nodes))
     _check(L.vt_build_bvh(C.cast(scene.ptr(), _vp), nodes.ctypes.data, C.addressof(cap), prims.ctypes.data), "vt_build_bvh")
-    return nodes, prims
+    return nodes[: cap.value].copy(), prims
 
 
 def build_bvh_ploc(scene, collapse=True):
     """Host-only: the reference's own PLOC (+ LeafCollapser) hierarchy rebuilt from its algorithm -> (nodes, prim_indices)."""
     L = lib()
-    cnt = C.c_uint64(0)
-    _check(L.vt_build_bvh_ploc(C.cast(scene.ptr(), _vp), int(collapse), None, C.addressof(cnt), None), "vt_build_bvh_ploc")
-    nodes = np.zeros(cnt.value, abi.NODE)
+    nodes = np.zeros(max(1, 2 * scene.n_tris), abi.NODE)
     prims = np.zeros(scene.n_tris, np.uint64)
     cap = C.c_uint64(len(nodes))
     _check(L.vt_build_bvh_ploc(C.cast(scene.ptr(), _vp), int(collapse), nodes.ctypes.data, C.addressof(cap), prims.ctypes.data), "vt_build_bvh_ploc")
-    return nodes, prims
+    return nodes[: cap.value].copy(), prims
 
 
 def refit_bvh(scene, nodes, prim_indices):
@@ -237,14 +235,13 @@ def build_quads(nodes, prim_indices):
     L = lib()
     nodes = np.ascontiguousarray(nodes, abi.NODE)
     prim_indices = np.ascontiguousarray(prim_indices, np.uint64)
-    cnt = C.c_uint64(0)
     args = (nodes.ctypes.data, len(nodes), prim_indices.ctypes.data, len(prim_indices))
-    _check(L.vt_build_quads(*args, None, C.addressof(cnt), None, None, None), "vt_build_quads")
-    quads = np.zeros(cnt.value, QUAD)
+    quads = np.zeros(max(1, len(nodes)), QUAD)  # never more quads than binary nodes: one call
+    cnt = C.c_uint64(len(quads))
     order = np.zeros(len(prim_indices), np.uint32)
     rl, ms = C.c_uint32(0), C.c_uint32(0)
     _check(L.vt_build_quads(*args, quads.ctypes.data, C.addressof(cnt), order.ctypes.data, C.addressof(rl), C.addressof(ms)), "vt_build_quads")
-    return {"quads": quads, "leaf_order": order, "root_leaf_count": rl.value, "max_stack": ms.value}
+    return {"quads": quads[: cnt.value].copy(), "leaf_order": order, "root_leaf_count": rl.value, "max_stack": ms.value}
 
 
 class Accel:
@@ -307,6 +304,16 @@ class Accel:
         tris = np.ascontiguousarray(tris, abi.TRI_IN)
         _check(self.L.vt_accel_refit_range(self.h, tris.ctypes.data, first, len(tris)), "vt_accel_refit_range")
         self.scene.tris[first:first + len(tris)] = tris  # keep the Python-side copy in step (tri_derived sizes, later refits)
+        return self
+
+    def refit_quality(self):
+        """(node-area sum now / as built, rebuilds triggered so far)."""
+        ratio, n = C.c_double(0), C.c_uint64(0)
+        _check(self.L.vt_accel_refit_quality(self.h, C.addressof(ratio), C.addressof(n)), "vt_accel_refit_quality")
+        return ratio.value, n.value
+
+    def set_refit_rebuild_ratio(self, ratio):
+        _check(self.L.vt_accel_set_refit_rebuild_ratio(self.h, float(ratio)), "vt_accel_set_refit_rebuild_ratio")
         return self
 
     def get_bvh(self):

@@ -14,6 +14,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <omp.h>
 
 #include "vt_accel_internal.h"
 #include "vt_math.cuh"
@@ -25,7 +26,7 @@ thread_local std::string g_last_error;
 // ------------------------------------------------------------------------------ Triangle
 Triangle::Triangle(const float p0_[3], const float p1[3], const float p2[3], uint32_t material_, const float uvs_[3][2],
                    bool oneSided_)
-    : oneSided(oneSided_), material(material_) {
+    : oneSided(oneSided_), material(material_), entIdx(0), lod(0.f) {
     for (int k = 0; k < 3; k++) {
         p0[k] = p0_[k];
         e1[k] = p0_[k] - p1[k];  // e1 = p0 - p1, e2 = p2 - p0  (Primitives.h:82)
@@ -131,6 +132,25 @@ void SkinTriangles(vt_tri_in *tris, const vt_tri_skin *skin, uint64_t n, const f
 }
 
 // ----------------------------------------------------------------------------- AccelStruct
+namespace {
+struct PhaseTimer {  // VT_TIMING=1: one stderr line per host phase of a populate (rebuild latency)
+    bool on = env_int("VT_TIMING", 0) != 0;
+    double t0 = omp_get_wtime();
+    void lap(const char *what) {
+        if (!on) return;
+        const double t = omp_get_wtime();
+        std::fprintf(stderr, "[populate] %-28s %.3f s\n", what, t - t0);
+        t0 = t;
+    }
+};
+}  // namespace
+
+double AccelStruct::RefitQuality() const {
+    const DeviceScene &D = *mpDevice;
+    if (!D.refit_ready || !(D.refit_cost_built > 0.0) || !(D.refit_cost_now > 0.0)) return 1.0;  // never refitted on the device
+    return D.refit_cost_now / D.refit_cost_built;
+}
+
 static void check_built(bool built) {
     // source/objects/AccelStruct.cpp:780
     if (!built) throw std::runtime_error("Unable to perform traversal, acceleration structure invalid (use AccelStruct:Rebuild to rebuild it)");
@@ -159,7 +179,18 @@ AccelStruct::AccelStruct(int device) : mDevice(device) {
     VT_CUDA(cudaStreamCreateWithFlags(&mpDevice->own_stream, cudaStreamNonBlocking));
 }
 
+void AccelStruct::JoinAttrUpload() {
+    if (mAttrUpload.joinable()) mAttrUpload.join();
+    RawVector<VtTriAttr>().swap(mAttrStage);
+    if (!mAttrUploadError.empty()) {
+        const std::string e = mAttrUploadError;
+        mAttrUploadError.clear();
+        throw std::runtime_error(e);
+    }
+}
+
 AccelStruct::~AccelStruct() {
+    if (mAttrUpload.joinable()) mAttrUpload.join();
     if (mpDevice) {
         cudaSetDevice(mDevice);
         delete mpDevice;
@@ -168,7 +199,7 @@ AccelStruct::~AccelStruct() {
 
 uint64_t AccelStruct::DeviceBytes() const { return mpDevice ? mpDevice->scene_bytes() : 0; }
 
-void AccelStruct::Ingest(const vt_scene &scene) {
+void AccelStruct::Ingest(const vt_scene &scene, bool stage_attrs) {
     // PopulateAccel prologue (source/objects/AccelStruct.cpp:537-556): drop the old structure, refill containers
     mAccelBuilt = false;
     mTriangles.clear();
@@ -193,7 +224,9 @@ void AccelStruct::Ingest(const vt_scene &scene) {
         for (uint32_t m = 0; m < t.mip_count; m++) need += (uint64_t)std::max(1, t.width >> m) * std::max(1, t.height >> m) * 4;
         if (need != t.nbytes) throw std::runtime_error("texture " + std::to_string(i) + ": nbytes does not match the RGBA8888 mip chain");
     }
+    if (mAttrUpload.joinable()) mAttrUpload.join();
     mTriangles.resize(scene.n_tris);
+    mAttrStage.resize(stage_attrs ? scene.n_tris : 0);
     bool bad = false;
 #pragma omp parallel for
     for (int64_t i = 0; i < (int64_t)scene.n_tris; i++) {
@@ -205,8 +238,36 @@ void AccelStruct::Ingest(const vt_scene &scene) {
         t.entIdx = in.ent_idx;
         if (in.material >= scene.n_materials || in.ent_idx >= scene.n_entities) bad = true;
         mTriangles[i] = t;
+        if (!stage_attrs) continue;
+        VtTriAttr &a = mAttrStage[i];  // everything TraceResult::TraceResult copies (TraceResult.cpp:58-78), original order
+        std::memset(&a, 0, sizeof(a));
+        std::memcpy(a.p0, t.p0, 12);
+        std::memcpy(a.e1, t.e1, 12);
+        std::memcpy(a.e2, t.e2, 12);
+        std::memcpy(a.nNorm, t.nNorm, 12);
+        std::memcpy(a.normals, t.normals, 36);
+        std::memcpy(a.tangents, t.tangents, 36);
+        std::memcpy(a.uvs, t.uvs, 24);
+        std::memcpy(a.alphas, t.alphas, 12);
+        a.lod = t.lod;
+        a.material = t.material;
+        a.ent_idx = t.entIdx;
     }
-    if (bad) throw std::runtime_error("triangle references a material or entity out of range");
+    if (bad) {
+        RawVector<VtTriAttr>().swap(mAttrStage);
+        throw std::runtime_error("triangle references a material or entity out of range");
+    }
+    if (!stage_attrs) return;
+    // async upload: the attribute records go up while the caller builds / flattens the hierarchy; Upload() joins
+    mAttrUploadError.clear();
+    mAttrUpload = std::thread([this] {
+        try {
+            VT_CUDA(cudaSetDevice(mDevice));
+            mpDevice->attrs.upload(mAttrStage.data(), mAttrStage.size());
+        } catch (const std::exception &e) {
+            mAttrUploadError = e.what();
+        }
+    });
 }
 
 void AccelStruct::Upload(const vt_scene &scene) {
@@ -219,6 +280,7 @@ void AccelStruct::Upload(const vt_scene &scene) {
 
     // Node layout (include/vistrace_b200.h: VT_LAYOUT_*).  A tree the quantised layouts cannot hold (a leaf of
     // more than 15 triangles, non-finite bounds, too deep) falls back to the exact layout.
+    PhaseTimer timer;
     int layout = mWantLayout;
     uint32_t smem_pairs = layout == VT_LAYOUT_EXACT ? (uint32_t)env_int("VT_SMEM_PAIRS", 0) : 0u;  // exact only: breadth-first prefix staged in smem
     FlatBvh flat;
@@ -236,16 +298,17 @@ void AccelStruct::Upload(const vt_scene &scene) {
             cpairs.clear();
         }
     }
+    timer.lap("  node layout (collapse/quantise)");
     mLayout = layout;
-    const std::vector<uint32_t> &leaf_order = layout == VT_LAYOUT_QUAD ? quad.leaf_order : flat.leaf_order;
+    const uint32_t *leaf_order = layout == VT_LAYOUT_QUAD ? quad.leaf_order.data() : flat.leaf_order.data();
     const uint32_t root_leaf_count = layout == VT_LAYOUT_QUAD ? quad.root_leaf_count : flat.root_leaf_count;
     const uint32_t n_inner = layout == VT_LAYOUT_QUAD ? (uint32_t)quad.quads.size() : (uint32_t)flat.pairs.size();
 
     // leaf-order geometry records + UVs; original-order attribute records
     // quad layout: one extra all-NaN record behind the last triangle, the target of empty child slots (vt_device.h)
     const bool sentinel = VT_EMPTY_SENTINEL && layout == VT_LAYOUT_QUAD;
-    std::vector<VtTriRec> recs(n + (sentinel ? 1 : 0));
-    std::vector<float> uv((n + (sentinel ? 1 : 0)) * 6);
+    RawVector<VtTriRec> recs(n + (sentinel ? 1 : 0));  // every byte is written by the loops below: no zero-fill (vt_host.h)
+    RawVector<float> uv((n + (sentinel ? 1 : 0)) * 6);
     if (sentinel) {
         VtTriRec &r = recs[n];
         const float nan = std::numeric_limits<float>::quiet_NaN();
@@ -258,7 +321,6 @@ void AccelStruct::Upload(const vt_scene &scene) {
             for (int i = 0; i < 4; i++)
                 if (q.ref[i] == 0xFFFFFFFFu) q.ref[i] = ref;
     }
-    std::vector<VtTriAttr> attrs(n);
     uint32_t any_alpha = 0;
 #pragma omp parallel for reduction(| : any_alpha)
     for (int64_t s = 0; s < (int64_t)n; s++) {
@@ -281,23 +343,6 @@ void AccelStruct::Upload(const vt_scene &scene) {
         r.pad[0] = r.pad[1] = 0;
         std::memcpy(&uv[6 * s], t.uvs, 6 * sizeof(float));
     }
-#pragma omp parallel for
-    for (int64_t i = 0; i < (int64_t)n; i++) {
-        const Triangle &t = mTriangles[i];
-        VtTriAttr &a = attrs[i];
-        std::memcpy(a.p0, t.p0, 12);
-        std::memcpy(a.e1, t.e1, 12);
-        std::memcpy(a.e2, t.e2, 12);
-        std::memcpy(a.nNorm, t.nNorm, 12);
-        std::memcpy(a.normals, t.normals, 36);
-        std::memcpy(a.tangents, t.tangents, 36);
-        std::memcpy(a.uvs, t.uvs, 24);
-        std::memcpy(a.alphas, t.alphas, 12);
-        a.lod = t.lod;
-        a.material = t.material;
-        a.ent_idx = t.entIdx;
-    }
-
     // materials / entities / textures (+ the 1x1 white stand-in for a null baseTexture: ingestion never
     // leaves it null — fallback MISSING_TEXTURE, source/objects/AccelStruct.cpp:120,286)
     std::vector<VtDevMaterial> dm(mMaterials.size());
@@ -360,7 +405,9 @@ void AccelStruct::Upload(const vt_scene &scene) {
     const uint8_t white[4] = {255, 255, 255, 255};
     add_texture(dt[scene.n_textures], 1, 1, 1, 0, white, 4);
 
+    timer.lap("  triangle / attr records");
     D.refit_ready = false;
+    D.refit_cost_built = D.refit_cost_now = 0.0;
     mBvhStale = false;
     mReplica = false;
     D.pairs.release();
@@ -371,12 +418,13 @@ void AccelStruct::Upload(const vt_scene &scene) {
     else D.pairs.upload(flat.pairs.data(), flat.pairs.size());
     D.tris.upload(recs.data(), recs.size());
     D.tri_uv.upload(uv.data(), uv.size());
-    D.attrs.upload(attrs.data(), n);
+    JoinAttrUpload();  // D.attrs: uploaded by Ingest's helper thread while the hierarchy was being built
     D.mats.upload(dm.data(), dm.size());
     D.ents.upload(de.data(), de.size());
     D.texs.upload(dt.data(), dt.size());
     D.texels.upload(texels.data(), texels.size());
 
+    timer.lap("  cudaMalloc + H2D");
     VtSceneView &V = D.view;
     V.pairs = layout == VT_LAYOUT_EXACT ? D.pairs.p : nullptr;
     V.cpairs = layout == VT_LAYOUT_COMPACT ? D.cpairs.p : nullptr;
@@ -408,7 +456,9 @@ void AccelStruct::Upload(const vt_scene &scene) {
 }
 
 void AccelStruct::Populate(const vt_scene &scene) {
+    PhaseTimer timer;
     Ingest(scene);
+    timer.lap("ingest (Triangle ctor)");
     // the build step of source/objects/AccelStruct.cpp:762-770, host side: the product's binned-SAH builder, or (VT_BUILDER=ploc)
     // the reference's own PLOC + LeafCollapser tree, node for node (vt_bvh_ploc.cpp)
     const char *builder = std::getenv("VT_BUILDER");
@@ -418,7 +468,9 @@ void AccelStruct::Populate(const vt_scene &scene) {
     } else {
         build_bvh(mTriangles, mAccel, env_int("VT_MAX_LEAF", 4), env_float("VT_TRAV_COST", 1.0f));
     }
+    timer.lap("hierarchy build");
     Upload(scene);
+    timer.lap("flatten + records + upload");
 }
 
 void AccelStruct::PopulateWithBvh(const vt_scene &scene, const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices) {
@@ -550,15 +602,24 @@ void AccelStruct::Refit(const vt_scene &scene) {
             D.refit_qbox.ensure((size_t)V.n_pairs * 6);
             D.refit_slot_of.ensure(V.n_tris);
             D.refit_error.ensure(1);
+            D.refit_cost.ensure(1);
             VT_CUDA(vt_launch_refit_prepare(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_slot_of.p, stream));
-            mLaunches++;
+            // the tree AS BUILT: one bottom-up pass over the unchanged geometry fills the box table and gives the node-area sum that
+            // later refits are measured against (the pass re-derives the very bytes it reads: idempotent)
+            VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
+            VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
+            VT_CUDA(vt_launch_refit_cost(D.refit_qbox.p, V.n_pairs, D.refit_cost.p, stream));
+            VT_CUDA(cudaMemcpyAsync(&D.refit_cost_built, D.refit_cost.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+            mLaunches += 3;
             D.refit_ready = true;
         }
         VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
         VT_CUDA(vt_launch_refit_tris(V, D.refit_in.p, 0, (uint32_t)scene.n_tris, D.refit_slot_of.p, stream));
         VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
-        mLaunches += 2;
-        Ingest(scene);  // host copies of the containers (clears mAccelBuilt; mAccel keeps the structure)
+        VT_CUDA(vt_launch_refit_cost(D.refit_qbox.p, V.n_pairs, D.refit_cost.p, stream));
+        VT_CUDA(cudaMemcpyAsync(&D.refit_cost_now, D.refit_cost.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        mLaunches += 3;
+        Ingest(scene, false);  // host copies of the containers only (K5 writes the device records; clears mAccelBuilt, mAccel keeps the structure)
         uint32_t failed = 0;
         VT_CUDA(cudaMemcpyAsync(&failed, D.refit_error.p, sizeof(failed), cudaMemcpyDeviceToHost, stream));
         VT_CUDA(cudaStreamSynchronize(stream));
@@ -566,6 +627,13 @@ void AccelStruct::Refit(const vt_scene &scene) {
         if (!failed) {
             mBvhStale = true;
             mAccelBuilt = true;
+            // rebuild trigger: refits keep the topology of the ORIGINAL geometry; when the moved geometry has loosened the boxes
+            // beyond the caller's tolerance the structure is rebuilt from scratch (what accel:Rebuild always does in the reference)
+            const double limit = mRefitRebuildRatio > 0.0 ? mRefitRebuildRatio : (double)env_float("VT_REFIT_REBUILD_RATIO", 0.f);
+            if (limit > 0.0 && RefitQuality() > limit) {
+                Populate(scene);
+                mRebuilds++;
+            }
             return;
         }
         // a box left the float grid the quantised layout can hold: re-derive the layout on the host (may fall back to exact)
@@ -608,14 +676,21 @@ void AccelStruct::RefitRange(const vt_tri_in *tris, uint64_t first, uint64_t cou
         D.refit_qbox.ensure((size_t)V.n_pairs * 6);
         D.refit_slot_of.ensure(V.n_tris);
         D.refit_error.ensure(1);
+        D.refit_cost.ensure(1);
         VT_CUDA(vt_launch_refit_prepare(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_slot_of.p, stream));
-        mLaunches++;
+        VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));  // the tree as built: see Refit
+        VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
+        VT_CUDA(vt_launch_refit_cost(D.refit_qbox.p, V.n_pairs, D.refit_cost.p, stream));
+        VT_CUDA(cudaMemcpyAsync(&D.refit_cost_built, D.refit_cost.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        mLaunches += 3;
         D.refit_ready = true;
     }
     VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
     VT_CUDA(vt_launch_refit_tris(V, D.refit_in.p, (uint32_t)first, (uint32_t)count, D.refit_slot_of.p, stream));
     VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
-    mLaunches += 2;
+    VT_CUDA(vt_launch_refit_cost(D.refit_qbox.p, V.n_pairs, D.refit_cost.p, stream));
+    VT_CUDA(cudaMemcpyAsync(&D.refit_cost_now, D.refit_cost.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    mLaunches += 3;
     mAccelBuilt = false;  // until the device reports success
 #pragma omp parallel for
     for (int64_t i = 0; i < (int64_t)count; i++) {  // the host copy of the containers, as Ingest fills them
@@ -1313,7 +1388,7 @@ int vt_accel_refit_range(vt_accel *a, const vt_tri_in *tris, uint64_t first, uin
 int vt_refit_bvh(const vt_scene *scene, vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices) {
     VT_TRY
     if (!scene || !nodes || !prim_indices) throw std::runtime_error("null argument");
-    std::vector<vt::Triangle> tris(scene->n_tris);
+    vt::TriangleVec tris(scene->n_tris);
 #pragma omp parallel for
     for (int64_t i = 0; i < (int64_t)scene->n_tris; i++) {
         const vt_tri_in &in = scene->tris[i];
@@ -1500,6 +1575,23 @@ int vt_accel_traverse_stats(vt_accel *a, const vt_ray *rays, uint64_t n, uint32_
     VT_CATCH(1)
 }
 
+int vt_accel_refit_quality(const vt_accel *a, double *area_ratio, uint64_t *rebuilds) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    if (area_ratio) *area_ratio = a->impl.RefitQuality();
+    if (rebuilds) *rebuilds = a->impl.Rebuilds();
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_set_refit_rebuild_ratio(vt_accel *a, double ratio) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.SetRefitRebuildRatio(ratio);
+    return 0;
+    VT_CATCH(1)
+}
+
 uint64_t vt_accel_invalid_rays(const vt_accel *a) { return a ? a->impl.InvalidRays() : 0; }
 uint64_t vt_accel_launch_count(const vt_accel *a) { return a ? a->impl.Launches() : 0; }
 
@@ -1540,7 +1632,7 @@ int vt_accel_get_tri_derived(const vt_accel *a, float *out16) {
 int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices) {
     VT_TRY
     if (!scene || !node_count) throw std::runtime_error("null argument");
-    std::vector<vt::Triangle> tris(scene->n_tris);
+    vt::TriangleVec tris(scene->n_tris);
 #pragma omp parallel for
     for (int64_t i = 0; i < (int64_t)scene->n_tris; i++) {
         const vt_tri_in &in = scene->tris[i];
@@ -1561,7 +1653,7 @@ int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, ui
 int vt_build_bvh_ploc(const vt_scene *scene, int collapse, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices) {
     VT_TRY
     if (!scene || !node_count) throw std::runtime_error("null argument");
-    std::vector<vt::Triangle> tris(scene->n_tris);
+    vt::TriangleVec tris(scene->n_tris);
 #pragma omp parallel for
     for (int64_t i = 0; i < (int64_t)scene->n_tris; i++) {
         const vt_tri_in &in = scene->tris[i];

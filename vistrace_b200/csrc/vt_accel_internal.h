@@ -117,6 +117,8 @@ struct DeviceScene {
     DevBuf<vt_tri_in> refit_in;
     DevBuf<uint32_t> refit_parent, refit_n_inner, refit_slot_of, refit_arrive, refit_error;
     DevBuf<float> refit_qbox;  // 6 floats per quad
+    DevBuf<double> refit_cost;  // device scalar of k_refit_cost
+    double refit_cost_built = 0.0, refit_cost_now = 0.0;  // node-area sums: as built (taken when the refit state is prepared) / after the last refit
     bool refit_ready = false;
     VtSceneView view{};
     VtLaunchConfig cfg;
@@ -157,6 +159,7 @@ struct DeviceScene {
         refit_arrive.release();
         refit_error.release();
         refit_qbox.release();
+        refit_cost.release();
         for (auto &l : lanes) {
             l.brays.release();
             l.hits.release();

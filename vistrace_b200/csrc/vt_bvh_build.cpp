@@ -14,8 +14,11 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <omp.h>
 
 namespace vt {
@@ -47,10 +50,11 @@ struct Box {
 
 constexpr int kBins = 16;
 constexpr int kMaxDepth = 60;
+constexpr uint32_t kParallelNode = 1u << 17;  // nodes with at least this many primitives are binned / partitioned by the whole team
 
 struct BuildCtx {
     const float *bmin, *bmax, *cen;  // n x 3 each
-    uint32_t *idx;
+    uint32_t *idx, *scratch;         // scratch: n entries, the target of the parallel partition
     vt_node *nodes;
     std::atomic<uint32_t> next_node;
     int max_leaf;
@@ -72,8 +76,61 @@ int ceil_log2(uint64_t v) {
     return l;
 }
 
-// Build the subtree over idx[begin, end) into nodes[node]; `box` is its bounds.
-void build_range(BuildCtx &c, uint32_t node, uint32_t begin, uint32_t end, const Box &box, int depth) {
+// One bin of one axis: the primitives whose centroid falls into it — their box, the box of their centroids, their number.
+struct Bin {
+    Box box, cbox;
+    uint32_t count;
+    // the boxes of an empty bin are never read (every reader checks `count`) and the first primitive ASSIGNS them, so clearing a
+    // bin is one store — 2.6 M inner nodes x 48 bins of 52 bytes would otherwise be 6.5 GB of resets at 5 M triangles
+    void add(const float *mn, const float *mx, const float *ce) {
+        if (count++ == 0) {
+            for (int k = 0; k < 3; k++) box.lo[k] = mn[k], box.hi[k] = mx[k], cbox.lo[k] = cbox.hi[k] = ce[k];
+        } else {
+            box.grow(mn, mx);
+            cbox.grow_pt(ce);
+        }
+    }
+    void merge(const Bin &o) {
+        if (!o.count) return;
+        if (!count) {
+            *this = o;
+            return;
+        }
+        box.grow(o.box);
+        cbox.grow(o.cbox);
+        count += o.count;
+    }
+};
+struct Bins {
+    Bin b[3][kBins];
+    void reset() {
+        for (int a = 0; a < 3; a++)
+            for (int k = 0; k < kBins; k++) b[a][k].count = 0;
+    }
+};
+
+inline int bin_of(float c, float lo, float scale) {
+    int b = (int)((c - lo) * scale);
+    return b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+}
+
+// ONE pass over idx[begin, end): all three axes binned at once.  Child boxes and child centroid boxes fall out of the bins
+// (min / max are exact, so they equal what a pass over the child's primitives would give), which leaves two passes per node —
+// this one and the partition — instead of seven.
+void bin_range(const BuildCtx &c, uint32_t begin, uint32_t end, const Box &cb, const float scale[3], Bins &out) {
+    out.reset();
+    for (uint32_t i = begin; i < end; i++) {
+        const size_t p = c.idx[i];
+        const float *mn = c.bmin + 3 * p, *mx = c.bmax + 3 * p, *ce = c.cen + 3 * p;
+        for (int a = 0; a < 3; a++) {
+            if (!(scale[a] > 0.f)) continue;
+            out.b[a][bin_of(ce[a], cb.lo[a], scale[a])].add(mn, mx, ce);
+        }
+    }
+}
+
+// Build the subtree over idx[begin, end) into nodes[node]; `box` is its bounds, `cb` the bounds of its centroids.
+void build_range(BuildCtx &c, uint32_t node, uint32_t begin, uint32_t end, const Box &box, const Box &cb, int depth) {
     vt_node &nd = c.nodes[node];
     set_bounds(nd, box);
     const uint32_t count = end - begin;
@@ -83,48 +140,52 @@ void build_range(BuildCtx &c, uint32_t node, uint32_t begin, uint32_t end, const
     };
     if (count <= 1) return make_leaf();
 
-    Box cb;
-    cb.reset();
-    for (uint32_t i = begin; i < end; i++) cb.grow_pt(c.cen + 3 * (size_t)c.idx[i]);
-
     // binned SAH over the three axes
     float best_cost = std::numeric_limits<float>::max();
     int best_axis = -1, best_bin = -1;
+    float scale[3];
+    for (int a = 0; a < 3; a++) {
+        const float ext = cb.hi[a] - cb.lo[a];
+        scale[a] = ext > 0.f ? kBins / ext : 0.f;
+    }
     const bool force_balance = depth + ceil_log2((count + c.max_leaf - 1) / c.max_leaf) >= kMaxDepth - 1;
+    Bins bins;
+    const bool big = count >= kParallelNode;
     if (!force_balance) {
+        if (big) {  // the top of the tree: every thread bins a slice, the slices are merged
+            const int parts = std::max(1, std::min(omp_get_num_threads() * 4, (int)(count / 32768)));
+            std::vector<Bins> part(parts);
+#pragma omp taskloop shared(c, part, cb, scale) grainsize(1)
+            for (int t = 0; t < parts; t++) {
+                const uint32_t b0 = begin + (uint32_t)((uint64_t)count * t / parts), b1 = begin + (uint32_t)((uint64_t)count * (t + 1) / parts);
+                bin_range(c, b0, b1, cb, scale, part[t]);
+            }
+            bins.reset();
+            for (int t = 0; t < parts; t++)
+                for (int a = 0; a < 3; a++)
+                    for (int k = 0; k < kBins; k++) bins.b[a][k].merge(part[t].b[a][k]);
+        } else {
+            bin_range(c, begin, end, cb, scale, bins);
+        }
         for (int axis = 0; axis < 3; axis++) {
-            const float ext = cb.hi[axis] - cb.lo[axis];
-            if (!(ext > 0.f)) continue;
-            const float scale = kBins / ext;
-            Box bb[kBins];
-            uint32_t bc[kBins];
-            for (int b = 0; b < kBins; b++) {
-                bb[b].reset();
-                bc[b] = 0;
-            }
-            for (uint32_t i = begin; i < end; i++) {
-                const size_t p = c.idx[i];
-                int b = (int)((c.cen[3 * p + axis] - cb.lo[axis]) * scale);
-                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-                bb[b].grow(c.bmin + 3 * p, c.bmax + 3 * p);
-                bc[b]++;
-            }
+            if (!(scale[axis] > 0.f)) continue;
+            const Bin *bb = bins.b[axis];
             float right_area[kBins];
             uint32_t right_cnt[kBins];
             Box acc;
             acc.reset();
             uint32_t n = 0;
             for (int b = kBins - 1; b > 0; b--) {
-                if (bc[b]) acc.grow(bb[b]);
-                n += bc[b];
+                if (bb[b].count) acc.grow(bb[b].box);
+                n += bb[b].count;
                 right_area[b] = acc.valid() ? acc.half_area() : 0.f;
                 right_cnt[b] = n;
             }
             acc.reset();
             n = 0;
             for (int b = 0; b < kBins - 1; b++) {
-                if (bc[b]) acc.grow(bb[b]);
-                n += bc[b];
+                if (bb[b].count) acc.grow(bb[b].box);
+                n += bb[b].count;
                 if (n == 0 || right_cnt[b + 1] == 0) continue;
                 const float cost = acc.half_area() * (float)n + right_area[b + 1] * (float)right_cnt[b + 1];
                 if (cost < best_cost) {
@@ -143,15 +204,51 @@ void build_range(BuildCtx &c, uint32_t node, uint32_t begin, uint32_t end, const
     }
 
     uint32_t mid;
+    Box lb, rb, lcb, rcb;
+    lb.reset(), rb.reset(), lcb.reset(), rcb.reset();
+    bool boxes_known = false;
     if (best_axis >= 0) {
-        const float lo = cb.lo[best_axis], scale = kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+        const float lo = cb.lo[best_axis], sc = scale[best_axis];
         const int axis = best_axis, bin = best_bin;
-        uint32_t *m = std::partition(c.idx + begin, c.idx + end, [&](uint32_t p) {
-            int b = (int)((c.cen[3 * (size_t)p + axis] - lo) * scale);
-            b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-            return b <= bin;
-        });
-        mid = (uint32_t)(m - c.idx);
+        uint32_t n_left = 0;
+        for (int b = 0; b < kBins; b++) {
+            const Bin &bn = bins.b[axis][b];
+            if (!bn.count) continue;
+            if (b <= bin) lb.grow(bn.box), lcb.grow(bn.cbox), n_left += bn.count;
+            else rb.grow(bn.box), rcb.grow(bn.cbox);
+        }
+        boxes_known = true;
+        if (big) {  // stable partition through the scratch array: slices count, offsets follow from the counts, slices scatter
+            const int parts = std::max(1, std::min(omp_get_num_threads() * 4, (int)(count / 32768)));
+            std::vector<uint32_t> left_in(parts + 1, 0);
+#pragma omp taskloop shared(c, left_in) grainsize(1)
+            for (int t = 0; t < parts; t++) {
+                const uint32_t b0 = begin + (uint32_t)((uint64_t)count * t / parts), b1 = begin + (uint32_t)((uint64_t)count * (t + 1) / parts);
+                uint32_t k = 0;
+                for (uint32_t i = b0; i < b1; i++) k += bin_of(c.cen[3 * (size_t)c.idx[i] + axis], lo, sc) <= bin ? 1u : 0u;
+                left_in[t + 1] = k;
+            }
+            for (int t = 0; t < parts; t++) left_in[t + 1] += left_in[t];
+#pragma omp taskloop shared(c, left_in) grainsize(1)
+            for (int t = 0; t < parts; t++) {
+                const uint32_t b0 = begin + (uint32_t)((uint64_t)count * t / parts), b1 = begin + (uint32_t)((uint64_t)count * (t + 1) / parts);
+                uint32_t l = begin + left_in[t], r = begin + n_left + (b0 - begin - left_in[t]);
+                for (uint32_t i = b0; i < b1; i++) {
+                    const uint32_t p = c.idx[i];
+                    if (bin_of(c.cen[3 * (size_t)p + axis], lo, sc) <= bin) c.scratch[l++] = p;
+                    else c.scratch[r++] = p;
+                }
+            }
+#pragma omp taskloop shared(c) grainsize(1)
+            for (int t = 0; t < parts; t++) {
+                const uint32_t b0 = begin + (uint32_t)((uint64_t)count * t / parts), b1 = begin + (uint32_t)((uint64_t)count * (t + 1) / parts);
+                std::memcpy(c.idx + b0, c.scratch + b0, (size_t)(b1 - b0) * sizeof(uint32_t));
+            }
+            mid = begin + n_left;
+        } else {
+            uint32_t *m = std::partition(c.idx + begin, c.idx + end, [&](uint32_t p) { return bin_of(c.cen[3 * (size_t)p + axis], lo, sc) <= bin; });
+            mid = (uint32_t)(m - c.idx);
+        }
     } else {
         // all centroids coincide, or the depth budget forces a balanced split: median along the widest axis
         int axis = 0;
@@ -163,25 +260,27 @@ void build_range(BuildCtx &c, uint32_t node, uint32_t begin, uint32_t end, const
             return ca < cb2 || (ca == cb2 && a < b);
         });
     }
-    if (mid == begin || mid == end) mid = begin + count / 2;
-
-    Box lb, rb;
-    lb.reset();
-    rb.reset();
-    for (uint32_t i = begin; i < mid; i++) lb.grow(c.bmin + 3 * (size_t)c.idx[i], c.bmax + 3 * (size_t)c.idx[i]);
-    for (uint32_t i = mid; i < end; i++) rb.grow(c.bmin + 3 * (size_t)c.idx[i], c.bmax + 3 * (size_t)c.idx[i]);
+    if (mid == begin || mid == end) {
+        mid = begin + count / 2;
+        boxes_known = false;
+    }
+    if (!boxes_known) {
+        lb.reset(), rb.reset(), lcb.reset(), rcb.reset();
+        for (uint32_t i = begin; i < mid; i++) lb.grow(c.bmin + 3 * (size_t)c.idx[i], c.bmax + 3 * (size_t)c.idx[i]), lcb.grow_pt(c.cen + 3 * (size_t)c.idx[i]);
+        for (uint32_t i = mid; i < end; i++) rb.grow(c.bmin + 3 * (size_t)c.idx[i], c.bmax + 3 * (size_t)c.idx[i]), rcb.grow_pt(c.cen + 3 * (size_t)c.idx[i]);
+    }
 
     const uint32_t child = c.next_node.fetch_add(2);
     nd.prim_count = 0;
     nd.first = child;
     if (count > 4096) {
-#pragma omp task shared(c) firstprivate(child, begin, mid, lb, depth)
-        build_range(c, child, begin, mid, lb, depth + 1);
-#pragma omp task shared(c) firstprivate(child, mid, end, rb, depth)
-        build_range(c, child + 1, mid, end, rb, depth + 1);
+#pragma omp task shared(c) firstprivate(child, begin, mid, lb, lcb, depth)
+        build_range(c, child, begin, mid, lb, lcb, depth + 1);
+#pragma omp task shared(c) firstprivate(child, mid, end, rb, rcb, depth)
+        build_range(c, child + 1, mid, end, rb, rcb, depth + 1);
     } else {
-        build_range(c, child, begin, mid, lb, depth + 1);
-        build_range(c, child + 1, mid, end, rb, depth + 1);
+        build_range(c, child, begin, mid, lb, lcb, depth + 1);
+        build_range(c, child + 1, mid, end, rb, rcb, depth + 1);
     }
 }
 
@@ -189,18 +288,28 @@ void build_range(BuildCtx &c, uint32_t node, uint32_t begin, uint32_t end, const
 
 // Build a bvh::Bvh<float>-form hierarchy over the triangles.  Deterministic: the tree depends only
 // on the input, and the final node order is a depth-first relayout of it.
-void build_bvh(const std::vector<Triangle> &tris, HostBvh &out, int max_leaf, float trav_cost) {
+void build_bvh(const TriangleVec &tris, HostBvh &out, int max_leaf, float trav_cost) {
     const size_t n = tris.size();
     out.nodes.clear();
     out.prim_indices.clear();
     if (n == 0) return;
-    std::vector<float> bmin(3 * n), bmax(3 * n), cen(3 * n);
-    Box global;
+    const bool timing = std::getenv("VT_TIMING") && std::atoi(std::getenv("VT_TIMING")) != 0;
+    double t_phase = omp_get_wtime();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const double t = omp_get_wtime();
+        std::fprintf(stderr, "[build_bvh] %-24s %.3f s\n", what, t - t_phase);
+        t_phase = t;
+    };
+    RawVector<float> bmin(3 * n), bmax(3 * n), cen(3 * n);
+    Box global, global_c;
     global.reset();
+    global_c.reset();
 #pragma omp parallel
     {
-        Box local;
+        Box local, local_c;
         local.reset();
+        local_c.reset();
 #pragma omp for nowait
         for (int64_t i = 0; i < (int64_t)n; i++) {
             const Triangle &t = tris[i];
@@ -213,38 +322,73 @@ void build_bvh(const std::vector<Triangle> &tris, HostBvh &out, int max_leaf, fl
                 cen[3 * i + k] = (a + b + cc) * (1.0f / 3.0f);
             }
             local.grow(&bmin[3 * i], &bmax[3 * i]);
+            local_c.grow_pt(&cen[3 * i]);
         }
 #pragma omp critical
-        global.grow(local);
+        {
+            global.grow(local);
+            global_c.grow(local_c);
+        }
     }
-    std::vector<uint32_t> idx(n);
-    for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)i;
-    std::vector<vt_node> tmp(2 * n + 1);
-    BuildCtx c{bmin.data(), bmax.data(), cen.data(), idx.data(), tmp.data(), {1}, max_leaf, trav_cost};
+    lap("primitive boxes");
+    RawVector<uint32_t> idx(n), scratch(n >= kParallelNode ? n : 0);
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; i++) idx[i] = (uint32_t)i;
+    RawVector<vt_node> tmp(2 * n + 1);
+    BuildCtx c{bmin.data(), bmax.data(), cen.data(), idx.data(), scratch.data(), tmp.data(), {1}, max_leaf, trav_cost};
 #pragma omp parallel
 #pragma omp single
-    build_range(c, 0, 0, (uint32_t)n, global, 0);
+    build_range(c, 0, 0, (uint32_t)n, global, global_c, 0);
 
-    // depth-first relayout: node ids handed out by the task scheduler are not reproducible, this order is
+    lap("top-down SAH");
+    // depth-first relayout: node ids handed out by the task scheduler are not reproducible, this order is — root at 0, the two
+    // children of a node adjacent, then everything below the left child, then everything below the right child.  A child's id
+    // is always larger than its parent's (ids are handed out when the parent splits), so the descendant counts come from one
+    // backward sweep and every subtree knows its slice of the output: the copy itself runs as tasks.
     const uint32_t total = c.next_node.load();
     out.nodes.resize(total);
     out.prim_indices.resize(n);
+    std::vector<uint32_t> desc(total, 0);
+    for (uint32_t i = total; i-- > 0;)
+        if (tmp[i].prim_count == 0) desc[i] = 2 + desc[tmp[i].first] + desc[tmp[i].first + 1];
     out.nodes[0] = tmp[0];
-    uint32_t next = 1;
-    std::vector<std::pair<uint32_t, uint32_t>> stack;  // (old index, new index) of inner nodes to expand
-    if (tmp[0].prim_count == 0) stack.push_back({0u, 0u});
-    while (!stack.empty()) {
-        auto [oi, ni] = stack.back();
-        stack.pop_back();
-        const uint32_t oc = tmp[oi].first, nc = next;
-        next += 2;
-        out.nodes[ni].first = nc;
-        out.nodes[nc] = tmp[oc];
-        out.nodes[nc + 1] = tmp[oc + 1];
-        if (tmp[oc + 1].prim_count == 0) stack.push_back({oc + 1, nc + 1});
-        if (tmp[oc].prim_count == 0) stack.push_back({oc, nc});  // left subtree is laid out first
+    struct Relayout {
+        const vt_node *tmp;
+        const uint32_t *desc;
+        vt_node *out;
+        void place(uint32_t oi, uint32_t ni, uint32_t base) const {  // inner node oi sits at out[ni]; its subtree fills out[base ...)
+            const uint32_t oc = tmp[oi].first;
+            out[ni].first = base;
+            out[base] = tmp[oc];
+            out[base + 1] = tmp[oc + 1];
+            const uint32_t left_base = base + 2, right_base = base + 2 + desc[oc];
+            const bool big = desc[oi] > 8192;
+            if (tmp[oc].prim_count == 0) {
+                if (big) {
+#pragma omp task firstprivate(oc, base, left_base)
+                    place(oc, base, left_base);
+                } else {
+                    place(oc, base, left_base);
+                }
+            }
+            if (tmp[oc + 1].prim_count == 0) {
+                if (big) {
+#pragma omp task firstprivate(oc, base, right_base)
+                    place(oc + 1, base + 1, right_base);
+                } else {
+                    place(oc + 1, base + 1, right_base);
+                }
+            }
+        }
+    } relayout{tmp.data(), desc.data(), out.nodes.data()};
+    if (tmp[0].prim_count == 0) {
+#pragma omp parallel
+#pragma omp single
+        relayout.place(0, 0, 1);
     }
+#pragma omp parallel for
     for (size_t i = 0; i < n; i++) out.prim_indices[i] = idx[i];
+    lap("depth-first relayout");
 }
 
 // ------------------------------------------------------------------------------------ refit
@@ -254,7 +398,7 @@ void build_bvh(const std::vector<Triangle> &tris, HostBvh &out, int max_leaf, fl
 // refit test updates leaves (libs/bvh/test/refit_bvh.cpp:79-89), in parallel; inner boxes are the union of their two
 // children, children first.  The reference library walks up from every leaf with per-node arrival flags
 // (bottom_up_algorithm.hpp:52-80); min/max are exact, so this level-free reverse pre-order pass gives the same boxes.
-bool refit_bvh(const std::vector<Triangle> &tris, HostBvh &bvh, std::string &err) {
+bool refit_bvh(const TriangleVec &tris, HostBvh &bvh, std::string &err) {
     const size_t node_count = bvh.nodes.size();
     if (node_count == 0) return true;
     if (bvh.prim_indices.size() != tris.size()) {
@@ -555,57 +699,100 @@ bool compact_pairs(const std::vector<VtPair> &pairs, std::vector<VtCPair> &out, 
 // --------------------------------------------------------------------------------------- quads
 namespace {
 
+// Two passes over the collapsed tree, both as OpenMP tasks: measure() gives every quad-to-be the number of quads and triangles
+// below it (and the stack its subtree needs), so emit() knows the slice of the quad array and of the leaf order each subtree owns
+// and the subtrees are written independently.  The order is the sequential one: a quad, its leaf children's triangles, then its
+// inner children depth-first.
 struct QuadBuilder {
     const HostBvh &bvh;
     uint64_t n_tris;
     QuadBvh &out;
     std::string &err;
     const CollapsePlan &plan;
-    bool ok = true;
+    std::vector<uint32_t> quads_below, tris_below;  // indexed by the binary node that becomes the quad (itself included)
+    std::vector<uint8_t> need_below;
+    std::atomic<bool> ok{true};
+    std::mutex err_mutex;
 
-    static float half_area(const vt_node &n) {
-        const float dx = n.bounds[1] - n.bounds[0], dy = n.bounds[3] - n.bounds[2], dz = n.bounds[5] - n.bounds[4];
-        return dx * dy + dy * dz + dz * dx;
-    }
+    QuadBuilder(const HostBvh &b, uint64_t n, QuadBvh &o, std::string &e, const CollapsePlan &p) : bvh(b), n_tris(n), out(o), err(e), plan(p) {}
+
     bool fail(const char *why) {
-        if (ok) err = why;
+        std::lock_guard<std::mutex> lock(err_mutex);
+        if (ok.load()) err = why;
         ok = false;
         return false;
     }
 
-    // Emit the quad that replaces binary inner node `ni`; returns its index, *need = worst-case stack entries below it.
-    uint32_t emit(uint32_t ni, uint32_t depth, uint32_t *need) {
+    void measure(uint32_t ni, uint32_t depth) {
         const size_t node_count = bvh.nodes.size();
-        uint32_t kids[4];
+        quads_below[ni] = 1, tris_below[ni] = 0, need_below[ni] = 0;
+        if (!ok.load()) return;
         if (bvh.nodes[ni].first == 0 || (size_t)bvh.nodes[ni].first + 1 >= node_count || depth > 64) {
             fail("quad layout: malformed hierarchy");
-            *need = 0;
-            return 0;
+            return;
         }
+        uint32_t kids[4];
         const int nk = plan.children(bvh, ni, kids);
-        const uint32_t qi = (uint32_t)out.quads.size();
-        if (out.quads.size() > bvh.nodes.size()) {  // not a tree: a node is reachable twice
-            fail("BVH is not a tree (a node pair is referenced twice)");
-            *need = 0;
-            return 0;
+        const bool spawn = depth < 10;
+        for (int i = 0; i < nk; i++) {
+            if (bvh.nodes[kids[i]].prim_count != 0) continue;
+            if ((size_t)kids[i] >= node_count || quads_below[kids[i]] != 0) {  // not a tree: a node is reachable twice
+                fail("BVH is not a tree (a node pair is referenced twice)");
+                return;
+            }
+            const uint32_t k = kids[i];
+            if (spawn) {
+#pragma omp task firstprivate(k, depth)
+                measure(k, depth + 1);
+            } else {
+                measure(k, depth + 1);
+            }
         }
-        out.quads.emplace_back();
+        if (spawn) {
+#pragma omp taskwait
+        }
+        uint32_t q = 1, t = 0, below = 0;
+        for (int i = 0; i < nk; i++) {
+            const vt_node &c = bvh.nodes[kids[i]];
+            if (c.prim_count != 0) {
+                t += c.prim_count;
+            } else {
+                q += quads_below[kids[i]], t += tris_below[kids[i]];
+                below = std::max<uint32_t>(below, need_below[kids[i]]);
+            }
+        }
+        // while a child is being walked, up to nk - 1 siblings are pending — and with VT_EMPTY_SENTINEL the kernel does not test
+        // "slot in use": an empty slot's inverted box can pass the rounded slab test (vt_traverse.cu, slab_quad) and its sentinel
+        // leaf is then pushed like any other child, so every level is budgeted with all 3 non-nearest slots
+        const uint32_t need = (uint32_t)(VT_EMPTY_SENTINEL ? 3 : nk - 1) + below;
+        quads_below[ni] = q, tris_below[ni] = t, need_below[ni] = (uint8_t)std::min<uint32_t>(need, 255);
+    }
+
+    // Write the quad that replaces binary inner node `ni` at out.quads[qi]; its subtree's triangles start at leaf slot `tri_base`.
+    void emit(uint32_t ni, uint32_t qi, uint32_t tri_base, uint32_t depth) {
+        if (!ok.load()) return;
+        uint32_t kids[4];
+        const int nk = plan.children(bvh, ni, kids);
         VtQuad q;
         std::memset(&q, 0, sizeof(q));
         // shared grid over the union of the children
-        for (int a = 0; a < 3 && ok; a++) {
+        for (int a = 0; a < 3; a++) {
             double lo = 1e300, hi = -1e300;
             for (int i = 0; i < nk; i++) {
                 const vt_node &c = bvh.nodes[kids[i]];
-                if (!(std::isfinite(c.bounds[2 * a]) && std::isfinite(c.bounds[2 * a + 1])) || c.bounds[2 * a + 1] < c.bounds[2 * a])
+                if (!(std::isfinite(c.bounds[2 * a]) && std::isfinite(c.bounds[2 * a + 1])) || c.bounds[2 * a + 1] < c.bounds[2 * a]) {
                     fail("quad layout: non-finite or inverted bounds");
+                    return;
+                }
                 lo = std::min(lo, (double)c.bounds[2 * a]);
                 hi = std::max(hi, (double)c.bounds[2 * a + 1]);
             }
             int E = 0;
             int64_t k = 0;
-            if (ok && !choose_grid(lo, hi, E, k)) fail("quad layout: coordinates out of float grid range");
-            if (!ok) break;
+            if (!choose_grid(lo, hi, E, k)) {
+                fail("quad layout: coordinates out of float grid range");
+                return;
+            }
             const double s = std::ldexp(1.0, E);
             q.origin_adj[a] = (float)((double)(k - VT_QUAD_OFFSET) * s);
             q.scale[a] = (float)s;
@@ -622,40 +809,44 @@ struct QuadBuilder {
         }
         // leaves first (their triangles sit next to each other), then the inner children, depth-first
         for (int i = 0; i < 4; i++) q.ref[i] = 0xFFFFFFFFu;
-        for (int i = 0; i < nk && ok; i++) {
+        uint32_t slot = tri_base;
+        for (int i = 0; i < nk; i++) {
             const vt_node &c = bvh.nodes[kids[i]];
             if (c.prim_count == 0) continue;
             if (c.prim_count > 15) {
                 fail("quad layout: a leaf holds more than 15 triangles");
-                break;
+                return;
             }
             if ((uint64_t)c.first + c.prim_count > n_tris) {
                 fail("BVH leaf addresses primitives past the end of prim_indices");
-                break;
+                return;
             }
-            q.ref[i] = (c.prim_count << 28) | (uint32_t)out.leaf_order.size();
+            q.ref[i] = (c.prim_count << 28) | slot;
             for (uint32_t t = 0; t < c.prim_count; t++) {
                 const uint64_t p = bvh.prim_indices[c.first + t];
                 if (p >= n_tris) {
                     fail("BVH primitive index out of range");
-                    break;
+                    return;
                 }
-                out.leaf_order.push_back((uint32_t)p);
+                out.leaf_order[slot++] = (uint32_t)p;
             }
         }
-        uint32_t below = 0;
-        for (int i = 0; i < nk && ok; i++) {
+        uint32_t next_q = qi + 1;
+        const bool spawn = quads_below[ni] > 4096;
+        for (int i = 0; i < nk; i++) {
             if (bvh.nodes[kids[i]].prim_count != 0) continue;
-            uint32_t n = 0;
-            q.ref[i] = emit(kids[i], depth + 1, &n);
-            below = std::max(below, n);
+            const uint32_t k = kids[i], cq = next_q, ct = slot;
+            q.ref[i] = cq;
+            if (spawn) {
+#pragma omp task firstprivate(k, cq, ct, depth)
+                emit(k, cq, ct, depth + 1);
+            } else {
+                emit(k, cq, ct, depth + 1);
+            }
+            next_q += quads_below[k];
+            slot += tris_below[k];
         }
-        // while a child is being walked, up to nk - 1 siblings are pending — and with VT_EMPTY_SENTINEL the kernel does not test
-        // "slot in use": an empty slot's inverted box can pass the rounded slab test (vt_traverse.cu, slab_quad) and its sentinel
-        // leaf is then pushed like any other child, so every level is budgeted with all 3 non-nearest slots
-        *need = (uint32_t)(VT_EMPTY_SENTINEL ? 3 : nk - 1) + below;
         out.quads[qi] = q;
-        return qi;
     }
 };
 
@@ -682,18 +873,28 @@ bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string 
         out.root_leaf_count = root.prim_count;
         return out.leaf_order.size() == n_tris;
     }
-    out.quads.reserve(bvh.nodes.size() / 3 + 1);
     CollapsePlan plan;
     if (!plan_collapse(bvh, 4, plan, err)) return false;
-    QuadBuilder b{bvh, n_tris, out, err, plan};
-    uint32_t need = 0;
-    b.emit(0, 0, &need);
+    QuadBuilder b(bvh, n_tris, out, err, plan);
+    b.quads_below.assign(bvh.nodes.size(), 0);
+    b.tris_below.assign(bvh.nodes.size(), 0);
+    b.need_below.assign(bvh.nodes.size(), 0);
+#pragma omp parallel
+#pragma omp single
+    b.measure(0, 0);
     if (!b.ok) return false;
-    out.max_stack = need;
-    if (out.leaf_order.size() != n_tris) {
+    if (b.tris_below[0] != n_tris) {
         err = "BVH leaves do not cover every primitive exactly once";
         return false;
     }
+    out.quads.resize(b.quads_below[0]);
+    out.leaf_order.resize(n_tris);
+#pragma omp parallel
+#pragma omp single
+    b.emit(0, 0, 0, 0);
+    if (!b.ok) return false;
+    const uint32_t need = b.need_below[0];
+    out.max_stack = need;
     std::vector<uint8_t> seen(n_tris, 0);
     for (uint32_t p : out.leaf_order) {
         if (seen[p]) {

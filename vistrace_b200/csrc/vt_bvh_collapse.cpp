@@ -9,6 +9,7 @@
 // Leaves are kept as the builder made them (no triangles are merged or moved), so the set of triangles a ray can reach through a
 // given box is unchanged; only how many box tests and dependent fetches it takes to get there.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -38,60 +39,70 @@ bool plan_collapse(const HostBvh &bvh, int width, CollapsePlan &plan, std::strin
     const float c_node = 1.0f;
     const char *cp = std::getenv("VT_COLLAPSE_CPRIM");
     const float c_prim = (cp && *cp) ? (float)std::atof(cp) : 0.6f;
-    // pre-order, parents before children (children need not have larger indices in a caller's tree)
-    std::vector<uint32_t> order;
-    order.reserve(n);
-    std::vector<uint32_t> stack{0u};
-    while (!stack.empty()) {
-        const uint32_t i = stack.back();
-        stack.pop_back();
-        order.push_back(i);
-        if (order.size() > n) {
-            err = "collapse: hierarchy is not a tree";
-            return false;
-        }
-        const vt_node &nd = bvh.nodes[i];
-        if (nd.prim_count == 0) {
-            if (nd.first == 0 || (size_t)nd.first + 1 >= n) {
-                err = "collapse: malformed hierarchy";
-                return false;
-            }
-            stack.push_back(nd.first);
-            stack.push_back(nd.first + 1);
-        }
-    }
     const int W = width;
-    std::vector<float> cost(n * (size_t)W);  // cost[node * W + (i - 1)], i = 1 .. W - 1 used; slot W - 1 holds distribute(n, W)
+    std::vector<float> cost(n * (size_t)W);  // cost[node * W + (i - 1)], i = 1 .. W - 1 used
     plan.split.assign(n * (size_t)W, 0);
-    for (size_t q = order.size(); q-- > 0;) {  // children before parents
-        const uint32_t ni = order[q];
-        const vt_node &nd = bvh.nodes[ni];
-        float *c = &cost[(size_t)ni * W];
-        uint8_t *sp = &plan.split[(size_t)ni * W];
-        if (nd.prim_count != 0) {
-            const float leaf = half_area(nd) * (float)nd.prim_count * c_prim;
-            for (int i = 0; i < W; i++) c[i] = leaf;
-            continue;
-        }
-        const float *cl = &cost[(size_t)nd.first * W], *cr = &cost[((size_t)nd.first + 1) * W];
-        // distribute(n, j) for j = 2 .. W; a child may take 1 .. W - 1 roots
-        float dist[9];
-        uint8_t dk[9];
-        for (int j = 2; j <= W; j++) {
-            float best = std::numeric_limits<float>::max();
-            int bk = 1;
-            for (int k = 1; k < j; k++) {
-                const float v = cl[k - 1] + cr[j - k - 1];
-                if (v < best) best = v, bk = k;
+    std::atomic<int> bad{0};
+    // post-order over the binary tree as OpenMP tasks (children before parents); the depth bound also stops a malformed "tree"
+    struct Dp {
+        const HostBvh &bvh;
+        int W;
+        float c_node, c_prim;
+        float *cost;
+        uint8_t *split;
+        std::atomic<int> &bad;
+        void run(uint32_t ni, int depth) const {
+            const size_t n = bvh.nodes.size();
+            const vt_node &nd = bvh.nodes[ni];
+            float *c = cost + (size_t)ni * W;
+            uint8_t *sp = split + (size_t)ni * W;
+            if (nd.prim_count != 0) {
+                const float leaf = half_area(nd) * (float)nd.prim_count * c_prim;
+                for (int i = 0; i < W; i++) c[i] = leaf;
+                return;
             }
-            dist[j] = best, dk[j] = (uint8_t)bk;
+            if (nd.first == 0 || (size_t)nd.first + 1 >= n || depth > 128) {
+                bad = 1;
+                for (int i = 0; i < W; i++) c[i] = 0.f;
+                return;
+            }
+            if (depth < 12) {
+#pragma omp task
+                run(nd.first, depth + 1);
+#pragma omp task
+                run(nd.first + 1, depth + 1);
+#pragma omp taskwait
+            } else {
+                run(nd.first, depth + 1);
+                run(nd.first + 1, depth + 1);
+            }
+            const float *cl = cost + (size_t)nd.first * W, *cr = cost + ((size_t)nd.first + 1) * W;
+            // distribute(n, j) for j = 2 .. W; a child may take 1 .. W - 1 roots
+            float dist[9];
+            uint8_t dk[9];
+            for (int j = 2; j <= W; j++) {
+                float best = std::numeric_limits<float>::max();
+                int bk = 1;
+                for (int k = 1; k < j; k++) {
+                    const float v = cl[k - 1] + cr[j - k - 1];
+                    if (v < best) best = v, bk = k;
+                }
+                dist[j] = best, dk[j] = (uint8_t)bk;
+            }
+            c[0] = half_area(nd) * c_node + dist[W];
+            sp[0] = dk[W];  // the wide node's own children: forest of W roots split dk[W] : W - dk[W]
+            for (int i = 2; i < W; i++) {
+                if (dist[i] < c[i - 2]) c[i - 1] = dist[i], sp[i - 1] = dk[i];
+                else c[i - 1] = c[i - 2], sp[i - 1] = 0;  // one root fewer is cheaper
+            }
         }
-        c[0] = half_area(nd) * c_node + dist[W];
-        sp[0] = dk[W];  // the wide node's own children: forest of W roots split dk[W] : W - dk[W]
-        for (int i = 2; i < W; i++) {
-            if (dist[i] < c[i - 2]) c[i - 1] = dist[i], sp[i - 1] = dk[i];
-            else c[i - 1] = c[i - 2], sp[i - 1] = 0;  // one root fewer is cheaper
-        }
+    } dp{bvh, W, c_node, c_prim, cost.data(), plan.split.data(), bad};
+#pragma omp parallel
+#pragma omp single
+    dp.run(0, 0);
+    if (bad.load()) {
+        err = "collapse: malformed hierarchy";
+        return false;
     }
     return true;
 }

@@ -68,7 +68,7 @@ constexpr size_t kSearchRadius = 14;  // LocallyOrderedClusteringBuilder::search
 
 }  // namespace
 
-void build_bvh_ploc(const std::vector<Triangle> &tris, HostBvh &out) {
+void build_bvh_ploc(const TriangleVec &tris, HostBvh &out) {
     const size_t n = tris.size();
     out.nodes.clear();
     out.prim_indices.clear();
@@ -188,8 +188,8 @@ void build_bvh_ploc(const std::vector<Triangle> &tris, HostBvh &out) {
         begin = unmerged_begin;
         end = children_begin;
     }
-    out.nodes = std::move(nodes);
-    out.prim_indices = std::move(order);
+    out.nodes.assign(nodes.begin(), nodes.end());
+    out.prim_indices.assign(order.begin(), order.end());
 }
 
 // bvh::LeafCollapser::collapse.  When the root itself becomes a leaf the reference turns node 0 into a leaf over all
@@ -276,8 +276,8 @@ bool collapse_leaves(HostBvh &bvh) {
         }
         nodes[node_index] = nd;
     }
-    bvh.nodes = std::move(nodes);
-    bvh.prim_indices = std::move(prims);
+    bvh.nodes.assign(nodes.begin(), nodes.end());
+    bvh.prim_indices.assign(prims.begin(), prims.end());
     return true;
 }
 

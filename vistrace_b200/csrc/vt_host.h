@@ -6,7 +6,11 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <memory>
 #include <mutex>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/vistrace_b200.h"
@@ -14,17 +18,42 @@
 
 namespace vt {
 
-// TriangleBackfaceCull<float> (source/objects/Primitives.h:43-73) without the skinning scratch data.
+// Allocator whose value-construction is DEFAULT-initialisation: vector<T>(n) / resize(n) of a trivially constructible T touches
+// no memory.  The containers of a 5 M-triangle scene are ~3 GB; zero-filling them on one thread before the parallel loops
+// overwrite every byte was a quarter of the rebuild latency, and it put every page on the NUMA node of that one thread.
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        using other = DefaultInitAllocator<U>;
+    };
+    DefaultInitAllocator() = default;
+    template <class U>
+    DefaultInitAllocator(const DefaultInitAllocator<U> &) {}
+    template <class U>
+    void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+        ::new (static_cast<void *>(p)) U;
+    }
+    template <class U, class... Args>
+    void construct(U *p, Args &&...args) {
+        ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...);
+    }
+};
+template <class T>
+using RawVector = std::vector<T, DefaultInitAllocator<T>>;
+
+// TriangleBackfaceCull<float> (source/objects/Primitives.h:43-73) without the skinning scratch data.  Trivially default
+// constructible on purpose (see DefaultInitAllocator): the six-argument constructor sets every field.
 struct Triangle {
     float p0[3], e1[3], e2[3], n[3], nNorm[3];
-    bool oneSided = false;
-    uint32_t material = 0;
-    uint16_t entIdx = 0;
+    bool oneSided;
+    uint32_t material;
+    uint16_t entIdx;
     float normals[3][3];
     float tangents[3][3];
     float uvs[3][2];
     float alphas[3];
-    float lod = 0.f;
+    float lod;
 
     Triangle() = default;
     // Triangle(p0, p1, p2, material, uvs, oneSided) — Primitives.h:75-89
@@ -33,12 +62,13 @@ struct Triangle {
     void ComputeNormalAndLoD();  // Primitives.h:91-102
 };
 
+using TriangleVec = RawVector<Triangle>;
 using Entity = vt_entity;      // source/objects/AccelStruct.h:33-40 (id, colour)
 using Material = vt_material;  // source/objects/Material.h:74-125 (subset on the path)
 
 struct HostBvh {  // bvh::Bvh<float>: nodes, primitive_indices, node_count (bvh.hpp:96-99)
-    std::vector<vt_node> nodes;
-    std::vector<uint64_t> prim_indices;
+    RawVector<vt_node> nodes;
+    RawVector<uint64_t> prim_indices;
 };
 
 struct FlatBvh {
@@ -48,20 +78,20 @@ struct FlatBvh {
     uint32_t max_depth = 0;
 };
 
-void build_bvh(const std::vector<Triangle> &tris, HostBvh &out, int max_leaf, float trav_cost);
+void build_bvh(const TriangleVec &tris, HostBvh &out, int max_leaf, float trav_cost);
 // The reference's own hierarchy rebuilt from its algorithm (vt_bvh_ploc.cpp): bvh::LocallyOrderedClusteringBuilder<BVH, uint32_t>
 // (search radius 14, 30-bit Morton codes) and bvh::LeafCollapser, the sequence of source/objects/AccelStruct.cpp:762-770.
-void build_bvh_ploc(const std::vector<Triangle> &tris, HostBvh &out);
+void build_bvh_ploc(const TriangleVec &tris, HostBvh &out);
 bool collapse_leaves(HostBvh &bvh);
 // bvh::HierarchyRefitter over moved geometry of unchanged topology (hierarchy_refitter.hpp:20-31): node boxes only.
-bool refit_bvh(const std::vector<Triangle> &tris, HostBvh &bvh, std::string &err);
+bool refit_bvh(const TriangleVec &tris, HostBvh &bvh, std::string &err);
 bool flatten_bvh(const HostBvh &bvh, uint64_t n_tris, uint32_t bfs_pairs, FlatBvh &out, std::string &err);
 // bvh::Bvh<float> form -> 4-wide quantised nodes (vt_device.h: VtQuad) in depth-first order + the leaf-order
 // permutation of the triangles.  False (with a reason) when the tree cannot be held: a leaf of more than 15
 // triangles, non-finite bounds, or a worst-case traversal stack deeper than VT_STACK_SIZE.
 struct QuadBvh {
-    std::vector<VtQuad> quads;
-    std::vector<uint32_t> leaf_order;
+    RawVector<VtQuad> quads;
+    RawVector<uint32_t> leaf_order;
     uint32_t root_leaf_count = 0;
     uint32_t max_stack = 0;  // worst-case number of pending references
 };
@@ -130,16 +160,24 @@ class AccelStruct {
     mutable HostBvh mAccel;
     mutable bool mBvhStale = false;
     mutable std::mutex mBvhMutex;  // guards the lazy host-side refit in Bvh()  // a device-side refit moved the boxes; the host copy is refitted on demand
-    std::vector<Triangle> mTriangles;
+    TriangleVec mTriangles;
     std::vector<Entity> mEntities;
     std::vector<Material> mMaterials;
     DeviceScene *mpDevice = nullptr;
     uint64_t mInvalidRays = 0;
     uint64_t mLaunches = 0;
+    double mRefitRebuildRatio = 0.0;  // > 0: vt_accel_refit rebuilds from scratch once RefitQuality() exceeds it
+    uint64_t mRebuilds = 0;
 
+    // per-triangle TraceResult inputs (VtTriAttr, original order): independent of the hierarchy, so Ingest writes them in the same
+    // pass as the Triangle constructor and a helper thread uploads them (0.9 GB at 5 M triangles) WHILE the hierarchy is being built
+    RawVector<VtTriAttr> mAttrStage;
+    std::thread mAttrUpload;
+    std::string mAttrUploadError;
+    void JoinAttrUpload();
     bool mReplica = false;  // device arrays copied from another handle (vt_group.cu): no host containers, no refit / get_bvh
 
-    void Ingest(const vt_scene &scene);
+    void Ingest(const vt_scene &scene, bool stage_attrs = true);
     void Upload(const vt_scene &scene);
     friend class Group;
 
@@ -233,11 +271,15 @@ public:
                           float tMax = 3.402823466e+38f, float coneWidth = -1.f, float coneAngle = -1.f);
 
     const Material &GetMaterial(size_t i) const { return mMaterials[i]; }  // AccelStruct.cpp:840-843
-    const std::vector<Triangle> &Triangles() const { return mTriangles; }
+    const TriangleVec &Triangles() const { return mTriangles; }
     const HostBvh &Bvh() const;  // boxes refreshed lazily after a device-side refit
     bool Built() const { return mAccelBuilt; }
     int Layout() const { return mLayout; }
     void SetLayout(int layout) { mWantLayout = layout; }
+    // node-area sum of the resident quad hierarchy relative to the sum right after the build (1 = as built); rebuild trigger
+    double RefitQuality() const;
+    void SetRefitRebuildRatio(double r) { mRefitRebuildRatio = r; }
+    uint64_t Rebuilds() const { return mRebuilds; }
     uint64_t InvalidRays() const { return mInvalidRays; }
     uint64_t Launches() const { return mLaunches; }
     uint64_t DeviceBytes() const;

@@ -90,5 +90,7 @@ cudaError_t vt_launch_path_shade(const vt_attr *attrs, const vt_hit *shadow_hits
 cudaError_t vt_launch_refit_prepare(const VtSceneView &S, uint32_t *parent, uint32_t *n_inner, uint32_t *slot_of, cudaStream_t stream);
 cudaError_t vt_launch_refit_tris(const VtSceneView &S, const vt_tri_in *in, uint32_t first, uint32_t count, const uint32_t *slot_of,
                                  cudaStream_t stream);  // in[j] = new vertices of original triangle first + j
+// *sum = sum of the half surface areas of the n_quads boxes in qbox (as left by vt_launch_refit_quads): the rebuild trigger's measure.
+cudaError_t vt_launch_refit_cost(const void *qbox, uint32_t n_quads, double *sum, cudaStream_t stream);
 cudaError_t vt_launch_refit_quads(const VtSceneView &S, const uint32_t *parent, const uint32_t *n_inner, uint32_t *arrive, void *qbox,
                                   unsigned int *error, cudaStream_t stream);

@@ -47,53 +47,75 @@ __global__ void k_refit_prepare(const VtQuad *__restrict__ quads, uint32_t n_qua
     if (i < n_tris) slot_of[tris[i].orig] = i;
 }
 
-// in[j] holds the new vertices of ORIGINAL triangle first + j, j < count
-__global__ void k_refit_tris(const vt_tri_in *__restrict__ in, uint32_t first, uint32_t count, const uint32_t *__restrict__ slot_of,
-                             const VtDevMaterial *__restrict__ mats, VtTriRec *__restrict__ recs, float *__restrict__ tri_uv,
-                             VtTriAttr *__restrict__ attrs) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
-    const uint32_t i = first + j;
-    const vt_tri_in t = in[j];
-    float p0[3], e1[3], e2[3], n[3], nn[3];
-    for (int k = 0; k < 3; k++) {
-        p0[k] = t.p[0][k];
-        e1[k] = t.p[0][k] - t.p[1][k];  // e1 = p0 - p1, e2 = p2 - p0 (Primitives.h:82)
-        e2[k] = t.p[2][k] - t.p[0][k];
+// in[j] holds the new vertices of ORIGINAL triangle first + j, j < count.  A block of 128 threads handles 128 consecutive
+// triangles: their 152-byte input records and their 176-byte attribute records are CONTIGUOUS in global memory, so both go through
+// shared memory with 16-byte coalesced accesses (a thread reading / writing its own record walks a 152- / 176-byte stride: 2.6 TB/s,
+// profiles/r1). Only the 64-byte geometry record and the 24 bytes of UVs go to the triangle's leaf slot, which is scattered by nature.
+constexpr int kRefitBlock = 128;
+__global__ void __launch_bounds__(kRefitBlock)
+k_refit_tris(const vt_tri_in *__restrict__ in, uint32_t first, uint32_t count, const uint32_t *__restrict__ slot_of,
+             const VtDevMaterial *__restrict__ mats, VtTriRec *__restrict__ recs, float *__restrict__ tri_uv,
+             VtTriAttr *__restrict__ attrs) {
+    static_assert(sizeof(vt_tri_in) % 8 == 0 && sizeof(VtTriAttr) % 16 == 0, "staging moves 8- / 16-byte words");
+    __shared__ __align__(16) unsigned char s_in[kRefitBlock * sizeof(vt_tri_in)];
+    __shared__ __align__(16) unsigned char s_attr[kRefitBlock * sizeof(VtTriAttr)];
+    const uint32_t j0 = blockIdx.x * kRefitBlock;
+    const uint32_t m = min((uint32_t)kRefitBlock, count - j0);
+    {   // vt_tri_in is 152 bytes (8-byte multiples; the array base is at least 8-byte aligned): coalesced 8-byte loads
+        const uint2 *src = reinterpret_cast<const uint2 *>(in + j0);
+        uint2 *dst = reinterpret_cast<uint2 *>(s_in);
+        for (uint32_t w = threadIdx.x; w < m * (uint32_t)(sizeof(vt_tri_in) / 8); w += kRefitBlock) dst[w] = __ldg(src + w);
     }
-    n[0] = e1[1] * e2[2] - e1[2] * e2[1];  // ComputeNormalAndLoD, Primitives.h:91-102
-    n[1] = e1[2] * e2[0] - e1[0] * e2[2];
-    n[2] = e1[0] * e2[1] - e1[1] * e2[0];
-    const float uv10x = t.uvs[1][0] - t.uvs[0][0], uv10y = t.uvs[1][1] - t.uvs[0][1];
-    const float uv20x = t.uvs[2][0] - t.uvs[0][0], uv20y = t.uvs[2][1] - t.uvs[0][1];
-    const float area = fabsf(uv10x * uv20y - uv20x * uv10y);
-    float d = n[0] * n[0];
-    d += n[1] * n[1];
-    d += n[2] * n[2];
-    const float len = sqrtf(d);
-    const float lod = 0.5f * log2f(area / len);
-    for (int k = 0; k < 3; k++) nn[k] = n[k] / len;
+    __syncthreads();
+    const uint32_t j = j0 + threadIdx.x;
+    if (threadIdx.x < m) {
+        const uint32_t i = first + j;
+        const vt_tri_in &t = *reinterpret_cast<const vt_tri_in *>(s_in + threadIdx.x * sizeof(vt_tri_in));
+        float p0[3], e1[3], e2[3], n[3], nn[3];
+        for (int k = 0; k < 3; k++) {
+            p0[k] = t.p[0][k];
+            e1[k] = t.p[0][k] - t.p[1][k];  // e1 = p0 - p1, e2 = p2 - p0 (Primitives.h:82)
+            e2[k] = t.p[2][k] - t.p[0][k];
+        }
+        n[0] = e1[1] * e2[2] - e1[2] * e2[1];  // ComputeNormalAndLoD, Primitives.h:91-102
+        n[1] = e1[2] * e2[0] - e1[0] * e2[2];
+        n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+        const float uv10x = t.uvs[1][0] - t.uvs[0][0], uv10y = t.uvs[1][1] - t.uvs[0][1];
+        const float uv20x = t.uvs[2][0] - t.uvs[0][0], uv20y = t.uvs[2][1] - t.uvs[0][1];
+        const float area = fabsf(uv10x * uv20y - uv20x * uv10y);
+        float d = n[0] * n[0];
+        d += n[1] * n[1];
+        d += n[2] * n[2];
+        const float len = sqrtf(d);
+        const float lod = 0.5f * log2f(area / len);
+        for (int k = 0; k < 3; k++) nn[k] = n[k] / len;
 
-    const uint32_t s = slot_of[i];
-    VtTriRec r;
-    for (int k = 0; k < 3; k++) r.p0[k] = p0[k], r.e1[k] = e1[k], r.e2[k] = e2[k], r.n[k] = n[k];
-    const uint32_t mflags = mats[t.material].flags;
-    uint32_t fl = 0;
-    if (t.one_sided && (mflags & VT_MATFLAG_NOCULL) == 0) fl |= VT_TRI_FLAG_CULL;  // Primitives.h:174
-    if (mflags & VT_MATFLAG_ALPHATEST) fl |= VT_TRI_FLAG_ALPHATEST;               // Primitives.h:195
-    r.matflags = (t.material << 2) | fl;
-    r.orig = i;
-    r.pad[0] = r.pad[1] = 0;
-    recs[s] = r;
-    for (int k = 0; k < 6; k++) tri_uv[(size_t)s * 6 + k] = (&t.uvs[0][0])[k];
-    VtTriAttr a;
-    for (int k = 0; k < 3; k++) a.p0[k] = p0[k], a.e1[k] = e1[k], a.e2[k] = e2[k], a.nNorm[k] = nn[k], a.alphas[k] = t.alphas[k];
-    for (int k = 0; k < 9; k++) (&a.normals[0][0])[k] = (&t.normals[0][0])[k], (&a.tangents[0][0])[k] = (&t.tangents[0][0])[k];
-    for (int k = 0; k < 6; k++) (&a.uvs[0][0])[k] = (&t.uvs[0][0])[k];
-    a.lod = lod;
-    a.material = t.material;
-    a.ent_idx = t.ent_idx;
-    attrs[i] = a;
+        const uint32_t s = slot_of[i];
+        VtTriRec r;
+        for (int k = 0; k < 3; k++) r.p0[k] = p0[k], r.e1[k] = e1[k], r.e2[k] = e2[k], r.n[k] = n[k];
+        const uint32_t mflags = mats[t.material].flags;
+        uint32_t fl = 0;
+        if (t.one_sided && (mflags & VT_MATFLAG_NOCULL) == 0) fl |= VT_TRI_FLAG_CULL;  // Primitives.h:174
+        if (mflags & VT_MATFLAG_ALPHATEST) fl |= VT_TRI_FLAG_ALPHATEST;               // Primitives.h:195
+        r.matflags = (t.material << 2) | fl;
+        r.orig = i;
+        r.pad[0] = r.pad[1] = 0;
+        recs[s] = r;
+        for (int k = 0; k < 6; k++) tri_uv[(size_t)s * 6 + k] = (&t.uvs[0][0])[k];
+        VtTriAttr &a = *reinterpret_cast<VtTriAttr *>(s_attr + threadIdx.x * sizeof(VtTriAttr));
+        for (int k = 0; k < 3; k++) a.p0[k] = p0[k], a.e1[k] = e1[k], a.e2[k] = e2[k], a.nNorm[k] = nn[k], a.alphas[k] = t.alphas[k];
+        for (int k = 0; k < 9; k++) (&a.normals[0][0])[k] = (&t.normals[0][0])[k], (&a.tangents[0][0])[k] = (&t.tangents[0][0])[k];
+        for (int k = 0; k < 6; k++) (&a.uvs[0][0])[k] = (&t.uvs[0][0])[k];
+        a.lod = lod;
+        a.material = t.material;
+        a.ent_idx = t.ent_idx;
+    }
+    __syncthreads();
+    {   // VtTriAttr is 176 bytes, 16-byte aligned: coalesced 16-byte stores of the block's contiguous output range
+        const uint4 *src = reinterpret_cast<const uint4 *>(s_attr);
+        uint4 *dst = reinterpret_cast<uint4 *>(attrs + first + j0);
+        for (uint32_t w = threadIdx.x; w < m * (uint32_t)(sizeof(VtTriAttr) / 16); w += kRefitBlock) dst[w] = src[w];
+    }
 }
 
 // choose_grid of vt_bvh_build.cpp: the smallest power-of-two cell 2^E on which [lo, hi] spans <= 255 cells from
@@ -191,7 +213,28 @@ __global__ void k_refit_quads(VtQuad *quads, uint32_t n_quads, const VtTriRec *_
     }
 }
 
+// Sum of the half surface areas of all quad boxes: the SAH's inner-node term of the resident hierarchy (the expected number of
+// node visits of a random ray is proportional to it, libs/bvh/include/bvh/sah_based_algorithm.hpp:16-41).  Compared with the value
+// right after the build it tells how much a sequence of refits has loosened the tree — the rebuild trigger of vt_accel_refit.
+__global__ void k_refit_cost(const Box6 *__restrict__ qbox, uint32_t n_quads, double *__restrict__ sum) {
+    double local = 0.0;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += gridDim.x * blockDim.x) {
+        const Box6 b = qbox[q];
+        const double dx = (double)b.hi[0] - b.lo[0], dy = (double)b.hi[1] - b.lo[1], dz = (double)b.hi[2] - b.lo[2];
+        local += dx * dy + dy * dz + dz * dx;
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(sum, local);
+}
+
 }  // namespace
+
+cudaError_t vt_launch_refit_cost(const void *qbox, uint32_t n_quads, double *sum, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(sum, 0, sizeof(double), stream);
+    if (e != cudaSuccess || n_quads == 0) return e;
+    k_refit_cost<<<296, 256, 0, stream>>>(static_cast<const Box6 *>(qbox), n_quads, sum);
+    return cudaGetLastError();
+}
 
 cudaError_t vt_launch_refit_prepare(const VtSceneView &S, uint32_t *parent, uint32_t *n_inner, uint32_t *slot_of, cudaStream_t stream) {
     const uint32_t n = S.n_pairs > S.n_tris ? S.n_pairs : S.n_tris;
@@ -204,7 +247,8 @@ cudaError_t vt_launch_refit_tris(const VtSceneView &S, const vt_tri_in *in, uint
                                  cudaStream_t stream) {
     if (count == 0) return cudaSuccess;
     if ((uint64_t)first + count > S.n_tris) return cudaErrorInvalidValue;
-    k_refit_tris<<<(count + 127) / 128, 128, 0, stream>>>(in, first, count, slot_of, S.mats, const_cast<VtTriRec *>(S.tris),
+    if (((uintptr_t)in & 7) != 0) return cudaErrorInvalidValue;  // cudaMalloc'd staging: always true
+    k_refit_tris<<<(count + kRefitBlock - 1) / kRefitBlock, kRefitBlock, 0, stream>>>(in, first, count, slot_of, S.mats, const_cast<VtTriRec *>(S.tris),
                                                           const_cast<float *>(S.tri_uv), const_cast<VtTriAttr *>(S.attrs));
     return cudaGetLastError();
 }
