@@ -298,6 +298,90 @@ class ResidentFrame:
         return int(((attrs["prim"] != abi.VT_MISS) & ((attrs["flags"] & abi.VT_ATTR_HIT_SKY) == 0)).sum()) * SPP
 
 
+def config5_side(args, torch, dist, dev, world, rank, local_rank, sync_all, max_over_ranks):
+    """BASELINE.json configs[4], the world-scale path-tracing workload, as a SIDE measurement next to the headline: a 19 995 044-
+    triangle scene (terrain + 143 props), 3840x2160, 16 samples per pixel, per sample primary + shadow + 3 diffuse bounces each with
+    a shadow ray (vt_accel_trace_paths: wave compaction).  N > 1 shards by SAMPLE INDEX: rank r traces samples r, r + N, ... of
+    every pixel and the per-rank images are summed on rank 0 with one ncclReduce (strong scaling: the frame is fixed).
+    `value` = device-resident (primary rays in HBM), `e2e` = host rays up on every rank, host image down on rank 0."""
+    import vistrace_b200 as vt
+    from vistrace_b200 import scenes
+
+    W5, H5, SPP5, BOUNCES = 3840, 2160, 16, 3
+    t0 = time.time()
+    scene = scenes.scene_terrain_closed(2980, n_props=143) if rank == 0 else None
+    rays = scenes.pinhole_rays(W5, H5, *CAMERA)
+    n = len(rays)
+    gen_s = time.time() - t0
+    t0 = time.time()
+    if world == 1:
+        group, accel = None, vt.Accel(local_rank).populate(scene)
+    else:
+        uid = torch.from_numpy(vt.group_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+        dist.broadcast(uid, src=0)
+        group = vt.Group(device=local_rank, rank=rank, world=world, unique_id=uid.cpu().numpy()).populate(scene)
+        accel = group.accel(0)
+    populate_s = time.time() - t0
+    n_tris = int(scene.n_tris) if scene is not None else None
+    del scene
+    sun = np.array((0.3, 0.2, 0.93), np.float32)
+    sun = sun / np.linalg.norm(sun)
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    h_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).pin_memory()
+    d_rays = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    d_rays.copy_(h_rays)
+    d_fb = torch.zeros(n * 3, dtype=torch.float32, device=dev)
+    h_fb = torch.empty(n * 3, dtype=torch.float32).pin_memory() if rank == 0 else None
+    my_samples = list(range(rank, SPP5, world))
+    counts = accel.trace_paths_device(d_rays.data_ptr(), n, BOUNCES, sun, (1, 1, 1), 1, 0.0, d_fb.data_ptr(), want_counts=True, stream=sh)
+    rays_per_sample = int(counts.sum())  # the same for every sample up to the random directions of the bounces (counted once, outside the timed region)
+
+    def frame(it, host):
+        if host:
+            d_rays.copy_(h_rays, non_blocking=True)
+        d_fb.zero_()
+        for smp in my_samples:
+            accel.trace_paths_device(d_rays.data_ptr(), n, BOUNCES, sun, (1, 1, 1), 1000 * it + smp, 1.0 / SPP5, d_fb.data_ptr(), stream=sh)
+        if group is not None:
+            group.reduce_device(d_fb.data_ptr(), n * 3, stream=sh)
+        if host and rank == 0:
+            h_fb.copy_(d_fb, non_blocking=True)
+        if host:
+            stream.synchronize()
+
+    frames = 2
+    frame(0, False)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for it in range(frames):
+        frame(1 + it, False)
+    e1.record(stream)
+    sync_all()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / frames
+    frame(0, True)
+    sync_all()
+    t0 = time.perf_counter()
+    for it in range(frames):
+        frame(1 + it, True)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / frames
+    rays_per_frame = rays_per_sample * SPP5
+    out = {"workload": f"config5: {n_tris}-tri terrain + props, {W5}x{H5}, {SPP5} spp, per sample primary + shadow + {BOUNCES} diffuse bounces each with a shadow ray (wave compaction)",
+           "scaling": "strong", "sharding": "one GPU" if world == 1 else f"by sample index over {world} ranks, one ncclReduce of the {n * 12 // 1000000} MB image per frame",
+           "rays_per_frame": rays_per_frame, "value": round(rays_per_frame / ms / 1e3, 2), "unit": "Mrays/s", "ms_per_frame": round(ms, 3),
+           "e2e": {"value": round(rays_per_frame / e2e_ms / 1e3, 2), "ms_per_frame": round(e2e_ms, 3), "h2d_bytes_per_frame": n * 32, "d2h_bytes_per_frame": n * 12},
+           "rays_per_wave_of_one_sample": [int(c) for c in counts], "scene_generation_s": round(gen_s, 1), "populate_s": round(populate_s, 1)}
+    if group is not None:
+        group.close()
+    else:
+        accel.close()
+    del d_rays, d_fb
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -369,6 +453,7 @@ def run_ours(args):
         log(f"[bench] scene {st['n_tris']} tris, {st['node_count']} nodes, {st['device_bytes'] / 1e6:.0f} MB resident, scene generation {gen_s:.1f}s, "
             f"populate (ingest + build + flatten + upload{' + ncclBroadcast' if world > 1 else ''}) {populate_s:.1f}s")
     layout = accel.layout
+    shard_tile = group.shard(n)[0] if group else None
     use_queue = os.environ.get("VT_BENCH_QUEUE", "1") != "0"
     seed0 = 1000
     steps, warmup = args.steps, args.warmup
@@ -497,16 +582,9 @@ def run_ours(args):
         hits_variant = {"call": "vt_accel_trace_diffuse_wave", "value": round((n + int(res["live_bounce"])) / (e2e_hits_ms * 1e-3) / 1e6, 2),
                         "ms_per_step": round(e2e_hits_ms, 3), "d2h_bytes_per_step": n * 16 + n * SPP * 16}
 
-    if rank != 0:
-        if group:
-            group.close()
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
     # ------------------------------------------------------------------ rank 0: roofline, CPU baseline, parity
     roof, cpu_line, parity = None, None, None
-    if world == 1:
+    if world == 1 and rank == 0:
         brays_host = np.frombuffer(frame.d_brays.cpu().numpy().tobytes(), abi.RAY)[: n * SPP]
         bhits_host = np.frombuffer(frame.d_bhits.cpu().numpy().tobytes(), abi.HIT)[: n * SPP]
         phits_host = np.frombuffer(frame.d_hits.cpu().numpy().tobytes(), abi.HIT)[:n]
@@ -576,12 +654,32 @@ def run_ours(args):
                 parity["checker"] = f"{cpu['kind']} traversal on its own hierarchy, every ray of one step (primary + bounce)"
             except Exception as e:  # the checker is optional for the number itself
                 log(f"[bench] cpu_baseline leg unavailable: {e}")
+    # ------------------------------------------------------------------ side measurement: BASELINE configs[4] (every rank takes part)
+    config5 = None
+    if args.config5 != "off":
+        if group:
+            group.close()
+            group = None
+        else:
+            accel.close()
+        torch.cuda.empty_cache()
+        try:
+            config5 = config5_side(args, torch, dist, dev, world, rank, local_rank, sync_all, max_over_ranks)
+        except Exception as e:  # a side field must never cost the headline line
+            log(f"[bench] config5 side measurement failed on rank {rank}: {e}")
+    if rank != 0:
+        if group:
+            group.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": CONFIG,
         "details": {"rays_per_step": rays_per_step, "numa_node": numa, "setup_s": round(setup_s, 1), "populate_s": round(populate_s, 2),
-                    "parallelism": "one GPU" if world == 1 else f"hierarchy built once and replicated (ncclBroadcast), frame cut into {group.shard(n)[0]}-pixel tiles dealt round-robin to {world} ranks, "
+                    "parallelism": "one GPU" if world == 1 else f"hierarchy built once and replicated (ncclBroadcast), frame cut into {shard_tile}-pixel tiles dealt round-robin to {world} ranks, "
                                    "no ray traced twice, framebuffer shards gathered on rank 0 (ncclSend/ncclRecv)",
                     "hierarchy": ("reference-identical PLOC + LeafCollapser (vt_build_bvh_ploc)" if args.builder == "ploc" else "product builder (binned SAH)")
                                  + f", {layout} node layout"},
@@ -592,6 +690,8 @@ def run_ours(args):
     }
     if weak:
         line["weak"] = weak
+    if config5:
+        line["config5"] = config5
     if roof:
         line["roofline"] = roof
     if cpu_line:
@@ -618,6 +718,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-stride", type=int, default=1, help="reference arm: trace every n-th pixel per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config5", default="on", choices=["on", "off"], help="side measurement of BASELINE configs[4] (20 M triangles, 4K, 16 spp path waves)")
     ap.add_argument("--builder", default="product", choices=["product", "ploc"],
                     help="hierarchy of our arm: the product's binned-SAH builder (default, the headline) or the bit-identical "
                          "restatement of the reference's PLOC + LeafCollapser build (the tree the reference arm traverses)")

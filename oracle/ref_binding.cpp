@@ -18,6 +18,8 @@
 // here as source so that both shared objects are built from one definition.
 #include "ref_harness.cpp"
 
+#include "../include/vistrace_b200_ivtf.hpp"
+
 #include <map>
 
 namespace {
@@ -31,27 +33,11 @@ struct GpuAccelBinding {
         if (mpGpu) vt_accel_destroy(mpGpu);
     }
 
-    // IVTFTexture -> RGBA8888 mip chain, smallest mip first like the VTF file (libs/VTFParser/VTFParser.cpp:44-78): every byte b
-    // satisfies b / 255.f == the channel GetPixel returns for an 8-bit source format, which is what the device sampler assumes.
+    // IVTFTexture -> RGBA8888 mip chain through the public interface only: the product's header-only helper
+    // (include/vistrace_b200_ivtf.hpp), instantiated here with the reference's own VisTrace::IVTFTexture
     vt_texture DecodeTexture(const VisTrace::IVTFTexture *tex) {
-        const uint16_t mips = tex->GetMIPLevels();
         mTexelStorage.emplace_back();
-        std::vector<uint8_t> &px = mTexelStorage.back();
-        for (int m = (int)mips - 1; m >= 0; m--) {
-            const uint16_t w = tex->GetWidth((uint8_t)m), h = tex->GetHeight((uint8_t)m);
-            for (uint16_t y = 0; y < h; y++)
-                for (uint16_t x = 0; x < w; x++) {
-                    const VisTrace::Pixel p = tex->GetPixel(x, y, 0, (uint8_t)m, 0, 0);
-                    const float c[4] = {p.r, p.g, p.b, p.a};
-                    for (float v : c) px.push_back((uint8_t)std::lround(std::min(1.f, std::max(0.f, v)) * 255.f));
-                }
-        }
-        vt_texture t;
-        std::memset(&t, 0, sizeof(t));
-        t.width = tex->GetWidth(0), t.height = tex->GetHeight(0), t.mip_count = mips;
-        t.flags = 0;  // IVTFTexture does not expose TEXTURE_FLAGS; a VTFTexture-backed implementation passes GetFlags() here
-        t.rgba = px.data(), t.nbytes = px.size();
-        return t;
+        return vt::decode_ivtf_texture(tex, mTexelStorage.back());
     }
 
     static void mat_out(const glm::mat2x4 &m, float out[8]) {

@@ -466,7 +466,7 @@ void AccelStruct::Populate(const vt_scene &scene) {
         build_bvh_ploc(mTriangles, mAccel);
         collapse_leaves(mAccel);
     } else {
-        build_bvh(mTriangles, mAccel, env_int("VT_MAX_LEAF", 4), env_float("VT_TRAV_COST", 1.0f));
+        build_bvh(mTriangles, mAccel, env_int("VT_MAX_LEAF", 4), env_float("VT_TRAV_COST", 1.0f), (uint32_t)std::max(0, env_int("VT_SAH_SWEEP", 0)));
     }
     timer.lap("hierarchy build");
     Upload(scene);
@@ -1639,7 +1639,7 @@ int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, ui
         tris[i] = vt::Triangle(in.p[0], in.p[1], in.p[2], in.material, in.uvs, in.one_sided != 0);
     }
     vt::HostBvh bvh;
-    vt::build_bvh(tris, bvh, vt::env_int("VT_MAX_LEAF", 4), vt::env_float("VT_TRAV_COST", 1.0f));
+    vt::build_bvh(tris, bvh, vt::env_int("VT_MAX_LEAF", 4), vt::env_float("VT_TRAV_COST", 1.0f), (uint32_t)std::max(0, vt::env_int("VT_SAH_SWEEP", 0)));
     if (nodes) {
         if (*node_count < bvh.nodes.size()) throw std::runtime_error("node buffer too small");
         std::memcpy(nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(vt_node));

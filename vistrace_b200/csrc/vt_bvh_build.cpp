@@ -59,6 +59,7 @@ struct BuildCtx {
     std::atomic<uint32_t> next_node;
     int max_leaf;
     float trav_cost;
+    uint32_t sweep_below;  // nodes with at most this many primitives are split by the exact SAH sweep instead of 16 bins (0 = never)
 };
 
 void set_bounds(vt_node &nd, const Box &b) {
@@ -196,6 +197,44 @@ void build_range(BuildCtx &c, uint32_t node, uint32_t begin, uint32_t end, const
             }
         }
     }
+    // Quality option (what bvh::SweepSahBuilder does for every node, libs/bvh/include/bvh/sweep_sah_builder.hpp:60-120): below
+    // `sweep_below` primitives every split position along every axis is evaluated on the sorted centroids instead of 16 bins.
+    uint32_t sweep_mid = 0;
+    if (!force_balance && c.sweep_below && count <= c.sweep_below && count <= 256) {
+        uint32_t order[256], best_order[256];
+        float right_area[256];
+        float sweep_best = best_cost;
+        bool found = false;
+        for (int axis = 0; axis < 3; axis++) {
+            for (uint32_t i = 0; i < count; i++) order[i] = c.idx[begin + i];
+            std::sort(order, order + count, [&](uint32_t a, uint32_t b) {
+                const float ca = c.cen[3 * (size_t)a + axis], cb2 = c.cen[3 * (size_t)b + axis];
+                return ca < cb2 || (ca == cb2 && a < b);
+            });
+            Box acc;
+            acc.reset();
+            for (uint32_t i = count; i-- > 1;) {
+                acc.grow(c.bmin + 3 * (size_t)order[i], c.bmax + 3 * (size_t)order[i]);
+                right_area[i] = acc.half_area();
+            }
+            acc.reset();
+            for (uint32_t i = 0; i + 1 < count; i++) {
+                acc.grow(c.bmin + 3 * (size_t)order[i], c.bmax + 3 * (size_t)order[i]);
+                const float cost = acc.half_area() * (float)(i + 1) + right_area[i + 1] * (float)(count - i - 1);
+                if (cost < sweep_best) {
+                    sweep_best = cost;
+                    sweep_mid = i + 1;
+                    found = true;
+                    std::memcpy(best_order, order, count * sizeof(uint32_t));
+                }
+            }
+        }
+        if (found) {  // strictly better than the best binned split
+            best_cost = sweep_best;
+            best_axis = 3;  // marks "already partitioned"
+            std::memcpy(c.idx + begin, best_order, count * sizeof(uint32_t));
+        }
+    }
     // SAH termination: leaf cost = N * area, split cost = traversal * area + children
     const float area = box.half_area();
     if ((int)count <= c.max_leaf) {
@@ -207,7 +246,9 @@ void build_range(BuildCtx &c, uint32_t node, uint32_t begin, uint32_t end, const
     Box lb, rb, lcb, rcb;
     lb.reset(), rb.reset(), lcb.reset(), rcb.reset();
     bool boxes_known = false;
-    if (best_axis >= 0) {
+    if (best_axis == 3) {
+        mid = begin + sweep_mid;  // the sweep left idx[begin, end) sorted along its axis
+    } else if (best_axis >= 0) {
         const float lo = cb.lo[best_axis], sc = scale[best_axis];
         const int axis = best_axis, bin = best_bin;
         uint32_t n_left = 0;
@@ -288,7 +329,7 @@ void build_range(BuildCtx &c, uint32_t node, uint32_t begin, uint32_t end, const
 
 // Build a bvh::Bvh<float>-form hierarchy over the triangles.  Deterministic: the tree depends only
 // on the input, and the final node order is a depth-first relayout of it.
-void build_bvh(const TriangleVec &tris, HostBvh &out, int max_leaf, float trav_cost) {
+void build_bvh(const TriangleVec &tris, HostBvh &out, int max_leaf, float trav_cost, uint32_t sweep_below) {
     const size_t n = tris.size();
     out.nodes.clear();
     out.prim_indices.clear();
@@ -335,7 +376,7 @@ void build_bvh(const TriangleVec &tris, HostBvh &out, int max_leaf, float trav_c
 #pragma omp parallel for
     for (int64_t i = 0; i < (int64_t)n; i++) idx[i] = (uint32_t)i;
     RawVector<vt_node> tmp(2 * n + 1);
-    BuildCtx c{bmin.data(), bmax.data(), cen.data(), idx.data(), scratch.data(), tmp.data(), {1}, max_leaf, trav_cost};
+    BuildCtx c{bmin.data(), bmax.data(), cen.data(), idx.data(), scratch.data(), tmp.data(), {1}, max_leaf, trav_cost, sweep_below};
 #pragma omp parallel
 #pragma omp single
     build_range(c, 0, 0, (uint32_t)n, global, global_c, 0);

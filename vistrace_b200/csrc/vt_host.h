@@ -78,7 +78,9 @@ struct FlatBvh {
     uint32_t max_depth = 0;
 };
 
-void build_bvh(const TriangleVec &tris, HostBvh &out, int max_leaf, float trav_cost);
+// sweep_below: builder-quality option — nodes of at most that many primitives are split by the exact SAH sweep over sorted
+// centroids (bvh::SweepSahBuilder's evaluation, libs/bvh/include/bvh/sweep_sah_builder.hpp) instead of 16 bins; 0 = binned only.
+void build_bvh(const TriangleVec &tris, HostBvh &out, int max_leaf, float trav_cost, uint32_t sweep_below = 0);
 // The reference's own hierarchy rebuilt from its algorithm (vt_bvh_ploc.cpp): bvh::LocallyOrderedClusteringBuilder<BVH, uint32_t>
 // (search radius 14, 30-bit Morton codes) and bvh::LeafCollapser, the sequence of source/objects/AccelStruct.cpp:762-770.
 void build_bvh_ploc(const TriangleVec &tris, HostBvh &out);
