@@ -113,6 +113,36 @@ int vt_vtf_read_info(const uint8_t *file, uint64_t size, vt_vtf_info *info);
 int vt_vtf_decode(const uint8_t *file, uint64_t size, uint32_t frame, uint32_t face, uint8_t *rgba_out, uint64_t capacity,
                   vt_vtf_info *info_or_null);
 
+/* Source-engine model ingestion, host only: .mdl + .vvd + .vtx -> the triangles the reference's Model /
+ * Mesh classes hand to PopulateAccel.  Restates libs/MDLParser (MDLParser.cpp:33-60, VVDParser.cpp:33-83, VTXParser.cpp:33-56:
+ * ids, versions <= 48 / 4 / 7, the checksum tying the three files together, the VVD fix-up table) and source/objects/Model.cpp
+ * (Mesh::Mesh :11-128: LoD 0, triangle-list strips, normals / tangents through glm::normalize, a non-finite tangent replaced by
+ * normalize(e1), per-vertex bone weights; bind matrices :242-254; skin table :349-357; material paths :256-274).  Every offset and
+ * index is checked against the file sizes.  The triangles come out in MODEL space with their skinning data: vt_skin_triangles
+ * (SkinTriangle) bakes them into world space, as AccelStruct::PopulateAccel does per entity (source/objects/AccelStruct.cpp:716-749). */
+typedef struct vt_mdl_files {
+    const uint8_t *mdl; uint64_t mdl_size;
+    const uint8_t *vvd; uint64_t vvd_size;
+    const uint8_t *vtx; uint64_t vtx_size;
+} vt_mdl_files;
+typedef struct vt_mdl_info {
+    uint32_t version;         /* studio header version (<= 48) */
+    uint32_t n_bodygroups;    /* Model::GetNumBodyGroups */
+    uint32_t n_bones;         /* Model::GetNumBones */
+    uint32_t n_materials;     /* Model::GetNumMaterials */
+    uint32_t n_material_dirs;
+    uint32_t n_skin_refs, n_skin_families; /* Model::GetNumSkinFamilies */
+    uint32_t n_vertices;      /* root-LoD vertices of the vvd */
+} vt_mdl_info;
+int vt_mdl_read_info(const vt_mdl_files *files, vt_mdl_info *info);
+int vt_mdl_bodygroup_values(const vt_mdl_files *files, uint32_t bodygroup, uint32_t *n_values); /* BodyGroup::GetNumMeshes */
+/* Model::GetMesh(bodygroup, value)->GetTriangles(): call with tris == NULL for the count; *n_tris = capacity in, count out.
+ * tris[i].material is the MODEL-LOCAL material id (Mesh::material); map it with vt_mdl_material_index. */
+int vt_mdl_mesh_triangles(const vt_mdl_files *files, uint32_t bodygroup, uint32_t value, vt_tri_in *tris, vt_tri_skin *skin, uint64_t *n_tris);
+int vt_mdl_bind_matrices(const vt_mdl_files *files, float *out16); /* Model::GetBindMatrix: n_bones glm::mat4, column-major */
+int vt_mdl_material_index(const vt_mdl_files *files, uint32_t skin, uint32_t material_id, int32_t *index); /* Model::GetMaterialIdx */
+int vt_mdl_material_path(const vt_mdl_files *files, uint32_t material_id, uint32_t dir, char *out, uint64_t capacity); /* directory + name */
+
 /* Material subset on the path (source/objects/Material.h:74-125).  Texture slots
  * are indices into the texture array, -1 = nullptr.  *_mat are glm::mat2x4 in
  * memory order: [0..3] = column 0 (drives u), [4..7] = column 1 (drives v)

@@ -67,6 +67,14 @@ def _lib(kind):
     if kind != "port":  # reference only: its VTF parser is not restated in the C port (the product's decoder is checked against it)
         sig["vtf_pixels"] = (C.c_int64, [vp, u64, C.c_uint32, C.c_uint32, vp, u64])
         sig["reinsertion_optimize"] = (None, [vp, vp])
+        sig["mdl_open"] = (vp, [vp, u64, vp, u64, vp, u64])
+        sig["mdl_close"] = (None, [vp])
+        sig["mdl_info"] = (None, [vp, vp])
+        sig["mdl_bodygroup_values"] = (C.c_int32, [vp, C.c_uint32])
+        sig["mdl_mesh"] = (C.c_int64, [vp, C.c_uint32, C.c_uint32, vp, vp, u64])
+        sig["mdl_bind_matrices"] = (None, [vp, vp])
+        sig["mdl_material_index"] = (C.c_int32, [vp, C.c_int32, C.c_int32])
+        sig["mdl_material_path"] = (C.c_int32, [vp, C.c_int32, C.c_int32, vp, u64])
     ns = type("ns", (), {})()
     for name, (res, args) in sig.items():
         fn = getattr(lib, pre + name)
@@ -232,3 +240,52 @@ def sample_bsdf_diffuse(attrs, wo, rnd, kind="reference"):
     ret = np.zeros(len(attrs), np.int32)
     _lib(kind).sample_bsdf_diffuse(attrs.ctypes.data, wo.ctypes.data, rnd.ctypes.data, len(attrs), out.ctypes.data, ret.ctypes.data)
     return out, ret
+
+
+class RefModel:
+    """The reference's own MDL / VVD / VTX parsers + BodyGroup / Mesh (libs/MDLParser, source/objects/Model.cpp) over file bytes."""
+
+    def __init__(self, mdl, vvd, vtx):
+        self.lib = _lib("reference")
+        self._bufs = [np.frombuffer(bytes(b), np.uint8).copy() for b in (mdl, vvd, vtx)]
+        args = [v for b in self._bufs for v in (b.ctypes.data if len(b) else None, len(b))]
+        self.h = self.lib.mdl_open(*args)
+        info = np.zeros(6, np.int32)
+        self.lib.mdl_info(self.h, info.ctypes.data)
+        self.valid = bool(info[0])
+        self.n_bodygroups, self.n_bones, self.n_materials, self.n_skin_families, self.n_vertices = (int(v) for v in info[1:])
+
+    def close(self):
+        if self.h:
+            self.lib.mdl_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def bodygroup_values(self, bodygroup):
+        return int(self.lib.mdl_bodygroup_values(self.h, bodygroup))
+
+    def mesh(self, bodygroup, value):
+        """(records with p = {p0, e1, e2} as the reference's Triangle stores them, skin records) or None."""
+        n = int(self.lib.mdl_mesh(self.h, bodygroup, value, None, None, 0))
+        if n < 0:
+            return None
+        tris, skin = np.zeros(n, abi.TRI_IN), np.zeros(n, abi.TRI_SKIN)
+        if n:
+            self.lib.mdl_mesh(self.h, bodygroup, value, tris.ctypes.data, skin.ctypes.data, n)
+        return tris, skin
+
+    def bind_matrices(self):
+        out = np.zeros((self.n_bones, 16), np.float32)
+        if self.n_bones:
+            self.lib.mdl_bind_matrices(self.h, out.ctypes.data)
+        return out
+
+    def material_index(self, skin, material_id):
+        return int(self.lib.mdl_material_index(self.h, skin, material_id))
+
+    def material_path(self, material_id, directory=0):
+        buf = C.create_string_buffer(4200)
+        self.lib.mdl_material_path(self.h, material_id, directory, buf, len(buf))
+        return buf.value.decode("latin-1")

@@ -14,6 +14,7 @@
 //   * TraceResult ctor and getters                  source/objects/TraceResult.cpp:45-262
 //   * VTFTexture(const uint8_t*, size_t)::Sample    libs/VTFParser/VTFParser.cpp:311-330
 //   * SampleBSDF + BSDFMaterial::PrepShadingData    source/libraries/BSDF.cpp:11-21,770-825 (diffuse lobe)
+//   * MDL / VVD / VTX parsers + BodyGroup / Mesh    libs/MDLParser/source/*.cpp, source/objects/Model.cpp:11-176
 // The ingestion paths (Lua, engine filesystem) are bypassed by filling the
 // private containers directly, which is why `private` is opened up below.
 #include <algorithm>
@@ -35,6 +36,7 @@
 
 #define private public
 #include "AccelStruct.h"
+#include "Model.h"
 #include "TraceResult.h"
 #undef private
 
@@ -567,5 +569,102 @@ void vtref_sample_bsdf_diffuse(const vt_attr *attrs, const float *wo3, const flo
         out[i].weight[0] = res.weight.x, out[i].weight[1] = res.weight.y, out[i].weight[2] = res.weight.z;
         out[i].lobe = (uint32_t)res.lobe;
     }
+}
+
+// ---- model ingestion: the reference's own MDL / VVD / VTX parsers and its BodyGroup / Mesh constructors (source/objects/Model.cpp:11-176).
+// Model::Model(path) reads through the game's file system, so the Model object is assembled by hand: raw storage, the MDL member
+// constructed from the caller's bytes, and the bind matrices by the statements of Model.cpp:242-254.
+namespace {
+struct RefModel {
+    alignas(Model) unsigned char storage[sizeof(Model)];
+    Model *m = nullptr;
+    std::vector<BodyGroup *> groups;
+    std::vector<glm::mat4> binds;
+    bool valid = false;
+    ~RefModel() {
+        for (BodyGroup *g : groups) delete g;
+        if (m) m->mMDL.~MDL();
+    }
+};
+}  // namespace
+void *vtref_mdl_open(const uint8_t *mdl, uint64_t mdl_size, const uint8_t *vvd, uint64_t vvd_size, const uint8_t *vtx, uint64_t vtx_size) {
+    auto *r = new RefModel();
+    std::memset(r->storage, 0, sizeof(r->storage));
+    r->m = reinterpret_cast<Model *>(r->storage);
+    new (&r->m->mMDL) MDL(mdl, mdl_size, vvd, vvd_size, vtx, vtx_size);
+    r->valid = r->m->mMDL.IsValid();
+    if (!r->valid) return r;
+    const MDL &M = r->m->mMDL;
+    for (int i = 0; i < M.GetNumBodyParts(); i++) {  // Model.cpp:230-238
+        const MDLStructs::BodyPart *bodypart;
+        const VTXStructs::BodyPart *vtxBodypart;
+        M.GetBodyPart(i, &bodypart, &vtxBodypart);
+        r->groups.push_back(new BodyGroup(r->m, bodypart, vtxBodypart));
+        if (!r->groups.back()->IsValid()) r->valid = false;
+    }
+    for (int i = 0; i < M.GetNumBones(); i++) {  // Model.cpp:242-254
+        const MDLStructs::Matrix3x4 &m = M.GetBone(i)->poseToBone;
+        glm::mat4x4 bind(m[0][0], m[1][0], m[2][0], 0, m[0][1], m[1][1], m[2][1], 0, m[0][2], m[1][2], m[2][2], 0, m[0][3], m[1][3], m[2][3], 1);
+        r->binds.push_back(bind);
+    }
+    return r;
+}
+void vtref_mdl_close(void *h) { delete static_cast<RefModel *>(h); }
+// out: {valid, body groups, bones, materials, skin families, vertices}
+void vtref_mdl_info(void *h, int32_t *out6) {
+    auto *r = static_cast<RefModel *>(h);
+    std::memset(out6, 0, 6 * sizeof(int32_t));
+    out6[0] = r->valid ? 1 : 0;
+    if (!r->valid) return;
+    const MDL &M = r->m->mMDL;
+    out6[1] = M.GetNumBodyParts(), out6[2] = M.GetNumBones(), out6[3] = M.GetNumMaterials(), out6[4] = M.GetNumSkinFamilies(), out6[5] = M.GetNumVertices();
+}
+int32_t vtref_mdl_bodygroup_values(void *h, uint32_t bodygroup) {
+    auto *r = static_cast<RefModel *>(h);
+    return (r->valid && bodygroup < r->groups.size()) ? r->groups[bodygroup]->GetNumMeshes() : -1;
+}
+// Triangles of BodyGroup::GetMesh(value) as the reference's Triangle holds them: tris[i].p = {p0, e1, e2} (NOT three vertices),
+// normals / tangents / uvs / alphas / material as stored, skin = numBones / weights / boneIds.  Returns the count (-1: no such mesh).
+int64_t vtref_mdl_mesh(void *h, uint32_t bodygroup, uint32_t value, vt_tri_in *tris, vt_tri_skin *skin, uint64_t capacity) {
+    auto *r = static_cast<RefModel *>(h);
+    if (!r->valid || bodygroup >= r->groups.size() || (int32_t)value >= r->groups[bodygroup]->GetNumMeshes()) return -1;
+    const Mesh *mesh = r->groups[bodygroup]->GetMesh((int)value);
+    const int32_t n = mesh->GetNumTriangles();
+    if (!tris) return n;
+    const Triangle *T = mesh->GetTriangles();
+    for (int32_t i = 0; i < n && (uint64_t)i < capacity; i++) {
+        const Triangle &t = T[i];
+        vt_tri_in &o = tris[i];
+        vt_tri_skin &sk = skin[i];
+        std::memset(&o, 0, sizeof(o));
+        std::memset(&sk, 0, sizeof(sk));
+        for (int k = 0; k < 3; k++) o.p[0][k] = t.p0[k], o.p[1][k] = t.e1[k], o.p[2][k] = t.e2[k];
+        std::memcpy(o.normals, t.normals, sizeof o.normals);
+        std::memcpy(o.tangents, t.tangents, sizeof o.tangents);
+        std::memcpy(o.uvs, t.uvs, sizeof o.uvs);
+        std::memcpy(o.alphas, t.alphas, sizeof o.alphas);
+        o.material = (uint32_t)t.material, o.one_sided = t.oneSided;
+        for (int j = 0; j < 3; j++) {
+            sk.num_bones[j] = t.numBones[j];
+            // the reference fills all three slots when the VTX vertex has bones and only slot 0 otherwise (Model.cpp:105-116)
+            const int filled = t.numBones[j] == 1 && t.weights[j][0] == 1.f && t.boneIds[j][0] == 0 ? 1 : 3;
+            for (int b = 0; b < filled; b++) sk.weights[j][b] = t.weights[j][b], sk.bone_ids[j][b] = t.boneIds[j][b];
+        }
+    }
+    return n;
+}
+void vtref_mdl_bind_matrices(void *h, float *out16) {
+    auto *r = static_cast<RefModel *>(h);
+    for (size_t i = 0; i < r->binds.size(); i++) std::memcpy(out16 + 16 * i, &r->binds[i][0][0], 64);
+}
+int32_t vtref_mdl_material_index(void *h, int32_t skin, int32_t material_id) {  // Model::GetMaterialIdx, Model.cpp:349-357
+    auto *r = static_cast<RefModel *>(h);
+    return r->m->GetMaterialIdx(skin, material_id);
+}
+int32_t vtref_mdl_material_path(void *h, int32_t material_id, int32_t dir, char *out, uint64_t cap) {
+    auto *r = static_cast<RefModel *>(h);
+    const std::string s = std::string(r->m->mMDL.GetMaterialDirectory(dir)) + r->m->mMDL.GetMaterialName(material_id);
+    std::snprintf(out, cap, "%s", s.c_str());
+    return (int32_t)s.size();
 }
 } // extern "C"

@@ -52,6 +52,12 @@ SYMBOLS = {
     "vt_quad_plane_offset": (_u32, []),
     "vt_vtf_read_info": (_i32, [_vp, _u64, _vp]),
     "vt_vtf_decode": (_i32, [_vp, _u64, _u32, _u32, _vp, _u64, _vp]),
+    "vt_mdl_read_info": (_i32, [_vp, _vp]),
+    "vt_mdl_bodygroup_values": (_i32, [_vp, _u32, _vp]),
+    "vt_mdl_mesh_triangles": (_i32, [_vp, _u32, _u32, _vp, _vp, _vp]),
+    "vt_mdl_bind_matrices": (_i32, [_vp, _vp]),
+    "vt_mdl_material_index": (_i32, [_vp, _u32, _u32, _vp]),
+    "vt_mdl_material_path": (_i32, [_vp, _u32, _u32, _vp, _u64]),
     "vt_build_bvh_ploc": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "vt_build_quads": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_refit_quality": (_i32, [_vp, _vp, _vp]),
@@ -223,6 +229,60 @@ def vtf_decode(data, frame=0, face=0):
     out = np.zeros(int(info["rgba_bytes"]), np.uint8)
     _check(lib().vt_vtf_decode(buf.ctypes.data, len(buf), frame, face, out.ctypes.data, len(out), None), "vt_vtf_decode")
     return int(info["width"]), int(info["height"]), int(info["mip_count"]), int(info["flags"]), out
+
+
+MDL_INFO = np.dtype([("version", np.uint32), ("n_bodygroups", np.uint32), ("n_bones", np.uint32), ("n_materials", np.uint32), ("n_material_dirs", np.uint32),
+                     ("n_skin_refs", np.uint32), ("n_skin_families", np.uint32), ("n_vertices", np.uint32)])
+
+
+class MdlFiles:
+    """The three files of a Source-engine model (bytes) behind vt_mdl_* (host-only ingestion, include/vistrace_b200.h)."""
+
+    class _C(C.Structure):
+        _fields_ = [("mdl", _vp), ("mdl_size", _u64), ("vvd", _vp), ("vvd_size", _u64), ("vtx", _vp), ("vtx_size", _u64)]
+
+    def __init__(self, mdl, vvd, vtx):
+        self._bufs = [np.frombuffer(bytes(b), np.uint8).copy() if len(b) else np.zeros(0, np.uint8) for b in (mdl, vvd, vtx)]
+        self.c = self._C(*[v for b in self._bufs for v in (b.ctypes.data if len(b) else None, len(b))])
+        self.L = lib()
+
+    def _p(self):
+        return C.addressof(self.c)
+
+    def info(self):
+        out = np.zeros(1, MDL_INFO)
+        _check(self.L.vt_mdl_read_info(self._p(), out.ctypes.data), "vt_mdl_read_info")
+        return out[0]
+
+    def bodygroup_values(self, bodygroup):
+        n = C.c_uint32(0)
+        _check(self.L.vt_mdl_bodygroup_values(self._p(), bodygroup, C.addressof(n)), "vt_mdl_bodygroup_values")
+        return n.value
+
+    def mesh_triangles(self, bodygroup, value):
+        """(vt_tri_in records in model space, vt_tri_skin records) of Model::GetMesh(bodygroup, value)."""
+        n = C.c_uint64(0)
+        _check(self.L.vt_mdl_mesh_triangles(self._p(), bodygroup, value, None, None, C.addressof(n)), "vt_mdl_mesh_triangles")
+        tris, skin = np.zeros(n.value, abi.TRI_IN), np.zeros(n.value, abi.TRI_SKIN)
+        if n.value:
+            _check(self.L.vt_mdl_mesh_triangles(self._p(), bodygroup, value, tris.ctypes.data, skin.ctypes.data, C.addressof(n)), "vt_mdl_mesh_triangles")
+        return tris, skin
+
+    def bind_matrices(self):
+        out = np.zeros((int(self.info()["n_bones"]), 16), np.float32)
+        if len(out):
+            _check(self.L.vt_mdl_bind_matrices(self._p(), out.ctypes.data), "vt_mdl_bind_matrices")
+        return out
+
+    def material_index(self, skin, material_id):
+        v = C.c_int32(0)
+        _check(self.L.vt_mdl_material_index(self._p(), skin, material_id, C.addressof(v)), "vt_mdl_material_index")
+        return v.value
+
+    def material_path(self, material_id, directory=0):
+        buf = C.create_string_buffer(4200)
+        _check(self.L.vt_mdl_material_path(self._p(), material_id, directory, buf, len(buf)), "vt_mdl_material_path")
+        return buf.value.decode("latin-1")
 
 
 def quad_plane_offset():

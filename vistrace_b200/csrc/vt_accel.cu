@@ -1708,6 +1708,56 @@ int vt_vtf_decode(const uint8_t *file, uint64_t size, uint32_t frame, uint32_t f
     VT_CATCH(1)
 }
 
+int vt_mdl_read_info(const vt_mdl_files *files, vt_mdl_info *info) {
+    VT_TRY
+    if (!files || !info) throw std::runtime_error("null argument");
+    vt::MdlInfo(files, info);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_mdl_bodygroup_values(const vt_mdl_files *files, uint32_t bodygroup, uint32_t *n_values) {
+    VT_TRY
+    if (!files || !n_values) throw std::runtime_error("null argument");
+    *n_values = vt::MdlBodygroupValues(files, bodygroup);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_mdl_mesh_triangles(const vt_mdl_files *files, uint32_t bodygroup, uint32_t value, vt_tri_in *tris, vt_tri_skin *skin, uint64_t *n_tris) {
+    VT_TRY
+    if (!files || !n_tris) throw std::runtime_error("null argument");
+    *n_tris = vt::MdlMeshTriangles(files, bodygroup, value, tris, skin, tris ? *n_tris : 0);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_mdl_bind_matrices(const vt_mdl_files *files, float *out16) {
+    VT_TRY
+    if (!files || !out16) throw std::runtime_error("null argument");
+    vt::MdlBindMatrices(files, out16);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_mdl_material_index(const vt_mdl_files *files, uint32_t skin, uint32_t material_id, int32_t *index) {
+    VT_TRY
+    if (!files || !index) throw std::runtime_error("null argument");
+    *index = vt::MdlMaterialIndex(files, skin, material_id);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_mdl_material_path(const vt_mdl_files *files, uint32_t material_id, uint32_t dir, char *out, uint64_t capacity) {
+    VT_TRY
+    if (!files || !out || !capacity) throw std::runtime_error("null argument");
+    const std::string s = vt::MdlMaterialPath(files, material_id, dir);
+    if (s.size() + 1 > capacity) throw std::runtime_error("mdl: path buffer too small");
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return 0;
+    VT_CATCH(1)
+}
+
 uint32_t vt_quad_plane_offset(void) { return (uint32_t)VT_QUAD_OFFSET; }
 
 int vt_build_quads(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris, void *quads_out,

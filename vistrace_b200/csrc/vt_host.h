@@ -121,6 +121,15 @@ void SkinTriangles(vt_tri_in *tris, const vt_tri_skin *skin, uint64_t n, const f
 void VtfInfo(const uint8_t *file, uint64_t size, vt_vtf_info *out);
 void VtfDecode(const uint8_t *file, uint64_t size, uint32_t frame, uint32_t face, uint8_t *rgba, uint64_t capacity, vt_vtf_info *info_out);
 
+// Source-engine model files -> triangles (vt_mdl.cpp; libs/MDLParser + source/objects/Model.cpp restated).  Throw std::runtime_error on
+// malformed / unsupported files.
+void MdlInfo(const vt_mdl_files *f, vt_mdl_info *info);
+uint32_t MdlBodygroupValues(const vt_mdl_files *f, uint32_t bodygroup);
+uint64_t MdlMeshTriangles(const vt_mdl_files *f, uint32_t bodygroup, uint32_t value, vt_tri_in *tris, vt_tri_skin *skin, uint64_t capacity);
+void MdlBindMatrices(const vt_mdl_files *f, float *out16);
+int32_t MdlMaterialIndex(const vt_mdl_files *f, uint32_t skin, uint32_t material_id);
+std::string MdlMaterialPath(const vt_mdl_files *f, uint32_t material_id, uint32_t dir);
+
 struct DeviceScene;  // HBM-resident copy, vt_accel.cu
 
 // Eager TraceResult for one hit (source/objects/TraceResult.h:54-111): the batched path fills
