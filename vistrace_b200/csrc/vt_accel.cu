@@ -450,8 +450,6 @@ void AccelStruct::Upload(const vt_scene &scene) {
     if (blocks < 1) blocks = 1;
     const int mult = env_int("VT_GRID_BLOCKS_PER_SM", blocks);
     D.cfg.grid = D.sm_count * std::max(1, std::min(mult, blocks));
-    D.cfg.sm_count = D.sm_count;
-    D.cfg.min_rays_per_lane = env_int("VT_K1_RAYS_PER_LANE", D.cfg.min_rays_per_lane);
     mAccelBuilt = true;
 }
 
@@ -549,8 +547,6 @@ void AccelStruct::AllocReplica(const ReplicaImage &img, void *bufs[10]) {
     if (blocks < 1) blocks = 1;
     const int mult = env_int("VT_GRID_BLOCKS_PER_SM", blocks);
     D.cfg.grid = D.sm_count * std::max(1, std::min(mult, blocks));
-    D.cfg.sm_count = D.sm_count;
-    D.cfg.min_rays_per_lane = env_int("VT_K1_RAYS_PER_LANE", D.cfg.min_rays_per_lane);
     mReplica = true;
     mBvhStale = false;
     mAccelBuilt = true;  // valid once the caller has filled the buffers (it does so before anything is enqueued)

@@ -20,9 +20,6 @@
 struct VtLaunchConfig {
     int persistent = 1;         // 1: machine-sized grid pulling rays from a counter; 0: one ray per thread
     int grid = 0;               // CTAs for the persistent launch (SMs x resident CTAs)
-    int sm_count = 0;           // SMs of the device (lower bound of a shrunk grid)
-    int min_rays_per_lane = 0;  // > 0: shrink the persistent grid of a SMALL launch so that every lane gets about this many rays
-                                // (fewer resident warps = shorter rounds = a shorter tail of the slowest rays); 0 = always the full grid
     int refill_threshold = 24;  // refill a warp when <= this many of its lanes still own a ray
     int tri_threshold = 10;     // run a triangle round when >= this many lanes have a candidate queued (6 / 8 / 10: 3.39 / 3.47 / 3.51 Grays/s)
 };

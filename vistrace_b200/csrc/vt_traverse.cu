@@ -879,12 +879,6 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
     int grid;
     if (cfg.persistent) {
         grid = cfg.grid;
-        if (cfg.min_rays_per_lane > 0 && cfg.sm_count > 0) {
-            const uint64_t want = (n + (uint64_t)VT_TRAVERSE_BLOCK * cfg.min_rays_per_lane - 1) / ((uint64_t)VT_TRAVERSE_BLOCK * cfg.min_rays_per_lane);
-            // whole multiples of the SM count, at least one CTA per SM, never more than the resident maximum
-            const uint64_t per_sm = std::max<uint64_t>(1, (want + cfg.sm_count - 1) / cfg.sm_count);
-            grid = (int)std::min<uint64_t>((uint64_t)cfg.grid, per_sm * cfg.sm_count);
-        }
     } else {
         grid = (int)((n + VT_TRAVERSE_BLOCK - 1) / VT_TRAVERSE_BLOCK);
     }
