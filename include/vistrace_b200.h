@@ -586,6 +586,11 @@ int vt_group_render_diffuse_wave(vt_group *group, const vt_ray *rays, uint64_t n
  * rank 0's, in place — one ncclReduce over NVLink, enqueued on `stream`.  Multi-process groups. */
 int vt_group_reduce_device(vt_group *group, float *buf, uint64_t count, void *stream);
 
+/* The other collective of a sample-index-sharded frame: every rank has uploaded ITS 1 / w of a device buffer (bytes_per_rank
+ * bytes at buf + rank * bytes_per_rank, e.g. its slice of the primary rays) and receives the other slices over NVLink —
+ * one ncclAllGather, in place, enqueued on `stream`.  Multi-process groups. */
+int vt_group_all_gather_device(vt_group *group, void *buf, uint64_t bytes_per_rank, void *stream);
+
 /* Kernel launches + collectives issued through the group so far. */
 uint64_t vt_group_launch_count(const vt_group *group);
 

@@ -41,6 +41,14 @@ part = torch.full((1000,), float(rank + 1), dtype=torch.float32, device=dev)
 group.reduce_device(part.data_ptr(), 1000, stream=torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 
+# every rank contributes its slice of a device buffer; afterwards every rank holds the whole buffer (ncclAllGather, in place)
+slice_bytes = 4096
+gathered = torch.zeros(world * slice_bytes, dtype=torch.uint8, device=dev)
+gathered[rank * slice_bytes:(rank + 1) * slice_bytes] = rank + 1
+group.all_gather_device(gathered.data_ptr(), slice_bytes, stream=torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+assert gathered.cpu().numpy().reshape(world, slice_bytes).tolist() == [[r + 1] * slice_bytes for r in range(world)]
+
 single = vt.Accel(local).populate(scene)  # each rank checks what it holds against its own single-GPU run
 want_hits, want_attrs = single.traverse(rays, want_attrs=True)
 want_img, want_live = single.render_diffuse_wave(rays, spp, seed=9, weight=0.5)

@@ -82,6 +82,7 @@ SYMBOLS = {
     "vt_shard_geometry": (_i32, [_u64, _i32, _i32, _u64, _vp, _vp]),
     "vt_group_render_diffuse_wave": (_i32, [_vp, _vp, _u64, _u32, _u64, C.c_float, _vp, _vp, _u32, _vp]),
     "vt_group_reduce_device": (_i32, [_vp, _vp, _u64, _vp]),
+    "vt_group_all_gather_device": (_i32, [_vp, _vp, _u64, _vp]),
     "vt_group_launch_count": (_u64, [_vp]),
     "vt_last_error": (C.c_char_p, []),
 }
@@ -683,6 +684,9 @@ class Group:
         """Device-resident shard in, frame-sized device image out (complete on rank 0); enqueued on `stream`."""
         _check(self.L.vt_group_render_diffuse_wave(self.h, _ptr(d_rays_shard), n, spp, seed, weight, _ptr(d_fb), None,
                                                    abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)), "vt_group_render_diffuse_wave")
+
+    def all_gather_device(self, d_buf, bytes_per_rank, stream=None):
+        _check(self.L.vt_group_all_gather_device(self.h, _ptr(d_buf), bytes_per_rank, _ptr(stream)), "vt_group_all_gather_device")
 
     def reduce_device(self, d_buf, count, stream=None):
         _check(self.L.vt_group_reduce_device(self.h, _ptr(d_buf), count, _ptr(stream)), "vt_group_reduce_device")

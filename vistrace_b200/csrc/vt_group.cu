@@ -44,6 +44,7 @@ struct NcclApi {
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclBroadcast) Broadcast = nullptr;
     decltype(&ncclReduce) Reduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclGetVersion) GetVersion = nullptr;
     void *handle = nullptr;
@@ -69,6 +70,7 @@ struct NcclApi {
             VT_SYM(Recv);
             VT_SYM(Broadcast);
             VT_SYM(Reduce);
+            VT_SYM(AllGather);
             VT_SYM(GetErrorString);
             VT_SYM(GetVersion);
 #undef VT_SYM
@@ -678,6 +680,20 @@ public:
         mLaunches++;
     }
 
+    // every rank contributes bytes_per_rank bytes at buf + rank * bytes_per_rank; afterwards every rank holds all of buf.  What a
+    // sample-index-sharded frame does with its primary rays: each rank uploads 1 / N of them over its own PCIe link and the rest
+    // arrives over NVLink instead of every rank pulling the whole array through PCIe switches it shares with its neighbours.
+    void AllGatherDevice(void *buf, uint64_t bytes_per_rank, cudaStream_t stream) {
+        if (!mMultiProcess) throw std::runtime_error("vt_group_all_gather_device: multi-process groups only");
+        if (mWorld == 1 || bytes_per_rank == 0) return;
+        Member &m = *mMembers[0];
+        VT_CUDA(cudaSetDevice(m.device));
+        NcclApi &nccl = NcclApi::get();
+        if (!nccl.AllGather) throw std::runtime_error("ncclAllGather not found");
+        VT_NCCL(nccl.AllGather(static_cast<const char *>(buf) + (uint64_t)m.rank * bytes_per_rank, buf, bytes_per_rank, ncclUint8, m.comm, stream));
+        mLaunches++;
+    }
+
     ShardGeom Geom(uint64_t n, uint32_t rank) const {
         ShardGeom g;
         g.n = n, g.tile = FrameTile(), g.world = mWorld, g.rank = rank;
@@ -776,6 +792,14 @@ int vt_group_reduce_device(vt_group *g, float *buf, uint64_t count, void *stream
     VT_TRY
     if (!g) throw std::runtime_error("null argument");
     g->impl.ReduceDevice(buf, count, (cudaStream_t)stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_group_all_gather_device(vt_group *g, void *buf, uint64_t bytes_per_rank, void *stream) {
+    VT_TRY
+    if (!g) throw std::runtime_error("null argument");
+    g->impl.AllGatherDevice(buf, bytes_per_rank, (cudaStream_t)stream);
     return 0;
     VT_CATCH(1)
 }
