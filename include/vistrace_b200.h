@@ -574,7 +574,9 @@ int vt_shard_geometry(uint64_t n, int world, int rank, uint64_t tile, uint64_t *
 /* vt_accel_render_diffuse_wave over the group, STRONG scaling of one frame: every pixel is traced exactly once, by the rank
  * that owns its tile, and the image equals the single-GPU image bit for bit (the bounce rays' random-number counters come
  * from global pixel indices).  flags = 0: HOST rays[n] in, HOST RGBFFF framebuffer_rgb[3n] out (include/vistrace/IRenderTarget.h:40),
- * complete on return in a single-process group and on rank 0 of a multi-process group (other ranks receive their own tiles);
+ * complete on return in a single-process group and on rank 0 of a multi-process group (the other ranks' framebuffer is not
+ * written: their GPUs store finished pixels straight into rank 0's frame over NVLink — peer memory, CUDA IPC — which rank 0
+ * downloads stretch by stretch as the ranks deliver; VT_GROUP_GATHER=nccl: ncclSend / ncclRecv of the shards instead);
  * *live_out (nullable) = bounce rays spawned by THIS process's GPUs.
  * flags = VT_TRAVERSE_DEVICE_PTRS (multi-process groups): rays = this rank's COMPACT shard already resident on its GPU
  * (vt_group_shard: local_count records in tile order), framebuffer_rgb = frame-sized DEVICE image, complete on rank 0; everything

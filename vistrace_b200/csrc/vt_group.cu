@@ -10,8 +10,12 @@
 //                                            (cudaMemcpyPeer over NVLink).  No NCCL needed.
 //   * vt_group_create_rank(dev, r, w, id)    ONE process per GPU (torchrun / MPI launchers; bench.py --gpus N).  The processes
 //                                            share a 128-byte ncclUniqueId; the scene image is ncclBroadcast from rank 0 (the only
-//                                            rank that builds), hit-buffer slices / framebuffer shards are gathered on rank 0
-//                                            with grouped ncclSend / ncclRecv over NVLink.  NCCL is bound at run time (dlopen of
+//                                            rank that builds); hit-buffer slices are gathered on rank 0 with grouped ncclSend /
+//                                            ncclRecv over NVLink; FRAMES are delivered through peer memory: rank 0's frame is mapped
+//                                            into every rank (CUDA IPC) and each rank's K4 stores its finished pixels straight into it —
+//                                            the shading kernel IS the gather, flag words in rank 0's memory do the hand-shake, no
+//                                            collective kernel competes with the persistent traversal grids for SMs
+//                                            (VT_GROUP_GATHER=nccl selects the ncclSend / ncclRecv gather instead).  NCCL is bound at run time (dlopen of
 //                                            libnccl.so.2 — the copy PyTorch already loaded when there is one), so the library has
 //                                            no link-time dependency on it.
 //
@@ -151,6 +155,12 @@ public:
         DevBuf<vt_hit> hit_stage;
         DevBuf<vt_attr> attr_stage;
         DevBuf<unsigned char> header;
+        // peer-memory frame (multi-process groups): rank 0 owns `frame` = n x 12 bytes of RGBFFF pixels in GLOBAL pixel order + flag
+        // words; every other rank maps it over NVLink (CUDA IPC) and its K4 stores finished pixels straight into it
+        DevBuf<unsigned char> frame;
+        void *peer_frame = nullptr;
+        uint64_t frame_pixels = 0;
+        uint32_t step = 0;
         uint64_t live = 0;
         // worker thread (single-process groups with several GPUs)
         std::thread th;
@@ -165,6 +175,7 @@ private:
     std::vector<std::unique_ptr<Member>> mMembers;
     uint32_t mWorld = 1;
     bool mMultiProcess = false;
+    bool mPeerFrameUnavailable = false;  // CUDA IPC could not map rank 0's frame on some rank: every rank uses the NCCL gather instead
     uint64_t mLaunches = 0;
 
     static void worker_loop(Member *m) {
@@ -283,6 +294,8 @@ public:
             }
             cudaSetDevice(m.device);
             cudaDeviceSynchronize();
+            if (m.peer_frame && m.rank != 0) cudaIpcCloseMemHandle(m.peer_frame);
+            m.frame.release();
             if (m.comm) NcclApi::get().CommDestroy(m.comm);
             m.fb_local.release();
             m.fb_stage.release();
@@ -431,7 +444,8 @@ public:
     // schedule is computed from geometry `sched` (rank 0's, the longest shard) so that every rank cuts at the same tile indices.
     void member_render(Member &m, const ShardGeom &g, const vt_ray *rays, bool rays_on_device, uint32_t spp, uint64_t seed, float weight,
                        float *fb_host, bool count_live, cudaStream_t caller_stream, const ShardGeom *sched = nullptr,
-                       const std::function<void(uint64_t, uint64_t, cudaStream_t)> &after_chunk = nullptr) {
+                       const std::function<void(uint64_t, uint64_t, cudaStream_t)> &after_chunk = nullptr, float *frame_target = nullptr,
+                       const uint32_t *consumed_flag = nullptr, uint32_t step = 0) {
         AccelStruct &A = m.accel->impl;
         if (!A.Built()) throw std::runtime_error("vt_group: populate the group first");
         VT_CUDA(cudaSetDevice(m.device));
@@ -505,7 +519,7 @@ public:
             VT_CUDA(cudaMemsetAsync(c1, 0, 16, st));
             VT_CUDA(cudaMemsetAsync(l.queue_count.p, 0, sizeof(unsigned long long), st));
             float *d_fb = m.fb_local.p + cb * 3;
-            VT_CUDA(cudaMemsetAsync(d_fb, 0, mpix * 3 * sizeof(float), st));
+            if (!frame_target) VT_CUDA(cudaMemsetAsync(d_fb, 0, mpix * 3 * sizeof(float), st));
             const vt_ray *d_rays;
             if (rays_on_device) {
                 d_rays = rays + cb;
@@ -528,7 +542,16 @@ public:
             VT_CUDA(vt_launch_bounce_rays(l.attrs.p, mpix, spp, seed, 0, l.brays.p, count_live ? D.live.p : nullptr, st, l.queue.p, l.queue_count.p,
                                           l.bhits.p, &map));
             VT_CUDA(vt_launch_traverse(D.view, l.brays.p, l.bhits.p, mpix * spp, false, c1, cfg, st, false, l.queue.p, l.queue_count.p));
-            VT_CUDA(vt_launch_accumulate_sky(D.view, l.attrs.p, l.bhits.p, mpix, spp, weight, d_fb, st));
+            if (frame_target) {
+                // K4 delivers the shard: its stores go to the pixels' places in the frame on rank 0 (peer memory over NVLink for the
+                // other ranks) — no staging buffer, no collective kernel, no de-interleave.  The frame of the PREVIOUS step must have
+                // been consumed by rank 0 first (flag in rank 0's memory).
+                VT_CUDA(vt_launch_flag_wait(consumed_flag, 1, 1, step - 1, st));
+                VT_CUDA(vt_launch_accumulate_sky(D.view, l.attrs.p, l.bhits.p, mpix, spp, weight, frame_target, st, &map, true));
+                A.mLaunches += 1;
+            } else {
+                VT_CUDA(vt_launch_accumulate_sky(D.view, l.attrs.p, l.bhits.p, mpix, spp, weight, d_fb, st));
+            }
             A.mLaunches += 5;
             if (fb_host) copy_tiles(g, j0, j1, 3 * sizeof(float), m.fb_local.p, fb_host, true, cudaMemcpyDeviceToHost, st);
             if (after_chunk) after_chunk(s0, s1, st);
@@ -550,6 +573,110 @@ public:
         if (count_live && D.live.p) VT_CUDA(cudaMemcpyAsync(&v, D.live.p, sizeof(v), cudaMemcpyDeviceToHost, st));
         VT_CUDA(cudaStreamSynchronize(st));
         m.live = v;
+    }
+
+    static constexpr uint32_t kMaxChunks = 64;
+    static uint64_t frame_flag_offset(uint64_t pixels) { return (pixels * 12 + 255) / 256 * 256; }
+
+    // Collective: make rank 0's frame hold `pixels` pixels and map it into every other rank (CUDA IPC over NVLink).
+    void ensure_peer_frame(uint64_t pixels) {
+        Member &m = *mMembers[0];
+        if (m.peer_frame && pixels <= m.frame_pixels) return;
+        NcclApi &nccl = NcclApi::get();
+        VT_CUDA(cudaSetDevice(m.device));
+        VT_CUDA(cudaDeviceSynchronize());
+        if (m.peer_frame && m.rank != 0) VT_CUDA(cudaIpcCloseMemHandle(m.peer_frame));
+        m.peer_frame = nullptr;
+        m.header.ensure(256);
+        // nobody maps the old frame any more once everybody has passed this collective
+        VT_NCCL(nccl.Broadcast(m.header.p, m.header.p, 4, ncclUint8, 0, m.comm, m.stream));
+        VT_CUDA(cudaStreamSynchronize(m.stream));
+        cudaIpcMemHandle_t handle;
+        std::memset(&handle, 0, sizeof(handle));
+        const uint64_t bytes = frame_flag_offset(pixels) + ((uint64_t)mWorld * kMaxChunks + 64) * sizeof(uint32_t);
+        if (m.rank == 0) {
+            m.frame.release();
+            m.frame.ensure(bytes);
+            VT_CUDA(cudaMemset(m.frame.p, 0, bytes));
+            VT_CUDA(cudaIpcGetMemHandle(&handle, m.frame.p));
+            VT_CUDA(cudaMemcpy(m.header.p, &handle, sizeof(handle), cudaMemcpyHostToDevice));
+        }
+        static_assert(sizeof(handle) <= 256, "IPC handle fits the header buffer");
+        VT_NCCL(nccl.Broadcast(m.header.p, m.header.p, sizeof(handle), ncclUint8, 0, m.comm, m.stream));
+        VT_CUDA(cudaMemcpyAsync(&handle, m.header.p, sizeof(handle), cudaMemcpyDeviceToHost, m.stream));
+        VT_CUDA(cudaStreamSynchronize(m.stream));
+        unsigned char ok = 1;
+        if (m.rank == 0) {
+            m.peer_frame = m.frame.p;
+        } else if (cudaIpcOpenMemHandle(&m.peer_frame, handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            m.peer_frame = nullptr;
+            ok = 0;
+        }
+        // all ranks must agree before anybody waits on a flag a peer could never set: gather one status byte per rank
+        m.header.ensure(std::max<size_t>(256, mWorld));
+        VT_CUDA(cudaMemcpyAsync(m.header.p + m.rank, &ok, 1, cudaMemcpyHostToDevice, m.stream));
+        if (!nccl.AllGather) throw std::runtime_error("ncclAllGather not found");
+        VT_NCCL(nccl.AllGather(m.header.p + m.rank, m.header.p, 1, ncclUint8, m.comm, m.stream));
+        std::vector<unsigned char> all(mWorld, 0);
+        VT_CUDA(cudaMemcpyAsync(all.data(), m.header.p, mWorld, cudaMemcpyDeviceToHost, m.stream));
+        VT_CUDA(cudaStreamSynchronize(m.stream));
+        for (unsigned char v : all)
+            if (!v) mPeerFrameUnavailable = true;
+        if (mPeerFrameUnavailable) {
+            if (m.peer_frame && m.rank != 0) cudaIpcCloseMemHandle(m.peer_frame);
+            m.peer_frame = nullptr;
+            return;
+        }
+        m.frame_pixels = pixels;
+        m.step = 0;
+    }
+
+    // Multi-process frame through peer memory: every rank's K4 stores its finished pixels into rank 0's frame; flag words say which
+    // chunk of which rank has landed; rank 0 downloads (or hands over) each stretch of the frame as soon as all ranks have delivered it.
+    bool render_peer(Member &m, const ShardGeom &g0, const vt_ray *rays, bool dev_ptrs, uint32_t spp, uint64_t seed, float weight, float *fb,
+                     uint64_t *live_out, cudaStream_t stream) {
+        const ShardGeom g = g0.of(m.rank), sched = g0.of(0);
+        const bool root = m.rank == 0;
+        if (!mPeerFrameUnavailable) ensure_peer_frame(g0.n);
+        if (mPeerFrameUnavailable) return false;
+        const uint32_t step = ++m.step;
+        unsigned char *base = static_cast<unsigned char *>(m.peer_frame);
+        float *frame = reinterpret_cast<float *>(base);
+        uint32_t *flags = reinterpret_cast<uint32_t *>(base + frame_flag_offset(m.frame_pixels));
+        uint32_t *consumed = flags + (uint64_t)mWorld * kMaxChunks;
+        cudaStream_t st = dev_ptrs ? stream : m.stream;
+        uint32_t chunk = 0;
+        int ev = 0;
+        auto landed = [&](uint64_t s0, uint64_t s1, cudaStream_t lane) {
+            if (chunk >= kMaxChunks) throw std::runtime_error("vt_group: more than 64 chunks per shard (raise VT_WAVE_TILE)");
+            // this rank's tiles of the chunk are in the frame: say so (a rank without tiles in the chunk says so as well)
+            VT_CUDA(vt_launch_flag_set(flags + (uint64_t)m.rank * kMaxChunks + chunk, step, lane));
+            mLaunches++;
+            if (root) {
+                if (lane != st) {
+                    cudaEvent_t done = m.lane_done[ev++ % 8];
+                    VT_CUDA(cudaEventRecord(done, lane));
+                    VT_CUDA(cudaStreamWaitEvent(st, done, 0));
+                }
+                VT_CUDA(vt_launch_flag_wait(flags + chunk, mWorld, kMaxChunks, step, st));
+                mLaunches++;
+                // the chunk's tiles of ALL ranks are one contiguous stretch of the frame: global tiles [s0 * W, s1 * W)
+                const uint64_t p0 = std::min(g0.n, s0 * mWorld * g0.tile), p1 = std::min(g0.n, s1 * mWorld * g0.tile);
+                if (p1 > p0 && fb != frame)
+                    VT_CUDA(cudaMemcpyAsync(fb + p0 * 3, frame + p0 * 3, (p1 - p0) * 3 * sizeof(float), dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+            }
+            chunk++;
+        };
+        member_render(m, g, rays, dev_ptrs, spp, seed, weight, nullptr, live_out != nullptr, st, &sched, landed, frame, consumed, step);
+        if (root) {  // the frame may be overwritten by the next step once everything above has run
+            VT_CUDA(vt_launch_flag_set(consumed, step, st));
+            mLaunches++;
+        }
+        if (dev_ptrs) return true;
+        member_finish(m, live_out != nullptr, st);
+        if (live_out) *live_out = m.live;
+        return true;
     }
 
     // rays / fb: HOST frame arrays (flags = 0; a non-root process of a multi-process group only reads its own tiles of `rays`
@@ -584,6 +711,18 @@ public:
         if (root && !fb) throw std::runtime_error("vt_group_render_diffuse_wave: rank 0 needs the framebuffer");
         VT_CUDA(cudaSetDevice(m.device));
         cudaStream_t st = dev_ptrs ? stream : m.stream;
+        if (!dev_ptrs && mWorld > 1 && env_int("VT_GROUP_NO_GATHER", 0) != 0) {  // diagnosis only: every rank keeps its own tiles, nothing is gathered
+            member_render(m, g, rays, false, spp, seed, weight, fb, live_out != nullptr, st);
+            member_finish(m, live_out != nullptr, st);
+            if (live_out) *live_out = m.live;
+            return;
+        }
+        if (mWorld > 1) {
+            const char *gather = std::getenv("VT_GROUP_GATHER");
+            if (!(gather && std::string(gather) == "nccl")) {  // default: K4 stores into rank 0's frame over NVLink (peer memory)
+                if (render_peer(m, g0, rays, dev_ptrs, spp, seed, weight, fb, live_out, stream)) return;
+            }
+        }
         const bool pipelined = !dev_ptrs && mWorld > 1 && env_int("VT_GROUP_PIPELINE", 1) != 0;
         if (pipelined) {
             // host pointers, several ranks: every finished chunk is shipped at once — rank r sends its tiles of the chunk, rank 0

@@ -73,8 +73,15 @@ cudaError_t vt_launch_bsdf_diffuse_rays(const vt_ray *rays, const vt_attr *attrs
 cudaError_t vt_launch_pinhole_rays(const float *cam12, uint32_t width, uint32_t height, vt_ray *out, cudaStream_t stream);
 
 // K4 — fb[i] += weight * albedo_i * (escaped bounce rays of pixel i) / spp, RGBFFF framebuffer.
+// map (optional): pixel i of the batch is written to the GLOBAL pixel the shard map gives (VtSlotMap) — fb is then the frame, which
+// may live on another GPU (peer memory over NVLink); overwrite: store instead of accumulate (same value as += into a zeroed buffer).
 cudaError_t vt_launch_accumulate_sky(const VtSceneView &S, const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n,
-                                     uint32_t spp, float weight, float *fb, cudaStream_t stream);
+                                     uint32_t spp, float weight, float *fb, cudaStream_t stream, const VtSlotMap *map = nullptr,
+                                     bool overwrite = false);
+// Flag words for the cross-GPU hand-shake of the peer-memory frame: set after everything enqueued before on `stream`; wait until all
+// flags[k * stride], k < count, have reached `step` (wrap-around safe).
+cudaError_t vt_launch_flag_set(uint32_t *flag, uint32_t step, cudaStream_t stream);
+cudaError_t vt_launch_flag_wait(const uint32_t *flags, uint32_t count, uint32_t stride, uint32_t step, cudaStream_t stream);
 
 // Path shading between the waves of vt_accel_trace_paths: one thread per live vertex (queue-listed slots, or all n when queue is null).
 cudaError_t vt_launch_path_shade(const vt_attr *attrs, const vt_hit *shadow_hits, const uint32_t *queue, const unsigned long long *queue_count,

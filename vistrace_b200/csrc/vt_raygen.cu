@@ -261,9 +261,16 @@ k_pinhole_rays(const float *__restrict__ cam, uint32_t width, uint32_t height, v
 // multi-GPU path sums with ONE collective; it is harness-level shading, not part of accel:Traverse.
 __global__ void __launch_bounds__(256)
 k_accumulate_sky(const VtSceneView S, const vt_attr *__restrict__ attrs, const vt_hit *__restrict__ bounce_hits,
-                 unsigned long long n, uint32_t spp, float weight, float *__restrict__ fb) {
+                 unsigned long long n, uint32_t spp, float weight, float *__restrict__ fb, const VtSlotMap map, int overwrite) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // where pixel i lands: slot i of fb, or — a shard writing into the FRAME (multi-GPU, vt_group.cu) — its global pixel: the
+    // frame may be another GPU's memory mapped over NVLink, so the result of the shard is delivered by these very stores
+    unsigned long long o = i;
+    if (map.tile) {
+        const unsigned long long li = map.local_base + i;
+        o = ((li / map.tile) * map.stride + map.phase) * map.tile + li % map.tile;
+    }
     const float4 *a = reinterpret_cast<const float4 *>(attrs + i);
     const float4 q7 = __ldg(a + 7);
     const uint32_t flags = __float_as_uint(q7.z), prim = __float_as_uint(q7.w);
@@ -288,9 +295,36 @@ k_accumulate_sky(const VtSceneView S, const vt_attr *__restrict__ attrs, const v
             r = q5.x * vis, g = q5.y * vis, b = q5.z * vis;
         }
     }
-    fb[3 * i + 0] += weight * r;
-    fb[3 * i + 1] += weight * g;
-    fb[3 * i + 2] += weight * b;
+    if (overwrite) {
+        fb[3 * o + 0] = 0.f + weight * r;  // the value an accumulation into a zeroed buffer gives, bit for bit
+        fb[3 * o + 1] = 0.f + weight * g;
+        fb[3 * o + 2] = 0.f + weight * b;
+    } else {
+        fb[3 * o + 0] += weight * r;
+        fb[3 * o + 1] += weight * g;
+        fb[3 * o + 2] += weight * b;
+    }
+}
+
+// Cross-GPU hand-shake of the peer-memory frame (vt_group.cu): a flag word in the frame owner's memory carries the step number.
+// k_flag_set publishes "everything this stream did before is done" (the stores of the preceding kernels are complete at the kernel
+// boundary; the fences order the flag behind them system-wide); k_flag_wait holds a stream until all `count` flags reached `step`.
+__global__ void k_flag_set(volatile uint32_t *flag, uint32_t step) {
+    __threadfence_system();
+    *flag = step;
+    __threadfence_system();
+}
+__global__ void k_flag_wait(const volatile uint32_t *flags, uint32_t count, uint32_t stride, uint32_t step) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (uint32_t k = threadIdx.x; k < count; k += blockDim.x)
+        while ((int32_t)(flags[(size_t)k * stride] - step) < 0) {
+            __nanosleep(200);
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 20000000000ull) __trap();  // a peer died or never called the collective: fail loudly after 20 s instead of hanging the GPU
+        }
+    __threadfence_system();
 }
 
 // Path shading between two waves of vt_accel_trace_paths (harness-level, like K4: it exists so that a multi-bounce workload has
@@ -343,10 +377,22 @@ cudaError_t vt_launch_path_shade(const vt_attr *attrs, const vt_hit *shadow_hits
 }
 
 cudaError_t vt_launch_accumulate_sky(const VtSceneView &S, const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n,
-                                     uint32_t spp, float weight, float *fb, cudaStream_t stream) {
+                                     uint32_t spp, float weight, float *fb, cudaStream_t stream, const VtSlotMap *map, bool overwrite) {
     if (n == 0) return cudaSuccess;
     const unsigned block = 256;
-    k_accumulate_sky<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(S, attrs, bounce_hits, n, spp, weight, fb);
+    k_accumulate_sky<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(S, attrs, bounce_hits, n, spp, weight, fb, map ? *map : VtSlotMap(),
+                                                                               overwrite ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t vt_launch_flag_set(uint32_t *flag, uint32_t step, cudaStream_t stream) {
+    k_flag_set<<<1, 1, 0, stream>>>(flag, step);
+    return cudaGetLastError();
+}
+
+cudaError_t vt_launch_flag_wait(const uint32_t *flags, uint32_t count, uint32_t stride, uint32_t step, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    k_flag_wait<<<1, 32, 0, stream>>>(flags, count, stride, step);
     return cudaGetLastError();
 }
 
