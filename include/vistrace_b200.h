@@ -143,6 +143,45 @@ int vt_mdl_bind_matrices(const vt_mdl_files *files, float *out16); /* Model::Get
 int vt_mdl_material_index(const vt_mdl_files *files, uint32_t skin, uint32_t material_id, int32_t *index); /* Model::GetMaterialIdx */
 int vt_mdl_material_path(const vt_mdl_files *files, uint32_t material_id, uint32_t dir, char *out, uint64_t capacity); /* directory + name */
 
+/* Source-engine map ingestion, host only: .bsp (VBSP 19-21) -> the world triangles, materials and static-prop
+ * placements the reference's World object is built from.  Restates libs/BSPParser (FileFormat/Parser.cpp:11-73: which lumps a valid
+ * map carries; BSPParser.cpp:184-523 Triangulate: worldspawn faces, nodraw / skip / trigger dropped, polygons fanned from their first
+ * vertex, flat normals and tangent frames from the texture axes, UVs from the texture vectors; Displacements/ (all six files):
+ * displacement vertices, normals, tangent frames, UVs and the three smoothing passes across neighbouring displacements) and the
+ * world half of World::World (source/objects/AccelStruct.cpp:236-414: one material per distinct texture path in order of first use,
+ * every world triangle one-sided, entity 0).  The records equal BSPMap's arrays bit for bit.  Every offset, count and index is
+ * checked against the file: where the reference would read out of bounds the file is rejected. */
+typedef struct vt_bsp_info {
+    uint32_t version;              /* 19, 20 or 21 */
+    uint32_t n_materials;          /* distinct texture paths among the emitted triangles, in order of first use */
+    uint32_t n_texinfos;
+    uint32_t n_displacements;
+    uint32_t n_static_props;       /* BSPMap::GetNumStaticProps */
+    uint32_t static_props_version; /* 4, 5 or 6; 0 when the map has no static-prop lump */
+    uint64_t n_tris;               /* BSPMap::GetNumTris */
+} vt_bsp_info;
+typedef struct vt_bsp_material {
+    uint32_t surf_flags;   /* BSPTexture::flags (BSPEnums::SURF) of the texinfo that introduced the path -> vt_material.surf_flags */
+    int32_t texinfo;       /* that texinfo */
+    int32_t width, height; /* BSPTexture::width / height */
+    float reflectivity[3]; /* BSPTexture::reflectivity */
+    char path[260];        /* BSPTexture::path: the name World::World hands to Material() */
+} vt_bsp_material;
+typedef struct vt_bsp_static_prop {
+    float pos[3];   /* BSPStaticProp::pos */
+    float ang[3];   /* BSPStaticProp::ang (QAngle: pitch, yaw, roll) */
+    int32_t skin;   /* BSPStaticProp::skin */
+    char model[128]; /* BSPStaticProp::model: the .mdl path (vt_mdl_* ingests it) */
+} vt_bsp_static_prop;
+int vt_bsp_read_info(const uint8_t *file, uint64_t size, vt_bsp_info *info);
+/* BSPMap::GetVertices / GetNormals / GetTangents / GetUVs / GetAlphas as World::World packs them into Triangles: call with tris == NULL
+ * for the count; *n_tris = capacity in, count out.  tris[i].material indexes the material list (vt_bsp_get_material), ent_idx = 0,
+ * one_sided = 1.  binormals_or_null: 9 floats per triangle (GetBinormals: the reference computes them, Triangle does not keep them);
+ * texinfo_or_null: one int16 per triangle (GetTriTextures). */
+int vt_bsp_triangles(const uint8_t *file, uint64_t size, vt_tri_in *tris, float *binormals_or_null, int16_t *texinfo_or_null, uint64_t *n_tris);
+int vt_bsp_get_material(const uint8_t *file, uint64_t size, uint32_t material, vt_bsp_material *out); /* BSPMap::GetTexture of material's first texinfo */
+int vt_bsp_get_static_prop(const uint8_t *file, uint64_t size, uint32_t index, vt_bsp_static_prop *out); /* BSPMap::GetStaticProp */
+
 /* Material subset on the path (source/objects/Material.h:74-125).  Texture slots
  * are indices into the texture array, -1 = nullptr.  *_mat are glm::mat2x4 in
  * memory order: [0..3] = column 0 (drives u), [4..7] = column 1 (drives v)

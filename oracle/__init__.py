@@ -75,6 +75,12 @@ def _lib(kind):
         sig["mdl_bind_matrices"] = (None, [vp, vp])
         sig["mdl_material_index"] = (C.c_int32, [vp, C.c_int32, C.c_int32])
         sig["mdl_material_path"] = (C.c_int32, [vp, C.c_int32, C.c_int32, vp, u64])
+        sig["bsp_open"] = (vp, [vp, u64])
+        sig["bsp_close"] = (None, [vp])
+        sig["bsp_info"] = (None, [vp, vp])
+        sig["bsp_triangles"] = (None, [vp, vp, vp, vp])
+        sig["bsp_material"] = (C.c_int32, [vp, C.c_uint32, vp])
+        sig["bsp_static_prop"] = (C.c_int32, [vp, C.c_int32, vp])
     ns = type("ns", (), {})()
     for name, (res, args) in sig.items():
         fn = getattr(lib, pre + name)
@@ -289,3 +295,41 @@ class RefModel:
         buf = C.create_string_buffer(4200)
         self.lib.mdl_material_path(self.h, material_id, directory, buf, len(buf))
         return buf.value.decode("latin-1")
+
+
+class RefBsp:
+    """The reference's own BSPMap (libs/BSPParser: parse, Triangulate, displacement smoothing) over file bytes, plus the material
+    bookkeeping of World::World (source/objects/AccelStruct.cpp:236-414) — the checker of vt_bsp_*."""
+
+    def __init__(self, data):
+        self.lib = _lib("reference")
+        self._buf = np.frombuffer(bytes(data), np.uint8).copy()
+        self.h = self.lib.bsp_open(self._buf.ctypes.data if len(self._buf) else None, len(self._buf))
+        info = np.zeros(5, np.int64)
+        self.lib.bsp_info(self.h, info.ctypes.data)
+        self.valid, self.textures_ok = bool(info[0]), bool(info[1])
+        self.n_tris, self.n_materials, self.n_static_props = (int(v) for v in info[2:])
+
+    def close(self):
+        if self.h:
+            self.lib.bsp_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def triangles(self):
+        """(vt_tri_in records, binormals [n, 3, 3], texinfo indices [n])."""
+        n = self.n_tris if self.textures_ok else 0
+        tris, bino, texinfo = np.zeros(n, abi.TRI_IN), np.zeros((n, 3, 3), np.float32), np.zeros(n, np.int16)
+        if n:
+            self.lib.bsp_triangles(self.h, tris.ctypes.data, bino.ctypes.data, texinfo.ctypes.data)
+        return tris, bino, texinfo
+
+    def material(self, index):
+        out = np.zeros(1, abi.BSP_MATERIAL)
+        return out[0] if self.lib.bsp_material(self.h, index, out.ctypes.data) == 0 else None
+
+    def static_prop(self, index):
+        out = np.zeros(1, abi.BSP_STATIC_PROP)
+        return out[0] if self.lib.bsp_static_prop(self.h, index, out.ctypes.data) == 0 else None

@@ -15,6 +15,7 @@
 //   * VTFTexture(const uint8_t*, size_t)::Sample    libs/VTFParser/VTFParser.cpp:311-330
 //   * SampleBSDF + BSDFMaterial::PrepShadingData    source/libraries/BSDF.cpp:11-21,770-825 (diffuse lobe)
 //   * MDL / VVD / VTX parsers + BodyGroup / Mesh    libs/MDLParser/source/*.cpp, source/objects/Model.cpp:11-176
+//   * BSPMap (parse + Triangulate + displacements)  libs/BSPParser/BSPParser.cpp, Displacements/*.cpp
 // The ingestion paths (Lua, engine filesystem) are bypassed by filling the
 // private containers directly, which is why `private` is opened up below.
 #include <algorithm>
@@ -42,6 +43,7 @@
 
 #include "BSDF.h"
 #include "VTFParser.h"
+#include "BSPParser.h"
 #include "bvh/hierarchy_refitter.hpp"
 #include "bvh/leaf_collapser.hpp"
 #include "bvh/locally_ordered_clustering_builder.hpp"
@@ -666,5 +668,98 @@ int32_t vtref_mdl_material_path(void *h, int32_t material_id, int32_t dir, char 
     const std::string s = std::string(r->m->mMDL.GetMaterialDirectory(dir)) + r->m->mMDL.GetMaterialName(material_id);
     std::snprintf(out, cap, "%s", s.c_str());
     return (int32_t)s.size();
+}
+// ---------------------------------------------------------------- BSPMap (libs/BSPParser): the checker of vt_bsp_*
+// The world half of World::World (source/objects/AccelStruct.cpp:236-414) needs the engine (Material(), IMaterial); what it does with
+// the map is restated here statement by statement: texture of every triangle through BSPMap::GetTexture, one material per distinct
+// path in order of first use.
+namespace {
+struct RefBsp {
+    BSPMap *map = nullptr;
+    std::vector<uint32_t> tri_material;
+    std::vector<int16_t> material_texinfo;
+    bool textures_ok = true;
+    ~RefBsp() { delete map; }
+};
+}  // namespace
+void *vtref_bsp_open(const uint8_t *file, uint64_t size) {
+    auto *r = new RefBsp();
+    r->map = new BSPMap(file, size);
+    if (!r->map->IsValid()) return r;
+    std::unordered_map<std::string, size_t> ids;
+    const int16_t *textures = r->map->GetTriTextures();
+    for (size_t i = 0; i < r->map->GetNumTris(); i++) {
+        BSPTexture tex;
+        try {
+            tex = r->map->GetTexture(textures[i]);  // AccelStruct.cpp:243-249
+        } catch (const std::out_of_range &) {
+            r->textures_ok = false;
+            break;
+        }
+        const std::string path = tex.path;
+        if (ids.find(path) == ids.end()) {
+            ids.emplace(path, r->material_texinfo.size());
+            r->material_texinfo.push_back(textures[i]);
+        }
+        r->tri_material.push_back((uint32_t)ids[path]);
+    }
+    return r;
+}
+void vtref_bsp_close(void *h) { delete static_cast<RefBsp *>(h); }
+// out: {valid, textures resolvable, triangles, materials, static props}
+void vtref_bsp_info(void *h, int64_t *out5) {
+    auto *r = static_cast<RefBsp *>(h);
+    std::memset(out5, 0, 5 * sizeof(int64_t));
+    out5[0] = r->map->IsValid() ? 1 : 0;
+    if (!out5[0]) return;
+    out5[1] = r->textures_ok ? 1 : 0;
+    out5[2] = (int64_t)r->map->GetNumTris();
+    out5[3] = (int64_t)r->material_texinfo.size();
+    out5[4] = r->map->GetNumStaticProps();
+}
+// BSPMap's arrays packed the way World::World packs them into Triangles (AccelStruct.cpp:390-412): three vertices, normals, tangents,
+// uvs, alphas, material, one-sided; binormals (9 floats per triangle) and texinfo indices beside them
+void vtref_bsp_triangles(void *h, vt_tri_in *tris, float *binormals, int16_t *texinfo) {
+    auto *r = static_cast<RefBsp *>(h);
+    const BSPMap &m = *r->map;
+    const float *pos = reinterpret_cast<const float *>(m.GetVertices()), *nrm = reinterpret_cast<const float *>(m.GetNormals());
+    const float *tan = reinterpret_cast<const float *>(m.GetTangents()), *bin = reinterpret_cast<const float *>(m.GetBinormals());
+    const size_t n = r->textures_ok ? m.GetNumTris() : 0;
+    for (size_t i = 0; i < n; i++) {
+        vt_tri_in &o = tris[i];
+        std::memset(&o, 0, sizeof(o));
+        std::memcpy(o.p, pos + 9 * i, 36);
+        std::memcpy(o.normals, nrm + 9 * i, 36);
+        std::memcpy(o.tangents, tan + 9 * i, 36);
+        std::memcpy(o.uvs, m.GetUVs() + 6 * i, 24);
+        std::memcpy(o.alphas, m.GetAlphas() + 3 * i, 12);
+        o.material = r->tri_material[i], o.ent_idx = 0, o.one_sided = 1;
+        std::memcpy(binormals + 9 * i, bin + 9 * i, 36);
+        texinfo[i] = m.GetTriTextures()[i];
+    }
+}
+int32_t vtref_bsp_material(void *h, uint32_t material, vt_bsp_material *out) {
+    auto *r = static_cast<RefBsp *>(h);
+    if (material >= r->material_texinfo.size()) return -1;
+    const BSPTexture t = r->map->GetTexture(r->material_texinfo[material]);
+    std::memset(out, 0, sizeof(*out));
+    out->surf_flags = (uint32_t)t.flags, out->texinfo = r->material_texinfo[material], out->width = t.width, out->height = t.height;
+    out->reflectivity[0] = t.reflectivity.x, out->reflectivity[1] = t.reflectivity.y, out->reflectivity[2] = t.reflectivity.z;
+    std::snprintf(out->path, sizeof(out->path), "%s", t.path);
+    return 0;
+}
+int32_t vtref_bsp_static_prop(void *h, int32_t index, vt_bsp_static_prop *out) {
+    auto *r = static_cast<RefBsp *>(h);
+    try {
+        const BSPStaticProp p = r->map->GetStaticProp(index);
+        std::memset(out, 0, sizeof(*out));
+        out->pos[0] = p.pos.x, out->pos[1] = p.pos.y, out->pos[2] = p.pos.z;
+        out->ang[0] = p.ang.x, out->ang[1] = p.ang.y, out->ang[2] = p.ang.z;
+        out->skin = p.skin;
+        std::snprintf(out->model, sizeof(out->model), "%s", p.model);
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
 }
 } // extern "C"

@@ -44,6 +44,11 @@ TRI_IN = np.dtype(
     align=False,
 )
 TRI_SKIN = np.dtype([("num_bones", u1, 3), ("pad", u1), ("bone_ids", np.int8, (3, 3)), ("pad2", u1, 3), ("weights", f4, (3, 3))], align=False)
+# vt_bsp_info / vt_bsp_material / vt_bsp_static_prop (include/vistrace_b200.h)
+BSP_INFO = np.dtype([("version", np.uint32), ("n_materials", np.uint32), ("n_texinfos", np.uint32), ("n_displacements", np.uint32), ("n_static_props", np.uint32),
+                     ("static_props_version", np.uint32), ("n_tris", np.uint64)])
+BSP_MATERIAL = np.dtype([("surf_flags", np.uint32), ("texinfo", np.int32), ("width", np.int32), ("height", np.int32), ("reflectivity", f4, 3), ("path", "S260")])
+BSP_STATIC_PROP = np.dtype([("pos", f4, 3), ("ang", f4, 3), ("skin", np.int32), ("model", "S128")])
 ATTR = np.dtype(
     [
         ("pos", f4, 3),

@@ -58,6 +58,10 @@ SYMBOLS = {
     "vt_mdl_bind_matrices": (_i32, [_vp, _vp]),
     "vt_mdl_material_index": (_i32, [_vp, _u32, _u32, _vp]),
     "vt_mdl_material_path": (_i32, [_vp, _u32, _u32, _vp, _u64]),
+    "vt_bsp_read_info": (_i32, [_vp, _u64, _vp]),
+    "vt_bsp_triangles": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp]),
+    "vt_bsp_get_material": (_i32, [_vp, _u64, _u32, _vp]),
+    "vt_bsp_get_static_prop": (_i32, [_vp, _u64, _u32, _vp]),
     "vt_build_bvh_ploc": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "vt_build_quads": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_refit_quality": (_i32, [_vp, _vp, _vp]),
@@ -284,6 +288,40 @@ class MdlFiles:
         buf = C.create_string_buffer(4200)
         _check(self.L.vt_mdl_material_path(self._p(), material_id, directory, buf, len(buf)), "vt_mdl_material_path")
         return buf.value.decode("latin-1")
+
+
+class BspFile:
+    """A Source-engine map (bytes) behind vt_bsp_* (host-only ingestion, include/vistrace_b200.h)."""
+
+    def __init__(self, data):
+        self._buf = np.frombuffer(bytes(data), np.uint8).copy() if len(data) else np.zeros(0, np.uint8)
+        self.L = lib()
+
+    def _a(self):
+        return (self._buf.ctypes.data if len(self._buf) else None), len(self._buf)
+
+    def info(self):
+        out = np.zeros(1, abi.BSP_INFO)
+        _check(self.L.vt_bsp_read_info(*self._a(), out.ctypes.data), "vt_bsp_read_info")
+        return out[0]
+
+    def triangles(self):
+        """(vt_tri_in records of the world, binormals [n, 3, 3], texinfo index per triangle)."""
+        n = C.c_uint64(0)
+        _check(self.L.vt_bsp_triangles(*self._a(), None, None, None, C.addressof(n)), "vt_bsp_triangles")
+        tris, bino, texinfo = np.zeros(n.value, abi.TRI_IN), np.zeros((n.value, 3, 3), np.float32), np.zeros(n.value, np.int16)
+        _check(self.L.vt_bsp_triangles(*self._a(), tris.ctypes.data, bino.ctypes.data, texinfo.ctypes.data, C.addressof(n)), "vt_bsp_triangles")
+        return tris, bino, texinfo
+
+    def material(self, index):
+        out = np.zeros(1, abi.BSP_MATERIAL)
+        _check(self.L.vt_bsp_get_material(*self._a(), index, out.ctypes.data), "vt_bsp_get_material")
+        return out[0]
+
+    def static_prop(self, index):
+        out = np.zeros(1, abi.BSP_STATIC_PROP)
+        _check(self.L.vt_bsp_get_static_prop(*self._a(), index, out.ctypes.data), "vt_bsp_get_static_prop")
+        return out[0]
 
 
 def quad_plane_offset():

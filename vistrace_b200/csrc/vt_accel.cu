@@ -1754,6 +1754,38 @@ int vt_mdl_material_path(const vt_mdl_files *files, uint32_t material_id, uint32
     VT_CATCH(1)
 }
 
+int vt_bsp_read_info(const uint8_t *file, uint64_t size, vt_bsp_info *info) {
+    VT_TRY
+    if (!file || !info) throw std::runtime_error("null argument");
+    vt::BspInfo(file, size, info);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_bsp_triangles(const uint8_t *file, uint64_t size, vt_tri_in *tris, float *binormals_or_null, int16_t *texinfo_or_null, uint64_t *n_tris) {
+    VT_TRY
+    if (!file || !n_tris) throw std::runtime_error("null argument");
+    *n_tris = vt::BspTriangles(file, size, tris, binormals_or_null, texinfo_or_null, tris ? *n_tris : 0);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_bsp_get_material(const uint8_t *file, uint64_t size, uint32_t material, vt_bsp_material *out) {
+    VT_TRY
+    if (!file || !out) throw std::runtime_error("null argument");
+    vt::BspMaterial(file, size, material, out);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_bsp_get_static_prop(const uint8_t *file, uint64_t size, uint32_t index, vt_bsp_static_prop *out) {
+    VT_TRY
+    if (!file || !out) throw std::runtime_error("null argument");
+    vt::BspStaticProp(file, size, index, out);
+    return 0;
+    VT_CATCH(1)
+}
+
 uint32_t vt_quad_plane_offset(void) { return (uint32_t)VT_QUAD_OFFSET; }
 
 int vt_build_quads(const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices, uint64_t n_tris, void *quads_out,

@@ -130,6 +130,13 @@ void MdlBindMatrices(const vt_mdl_files *f, float *out16);
 int32_t MdlMaterialIndex(const vt_mdl_files *f, uint32_t skin, uint32_t material_id);
 std::string MdlMaterialPath(const vt_mdl_files *f, uint32_t material_id, uint32_t dir);
 
+// Source-engine map file -> world triangles, materials, static props (vt_bsp.cpp; libs/BSPParser + World::World restated).  Throw
+// std::runtime_error on malformed / unsupported files.
+void BspInfo(const uint8_t *file, uint64_t size, vt_bsp_info *info);
+uint64_t BspTriangles(const uint8_t *file, uint64_t size, vt_tri_in *tris, float *binormals, int16_t *texinfos, uint64_t capacity);
+void BspMaterial(const uint8_t *file, uint64_t size, uint32_t material, vt_bsp_material *out);
+void BspStaticProp(const uint8_t *file, uint64_t size, uint32_t index, vt_bsp_static_prop *out);
+
 struct DeviceScene;  // HBM-resident copy, vt_accel.cu
 
 // Eager TraceResult for one hit (source/objects/TraceResult.h:54-111): the batched path fills
