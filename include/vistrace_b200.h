@@ -362,6 +362,9 @@ int vt_accel_traverse(vt_accel *accel, const vt_ray *rays, uint64_t n, vt_hit *h
  * equal the reference's; on the compact layout steps is slightly larger (conservative boxes). */
 int vt_accel_traverse_stats(vt_accel *accel, const vt_ray *rays, uint64_t n, uint32_t flags,
                             uint64_t *steps, uint64_t *tests);
+/* The same per ray (quad / compact layouts): per_ray[i] = steps | tests << 16 of ray i, each saturating at 65535 — the length of
+ * the ray's dependent chain, which bounds the duration of small launches.  per_ray is a HOST array of n words. */
+int vt_accel_traverse_ray_stats(vt_accel *accel, const vt_ray *rays, uint64_t n, uint32_t flags, uint32_t *per_ray);
 
 /* Same with per-ray texture-LOD cones: cones = n x {coneWidth, coneAngle}, the 5th and 6th
  * arguments of accel:Traverse (source/objects/AccelStruct.cpp:795-803).  NULL = (-1, -1) = mip 0. */

@@ -145,3 +145,56 @@ def test_batched_sample_bsdf_diffuse_lobe_against_the_reference(vt, oracle_mod):
     ns = np.where((wo[spawned] * a2["normal"][spawned]).sum(-1) >= 0, 1.0, -1.0)[:, None] * a2["normal"][spawned]
     cos = (out["d"][spawned] * ns).sum(-1) / np.linalg.norm(out["d"][spawned], axis=1)
     assert abs(cos.mean() - 2.0 / 3.0) < 0.03
+
+
+def _two_engines(vt, scene, monkeypatch):
+    """The same scene and hierarchy with tail work-sharing off and on (VT_TAIL_SHARE is read when the engine is populated)."""
+    monkeypatch.setenv("VT_TAIL_SHARE", "0")
+    off = vt.Accel(0).populate(scene)
+    monkeypatch.setenv("VT_TAIL_SHARE", "1")
+    on = vt.Accel(0).populate(scene, bvh=off.get_bvh())
+    return off, on
+
+
+@pytest.mark.parametrize("scene_name", ["terrain", "foliage"])
+def test_tail_work_sharing_gives_the_unshared_answer(vt, scene_name, monkeypatch):
+    """K1's tail phase (idle lanes walk pending sub-trees of the warp's last rays, vt_traverse.cu) must not change a single byte:
+    with the canonical tie rule the closest hit does not depend on who walks which sub-tree.  Launch sizes that run dry at once,
+    sizes that are no multiple of the warp, waves with masked slots, grazing rays (the long chains the phase exists for)."""
+    from vistrace_b200 import abi, scenes
+
+    if scene_name == "terrain":
+        scene = scenes.scene_terrain_closed(300)
+        rays = scenes.pinhole_rays(640, 360, (0.0, -330.0, 200.0), (0.0, 0.0, 10.0))
+    else:
+        scene = scenes.scene_foliage(n_cards=30000, tex_size=64, ground_quads=16)
+        rays = scenes.pinhole_rays(480, 270, (0, -48, 20), (0, 0, 8))
+    off, on = _two_engines(vt, scene, monkeypatch)
+    assert on.layout == off.layout
+    hits, attrs = off.traverse(rays, want_attrs=True)
+    assert on.traverse(rays).tobytes() == hits.tobytes()
+    horizon = len(rays) * 3 // 4
+    for cnt in (1, 2, 31, 33, 100, 1000, 4097, 20001):
+        sub = np.ascontiguousarray(rays[horizon:horizon + cnt])
+        assert on.traverse(sub).tobytes() == off.traverse(sub).tobytes(), cnt
+    for seed in (1, 2):
+        brays, live = off.bounce_rays(attrs, 2, seed=seed)  # masked slots included
+        assert live > 0
+        a, b = off.traverse(brays), on.traverse(brays)
+        assert a.tobytes() == b.tobytes()
+        shadow = on.traverse(brays, any_hit=True)  # any-hit launches never share: same kernel either way
+        assert shadow.tobytes() == off.traverse(brays, any_hit=True).tobytes()
+    assert off.invalid_rays == on.invalid_rays == 0
+
+
+def test_per_ray_statistics_add_up(vt):
+    """vt_accel_traverse_ray_stats: the per-ray steps / tests sum to the totals of vt_accel_traverse_stats."""
+    from vistrace_b200 import scenes
+
+    scene = scenes.scene_terrain_closed(200)
+    rays = scenes.pinhole_rays(320, 180, (0.0, -330.0, 200.0), (0.0, 0.0, 10.0))
+    accel = vt.Accel(0).populate(scene)
+    steps, tests = accel.traverse_ray_stats(rays)
+    tot_steps, tot_tests = accel.traverse_stats(rays)
+    assert int(steps.sum()) == tot_steps and int(tests.sum()) == tot_tests
+    assert steps.max() > 2 * steps.mean()  # a few grazing rays are far longer than the rest: what bounds small launches

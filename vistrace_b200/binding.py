@@ -30,6 +30,7 @@ SYMBOLS = {
     "vt_accel_get_bvh": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "vt_accel_traverse": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_traverse_stats": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp]),
+    "vt_accel_traverse_ray_stats": (_i32, [_vp, _vp, _u64, _u32, _vp]),
     "vt_accel_traverse_cones": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_result": (_i32, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "vt_accel_bounce_rays": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _u32, _vp]),
@@ -453,6 +454,13 @@ class Accel:
             flags = abi.VT_TRAVERSE_DEVICE_PTRS
         _check(self.L.vt_accel_traverse_stats(self.h, _ptr(rays), n, flags, C.addressof(steps), C.addressof(tests)), "vt_accel_traverse_stats")
         return steps.value, tests.value
+
+    def traverse_ray_stats(self, rays):
+        """(steps, tests) per ray (quad / compact layouts), each saturating at 65535."""
+        rays = np.ascontiguousarray(rays, abi.RAY)
+        out = np.zeros(len(rays), np.uint32)
+        _check(self.L.vt_accel_traverse_ray_stats(self.h, rays.ctypes.data, len(rays), 0, out.ctypes.data), "vt_accel_traverse_ray_stats")
+        return out & 0xFFFF, out >> 16
 
     def traverse_device(self, d_rays, n, d_hits, d_attrs=None, any_hit=False, stream=None):
         """Device-pointer call (ints = CUDA device addresses): enqueues on `stream` and returns."""

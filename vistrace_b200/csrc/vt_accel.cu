@@ -276,6 +276,7 @@ void AccelStruct::Upload(const vt_scene &scene) {
     D.cfg.persistent = env_int("VT_PERSISTENT", 1);
     D.cfg.refill_threshold = env_int("VT_REFILL", D.cfg.refill_threshold);
     D.cfg.tri_threshold = env_int("VT_TRI_ROUND", D.cfg.tri_threshold);
+    D.cfg.tail_share = env_int("VT_TAIL_SHARE", D.cfg.tail_share);
     const size_t n = mTriangles.size();
 
     // Node layout (include/vistrace_b200.h: VT_LAYOUT_*).  A tree the quantised layouts cannot hold (a leaf of
@@ -542,6 +543,7 @@ void AccelStruct::AllocReplica(const ReplicaImage &img, void *bufs[10]) {
     D.cfg.persistent = env_int("VT_PERSISTENT", 1);
     D.cfg.refill_threshold = env_int("VT_REFILL", D.cfg.refill_threshold);
     D.cfg.tri_threshold = env_int("VT_TRI_ROUND", D.cfg.tri_threshold);
+    D.cfg.tail_share = env_int("VT_TAIL_SHARE", D.cfg.tail_share);
     int blocks = 0;
     VT_CUDA(vt_traverse_occupancy(&blocks, (size_t)V.n_smem_pairs * sizeof(VtPair), img.layout));
     if (blocks < 1) blocks = 1;
@@ -761,7 +763,7 @@ void AccelStruct::TraverseBatch(const vt_ray *rays, uint64_t n, vt_hit *hits, vt
     }
 }
 
-void AccelStruct::TraverseStats(const vt_ray *rays, uint64_t n, uint32_t flags, uint64_t *steps, uint64_t *tests) {
+void AccelStruct::TraverseStats(const vt_ray *rays, uint64_t n, uint32_t flags, uint64_t *steps, uint64_t *tests, uint32_t *per_ray) {
     check_built(mAccelBuilt);
     if (steps) *steps = 0;
     if (tests) *tests = 0;
@@ -771,8 +773,15 @@ void AccelStruct::TraverseStats(const vt_ray *rays, uint64_t n, uint32_t flags, 
     DeviceScene &D = *mpDevice;
     if (D.view.n_smem_pairs) throw std::runtime_error("traverse_stats: not available with VT_SMEM_PAIRS");
     cudaStream_t stream = D.own_stream;
-    D.stat_counters.ensure(4);
-    VT_CUDA(cudaMemsetAsync(D.stat_counters.p, 0, 4 * sizeof(unsigned long long), stream));
+    D.stat_counters.ensure(5);
+    VT_CUDA(cudaMemsetAsync(D.stat_counters.p, 0, 5 * sizeof(unsigned long long), stream));
+    if (per_ray) {  // per-ray records (quantised layouts): counters[4] carries the device address of the array
+        if (!D.view.quads && !D.view.cpairs) throw std::runtime_error("traverse_ray_stats: quad or compact layout only");
+        D.s_ray_stats.ensure(n);
+        VT_CUDA(cudaMemsetAsync(D.s_ray_stats.p, 0, n * sizeof(uint32_t), stream));
+        const unsigned long long addr = (unsigned long long)(uintptr_t)D.s_ray_stats.p;
+        VT_CUDA(cudaMemcpyAsync(D.stat_counters.p + 4, &addr, sizeof(addr), cudaMemcpyHostToDevice, stream));
+    }
     const vt_ray *d_rays = rays;
     D.s_hits.ensure(n);
     if (!(flags & VT_TRAVERSE_DEVICE_PTRS)) {
@@ -786,6 +795,7 @@ void AccelStruct::TraverseStats(const vt_ray *rays, uint64_t n, uint32_t flags, 
     mLaunches++;
     unsigned long long c[4];
     VT_CUDA(cudaMemcpyAsync(c, D.stat_counters.p, sizeof(c), cudaMemcpyDeviceToHost, stream));
+    if (per_ray) VT_CUDA(cudaMemcpyAsync(per_ray, D.s_ray_stats.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     VT_CUDA(cudaStreamSynchronize(stream));
     if (steps) *steps = c[2];
     if (tests) *tests = c[3];
@@ -1567,6 +1577,14 @@ int vt_accel_traverse_stats(vt_accel *a, const vt_ray *rays, uint64_t n, uint32_
     VT_TRY
     if (!a) throw std::runtime_error("null argument");
     a->impl.TraverseStats(rays, n, flags, steps, tests);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_traverse_ray_stats(vt_accel *a, const vt_ray *rays, uint64_t n, uint32_t flags, uint32_t *per_ray) {
+    VT_TRY
+    if (!a || !per_ray) throw std::runtime_error("null argument");
+    a->impl.TraverseStats(rays, n, flags, nullptr, nullptr, per_ray);
     return 0;
     VT_CATCH(1)
 }

@@ -76,6 +76,7 @@ struct DeviceScene {
     // staging for host-pointer calls
     DevBuf<vt_ray> s_rays;
     DevBuf<vt_hit> s_hits;
+    DevBuf<uint32_t> s_ray_stats;  // vt_accel_traverse_ray_stats
     DevBuf<vt_attr> s_attrs;
     DevBuf<float> s_cones;
     DevBuf<vt_bsdf_sample> s_samples;

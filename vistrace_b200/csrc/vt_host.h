@@ -235,7 +235,7 @@ public:
                        void *stream);
     // SingleRayTraverser::Statistics (single_ray_traverser.hpp:132-135,158-163) summed over the batch:
     // traversal steps (pair visits) and primitive intersections.  Synchronous, closest hit.
-    void TraverseStats(const vt_ray *rays, uint64_t n, uint32_t flags, uint64_t *steps, uint64_t *tests);
+    void TraverseStats(const vt_ray *rays, uint64_t n, uint32_t flags, uint64_t *steps, uint64_t *tests, uint32_t *per_ray = nullptr);
     void TraceResultBatch(const vt_ray *rays, const vt_hit *hits, uint64_t n, vt_attr *attrs, const float *cones,
                           uint32_t flags, void *stream);
 

@@ -27,6 +27,7 @@
 #include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 // Build-time knobs of the ALU-pipe diet (A/B builds: make EXTRA=-DVT_...=0); see the notes at slab_quad.
 #ifndef VT_SCHED2
@@ -44,6 +45,24 @@
 // wave; 64-entry rings 3.21) — the 9 KB of shared memory per CTA come out of the L1 that serves half of the node fetches.  Off.
 #ifndef VT_RAY_BATCH
 #define VT_RAY_BATCH 0
+#endif
+// Tail work-sharing (k_traverse_compact): lanes of a warp whose queue is dry help the warp's long rays once at most VT_SHARE_LANES
+// lanes still have work; the warp looks for new pairs every VT_SHARE_ROUNDS rounds.  VT_SHARE_GIVE=0 keeps the phase but never
+// hands work over (A/B, diagnosis).
+#ifndef VT_SHARE_LANES
+#define VT_SHARE_LANES 4
+#endif
+#ifndef VT_SHARE_ROUNDS
+#define VT_SHARE_ROUNDS 16
+#endif
+#ifndef VT_SHARE_REPS
+#define VT_SHARE_REPS 1
+#endif
+#ifndef VT_SHARE_GIVE
+#define VT_SHARE_GIVE 1
+#endif
+#ifndef VT_SHARE_DEBUG
+#define VT_SHARE_DEBUG 0
 #endif
 #ifndef VT_STACK_DIST
 #define VT_STACK_DIST 0  // measured: -7 % node visits / -22 % triangle tests on primary rays (+3 %), but -5.6 % on the bounce wave
@@ -97,7 +116,11 @@ VT_DEV float safe_inverse(float d) {
 
 // TriangleBackfaceCull::intersect — source/objects/Primitives.h:168-215.  Updates the ray's best
 // hit and tmax when the candidate is accepted (`t <= tmax`: a later equal-t candidate replaces).
-template <bool ALPHA>
+// CANON (quantised kernels): among candidates with EQUAL t the one with the larger original index wins, whatever the order they
+// are met in — the reference keeps the one it meets last (`t <= tmax` replaces), an order the quantised layouts do not promise
+// anyway (vt_device.h).  It makes the answer independent of the visit order, which the tail work-sharing below needs: the parts
+// of one ray that several lanes traverse can then be merged in any order.
+template <bool ALPHA, bool CANON = false>
 VT_DEV bool intersect_triangle(const VtSceneView &S, uint32_t slot, RayState &r) {
     float4 q0, q1, q2, q3;
 #if VT_TRI_ADDR_WIDE
@@ -124,6 +147,7 @@ VT_DEV bool intersect_triangle(const VtSceneView &S, uint32_t slot, RayState &r)
     if (u >= 0.f && v >= 0.f && w >= 0.f) {  // NaN-rejecting compares, tolerance 0 (:184-187)
         const float t = bvh_dot(n, c) * inv_det;
         if (t >= r.tmin && t <= r.tmax) {
+            if (CANON && t == r.tmax && r.prim != VT_MISS && __float_as_uint(q3.y) < r.prim) return false;
             if (ALPHA && (matflags & VT_TRI_FLAG_ALPHATEST)) {  // :195-208
                 const VtDevMaterial &m = S.mats[matflags >> 2];
                 const float *uv = S.tri_uv + (size_t)slot * 6;
@@ -215,6 +239,9 @@ VT_DEV void vt_prefetch_ref(const VtSceneView &S, uint32_t ref, bool quad) {
 #endif
 #ifndef VT_PREFETCH_FAR
 #define VT_PREFETCH_FAR 1
+#endif
+#ifndef VT_PREFETCH_ALL
+#define VT_PREFETCH_ALL 0  // every pushed child, not only the next one to be popped
 #endif
 #ifndef VT_LEAF_RUN_PER_ROUND
 #define VT_LEAF_RUN_PER_ROUND 1
@@ -626,7 +653,15 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
 // vt_device.h): a lane holds ONE tagged reference `cur` — an inner pair to step through, or a leaf run
 // whose remaining count and next slot are both encoded in it — leaves are ordered against inner siblings
 // by entry distance like any other child (ties: left first), and the far child of either kind is pushed.
-template <bool ANY_HIT, bool ALPHA, bool STATS, bool QUAD>
+//
+// TAIL WORK-SHARING (SHARE; closest hit only).  Once the ray queue is dry a launch is as long as its longest rays: measured on the
+// bench scene, 0.1 % of the primary rays (chains of 100 - 440 dependent rounds against a median of 24) hold the last 0.1 ms of
+// every launch — 40 % of a 262 k-ray launch, what one rank of an 8-GPU frame traces (profiles/r2_tail_sharing.md).  A ray's pending
+// sub-trees are independent, so in that phase an idle lane TAKES the nearest pending sub-tree of a lane that has one (with a copy of
+// the ray and its current tmax), walks it on its own stack, and hands its best candidate back; the owner keeps the closest (ties: the
+// canonical rule above) and writes the record when all its helpers have reported.  A helper may itself give work away; the count of
+// outstanding helpers is kept by the ray's owner.  Nothing changes while the queue still has rays: refills keep the lanes busy.
+template <bool ANY_HIT, bool ALPHA, bool STATS, bool QUAD, bool SHARE = false>
 __global__ void __launch_bounds__(VT_TRAVERSE_BLOCK, VT_COMPACT_MIN_BLOCKS)
 k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restrict__ hits, unsigned long long n,
                    unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold,
@@ -646,8 +681,15 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
     unsigned long long ray_idx = 0;
     RayState r;
     unsigned long long n_invalid = 0, n_steps = 0, n_tests = 0;
+    // STATS: optional per-ray record steps | tests << 16 (counters[4] holds the device address of a uint32 array, or 0)
+    uint32_t *per_ray = STATS ? reinterpret_cast<uint32_t *>(counters[4]) : nullptr;
+    uint32_t ray_steps = 0, ray_tests = 0;
     const uint32_t magic = (QUAD && VT_DECODE_HALF) ? S.magic_h : S.magic;
     bool warp_wild = false;  // warp-uniform: some lane holds a ray the one-fma plane form is not proven for (slab_quad)
+    constexpr bool TEAM = SHARE && !ANY_HIT && !STATS && !VT_RAY_BATCH;
+    int owner = -1;    // TEAM: >= 0 on a helper lane: the lane that owns the ray this lane walks a sub-tree of
+    int pending = 0;   // TEAM: on an owner lane: helpers that have not reported yet
+    bool last_tri = false;  // TEAM, warp-uniform: the kind of the previous round (tail phase: kinds alternate when both are wanted)
 
 #if VT_RAY_BATCH
     // prepared ray states of this warp: {o.xyz, tmin} {d.xyz, tmax} {inv.xyz, flags} {so.xyz, -} + the slot each belongs to
@@ -658,11 +700,32 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
 #endif
 
     for (;;) {
-        if (alive && cur == VT_REF_DONE) {
+        if (TEAM && exhausted) {
+            // helpers that have finished report to their owners (warp-uniform loop over the finished helpers)
+            unsigned fin = __ballot_sync(0xffffffffu, alive && owner >= 0 && cur == VT_REF_DONE);
+            while (fin) {
+                const int h = __ffs(fin) - 1;
+                fin &= fin - 1;
+                const int o = __shfl_sync(0xffffffffu, owner, h);
+                const float ht = __shfl_sync(0xffffffffu, r.tmax, h), hu = __shfl_sync(0xffffffffu, r.u, h), hv = __shfl_sync(0xffffffffu, r.v, h);
+                const uint32_t hp = __shfl_sync(0xffffffffu, r.prim, h);
+                if ((int)lane == o) {
+                    pending--;
+                    if (hp != VT_MISS && (ht < r.tmax || (ht == r.tmax && (r.prim == VT_MISS || hp > r.prim)))) r.tmax = ht, r.u = hu, r.v = hv, r.prim = hp;
+                }
+                if ((int)lane == h) alive = false, owner = -1;
+            }
+        }
+        if (alive && cur == VT_REF_DONE && (!TEAM || pending == 0)) {
+            if (VT_SHARE_DEBUG && TEAM && owner >= 0) atomicAdd(&counters[1], 1ull << 32);
+            if (VT_SHARE_DEBUG && TEAM && pending < 0) atomicAdd(&counters[1], 1ull << 40);
             write_hit(hits, ray_idx, r);
+            if (STATS && per_ray) per_ray[ray_idx] = min(ray_steps, 0xFFFFu) | (min(ray_tests, 0xFFFFu) << 16);
+            ray_steps = ray_tests = 0;
             alive = false;
         }
         const unsigned idle = __ballot_sync(0xffffffffu, !alive);
+        int round_budget = 0x7FFFFFFF;  // TEAM, tail phase: rounds before the warp looks for idle lanes again
 #if VT_RAY_BATCH
         if (idle == 0xffffffffu && exhausted && buf_pos == buf_cnt) break;
         if (idle && !(exhausted && buf_pos == buf_cnt) && __popc(idle) >= 32 - refill_threshold) {
@@ -767,10 +830,68 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
             // sticky for this warp's share of the launch: such rays are pathological input, the flag only has to be right, not tight
             if (__any_sync(0xffffffffu, fresh_wild)) warp_wild = true;
         }
-        const int keep = exhausted ? 0 : refill_threshold;
+        int keep = exhausted ? 0 : refill_threshold;
+        bool tail = false;  // warp-uniform: the queue is dry and few lanes still have work — the phase in which lanes share
+        if (TEAM && exhausted) {
+            tail = __popc(__ballot_sync(0xffffffffu, alive && owner < 0)) <= VT_SHARE_LANES;  // rays still in flight (helpers not counted)
+            if (!tail) keep = VT_SHARE_LANES;  // ordinary rounds until only the long rays are left
+        }
+        if (TEAM && tail) {
+            // idle lanes take the nearest pending sub-tree of lanes that have one: the k-th idle lane from the k-th such lane; repeated
+            // (VT_SHARE_REPS) so that a lone long ray with several pending sub-trees gets several helpers at once
+            for (int rep = 0; rep < VT_SHARE_REPS; rep++) {
+            const bool can_give = VT_SHARE_GIVE && alive && cur != VT_REF_DONE && sp != stack;
+            const unsigned givers = __ballot_sync(0xffffffffu, can_give);
+            // NOT `idle` from above: in the iteration in which the queue runs dry some of those lanes have just been refilled, and a
+            // giver whose partner does not take would drop the sub-tree it popped
+            const unsigned takers = __ballot_sync(0xffffffffu, !alive);
+            const int n_pairs = min(__popc(givers), __popc(takers));
+            if (n_pairs == 0) break;
+            {
+                const int my_rank = __popc((alive ? givers : takers) & lt_mask);
+                const bool gives = can_give && my_rank < n_pairs, takes = !alive && my_rank < n_pairs;
+                uint32_t given = VT_REF_DONE;
+                if (gives) given = stack_pop<DIST>(sp, stack, r.tmax);
+                const int src = takes ? (int)__fns(givers, 0, my_rank + 1) : (int)lane;
+                const uint32_t ref_in = __shfl_sync(0xffffffffu, given, src);
+                const int root_in = __shfl_sync(0xffffffffu, owner >= 0 ? owner : (int)lane, src);
+                const float ox = __shfl_sync(0xffffffffu, r.o.x, src), oy = __shfl_sync(0xffffffffu, r.o.y, src), oz = __shfl_sync(0xffffffffu, r.o.z, src);
+                const float dx = __shfl_sync(0xffffffffu, r.d.x, src), dy = __shfl_sync(0xffffffffu, r.d.y, src), dz = __shfl_sync(0xffffffffu, r.d.z, src);
+                const float ix = __shfl_sync(0xffffffffu, r.inv.x, src), iy = __shfl_sync(0xffffffffu, r.inv.y, src), iz = __shfl_sync(0xffffffffu, r.inv.z, src);
+                const float sx = __shfl_sync(0xffffffffu, r.so.x, src), sy = __shfl_sync(0xffffffffu, r.so.y, src), sz = __shfl_sync(0xffffffffu, r.so.z, src);
+                const float tmn = __shfl_sync(0xffffffffu, r.tmin, src), tmx = __shfl_sync(0xffffffffu, r.tmax, src);
+                if (takes && ref_in != VT_REF_DONE) {  // DONE: the giver's entry was discarded by the distance test of its stack
+                    r.o = mk3(ox, oy, oz), r.d = mk3(dx, dy, dz), r.inv = mk3(ix, iy, iz), r.so = mk3(sx, sy, sz);
+                    r.tmin = tmn, r.tmax = tmx;
+                    r.u = r.v = 0.f;
+                    r.prim = VT_MISS;
+                    cur = ref_in;
+                    sp = stack;
+                    alive = true;
+                    owner = root_in;
+                }
+                // the owners count their new helpers
+                unsigned joined = __ballot_sync(0xffffffffu, takes && ref_in != VT_REF_DONE);
+                while (joined) {
+                    const int t = __ffs(joined) - 1;
+                    joined &= joined - 1;
+                    if (__shfl_sync(0xffffffffu, owner, t) == (int)lane) pending++;
+                }
+            }
+            }
+            // back here as soon as a lane runs out of work, and after a few rounds while lanes are idle (new sub-trees appear on the stacks)
+            const unsigned working = __ballot_sync(0xffffffffu, alive && cur != VT_REF_DONE);
+            keep = max(0, __popc(working) - 1);
+            if (working != 0xffffffffu) round_budget = VT_SHARE_ROUNDS;
+        }
 #endif
 
+        // the rounds, until too few lanes have work left; instantiated twice so that the bookkeeping of the tail phase (round budget,
+        // alternating round kinds) costs nothing while the queue still has rays
+        auto run_rounds = [&](auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
         for (;;) {
+            if (TAIL && round_budget-- <= 0) break;
 #if VT_SCHED2
             // one compare per class: inner references are < 2^28, VT_REF_DONE is the only value that is neither
             const bool has = cur != VT_REF_DONE;
@@ -787,7 +908,12 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
             const unsigned want_node = __ballot_sync(0xffffffffu, has && !is_leaf);
             if (__popc(want_tri | want_node) <= keep) break;
 #endif
-            if (want_tri && (want_node == 0 || __popc(want_tri) >= tri_threshold)) {
+            bool tri_round = want_tri && (want_node == 0 || __popc(want_tri) >= tri_threshold);
+            if (TAIL) {  // few lanes, idle issue slots: nobody waits longer than one round for its kind
+                tri_round = want_tri && (want_node == 0 || !last_tri);
+                last_tri = tri_round;
+            }
+            if (tri_round) {
                 if (is_leaf) {
                     // the whole leaf run in one round, in order (tmax shrinks between candidates exactly as in
                     // intersect_leaf, single_ray_traverser.hpp:41-63); the run is contiguous, so after the first
@@ -795,8 +921,8 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
 #if VT_LEAF_RUN_PER_ROUND
                     bool any = false;
                     for (;;) {
-                        if (STATS) n_tests++;
-                        any |= intersect_triangle<ALPHA>(S, cur & VT_REF_MASK, r);
+                        if (STATS) n_tests++, ray_tests++;
+                        any |= intersect_triangle<ALPHA, !ANY_HIT>(S, cur & VT_REF_MASK, r);
                         if ((ANY_HIT && any) || (cur >> VT_REF_SHIFT) == 1u) break;
                         cur -= VT_REF_MASK;  // count - 1, slot + 1
                     }
@@ -808,7 +934,7 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                     }
 #else
                     if (STATS) n_tests++;
-                    const bool hit = intersect_triangle<ALPHA>(S, cur & VT_REF_MASK, r);
+                    const bool hit = intersect_triangle<ALPHA, !ANY_HIT>(S, cur & VT_REF_MASK, r);
                     if (ANY_HIT && hit) {
                         cur = VT_REF_DONE;
                         sp = stack;
@@ -820,15 +946,21 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
 #endif
                 }
             } else if (has && !is_leaf) {
-                if (STATS) n_steps++;
+                if (STATS) n_steps++, ray_steps++;
                 if (QUAD) {
                     int k[4];
                     uint32_t cr[4];
                     if (warp_wild) slab_quad<true>(S.quads, cur, magic, r, k, cr);
                     else slab_quad<false>(S.quads, cur, magic, r, k, cr);
                     // farthest first, so the nearest pending child is popped first
-                    if (k[3] != 0x7FFFFFFF) stack_push<DIST>(sp, cr[3], (uint32_t)k[3]);
-                    if (k[2] != 0x7FFFFFFF) stack_push<DIST>(sp, cr[2], (uint32_t)k[2]);
+                    if (k[3] != 0x7FFFFFFF) {
+                        stack_push<DIST>(sp, cr[3], (uint32_t)k[3]);
+                        if (VT_PREFETCH_ALL) vt_prefetch_ref(S, cr[3], true);
+                    }
+                    if (k[2] != 0x7FFFFFFF) {
+                        stack_push<DIST>(sp, cr[2], (uint32_t)k[2]);
+                        if (VT_PREFETCH_ALL) vt_prefetch_ref(S, cr[2], true);
+                    }
                     if (k[1] != 0x7FFFFFFF) {
                         stack_push<DIST>(sp, cr[1], (uint32_t)k[1]);
                         if (VT_PREFETCH_FAR) vt_prefetch_ref(S, cr[1], true);  // the next one to be popped
@@ -856,6 +988,9 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                 }
             }
         }
+        };
+        if (TEAM && tail) run_rounds(std::true_type{});
+        else run_rounds(std::false_type{});
     }
     if (n_invalid) atomicAdd(&counters[1], n_invalid);
     if (STATS) {
@@ -896,6 +1031,7 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
             return alpha ? launch(k_traverse_compact<false, true, true, true>) : launch(k_traverse_compact<false, false, true, true>);
         }
         if (any_hit) return alpha ? launch(k_traverse_compact<true, true, false, true>) : launch(k_traverse_compact<true, false, false, true>);
+        if (cfg.tail_share) return alpha ? launch(k_traverse_compact<false, true, false, true, true>) : launch(k_traverse_compact<false, false, false, true, true>);
         return alpha ? launch(k_traverse_compact<false, true, false, true>) : launch(k_traverse_compact<false, false, false, true>);
     }
     if (S.cpairs) {
@@ -904,6 +1040,7 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
             return alpha ? launch(k_traverse_compact<false, true, true, false>) : launch(k_traverse_compact<false, false, true, false>);
         }
         if (any_hit) return alpha ? launch(k_traverse_compact<true, true, false, false>) : launch(k_traverse_compact<true, false, false, false>);
+        if (cfg.tail_share) return alpha ? launch(k_traverse_compact<false, true, false, false, true>) : launch(k_traverse_compact<false, false, false, false, true>);
         return alpha ? launch(k_traverse_compact<false, true, false, false>) : launch(k_traverse_compact<false, false, false, false>);
     }
     if (stats) {
