@@ -539,13 +539,30 @@ def run_ours(args):
         def e2e_step(it):
             return accel.render_diffuse_wave(h_rays, SPP, seed=seed0 + it, weight=1.0, out=h_fb)[1]
     else:
-        e2e_call = ("vt_group_render_diffuse_wave (one process per GPU): each rank uploads the host rays of its own tiles, traces them, "
-                    "framebuffer shards gathered on rank 0 over NVLink (ncclSend/ncclRecv), rank 0 downloads the frame")
+        # the host frame is ONE buffer shared by the processes of the node (POSIX shm, pinned by each): every rank's GPU lands its own
+        # tiles through its own PCIe link, a one-byte ncclAllGather is the barrier; VT_BENCH_E2E_GATHER=1 measures the round-2 path
+        # instead (finished pixels stored into rank 0's device frame over NVLink, rank 0 downloads the whole image through one link)
+        shared_frame = None
+        if os.environ.get("VT_BENCH_E2E_GATHER", "0") == "0":
+            name = f"vt_bench_frame_{os.environ.get('MASTER_PORT', '0')}"
+            if rank == 0:
+                shared_frame = shard.SharedPinnedFrame(name, n * 12, create=True)
+            dist.barrier()
+            if rank != 0:
+                shared_frame = shard.SharedPinnedFrame(name, n * 12, create=False)
+            h_fb = shared_frame.array(np.float32, (n, 3))
+            e2e_call = ("vt_group_render_diffuse_wave(VT_GROUP_SHARED_HOST_FRAME), one process per GPU: each rank uploads the host rays of its own "
+                        "tiles, traces them and lands its tiles of the RGBFFF frame in host memory shared by all ranks (its own PCIe link); "
+                        "complete on every rank after a one-byte ncclAllGather")
+            d2h_step = len(idx) * 12
+        else:
+            e2e_call = ("vt_group_render_diffuse_wave (one process per GPU): each rank uploads the host rays of its own tiles, traces them, "
+                        "finished pixels stored into rank 0's frame over NVLink (peer memory), rank 0 downloads the frame")
+            d2h_step = n * 12 if rank == 0 else 0                # rank 0 lands the whole image
         h2d_step = len(idx) * 32                                 # this rank's tiles (max over ranks reported below)
-        d2h_step = n * 12 if rank == 0 else len(idx) * 12        # rank 0 lands the whole image
 
         def e2e_step(it):
-            return group.render_diffuse_wave(h_rays, SPP, seed=seed0 + it, weight=1.0, out=h_fb, want_live=False)[1]
+            return group.render_diffuse_wave(h_rays, SPP, seed=seed0 + it, weight=1.0, out=h_fb, want_live=False, shared_frame=shared_frame is not None)[1]
     for it in range(min(2, warmup)):
         e2e_step(it)
     sync_all()
@@ -558,9 +575,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
     launches += launch_count() - l0
+    if world > 1 and shared_frame is not None:
+        sync_all()
+        shared_frame.close()
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = rays_per_step / (e2e_s / e2e_steps) / 1e6
-    h2d_step, d2h_step = int(max_over_ranks(h2d_step)), int(max_over_ranks(d2h_step))
+    h2d_step, d2h_step = sum_over_ranks(h2d_step), sum_over_ranks(d2h_step)  # whole job, like `value`: bytes all ranks move per step
 
     # ------------------------------------------------------------------ side fields
     weak = None

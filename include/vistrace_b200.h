@@ -622,7 +622,12 @@ int vt_shard_geometry(uint64_t n, int world, int rank, uint64_t tile, uint64_t *
  * *live_out (nullable) = bounce rays spawned by THIS process's GPUs.
  * flags = VT_TRAVERSE_DEVICE_PTRS (multi-process groups): rays = this rank's COMPACT shard already resident on its GPU
  * (vt_group_shard: local_count records in tile order), framebuffer_rgb = frame-sized DEVICE image, complete on rank 0; everything
- * is enqueued on `stream` and the call returns without synchronising; live_out must be NULL. */
+ * is enqueued on `stream` and the call returns without synchronising; live_out must be NULL.
+ * flags = VT_GROUP_SHARED_HOST_FRAME (multi-process groups on one node, host pointers): framebuffer_rgb is the SAME host memory in
+ * every process — a shared mapping (POSIX shm) that each process pinned (cudaHostRegister) — e.g. the RGBFFF render target of the
+ * process that displays it.  Every rank lands its own tiles through its own PCIe link; nothing crosses NVLink, nothing funnels through
+ * rank 0's link; a one-byte ncclAllGather behind the copies makes the frame complete on EVERY rank's return. */
+#define VT_GROUP_SHARED_HOST_FRAME 16u
 int vt_group_render_diffuse_wave(vt_group *group, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight,
                                  float *framebuffer_rgb, uint64_t *live_out, uint32_t flags, void *stream);
 

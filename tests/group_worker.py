@@ -40,6 +40,26 @@ del os.environ["VT_GROUP_GATHER"]
 if rank == 0:
     np.testing.assert_array_equal(img_nccl, img)
 
+# one host frame shared by all processes (POSIX shm, pinned by each): every rank lands its own tiles, complete on every rank
+from vistrace_b200 import shard  # noqa: E402
+frame = shard.SharedPinnedFrame(f"vt_test_frame_{os.environ.get('MASTER_PORT', '0')}", n * 12, create=(rank == 0)) if rank == 0 else None
+dist.barrier()
+if rank != 0:
+    frame = shard.SharedPinnedFrame(f"vt_test_frame_{os.environ.get('MASTER_PORT', '0')}", n * 12, create=False)
+shared = frame.array(np.float32, (n, 3))
+want = torch.from_numpy(img if rank == 0 else np.zeros((n, 3), np.float32)).to(dev)
+dist.broadcast(want, src=0)  # rank 0's gathered image: what the shared frame must hold on EVERY rank when the call returns
+want = want.cpu().numpy()
+for it in range(3):
+    if rank == 0:
+        shared[:] = -1.0
+    dist.barrier()
+    group.render_diffuse_wave(rays, spp, seed=9, weight=0.5, out=shared, want_live=False, shared_frame=True)
+    np.testing.assert_array_equal(shared, want)
+    dist.barrier()
+dist.barrier()
+frame.close()
+
 # device-resident shards -> frame-sized device image on rank 0
 idx = group.shard_indices(n)
 d_rays = torch.from_numpy(np.ascontiguousarray(rays[idx]).view(np.uint8).reshape(-1).copy()).to(dev)

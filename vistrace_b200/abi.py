@@ -20,6 +20,7 @@ VT_ATTR_HIT_WATER = 4
 VT_TRAVERSE_DEVICE_PTRS = 1
 VT_TRAVERSE_ANY_HIT = 2
 VT_TRAVERSE_QUEUE_ATTRS = 4
+VT_GROUP_SHARED_HOST_FRAME = 16
 VT_PATHS_NO_COMPACTION = 8
 VT_LOBE_NONE, VT_LOBE_DIFFUSE_REFLECTION = 0, 1
 

@@ -717,13 +717,15 @@ class Group:
                "vt_group_traverse")
         return (hits, attrs) if want_attrs else hits
 
-    def render_diffuse_wave(self, rays, spp, seed=0, weight=1.0, out=None, want_live=True):
-        """Host rays (frame-sized array) in, host RGBFFF framebuffer out; returns (framebuffer, bounce rays spawned by this process)."""
+    def render_diffuse_wave(self, rays, spp, seed=0, weight=1.0, out=None, want_live=True, shared_frame=False):
+        """Host rays (frame-sized array) in, host RGBFFF framebuffer out; returns (framebuffer, bounce rays spawned by this process).
+        shared_frame: `out` is the same pinned host memory in every process of the group (VT_GROUP_SHARED_HOST_FRAME)."""
         rays = rays if isinstance(rays, np.ndarray) and rays.dtype == abi.RAY and rays.flags.c_contiguous else np.ascontiguousarray(rays, abi.RAY)
         fb = np.zeros((len(rays), 3), np.float32) if out is None else out
         live = C.c_uint64(0)
         _check(self.L.vt_group_render_diffuse_wave(self.h, rays.ctypes.data, len(rays), spp, seed, weight, fb.ctypes.data,
-                                                   C.addressof(live) if want_live else None, 0, None), "vt_group_render_diffuse_wave")
+                                                   C.addressof(live) if want_live else None, abi.VT_GROUP_SHARED_HOST_FRAME if shared_frame else 0, None),
+               "vt_group_render_diffuse_wave")
         return fb, live.value
 
     def render_diffuse_wave_device(self, d_rays_shard, n, spp, seed, weight, d_fb, stream=None):

@@ -717,6 +717,23 @@ public:
             if (live_out) *live_out = m.live;
             return;
         }
+        if (!dev_ptrs && (flags & VT_GROUP_SHARED_HOST_FRAME)) {
+            // `fb` is the SAME host memory in every process (a shared mapping, pinned by each): every rank lands its own tiles over its
+            // own PCIe link — no gather at all, N links instead of rank 0's one — and a one-byte ncclAllGather behind the copies is the
+            // barrier that tells every rank the frame is complete
+            if (!fb) throw std::runtime_error("vt_group_render_diffuse_wave: the shared framebuffer must not be null");
+            member_render(m, g, rays, false, spp, seed, weight, fb, live_out != nullptr, st);
+            if (mWorld > 1) {
+                NcclApi &nccl = NcclApi::get();
+                if (!nccl.AllGather) throw std::runtime_error("ncclAllGather not found");
+                m.header.ensure(std::max<size_t>(256, mWorld));
+                VT_NCCL(nccl.AllGather(m.header.p + m.rank, m.header.p, 1, ncclUint8, m.comm, st));
+                mLaunches++;
+            }
+            member_finish(m, live_out != nullptr, st);
+            if (live_out) *live_out = m.live;
+            return;
+        }
         if (mWorld > 1) {
             const char *gather = std::getenv("VT_GROUP_GATHER");
             if (!(gather && std::string(gather) == "nccl")) {  // default: K4 stores into rank 0's frame over NVLink (peer memory)

@@ -143,3 +143,33 @@ def bind_to_gpu_numa_node(local_rank):
         return node
     except (OSError, ValueError, AttributeError, RuntimeError):
         return None
+
+
+class SharedPinnedFrame:
+    """One host buffer mapped into every process of a one-node job (POSIX shared memory) and pinned by each of them
+    (cudaHostRegister): the landing frame of vt_group_render_diffuse_wave(..., VT_GROUP_SHARED_HOST_FRAME) — every rank's GPU
+    writes its own tiles into it through its own PCIe link.  `create` on exactly one process, before the others open it."""
+
+    def __init__(self, name, nbytes, create):
+        self.path = os.path.join("/dev/shm", name)
+        self.nbytes = int(nbytes)
+        self.owner = bool(create)
+        if create:
+            with open(self.path, "wb") as f:
+                f.truncate(self.nbytes)
+        self.map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.nbytes,))
+        rc = torch.cuda.cudart().cudaHostRegister(self.map.ctypes.data, self.nbytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister of the shared frame failed: {rc}")
+        self.registered = True
+
+    def array(self, dtype, shape):
+        return self.map.view(dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "registered", False):
+            torch.cuda.cudart().cudaHostUnregister(self.map.ctypes.data)
+            self.registered = False
+        if self.owner and os.path.exists(self.path):
+            os.unlink(self.path)
+            self.owner = False
