@@ -77,35 +77,42 @@ typedef struct vt_tri_skin {
     float weights[3][3];    /* Triangle::weights */
 } vt_tri_skin;
 
-/* Texture: decoded RGBA8888 mip chain exactly as VTFTexture keeps it in memory,
- * i.e. SMALLEST mip first (libs/VTFParser/VTFParser.cpp:44-78,178-188), one
- * frame, one face, depth 1.  flags are VTF TEXTURE_FLAGS (CLAMPS 0x4, CLAMPT 0x8). */
+/* Texture: decoded mip chain in the order VTFTexture keeps it in memory, i.e. SMALLEST mip first
+ * (libs/VTFParser/VTFParser.cpp:44-78,178-188), one frame, one face, depth 1.  flags are VTF TEXTURE_FLAGS (CLAMPS 0x4, CLAMPT 0x8).
+ * texel_layout = 0: RGBA8888, a channel is byte / 255.f (ParsePixel's RGBA8888 case, FileFormat/Parser.cpp:161-168).
+ * texel_layout = VT_TEXEL_WIDE | codes: 8 bytes per texel, four uint16 NUMERATORS r, g, b, a; channel c is numerator / divisor with
+ * the divisor named by the 2-bit code in bits 2c, 2c + 1 (VT_TEXEL_DIV_255 / _65535 / _1) — what the reference's 16-bit formats need:
+ * their ParsePixel expressions exceed 255 / 255 (Parser.cpp:190-196,238-262) or divide by 65535 (:281-294).  vt_vtf_decode emits it. */
 #define VT_TEXFLAG_CLAMPS 0x00000004u
 #define VT_TEXFLAG_CLAMPT 0x00000008u
+#define VT_TEXEL_WIDE      0x100u
+#define VT_TEXEL_DIV_255   0u
+#define VT_TEXEL_DIV_65535 1u
+#define VT_TEXEL_DIV_1     2u
 typedef struct vt_texture {
     uint16_t width, height; /* size of mip 0 */
     uint16_t mip_count;
     uint16_t pad;
     uint32_t flags;
-    uint32_t pad2;
-    const uint8_t *rgba;    /* host pointer, nbytes long */
+    uint32_t texel_layout;
+    const uint8_t *rgba;    /* host pointer, nbytes long: 4 (or, wide, 8) bytes per texel */
     uint64_t nbytes;
 } vt_texture;
 
-/* VTF file -> the RGBA8888 mip chain of a vt_texture; host only.  Restates libs/VTFParser: header and image-data
+/* VTF file -> the mip chain of a vt_texture; host only.  Restates libs/VTFParser: header and image-data
  * location (FileFormat/Parser.cpp:99-155, FileFormat/Structs.h:21-75), DXT1/3/5 decompressed at load
- * (VTFParser.cpp:26-84, DXTn/DXT1.cpp, DXT3.cpp, DXT5.cpp), the 8-bit-per-channel formats swizzled as ParsePixel
- * reads them (Parser.cpp:157-298) — every output byte b satisfies b / 255.f == the channel VTFTexture::GetPixel
- * returns.  Formats that arithmetic cannot express in 8 bits (RGB565, BGR565, BGRX5551, BGRA5551, BGRA4444,
- * RGBA16161616(F), P8) are rejected: vt_vtf_info.supported = 0 and vt_vtf_decode fails. */
+ * (VTFParser.cpp:26-84, DXTn/DXT1.cpp, DXT3.cpp, DXT5.cpp), every other format converted as ParsePixel reads it
+ * (Parser.cpp:157-298): the 8-bit-per-channel formats (and P8, which ParsePixel reads as opaque black) to RGBA8888, the 16-bit
+ * formats (RGB565, BGR565, BGRX5551, BGRA5551, BGRA4444, RGBA16161616(F)) to WIDE texels (vt_texture.texel_layout) — every channel
+ * the device samples equals the float VTFTexture::GetPixel returns, bit for bit. */
 typedef struct vt_vtf_info {
     uint32_t width, height; /* mip 0 */
     uint32_t mip_count;
     uint32_t flags;         /* VTF TEXTURE_FLAGS: pass on as vt_texture.flags (CLAMPS / CLAMPT) */
     int32_t format;         /* IMAGE_FORMAT of the file (FileFormat/Enums.h:5-35) */
     uint32_t frames, faces, depth;
-    uint32_t supported;     /* 1 when vt_vtf_decode can produce the chain */
-    uint32_t pad;
+    uint32_t supported;     /* 1 when vt_vtf_decode can produce the chain (every format ParsePixel knows) */
+    uint32_t texel_layout;  /* pass on as vt_texture.texel_layout: 0 = RGBA8888, else wide texels */
     uint64_t rgba_bytes;    /* size of the decoded chain of ONE frame / face / z-slice 0, smallest mip first */
 } vt_vtf_info;
 int vt_vtf_read_info(const uint8_t *file, uint64_t size, vt_vtf_info *info);

@@ -77,6 +77,12 @@ public:
         hdr.firstFrame = 0;
         hdr.bumpmapScale = 1.f;
         hdr.highResImageFormat = IMAGE_FORMAT::RGBA8888;
+        if (t.texel_layout != 0) {
+            // wide texels: numerators over 65535 in every channel are the raw bytes of an RGBA16161616 file; the other wide layouts
+            // (the packed 16-bit formats after ParsePixel) have no file the reference could be handed — the C port covers them
+            if (t.texel_layout != (VT_TEXEL_WIDE | (VT_TEXEL_DIV_65535 * 0x55u))) throw std::runtime_error("reference harness: wide texture that is not RGBA16161616");
+            hdr.highResImageFormat = IMAGE_FORMAT::RGBA16161616;
+        }
         hdr.mipmapCount = static_cast<uint8_t>(t.mip_count);
         hdr.lowResImageFormat = IMAGE_FORMAT::NONE;
         hdr.depth = 1;

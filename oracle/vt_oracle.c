@@ -50,6 +50,7 @@ typedef struct {
 typedef struct {
     uint16_t width, height, mips;
     uint32_t flags;
+    uint32_t layout; /* vt_texture.texel_layout: 0 = RGBA8888, else wide texels */
     uint8_t *data;
 } OTex;
 
@@ -126,6 +127,19 @@ static inline px4 parse_pixel(const uint8_t *p) {
     px4 r = {p[0] / 255.f, p[1] / 255.f, p[2] / 255.f, p[3] / 255.f};
     return r;
 }
+/* The 16-bit formats (Parser.cpp:190-196,238-262,281-294) as vt_texture's wide texels hold them: four uint16 numerators over the
+ * divisor each channel's 2-bit code names (include/vistrace_b200.h: VT_TEXEL_WIDE) */
+static inline float wide_divisor(uint32_t layout, int c) {
+    const uint32_t code = (layout >> (2 * c)) & 3u;
+    return code == VT_TEXEL_DIV_255 ? 255.f : (code == VT_TEXEL_DIV_65535 ? 65535.f : 1.f);
+}
+static inline px4 parse_pixel_wide(const uint8_t *p, uint32_t layout) {
+    uint16_t n[4];
+    memcpy(n, p, 8);
+    px4 r = {(float)n[0] / wide_divisor(layout, 0), (float)n[1] / wide_divisor(layout, 1), (float)n[2] / wide_divisor(layout, 2),
+             (float)n[3] / wide_divisor(layout, 3)};
+    return r;
+}
 
 /* VTFTexture::SampleBilinear (libs/VTFParser/VTFParser.cpp:207-309), z = frame = face = 0, depth 1 */
 static px4 sample_bilinear(const OTex *t, float u, float v, uint8_t mipLevel) {
@@ -136,13 +150,13 @@ static px4 sample_bilinear(const OTex *t, float u, float v, uint8_t mipLevel) {
         height >>= 1;
         if (width < 1) width = 1;
         if (height < 1) height = 1;
-        offset += (uint32_t)width * height * 4u;
+        offset += (uint32_t)width * height * (t->layout ? 8u : 4u);
     }
     width = t->width >> mipLevel;
     height = t->height >> mipLevel;
     if (width < 1) width = 1;
     if (height < 1) height = 1;
-    const uint32_t pixelSize = 4;
+    const uint32_t pixelSize = t->layout ? 8 : 4;
     int clampX = (t->flags & VT_TEXFLAG_CLAMPS) != 0, clampY = (t->flags & VT_TEXFLAG_CLAMPT) != 0;
     if (clampX) u = fclampf(u, 0.f, 0.9999f); else u -= floorf(u); /* :250-258 */
     if (clampY) v = fclampf(v, 0.f, 0.9999f); else v -= floorf(v);
@@ -157,7 +171,8 @@ static px4 sample_bilinear(const OTex *t, float u, float v, uint8_t mipLevel) {
             int xc = x + xOff, yc = y + yOff;
             xc = clampX ? iclamp(xc, 0, (int)width - 1) : intmod(xc, width);
             yc = clampY ? iclamp(yc, 0, (int)height - 1) : intmod(yc, height);
-            c[xOff][yOff] = parse_pixel(t->data + offset + (uint32_t)yc * width * pixelSize + (uint32_t)xc * pixelSize);
+            const uint8_t *px = t->data + offset + (uint32_t)yc * width * pixelSize + (uint32_t)xc * pixelSize;
+            c[xOff][yOff] = t->layout ? parse_pixel_wide(px, t->layout) : parse_pixel(px);
         }
     px4 r; /* :295-308 */
     r.r = (c[0][0].r * uFractInv + c[1][0].r * uFract) * vFractInv + (c[0][1].r * uFractInv + c[1][1].r * uFract) * vFract;
@@ -629,6 +644,7 @@ void *vto_create(const vt_scene *sc, int build) {
         s->texs[i].height = t->height;
         s->texs[i].mips = t->mip_count;
         s->texs[i].flags = t->flags;
+        s->texs[i].layout = t->texel_layout;
         s->texs[i].data = (uint8_t *)malloc(t->nbytes);
         memcpy(s->texs[i].data, t->rgba, t->nbytes);
     }

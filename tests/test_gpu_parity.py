@@ -716,6 +716,30 @@ def test_alpha_test_through_dxt_compressed_vtf_files(vt, oracle_mod, kind, layou
     assert alpha_tested.sum() > 1000 and len(np.unique(attrs["alpha"][hit][alpha_tested])) > 20  # texels really sampled
 
 
+@pytest.mark.parametrize("kind", oracle_kinds())
+def test_alpha_test_through_16_bit_vtf_files(vt, oracle_mod, kind, layout):
+    """The 16-bit VTF formats end to end: files -> vt_vtf_decode -> WIDE texels (uint16 numerators + divisor codes) -> the alpha
+    test inside K1 and the albedo / alpha of K2.  Against the unmodified reference with RGBA16161616 files (its own parser reads
+    them); against the C port additionally with BGRA4444 and RGB565, whose ParsePixel values leave [0, 1] (alpha up to 16,
+    green up to 32: exactly what the reference samples)."""
+    from test_vtf import make_vtf
+    from vistrace_b200 import abi, scenes
+
+    base = scenes.scene_foliage(n_cards=1500, tex_size=32, ground_quads=8)
+    fmts = ("RGBA16161616", "RGBA16161616F") if kind == "reference" else ("BGRA4444", "RGB565")
+    files = [make_vtf(fmts[0], 64, 64, 7, seed=31), make_vtf(fmts[1], 32, 32, 6, flags=0x4 | 0x8, seed=32)]
+    texs = [vt.vtf_decode(f) for f in files]
+    assert all(t[5] & abi.VT_TEXEL_WIDE for t in texs)
+    scene = abi.SceneData(base.tris, base.materials, base.entities, textures=texs)
+    rays = np.concatenate([scenes.pinhole_rays(320, 180, (0, -48, 20), (0, 0, 8)), scenes.random_rays(15000, (-45, -45, -3), (45, 45, 50), seed=5)])
+    accel, cpu, hits, attrs, want = _check_against(vt, oracle_mod, scene, rays, kind, "product", layout)
+    hit = hits["prim"] != abi.VT_MISS
+    alpha_tested = (scene.materials["flags"][scene.tris["material"][hits["prim"][hit]]] & abi.VT_MATFLAG_ALPHATEST) != 0
+    assert alpha_tested.sum() > 1000 and len(np.unique(attrs["alpha"][hit][alpha_tested])) > 20  # texels really sampled
+    if kind != "reference":
+        assert attrs["alpha"][hit].max() > 1.0  # BGRA4444's unmasked alpha shift: the reference's value, not a clamped one
+
+
 def test_two_gpu_sharded_trace_nccl(vt):
     """Real multi-GPU plumbing when the box has >= 2 GPUs (gpurun --gpus 2): replicated hierarchy, ray shards, NCCL gather."""
     import subprocess

@@ -18,7 +18,19 @@ FMT = {"RGBA8888": 0, "ABGR8888": 1, "RGB888": 2, "BGR888": 3, "RGB565": 4, "I8"
 BPP = {0: 4, 1: 4, 2: 3, 3: 3, 4: 2, 5: 1, 6: 2, 7: 1, 8: 1, 9: 3, 10: 3, 11: 4, 12: 4, 16: 4, 17: 2, 18: 2, 19: 2, 21: 2, 22: 2, 23: 4, 24: 8, 25: 8, 26: 4}
 SUPPORTED = ["RGBA8888", "ABGR8888", "RGB888", "BGR888", "I8", "IA88", "A8", "RGB888_BLUESCREEN", "BGR888_BLUESCREEN", "ARGB8888",
              "BGRA8888", "DXT1", "DXT3", "DXT5", "BGRX8888", "DXT1_ONEBITALPHA", "UV88", "UVWQ8888", "UVLX8888"]
-REJECTED = ["RGB565", "BGR565", "BGRX5551", "BGRA4444", "BGRA5551", "RGBA16161616F", "RGBA16161616", "P8"]
+SUPPORTED.append("P8")  # no case in ParsePixel: reads as VTFPixel{} = opaque black
+# the 16-bit formats decode to WIDE texels: four uint16 numerators + a divisor code per channel (vt_texture.texel_layout)
+WIDE = {"RGB565": (255, 255, 255, 255), "BGR565": (255, 255, 255, 255), "BGRX5551": (255, 255, 255, 1), "BGRA5551": (255, 255, 255, 1),
+        "BGRA4444": (255, 255, 255, 255), "RGBA16161616F": (65535,) * 4, "RGBA16161616": (65535,) * 4}
+
+
+def texels_as_floats(rgba, layout):
+    """The channel values the device (and the C port) form from a decoded chain: byte / 255.f, or numerator / divisor."""
+    if layout == 0:
+        return rgba.reshape(-1, 4).astype(np.float32) / np.float32(255.0)
+    assert layout & 0x100
+    div = np.array([{0: 255.0, 1: 65535.0, 2: 1.0}[(layout >> (2 * c)) & 3] for c in range(4)], np.float32)
+    return rgba.view(np.uint16).reshape(-1, 4).astype(np.float32) / div[None, :]
 
 
 def image_size(w, h, d, f):
@@ -102,12 +114,12 @@ def test_vtf_decode_matches_the_reference_parser(built, oracle_mod, case):
     data = make_vtf(fmt, w, h, mips, **kw)
     info = vt.vtf_info(data)
     assert (info["width"], info["height"], info["mip_count"], info["format"], info["supported"]) == (w, h, mips, FMT[fmt], 1)
-    gw, gh, gm, gflags, rgba = vt.vtf_decode(data, frame, face)
+    gw, gh, gm, gflags, rgba, layout = vt.vtf_decode(data, frame, face)
     n_tex = sum(max(1, w >> m) * max(1, h >> m) for m in range(mips))
-    assert len(rgba) == 4 * n_tex == info["rgba_bytes"] and gflags == kw.get("flags", 0)
+    assert layout == 0 and len(rgba) == 4 * n_tex == info["rgba_bytes"] and gflags == kw.get("flags", 0)
     want = oracle_mod.vtf_pixels(data, n_tex, frame, face)
     assert want is not None, "the reference parser rejected the synthetic file"
-    got = rgba.reshape(-1, 4).astype(np.float32) / np.float32(255.0)
+    got = texels_as_floats(rgba, layout)
     assert got.tobytes() == want.tobytes()
 
 
@@ -141,20 +153,32 @@ def test_vtf_decode_random_files(built, oracle_mod):
         n_tex = sum(max(1, w >> m) * max(1, h >> m) for m in range(mips))
         want = oracle_mod.vtf_pixels(data, n_tex, frame, face)
         assert want is not None, (it, fmt, w, h, mips, kw)
-        rgba = vt.vtf_decode(data, frame, face)[4]
-        got = rgba.reshape(-1, 4).astype(np.float32) / np.float32(255.0)
+        dec = vt.vtf_decode(data, frame, face)
+        got = texels_as_floats(dec[4], dec[5])
         assert got.tobytes() == want.tobytes(), (it, fmt, w, h, mips, kw)
 
 
-@pytest.mark.parametrize("fmt", REJECTED)
-def test_vtf_formats_outside_8_bits_are_rejected_not_approximated(built, fmt):
+@pytest.mark.parametrize("fmt", sorted(WIDE))
+def test_vtf_16_bit_formats_decode_to_wide_texels(built, oracle_mod, fmt):
+    """RGB565, BGR565, BGRX5551, BGRA5551, BGRA4444, RGBA16161616(F): the reference's ParsePixel leaves [0, 1] for them (unmasked
+    shifts: green of an RGB565 texel reaches 32.1) or divides by 65535, which no RGBA8888 texel can hold; the decoder emits the
+    integer numerators and a divisor per channel instead, and numerator / divisor equals VTFTexture::GetPixel bit for bit."""
     import vistrace_b200 as vt
 
-    data = make_vtf(fmt, 8, 8, 2)
-    info = vt.vtf_info(data)
-    assert info["supported"] == 0 and info["format"] == FMT[fmt]
-    with pytest.raises(RuntimeError, match="not representable"):
-        vt.vtf_decode(data)
+    for seed, (w, h, mips) in enumerate([(8, 8, 2), (16, 4, 5), (5, 9, 3), (64, 64, 7)]):
+        data = make_vtf(fmt, w, h, mips, seed=seed, flags=0x4 if seed == 1 else 0)
+        info = vt.vtf_info(data)
+        want_layout = 0x100 | sum({255: 0, 65535: 1, 1: 2}[d] << (2 * c) for c, d in enumerate(WIDE[fmt]))
+        assert (int(info["supported"]), int(info["format"]), int(info["texel_layout"])) == (1, FMT[fmt], want_layout)
+        gw, gh, gm, gflags, rgba, layout = vt.vtf_decode(data)
+        n_tex = sum(max(1, w >> m) * max(1, h >> m) for m in range(mips))
+        assert layout == want_layout and len(rgba) == 8 * n_tex == info["rgba_bytes"]
+        got = texels_as_floats(rgba, layout)
+        if fmt in ("RGB565", "BGR565"):
+            assert got[:, 1].max() > 1.0  # the reference's unmasked green: out of range on purpose
+        if oracle_mod.available("reference"):
+            want = oracle_mod.vtf_pixels(data, n_tex)
+            assert want is not None and got.tobytes() == want.tobytes(), (fmt, w, h, mips)
 
 
 def test_vtf_malformed_files_fail_like_the_reference(built, oracle_mod):
@@ -180,6 +204,6 @@ def test_vtf_golden_fixture(built):
     names = sorted(k[5:] for k in g.files if k.startswith("file_"))
     assert len(names) >= 6
     for name in names:
-        _, _, _, _, rgba = vt.vtf_decode(g["file_" + name].tobytes())
-        got = rgba.reshape(-1, 4).astype(np.float32) / np.float32(255.0)
+        _, _, _, _, rgba, layout = vt.vtf_decode(g["file_" + name].tobytes())
+        got = texels_as_floats(rgba, layout)
         assert got.tobytes() == g["want_" + name].tobytes(), name

@@ -21,6 +21,7 @@ VT_TRAVERSE_DEVICE_PTRS = 1
 VT_TRAVERSE_ANY_HIT = 2
 VT_TRAVERSE_QUEUE_ATTRS = 4
 VT_GROUP_SHARED_HOST_FRAME = 16
+VT_TEXEL_WIDE, VT_TEXEL_DIV_255, VT_TEXEL_DIV_65535, VT_TEXEL_DIV_1 = 0x100, 0, 1, 2
 VT_PATHS_NO_COMPACTION = 8
 VT_LOBE_NONE, VT_LOBE_DIFFUSE_REFLECTION = 0, 1
 
@@ -135,7 +136,7 @@ class Texture(C.Structure):
         ("mip_count", C.c_uint16),
         ("pad", C.c_uint16),
         ("flags", C.c_uint32),
-        ("pad2", C.c_uint32),
+        ("texel_layout", C.c_uint32),
         ("rgba", C.c_void_p),
         ("nbytes", C.c_uint64),
     ]
@@ -167,11 +168,12 @@ class SceneData:
             entities = np.zeros(1, ENTITY)
             entities["colour"] = 1.0
         self.entities = np.ascontiguousarray(entities, ENTITY)
-        # textures: list of (width, height, mip_count, flags, uint8 array in VTF order: smallest mip first)
-        self.textures = [(int(w), int(h), int(m), int(fl), np.ascontiguousarray(px, np.uint8).ravel()) for (w, h, m, fl, px) in textures]
+        # textures: list of (width, height, mip_count, flags, uint8 array in VTF order: smallest mip first[, texel_layout]) — what
+        # vtf_decode returns; texel_layout 0 (default) = RGBA8888, else wide texels (include/vistrace_b200.h: VT_TEXEL_WIDE)
+        self.textures = [(int(t[0]), int(t[1]), int(t[2]), int(t[3]), np.ascontiguousarray(t[4], np.uint8).ravel(), int(t[5]) if len(t) > 5 else 0) for t in textures]
         self._tex_arr = (Texture * max(1, len(self.textures)))()
-        for i, (w, h, m, fl, px) in enumerate(self.textures):
-            self._tex_arr[i] = Texture(w, h, m, 0, fl, 0, px.ctypes.data, px.nbytes)
+        for i, (w, h, m, fl, px, layout) in enumerate(self.textures):
+            self._tex_arr[i] = Texture(w, h, m, 0, fl, layout, px.ctypes.data, px.nbytes)
         self.c = Scene(
             self.tris.ctypes.data,
             len(self.tris),

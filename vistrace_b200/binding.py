@@ -216,7 +216,7 @@ assert QUAD.itemsize == 64
 
 
 VTF_INFO = np.dtype([("width", np.uint32), ("height", np.uint32), ("mip_count", np.uint32), ("flags", np.uint32), ("format", np.int32),
-                     ("frames", np.uint32), ("faces", np.uint32), ("depth", np.uint32), ("supported", np.uint32), ("pad", np.uint32),
+                     ("frames", np.uint32), ("faces", np.uint32), ("depth", np.uint32), ("supported", np.uint32), ("texel_layout", np.uint32),
                      ("rgba_bytes", np.uint64)])
 
 
@@ -229,12 +229,12 @@ def vtf_info(data):
 
 
 def vtf_decode(data, frame=0, face=0):
-    """VTF file -> (width, height, mip_count, flags, rgba uint8 chain, smallest mip first): a SceneData texture tuple."""
+    """VTF file -> (width, height, mip_count, flags, texel chain as uint8, smallest mip first, texel_layout): a SceneData texture tuple."""
     buf = np.frombuffer(bytes(data), np.uint8)
     info = vtf_info(data)
     out = np.zeros(int(info["rgba_bytes"]), np.uint8)
     _check(lib().vt_vtf_decode(buf.ctypes.data, len(buf), frame, face, out.ctypes.data, len(out), None), "vt_vtf_decode")
-    return int(info["width"]), int(info["height"]), int(info["mip_count"]), int(info["flags"]), out
+    return int(info["width"]), int(info["height"]), int(info["mip_count"]), int(info["flags"]), out, int(info["texel_layout"])
 
 
 MDL_INFO = np.dtype([("version", np.uint32), ("n_bodygroups", np.uint32), ("n_bones", np.uint32), ("n_materials", np.uint32), ("n_material_dirs", np.uint32),

@@ -220,9 +220,13 @@ void AccelStruct::Ingest(const vt_scene &scene, bool stage_attrs) {
         const vt_texture &t = scene.textures[i];
         if (t.width == 0 || t.height == 0 || t.mip_count == 0 || t.mip_count > 16 || !t.rgba)
             throw std::runtime_error("texture " + std::to_string(i) + ": bad header");
+        if (t.texel_layout != 0 && ((t.texel_layout & ~0xFFu) != VT_TEXEL_WIDE))
+            throw std::runtime_error("texture " + std::to_string(i) + ": unknown texel layout");
+        for (int c = 0; c < 4; c++)
+            if (t.texel_layout && ((t.texel_layout >> (2 * c)) & 3u) == 3u) throw std::runtime_error("texture " + std::to_string(i) + ": unknown divisor code");
         uint64_t need = 0;
-        for (uint32_t m = 0; m < t.mip_count; m++) need += (uint64_t)std::max(1, t.width >> m) * std::max(1, t.height >> m) * 4;
-        if (need != t.nbytes) throw std::runtime_error("texture " + std::to_string(i) + ": nbytes does not match the RGBA8888 mip chain");
+        for (uint32_t m = 0; m < t.mip_count; m++) need += (uint64_t)std::max(1, t.width >> m) * std::max(1, t.height >> m) * (t.texel_layout ? 8 : 4);
+        if (need != t.nbytes) throw std::runtime_error("texture " + std::to_string(i) + ": nbytes does not match the mip chain of its texel layout");
     }
     if (mAttrUpload.joinable()) mAttrUpload.join();
     mTriangles.resize(scene.n_tris);
@@ -383,17 +387,18 @@ void AccelStruct::Upload(const vt_scene &scene) {
     }
     std::vector<VtDevTexture> dt(scene.n_textures + 1);
     std::vector<uint8_t> texels;
-    auto add_texture = [&](VtDevTexture &o, uint32_t w, uint32_t h, uint32_t mips, uint32_t flags, const uint8_t *px, uint64_t nbytes) {
+    auto add_texture = [&](VtDevTexture &o, uint32_t w, uint32_t h, uint32_t mips, uint32_t flags, uint32_t layout, const uint8_t *px, uint64_t nbytes) {
         std::memset(&o, 0, sizeof(o));
         o.width = w;
         o.height = h;
         o.mips = mips;
         o.flags = flags;
+        o.layout = layout;
         o.base = texels.size();
-        // chain is smallest mip first: offset of mip m = sizes of mips m+1 .. last (VTFParser.cpp:219-229)
+        // chain is smallest mip first: offset of mip m = sizes of mips m+1 .. last (VTFParser.cpp:219-229), in texels
         for (uint32_t m = 0; m < mips; m++) {
             uint32_t off = 0;
-            for (uint32_t i = m + 1; i < mips; i++) off += std::max(1u, w >> i) * std::max(1u, h >> i) * 4u;
+            for (uint32_t i = m + 1; i < mips; i++) off += std::max(1u, w >> i) * std::max(1u, h >> i);
             o.mip_offset[m] = off;
         }
         texels.insert(texels.end(), px, px + nbytes);
@@ -401,10 +406,10 @@ void AccelStruct::Upload(const vt_scene &scene) {
     };
     for (uint32_t i = 0; i < scene.n_textures; i++) {
         const vt_texture &t = scene.textures[i];
-        add_texture(dt[i], t.width, t.height, t.mip_count, t.flags, t.rgba, t.nbytes);
+        add_texture(dt[i], t.width, t.height, t.mip_count, t.flags, t.texel_layout, t.rgba, t.nbytes);
     }
     const uint8_t white[4] = {255, 255, 255, 255};
-    add_texture(dt[scene.n_textures], 1, 1, 1, 0, white, 4);
+    add_texture(dt[scene.n_textures], 1, 1, 1, 0, 0, white, 4);
 
     timer.lap("  triangle / attr records");
     D.refit_ready = false;

@@ -107,8 +107,9 @@ static_assert(sizeof(VtTriAttr) == 176, "attr layout");
 struct VtDevTexture {
     uint32_t width, height, mips, flags;
     uint64_t base;  // byte offset of the chain inside the texel buffer
-    uint32_t mip_offset[16];
-    uint32_t pad[2];
+    uint32_t mip_offset[16];  // TEXEL index of mip m inside the chain
+    uint32_t layout;  // vt_texture.texel_layout: 0 = RGBA8888 (4 bytes per texel), else wide (8 bytes: four uint16 numerators + divisor codes)
+    uint32_t pad;
 };
 
 struct VtDevMaterial {

@@ -76,7 +76,7 @@ VT_DEV int vtf_intmod(int a, int b) { return (a % b + b) % b; }
 // Corner addressing + fractional weights of VTFTexture::SampleBilinear
 // (libs/VTFParser/VTFParser.cpp:207-309), shared by the alpha-only and RGBA paths.
 struct BilinearTaps {
-    uint32_t o00, o10, o01, o11;  // byte offsets into the texel buffer: corners[xOff][yOff]
+    uint32_t o00, o10, o01, o11;  // texel indices inside the chain: corners[xOff][yOff]
     float uF, vF, uFi, vFi;
 };
 
@@ -111,10 +111,10 @@ VT_DEV BilinearTaps bilinear_taps(const VtDevTexture &t, float u, float v, uint3
         y1 = vtf_intmod(y + 1, (int)height);
     }
     const uint32_t base = t.mip_offset[mip];
-    b.o00 = base + ((uint32_t)y0 * width + (uint32_t)x0) * 4u;
-    b.o10 = base + ((uint32_t)y0 * width + (uint32_t)x1) * 4u;
-    b.o01 = base + ((uint32_t)y1 * width + (uint32_t)x0) * 4u;
-    b.o11 = base + ((uint32_t)y1 * width + (uint32_t)x1) * 4u;
+    b.o00 = base + ((uint32_t)y0 * width + (uint32_t)x0);
+    b.o10 = base + ((uint32_t)y0 * width + (uint32_t)x1);
+    b.o01 = base + ((uint32_t)y1 * width + (uint32_t)x0);
+    b.o11 = base + ((uint32_t)y1 * width + (uint32_t)x1);
     return b;
 }
 
@@ -125,13 +125,38 @@ VT_DEV float bilerp(float c00, float c10, float c01, float c11, const BilinearTa
     return (c00 * b.uFi + c10 * b.uF) * b.vFi + (c01 * b.uFi + c11 * b.uF) * b.vF;  // :295-308
 }
 
-VT_DEV uint32_t ld_texel(const uint8_t *texels, uint64_t off) { return __ldg(reinterpret_cast<const uint32_t *>(texels + off)); }
+VT_DEV uint32_t ld_texel(const uint8_t *texels, uint64_t base, uint32_t index) {
+    return __ldg(reinterpret_cast<const uint32_t *>(texels + base) + index);
+}
+// Wide texels (vt_texture.texel_layout != 0): four uint16 numerators; channel = numerator / divisor, the divisor (255, 65535 or 1)
+// named by a 2-bit code per channel — the reference's ParsePixel expressions for the 16-bit formats (FileFormat/Parser.cpp:190-196,
+// 238-262, 281-294), which an RGBA8888 texel cannot hold.  Warp-uniform per texture in practice, rare: kept out of line of the byte path.
+VT_DEV uint2 ld_texel_wide(const uint8_t *texels, uint64_t base, uint32_t index) {
+    return __ldg(reinterpret_cast<const uint2 *>(texels + base) + index);
+}
+VT_DEV float wide_divisor(uint32_t layout, int c) {
+    const uint32_t code = (layout >> (2 * c)) & 3u;
+    return code == 0u ? 255.f : (code == 1u ? 65535.f : 1.f);
+}
+VT_DEV float wide_channel(uint2 p, int c) { return (float)((c < 2 ? p.x : p.y) >> ((c & 1) * 16) & 0xFFFFu); }
 
 VT_DEV Px sample_bilinear(const VtDevTexture &t, const uint8_t *texels, float u, float v, uint32_t mip) {
     BilinearTaps b = bilinear_taps(t, u, v, mip);
-    uint32_t p00 = ld_texel(texels, t.base + b.o00), p10 = ld_texel(texels, t.base + b.o10);
-    uint32_t p01 = ld_texel(texels, t.base + b.o01), p11 = ld_texel(texels, t.base + b.o11);
     Px r;
+    if (t.layout) {
+        const uint2 q00 = ld_texel_wide(texels, t.base, b.o00), q10 = ld_texel_wide(texels, t.base, b.o10);
+        const uint2 q01 = ld_texel_wide(texels, t.base, b.o01), q11 = ld_texel_wide(texels, t.base, b.o11);
+        float ch[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float d = wide_divisor(t.layout, c);
+            ch[c] = bilerp(wide_channel(q00, c) / d, wide_channel(q10, c) / d, wide_channel(q01, c) / d, wide_channel(q11, c) / d, b);
+        }
+        r.r = ch[0], r.g = ch[1], r.b = ch[2], r.a = ch[3];
+        return r;
+    }
+    uint32_t p00 = ld_texel(texels, t.base, b.o00), p10 = ld_texel(texels, t.base, b.o10);
+    uint32_t p01 = ld_texel(texels, t.base, b.o01), p11 = ld_texel(texels, t.base, b.o11);
     r.r = bilerp(u8f(p00 & 255u), u8f(p10 & 255u), u8f(p01 & 255u), u8f(p11 & 255u), b);
     r.g = bilerp(u8f((p00 >> 8) & 255u), u8f((p10 >> 8) & 255u), u8f((p01 >> 8) & 255u), u8f((p11 >> 8) & 255u), b);
     r.b = bilerp(u8f((p00 >> 16) & 255u), u8f((p10 >> 16) & 255u), u8f((p01 >> 16) & 255u), u8f((p11 >> 16) & 255u), b);
@@ -142,8 +167,13 @@ VT_DEV Px sample_bilinear(const VtDevTexture &t, const uint8_t *texels, float u,
 // Alpha channel only, mip 0: what the alpha test consumes (source/objects/Primitives.h:203).
 VT_DEV float sample_alpha_mip0(const VtDevTexture &t, const uint8_t *texels, float u, float v) {
     BilinearTaps b = bilinear_taps(t, u, v, 0);
-    uint32_t p00 = ld_texel(texels, t.base + b.o00), p10 = ld_texel(texels, t.base + b.o10);
-    uint32_t p01 = ld_texel(texels, t.base + b.o01), p11 = ld_texel(texels, t.base + b.o11);
+    if (t.layout) {
+        const float d = wide_divisor(t.layout, 3);
+        return bilerp((float)(ld_texel_wide(texels, t.base, b.o00).y >> 16) / d, (float)(ld_texel_wide(texels, t.base, b.o10).y >> 16) / d,
+                      (float)(ld_texel_wide(texels, t.base, b.o01).y >> 16) / d, (float)(ld_texel_wide(texels, t.base, b.o11).y >> 16) / d, b);
+    }
+    uint32_t p00 = ld_texel(texels, t.base, b.o00), p10 = ld_texel(texels, t.base, b.o10);
+    uint32_t p01 = ld_texel(texels, t.base, b.o01), p11 = ld_texel(texels, t.base, b.o11);
     return bilerp(u8f(p00 >> 24), u8f(p10 >> 24), u8f(p01 >> 24), u8f(p11 >> 24), b);
 }
 

@@ -1,4 +1,4 @@
-// vt_vtf.cpp — VTF file -> RGBA8888 mip chain (the vt_texture the alpha-test and TraceResult kernels sample).
+// vt_vtf.cpp — VTF file -> texel mip chain (the vt_texture the alpha-test and TraceResult kernels sample): RGBA8888, or wide texels.
 //
 // SURVEY.md §8 f4 (the data format on the input side of the path): the reference reads textures through
 // libs/VTFParser — header (FileFormat/Parser.cpp:99-121, FileFormat/Structs.h:21-75), image-data location incl. the
@@ -8,9 +8,11 @@
 // satisfy  b / 255.f == the float ParsePixel / the decompressor would hand VTFTexture::Sample  for every channel, so
 // the device's manual bilinear filter over RGBA8888 (vt_math.cuh) sees the reference's texel values bit for bit.
 //
-// Formats whose reference arithmetic is not representable in 8 bits per channel are REJECTED, not approximated: the
-// 16-bit packed formats (RGB565, BGR565, BGRX5551, BGRA5551, BGRA4444 — Parser.cpp:191-196,238-262 shift without
-// masking, so a channel can exceed 255/255), RGBA16161616(F) and P8.
+// The 16-bit formats (RGB565, BGR565, BGRX5551, BGRA5551, BGRA4444: Parser.cpp:191-196,238-262; RGBA16161616(F): :281-294) are
+// not representable in 8 bits per channel under the reference's arithmetic — its shifts are not masked, so green of an RGB565
+// texel is ((b0 << 5) + ((b1 & 0xE0) >> 3)) / 255.f, up to 32.1 — and are decoded to WIDE texels instead: four 16-bit numerators
+// per texel plus a divisor code per channel (255, 65535 or 1; vt_texture.texel_layout), numerator / divisor being exactly the float
+// ParsePixel returns.  P8 has no case in ParsePixel and reads as VTFPixel{} = opaque black (Parser.cpp:295-297).
 //
 // Quirks kept: 5/6-bit endpoints widen by a plain shift (<< 3, << 2: white is 248/252/248, DXT1.cpp:31-39); DXT1's
 // 3-colour mode still derives colour 3 as (c0 + 2 c1 + 1) / 3 with alpha 0 (DXT1.cpp:62-65); DXT3 alpha nibbles are
@@ -199,7 +201,42 @@ void convert_pixel(const uint8_t *p, int32_t f, uint8_t *o) {
         case F_ARGB8888: o[0] = p[1], o[1] = p[2], o[2] = p[3], o[3] = p[0]; break;
         case F_BGRA8888: case F_BGRX8888: o[0] = p[2], o[1] = p[1], o[2] = p[0], o[3] = p[3]; break;
         case F_UV88: o[0] = p[0], o[1] = p[1], o[2] = 0, o[3] = 255; break;
+        case F_P8: o[0] = o[1] = o[2] = 0, o[3] = 255; break;  // no case in ParsePixel: VTFPixel{} (Parser.cpp:295-297)
         default: break;
+    }
+}
+
+// ParsePixel for the formats whose channels leave [0, 255] / 255: the integer NUMERATORS of its expressions, evaluated in int as
+// C++ does (integer promotion, no masking where the reference does not mask); the divisors are in wide_layout()
+void convert_pixel_wide(const uint8_t *p, int32_t f, uint16_t *o) {
+    const int b0 = p[0], b1 = p[1];
+    switch (f) {
+        case F_RGB565:  // :191-196
+            o[0] = (uint16_t)(b0 & 0xF8), o[1] = (uint16_t)((b0 << 5) + ((b1 & 0xE0) >> 3)), o[2] = (uint16_t)((b1 & 0x1F) << 3), o[3] = 255;
+            break;
+        case F_BGR565:  // :238-243
+            o[0] = (uint16_t)((b1 & 0x1F) << 3), o[1] = (uint16_t)((b0 << 5) + ((b1 & 0xE0) >> 3)), o[2] = (uint16_t)(b0 & 0xF8), o[3] = 255;
+            break;
+        case F_BGRX5551: case F_BGRA5551:  // :244-251: alpha is static_cast<float>(b1 & 1), divisor 1
+            o[0] = (uint16_t)((b1 & 0x3E) << 2), o[1] = (uint16_t)((b0 << 5) + ((b1 & 0xC0) >> 3)), o[2] = (uint16_t)(b0 & 0xF8), o[3] = (uint16_t)(b1 & 1);
+            break;
+        case F_BGRA4444:  // :252-258
+            o[0] = (uint16_t)(b1 & 0xF0), o[1] = (uint16_t)(b0 << 4), o[2] = (uint16_t)(b0 & 0xF0), o[3] = (uint16_t)(b1 << 4);
+            break;
+        case F_RGBA16161616: case F_RGBA16161616F:  // :281-294: both read as four uint16 over 65535
+            std::memcpy(o, p, 8);
+            break;
+        default: break;
+    }
+}
+
+// vt_texture.texel_layout of a format: 0 = RGBA8888, else VT_TEXEL_WIDE | divisor code of channel c in bits 2c, 2c + 1
+uint32_t wide_layout(int32_t f) {
+    switch (f) {
+        case F_RGB565: case F_BGR565: case F_BGRA4444: return VT_TEXEL_WIDE;                                  // every channel over 255
+        case F_BGRX5551: case F_BGRA5551: return VT_TEXEL_WIDE | (VT_TEXEL_DIV_1 << 6);                       // alpha over 1
+        case F_RGBA16161616: case F_RGBA16161616F: return VT_TEXEL_WIDE | (VT_TEXEL_DIV_65535 * 0x55u);       // every channel over 65535
+        default: return 0;
     }
 }
 
@@ -207,8 +244,8 @@ bool representable(int32_t f) {
     switch (f) {
         case F_RGBA8888: case F_UVWQ8888: case F_UVLX8888: case F_ABGR8888: case F_RGB888: case F_RGB888_BLUESCREEN: case F_BGR888:
         case F_BGR888_BLUESCREEN: case F_I8: case F_IA88: case F_A8: case F_ARGB8888: case F_BGRA8888: case F_BGRX8888: case F_UV88:
-        case F_DXT1: case F_DXT1_ONEBITALPHA: case F_DXT3: case F_DXT5: return true;
-        default: return false;
+        case F_DXT1: case F_DXT1_ONEBITALPHA: case F_DXT3: case F_DXT5: case F_P8: return true;
+        default: return wide_layout(f) != 0;
     }
 }
 
@@ -227,8 +264,9 @@ void VtfInfo(const uint8_t *file, uint64_t size, vt_vtf_info *out) {
     out->faces = face_count(h);
     out->depth = h.depth ? h.depth : 1;
     out->supported = representable(h.format) ? 1 : 0;
+    out->texel_layout = wide_layout(h.format);
     uint64_t n = 0;
-    for (uint32_t m = 0; m < h.mips; m++) n += (uint64_t)std::max(1, h.width >> m) * std::max(1, h.height >> m) * 4;
+    for (uint32_t m = 0; m < h.mips; m++) n += (uint64_t)std::max(1, h.width >> m) * std::max(1, h.height >> m) * (out->texel_layout ? 8 : 4);
     out->rgba_bytes = n;
 }
 
@@ -238,7 +276,7 @@ void VtfDecode(const uint8_t *file, uint64_t size, uint32_t frame, uint32_t face
     if (info_out) *info_out = info;
     if (!info.supported)
         throw std::runtime_error("vtf: image format " + std::to_string(info.format) +
-                                 " is not representable as RGBA8888 under the reference's ParsePixel arithmetic");
+                                 " is not a format the reference's ParsePixel reads");
     if (frame >= info.frames || face >= info.faces) throw std::runtime_error("vtf: frame or face out of range");
     if (!rgba || capacity < info.rgba_bytes) throw std::runtime_error("vtf: output buffer too small");
     const Header h = parse_header(file, size);
@@ -264,10 +302,18 @@ void VtfDecode(const uint8_t *file, uint64_t size, uint32_t frame, uint32_t face
             decode_dxt(img, dst, w, hh, h.format);
         } else {
             const uint32_t bpp = bytes_per_pixel(h.format);
-            for (uint64_t i = 0; i < (uint64_t)w * hh; i++) convert_pixel(img + i * bpp, h.format, dst + i * 4);
+            if (info.texel_layout) {
+                for (uint64_t i = 0; i < (uint64_t)w * hh; i++) {
+                    uint16_t px[4];
+                    convert_pixel_wide(img + i * bpp, h.format, px);
+                    std::memcpy(dst + i * 8, px, 8);
+                }
+            } else {
+                for (uint64_t i = 0; i < (uint64_t)w * hh; i++) convert_pixel(img + i * bpp, h.format, dst + i * 4);
+            }
         }
         src += slice * d * h.frames * info.faces;
-        dst += (uint64_t)w * hh * 4;
+        dst += (uint64_t)w * hh * (info.texel_layout ? 8 : 4);
     }
 }
 
