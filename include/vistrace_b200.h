@@ -635,6 +635,12 @@ int vt_shard_geometry(uint64_t n, int world, int rank, uint64_t tile, uint64_t *
  * process that displays it.  Every rank lands its own tiles through its own PCIe link; nothing crosses NVLink, nothing funnels through
  * rank 0's link; a one-byte ncclAllGather behind the copies makes the frame complete on EVERY rank's return. */
 #define VT_GROUP_SHARED_HOST_FRAME 16u
+/* With VT_TRAVERSE_DEVICE_PTRS (multi-process groups): the call uses the group's SECOND set of per-frame state — its own peer-memory
+ * frame and hand-shake flags on rank 0, its own scratch buffers.  Calls with and without the flag share nothing, so a caller that
+ * alternates consecutive frames between two streams (frame k: stream A, flags without; frame k + 1: stream B, with) has two frames
+ * in flight: one frame's launch tails run under the other frame's bulk (profiles/r2_tail_sharing.md: 1.4x on a 1/8-frame shard).
+ * Calls on the SAME slot must be issued in stream order on one stream, in the same order on every rank. */
+#define VT_GROUP_FRAME_SLOT1 32u
 int vt_group_render_diffuse_wave(vt_group *group, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight,
                                  float *framebuffer_rgb, uint64_t *live_out, uint32_t flags, void *stream);
 

@@ -67,6 +67,18 @@ d_fb = torch.full((n * 3,), -1.0, dtype=torch.float32, device=dev)
 group.render_diffuse_wave_device(d_rays.data_ptr(), n, spp, 9, 0.5, d_fb.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 
+# two frames in flight: consecutive frames alternate between the group's two frame slots on two streams (different seeds, so a
+# frame landing in the wrong slot or a stale hand-shake flag would show)
+streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+d_slot = [torch.full((n * 3,), -1.0, dtype=torch.float32, device=dev) for _ in range(2)]
+torch.cuda.synchronize()
+for it in range(7):
+    k = it % 2
+    group.render_diffuse_wave_device(d_rays.data_ptr(), n, spp, 20 + it, 0.5, d_slot[k].data_ptr(), stream=streams[k].cuda_stream, slot=k)
+torch.cuda.synchronize()
+dist.barrier()
+slot_imgs = [d.cpu().numpy().reshape(-1, 3) for d in d_slot]  # frames 6 (slot 0) and 5 (slot 1) were the last to land
+
 # sample-index sharding: per-rank partial images summed on rank 0 with one ncclReduce
 part = torch.full((1000,), float(rank + 1), dtype=torch.float32, device=dev)
 group.reduce_device(part.data_ptr(), 1000, stream=torch.cuda.current_stream().cuda_stream)
@@ -87,6 +99,8 @@ if rank == 0:
     assert hits.tobytes() == want_hits.tobytes() and attrs.tobytes() == want_attrs.tobytes(), "gathered hit buffer differs"
     np.testing.assert_array_equal(img, want_img)
     np.testing.assert_array_equal(d_fb.cpu().numpy().reshape(-1, 3), want_img)
+    for k, seed in ((0, 26), (1, 25)):
+        np.testing.assert_array_equal(slot_imgs[k], single.render_diffuse_wave(rays, spp, seed=seed, weight=0.5)[0], err_msg=f"frame slot {k}")
     assert int(live_t.item()) == want_live
     assert float(part[0].item()) == sum(range(1, world + 1))
 else:  # a non-root rank holds its own slice / tiles

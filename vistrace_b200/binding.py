@@ -728,10 +728,12 @@ class Group:
                "vt_group_render_diffuse_wave")
         return fb, live.value
 
-    def render_diffuse_wave_device(self, d_rays_shard, n, spp, seed, weight, d_fb, stream=None):
-        """Device-resident shard in, frame-sized device image out (complete on rank 0); enqueued on `stream`."""
+    def render_diffuse_wave_device(self, d_rays_shard, n, spp, seed, weight, d_fb, stream=None, slot=0):
+        """Device-resident shard in, frame-sized device image out (complete on rank 0); enqueued on `stream`.  slot 0 / 1: the group's
+        two independent sets of per-frame state (VT_GROUP_FRAME_SLOT1) — alternate them over two streams for two frames in flight."""
         _check(self.L.vt_group_render_diffuse_wave(self.h, _ptr(d_rays_shard), n, spp, seed, weight, _ptr(d_fb), None,
-                                                   abi.VT_TRAVERSE_DEVICE_PTRS, _ptr(stream)), "vt_group_render_diffuse_wave")
+                                                   abi.VT_TRAVERSE_DEVICE_PTRS | (abi.VT_GROUP_FRAME_SLOT1 if slot else 0), _ptr(stream)),
+               "vt_group_render_diffuse_wave")
 
     def all_gather_device(self, d_buf, bytes_per_rank, stream=None):
         _check(self.L.vt_group_all_gather_device(self.h, _ptr(d_buf), bytes_per_rank, _ptr(stream)), "vt_group_all_gather_device")

@@ -157,10 +157,14 @@ public:
         DevBuf<unsigned char> header;
         // peer-memory frame (multi-process groups): rank 0 owns `frame` = n x 12 bytes of RGBFFF pixels in GLOBAL pixel order + flag
         // words; every other rank maps it over NVLink (CUDA IPC) and its K4 stores finished pixels straight into it
-        DevBuf<unsigned char> frame;
-        void *peer_frame = nullptr;
-        uint64_t frame_pixels = 0;
-        uint32_t step = 0;
+        // Two of them (VT_GROUP_FRAME_SLOT1): calls on different slots share nothing — own frame, own flags, own scratch (the wave lane
+        // of the same index) — so a caller that issues consecutive frames on two streams has two frames in flight.
+        struct PeerFrame {
+            DevBuf<unsigned char> frame;
+            void *peer_frame = nullptr;
+            uint64_t frame_pixels = 0;
+            uint32_t step = 0;
+        } pf[2];
         uint64_t live = 0;
         // worker thread (single-process groups with several GPUs)
         std::thread th;
@@ -294,8 +298,10 @@ public:
             }
             cudaSetDevice(m.device);
             cudaDeviceSynchronize();
-            if (m.peer_frame && m.rank != 0) cudaIpcCloseMemHandle(m.peer_frame);
-            m.frame.release();
+            for (auto &P : m.pf) {
+                if (P.peer_frame && m.rank != 0) cudaIpcCloseMemHandle(P.peer_frame);
+                P.frame.release();
+            }
             if (m.comm) NcclApi::get().CommDestroy(m.comm);
             m.fb_local.release();
             m.fb_stage.release();
@@ -445,7 +451,7 @@ public:
     void member_render(Member &m, const ShardGeom &g, const vt_ray *rays, bool rays_on_device, uint32_t spp, uint64_t seed, float weight,
                        float *fb_host, bool count_live, cudaStream_t caller_stream, const ShardGeom *sched = nullptr,
                        const std::function<void(uint64_t, uint64_t, cudaStream_t)> &after_chunk = nullptr, float *frame_target = nullptr,
-                       const uint32_t *consumed_flag = nullptr, uint32_t step = 0) {
+                       const uint32_t *consumed_flag = nullptr, uint32_t step = 0, int slot = 0) {
         AccelStruct &A = m.accel->impl;
         if (!A.Built()) throw std::runtime_error("vt_group: populate the group first");
         VT_CUDA(cudaSetDevice(m.device));
@@ -496,7 +502,7 @@ public:
             s1 = std::min(lt_sched, s0 + chunk_tiles);
             if (lt_sched - s1 < chunk_tiles / 2) s1 = lt_sched;  // no small tail chunk
             const uint64_t j0 = std::min(s0, lt), j1 = std::min(s1, lt);  // this rank's part of the chunk (may be empty at the end)
-            DeviceScene::WaveLane &l = D.lanes[li];
+            DeviceScene::WaveLane &l = D.lanes[on_caller ? slot : li];  // a device-resident call on the caller's stream: the slot's own scratch
             cudaStream_t st = on_caller ? caller_stream : l.stream;
             used[li] = true;
             if (j1 <= j0) {
@@ -579,14 +585,15 @@ public:
     static uint64_t frame_flag_offset(uint64_t pixels) { return (pixels * 12 + 255) / 256 * 256; }
 
     // Collective: make rank 0's frame hold `pixels` pixels and map it into every other rank (CUDA IPC over NVLink).
-    void ensure_peer_frame(uint64_t pixels) {
+    void ensure_peer_frame(uint64_t pixels, int slot) {
         Member &m = *mMembers[0];
-        if (m.peer_frame && pixels <= m.frame_pixels) return;
+        Member::PeerFrame &P = m.pf[slot];
+        if (P.peer_frame && pixels <= P.frame_pixels) return;
         NcclApi &nccl = NcclApi::get();
         VT_CUDA(cudaSetDevice(m.device));
         VT_CUDA(cudaDeviceSynchronize());
-        if (m.peer_frame && m.rank != 0) VT_CUDA(cudaIpcCloseMemHandle(m.peer_frame));
-        m.peer_frame = nullptr;
+        if (P.peer_frame && m.rank != 0) VT_CUDA(cudaIpcCloseMemHandle(P.peer_frame));
+        P.peer_frame = nullptr;
         m.header.ensure(256);
         // nobody maps the old frame any more once everybody has passed this collective
         VT_NCCL(nccl.Broadcast(m.header.p, m.header.p, 4, ncclUint8, 0, m.comm, m.stream));
@@ -595,10 +602,10 @@ public:
         std::memset(&handle, 0, sizeof(handle));
         const uint64_t bytes = frame_flag_offset(pixels) + ((uint64_t)mWorld * kMaxChunks + 64) * sizeof(uint32_t);
         if (m.rank == 0) {
-            m.frame.release();
-            m.frame.ensure(bytes);
-            VT_CUDA(cudaMemset(m.frame.p, 0, bytes));
-            VT_CUDA(cudaIpcGetMemHandle(&handle, m.frame.p));
+            P.frame.release();
+            P.frame.ensure(bytes);
+            VT_CUDA(cudaMemset(P.frame.p, 0, bytes));
+            VT_CUDA(cudaIpcGetMemHandle(&handle, P.frame.p));
             VT_CUDA(cudaMemcpy(m.header.p, &handle, sizeof(handle), cudaMemcpyHostToDevice));
         }
         static_assert(sizeof(handle) <= 256, "IPC handle fits the header buffer");
@@ -607,10 +614,10 @@ public:
         VT_CUDA(cudaStreamSynchronize(m.stream));
         unsigned char ok = 1;
         if (m.rank == 0) {
-            m.peer_frame = m.frame.p;
-        } else if (cudaIpcOpenMemHandle(&m.peer_frame, handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            P.peer_frame = P.frame.p;
+        } else if (cudaIpcOpenMemHandle(&P.peer_frame, handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
             cudaGetLastError();
-            m.peer_frame = nullptr;
+            P.peer_frame = nullptr;
             ok = 0;
         }
         // all ranks must agree before anybody waits on a flag a peer could never set: gather one status byte per rank
@@ -624,26 +631,27 @@ public:
         for (unsigned char v : all)
             if (!v) mPeerFrameUnavailable = true;
         if (mPeerFrameUnavailable) {
-            if (m.peer_frame && m.rank != 0) cudaIpcCloseMemHandle(m.peer_frame);
-            m.peer_frame = nullptr;
+            if (P.peer_frame && m.rank != 0) cudaIpcCloseMemHandle(P.peer_frame);
+            P.peer_frame = nullptr;
             return;
         }
-        m.frame_pixels = pixels;
-        m.step = 0;
+        P.frame_pixels = pixels;
+        P.step = 0;
     }
 
     // Multi-process frame through peer memory: every rank's K4 stores its finished pixels into rank 0's frame; flag words say which
     // chunk of which rank has landed; rank 0 downloads (or hands over) each stretch of the frame as soon as all ranks have delivered it.
     bool render_peer(Member &m, const ShardGeom &g0, const vt_ray *rays, bool dev_ptrs, uint32_t spp, uint64_t seed, float weight, float *fb,
-                     uint64_t *live_out, cudaStream_t stream) {
+                     uint64_t *live_out, cudaStream_t stream, int slot) {
         const ShardGeom g = g0.of(m.rank), sched = g0.of(0);
         const bool root = m.rank == 0;
-        if (!mPeerFrameUnavailable) ensure_peer_frame(g0.n);
+        Member::PeerFrame &P = m.pf[slot];
+        if (!mPeerFrameUnavailable) ensure_peer_frame(g0.n, slot);
         if (mPeerFrameUnavailable) return false;
-        const uint32_t step = ++m.step;
-        unsigned char *base = static_cast<unsigned char *>(m.peer_frame);
+        const uint32_t step = ++P.step;
+        unsigned char *base = static_cast<unsigned char *>(P.peer_frame);
         float *frame = reinterpret_cast<float *>(base);
-        uint32_t *flags = reinterpret_cast<uint32_t *>(base + frame_flag_offset(m.frame_pixels));
+        uint32_t *flags = reinterpret_cast<uint32_t *>(base + frame_flag_offset(P.frame_pixels));
         uint32_t *consumed = flags + (uint64_t)mWorld * kMaxChunks;
         cudaStream_t st = dev_ptrs ? stream : m.stream;
         uint32_t chunk = 0;
@@ -668,7 +676,7 @@ public:
             }
             chunk++;
         };
-        member_render(m, g, rays, dev_ptrs, spp, seed, weight, nullptr, live_out != nullptr, st, &sched, landed, frame, consumed, step);
+        member_render(m, g, rays, dev_ptrs, spp, seed, weight, nullptr, live_out != nullptr, st, &sched, landed, frame, consumed, step, slot);
         if (root) {  // the frame may be overwritten by the next step once everything above has run
             VT_CUDA(vt_launch_flag_set(consumed, step, st));
             mLaunches++;
@@ -737,7 +745,11 @@ public:
         if (mWorld > 1) {
             const char *gather = std::getenv("VT_GROUP_GATHER");
             if (!(gather && std::string(gather) == "nccl")) {  // default: K4 stores into rank 0's frame over NVLink (peer memory)
-                if (render_peer(m, g0, rays, dev_ptrs, spp, seed, weight, fb, live_out, stream)) return;
+                const int slot = (flags & VT_GROUP_FRAME_SLOT1) ? 1 : 0;
+                if (slot && !dev_ptrs) throw std::runtime_error("vt_group_render_diffuse_wave: VT_GROUP_FRAME_SLOT1 needs device pointers (host-pointer calls are synchronous)");
+                if (slot && env_int("VT_GROUP_DEV_LANES", 1) > 1) throw std::runtime_error("vt_group_render_diffuse_wave: frame slots and VT_GROUP_DEV_LANES > 1 exclude each other");
+                if (render_peer(m, g0, rays, dev_ptrs, spp, seed, weight, fb, live_out, stream, slot)) return;
+                if (slot) throw std::runtime_error("vt_group_render_diffuse_wave: VT_GROUP_FRAME_SLOT1 needs the peer-memory frame");
             }
         }
         const bool pipelined = !dev_ptrs && mWorld > 1 && env_int("VT_GROUP_PIPELINE", 1) != 0;
