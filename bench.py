@@ -559,9 +559,18 @@ def run_ours(args):
     h_rays[:] = rays
     h_fb = h_fb_t.numpy().view(np.float32).reshape(n, 3)
     e2e_steps = max(1, steps)
+    e2e_async = False
     if world == 1:
-        e2e_call = "vt_accel_render_diffuse_wave: host rays in, host RGBFFF framebuffer out"
         h2d_step, d2h_step = n * 32, n * 12
+        if fif > 1:
+            # two frames in flight through the split call: every step still uploads its rays and lands its own image in host memory
+            e2e_async = True
+            e2e_call = ("vt_accel_render_diffuse_wave_begin / _wait, two frames in flight: host rays in, host RGBFFF framebuffer out "
+                        "(each step its own pinned framebuffer)")
+            h_fb2_t = pinned(n * 12)
+            h_fbs = [h_fb, h_fb2_t.numpy().view(np.float32).reshape(n, 3)]
+        else:
+            e2e_call = "vt_accel_render_diffuse_wave: host rays in, host RGBFFF framebuffer out"
 
         def e2e_step(it):
             return accel.render_diffuse_wave(h_rays, SPP, seed=seed0 + it, weight=1.0, out=h_fb)[1]
@@ -597,8 +606,16 @@ def run_ours(args):
     with clocks:
         sync_all()
         t0 = time.perf_counter()
-        for it in range(e2e_steps):
-            e2e_step(warmup + it)
+        if e2e_async:
+            for it in range(e2e_steps):
+                if it >= 2:
+                    accel.render_diffuse_wave_wait()
+                accel.render_diffuse_wave_begin(h_rays, SPP, seed0 + warmup + it, 1.0, h_fbs[it % 2])
+            for it in range(min(2, e2e_steps)):
+                accel.render_diffuse_wave_wait()
+        else:
+            for it in range(e2e_steps):
+                e2e_step(warmup + it)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
     launches += launch_count() - l0

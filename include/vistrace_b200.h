@@ -515,6 +515,14 @@ int vt_accel_get_layout(const vt_accel *accel);
  * live_out (nullable) receives the number of bounce rays spawned. */
 int vt_accel_render_diffuse_wave(vt_accel *accel, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed,
                                  float weight, float *framebuffer_rgb, uint64_t *live_out);
+/* The same call split in two, so that a host can keep TWO frames in flight: _begin enqueues the frame (uploads, kernels, download) and
+ * returns; _wait blocks until the OLDEST frame begun on this handle is complete in its framebuffer (frames complete in the order they
+ * were begun; at most two may be outstanding).  Frame k's last tiles, launch tails and download then run under frame k + 1's first
+ * uploads and kernels.  rays and framebuffer_rgb must stay valid (and pinned, for the copies to be asynchronous) until the frame's
+ * _wait returns; consecutive frames need different framebuffers. */
+int vt_accel_render_diffuse_wave_begin(vt_accel *accel, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight,
+                                       float *framebuffer_rgb);
+int vt_accel_render_diffuse_wave_wait(vt_accel *accel);
 
 /* Rays rejected by the argument rules during the last synchronous traverse. */
 uint64_t vt_accel_invalid_rays(const vt_accel *accel);

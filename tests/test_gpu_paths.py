@@ -198,3 +198,45 @@ def test_per_ray_statistics_add_up(vt):
     tot_steps, tot_tests = accel.traverse_stats(rays)
     assert int(steps.sum()) == tot_steps and int(tests.sum()) == tot_tests
     assert steps.max() > 2 * steps.mean()  # a few grazing rays are far longer than the rest: what bounds small launches
+
+
+def test_two_host_frames_in_flight_equal_the_synchronous_frames(vt):
+    """vt_accel_render_diffuse_wave_begin / _wait: frames begun back to back (two in flight, alternating staging buffers, tiles of
+    consecutive frames sharing the wave lanes) land the images of the synchronous call, in order; a third begin is refused."""
+    import torch
+
+    from vistrace_b200 import abi, scenes
+
+    scene = scenes.scene_terrain_closed(200)
+    rays = scenes.pinhole_rays(400, 225, (0.0, -330.0, 200.0), (0.0, 0.0, 10.0))
+    n, spp = len(rays), 3
+    accel = vt.Accel(0).populate(scene)
+    want = [accel.render_diffuse_wave(rays, spp, seed=40 + k, weight=0.25)[0].copy() for k in range(5)]
+    h_rays_t = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+    h_rays = h_rays_t.numpy().view(abi.RAY)
+    h_rays[:] = rays
+    fb_t = [torch.empty(n * 12, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    fbs = [t.numpy().view(np.float32).reshape(n, 3) for t in fb_t]
+    import os
+    os.environ["VT_WAVE_TILE"] = "20000"  # several tiles per frame over the four lanes
+    try:
+        got = []
+        for k in range(5):
+            if k >= 2:
+                accel.render_diffuse_wave_wait()
+                got.append(fbs[k % 2].copy())  # frame k - 2 is complete; its buffer is about to be reused
+            fbs[k % 2][:] = -1.0
+            accel.render_diffuse_wave_begin(h_rays, spp, 40 + k, 0.25, fbs[k % 2])
+        with pytest.raises(RuntimeError, match="two frames"):
+            accel.render_diffuse_wave_begin(h_rays, spp, 99, 0.25, fbs[0])
+        for k in (3, 4):
+            accel.render_diffuse_wave_wait()
+            got.append(fbs[k % 2].copy())
+        with pytest.raises(RuntimeError, match="no frame in flight"):
+            accel.render_diffuse_wave_wait()
+    finally:
+        del os.environ["VT_WAVE_TILE"]
+    for k in range(5):
+        np.testing.assert_array_equal(got[k], want[k], err_msg=f"frame {k}")
+    # the synchronous call still works afterwards
+    np.testing.assert_array_equal(accel.render_diffuse_wave(rays, spp, seed=40, weight=0.25)[0], want[0])

@@ -31,6 +31,8 @@ SYMBOLS = {
     "vt_accel_traverse": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_traverse_stats": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp]),
     "vt_accel_traverse_ray_stats": (_i32, [_vp, _vp, _u64, _u32, _vp]),
+    "vt_accel_render_diffuse_wave_begin": (_i32, [_vp, _vp, _u64, _u32, _u64, C.c_float, _vp]),
+    "vt_accel_render_diffuse_wave_wait": (_i32, [_vp]),
     "vt_accel_traverse_cones": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "vt_accel_trace_result": (_i32, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "vt_accel_bounce_rays": (_i32, [_vp, _vp, _u64, _u32, _u64, _vp, _vp, _u32, _vp]),
@@ -583,6 +585,15 @@ class Accel:
         _check(self.L.vt_accel_render_diffuse_wave(self.h, rays.ctypes.data, len(rays), spp, seed, weight, fb.ctypes.data, C.addressof(live)),
                "vt_accel_render_diffuse_wave")
         return fb, live.value
+
+    def render_diffuse_wave_begin(self, rays, spp, seed, weight, out):
+        """Asynchronous form: enqueue the frame (rays / out: pinned numpy arrays that stay alive) and return; at most two in flight."""
+        _check(self.L.vt_accel_render_diffuse_wave_begin(self.h, rays.ctypes.data, len(rays), spp, seed, weight, out.ctypes.data),
+               "vt_accel_render_diffuse_wave_begin")
+
+    def render_diffuse_wave_wait(self):
+        """Block until the oldest frame begun with render_diffuse_wave_begin is complete in its framebuffer."""
+        _check(self.L.vt_accel_render_diffuse_wave_wait(self.h), "vt_accel_render_diffuse_wave_wait")
 
     def trace_paths_device(self, d_rays, n, bounces, sun_dir, sun_rgb, seed, weight, d_fb, want_counts=False, compact=True, stream=None):
         """Path waves with compaction over device-resident primary rays; returns the per-wave ray counts when asked (synchronous then)."""

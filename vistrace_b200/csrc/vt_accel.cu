@@ -1117,30 +1117,32 @@ void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp,
     }
 }
 
-void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb,
-                                    uint64_t *live_out) {
+// The frame is ENQUEUED here (tiles round-robin over the wave lanes, uploads on the copy stream) and awaited in RenderDiffuseWaveWait:
+// the synchronous call is the two back to back; a caller that begins frame k + 1 before it waits for frame k keeps two frames in
+// flight — frame k's last tiles, launch tails and download run under frame k + 1's first uploads and kernels.  Tiles of consecutive
+// frames follow each other on the same lane streams, so a lane's scratch needs no extra fencing; the ray staging buffer alternates.
+void AccelStruct::RenderDiffuseWaveBegin(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb, bool count_live) {
     check_built(mAccelBuilt);
-    if (live_out) *live_out = 0;
-    if (n == 0) return;
     if (!rays || !fb) throw std::runtime_error("render_diffuse_wave: rays and framebuffer must not be null");
+    if (mWaveFrames.size() >= 2) throw std::runtime_error("render_diffuse_wave: two frames are already in flight (wait for one first)");
     VT_CUDA(cudaSetDevice(mDevice));
     DeviceScene &D = *mpDevice;
+    const uint64_t *live_out = count_live ? &n : nullptr;  // only its non-nullness is used below
     D.live.ensure(1);
     auto next_counter = [&]() { return D.counters.p + 2 * (D.next_slot.fetch_add(1) % kCounterSlots); };
     // tiles round-robin over three streams: H2D(rays) | K1 K2 K3 K1 K4 | D2H(framebuffer tile) overlap across tiles
     const uint64_t tile = (uint64_t)std::max(1, env_int("VT_WAVE_TILE", 1 << 19));
-    VT_CUDA(cudaMemsetAsync(D.live.p, 0, sizeof(unsigned long long), D.own_stream));
-    VT_CUDA(cudaStreamSynchronize(D.own_stream));
+    if (count_live) {
+        if (!mWaveFrames.empty()) throw std::runtime_error("render_diffuse_wave: the live-ray count needs the handle to itself");
+        VT_CUDA(cudaMemsetAsync(D.live.p, 0, sizeof(unsigned long long), D.own_stream));
+        VT_CUDA(cudaStreamSynchronize(D.own_stream));
+    }
     const int n_lanes = std::max(1, std::min(8, env_int("VT_WAVE_LANES", 4)));
     for (int i = 0; i < n_lanes; i++)
         if (!D.lanes[i].stream) VT_CUDA(cudaStreamCreateWithFlags(&D.lanes[i].stream, cudaStreamNonBlocking));
     // VT_WAVE_TRACE=1: one line per tile with the stream-time (ms since the first submission) at which each stage finished
     const bool trace = env_int("VT_WAVE_TRACE", 0) != 0;
-    struct TileTrace {
-        uint64_t base, m;
-        int lane;
-        cudaEvent_t ev[6];  // after H2D, K1 primary, K2+K3, K1 bounce, K4, D2H
-    };
+    using TileTrace = WaveFrame::TileTrace;
     std::vector<TileTrace> tiles;
     cudaEvent_t ev_begin = nullptr;
     if (trace) {
@@ -1159,8 +1161,10 @@ void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp
         const int per_sm = env_int("VT_WAVE_CTAS_PER_SM", 6);
         if (per_sm > 0) tile_cfg.grid = std::min(D.cfg.grid, D.sm_count * per_sm);
     }
-    // uploads go through one copy stream into a frame-sized staging buffer (see DeviceScene::wave_rays)
-    D.wave_rays.ensure(n);
+    // uploads go through one copy stream into a frame-sized staging buffer (see DeviceScene::wave_rays); consecutive frames alternate
+    // between two of them: frame k + 1's uploads run while frame k's kernels still read theirs
+    DevBuf<vt_ray> &staging = (mWaveFrameCount++ & 1) ? D.wave_rays_b : D.wave_rays;
+    staging.ensure(n);
     if (!D.copy_stream) VT_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
     size_t n_uploads = 0;
     auto upload_tile = [&](uint64_t base, uint64_t m, cudaStream_t consumer) -> const vt_ray * {
@@ -1170,10 +1174,10 @@ void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp
             D.upload_done.push_back(e);
         }
         cudaEvent_t done = D.upload_done[n_uploads++];
-        VT_CUDA(cudaMemcpyAsync(D.wave_rays.p + base, rays + base, m * sizeof(vt_ray), cudaMemcpyHostToDevice, D.copy_stream));
+        VT_CUDA(cudaMemcpyAsync(staging.p + base, rays + base, m * sizeof(vt_ray), cudaMemcpyHostToDevice, D.copy_stream));
         VT_CUDA(cudaEventRecord(done, D.copy_stream));
         VT_CUDA(cudaStreamWaitEvent(consumer, done, 0));
-        return D.wave_rays.p + base;
+        return staging.p + base;
     };
     int li = 0, tiles_since_fence = 0;
     // the first tiles are small so the first kernel starts after a short upload; sizes double up to `tile`
@@ -1218,22 +1222,54 @@ void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp
         mark(tt, 5, l.stream);
         if (trace) tiles.push_back(tt);
     }
-    for (int i = 0; i < n_lanes; i++) VT_CUDA(cudaStreamSynchronize(D.lanes[i].stream));
-    if (trace) {
-        for (TileTrace &t : tiles) {
+    WaveFrame f;
+    f.n_lanes = n_lanes;
+    for (int i = 0; i < n_lanes; i++) {
+        VT_CUDA(cudaEventCreateWithFlags(&f.done[i], cudaEventDisableTiming | cudaEventBlockingSync));
+        VT_CUDA(cudaEventRecord(f.done[i], D.lanes[i].stream));
+    }
+    f.tiles = std::move(tiles);
+    f.ev_begin = ev_begin;
+    mWaveFrames.push_back(std::move(f));
+}
+
+// Waits for the OLDEST frame in flight (frames complete in the order they were begun).
+void AccelStruct::RenderDiffuseWaveWait() {
+    if (mWaveFrames.empty()) throw std::runtime_error("render_diffuse_wave: no frame in flight");
+    VT_CUDA(cudaSetDevice(mDevice));
+    WaveFrame f = std::move(mWaveFrames.front());
+    mWaveFrames.pop_front();
+    cudaError_t err = cudaSuccess;
+    for (int i = 0; i < f.n_lanes; i++) {
+        const cudaError_t e = cudaEventSynchronize(f.done[i]);
+        if (e != cudaSuccess) err = e;
+        cudaEventDestroy(f.done[i]);
+    }
+    VT_CUDA(err);
+    if (f.ev_begin) {
+        for (WaveFrame::TileTrace &t : f.tiles) {
             float ms[6];
             for (int k = 0; k < 6; k++) {
-                VT_CUDA(cudaEventElapsedTime(&ms[k], ev_begin, t.ev[k]));
+                VT_CUDA(cudaEventElapsedTime(&ms[k], f.ev_begin, t.ev[k]));
                 cudaEventDestroy(t.ev[k]);
             }
             std::fprintf(stderr, "[wave] tile base %8llu rays %7llu lane %d: H2D %.3f  K1p %.3f  K2K3 %.3f  K1b %.3f  K4 %.3f  D2H %.3f ms\n",
                          (unsigned long long)t.base, (unsigned long long)t.m, t.lane, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5]);
         }
-        cudaEventDestroy(ev_begin);
+        cudaEventDestroy(f.ev_begin);
     }
+}
+
+void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb,
+                                    uint64_t *live_out) {
+    if (live_out) *live_out = 0;
+    if (n == 0) return;
+    if (!mWaveFrames.empty()) throw std::runtime_error("render_diffuse_wave: frames begun asynchronously are still in flight");
+    RenderDiffuseWaveBegin(rays, n, spp, seed, weight, fb, live_out != nullptr);
+    RenderDiffuseWaveWait();
     if (live_out) {
         unsigned long long v = 0;
-        VT_CUDA(cudaMemcpy(&v, D.live.p, sizeof(v), cudaMemcpyDeviceToHost));
+        VT_CUDA(cudaMemcpy(&v, mpDevice->live.p, sizeof(v), cudaMemcpyDeviceToHost));
         *live_out = v;
     }
 }
@@ -1805,6 +1841,23 @@ int vt_bsp_get_static_prop(const uint8_t *file, uint64_t size, uint32_t index, v
     VT_TRY
     if (!file || !out) throw std::runtime_error("null argument");
     vt::BspStaticProp(file, size, index, out);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_render_diffuse_wave_begin(vt_accel *a, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *framebuffer_rgb) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    if (n == 0) throw std::runtime_error("render_diffuse_wave_begin: empty frame");
+    a->impl.RenderDiffuseWaveBegin(rays, n, spp, seed, weight, framebuffer_rgb, false);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_accel_render_diffuse_wave_wait(vt_accel *a) {
+    VT_TRY
+    if (!a) throw std::runtime_error("null argument");
+    a->impl.RenderDiffuseWaveWait();
     return 0;
     VT_CATCH(1)
 }

@@ -111,7 +111,7 @@ struct DeviceScene {
     DevBuf<unsigned long long> live;
     // host-pointer waves: the whole frame's rays are staged here by ONE copy stream, tile after tile, so an upload never
     // waits for the lane (stream) its tile will run on; upload_done[k] gates tile k's kernels
-    DevBuf<vt_ray> wave_rays;
+    DevBuf<vt_ray> wave_rays, wave_rays_b;  // two: consecutive frames in flight alternate (AccelStruct::RenderDiffuseWaveBegin)
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> upload_done;
     // K5 (device refit) state, built on the first refit of a resident quad hierarchy
@@ -151,6 +151,7 @@ struct DeviceScene {
         for (int i = 0; i < 3; i++) path.queue[i].release();
         path.shits.release(), path.brays.release(), path.srays.release(), path.counts.release(), path.throughput.release();
         wave_rays.release();
+        wave_rays_b.release();
         for (cudaEvent_t e : upload_done) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         refit_in.release();

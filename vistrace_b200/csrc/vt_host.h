@@ -11,10 +11,13 @@
 #include <mutex>
 #include <type_traits>
 #include <utility>
+#include <deque>
 #include <vector>
 
 #include "../../include/vistrace_b200.h"
 #include "vt_device.h"
+
+struct CUevent_st;  // cudaEvent_t is `CUevent_st *`; this header is also read by translation units without the CUDA headers
 
 namespace vt {
 
@@ -184,6 +187,20 @@ class AccelStruct {
     DeviceScene *mpDevice = nullptr;
     uint64_t mInvalidRays = 0;
     uint64_t mLaunches = 0;
+    // host-pointer diffuse waves in flight (RenderDiffuseWaveBegin / Wait): per frame one "lane finished" event per wave lane
+    struct WaveFrame {
+        struct TileTrace {
+            uint64_t base, m;
+            int lane;
+            ::CUevent_st *ev[6];  // cudaEvent_t; after H2D, K1 primary, K2+K3, K1 bounce, K4, D2H (VT_WAVE_TRACE)
+        };
+        ::CUevent_st *done[8] = {};  // cudaEvent_t (this header is also read by translation units without the CUDA headers)
+        int n_lanes = 0;
+        std::vector<TileTrace> tiles;
+        ::CUevent_st *ev_begin = nullptr;
+    };
+    std::deque<WaveFrame> mWaveFrames;
+    uint64_t mWaveFrameCount = 0;
     double mRefitRebuildRatio = 0.0;  // > 0: vt_accel_refit rebuilds from scratch once RefitQuality() exceeds it
     uint64_t mRebuilds = 0;
 
@@ -278,6 +295,9 @@ public:
     // The same wave with the framebuffer as its only result: HOST rays in, HOST RGBFFF image out
     // (fb[i] = weight * albedo_i * escaped fraction of pixel i's bounce rays), tiled over streams like TraceDiffuseWave.
     void RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb, uint64_t *live_out);
+    // the same, split: enqueue a frame / wait for the oldest frame in flight (at most two): vt_accel_render_diffuse_wave_begin / _wait
+    void RenderDiffuseWaveBegin(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb, bool count_live);
+    void RenderDiffuseWaveWait();
 
     // Fold a diffuse wave into an RGBFFF framebuffer (device pointers only): see k_accumulate_sky.
     void AccumulateSky(const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n, uint32_t spp, float weight, float *fb,
