@@ -579,17 +579,23 @@ def run_ours(args):
         # tiles through its own PCIe link, a one-byte ncclAllGather is the barrier; VT_BENCH_E2E_GATHER=1 measures the round-2 path
         # instead (finished pixels stored into rank 0's device frame over NVLink, rank 0 downloads the whole image through one link)
         shared_frame = None
+        shared_frames = []
         if os.environ.get("VT_BENCH_E2E_GATHER", "0") == "0":
-            name = f"vt_bench_frame_{os.environ.get('MASTER_PORT', '0')}"
-            if rank == 0:
-                shared_frame = shard.SharedPinnedFrame(name, n * 12, create=True)
-            dist.barrier()
-            if rank != 0:
-                shared_frame = shard.SharedPinnedFrame(name, n * 12, create=False)
-            h_fb = shared_frame.array(np.float32, (n, 3))
+            for k in range(fif):
+                name = f"vt_bench_frame_{os.environ.get('MASTER_PORT', '0')}_{k}"
+                fr = shard.SharedPinnedFrame(name, n * 12, create=True) if rank == 0 else None
+                dist.barrier()
+                if rank != 0:
+                    fr = shard.SharedPinnedFrame(name, n * 12, create=False)
+                shared_frames.append(fr)
+            shared_frame = shared_frames[0]
+            h_fbs = [fr.array(np.float32, (n, 3)) for fr in shared_frames]
+            h_fb = h_fbs[0]
+            e2e_async = fif > 1
             e2e_call = ("vt_group_render_diffuse_wave(VT_GROUP_SHARED_HOST_FRAME), one process per GPU: each rank uploads the host rays of its own "
                         "tiles, traces them and lands its tiles of the RGBFFF frame in host memory shared by all ranks (its own PCIe link); "
-                        "complete on every rank after a one-byte ncclAllGather")
+                        "complete on every rank after a one-byte ncclAllGather"
+                        + ("; two frames in flight (VT_GROUP_ASYNC + vt_group_wait_frame), each step its own shared frame" if fif > 1 else ""))
             d2h_step = len(idx) * 12
         else:
             e2e_call = ("vt_group_render_diffuse_wave (one process per GPU): each rank uploads the host rays of its own tiles, traces them, "
@@ -607,12 +613,15 @@ def run_ours(args):
         sync_all()
         t0 = time.perf_counter()
         if e2e_async:
+            begin = (lambda it: accel.render_diffuse_wave_begin(h_rays, SPP, seed0 + warmup + it, 1.0, h_fbs[it % 2])) if world == 1 else \
+                    (lambda it: group.render_diffuse_wave_begin(h_rays, SPP, seed0 + warmup + it, 1.0, h_fbs[it % 2]))
+            wait = accel.render_diffuse_wave_wait if world == 1 else group.wait_frame
             for it in range(e2e_steps):
                 if it >= 2:
-                    accel.render_diffuse_wave_wait()
-                accel.render_diffuse_wave_begin(h_rays, SPP, seed0 + warmup + it, 1.0, h_fbs[it % 2])
+                    wait()
+                begin(it)
             for it in range(min(2, e2e_steps)):
-                accel.render_diffuse_wave_wait()
+                wait()
         else:
             for it in range(e2e_steps):
                 e2e_step(warmup + it)
@@ -621,7 +630,8 @@ def run_ours(args):
     launches += launch_count() - l0
     if world > 1 and shared_frame is not None:
         sync_all()
-        shared_frame.close()
+        for fr in shared_frames:
+            fr.close()
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = rays_per_step / (e2e_s / e2e_steps) / 1e6
     h2d_step, d2h_step = sum_over_ranks(h2d_step), sum_over_ranks(d2h_step)  # whole job, like `value`: bytes all ranks move per step

@@ -649,8 +649,14 @@ int vt_shard_geometry(uint64_t n, int world, int rank, uint64_t tile, uint64_t *
  * in flight: one frame's launch tails run under the other frame's bulk (profiles/r2_tail_sharing.md: 1.4x on a 1/8-frame shard).
  * Calls on the SAME slot must be issued in stream order on one stream, in the same order on every rank. */
 #define VT_GROUP_FRAME_SLOT1 32u
+/* With VT_GROUP_SHARED_HOST_FRAME: the call enqueues the frame and returns; vt_group_wait_frame blocks until the OLDEST such frame is
+ * complete in its shared framebuffer on every rank (at most two in flight; consecutive frames need different framebuffers; rays and
+ * framebuffer stay valid until the frame's wait returns; live_out must be NULL).  Two frames in flight hide one frame's last tiles,
+ * launch tails and download under the next frame's uploads and kernels. */
+#define VT_GROUP_ASYNC 64u
 int vt_group_render_diffuse_wave(vt_group *group, const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight,
                                  float *framebuffer_rgb, uint64_t *live_out, uint32_t flags, void *stream);
+int vt_group_wait_frame(vt_group *group); /* collective like the call that began the frame */
 
 /* Sample-index sharding (every rank renders the whole frame for its own samples): sum the per-rank DEVICE images into
  * rank 0's, in place — one ncclReduce over NVLink, enqueued on `stream`.  Multi-process groups. */

@@ -57,7 +57,31 @@ for it in range(3):
     group.render_diffuse_wave(rays, spp, seed=9, weight=0.5, out=shared, want_live=False, shared_frame=True)
     np.testing.assert_array_equal(shared, want)
     dist.barrier()
+# two such frames in flight (VT_GROUP_ASYNC): frame k + 1 is begun before frame k is awaited
+frame_b = shard.SharedPinnedFrame(f"vt_test_frame_b_{os.environ.get('MASTER_PORT', '0')}", n * 12, create=True) if rank == 0 else None
 dist.barrier()
+if rank != 0:
+    frame_b = shard.SharedPinnedFrame(f"vt_test_frame_b_{os.environ.get('MASTER_PORT', '0')}", n * 12, create=False)
+pair = [shared, frame_b.array(np.float32, (n, 3))]
+seeds = [9, 11, 9, 11, 9]
+img11 = group.render_diffuse_wave(rays, spp, seed=11, weight=0.5, want_live=False)[0]  # collective: every rank calls it; complete on rank 0
+want11 = torch.from_numpy(np.ascontiguousarray(img11) if rank == 0 else np.zeros((n, 3), np.float32)).to(dev)
+dist.broadcast(want11, src=0)
+wants = {9: want, 11: want11.cpu().numpy()}
+landed = []
+for k, seed in enumerate(seeds):
+    if k >= 2:
+        group.wait_frame()
+        landed.append(pair[k % 2].copy())
+        dist.barrier()  # everybody has looked at the frame before anybody's GPU overwrites it
+    group.render_diffuse_wave_begin(rays, spp, seed, 0.5, pair[k % 2])
+for k in (3, 4):
+    group.wait_frame()
+    landed.append(pair[k % 2].copy())
+for k, seed in enumerate(seeds):
+    np.testing.assert_array_equal(landed[k], wants[seed], err_msg=f"frame {k} in flight")
+dist.barrier()
+frame_b.close()
 frame.close()
 
 # device-resident shards -> frame-sized device image on rank 0

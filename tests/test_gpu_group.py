@@ -116,6 +116,6 @@ def test_multi_process_group_two_ranks_nccl(vt):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29573", f"{ROOT}/tests/group_worker.py"], capture_output=True, text=True, timeout=600)
+                        "--master-port", "29573", f"{ROOT}/tests/group_worker.py"], capture_output=True, text=True, timeout=150)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "GROUP_OK" in r.stdout

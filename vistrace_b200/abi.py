@@ -22,6 +22,7 @@ VT_TRAVERSE_ANY_HIT = 2
 VT_TRAVERSE_QUEUE_ATTRS = 4
 VT_GROUP_SHARED_HOST_FRAME = 16
 VT_GROUP_FRAME_SLOT1 = 32
+VT_GROUP_ASYNC = 64
 VT_TEXEL_WIDE, VT_TEXEL_DIV_255, VT_TEXEL_DIV_65535, VT_TEXEL_DIV_1 = 0x100, 0, 1, 2
 VT_PATHS_NO_COMPACTION = 8
 VT_LOBE_NONE, VT_LOBE_DIFFUSE_REFLECTION = 0, 1

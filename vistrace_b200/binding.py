@@ -91,6 +91,7 @@ SYMBOLS = {
     "vt_group_reduce_device": (_i32, [_vp, _vp, _u64, _vp]),
     "vt_group_all_gather_device": (_i32, [_vp, _vp, _u64, _vp]),
     "vt_group_launch_count": (_u64, [_vp]),
+    "vt_group_wait_frame": (_i32, [_vp]),
     "vt_last_error": (C.c_char_p, []),
 }
 
@@ -738,6 +739,14 @@ class Group:
                                                    C.addressof(live) if want_live else None, abi.VT_GROUP_SHARED_HOST_FRAME if shared_frame else 0, None),
                "vt_group_render_diffuse_wave")
         return fb, live.value
+
+    def render_diffuse_wave_begin(self, rays, spp, seed, weight, shared_out):
+        """Enqueue one frame into the host frame all processes share (VT_GROUP_SHARED_HOST_FRAME | VT_GROUP_ASYNC); at most two in flight."""
+        _check(self.L.vt_group_render_diffuse_wave(self.h, rays.ctypes.data, len(rays), spp, seed, weight, shared_out.ctypes.data, None,
+                                                   abi.VT_GROUP_SHARED_HOST_FRAME | abi.VT_GROUP_ASYNC, None), "vt_group_render_diffuse_wave")
+
+    def wait_frame(self):
+        _check(self.L.vt_group_wait_frame(self.h), "vt_group_wait_frame")
 
     def render_diffuse_wave_device(self, d_rays_shard, n, spp, seed, weight, d_fb, stream=None, slot=0):
         """Device-resident shard in, frame-sized device image out (complete on rank 0); enqueued on `stream`.  slot 0 / 1: the group's

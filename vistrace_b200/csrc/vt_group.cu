@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <memory>
 #include <thread>
@@ -177,6 +178,8 @@ public:
 
 private:
     std::vector<std::unique_ptr<Member>> mMembers;
+    std::deque<cudaEvent_t> mSharedFrames;  // VT_GROUP_SHARED_HOST_FRAME | VT_GROUP_ASYNC frames in flight (at most two)
+    uint64_t mSharedFrameCount = 0;
     uint32_t mWorld = 1;
     bool mMultiProcess = false;
     bool mPeerFrameUnavailable = false;  // CUDA IPC could not map rank 0's frame on some rank: every rank uses the NCCL gather instead
@@ -451,7 +454,7 @@ public:
     void member_render(Member &m, const ShardGeom &g, const vt_ray *rays, bool rays_on_device, uint32_t spp, uint64_t seed, float weight,
                        float *fb_host, bool count_live, cudaStream_t caller_stream, const ShardGeom *sched = nullptr,
                        const std::function<void(uint64_t, uint64_t, cudaStream_t)> &after_chunk = nullptr, float *frame_target = nullptr,
-                       const uint32_t *consumed_flag = nullptr, uint32_t step = 0, int slot = 0) {
+                       const uint32_t *consumed_flag = nullptr, uint32_t step = 0, int slot = 0, bool staging_alt = false) {
         AccelStruct &A = m.accel->impl;
         if (!A.Built()) throw std::runtime_error("vt_group: populate the group first");
         VT_CUDA(cudaSetDevice(m.device));
@@ -492,7 +495,7 @@ public:
         uint64_t chunk_tiles = rays_on_device ? chunk_tiles_max
                                               : std::max<uint64_t>(1, std::min(chunk_tiles_max, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)(chunk_records / 8))) / g.tile));
         if (!rays_on_device) {
-            D.wave_rays.ensure(std::max<uint64_t>(1, L));
+            (staging_alt ? D.wave_rays_b : D.wave_rays).ensure(std::max<uint64_t>(1, L));
             if (!D.copy_stream) VT_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
         }
         size_t n_uploads = 0;
@@ -536,10 +539,11 @@ public:
                     D.upload_done.push_back(ev);
                 }
                 cudaEvent_t done = D.upload_done[n_uploads++];
-                copy_tiles(g, j0, j1, sizeof(vt_ray), D.wave_rays.p, const_cast<vt_ray *>(rays), false, cudaMemcpyHostToDevice, D.copy_stream);
+                vt_ray *staging = (staging_alt ? D.wave_rays_b : D.wave_rays).p;  // consecutive frames in flight alternate
+                copy_tiles(g, j0, j1, sizeof(vt_ray), staging, const_cast<vt_ray *>(rays), false, cudaMemcpyHostToDevice, D.copy_stream);
                 VT_CUDA(cudaEventRecord(done, D.copy_stream));
                 VT_CUDA(cudaStreamWaitEvent(st, done, 0));
-                d_rays = D.wave_rays.p + cb;
+                d_rays = staging + cb;
             }
             VtSlotMap map;
             map.local_base = cb, map.tile = g.tile, map.stride = g.world, map.phase = g.rank;
@@ -730,13 +734,23 @@ public:
             // own PCIe link — no gather at all, N links instead of rank 0's one — and a one-byte ncclAllGather behind the copies is the
             // barrier that tells every rank the frame is complete
             if (!fb) throw std::runtime_error("vt_group_render_diffuse_wave: the shared framebuffer must not be null");
-            member_render(m, g, rays, false, spp, seed, weight, fb, live_out != nullptr, st);
+            const bool async = (flags & VT_GROUP_ASYNC) != 0;
+            if (async && live_out) throw std::runtime_error("vt_group_render_diffuse_wave: live_out must be NULL with VT_GROUP_ASYNC");
+            if (mSharedFrames.size() >= (async ? 2u : 1u)) throw std::runtime_error("vt_group_render_diffuse_wave: frames are still in flight (vt_group_wait_frame)");
+            member_render(m, g, rays, false, spp, seed, weight, fb, live_out != nullptr, st, nullptr, nullptr, nullptr, nullptr, 0, 0, (mSharedFrameCount++ & 1) != 0);
             if (mWorld > 1) {
                 NcclApi &nccl = NcclApi::get();
                 if (!nccl.AllGather) throw std::runtime_error("ncclAllGather not found");
                 m.header.ensure(std::max<size_t>(256, mWorld));
                 VT_NCCL(nccl.AllGather(m.header.p + m.rank, m.header.p, 1, ncclUint8, m.comm, st));
                 mLaunches++;
+            }
+            if (async) {  // the frame is awaited by vt_group_wait_frame: this rank's copies and the barrier behind them are all on `st`
+                cudaEvent_t done;
+                VT_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming | cudaEventBlockingSync));
+                VT_CUDA(cudaEventRecord(done, st));
+                mSharedFrames.push_back(done);
+                return;
             }
             member_finish(m, live_out != nullptr, st);
             if (live_out) *live_out = m.live;
@@ -834,6 +848,18 @@ public:
         }
         member_finish(m, live_out != nullptr, st);
         if (live_out) *live_out = m.live;
+    }
+
+    // the oldest frame begun with VT_GROUP_ASYNC is complete in the shared host frame on every rank
+    void WaitFrame() {
+        if (mSharedFrames.empty()) throw std::runtime_error("vt_group_wait_frame: no frame in flight");
+        Member &m = *mMembers[0];
+        VT_CUDA(cudaSetDevice(m.device));
+        cudaEvent_t done = mSharedFrames.front();
+        mSharedFrames.pop_front();
+        const cudaError_t e = cudaEventSynchronize(done);
+        cudaEventDestroy(done);
+        VT_CUDA(e);
     }
 
     // sum of per-rank device buffers on rank 0 (sample-index sharding: every rank holds a partial image of the whole frame)
@@ -968,6 +994,14 @@ int vt_group_all_gather_device(vt_group *g, void *buf, uint64_t bytes_per_rank, 
     VT_TRY
     if (!g) throw std::runtime_error("null argument");
     g->impl.AllGatherDevice(buf, bytes_per_rank, (cudaStream_t)stream);
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_group_wait_frame(vt_group *g) {
+    VT_TRY
+    if (!g) throw std::runtime_error("null argument");
+    g->impl.WaitFrame();
     return 0;
     VT_CATCH(1)
 }
