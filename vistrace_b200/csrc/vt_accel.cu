@@ -190,6 +190,7 @@ void AccelStruct::JoinAttrUpload() {
 }
 
 AccelStruct::~AccelStruct() {
+    DrainWaveFrames();
     if (mAttrUpload.joinable()) mAttrUpload.join();
     if (mpDevice) {
         cudaSetDevice(mDevice);
@@ -460,6 +461,7 @@ void AccelStruct::Upload(const vt_scene &scene) {
 }
 
 void AccelStruct::Populate(const vt_scene &scene) {
+    DrainWaveFrames();
     PhaseTimer timer;
     Ingest(scene);
     timer.lap("ingest (Triangle ctor)");
@@ -478,6 +480,7 @@ void AccelStruct::Populate(const vt_scene &scene) {
 }
 
 void AccelStruct::PopulateWithBvh(const vt_scene &scene, const vt_node *nodes, uint64_t node_count, const uint64_t *prim_indices) {
+    DrainWaveFrames();
     Ingest(scene);
     if (!nodes || !prim_indices || node_count == 0) throw std::runtime_error("populate_with_bvh: null hierarchy");
     mAccel.nodes.assign(nodes, nodes + node_count);
@@ -571,6 +574,7 @@ const HostBvh &AccelStruct::Bvh() const {
 }
 
 void AccelStruct::Refit(const vt_scene &scene) {
+    DrainWaveFrames();
     if (mReplica) throw std::runtime_error("refit: this handle is a replica (vt_group): refit the group");
     if (!mAccelBuilt) throw std::runtime_error("refit: nothing built yet (use Populate)");
     if (scene.n_tris != mAccel.prim_indices.size()) throw std::runtime_error("refit: triangle count changed (use Populate to rebuild)");
@@ -649,6 +653,7 @@ void AccelStruct::Refit(const vt_scene &scene) {
 }
 
 void AccelStruct::RefitRange(const vt_tri_in *tris, uint64_t first, uint64_t count) {
+    DrainWaveFrames();
     if (mReplica) throw std::runtime_error("refit: this handle is a replica (vt_group): refit the group");
     if (!mAccelBuilt) throw std::runtime_error("refit: nothing built yet (use Populate)");
     if (count == 0) return;
@@ -1194,7 +1199,7 @@ void AccelStruct::RenderDiffuseWaveBegin(const vt_ray *rays, uint64_t n, uint32_
         l.fb.ensure(cap * 3);
         l.queue.ensure(cap * spp);
         l.queue_count.ensure(1);
-        if (++tiles_since_fence >= kCounterSlots / 2 - 16) {  // see TraceDiffuseWave: the counter ring must not wrap onto a live slot
+        if (++tiles_since_fence >= kCounterSlots / 4 - 8) {  // see TraceDiffuseWave: the counter ring must not wrap onto a live slot (two frames may be in flight)
             for (int i = 0; i < n_lanes; i++) VT_CUDA(cudaStreamSynchronize(D.lanes[i].stream));
             tiles_since_fence = 0;
         }
@@ -1231,6 +1236,16 @@ void AccelStruct::RenderDiffuseWaveBegin(const vt_ray *rays, uint64_t n, uint32_
     f.tiles = std::move(tiles);
     f.ev_begin = ev_begin;
     mWaveFrames.push_back(std::move(f));
+}
+
+// populate / refit / destruction: nothing may still be reading the scene or the staging buffers
+void AccelStruct::DrainWaveFrames() {
+    while (!mWaveFrames.empty()) {
+        try {
+            RenderDiffuseWaveWait();
+        } catch (const std::exception &) {  // a failed frame is dropped with its events; the caller's own operation reports what it finds
+        }
+    }
 }
 
 // Waits for the OLDEST frame in flight (frames complete in the order they were begun).

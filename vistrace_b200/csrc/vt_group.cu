@@ -301,6 +301,8 @@ public:
             }
             cudaSetDevice(m.device);
             cudaDeviceSynchronize();
+            for (cudaEvent_t e : mSharedFrames) cudaEventDestroy(e);  // frames begun with VT_GROUP_ASYNC and never awaited
+            mSharedFrames.clear();
             for (auto &P : m.pf) {
                 if (P.peer_frame && m.rank != 0) cudaIpcCloseMemHandle(P.peer_frame);
                 P.frame.release();

@@ -298,6 +298,7 @@ public:
     // the same, split: enqueue a frame / wait for the oldest frame in flight (at most two): vt_accel_render_diffuse_wave_begin / _wait
     void RenderDiffuseWaveBegin(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb, bool count_live);
     void RenderDiffuseWaveWait();
+    void DrainWaveFrames();
 
     // Fold a diffuse wave into an RGBFFF framebuffer (device pointers only): see k_accumulate_sky.
     void AccumulateSky(const vt_attr *attrs, const vt_hit *bounce_hits, uint64_t n, uint32_t spp, float weight, float *fb,
