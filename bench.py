@@ -334,6 +334,9 @@ def config5_side(args, torch, dist, dev, world, rank, local_rank, sync_all, max_
     d_fb = torch.zeros(n * 3, dtype=torch.float32, device=dev)
     h_fb = torch.empty(n * 3, dtype=torch.float32).pin_memory() if rank == 0 else None
     my_samples = list(range(rank, SPP5, world))
+    fif5 = 2 if (len(my_samples) > 1 and os.environ.get("VT_BENCH_FRAMES_IN_FLIGHT", "2") != "1") else 1
+    stream2 = torch.cuda.Stream() if fif5 > 1 else None
+    d_fb2 = torch.zeros(n * 3, dtype=torch.float32, device=dev) if fif5 > 1 else None
     counts = accel.trace_paths_device(d_rays.data_ptr(), n, BOUNCES, sun, (1, 1, 1), 1, 0.0, d_fb.data_ptr(), want_counts=True, stream=sh)
     rays_per_sample = int(counts.sum())  # the same for every sample up to the random directions of the bounces (counted once, outside the timed region)
 
@@ -355,8 +358,24 @@ def config5_side(args, torch, dist, dev, world, rank, local_rank, sync_all, max_
             group.all_gather_device(d_rays_padded.data_ptr(), chunk, stream=sh)
             rays_ptr = d_rays_padded.data_ptr()
         d_fb.zero_()
-        for smp in my_samples:
-            accel.trace_paths_device(rays_ptr, n, BOUNCES, sun, (1, 1, 1), 1000 * it + smp, 1.0 / SPP5, d_fb.data_ptr(), stream=sh)
+        if fif5 > 1:
+            # two samples in flight (the handle's two path-scratch slots on two streams, one framebuffer each): a sample's small late
+            # waves and launch tails run under the other sample's large early waves
+            d_fb2.zero_()
+            fork = torch.cuda.Event()
+            fork.record(stream)
+            stream2.wait_event(fork)
+            for j, smp in enumerate(my_samples):
+                k = j % 2
+                accel.trace_paths_device(rays_ptr, n, BOUNCES, sun, (1, 1, 1), 1000 * it + smp, 1.0 / SPP5, (d_fb2 if k else d_fb).data_ptr(),
+                                         stream=(stream2 if k else stream).cuda_stream, slot=k)
+            join = torch.cuda.Event()
+            join.record(stream2)
+            stream.wait_event(join)
+            d_fb.add_(d_fb2)
+        else:
+            for smp in my_samples:
+                accel.trace_paths_device(rays_ptr, n, BOUNCES, sun, (1, 1, 1), 1000 * it + smp, 1.0 / SPP5, d_fb.data_ptr(), stream=sh)
         if group is not None:
             group.reduce_device(d_fb.data_ptr(), n * 3, stream=sh)
         if host and rank == 0:
@@ -387,12 +406,12 @@ def config5_side(args, torch, dist, dev, world, rank, local_rank, sync_all, max_
            "rays_per_frame": rays_per_frame, "value": round(rays_per_frame / ms / 1e3, 2), "unit": "Mrays/s", "ms_per_frame": round(ms, 3),
            "e2e": {"value": round(rays_per_frame / e2e_ms / 1e3, 2), "ms_per_frame": round(e2e_ms, 3), "h2d_bytes_per_frame": n * 32 if world == 1 else chunk, "d2h_bytes_per_frame": n * 12,
                    "how": "host rays up, host image down" if world == 1 else "each rank uploads 1/N of the host rays, ncclAllGather, own samples, ncclReduce, rank 0 downloads the image"},
-           "rays_per_wave_of_one_sample": [int(c) for c in counts], "scene_generation_s": round(gen_s, 1), "populate_s": round(populate_s, 1)}
+           "samples_in_flight": fif5, "rays_per_wave_of_one_sample": [int(c) for c in counts], "scene_generation_s": round(gen_s, 1), "populate_s": round(populate_s, 1)}
     if group is not None:
         group.close()
     else:
         accel.close()
-    del d_rays, d_fb
+    del d_rays, d_fb, d_fb2
     torch.cuda.empty_cache()
     return out
 

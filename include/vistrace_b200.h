@@ -468,6 +468,10 @@ int vt_accel_shadow_rays_requeued(vt_accel *accel, const vt_attr *attrs, const u
  * wave — [0] primary, [1] its shadow rays, [2 + 2k], [3 + 2k] bounce k + 1 and its shadow rays.
  * DEVICE pointers (VT_TRAVERSE_DEVICE_PTRS required), enqueued on `stream`; at most 8 bounces. */
 #define VT_PATHS_NO_COMPACTION 8u
+/* the call uses the handle's SECOND set of path scratch buffers: calls with and without the flag may run concurrently on two streams
+ * (two samples of a frame in flight: one sample's small late waves run under the other's large early ones) — into DIFFERENT
+ * framebuffers, which the caller adds up */
+#define VT_PATHS_SLOT1 16u
 int vt_accel_trace_paths(vt_accel *accel, const vt_ray *rays, uint64_t n, uint32_t bounces, const float sun_dir[3],
                          const float sun_rgb[3], uint64_t seed, float weight, float *framebuffer_rgb, uint64_t *ray_counts,
                          uint32_t flags, void *stream);

@@ -91,6 +91,20 @@ def test_path_waves_compacted_equal_uncompacted_and_piecewise(vt, scene_name):
     accel.trace_paths_device(d_rays.data_ptr(), n, bounces, sun, sun_rgb, seed, weight, d_fb.data_ptr(), stream=sh)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(d_fb.cpu().numpy().reshape(-1, 3), (want_fb + want_fb).astype(np.float32))
+    # two samples in flight: the handle's two scratch slots on two streams, one framebuffer each — the images of the one-at-a-time calls
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    fbs = [torch.zeros(n * 3, dtype=torch.float32, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    for it in range(3):  # three rounds: the slots are reused while the other one is still busy
+        for k in range(2):
+            accel.trace_paths_device(d_rays.data_ptr(), n, bounces, sun, sun_rgb, seed + 5 * k, weight, fbs[k].data_ptr(), stream=streams[k].cuda_stream, slot=k)
+    torch.cuda.synchronize()
+    for k in range(2):
+        one = torch.zeros(n * 3, dtype=torch.float32, device="cuda")
+        accel.trace_paths_device(d_rays.data_ptr(), n, bounces, sun, sun_rgb, seed + 5 * k, weight, one.data_ptr(), stream=sh)
+        torch.cuda.synchronize()
+        w = one.cpu().numpy()
+        np.testing.assert_array_equal(fbs[k].cpu().numpy(), ((w + w).astype(np.float32) + w).astype(np.float32), err_msg=f"slot {k}")
 
 
 def test_batched_sample_bsdf_diffuse_lobe_against_the_reference(vt, oracle_mod):

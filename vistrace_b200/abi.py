@@ -25,6 +25,7 @@ VT_GROUP_FRAME_SLOT1 = 32
 VT_GROUP_ASYNC = 64
 VT_TEXEL_WIDE, VT_TEXEL_DIV_255, VT_TEXEL_DIV_65535, VT_TEXEL_DIV_1 = 0x100, 0, 1, 2
 VT_PATHS_NO_COMPACTION = 8
+VT_PATHS_SLOT1 = 16
 VT_LOBE_NONE, VT_LOBE_DIFFUSE_REFLECTION = 0, 1
 
 f4, u4, i4, u2, u1 = np.float32, np.uint32, np.int32, np.uint16, np.uint8

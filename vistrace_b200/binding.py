@@ -596,12 +596,12 @@ class Accel:
         """Block until the oldest frame begun with render_diffuse_wave_begin is complete in its framebuffer."""
         _check(self.L.vt_accel_render_diffuse_wave_wait(self.h), "vt_accel_render_diffuse_wave_wait")
 
-    def trace_paths_device(self, d_rays, n, bounces, sun_dir, sun_rgb, seed, weight, d_fb, want_counts=False, compact=True, stream=None):
+    def trace_paths_device(self, d_rays, n, bounces, sun_dir, sun_rgb, seed, weight, d_fb, want_counts=False, compact=True, stream=None, slot=0):
         """Path waves with compaction over device-resident primary rays; returns the per-wave ray counts when asked (synchronous then)."""
         sd = (C.c_float * 3)(*[float(x) for x in sun_dir])
         sc = (C.c_float * 3)(*[float(x) for x in sun_rgb])
         counts = np.zeros(2 + 2 * bounces, np.uint64) if want_counts else None
-        flags = abi.VT_TRAVERSE_DEVICE_PTRS | (0 if compact else abi.VT_PATHS_NO_COMPACTION)
+        flags = abi.VT_TRAVERSE_DEVICE_PTRS | (0 if compact else abi.VT_PATHS_NO_COMPACTION) | (abi.VT_PATHS_SLOT1 if slot else 0)
         _check(self.L.vt_accel_trace_paths(self.h, _ptr(d_rays), n, bounces, C.cast(sd, _vp), C.cast(sc, _vp), seed, weight, _ptr(d_fb), _ptr(counts),
                                            flags, _ptr(stream)), "vt_accel_trace_paths")
         return counts

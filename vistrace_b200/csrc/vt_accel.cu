@@ -1290,7 +1290,7 @@ void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp
 }
 
 void AccelStruct::TracePaths(const vt_ray *rays, uint64_t n, uint32_t bounces, const float sun_dir[3], const float sun_rgb[3], uint64_t seed,
-                             float weight, float *fb, uint64_t *ray_counts, bool compact, void *stream_) {
+                             float weight, float *fb, uint64_t *ray_counts, bool compact, void *stream_, int slot) {
     check_built(mAccelBuilt);
     if (n == 0) return;
     if (!rays || !fb || !sun_dir || !sun_rgb) throw std::runtime_error("trace_paths: null argument");
@@ -1299,7 +1299,7 @@ void AccelStruct::TracePaths(const vt_ray *rays, uint64_t n, uint32_t bounces, c
     if (((uintptr_t)rays & 31)) throw std::runtime_error("trace_paths: device ray buffers must be 32-byte aligned");
     VT_CUDA(cudaSetDevice(mDevice));
     DeviceScene &D = *mpDevice;
-    DeviceScene::PathScratch &P = D.path;
+    DeviceScene::PathScratch &P = D.path[slot & 1];
     cudaStream_t stream = (cudaStream_t)stream_;
     for (int i = 0; i < 2; i++) P.hits[i].ensure(n), P.attrs[i].ensure(n);
     for (int i = 0; i < 3; i++) P.queue[i].ensure(n);
@@ -1604,7 +1604,8 @@ int vt_accel_trace_paths(vt_accel *a, const vt_ray *rays, uint64_t n, uint32_t b
     VT_TRY
     if (!a) throw std::runtime_error("null argument");
     if (!(flags & VT_TRAVERSE_DEVICE_PTRS)) throw std::runtime_error("vt_accel_trace_paths: device pointers only (VT_TRAVERSE_DEVICE_PTRS)");
-    a->impl.TracePaths(rays, n, bounces, sun_dir, sun_rgb, seed, weight, framebuffer_rgb, ray_counts, !(flags & VT_PATHS_NO_COMPACTION), stream);
+    a->impl.TracePaths(rays, n, bounces, sun_dir, sun_rgb, seed, weight, framebuffer_rgb, ray_counts, !(flags & VT_PATHS_NO_COMPACTION), stream,
+                       (flags & VT_PATHS_SLOT1) ? 1 : 0);
     return 0;
     VT_CATCH(1)
 }

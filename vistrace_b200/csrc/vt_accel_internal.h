@@ -107,7 +107,7 @@ struct DeviceScene {
         DevBuf<uint32_t> queue[3];
         DevBuf<unsigned long long> counts;  // [0..2]: the three queue counters, [8 + 2k], [9 + 2k]: rays of wave k (bounce, shadow)
         DevBuf<float> throughput;
-    } path;
+    } path[2];  // two: samples traced on two streams at once (VT_PATHS_SLOT1) share nothing
     DevBuf<unsigned long long> live;
     // host-pointer waves: the whole frame's rays are staged here by ONE copy stream, tile after tile, so an upload never
     // waits for the lane (stream) its tile will run on; upload_done[k] gates tile k's kernels
@@ -147,9 +147,11 @@ struct DeviceScene {
         s_samples.release();
         s_rays2.release();
         live.release();
-        for (int i = 0; i < 2; i++) path.hits[i].release(), path.attrs[i].release();
-        for (int i = 0; i < 3; i++) path.queue[i].release();
-        path.shits.release(), path.brays.release(), path.srays.release(), path.counts.release(), path.throughput.release();
+        for (PathScratch &ps : path) {
+            for (int i = 0; i < 2; i++) ps.hits[i].release(), ps.attrs[i].release();
+            for (int i = 0; i < 3; i++) ps.queue[i].release();
+            ps.shits.release(), ps.brays.release(), ps.srays.release(), ps.counts.release(), ps.throughput.release();
+        }
         wave_rays.release();
         wave_rays_b.release();
         for (cudaEvent_t e : upload_done) cudaEventDestroy(e);

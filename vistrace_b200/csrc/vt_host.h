@@ -290,7 +290,7 @@ public:
     // Path waves with compaction (BASELINE config 5): per primary ray a path of up to `bounces` diffuse bounces, a shadow ray toward
     // the sun at every vertex; after the primary wave every kernel visits only the paths that are still alive.  DEVICE pointers.
     void TracePaths(const vt_ray *rays, uint64_t n, uint32_t bounces, const float sun_dir[3], const float sun_rgb[3], uint64_t seed,
-                    float weight, float *fb, uint64_t *ray_counts, bool compact, void *stream);
+                    float weight, float *fb, uint64_t *ray_counts, bool compact, void *stream, int slot = 0);
 
     // The same wave with the framebuffer as its only result: HOST rays in, HOST RGBFFF image out
     // (fb[i] = weight * albedo_i * escaped fraction of pixel i's bounce rays), tiled over streams like TraceDiffuseWave.
