@@ -1126,7 +1126,8 @@ void AccelStruct::TraceDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp,
 // the synchronous call is the two back to back; a caller that begins frame k + 1 before it waits for frame k keeps two frames in
 // flight — frame k's last tiles, launch tails and download run under frame k + 1's first uploads and kernels.  Tiles of consecutive
 // frames follow each other on the same lane streams, so a lane's scratch needs no extra fencing; the ray staging buffer alternates.
-void AccelStruct::RenderDiffuseWaveBegin(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb, bool count_live) {
+void AccelStruct::RenderDiffuseWaveBegin(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb, bool count_live,
+                                         bool pipelined) {
     check_built(mAccelBuilt);
     if (!rays || !fb) throw std::runtime_error("render_diffuse_wave: rays and framebuffer must not be null");
     if (mWaveFrames.size() >= 2) throw std::runtime_error("render_diffuse_wave: two frames are already in flight (wait for one first)");
@@ -1186,12 +1187,18 @@ void AccelStruct::RenderDiffuseWaveBegin(const vt_ray *rays, uint64_t n, uint32_
     };
     int li = 0, tiles_since_fence = 0;
     // the first tiles are small so the first kernel starts after a short upload; sizes double up to `tile`
-    uint64_t cur_tile = std::max<uint64_t>(1, std::min<uint64_t>(tile, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)(tile / 8)))));
+    // With another frame in flight the fill of the pipeline is hidden by that frame, so fewer, larger tiles win (measured,
+    // tools/e2e_chunk_probe.py, two frames in flight: 2.07 M rays 2.78 / 2.68 / 2.56 ms with a first tile of 64 k / 128 k / 256 k rays;
+    // 262 k rays 0.63 / 0.57 ms with 64 k / 128 k); a frame on its own starts small so that its first kernel follows a short upload
+    // (2.07 M rays, synchronous: 3.05 ms with 64 k).
+    uint64_t first_default = tile / 8;
+    if (pipelined) first_default = n <= tile ? std::max<uint64_t>(1, n / 2) : (n >= 4 * tile ? tile / 2 : tile / 8);  // 1.04 M rays: 64 k is best (1.44 vs 1.48 / 1.51 ms)
+    uint64_t cur_tile = std::max<uint64_t>(1, std::min<uint64_t>(tile, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)first_default))));
     for (uint64_t base = 0, m = 0; base < n; base += m, li = (li + 1) % n_lanes, cur_tile = std::min(tile, cur_tile * 2)) {
         m = std::min(cur_tile, n - base);
         if (n - base - m < cur_tile / 2) m = n - base;  // no small tail tile: its launch-latency chain would run alone at the end
         DeviceScene::WaveLane &l = D.lanes[li];
-        const uint64_t cap = tile + tile / 2;
+        const uint64_t cap = std::max<uint64_t>(tile + tile / 2, m);
         l.hits.ensure(cap);
         l.attrs.ensure(cap);
         l.brays.ensure(cap * spp);
@@ -1280,7 +1287,7 @@ void AccelStruct::RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp
     if (live_out) *live_out = 0;
     if (n == 0) return;
     if (!mWaveFrames.empty()) throw std::runtime_error("render_diffuse_wave: frames begun asynchronously are still in flight");
-    RenderDiffuseWaveBegin(rays, n, spp, seed, weight, fb, live_out != nullptr);
+    RenderDiffuseWaveBegin(rays, n, spp, seed, weight, fb, live_out != nullptr, false);
     RenderDiffuseWaveWait();
     if (live_out) {
         unsigned long long v = 0;
@@ -1865,7 +1872,7 @@ int vt_accel_render_diffuse_wave_begin(vt_accel *a, const vt_ray *rays, uint64_t
     VT_TRY
     if (!a) throw std::runtime_error("null argument");
     if (n == 0) throw std::runtime_error("render_diffuse_wave_begin: empty frame");
-    a->impl.RenderDiffuseWaveBegin(rays, n, spp, seed, weight, framebuffer_rgb, false);
+    a->impl.RenderDiffuseWaveBegin(rays, n, spp, seed, weight, framebuffer_rgb, false, true);
     return 0;
     VT_CATCH(1)
 }

@@ -456,7 +456,7 @@ public:
     void member_render(Member &m, const ShardGeom &g, const vt_ray *rays, bool rays_on_device, uint32_t spp, uint64_t seed, float weight,
                        float *fb_host, bool count_live, cudaStream_t caller_stream, const ShardGeom *sched = nullptr,
                        const std::function<void(uint64_t, uint64_t, cudaStream_t)> &after_chunk = nullptr, float *frame_target = nullptr,
-                       const uint32_t *consumed_flag = nullptr, uint32_t step = 0, int slot = 0, bool staging_alt = false) {
+                       const uint32_t *consumed_flag = nullptr, uint32_t step = 0, int slot = 0, bool staging_alt = false, bool pipelined = false) {
         AccelStruct &A = m.accel->impl;
         if (!A.Built()) throw std::runtime_error("vt_group: populate the group first");
         VT_CUDA(cudaSetDevice(m.device));
@@ -494,8 +494,12 @@ public:
         const uint64_t chunk_records = (uint64_t)std::max(1, env_int("VT_WAVE_TILE", 1 << 19));
         const uint64_t dev_chunks = (uint64_t)std::max(n_lanes, env_int("VT_GROUP_DEV_CHUNKS", n_lanes));
         const uint64_t chunk_tiles_max = rays_on_device ? std::max<uint64_t>(1, (lt_sched + dev_chunks - 1) / dev_chunks) : std::max<uint64_t>(1, chunk_records / g.tile);
+        // first chunk: small when the frame runs on its own (a short upload before the first kernel); with another frame in flight the
+        // fill is hidden and fewer, larger chunks win (AccelStruct::RenderDiffuseWaveBegin, tools/e2e_chunk_probe.py)
+        uint64_t first_default = chunk_records / 8;
+        if (pipelined) first_default = L <= chunk_records ? std::max<uint64_t>(1, L / 2) : (L >= 4 * chunk_records ? chunk_records / 2 : chunk_records / 8);
         uint64_t chunk_tiles = rays_on_device ? chunk_tiles_max
-                                              : std::max<uint64_t>(1, std::min(chunk_tiles_max, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)(chunk_records / 8))) / g.tile));
+                                              : std::max<uint64_t>(1, std::min(chunk_tiles_max, (uint64_t)std::max(1, env_int("VT_WAVE_FIRST", (int)first_default)) / g.tile));
         if (!rays_on_device) {
             (staging_alt ? D.wave_rays_b : D.wave_rays).ensure(std::max<uint64_t>(1, L));
             if (!D.copy_stream) VT_CUDA(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
@@ -739,7 +743,7 @@ public:
             const bool async = (flags & VT_GROUP_ASYNC) != 0;
             if (async && live_out) throw std::runtime_error("vt_group_render_diffuse_wave: live_out must be NULL with VT_GROUP_ASYNC");
             if (mSharedFrames.size() >= (async ? 2u : 1u)) throw std::runtime_error("vt_group_render_diffuse_wave: frames are still in flight (vt_group_wait_frame)");
-            member_render(m, g, rays, false, spp, seed, weight, fb, live_out != nullptr, st, nullptr, nullptr, nullptr, nullptr, 0, 0, (mSharedFrameCount++ & 1) != 0);
+            member_render(m, g, rays, false, spp, seed, weight, fb, live_out != nullptr, st, nullptr, nullptr, nullptr, nullptr, 0, 0, (mSharedFrameCount++ & 1) != 0, async);
             if (mWorld > 1) {
                 NcclApi &nccl = NcclApi::get();
                 if (!nccl.AllGather) throw std::runtime_error("ncclAllGather not found");

@@ -296,7 +296,7 @@ public:
     // (fb[i] = weight * albedo_i * escaped fraction of pixel i's bounce rays), tiled over streams like TraceDiffuseWave.
     void RenderDiffuseWave(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb, uint64_t *live_out);
     // the same, split: enqueue a frame / wait for the oldest frame in flight (at most two): vt_accel_render_diffuse_wave_begin / _wait
-    void RenderDiffuseWaveBegin(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb, bool count_live);
+    void RenderDiffuseWaveBegin(const vt_ray *rays, uint64_t n, uint32_t spp, uint64_t seed, float weight, float *fb, bool count_live, bool pipelined);
     void RenderDiffuseWaveWait();
     void DrainWaveFrames();
 
