@@ -600,13 +600,27 @@ def run_ours(args):
         shared_frame = None
         shared_frames = []
         if os.environ.get("VT_BENCH_E2E_GATHER", "0") == "0":
-            for k in range(fif):
-                name = f"vt_bench_frame_{os.environ.get('MASTER_PORT', '0')}_{k}"
-                fr = shard.SharedPinnedFrame(name, n * 12, create=True) if rank == 0 else None
-                dist.barrier()
+            ok = 1
+            names = [f"vt_bench_frame_{os.environ.get('MASTER_PORT', '0')}_{k}" for k in range(fif)]
+            try:
+                if rank == 0:
+                    shared_frames = [shard.SharedPinnedFrame(nm, n * 12, create=True) for nm in names]
+            except (OSError, RuntimeError) as e:
+                log(f"[bench] shared host frame unavailable on rank 0 ({e}): falling back to the NVLink gather")
+                ok = 0
+            dist.barrier()
+            try:
                 if rank != 0:
-                    fr = shard.SharedPinnedFrame(name, n * 12, create=False)
-                shared_frames.append(fr)
+                    shared_frames = [shard.SharedPinnedFrame(nm, n * 12, create=False) for nm in names]
+            except (OSError, RuntimeError):
+                ok = 0
+            ok_t = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)  # every rank must have the mapping, or nobody uses it
+            if int(ok_t.item()) == 0:
+                for fr in shared_frames:
+                    fr.close()
+                shared_frames = []
+        if shared_frames:
             shared_frame = shared_frames[0]
             h_fbs = [fr.array(np.float32, (n, 3)) for fr in shared_frames]
             h_fb = h_fbs[0]
@@ -626,15 +640,20 @@ def run_ours(args):
             return group.render_diffuse_wave(h_rays, SPP, seed=seed0 + it, weight=1.0, out=h_fb, want_live=False, shared_frame=shared_frame is not None)[1]
     for it in range(min(2, warmup)):
         e2e_step(it)
+    if e2e_async:
+        begin = (lambda it: accel.render_diffuse_wave_begin(h_rays, SPP, seed0 + warmup + it, 1.0, h_fbs[it % 2])) if world == 1 else \
+                (lambda it: group.render_diffuse_wave_begin(h_rays, SPP, seed0 + warmup + it, 1.0, h_fbs[it % 2]))
+        wait = accel.render_diffuse_wave_wait if world == 1 else group.wait_frame
+        for it in range(2):  # warm-up of the two-in-flight schedule (second staging buffer, tile sizes of its own)
+            begin(-2 + it)
+        wait()
+        wait()
     sync_all()
     l0 = launch_count()
     with clocks:
         sync_all()
         t0 = time.perf_counter()
         if e2e_async:
-            begin = (lambda it: accel.render_diffuse_wave_begin(h_rays, SPP, seed0 + warmup + it, 1.0, h_fbs[it % 2])) if world == 1 else \
-                    (lambda it: group.render_diffuse_wave_begin(h_rays, SPP, seed0 + warmup + it, 1.0, h_fbs[it % 2]))
-            wait = accel.render_diffuse_wave_wait if world == 1 else group.wait_frame
             for it in range(e2e_steps):
                 if it >= 2:
                     wait()
