@@ -294,6 +294,9 @@ void AccelStruct::Upload(const vt_scene &scene) {
     std::vector<VtCPair> cpairs;
     std::string err;
     if (layout == VT_LAYOUT_QUAD && !build_quads(mAccel, n, quad, err)) layout = VT_LAYOUT_EXACT;
+#if VT_SMEM_QUADS_BUILD
+    if (layout == VT_LAYOUT_QUAD) smem_pairs = quads_top_first(quad, (uint32_t)std::max(0, env_int("VT_SMEM_QUADS", 0)));  // A/B builds only
+#endif
     if (layout != VT_LAYOUT_QUAD) {
         if (!flatten_bvh(mAccel, n, smem_pairs, flat, err)) throw std::runtime_error(err);
         smem_pairs = (uint32_t)std::min<size_t>(smem_pairs, flat.pairs.size());
@@ -781,7 +784,7 @@ void AccelStruct::TraverseStats(const vt_ray *rays, uint64_t n, uint32_t flags, 
     if (!rays) throw std::runtime_error("traverse_stats: rays must not be null");
     VT_CUDA(cudaSetDevice(mDevice));
     DeviceScene &D = *mpDevice;
-    if (D.view.n_smem_pairs) throw std::runtime_error("traverse_stats: not available with VT_SMEM_PAIRS");
+    if (D.view.n_smem_pairs && D.view.pairs) throw std::runtime_error("traverse_stats: not available with VT_SMEM_PAIRS");
     cudaStream_t stream = D.own_stream;
     D.stat_counters.ensure(5);
     VT_CUDA(cudaMemsetAsync(D.stat_counters.p, 0, 5 * sizeof(unsigned long long), stream));

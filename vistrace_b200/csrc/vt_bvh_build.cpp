@@ -951,4 +951,41 @@ bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string 
     return true;
 }
 
+// Experiment knob (VT_SMEM_QUADS, with a library built -DVT_SMEM_QUADS_BUILD=1): move the top of the quad hierarchy — the first
+// `top` quads in BREADTH-first order from the root — to the front of the array, so that the traversal kernel can stage them in shared
+// memory as one block (BASELINE.json north_star: "the top BVH levels staged in shared memory"); every other quad keeps its depth-first
+// place behind them.  Only inner references change.  Returns the number of quads moved to the front.
+uint32_t quads_top_first(QuadBvh &qb, uint32_t top) {
+    const uint32_t n = (uint32_t)qb.quads.size();
+    top = std::min(top, n);
+    if (top <= 1) return top;
+    std::vector<uint32_t> order;  // new index -> old index
+    order.reserve(n);
+    std::vector<uint8_t> in_top(n, 0);
+    order.push_back(0);
+    in_top[0] = 1;
+    for (size_t head = 0; head < order.size() && order.size() < top; head++) {
+        const VtQuad &q = qb.quads[order[head]];
+        for (int i = 0; i < 4 && order.size() < top; i++) {
+            const uint32_t ref = q.ref[i];
+            if (ref == 0xFFFFFFFFu || (ref >> 28) != 0) continue;  // empty slot or leaf
+            if (!in_top[ref]) in_top[ref] = 1, order.push_back(ref);
+        }
+    }
+    const uint32_t moved = (uint32_t)order.size();
+    for (uint32_t i = 0; i < n; i++)
+        if (!in_top[i]) order.push_back(i);
+    std::vector<uint32_t> new_of(n);
+    for (uint32_t i = 0; i < n; i++) new_of[order[i]] = i;
+    RawVector<VtQuad> out(n);
+    for (uint32_t i = 0; i < n; i++) {
+        VtQuad q = qb.quads[order[i]];
+        for (int k = 0; k < 4; k++)
+            if (q.ref[k] != 0xFFFFFFFFu && (q.ref[k] >> 28) == 0) q.ref[k] = new_of[q.ref[k]];
+        out[i] = q;
+    }
+    qb.quads.swap(out);
+    return moved;
+}
+
 }  // namespace vt

@@ -101,6 +101,7 @@ struct QuadBvh {
     uint32_t max_stack = 0;  // worst-case number of pending references
 };
 bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string &err);
+uint32_t quads_top_first(QuadBvh &qb, uint32_t top);  // experiment: breadth-first prefix for shared-memory staging (VT_SMEM_QUADS)
 // Which binary nodes become the children of each WIDE node when the binary tree is collapsed to `width` children per node
 // (vt_bvh_collapse.cpp): the SAH-optimal choice by dynamic programming over the subtree costs, after Ylitie, Karras, Laine,
 // "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs" (HPG 2017), section 3.1 — cost(n, i) = cheapest way to

@@ -13,6 +13,10 @@
 #define VT_TRAVERSE_MIN_BLOCKS 8
 #endif
 
+// A/B builds only: the quad kernel stages the first S.n_smem_pairs quads (breadth-first prefix, quads_top_first) in shared memory
+#ifndef VT_SMEM_QUADS_BUILD
+#define VT_SMEM_QUADS_BUILD 0
+#endif
 #ifndef VT_COMPACT_MIN_BLOCKS
 #define VT_COMPACT_MIN_BLOCKS 9
 #endif

@@ -341,10 +341,19 @@ VT_DEV float2 decode_half_pair(uint32_t q, uint32_t magic_h, uint32_t sel) {
 }
 #endif
 template <bool TWO_FMA>
-VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const RayState &ray, int (&k)[4], uint32_t (&r)[4]) {
+VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const RayState &ray, int (&k)[4], uint32_t (&r)[4],
+                      const uint4 *s_top = nullptr, uint32_t n_top = 0) {
     uint4 a0, a1, b0, b1;
-    ldg256u(quads + cur, a0, a1);
-    ldg256u(reinterpret_cast<const char *>(quads + cur) + 32, b0, b1);
+#if VT_SMEM_QUADS_BUILD
+    if (cur < n_top) {  // the top of the hierarchy, staged per CTA (A/B builds)
+        const uint4 *p = s_top + cur * 4u;
+        a0 = p[0], a1 = p[1], b0 = p[2], b1 = p[3];
+    } else
+#endif
+    {
+        ldg256u(quads + cur, a0, a1);
+        ldg256u(reinterpret_cast<const char *>(quads + cur) + 32, b0, b1);
+    }
     // words: a0 = {origin_adj.xyz, scale.x}, a1 = {scale.y, scale.z, lo_x[4], hi_x[4]}, b0 = {lo_y[4], hi_y[4], lo_z[4], hi_z[4]}, b1 = refs
     const float ax = __uint_as_float(a0.x), ay = __uint_as_float(a0.y), az = __uint_as_float(a0.z);
     const float sx = __uint_as_float(a0.w), sy = __uint_as_float(a1.x), sz = __uint_as_float(a1.y);
@@ -667,6 +676,17 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                    unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold,
                    const uint32_t *__restrict__ queue, const unsigned long long *__restrict__ queue_count) {
     if (queue_count) n = min(n, *queue_count);  // ray queue: only the slots the generator listed are traced
+#if VT_SMEM_QUADS_BUILD
+    extern __shared__ uint4 s_top_quads[];
+    const uint32_t n_top = QUAD ? S.n_smem_pairs : 0u;
+    if (QUAD && n_top) {
+        for (uint32_t i = threadIdx.x; i < n_top * 4u; i += blockDim.x) s_top_quads[i] = __ldg(reinterpret_cast<const uint4 *>(S.quads) + i);
+        __syncthreads();
+    }
+#else
+    const uint4 *const s_top_quads = nullptr;
+    const uint32_t n_top = 0;
+#endif
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     // the layouts served by this kernel validate the worst-case stack depth on the host (<= VT_STACK_SIZE), so
@@ -950,8 +970,8 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                 if (QUAD) {
                     int k[4];
                     uint32_t cr[4];
-                    if (warp_wild) slab_quad<true>(S.quads, cur, magic, r, k, cr);
-                    else slab_quad<false>(S.quads, cur, magic, r, k, cr);
+                    if (warp_wild) slab_quad<true>(S.quads, cur, magic, r, k, cr, s_top_quads, n_top);
+                    else slab_quad<false>(S.quads, cur, magic, r, k, cr, s_top_quads, n_top);
                     // farthest first, so the nearest pending child is popped first
                     if (k[3] != 0x7FFFFFFF) {
                         stack_push<DIST>(sp, cr[3], (uint32_t)k[3]);
@@ -1010,7 +1030,8 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
     // L1-capacity sensitivity of the kernel can be measured in isolation
     const char *dyn_smem_env = std::getenv("VT_K1_DYN_SMEM");
     const int dyn_smem_probe = (dyn_smem_env && *dyn_smem_env) ? std::atoi(dyn_smem_env) : 0;
-    const size_t smem = (S.cpairs || S.quads) ? (size_t)dyn_smem_probe : (size_t)S.n_smem_pairs * sizeof(VtPair);
+    const size_t smem = (S.cpairs || S.quads) ? (size_t)dyn_smem_probe + (VT_SMEM_QUADS_BUILD && S.quads ? (size_t)S.n_smem_pairs * sizeof(VtQuad) : 0)
+                                              : (size_t)S.n_smem_pairs * sizeof(VtPair);
     int grid;
     if (cfg.persistent) {
         grid = cfg.grid;
