@@ -207,6 +207,9 @@ uint64_t count_triangles(const Map &M) {
         }
     }
     if (n == 0) fail("the map has no drawable world triangles");  // BSPParser.cpp:210
+    // a hostile face table can name the same surfedges over and over (65536 faces x 32767 edges): the reference would try to malloc
+    // ~300 GB for it; no compiled map comes near this bound
+    if (n > (1ull << 26)) fail("more world triangles than a compiled map can hold");
     return n;
 }
 
