@@ -10,6 +10,8 @@ differences the spec allows).  Every parity test runs on both node layouts:
                every other record must be bit-identical.  The synthetic scenes have no duplicate
                geometry, so in practice the tie count is 0 and the buffers are identical too.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -661,10 +663,33 @@ def test_refit_range_one_moved_entity(vt, oracle_mod):
     assert h_part.tobytes() == h_whole.tobytes() and a_part.tobytes() == a_whole.tobytes()
     np.testing.assert_array_equal(part.tri_derived().view(np.uint32), whole.tri_derived().view(np.uint32))
     assert np.array_equal(part.get_bvh()[0]["bounds"], whole.get_bvh()[0]["bounds"])
+    # the ranged walk (touched quads and their ancestors only) leaves the very quads of the whole-tree pass: the same node visits
+    # and triangle tests ray by ray (a stale ancestor box would prune differently), the same node-area sum
+    s_whole, s_part = whole.traverse_ray_stats(rays), part.traverse_ray_stats(rays)
+    assert np.array_equal(s_part[0], s_whole[0]) and np.array_equal(s_part[1], s_whole[1])
+    assert part.refit_quality()[0] == pytest.approx(whole.refit_quality()[0], rel=1e-9) and whole.refit_quality()[0] != 1.0  # atomic double sums: order varies
     kind = "reference" if oracle_mod.available("reference") else "port"
     cpu = oracle_mod.CpuScene(moved, kind, build_bvh=False)
     cpu.set_bvh(*part.get_bvh())
     assert same_hits(h_part, cpu.traverse(rays)["hits"], "quad", rays, cpu)
+    # back to the start through the whole-tree walk of the same entry point (VT_REFIT_RANGE_WALK=0): the as-built quads again
+    os.environ["VT_REFIT_RANGE_WALK"] = "0"
+    try:
+        for ent in range(1, len(scene.entities)):
+            idx = np.nonzero(scene.tris["ent_idx"] == ent)[0]
+            part.refit_range(scene.tris[idx[0]: idx[-1] + 1], int(idx[0]))
+    finally:
+        del os.environ["VT_REFIT_RANGE_WALK"]
+    fresh = vt.Accel(0, layout="quad").populate(scene)
+    assert part.traverse(rays).tobytes() == fresh.traverse(rays).tobytes()
+    s_fresh, s_back = fresh.traverse_ray_stats(rays), part.traverse_ray_stats(rays)
+    assert np.array_equal(s_back[0], s_fresh[0]) and np.array_equal(s_back[1], s_fresh[1])
+    for ent in range(1, len(scene.entities)):  # and forward again on the ranged walk: counters were left clean
+        idx = np.nonzero(scene.tris["ent_idx"] == ent)[0]
+        part.refit_range(moved.tris[idx[0]: idx[-1] + 1], int(idx[0]))
+    assert part.traverse(rays).tobytes() == h_whole.tobytes()
+    s_part = part.traverse_ray_stats(rays)
+    assert np.array_equal(s_part[0], s_whole[0]) and np.array_equal(s_part[1], s_whole[1])
     with pytest.raises(RuntimeError):
         part.refit_range(moved.tris[:4], scene.n_tris - 2)  # past the end
     with pytest.raises(RuntimeError):

@@ -39,7 +39,21 @@ def main():
     h2 = fresh.traverse(rays)
     st2 = fresh.traverse_stats(rays)
     differ = int(((h1["prim"] != h2["prim"]) | (h1["t"] != h2["t"])).sum())
-    print(json.dumps({"tris": scene.n_tris, "populate_s": round(t_build, 3), "refit_host_s": round(t_refit_host, 3), "refit_device_s": round(t_refit, 3), "refit_device_again_s": round(t_refit2, 3), "rebuild_moved_s": round(t_rebuild, 3),
+    # one moved entity through vt_accel_refit_range: the ranged walk (touched quads + ancestors) against the whole-tree walk
+    ent = len(scene.entities) - 1
+    idx = np.nonzero(scene.tris["ent_idx"] == ent)[0]
+    run_a, run_b = scene.tris[idx[0]: idx[-1] + 1], moved.tris[idx[0]: idx[-1] + 1]
+    ranged = {}
+    for walk in ("1", "0"):
+        os.environ["VT_REFIT_RANGE_WALK"] = walk
+        best = 1e9
+        for k in range(6):
+            t0 = time.time(); accel.refit_range(run_b if k % 2 else run_a, int(idx[0])); best = min(best, time.time() - t0)
+        ranged["ranged_walk_ms" if walk == "1" else "whole_tree_walk_ms"] = round(best * 1e3, 3)
+    del os.environ["VT_REFIT_RANGE_WALK"]
+    ranged["triangles"] = int(len(idx))
+    assert accel.traverse(rays).tobytes() == h1.tobytes()  # k = 5 put the moved run back
+    print(json.dumps({"tris": scene.n_tris, "refit_range_one_entity": ranged, "populate_s": round(t_build, 3), "refit_host_s": round(t_refit_host, 3), "refit_device_s": round(t_refit, 3), "refit_device_again_s": round(t_refit2, 3), "rebuild_moved_s": round(t_rebuild, 3),
                       "rays_changed_by_the_move": int(((h0["prim"] != h1["prim"]) | (h0["t"] != h1["t"])).sum()),
                       "refit_vs_rebuild_records_differing": differ,
                       "node_visits_per_ray_refit": round(st1[0] / len(rays), 2), "node_visits_per_ray_rebuild": round(st2[0] / len(rays), 2)}))

@@ -576,6 +576,32 @@ const HostBvh &AccelStruct::Bvh() const {
     return mAccel;
 }
 
+// K5 state of a resident quad hierarchy, built on its first refit: parent / inner-child count per quad, original triangle -> leaf
+// slot, leaf slot -> quad, the zeroed per-quad counters of the ranged walk — and the tree AS BUILT: one bottom-up pass over the
+// unchanged geometry fills the box table and gives the node-area sum that later refits are measured against (the pass re-derives the
+// very bytes it reads: idempotent).  Returns the number of kernels launched.
+static unsigned prepare_refit_state(DeviceScene &D, cudaStream_t stream) {
+    const VtSceneView &V = D.view;
+    D.refit_parent.ensure(V.n_pairs);
+    D.refit_n_inner.ensure(V.n_pairs);
+    D.refit_arrive.ensure(V.n_pairs);
+    D.refit_qbox.ensure((size_t)V.n_pairs * 6);
+    D.refit_slot_of.ensure(V.n_tris);
+    D.refit_leaf_quad.ensure(V.n_tris);
+    D.refit_range_state.ensure((size_t)V.n_pairs * 3);  // stamp | dirty children | arrivals (vt_refit.cu: k_refit_*_range)
+    D.refit_error.ensure(1);
+    D.refit_cost.ensure(1);
+    VT_CUDA(cudaMemsetAsync(D.refit_range_state.p, 0, (size_t)V.n_pairs * 3 * sizeof(uint32_t), stream));
+    D.refit_epoch = 1;
+    VT_CUDA(vt_launch_refit_prepare(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_slot_of.p, D.refit_leaf_quad.p, stream));
+    VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
+    VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
+    VT_CUDA(vt_launch_refit_cost(D.refit_qbox.p, V.n_pairs, D.refit_cost.p, stream));
+    VT_CUDA(cudaMemcpyAsync(&D.refit_cost_built, D.refit_cost.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    D.refit_ready = true;
+    return 3;
+}
+
 void AccelStruct::Refit(const vt_scene &scene) {
     DrainWaveFrames();
     if (mReplica) throw std::runtime_error("refit: this handle is a replica (vt_group): refit the group");
@@ -605,24 +631,7 @@ void AccelStruct::Refit(const vt_scene &scene) {
         cudaStream_t stream = D.own_stream;
         D.refit_in.ensure(scene.n_tris);
         VT_CUDA(cudaMemcpyAsync(D.refit_in.p, scene.tris, scene.n_tris * sizeof(vt_tri_in), cudaMemcpyHostToDevice, stream));
-        if (!D.refit_ready) {
-            D.refit_parent.ensure(V.n_pairs);
-            D.refit_n_inner.ensure(V.n_pairs);
-            D.refit_arrive.ensure(V.n_pairs);
-            D.refit_qbox.ensure((size_t)V.n_pairs * 6);
-            D.refit_slot_of.ensure(V.n_tris);
-            D.refit_error.ensure(1);
-            D.refit_cost.ensure(1);
-            VT_CUDA(vt_launch_refit_prepare(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_slot_of.p, stream));
-            // the tree AS BUILT: one bottom-up pass over the unchanged geometry fills the box table and gives the node-area sum that
-            // later refits are measured against (the pass re-derives the very bytes it reads: idempotent)
-            VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
-            VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
-            VT_CUDA(vt_launch_refit_cost(D.refit_qbox.p, V.n_pairs, D.refit_cost.p, stream));
-            VT_CUDA(cudaMemcpyAsync(&D.refit_cost_built, D.refit_cost.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
-            mLaunches += 3;
-            D.refit_ready = true;
-        }
+        if (!D.refit_ready) mLaunches += prepare_refit_state(D, stream);
         VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
         VT_CUDA(vt_launch_refit_tris(V, D.refit_in.p, 0, (uint32_t)scene.n_tris, D.refit_slot_of.p, stream));
         VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
@@ -680,25 +689,23 @@ void AccelStruct::RefitRange(const vt_tri_in *tris, uint64_t first, uint64_t cou
     cudaStream_t stream = D.own_stream;
     D.refit_in.ensure(count);
     VT_CUDA(cudaMemcpyAsync(D.refit_in.p, tris, count * sizeof(vt_tri_in), cudaMemcpyHostToDevice, stream));
-    if (!D.refit_ready) {
-        D.refit_parent.ensure(V.n_pairs);
-        D.refit_n_inner.ensure(V.n_pairs);
-        D.refit_arrive.ensure(V.n_pairs);
-        D.refit_qbox.ensure((size_t)V.n_pairs * 6);
-        D.refit_slot_of.ensure(V.n_tris);
-        D.refit_error.ensure(1);
-        D.refit_cost.ensure(1);
-        VT_CUDA(vt_launch_refit_prepare(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_slot_of.p, stream));
-        VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));  // the tree as built: see Refit
-        VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
-        VT_CUDA(vt_launch_refit_cost(D.refit_qbox.p, V.n_pairs, D.refit_cost.p, stream));
-        VT_CUDA(cudaMemcpyAsync(&D.refit_cost_built, D.refit_cost.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
-        mLaunches += 3;
-        D.refit_ready = true;
-    }
+    if (!D.refit_ready) mLaunches += prepare_refit_state(D, stream);
     VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
     VT_CUDA(vt_launch_refit_tris(V, D.refit_in.p, (uint32_t)first, (uint32_t)count, D.refit_slot_of.p, stream));
-    VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
+    if (env_int("VT_REFIT_RANGE_WALK", 1) != 0) {
+        // only the quads holding a touched triangle and their ancestors (every other quad keeps its bytes and its box-table entry)
+        if (D.refit_epoch > 0xFFFFFF00u) {
+            VT_CUDA(cudaMemsetAsync(D.refit_range_state.p, 0, (size_t)V.n_pairs * 3 * sizeof(uint32_t), stream));
+            D.refit_epoch = 1;
+        }
+        uint32_t *st = D.refit_range_state.p;
+        VT_CUDA(vt_launch_refit_quads_range(V, (uint32_t)first, (uint32_t)count, D.refit_slot_of.p, D.refit_leaf_quad.p, D.refit_parent.p, st,
+                                            st + V.n_pairs, st + 2 * (size_t)V.n_pairs, D.refit_qbox.p, D.refit_epoch, D.refit_error.p, stream));
+        D.refit_epoch += 3;
+        mLaunches += 2;
+    } else {
+        VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
+    }
     VT_CUDA(vt_launch_refit_cost(D.refit_qbox.p, V.n_pairs, D.refit_cost.p, stream));
     VT_CUDA(cudaMemcpyAsync(&D.refit_cost_now, D.refit_cost.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
     mLaunches += 3;

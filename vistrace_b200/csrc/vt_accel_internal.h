@@ -117,6 +117,9 @@ struct DeviceScene {
     // K5 (device refit) state, built on the first refit of a resident quad hierarchy
     DevBuf<vt_tri_in> refit_in;
     DevBuf<uint32_t> refit_parent, refit_n_inner, refit_slot_of, refit_arrive, refit_error;
+    DevBuf<uint32_t> refit_leaf_quad;    // leaf slot -> the quad that holds the leaf (ranged refit starts there)
+    DevBuf<uint32_t> refit_range_state;  // 3 x n_quads, all zero between calls: epoch stamps | dirty-child counts | arrivals
+    uint32_t refit_epoch = 1;            // += 3 per vt_accel_refit_range
     DevBuf<float> refit_qbox;  // 6 floats per quad
     DevBuf<double> refit_cost;  // device scalar of k_refit_cost
     double refit_cost_built = 0.0, refit_cost_now = 0.0;  // node-area sums: as built (taken when the refit state is prepared) / after the last refit
@@ -160,6 +163,8 @@ struct DeviceScene {
         refit_parent.release();
         refit_n_inner.release();
         refit_slot_of.release();
+        refit_leaf_quad.release();
+        refit_range_state.release();
         refit_arrive.release();
         refit_error.release();
         refit_qbox.release();

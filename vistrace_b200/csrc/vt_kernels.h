@@ -96,10 +96,17 @@ cudaError_t vt_launch_path_shade(const vt_attr *attrs, const vt_hit *shadow_hits
 // (parent / inner-child count per quad, original triangle -> leaf slot).  refit_tris: Triangle constructor over the
 // caller's new vertices into the resident triangle / attribute records.  refit_quads: bottom-up boxes + requantisation;
 // qbox = n_quads x 24 bytes of scratch, *error != 0 afterwards when a box could not be held on the float grid.
-cudaError_t vt_launch_refit_prepare(const VtSceneView &S, uint32_t *parent, uint32_t *n_inner, uint32_t *slot_of, cudaStream_t stream);
+cudaError_t vt_launch_refit_prepare(const VtSceneView &S, uint32_t *parent, uint32_t *n_inner, uint32_t *slot_of, uint32_t *leaf_quad,
+                                    cudaStream_t stream);
 cudaError_t vt_launch_refit_tris(const VtSceneView &S, const vt_tri_in *in, uint32_t first, uint32_t count, const uint32_t *slot_of,
                                  cudaStream_t stream);  // in[j] = new vertices of original triangle first + j
 // *sum = sum of the half surface areas of the n_quads boxes in qbox (as left by vt_launch_refit_quads): the rebuild trigger's measure.
 cudaError_t vt_launch_refit_cost(const void *qbox, uint32_t n_quads, double *sum, cudaStream_t stream);
 cudaError_t vt_launch_refit_quads(const VtSceneView &S, const uint32_t *parent, const uint32_t *n_inner, uint32_t *arrive, void *qbox,
                                   unsigned int *error, cudaStream_t stream);
+// The same for original triangles [first, first + count) only: the quads that hold them and their ancestors.  stamp / kids / arrive:
+// n_quads words each, zero before the first call and left zero by every call; epoch: odd, > 0, += 3 per call.  qbox must hold the
+// boxes of a previous vt_launch_refit_quads pass (untouched children are read from it).
+cudaError_t vt_launch_refit_quads_range(const VtSceneView &S, uint32_t first, uint32_t count, const uint32_t *slot_of, const uint32_t *leaf_quad,
+                                        const uint32_t *parent, uint32_t *stamp, uint32_t *kids, uint32_t *arrive, void *qbox, uint32_t epoch,
+                                        unsigned int *error, cudaStream_t stream);

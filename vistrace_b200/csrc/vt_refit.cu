@@ -30,15 +30,20 @@ namespace {
 #define VT_REF_MASK 0x0FFFFFFFu
 
 __global__ void k_refit_prepare(const VtQuad *__restrict__ quads, uint32_t n_quads, const VtTriRec *__restrict__ tris, uint32_t n_tris,
-                                uint32_t *__restrict__ parent, uint32_t *__restrict__ n_inner, uint32_t *__restrict__ slot_of) {
+                                uint32_t *__restrict__ parent, uint32_t *__restrict__ n_inner, uint32_t *__restrict__ slot_of,
+                                uint32_t *__restrict__ leaf_quad) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_quads) {
         uint32_t inner = 0;
         for (int c = 0; c < 4; c++) {
             const uint32_t ref = quads[i].ref[c];
-            if (ref != 0xFFFFFFFFu && (ref >> VT_REF_SHIFT) == 0) {
+            if (ref == 0xFFFFFFFFu) continue;
+            const uint32_t count = ref >> VT_REF_SHIFT, idx = ref & VT_REF_MASK;
+            if (count == 0) {
                 parent[ref] = i;
                 inner++;
+            } else if (idx < n_tris) {  // a real leaf (not the sentinel of an empty slot): its slots hang off this quad
+                for (uint32_t t = 0; t < count; t++) leaf_quad[idx + t] = i;
             }
         }
         n_inner[i] = inner;
@@ -143,73 +148,135 @@ struct Box6 {
     float lo[3], hi[3];
 };
 
+// One quad: exact child boxes (leaf children from their triangles, inner children from qbox), grid + plane bytes re-derived, the
+// quad and its exact union box stored.  false: the box cannot be put on a float grid (the caller raises the error flag).
+__device__ bool refit_one_quad(VtQuad *quads, uint32_t q, const VtTriRec *__restrict__ tris, uint32_t n_tris, Box6 *qbox) {
+    VtQuad node = quads[q];
+    Box6 cb[4], un;
+    bool used[4];
+    for (int a = 0; a < 3; a++) un.lo[a] = FLT_MAX, un.hi[a] = -FLT_MAX;
+    for (int c = 0; c < 4; c++) {
+        const uint32_t ref = node.ref[c];
+        const uint32_t count = ref >> VT_REF_SHIFT, idx = ref & VT_REF_MASK;
+        used[c] = ref != 0xFFFFFFFFu && !(count != 0 && idx >= n_tris);  // 0xFFFFFFFF or the sentinel leaf: empty slot
+        if (!used[c]) continue;
+        Box6 b;
+        if (count == 0) {
+            // written by the thread that finished that child before it signalled arrival (threadfence + atomic in the callers),
+            // or — ranged walk, untouched child — by an earlier pass
+            const volatile Box6 *src = qbox + idx;
+            for (int a = 0; a < 3; a++) b.lo[a] = src->lo[a], b.hi[a] = src->hi[a];
+        } else {
+            for (int a = 0; a < 3; a++) b.lo[a] = FLT_MAX, b.hi[a] = -FLT_MAX;
+            for (uint32_t t = 0; t < count; t++) {
+                const VtTriRec &tr = tris[idx + t];
+                for (int a = 0; a < 3; a++) {
+                    const float v0 = tr.p0[a], v1 = tr.p0[a] - tr.e1[a], v2 = tr.p0[a] + tr.e2[a];
+                    b.lo[a] = fminf(b.lo[a], fminf(v0, fminf(v1, v2)));
+                    b.hi[a] = fmaxf(b.hi[a], fmaxf(v0, fmaxf(v1, v2)));
+                }
+            }
+        }
+        cb[c] = b;
+        for (int a = 0; a < 3; a++) un.lo[a] = fminf(un.lo[a], b.lo[a]), un.hi[a] = fmaxf(un.hi[a], b.hi[a]);
+    }
+    for (int a = 0; a < 3; a++) {
+        int E = 0;
+        long long k = 0;
+        if (!(isfinite(un.lo[a]) && isfinite(un.hi[a])) || un.hi[a] < un.lo[a] || !choose_grid_dev(un.lo[a], un.hi[a], E, k)) return false;
+        const double s = ldexp(1.0, E);
+        node.origin_adj[a] = (float)((double)(k - VT_QUAD_OFFSET) * s);
+        node.scale[a] = (float)s;
+        for (int c = 0; c < 4; c++) {
+            if (used[c]) {
+                node.q[a][0][c] = (uint8_t)((long long)floor((double)cb[c].lo[a] / s) - k);
+                node.q[a][1][c] = (uint8_t)((long long)ceil((double)cb[c].hi[a] / s) - k);
+            } else {
+                node.q[a][0][c] = 255;  // empty slot: inverted box
+                node.q[a][1][c] = 0;
+            }
+        }
+    }
+    quads[q] = node;
+    qbox[q] = un;
+    return true;
+}
+
 __global__ void k_refit_quads(VtQuad *quads, uint32_t n_quads, const VtTriRec *__restrict__ tris, uint32_t n_tris,
                               const uint32_t *__restrict__ parent, const uint32_t *__restrict__ n_inner, uint32_t *arrive,
                               Box6 *qbox, unsigned int *error) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_quads || n_inner[q] != 0) return;  // start at the quads all of whose children are leaves
     for (;;) {
-        VtQuad node = quads[q];
-        Box6 cb[4], un;
-        bool used[4];
-        for (int a = 0; a < 3; a++) un.lo[a] = FLT_MAX, un.hi[a] = -FLT_MAX;
-        for (int c = 0; c < 4; c++) {
-            const uint32_t ref = node.ref[c];
-            const uint32_t count = ref >> VT_REF_SHIFT, idx = ref & VT_REF_MASK;
-            used[c] = ref != 0xFFFFFFFFu && !(count != 0 && idx >= n_tris);  // 0xFFFFFFFF or the sentinel leaf: empty slot
-            if (!used[c]) continue;
-            Box6 b;
-            if (count == 0) {
-                // written by the thread that finished that child before it signalled arrival (threadfence + atomic below)
-                const volatile Box6 *src = qbox + idx;
-                for (int a = 0; a < 3; a++) b.lo[a] = src->lo[a], b.hi[a] = src->hi[a];
-            } else {
-                for (int a = 0; a < 3; a++) b.lo[a] = FLT_MAX, b.hi[a] = -FLT_MAX;
-                for (uint32_t t = 0; t < count; t++) {
-                    const VtTriRec &tr = tris[idx + t];
-                    for (int a = 0; a < 3; a++) {
-                        const float v0 = tr.p0[a], v1 = tr.p0[a] - tr.e1[a], v2 = tr.p0[a] + tr.e2[a];
-                        b.lo[a] = fminf(b.lo[a], fminf(v0, fminf(v1, v2)));
-                        b.hi[a] = fmaxf(b.hi[a], fmaxf(v0, fmaxf(v1, v2)));
-                    }
-                }
-            }
-            cb[c] = b;
-            for (int a = 0; a < 3; a++) un.lo[a] = fminf(un.lo[a], b.lo[a]), un.hi[a] = fmaxf(un.hi[a], b.hi[a]);
-        }
-        bool ok = true;
-        for (int a = 0; a < 3; a++) {
-            int E = 0;
-            long long k = 0;
-            if (!(isfinite(un.lo[a]) && isfinite(un.hi[a])) || un.hi[a] < un.lo[a] || !choose_grid_dev(un.lo[a], un.hi[a], E, k)) {
-                ok = false;
-                break;
-            }
-            const double s = ldexp(1.0, E);
-            node.origin_adj[a] = (float)((double)(k - VT_QUAD_OFFSET) * s);
-            node.scale[a] = (float)s;
-            for (int c = 0; c < 4; c++) {
-                if (used[c]) {
-                    node.q[a][0][c] = (uint8_t)((long long)floor((double)cb[c].lo[a] / s) - k);
-                    node.q[a][1][c] = (uint8_t)((long long)ceil((double)cb[c].hi[a] / s) - k);
-                } else {
-                    node.q[a][0][c] = 255;  // empty slot: inverted box
-                    node.q[a][1][c] = 0;
-                }
-            }
-        }
-        if (!ok) {
+        if (!refit_one_quad(quads, q, tris, n_tris, qbox)) {
             atomicExch(error, 1u);  // non-finite geometry or coordinates out of float grid range: the host re-derives the layout
             return;
         }
-        quads[q] = node;
-        qbox[q] = un;
         const uint32_t p = parent[q];
         if (p == 0xFFFFFFFFu) return;  // the root
         __threadfence();               // box and node visible before the arrival is counted
         if (atomicAdd(&arrive[p], 1u) + 1u < n_inner[p]) return;  // a sibling subtree is still being refitted
         __threadfence();
         q = p;
+    }
+}
+
+// Ranged refit (vt_accel_refit_range: one entity moved): only the quads that hold a touched triangle and their ANCESTORS change;
+// every other quad keeps its bytes and its qbox entry from the previous pass.  Three kernels, one thread per touched triangle, over
+// per-quad state that is all-zero between calls (stamp[] compares against a per-call epoch E, E += 3 per call):
+//   k_refit_mark_range   walks from the triangle's quad to the root stamping E; the first thread to stamp a quad counts it as a dirty
+//                        child of its parent and goes on, later ones stop there (the first carries on upwards).
+//   k_refit_quads_range  claims the triangle's quad (E -> E + 1: one winner per quad); a quad without dirty inner children is a
+//                        starting point, the others are processed by their last dirty child to arrive — the bottom-up protocol of
+//                        k_refit_quads with kids[] in the place of n_inner.  kids[] is read-only here: a quad that holds touched
+//                        triangles AND dirty children must see the same count whenever its claimant looks.
+//   k_refit_clear_range  walks the same chains stamping E + 2 and zeroes kids[] / arrive[] (also after an aborted pass).
+// A one-entity range at 1.07 M quads touches a few thousand quads instead of all of them.
+__global__ void k_refit_mark_range(uint32_t first, uint32_t count, const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ leaf_quad,
+                                   const uint32_t *__restrict__ parent, uint32_t *stamp, uint32_t *kids, uint32_t epoch) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    uint32_t q = leaf_quad[slot_of[first + j]];
+    for (;;) {
+        if (atomicExch(&stamp[q], epoch) == epoch) return;
+        const uint32_t p = parent[q];
+        if (p == 0xFFFFFFFFu) return;
+        atomicAdd(&kids[p], 1u);
+        q = p;
+    }
+}
+
+__global__ void k_refit_quads_range(VtQuad *quads, const VtTriRec *__restrict__ tris, uint32_t n_tris, uint32_t first, uint32_t count,
+                                    const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ leaf_quad,
+                                    const uint32_t *__restrict__ parent, uint32_t *stamp, const uint32_t *kids, uint32_t *arrive,
+                                    Box6 *qbox, uint32_t epoch, unsigned int *error) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    uint32_t q = leaf_quad[slot_of[first + j]];
+    if (atomicCAS(&stamp[q], epoch, epoch + 1u) != epoch) return;  // another touched triangle of the same quad got here first
+    if (kids[q] != 0) return;                                      // its last dirty child processes it
+    for (;;) {
+        if (!refit_one_quad(quads, q, tris, n_tris, qbox)) {
+            atomicExch(error, 1u);
+            return;
+        }
+        const uint32_t p = parent[q];
+        if (p == 0xFFFFFFFFu) return;
+        __threadfence();
+        if (atomicAdd(&arrive[p], 1u) + 1u < kids[p]) return;
+        __threadfence();
+        q = p;
+    }
+}
+
+__global__ void k_refit_clear_range(uint32_t first, uint32_t count, const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ leaf_quad,
+                                    const uint32_t *__restrict__ parent, uint32_t *stamp, uint32_t *kids, uint32_t *arrive, uint32_t epoch) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    uint32_t q = leaf_quad[slot_of[first + j]];
+    while (q != 0xFFFFFFFFu && atomicExch(&stamp[q], epoch + 2u) != epoch + 2u) {
+        kids[q] = 0, arrive[q] = 0;
+        q = parent[q];
     }
 }
 
@@ -236,10 +303,11 @@ cudaError_t vt_launch_refit_cost(const void *qbox, uint32_t n_quads, double *sum
     return cudaGetLastError();
 }
 
-cudaError_t vt_launch_refit_prepare(const VtSceneView &S, uint32_t *parent, uint32_t *n_inner, uint32_t *slot_of, cudaStream_t stream) {
+cudaError_t vt_launch_refit_prepare(const VtSceneView &S, uint32_t *parent, uint32_t *n_inner, uint32_t *slot_of, uint32_t *leaf_quad,
+                                    cudaStream_t stream) {
     const uint32_t n = S.n_pairs > S.n_tris ? S.n_pairs : S.n_tris;
     if (n == 0) return cudaSuccess;
-    k_refit_prepare<<<(n + 255) / 256, 256, 0, stream>>>(S.quads, S.n_pairs, S.tris, S.n_tris, parent, n_inner, slot_of);
+    k_refit_prepare<<<(n + 255) / 256, 256, 0, stream>>>(S.quads, S.n_pairs, S.tris, S.n_tris, parent, n_inner, slot_of, leaf_quad);
     return cudaGetLastError();
 }
 
@@ -260,5 +328,18 @@ cudaError_t vt_launch_refit_quads(const VtSceneView &S, const uint32_t *parent, 
     if (e != cudaSuccess) return e;
     k_refit_quads<<<(S.n_pairs + 127) / 128, 128, 0, stream>>>(const_cast<VtQuad *>(S.quads), S.n_pairs, S.tris, S.n_tris, parent, n_inner,
                                                                arrive, static_cast<Box6 *>(qbox), error);
+    return cudaGetLastError();
+}
+
+cudaError_t vt_launch_refit_quads_range(const VtSceneView &S, uint32_t first, uint32_t count, const uint32_t *slot_of, const uint32_t *leaf_quad,
+                                        const uint32_t *parent, uint32_t *stamp, uint32_t *kids, uint32_t *arrive, void *qbox, uint32_t epoch,
+                                        unsigned int *error, cudaStream_t stream) {
+    if (S.n_pairs == 0 || count == 0) return cudaSuccess;
+    if ((uint64_t)first + count > S.n_tris || epoch == 0 || epoch > 0xFFFFFFF0u) return cudaErrorInvalidValue;
+    const uint32_t blocks = (count + 127) / 128;
+    k_refit_mark_range<<<blocks, 128, 0, stream>>>(first, count, slot_of, leaf_quad, parent, stamp, kids, epoch);
+    k_refit_quads_range<<<blocks, 128, 0, stream>>>(const_cast<VtQuad *>(S.quads), S.tris, S.n_tris, first, count, slot_of, leaf_quad, parent, stamp,
+                                                    kids, arrive, static_cast<Box6 *>(qbox), epoch, error);
+    k_refit_clear_range<<<blocks, 128, 0, stream>>>(first, count, slot_of, leaf_quad, parent, stamp, kids, arrive, epoch);
     return cudaGetLastError();
 }
