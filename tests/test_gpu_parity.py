@@ -646,13 +646,14 @@ def test_refit_range_one_moved_entity(vt, oracle_mod):
     """vt_accel_refit_range: only the moved entities' triangles go up; the resident scene ends up byte-identical in effect to a
     whole-scene refit — same hit records, same derived triangles, same refitted host boxes — and equal to the checker."""
     from test_host import _moved_props
-    from vistrace_b200 import scenes
+    from vistrace_b200 import abi, scenes
 
     scene = scenes.scene_props(8, 21, 11, 12)
     moved = _moved_props(scene)
     rays = np.concatenate([scenes.pinhole_rays(320, 180, (0, -95, 40), (0, 0, 10)), scenes.random_rays(20000, (-90, -90, -5), (90, 90, 60), seed=12)])
     whole = vt.Accel(0, layout="quad").populate(scene).refit(moved)
-    part = vt.Accel(0, layout="quad").populate(scene)
+    # its own copy of the scene: refit_range keeps the Python-side triangle array of the handle in step
+    part = vt.Accel(0, layout="quad").populate(abi.SceneData(scene.tris.copy(), scene.materials, scene.entities))
     for ent in range(1, len(scene.entities)):  # entity by entity, each a contiguous run of the triangle array
         idx = np.nonzero(scene.tris["ent_idx"] == ent)[0]
         assert idx[-1] - idx[0] + 1 == len(idx)

@@ -692,7 +692,15 @@ void AccelStruct::RefitRange(const vt_tri_in *tris, uint64_t first, uint64_t cou
     if (!D.refit_ready) mLaunches += prepare_refit_state(D, stream);
     VT_CUDA(cudaMemsetAsync(D.refit_error.p, 0, sizeof(uint32_t), stream));
     VT_CUDA(vt_launch_refit_tris(V, D.refit_in.p, (uint32_t)first, (uint32_t)count, D.refit_slot_of.p, stream));
-    if (env_int("VT_REFIT_RANGE_WALK", 1) != 0) {
+    const bool timing = env_int("VT_TIMING", 0) != 0;  // device time of the bottom-up walk, one stderr line
+    cudaEvent_t walk_t0 = nullptr, walk_t1 = nullptr;
+    if (timing) {
+        VT_CUDA(cudaEventCreate(&walk_t0));
+        VT_CUDA(cudaEventCreate(&walk_t1));
+        VT_CUDA(cudaEventRecord(walk_t0, stream));
+    }
+    const bool ranged_walk = env_int("VT_REFIT_RANGE_WALK", 1) != 0;
+    if (ranged_walk) {
         // only the quads holding a touched triangle and their ancestors (every other quad keeps its bytes and its box-table entry)
         if (D.refit_epoch > 0xFFFFFF00u) {
             VT_CUDA(cudaMemsetAsync(D.refit_range_state.p, 0, (size_t)V.n_pairs * 3 * sizeof(uint32_t), stream));
@@ -706,6 +714,7 @@ void AccelStruct::RefitRange(const vt_tri_in *tris, uint64_t first, uint64_t cou
     } else {
         VT_CUDA(vt_launch_refit_quads(V, D.refit_parent.p, D.refit_n_inner.p, D.refit_arrive.p, D.refit_qbox.p, D.refit_error.p, stream));
     }
+    if (timing) VT_CUDA(cudaEventRecord(walk_t1, stream));
     VT_CUDA(vt_launch_refit_cost(D.refit_qbox.p, V.n_pairs, D.refit_cost.p, stream));
     VT_CUDA(cudaMemcpyAsync(&D.refit_cost_now, D.refit_cost.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
     mLaunches += 3;
@@ -723,6 +732,13 @@ void AccelStruct::RefitRange(const vt_tri_in *tris, uint64_t first, uint64_t cou
     uint32_t failed = 0;
     VT_CUDA(cudaMemcpyAsync(&failed, D.refit_error.p, sizeof(failed), cudaMemcpyDeviceToHost, stream));
     VT_CUDA(cudaStreamSynchronize(stream));
+    if (timing) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, walk_t0, walk_t1);
+        std::fprintf(stderr, "[refit_range] %llu triangles, %s walk %.3f ms on the device\n", (unsigned long long)count, ranged_walk ? "ranged" : "whole-tree", ms);
+        cudaEventDestroy(walk_t0);
+        cudaEventDestroy(walk_t1);
+    }
     D.refit_in.release();
     mBvhStale = true;
     if (failed)  // the resident records are half updated: the handle stays invalid until the caller rebuilds
