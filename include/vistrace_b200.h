@@ -547,6 +547,17 @@ int vt_accel_get_tri_derived(const vt_accel *accel, float *out16);
  * entry and the node count on return; prim_indices has scene->n_tris entries. */
 int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, uint64_t *prim_indices);
 
+/* Host-only builder-quality option: reinsertion optimisation of a finished bvh::Bvh<float>-form hierarchy,
+ * in place — this library's version of bvh::ParallelReinsertionOptimizer (libs/bvh/include/bvh/parallel_reinsertion_optimizer.hpp),
+ * which the reference's library offers and the reference does not call.  `iterations` passes; each takes up to ~`fraction` of the
+ * nodes (largest boxes first; 0.05 is a good value) out of the tree and puts them back where the sum of the inner-node areas (the
+ * SAH traversal term) grows least.  Leaves keep their primitive ranges, so prim_indices stays valid; node order is depth-first
+ * again afterwards.  The array is left untouched when the result would be deeper than 60 levels or no better.  area_before /
+ * area_after (nullable): the sum of inner-node half-areas; moves (nullable): reinsertions applied.  VT_REINSERT=<iterations> makes
+ * vt_accel_populate / vt_build_bvh run it on the product builder's tree (off by default: profiles/r2_reinsertion.md). */
+int vt_optimize_bvh(vt_node *nodes, uint64_t node_count, int iterations, double fraction, double *area_before, double *area_after,
+                    uint64_t *moves);
+
 /* Host-only: the REFERENCE's hierarchy for the scene, rebuilt from its algorithm — bvh::LocallyOrderedClusteringBuilder
  * <BVH, uint32_t> (libs/bvh/include/bvh/locally_ordered_clustering_builder.hpp: search radius 14, 30-bit Morton codes) and,
  * with collapse != 0, bvh::LeafCollapser (leaf_collapser.hpp) — the sequence of source/objects/AccelStruct.cpp:762-770.

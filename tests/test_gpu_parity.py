@@ -642,6 +642,42 @@ def test_ploc_builder_gives_the_reference_answers_ties_included(vt, oracle_mod, 
     assert same_hits(quad.traverse(rays), want["hits"], "quad", rays, cpu)
 
 
+@pytest.mark.parametrize("scene_name", ["props", "foliage"])
+def test_reinsertion_optimised_tree_gives_the_checkers_answers(vt, oracle_mod, scene_name, monkeypatch):
+    """VT_REINSERT (builder-quality option, vt_bvh_reinsert.cpp): vt_accel_populate optimises the product builder's tree before it is
+    flattened; the engine over that tree equals the checker over the SAME tree — byte for byte on the exact layout, up to counted
+    ties on the quantised ones — and the plain build's hit records up to exact ties; on separate objects it takes fewer node visits."""
+    from vistrace_b200 import scenes
+
+    scene = scenes.scene_props(8, 21, 11, 12) if scene_name == "props" else scenes.scene_foliage(n_cards=3000, tex_size=64, ground_quads=16)
+    eye = (0, -95, 40) if scene_name == "props" else (0, -48, 20)
+    rays = np.concatenate([scenes.pinhole_rays(320, 180, eye, (0, 0, 10)), scenes.random_rays(20000, (-90, -90, -5), (90, 90, 60), seed=4)])
+    plain = vt.Accel(0, layout="quad").populate(scene)
+    monkeypatch.setenv("VT_REINSERT", "3")
+    monkeypatch.setenv("VT_REINSERT_FRACTION", "0.3")
+    kind = "reference" if oracle_mod.available("reference") else "port"
+    cpu = oracle_mod.CpuScene(scene, kind, build_bvh=False)
+    want = None
+    for layout in ("exact", "compact", "quad"):
+        accel = vt.Accel(0, layout=layout).populate(scene)
+        assert accel.layout == layout
+        nodes, prims = accel.get_bvh()
+        if want is None:
+            assert nodes.tobytes() != plain.get_bvh()[0].tobytes()  # the pass did move nodes
+            cpu.set_bvh(nodes, prims)
+            want = cpu.traverse(rays, want_attrs=True)
+        hits, attrs = accel.traverse(rays, want_attrs=True)
+        if layout == "exact":
+            assert hits.tobytes() == want["hits"].tobytes()
+            err = attr_max_rel_err(attrs, want["attrs"])
+            assert max(err[f] for f in ATTR_FLOAT_FIELDS) <= 1e-5
+        else:
+            assert same_hits(hits, want["hits"], layout, rays, cpu)
+    assert same_hits(plain.traverse(rays), want["hits"], "quad", rays, cpu)
+    if scene_name == "props":
+        assert accel.traverse_stats(rays)[0] < plain.traverse_stats(rays)[0]
+
+
 def test_refit_range_one_moved_entity(vt, oracle_mod):
     """vt_accel_refit_range: only the moved entities' triangles go up; the resident scene ends up byte-identical in effect to a
     whole-scene refit — same hit records, same derived triangles, same refitted host boxes — and equal to the checker."""

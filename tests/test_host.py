@@ -118,6 +118,83 @@ def test_builder_tree_is_valid_and_equivalent(oracle_mod, scene_name):
     assert nodes.tobytes() == nodes2.tobytes() and prims.tobytes() == prims2.tobytes()
 
 
+@pytest.mark.parametrize("scene_name", ["heightfield", "foliage", "props"])
+def test_reinsertion_optimisation_keeps_the_tree_valid_and_the_answers(oracle_mod, scene_name):
+    """vt_optimize_bvh (builder-quality option; the reference library's counterpart is
+    bvh::ParallelReinsertionOptimizer): the optimised array is a well-formed depth-first bvh::Bvh-form tree over the SAME leaves,
+    every inner box is exactly the union of its children, the sum of inner-node areas went down as reported, the oracle's
+    traverser finds the same hits over it (exact ties aside) and the result is deterministic."""
+    import vistrace_b200 as vt
+    from vistrace_b200 import binding, scenes
+
+    scene = {"heightfield": lambda: scenes.scene_heightfield(48), "foliage": lambda: scenes.scene_foliage(1200, tex_size=32),
+             "props": lambda: scenes.scene_props(5, 15, 9, 12)}[scene_name]()
+    nodes, prims = vt.build_bvh(scene)
+    opt, before, after, moves = binding.optimize_bvh(nodes, iterations=6, fraction=0.3)
+    assert len(opt) == len(nodes) and moves > 0 and 0 < after < before
+    # the same leaves (primitive ranges untouched), a tree again: every pair referenced once, children behind their parents
+    leaf = lambda a: sorted(zip(a["first"][a["prim_count"] > 0].tolist(), a["prim_count"][a["prim_count"] > 0].tolist()))
+    assert leaf(opt) == leaf(nodes)
+    inner = np.nonzero(opt["prim_count"] == 0)[0]
+    first = opt["first"][inner]
+    assert (first % 2 == 1).all() and len(set(first.tolist())) == len(inner) == (len(opt) - 1) // 2 and (first > inner).all()
+    lo, hi = opt["bounds"][:, 0::2], opt["bounds"][:, 1::2]
+    np.testing.assert_array_equal(lo[inner], np.minimum(lo[first], lo[first + 1]))
+    np.testing.assert_array_equal(hi[inner], np.maximum(hi[first], hi[first + 1]))
+
+    def inner_area(a):
+        e = (a["bounds"][:, 1::2] - a["bounds"][:, 0::2]).astype(np.float64)[a["prim_count"] == 0]
+        return float((e[:, 0] * e[:, 1] + e[:, 1] * e[:, 2] + e[:, 2] * e[:, 0]).sum())
+
+    assert inner_area(nodes) == pytest.approx(before, rel=1e-5) and inner_area(opt) == pytest.approx(after, rel=1e-5)
+    flat = vt.flatten_bvh(opt, prims)  # the product's own validation: adjacent odd pairs, every primitive once, depth <= 64
+    assert sorted(flat["leaf_order"].tolist()) == list(range(scene.n_tris))
+    quads = binding.build_quads(opt, prims)
+    assert sorted(quads["leaf_order"].tolist()) == list(range(scene.n_tris)) and quads["max_stack"] <= 64
+    rays = np.concatenate([scenes.pinhole_rays(96, 54, (0, -48, 20), (0, 0, 8)), scenes.random_rays(4000, (-45, -45, -2), (45, 45, 40), seed=5)])
+    cpu = oracle_mod.CpuScene(scene, "port", build_bvh=False)
+    cpu.set_bvh(nodes, prims)
+    want = cpu.traverse(rays, want_stats=True)
+    cpu.set_bvh(opt, prims)
+    got = cpu.traverse(rays, want_stats=True)
+    rep = compare_hits(got["hits"], want["hits"])
+    assert rep["hit_miss_mismatch"] == 0 and rep["prim_mismatch"] == rep["prim_mismatch_exact_tie"], rep
+    np.testing.assert_array_equal(got["hits"]["t"], want["hits"]["t"])
+    if scene_name == "props":  # separate objects on a ground plane: the case the pass is made for
+        assert got["steps"] < want["steps"]
+    again = binding.optimize_bvh(nodes, iterations=6, fraction=0.3)
+    assert again[0].tobytes() == opt.tobytes() and again[1:] == (before, after, moves)
+    # nothing to do / nothing done leaves the array as it was
+    assert binding.optimize_bvh(nodes, iterations=0)[0].tobytes() == nodes.tobytes()
+    tiny = np.zeros(3, nodes.dtype)  # a root over two leaves: nothing can move
+    tiny["bounds"] = [(0, 2, 0, 1, 0, 1), (0, 1, 0, 1, 0, 1), (1, 2, 0, 1, 0, 1)]
+    tiny["prim_count"], tiny["first"] = [0, 1, 1], [1, 0, 1]
+    out = binding.optimize_bvh(tiny, iterations=4)
+    assert out[0].tobytes() == tiny.tobytes() and out[3] == 0
+
+
+def test_reinsertion_rejects_malformed_arrays(built):
+    from vistrace_b200 import binding, scenes
+
+    nodes, _ = binding.build_bvh(scenes.scene_heightfield(16))
+    bad = nodes.copy()
+    k = int(np.nonzero(bad["prim_count"] == 0)[0][3])
+    bad["first"][k] = len(bad) + 5  # child pair outside the array
+    with pytest.raises(RuntimeError):
+        binding.optimize_bvh(bad)
+    bad = nodes.copy()
+    bad["first"][k] = bad["first"][k] + 1  # even index: not a sibling pair
+    with pytest.raises(RuntimeError):
+        binding.optimize_bvh(bad)
+    bad = nodes.copy()
+    inner = np.nonzero(bad["prim_count"] == 0)[0]
+    bad["first"][inner[5]] = bad["first"][inner[4]]  # two parents for one pair: not a tree
+    with pytest.raises(RuntimeError):
+        binding.optimize_bvh(bad)
+    with pytest.raises(RuntimeError):
+        binding.optimize_bvh(nodes[:-1])  # even node count
+
+
 def _emulate_pairs(flat, tris_derived, rays):
     """Tiny numpy traverser over the FLATTENED layout (pairs + leaf order) — checks the structure the GPU walks."""
     pairs, order = flat["pairs"], flat["leaf_order"]

@@ -66,6 +66,7 @@ SYMBOLS = {
     "vt_bsp_get_material": (_i32, [_vp, _u64, _u32, _vp]),
     "vt_bsp_get_static_prop": (_i32, [_vp, _u64, _u32, _vp]),
     "vt_build_bvh_ploc": (_i32, [_vp, _i32, _vp, _vp, _vp]),
+    "vt_optimize_bvh": (_i32, [_vp, _u64, _i32, C.c_double, _vp, _vp, _vp]),
     "vt_build_quads": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "vt_accel_refit_quality": (_i32, [_vp, _vp, _vp]),
     "vt_accel_set_refit_rebuild_ratio": (_i32, [_vp, C.c_double]),
@@ -150,6 +151,16 @@ def build_bvh_ploc(scene, collapse=True):
     cap = C.c_uint64(len(nodes))
     _check(L.vt_build_bvh_ploc(C.cast(scene.ptr(), _vp), int(collapse), nodes.ctypes.data, C.addressof(cap), prims.ctypes.data), "vt_build_bvh_ploc")
     return nodes[: cap.value].copy(), prims
+
+
+def optimize_bvh(nodes, iterations=4, fraction=0.05):
+    """Host-only reinsertion optimisation -> (optimised COPY of `nodes`, inner-node area before, after, moves applied);
+    prim_indices stays valid (leaves keep their ranges)."""
+    out = np.ascontiguousarray(nodes, abi.NODE).copy()
+    before, after, moves = C.c_double(0), C.c_double(0), C.c_uint64(0)
+    _check(lib().vt_optimize_bvh(out.ctypes.data, len(out), int(iterations), float(fraction), C.addressof(before), C.addressof(after),
+                                 C.addressof(moves)), "vt_optimize_bvh")
+    return out, before.value, after.value, moves.value
 
 
 def refit_bvh(scene, nodes, prim_indices):

@@ -478,6 +478,10 @@ void AccelStruct::Populate(const vt_scene &scene) {
         build_bvh(mTriangles, mAccel, env_int("VT_MAX_LEAF", 4), env_float("VT_TRAV_COST", 1.0f), (uint32_t)std::max(0, env_int("VT_SAH_SWEEP", 0)));
     }
     timer.lap("hierarchy build");
+    if (const int passes = env_int("VT_REINSERT", 0); passes > 0) {  // builder-quality option, off by default (vt_bvh_reinsert.cpp)
+        if (!reinsert_optimize(mAccel, passes, env_float("VT_REINSERT_FRACTION", 0.05f))) throw std::runtime_error("reinsertion: malformed hierarchy");
+        timer.lap("reinsertion optimisation");
+    }
     Upload(scene);
     timer.lap("flatten + records + upload");
 }
@@ -1744,12 +1748,29 @@ int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, ui
     }
     vt::HostBvh bvh;
     vt::build_bvh(tris, bvh, vt::env_int("VT_MAX_LEAF", 4), vt::env_float("VT_TRAV_COST", 1.0f), (uint32_t)std::max(0, vt::env_int("VT_SAH_SWEEP", 0)));
+    if (const int passes = vt::env_int("VT_REINSERT", 0); passes > 0 && !vt::reinsert_optimize(bvh, passes, vt::env_float("VT_REINSERT_FRACTION", 0.05f)))
+        throw std::runtime_error("reinsertion: malformed hierarchy");
     if (nodes) {
         if (*node_count < bvh.nodes.size()) throw std::runtime_error("node buffer too small");
         std::memcpy(nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(vt_node));
         if (prim_indices) std::memcpy(prim_indices, bvh.prim_indices.data(), bvh.prim_indices.size() * sizeof(uint64_t));
     }
     *node_count = bvh.nodes.size();
+    return 0;
+    VT_CATCH(1)
+}
+
+int vt_optimize_bvh(vt_node *nodes, uint64_t node_count, int iterations, double fraction, double *area_before, double *area_after, uint64_t *moves) {
+    VT_TRY
+    if (!nodes || node_count == 0) throw std::runtime_error("null hierarchy");
+    if (node_count % 2 == 0) throw std::runtime_error("optimize_bvh: a bvh::Bvh-form hierarchy has an odd node count (root + sibling pairs)");
+    for (uint64_t i = 0; i < node_count; i++)  // untrusted array: every inner node must name a pair inside it
+        if (nodes[i].prim_count == 0 && (nodes[i].first == 0 || nodes[i].first % 2 == 0 || (uint64_t)nodes[i].first + 1 >= node_count))
+            throw std::runtime_error("optimize_bvh: inner node " + std::to_string(i) + " does not reference a sibling pair of the array");
+    vt::HostBvh bvh;
+    bvh.nodes.assign(nodes, nodes + node_count);
+    if (!vt::reinsert_optimize(bvh, iterations, (float)fraction, area_before, area_after, moves)) throw std::runtime_error("optimize_bvh: the node array is not one tree");
+    std::memcpy(nodes, bvh.nodes.data(), node_count * sizeof(vt_node));
     return 0;
     VT_CATCH(1)
 }

@@ -84,6 +84,12 @@ struct FlatBvh {
 // sweep_below: builder-quality option — nodes of at most that many primitives are split by the exact SAH sweep over sorted
 // centroids (bvh::SweepSahBuilder's evaluation, libs/bvh/include/bvh/sweep_sah_builder.hpp) instead of 16 bins; 0 = binned only.
 void build_bvh(const TriangleVec &tris, HostBvh &out, int max_leaf, float trav_cost, uint32_t sweep_below = 0);
+// Builder-quality option (vt_bvh_reinsert.cpp): reinsertion optimisation of a finished hierarchy, the product's version of
+// bvh::ParallelReinsertionOptimizer (libs/bvh/include/bvh/parallel_reinsertion_optimizer.hpp).  `iterations` passes, each moving
+// up to ~`fraction` of the nodes (largest boxes first) to the position where the sum of inner-node areas grows least; leaves keep
+// their primitive ranges.  The tree is left as it was when the result would be deeper than 60 or no better.  false: malformed tree.
+bool reinsert_optimize(HostBvh &bvh, int iterations, float fraction = 0.05f, double *area_before = nullptr, double *area_after = nullptr,
+                       uint64_t *moves = nullptr);
 // The reference's own hierarchy rebuilt from its algorithm (vt_bvh_ploc.cpp): bvh::LocallyOrderedClusteringBuilder<BVH, uint32_t>
 // (search radius 14, 30-bit Morton codes) and bvh::LeafCollapser, the sequence of source/objects/AccelStruct.cpp:762-770.
 void build_bvh_ploc(const TriangleVec &tris, HostBvh &out);
