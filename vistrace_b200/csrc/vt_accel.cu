@@ -294,6 +294,11 @@ void AccelStruct::Upload(const vt_scene &scene) {
     std::vector<VtCPair> cpairs;
     std::string err;
     if (layout == VT_LAYOUT_QUAD && !build_quads(mAccel, n, quad, err)) layout = VT_LAYOUT_EXACT;
+    {   // child order of the quad kernel (vt_traverse.cu: VT_KEY_MID): by entry + exit where sibling boxes overlap, by entry elsewhere
+        const char *order = std::getenv("VT_KEY_ORDER");
+        const std::string o = order ? order : "auto";
+        D.cfg.key_mid = o == "mid" ? 1 : o == "entry" ? 0 : (quad.sibling_overlap > (double)env_float("VT_COLLAPSE_OVERLAP", 0.225f) ? 1 : 0);
+    }
 #if VT_SMEM_QUADS_BUILD
     if (layout == VT_LAYOUT_QUAD) smem_pairs = quads_top_first(quad, (uint32_t)std::max(0, env_int("VT_SMEM_QUADS", 0)));  // A/B builds only
 #endif
@@ -516,6 +521,7 @@ void AccelStruct::ExportReplica(ReplicaImage &img, const void *bufs[10]) const {
     for (int i = 0; i < 10; i++) img.bytes[i] = bytes[i], bufs[i] = bytes[i] ? ptrs[i] : nullptr;
     img.n_pairs = V.n_pairs, img.n_tris = V.n_tris, img.root_leaf_count = V.root_leaf_count, img.n_smem_pairs = V.n_smem_pairs;
     img.has_alphatest = V.has_alphatest, img.fallback_tex = V.fallback_tex;
+    img.key_mid = (uint32_t)D.cfg.key_mid;
     img.layout = mLayout;
     img.n_materials = (uint32_t)D.mats.cap;
 }
@@ -553,6 +559,7 @@ void AccelStruct::AllocReplica(const ReplicaImage &img, void *bufs[10]) {
     V.tris = D.tris.p, V.tri_uv = D.tri_uv.p, V.attrs = D.attrs.p, V.mats = D.mats.p, V.ents = D.ents.p, V.texs = D.texs.p, V.texels = D.texels.p;
     V.n_pairs = img.n_pairs, V.n_tris = img.n_tris, V.root_leaf_count = img.root_leaf_count, V.n_smem_pairs = img.n_smem_pairs;
     V.has_alphatest = img.has_alphatest, V.fallback_tex = img.fallback_tex;
+    D.cfg.key_mid = (int)img.key_mid;  // the child order chosen for the scene travels with its image
     V.magic = 0x4B000000u;
     V.magic_h = 0x64646464u;
     D.cfg.persistent = env_int("VT_PERSISTENT", 1);

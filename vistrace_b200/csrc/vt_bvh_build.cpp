@@ -916,6 +916,9 @@ bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string 
     }
     CollapsePlan plan;
     if (!plan_collapse(bvh, 4, plan, err)) return false;
+    out.sibling_overlap = plan.sibling_overlap, out.greedy_collapse = plan.greedy;
+    if (std::getenv("VT_TIMING") && std::atoi(std::getenv("VT_TIMING")) != 0)
+        std::fprintf(stderr, "[build_quads] sibling overlap %.3f -> %s collapse\n", plan.sibling_overlap, plan.greedy ? "greedy (largest child)" : "SAH-optimal");
     QuadBuilder b(bvh, n_tris, out, err, plan);
     b.quads_below.assign(bvh.nodes.size(), 0);
     b.tris_below.assign(bvh.nodes.size(), 0);

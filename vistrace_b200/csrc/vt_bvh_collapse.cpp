@@ -6,6 +6,13 @@
 //   distribute(n, j) = min over 0 < k < j of cost(left, k) + cost(right, j - k)
 //   cost(leaf, i) = A(leaf) * triangles * c_prim
 //
+// Which plan is used (VT_COLLAPSE = auto | dp | greedy, default auto): the SAH-optimal plan lowers the number of wide nodes a ray
+// visits on surfaces and separate objects (quad visits per bounce ray 21.28 -> 21.02 on the 5 M-triangle terrain) but on a volume of
+// heavily overlapping alpha-tested cards it ruins the front-to-back order of camera rays (config 4, primary K1: 3.10 ms greedy,
+// 5.72 ms SAH-optimal; 78.8 -> 109.7 visits, 83 -> 124 triangle tests per ray — session r4c).  auto measures the sibling overlap
+// of the binary tree (sibling_overlap below) and keeps the round-1 rule "adopt the children of the largest child" above 0.225 (VT_COLLAPSE_OVERLAP) — the same figure
+// switches the kernel's child order to entry + exit (vt_traverse.cu: VT_KEY_MID), which removes most of that loss by itself.
+//
 // Leaves are kept as the builder made them (no triangles are merged or moved), so the set of triangles a ray can reach through a
 // given box is unchanged; only how many box tests and dependent fetches it takes to get there.
 #include <algorithm>
@@ -25,12 +32,41 @@ float half_area(const vt_node &n) {
 }
 }  // namespace
 
+// Area-weighted overlap of sibling boxes: sum over inner nodes of A(left box ^ right box) / sum of A(node).  The SAH prices a tree for
+// rays that pass through everything; how well an ORDERED traversal terminates early depends on how much siblings overlap (Aila,
+// Karras, Laine, "On Quality Metrics of Bounding Volume Hierarchies", HPG 2013).  Measured on the product builder's trees: 0.15 - 0.20
+// for surfaces and separate objects (terrain, props), 0.35 - 0.44 for the alpha-tested foliage volume (profiles/r2_collapse_choice.md).
+double sibling_overlap(const HostBvh &bvh) {
+    const size_t n = bvh.nodes.size();
+    double overlap = 0.0, total = 0.0;
+#pragma omp parallel for reduction(+ : overlap, total) schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const vt_node &nd = bvh.nodes[i];
+        if (nd.prim_count != 0 || nd.first == 0 || (size_t)nd.first + 1 >= n) continue;
+        const vt_node &l = bvh.nodes[nd.first], &r = bvh.nodes[nd.first + 1];
+        double e[3];
+        bool apart = false;
+        for (int a = 0; a < 3; a++) {
+            e[a] = (double)std::min(l.bounds[2 * a + 1], r.bounds[2 * a + 1]) - (double)std::max(l.bounds[2 * a], r.bounds[2 * a]);
+            apart = apart || !(e[a] >= 0.0);
+        }
+        if (!apart) overlap += e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
+        total += (double)half_area(nd);
+    }
+    return total > 0.0 ? overlap / total : 0.0;
+}
+
 bool plan_collapse(const HostBvh &bvh, int width, CollapsePlan &plan, std::string &err) {
     plan.width = width;
     plan.split.clear();
     const char *mode = std::getenv("VT_COLLAPSE");
     plan.greedy = mode && std::string(mode) == "greedy";
     const size_t n = bvh.nodes.size();
+    plan.sibling_overlap = sibling_overlap(bvh);
+    if (!(mode && *mode) || std::string(mode) == "auto") {
+        const char *th = std::getenv("VT_COLLAPSE_OVERLAP");
+        plan.greedy = plan.sibling_overlap > ((th && *th) ? std::atof(th) : 0.225);
+    }
     if (plan.greedy || n == 0 || bvh.nodes[0].prim_count != 0) return true;
     if (width < 2 || width > 8) {
         err = "collapse: width must be 2..8";

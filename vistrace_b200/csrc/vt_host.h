@@ -105,6 +105,8 @@ struct QuadBvh {
     RawVector<uint32_t> leaf_order;
     uint32_t root_leaf_count = 0;
     uint32_t max_stack = 0;  // worst-case number of pending references
+    double sibling_overlap = 0.0;  // of the binary tree (vt_bvh_collapse.cpp): what the collapse rule and the kernel's child order are chosen by
+    bool greedy_collapse = false;
 };
 bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string &err);
 uint32_t quads_top_first(QuadBvh &qb, uint32_t top);  // experiment: breadth-first prefix for shared-memory staging (VT_SMEM_QUADS)
@@ -117,10 +119,12 @@ struct CollapsePlan {
     int width = 0;
     std::vector<uint8_t> split;  // [node * width + i]: how many of i + 1 roots go to the left child (0: use one root fewer)
     bool greedy = false;
+    double sibling_overlap = 0.0;  // of the binary tree the plan was made for (what VT_COLLAPSE=auto decided on)
     // children of the wide node that replaces binary inner node `ni` -> kids[0 .. return value)
     int children(const HostBvh &bvh, uint32_t ni, uint32_t *kids) const;
 };
 bool plan_collapse(const HostBvh &bvh, int width, CollapsePlan &plan, std::string &err);
+double sibling_overlap(const HostBvh &bvh);  // area-weighted overlap of sibling boxes, 0 .. ~0.5 (vt_bvh_collapse.cpp)
 // 64-byte pairs in depth-first order -> 32-byte conservative compact pairs (vt_device.h: VtCPair)
 bool compact_pairs(const std::vector<VtPair> &pairs, std::vector<VtCPair> &out, std::string &err);
 
@@ -229,7 +233,7 @@ public:
     // processes); every GPU then holds the whole scene (replicate, never partition).
     struct ReplicaImage {
         uint64_t bytes[10];  // pairs, cpairs, quads, tris, tri_uv, attrs, mats, ents, texs, texels
-        uint32_t n_pairs, n_tris, root_leaf_count, n_smem_pairs, has_alphatest, fallback_tex;
+        uint32_t n_pairs, n_tris, root_leaf_count, n_smem_pairs, has_alphatest, fallback_tex, key_mid;
         int32_t layout;
         uint32_t n_materials;
     };

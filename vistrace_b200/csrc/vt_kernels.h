@@ -26,6 +26,7 @@ struct VtLaunchConfig {
     int grid = 0;               // CTAs for the persistent launch (SMs x resident CTAs)
     int refill_threshold = 24;  // refill a warp when <= this many of its lanes still own a ray
     int tri_threshold = 10;     // run a triangle round when >= this many lanes have a candidate queued (6 / 8 / 10: 3.39 / 3.47 / 3.51 Grays/s)
+    int key_mid = 0;            // quad layout: order a node's children by entry + exit instead of entry (vt_traverse.cu: VT_KEY_MID); set per scene
     int tail_share = 1;         // quantised layouts, closest hit: idle lanes take pending sub-trees of long rays once the ray queue is dry (VT_TAIL_SHARE)
 };
 

@@ -312,6 +312,16 @@ VT_DEV void slab_cpair(const VtCPair *cpairs, uint32_t cur, uint32_t magic, cons
 //                      two HADD2.F32 (FMA pipe) widen it — 12 PRMT + 24 conversions instead of 24 PRMT per step.  The host
 //                      then stores origin_adj = (k - 1024) * 2^E (vt_device.h).  Measured: IMAD.HI is quarter rate on
 //                      B200 (tools/ubench/pipes.cu), so the byte-3 decode through IMAD.HI was slower and is gone.
+//   VT_KEY_MID         children are ordered by entry + exit (twice the midpoint of the ray's interval inside the box) instead of
+//                      the entry distance.  A box that CONTAINS the ray origin has entry = tmin whatever it holds, so the entry
+//                      order sends a camera inside a room's top-level boxes into the largest sub-tree first, however far its
+//                      content is; the midpoint prefers the box that ends sooner.  For boxes that do not overlap along the ray the
+//                      two orders are the same.  One FADD per child on the FMA pipe.  Foliage in a room, camera rays, SAH-optimal
+//                      collapse: 40.7 -> 31.9 quad visits, 20.2 -> 14.6 triangle tests per ray; terrain and props unchanged
+//                      (profiles/r2_child_order.md).  Any order is correct (canonical tie rule); order only prunes.
+//                      A template parameter of the kernel (KEYMID), chosen per scene by the host from the sibling overlap of
+//                      its hierarchy (VtLaunchConfig::key_mid; VT_KEY_ORDER = auto | entry | mid): on the bench terrain, where
+//                      the orders coincide, the extra FADDs cost 1 % of the bounce launch (1.610 -> 1.626 ms, session r4e).
 #ifndef VT_SORT_CE
 #define VT_SORT_CE 5
 #endif
@@ -340,7 +350,7 @@ VT_DEV float2 decode_half_pair(uint32_t q, uint32_t magic_h, uint32_t sel) {
     return __half22float2(*reinterpret_cast<const __half2 *>(&h));
 }
 #endif
-template <bool TWO_FMA>
+template <bool TWO_FMA, bool KEYMID>
 VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const RayState &ray, int (&k)[4], uint32_t (&r)[4],
                       const uint4 *s_top = nullptr, uint32_t n_top = 0) {
     uint4 a0, a1, b0, b1;
@@ -402,8 +412,8 @@ VT_DEV void slab_quad(const VtQuad *quads, uint32_t cur, uint32_t magic, const R
         /* an empty slot's inverted box can look hit after rounding when the node is tiny and far: either test the   \
            ref too, or let the slot reference the all-NaN sentinel triangle (VT_EMPTY_SENTINEL) */                     \
         const bool hit = (VT_EMPTY_SENTINEL || r[i] != VT_REF_DONE) && en <= ex;           \
-        /* en >= tmin >= 0: its bit pattern orders like the value (-0.0 sorts first) */    \
-        k[i] = hit ? VT_QUAD_KEY(en, i) : 0x7FFFFFFF;                                      \
+        /* en >= tmin >= 0 (and ex >= en when hit): the bit pattern orders like the value (-0.0 sorts first) */ \
+        k[i] = hit ? VT_QUAD_KEY(KEYMID ? en + ex : en, i) : 0x7FFFFFFF;                   \
     }
     VT_CHILD(0, 0x7650u)
     VT_CHILD(1, 0x7651u)
@@ -670,7 +680,7 @@ k_traverse(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restr
 // the ray and its current tmax), walks it on its own stack, and hands its best candidate back; the owner keeps the closest (ties: the
 // canonical rule above) and writes the record when all its helpers have reported.  A helper may itself give work away; the count of
 // outstanding helpers is kept by the ray's owner.  Nothing changes while the queue still has rays: refills keep the lanes busy.
-template <bool ANY_HIT, bool ALPHA, bool STATS, bool QUAD, bool SHARE = false>
+template <bool ANY_HIT, bool ALPHA, bool STATS, bool QUAD, bool SHARE = false, bool KEYMID = false>
 __global__ void __launch_bounds__(VT_TRAVERSE_BLOCK, VT_COMPACT_MIN_BLOCKS)
 k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit *__restrict__ hits, unsigned long long n,
                    unsigned long long *__restrict__ counters, int persistent, int refill_threshold, int tri_threshold,
@@ -970,8 +980,8 @@ k_traverse_compact(const VtSceneView S, const vt_ray *__restrict__ rays, vt_hit 
                 if (QUAD) {
                     int k[4];
                     uint32_t cr[4];
-                    if (warp_wild) slab_quad<true>(S.quads, cur, magic, r, k, cr, s_top_quads, n_top);
-                    else slab_quad<false>(S.quads, cur, magic, r, k, cr, s_top_quads, n_top);
+                    if (warp_wild) slab_quad<true, KEYMID>(S.quads, cur, magic, r, k, cr, s_top_quads, n_top);
+                    else slab_quad<false, KEYMID>(S.quads, cur, magic, r, k, cr, s_top_quads, n_top);
                     // farthest first, so the nearest pending child is popped first
                     if (k[3] != 0x7FFFFFFF) {
                         stack_push<DIST>(sp, cr[3], (uint32_t)k[3]);
@@ -1046,6 +1056,15 @@ cudaError_t vt_launch_traverse(const VtSceneView &S, const vt_ray *rays, vt_hit 
                                                           cfg.persistent ? 1 : 0, cfg.refill_threshold, cfg.tri_threshold, queue, queue_count);
         return cudaGetLastError();
     };
+    if (S.quads && cfg.key_mid && !VT_STACK_DIST) {  // children ordered by entry + exit (scenes whose sibling boxes overlap: VT_KEY_MID above)
+        if (stats) {
+            if (any_hit) return cudaErrorInvalidValue;
+            return alpha ? launch(k_traverse_compact<false, true, true, true, false, true>) : launch(k_traverse_compact<false, false, true, true, false, true>);
+        }
+        if (any_hit) return alpha ? launch(k_traverse_compact<true, true, false, true, false, true>) : launch(k_traverse_compact<true, false, false, true, false, true>);
+        if (cfg.tail_share) return alpha ? launch(k_traverse_compact<false, true, false, true, true, true>) : launch(k_traverse_compact<false, false, false, true, true, true>);
+        return alpha ? launch(k_traverse_compact<false, true, false, true, false, true>) : launch(k_traverse_compact<false, false, false, true, false, true>);
+    }
     if (S.quads) {
         if (stats) {  // closest hit only; counters[2] += traversal steps, counters[3] += triangle tests
             if (any_hit) return cudaErrorInvalidValue;
