@@ -79,38 +79,61 @@ def primary_rays():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed regions (resident and e2e) run."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed regions (resident and e2e) run.
+
+    ONE nvidia-smi process for the whole run, started before the first timed region and killed after the last (the recipe's
+    "start before, kill after"): its start-up initialises NVML, which takes driver locks for several hundred milliseconds — started
+    at the top of a 56 ms host-driven region (20 e2e steps) it slowed the region it was meant to observe (e2e 2.55 -> 2.82 ms per
+    step, session r4g).  A region begins only after the first sample has arrived; only samples taken inside a region are summarised."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread, self.windows, self.failed = index, [], None, None, [], False
 
-    def __enter__(self):  # re-enterable: rows accumulate over every timed region
+    def start(self):
+        if self.proc or self.failed:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
-            self.proc = None
-        return self
+            self.proc, self.failed = None, True
+            return
+        t_end = time.perf_counter() + 5.0
+        while not self.rows and self.proc.poll() is None and time.perf_counter() < t_end:  # NVML is up once the first line is out
+            time.sleep(0.01)
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def __enter__(self):  # re-enterable: one window per timed region
+        self.start()
+        self.windows.append([time.perf_counter(), None])
+        return self
 
     def __exit__(self, *exc):
         if self.proc:
-            time.sleep(0.25)
+            time.sleep(0.06)  # a region shorter than the sampling period still gets its sample (the GPU is busy until the sync before this)
+        self.windows[-1][1] = time.perf_counter()
+
+    def close(self):
+        if self.proc:
             self.proc.terminate()
             self.thread.join(timeout=2)
+            self.proc = None
 
     def summary(self):
+        self.close()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if not any(w0 <= t <= (w1 if w1 is not None else t) for w0, w1 in self.windows):
+                continue
             try:
                 sm.append(float(r[1]))
                 smax.append(float(r[2]))
@@ -492,6 +515,7 @@ def run_ours(args):
     seed0 = 1000
     steps, warmup = args.steps, args.warmup
     clocks = ClockSampler(local_rank)
+    clocks.start()  # NVML start-up happens here, not at the top of a timed region
     launch_count = (lambda: group.launch_count) if group else (lambda: accel.launch_count)
     launches = 0
 
