@@ -11,6 +11,7 @@
 //                                       GetMIPLevels / GetPixel, include/vistrace/IVTFTexture.h:44-97), so any extension's texture
 //                                       class works, not just VTFTexture;
 //   * GpuAccelBinding::TraverseBatch    the batched entry next to AccelStruct::Traverse;
+//   * vtbind_optimize_check            vt_optimize_bvh on the real mAccel.nodes, the reference's own traverser before and after (host only)
 //   * vtbind_selfcheck                  runs the reference's own per-ray statements (AccelStruct.cpp:810-831) and the batched GPU
 //                                       call over the same rays and reports every difference.
 //
@@ -180,6 +181,37 @@ int vtbind_selfcheck(const vt_scene *s, const vt_ray *rays, uint64_t n, int layo
         if (x.ent_id != y.ent_id || x.submat_idx != y.submat_idx || x.flags != y.flags) worst = 1e30;
     }
     if (max_attr_err) *max_attr_err = worst;
+    return 0;
+}
+
+// INTEGRATION.md section 5, "Builder options": vt_optimize_bvh in place on the REAL bvh::Bvh<float> of the reference's AccelStruct
+// (its own PLOC + LeafCollapser build), then the reference's own traverser over its own — now optimised — containers.  Host only.
+// report: [0] rays, [1] hit/miss mismatches, [2] t/u/v bit mismatches, [3] primitive mismatches (exact ties: same t), [4] reinsertions
+//         applied, [5] traversal steps before, [6] after, [7] node count.  areas: inner-node area before / after.
+int vtbind_optimize_check(const vt_scene *s, const vt_ray *rays, uint64_t n, int iterations, double fraction, uint64_t *report, double *areas,
+                          char *err, uint64_t err_cap) {
+    auto say = [&](const std::string &m) {
+        if (err && err_cap) std::snprintf(err, err_cap, "%s", m.c_str());
+        return 1;
+    };
+    std::unique_ptr<RefScene> rs(static_cast<RefScene *>(vtref_create(s, 1)));
+    AccelStruct &a = rs->accel;
+    std::vector<vt_hit> before(n), after(n);
+    uint64_t st0[2] = {0, 0}, st1[2] = {0, 0};
+    vtref_traverse(rs.get(), rays, n, before.data(), nullptr, 0, st0);
+    static_assert(sizeof(vt_node) == sizeof(BVH::Node), "vt_node is bit-compatible with bvh::Bvh<float>::Node");
+    uint64_t moves = 0;
+    if (vt_optimize_bvh(reinterpret_cast<vt_node *>(a.mAccel.nodes.get()), a.mAccel.node_count, iterations, fraction, &areas[0], &areas[1], &moves) != 0)
+        return say(std::string("vt_optimize_bvh: ") + vt_last_error());
+    vtref_traverse(rs.get(), rays, n, after.data(), nullptr, 0, st1);
+    std::memset(report, 0, 8 * sizeof(uint64_t));
+    report[0] = n, report[4] = moves, report[5] = st0[0], report[6] = st1[0], report[7] = a.mAccel.node_count;
+    for (uint64_t i = 0; i < n; i++) {
+        const vt_hit &g = after[i], &w = before[i];
+        if ((g.prim == VT_MISS) != (w.prim == VT_MISS)) report[1]++;
+        else if (g.prim != VT_MISS && std::memcmp(&g.t, &w.t, 4) != 0) report[2]++;
+        else if (g.prim != w.prim) report[3]++;
+    }
     return 0;
 }
 

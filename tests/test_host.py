@@ -173,6 +173,31 @@ def test_reinsertion_optimisation_keeps_the_tree_valid_and_the_answers(oracle_mo
     assert out[0].tobytes() == tiny.tobytes() and out[3] == 0
 
 
+def test_reinsertion_on_the_reference_objects_own_hierarchy(built):
+    """INTEGRATION.md "Builder options" compiled (oracle/ref_binding.cpp, vtbind_optimize_check; host only): vt_optimize_bvh runs in
+    place on the REAL bvh::Bvh<float> of the reference's AccelStruct — built by its own PLOC + LeafCollapser sequence
+    (source/objects/AccelStruct.cpp:762-770) — and the reference's own traverser (`:810-831`) then walks its own, optimised,
+    containers: same hits (exact ties aside), fewer traversal steps on a scene of separate objects."""
+    import ctypes as C
+
+    from vistrace_b200 import scenes
+
+    so = os.path.join(ROOT, "oracle", "_ref", "libvt_ref_binding.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libvt_ref_binding.so is built where /root/reference exists (make -C oracle binding)")
+    lib = C.CDLL(so)
+    lib.vtbind_optimize_check.restype = C.c_int
+    lib.vtbind_optimize_check.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint64]
+    scene = scenes.scene_props(8, 21, 11, 12)
+    rays = np.ascontiguousarray(np.concatenate([scenes.pinhole_rays(160, 90, (0, -95, 40), (0, 0, 10)), scenes.random_rays(8000, (-90, -90, -5), (90, 90, 60), seed=8)]))
+    report, areas, err = np.zeros(8, np.uint64), np.zeros(2, np.float64), C.create_string_buffer(512)
+    rc = lib.vtbind_optimize_check(C.cast(scene.ptr(), C.c_void_p), rays.ctypes.data, len(rays), 6, 0.3, report.ctypes.data, areas.ctypes.data, err, 512)
+    assert rc == 0, err.value.decode()
+    n, hit_miss, tuv, prim, moves, steps_before, steps_after, nodes = (int(v) for v in report)
+    assert n == len(rays) and hit_miss == 0 and tuv == 0 and prim <= 2, report
+    assert moves > 0 and 0 < areas[1] < areas[0] and steps_after < steps_before, (report, areas)
+
+
 def test_reinsertion_rejects_malformed_arrays(built):
     from vistrace_b200 import binding, scenes
 
