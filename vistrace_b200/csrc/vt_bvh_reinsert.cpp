@@ -15,8 +15,8 @@
 //      touched is dropped (its gain was computed for a tree that no longer exists);
 //   4. all inner boxes are recomputed bottom-up.
 // Leaves keep their primitive ranges, so prim_indices is untouched and every triangle stays in its leaf.  The result is laid out
-// depth-first again (children behind their parents), and it is discarded when it would be deeper than the 64-entry traversal
-// stack of single_ray_traverser.hpp:14 allows (the builder's own bound is 60).
+// depth-first again (children behind their parents); a pass that would make the tree deeper than the 64-entry traversal stack of
+// single_ray_traverser.hpp:14 allows (the builder's own bound is 60) ends the optimisation with the result of the pass before.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -197,7 +197,9 @@ bool reinsert_optimize(HostBvh &bvh, int iterations, float fraction, double *are
     std::vector<float> area(n);
     std::vector<Move> moves;
     std::vector<uint32_t> touched(n, 0);
-    uint64_t applied = 0;
+    uint64_t applied = 0, applied_good = 0;
+    RawVector<vt_node> good;  // the tree after the last pass that kept it within the depth bound (empty: the tree as built)
+    double area_good = before;
     for (int it = 0; it < iterations; it++) {
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < (int64_t)n; i++) area[i] = half_area(box_of(t.nodes[i]));
@@ -235,12 +237,21 @@ bool reinsert_optimize(HostBvh &bvh, int iterations, float fraction, double *are
         if (!t.preorder(order, nullptr, max_depth)) return false;
         t.refit(order);
         if (done == 0) break;
+        if (max_depth > kMaxDepth) break;  // deeper than the traversal stack allows: keep the result of the pass before
+        const double now = t.inner_area();
+        if (now < area_good) {
+            good.resize(n);
+            std::memcpy(good.data(), t.nodes, n * sizeof(vt_node));
+            area_good = now, applied_good = applied;
+        }
     }
-    if (!t.preorder(order, nullptr, max_depth)) return false;
-    const double after = t.inner_area();
     if (area_before) *area_before = before;
     if (area_after) *area_after = before;
-    if (max_depth > kMaxDepth || !(after < before)) return true;  // keep the tree as it was built
+    if (good.empty()) return true;  // keep the tree as it was built
+    std::memcpy(t.nodes, good.data(), n * sizeof(vt_node));
+    if (!t.preorder(order, nullptr, max_depth)) return false;
+    const double after = area_good;
+    applied = applied_good;
     // depth-first relayout: root at 0, a node's children adjacent and behind it, left sub-tree before the right one
     std::vector<uint32_t> new_pair(n, 0);  // old index of the first child of a pair -> new index
     {
