@@ -173,6 +173,33 @@ def test_reinsertion_optimisation_keeps_the_tree_valid_and_the_answers(oracle_mo
     assert out[0].tobytes() == tiny.tobytes() and out[3] == 0
 
 
+def test_collapse_rule_is_chosen_by_sibling_overlap(built, monkeypatch):
+    """VT_COLLAPSE=auto (the default): a dense volume of overlapping cards keeps the largest-child rule, surfaces and separate objects
+    get the SAH-optimal plan (vt_bvh_collapse.cpp: sibling_overlap against VT_COLLAPSE_OVERLAP, profiles/r2_child_order.md); either
+    way the quads hold every triangle once and fewer wide nodes than binary inner nodes."""
+    from vistrace_b200 import binding, scenes
+
+    cases = {"dense foliage": (scenes.scene_foliage(n_cards=12000, extent=16.0, tex_size=32, ground_quads=8), "greedy"),
+             "height field": (scenes.scene_heightfield(64), "dp"), "props": (scenes.scene_props(6, 15, 9, 8), "dp")}
+    for name, (scene, expect) in cases.items():
+        nodes, prims = binding.build_bvh(scene)
+        built_by = {}
+        for mode in ("auto", "dp", "greedy"):
+            monkeypatch.setenv("VT_COLLAPSE", mode)
+            built_by[mode] = binding.build_quads(nodes, prims)
+        monkeypatch.delenv("VT_COLLAPSE")
+        default = binding.build_quads(nodes, prims)
+        assert default["quads"].tobytes() == built_by["auto"]["quads"].tobytes()
+        assert built_by["auto"]["quads"].tobytes() == built_by[expect]["quads"].tobytes(), name
+        assert built_by["dp"]["quads"].tobytes() != built_by["greedy"]["quads"].tobytes()
+        assert len(built_by["dp"]["quads"]) < len(built_by["greedy"]["quads"]) < (len(nodes) - 1) // 2 + 1
+        for q in built_by.values():
+            assert sorted(q["leaf_order"].tolist()) == list(range(scene.n_tris))
+    monkeypatch.setenv("VT_COLLAPSE_OVERLAP", "0.0")  # threshold override: everything counts as overlapping
+    nodes, prims = binding.build_bvh(cases["props"][0])
+    assert binding.build_quads(nodes, prims)["quads"].tobytes() == built_by["greedy"]["quads"].tobytes()
+
+
 def test_reinsertion_on_the_reference_objects_own_hierarchy(built):
     """INTEGRATION.md "Builder options" compiled (oracle/ref_binding.cpp, vtbind_optimize_check; host only): vt_optimize_bvh runs in
     place on the REAL bvh::Bvh<float> of the reference's AccelStruct — built by its own PLOC + LeafCollapser sequence
