@@ -554,7 +554,7 @@ int vt_build_bvh(const vt_scene *scene, vt_node *nodes, uint64_t *node_count, ui
  * SAH traversal term) grows least.  Leaves keep their primitive ranges, so prim_indices stays valid; node order is depth-first
  * again afterwards.  The array is left untouched when the result would be deeper than 60 levels or no better.  area_before /
  * area_after (nullable): the sum of inner-node half-areas; moves (nullable): reinsertions applied.  VT_REINSERT=<iterations> makes
- * vt_accel_populate / vt_build_bvh run it on the product builder's tree (off by default: profiles/r2_reinsertion.md). */
+ * vt_accel_populate / vt_build_bvh run it on the product builder's tree (off by default: profiles/r2_child_order.md section 3). */
 int vt_optimize_bvh(vt_node *nodes, uint64_t node_count, int iterations, double fraction, double *area_before, double *area_after,
                     uint64_t *moves);
 

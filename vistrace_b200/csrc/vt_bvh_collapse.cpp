@@ -35,7 +35,7 @@ float half_area(const vt_node &n) {
 // Area-weighted overlap of sibling boxes: sum over inner nodes of A(left box ^ right box) / sum of A(node).  The SAH prices a tree for
 // rays that pass through everything; how well an ORDERED traversal terminates early depends on how much siblings overlap (Aila,
 // Karras, Laine, "On Quality Metrics of Bounding Volume Hierarchies", HPG 2013).  Measured on the product builder's trees: 0.15 - 0.20
-// for surfaces and separate objects (terrain, props), 0.35 - 0.44 for the alpha-tested foliage volume (profiles/r2_collapse_choice.md).
+// for surfaces and separate objects (terrain, props), 0.35 - 0.44 for the alpha-tested foliage volume (profiles/r2_child_order.md).
 double sibling_overlap(const HostBvh &bvh) {
     const size_t n = bvh.nodes.size();
     double overlap = 0.0, total = 0.0;
