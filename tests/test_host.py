@@ -73,6 +73,22 @@ def test_no_cpu_fallback(built):
         vt.Accel(0)
 
 
+def test_ingestion_survives_mutation_fuzz_under_sanitizers(built):
+    """tools/fuzz/run.sh: the host-only ingestion code (VTF / MDL / BSP) compiled with AddressSanitizer + UBSan reads a few hundred
+    mutated synthetic files from exact-size heap buffers — every file is either parsed or rejected, nothing reads out of bounds."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("g++"):
+        pytest.skip("no C++ compiler")
+    probe = subprocess.run("echo 'int main(){}' | g++ -x c++ - -fsanitize=address,undefined -o /dev/null", shell=True, capture_output=True)
+    if probe.returncode != 0:
+        pytest.skip("g++ cannot link the sanitizer runtimes here")
+    out = subprocess.run([os.path.join(ROOT, "tools", "fuzz", "run.sh"), "7", "300"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    assert "no sanitizer finding" in out.stdout and out.stdout.count("accepted") >= 3
+
+
 def test_product_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "vistrace_b200")):
         for f in files:

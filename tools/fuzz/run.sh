@@ -1,0 +1,17 @@
+#!/bin/bash
+# Mutation fuzz of the host-only ingestion code (vt_vtf.cpp, vt_mdl.cpp, vt_bsp.cpp) under AddressSanitizer + UBSan: synthetic files of
+# the test generators (tests/test_vtf.py, tests/mdl_files.py, tests/bsp_files.py) with random byte / word / offset mutations and
+# truncations, every file read into an exact-size heap buffer.  No GPU, no CUDA.
+# usage: tools/fuzz/run.sh [seed] [files per parser]      (a finding prints an ASan / UBSan report and the script exits 1)
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"; ROOT="$HERE/../.."
+SEED=${1:-1}; N=${2:-3000}
+W=$(mktemp -d)
+g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fno-sanitize-recover=undefined -fno-omit-frame-pointer -fopenmp -ffp-contract=off \
+    -I"$ROOT/vistrace_b200/csrc" -I"$ROOT/include" -I/usr/local/cuda/include \
+    "$HERE/ingest_driver.cpp" "$ROOT/vistrace_b200/csrc/vt_bsp.cpp" "$ROOT/vistrace_b200/csrc/vt_mdl.cpp" "$ROOT/vistrace_b200/csrc/vt_vtf.cpp" -o "$W/driver"
+python "$HERE/make_corpus.py" "$SEED" "$N" "$W/corpus"
+for k in bsp vtf; do ls "$W"/corpus/$k/* | xargs -n 500 "$W/driver" $k; done
+ls "$W"/corpus/mdl/*.mdl | sed 's/\.mdl$//' | awk '{print $0".mdl "$0".vvd "$0".vtx"}' | xargs -n 600 "$W/driver" mdl
+rm -rf "$W"
+echo "fuzz: seed $SEED, $N files per parser: no sanitizer finding"
