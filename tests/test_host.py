@@ -75,7 +75,8 @@ def test_no_cpu_fallback(built):
 
 def test_ingestion_survives_mutation_fuzz_under_sanitizers(built):
     """tools/fuzz/run.sh: the host-only ingestion code (VTF / MDL / BSP) compiled with AddressSanitizer + UBSan reads a few hundred
-    mutated synthetic files from exact-size heap buffers — every file is either parsed or rejected, nothing reads out of bounds."""
+    mutated synthetic files from exact-size heap buffers, and the hierarchy code (builders, flatten, layouts, refit, reinsertion) is
+    run over hostile geometry and mutated node arrays — everything is either processed or refused, nothing reads out of bounds."""
     import shutil
     import subprocess
 
@@ -84,9 +85,9 @@ def test_ingestion_survives_mutation_fuzz_under_sanitizers(built):
     probe = subprocess.run("echo 'int main(){}' | g++ -x c++ - -fsanitize=address,undefined -o /dev/null", shell=True, capture_output=True)
     if probe.returncode != 0:
         pytest.skip("g++ cannot link the sanitizer runtimes here")
-    out = subprocess.run([os.path.join(ROOT, "tools", "fuzz", "run.sh"), "7", "300"], capture_output=True, text=True, timeout=900)
+    out = subprocess.run([os.path.join(ROOT, "tools", "fuzz", "run.sh"), "7", "300"], capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
-    assert "no sanitizer finding" in out.stdout and out.stdout.count("accepted") >= 3
+    assert "no sanitizer finding" in out.stdout and out.stdout.count("accepted") >= 3 and "hierarchy: seed 7" in out.stdout
 
 
 def test_product_never_imports_the_oracle():
@@ -385,6 +386,52 @@ def test_flatten_rejects_malformed_trees(built):
     chain[2 * 69 + 1]["prim_count"], chain[2 * 69 + 1]["first"] = 1, 70
     with pytest.raises(RuntimeError, match="deeper"):
         vt.flatten_bvh(chain, np.arange(71, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("collapse", ["auto", "dp", "greedy"])
+def test_quad_builder_rejects_malformed_trees_under_every_collapse_rule(built, collapse, monkeypatch):
+    """Found by tools/fuzz/hierarchy_driver.cpp: the largest-child collapse followed grandchild references before anything had checked
+    them (a hostile `first` read past the node array).  Every rule now refuses a child reference that is even, zero, out of range or
+    shared by two parents — vt_build_quads is what vt_accel_populate_with_bvh runs on a caller's tree."""
+    from vistrace_b200 import binding, scenes
+
+    monkeypatch.setenv("VT_COLLAPSE", collapse)
+    scene = scenes.scene_foliage(n_cards=3000, extent=8.0, tex_size=32, ground_quads=4)  # dense: auto picks the largest-child rule
+    nodes, prims = binding.build_bvh(scene)
+    assert len(binding.build_quads(nodes, prims)["quads"]) > 100
+    inner = np.nonzero(nodes["prim_count"] == 0)[0]
+    deep = [int(i) for i in inner if i > 40][:50]
+    for k, value in enumerate([len(nodes) + 1000, 0xFFFFFFF1, 0, 2, len(nodes) - 1, int(nodes["first"][inner[3]])]):
+        bad = nodes.copy()
+        bad["first"][deep[3 * k]] = value
+        with pytest.raises(RuntimeError):
+            binding.build_quads(bad, prims)
+    bad = nodes.copy()
+    bad["prim_count"][deep[20]] = 0xFFFFFFFF  # an inner node turned into an impossible leaf
+    with pytest.raises(RuntimeError):
+        binding.build_quads(bad, prims)
+    with pytest.raises(RuntimeError):
+        binding.build_quads(nodes[:-2], prims)  # truncated array: some pair is gone
+
+
+def test_ploc_builder_terminates_on_non_finite_geometry(built):
+    """Found by tools/fuzz/hierarchy_driver.cpp: with NaN planes the cluster distance is not symmetric, a level of the clustering can
+    be left without any mutual nearest-neighbour pair, and the loop repeated that level for ever.  The build now always shrinks a
+    level; finite scenes are unaffected (the bit-identity tests above), non-finite triangles end up in a tree like any other."""
+    import vistrace_b200 as vt
+    from vistrace_b200 import abi
+
+    rng = np.random.default_rng(1)
+    for value, vertex in ((np.nan, 0), (np.inf, 0), (-np.inf, 2), (np.nan, 1)):
+        tris = np.zeros(40, abi.TRI_IN)
+        tris["p"] = rng.uniform(-20, 20, (40, 3, 3))
+        tris["p"][[0, 7, 14, 21], vertex, 0] = value
+        for collapse in (False, True):
+            nodes, prims = vt.build_bvh_ploc(abi.SceneData(tris), collapse=collapse)
+            assert sorted(prims.tolist()) == list(range(40)) and len(nodes) % 2 == 1
+            assert nodes["prim_count"][nodes["prim_count"] > 0].sum() == 40
+        nodes, prims = vt.build_bvh(abi.SceneData(tris))  # the product builder on the same triangles
+        assert sorted(prims.tolist()) == list(range(40))
 
 
 def test_scene_generators_are_deterministic_and_oriented():

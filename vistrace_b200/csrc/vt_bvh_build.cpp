@@ -520,6 +520,10 @@ bool flatten_bvh(const HostBvh &bvh, uint64_t n_tris, uint32_t bfs_pairs, FlatBv
     out.max_depth = 0;
     const size_t node_count = bvh.nodes.size();
     if (node_count == 0 || n_tris == 0) return true;
+    if (bvh.prim_indices.size() < n_tris) {
+        err = "BVH primitive index array is shorter than the triangle count";
+        return false;
+    }
     const vt_node &root = bvh.nodes[0];
     out.leaf_order.reserve(n_tris);
     auto emit_leaf = [&](const vt_node &nd, uint32_t &first_out) -> bool {
@@ -899,6 +903,10 @@ bool build_quads(const HostBvh &bvh, uint64_t n_tris, QuadBvh &out, std::string 
     out.root_leaf_count = 0;
     out.max_stack = 0;
     if (bvh.nodes.empty() || n_tris == 0) return true;
+    if (bvh.prim_indices.size() < n_tris) {
+        err = "BVH primitive index array is shorter than the triangle count";
+        return false;
+    }
     if (n_tris >= (1ull << 28) - 16 || bvh.nodes.size() >= (1ull << 28) - 16) {
         err = "quad layout: more than 2^28 triangles or nodes";
         return false;

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <vector>
 
 #include "vt_host.h"
 
@@ -62,6 +63,24 @@ bool plan_collapse(const HostBvh &bvh, int width, CollapsePlan &plan, std::strin
     const char *mode = std::getenv("VT_COLLAPSE");
     plan.greedy = mode && std::string(mode) == "greedy";
     const size_t n = bvh.nodes.size();
+    // The array may be a caller's (vt_accel_populate_with_bvh, vt_build_quads): before anything follows a child reference, every
+    // inner node must name an odd-indexed pair inside the array and no pair may have two parents — then whatever the root reaches is
+    // a tree and every walk below terminates.  (CollapsePlan::children follows grandchildren without further checks.)
+    if (n > 1 || (n == 1 && bvh.nodes[0].prim_count == 0)) {
+        std::vector<uint8_t> referenced((n + 1) / 2, 0);
+        for (size_t i = 0; i < n; i++) {
+            const vt_node &nd = bvh.nodes[i];
+            if (nd.prim_count != 0) continue;
+            if (nd.first == 0 || (nd.first & 1u) == 0 || (size_t)nd.first + 1 >= n) {
+                err = "BVH child index invalid (children must be an adjacent pair at an odd index)";
+                return false;
+            }
+            if (referenced[nd.first / 2]++) {
+                err = "BVH is not a tree (a node pair is referenced twice)";
+                return false;
+            }
+        }
+    }
     plan.sibling_overlap = sibling_overlap(bvh);
     if (!(mode && *mode) || std::string(mode) == "auto") {
         const char *th = std::getenv("VT_COLLAPSE_OVERLAP");

@@ -161,10 +161,16 @@ void build_bvh_ploc(const TriangleVec &tris, HostBvh &out) {
         }
         // pairs of mutual nearest neighbours merge; the lower index leads
         size_t merged_count = 0;
-        for (size_t i = 0; i < count; i++) {
-            const size_t j = neighbors[i];
-            merged_count += (i < j && neighbors[j] == i) ? 1 : 0;
-            merged[i] = merged_count;  // inclusive prefix sum
+        for (int attempt = 0; attempt < 2 && merged_count == 0; attempt++) {
+            // Finite boxes always contain a mutual pair (the closest two).  Non-finite ones do not have to: NaN planes make the
+            // distance asymmetric (std::min / std::max keep their FIRST argument on an unordered compare), and a cycle a -> b -> c -> a
+            // without any mutual pair would repeat this level for ever.  Then the first two nodes are merged, so every level shrinks.
+            if (attempt == 1) neighbors[0] = 1, neighbors[1] = 0;
+            for (size_t i = 0; i < count; i++) {
+                const size_t j = neighbors[i];
+                merged_count += (i < j && neighbors[j] == i) ? 1 : 0;
+                merged[i] = merged_count;  // inclusive prefix sum
+            }
         }
         const size_t children_begin = end - 2 * merged_count;
         const size_t unmerged_begin = begin - merged_count;  // = end - (2 m + (count - m))
